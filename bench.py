@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- demuxlet droplet-likelihood throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU algorithm (oracle port) on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic droplets: every barcode of the
+workload scored against all samples and all ordered sample pairs x alphas.  Workload at any N:
+BASELINE configs[1] ("demuxlet 1xB200: 64 samples, 200k SNPs, 20k barcodes, alpha grid 0-0.5 step
+0.05", ~200 SNP-reads per cell -- our assumption, printed in config) PER GPU: barcodes are sharded
+across ranks with the genotype matrix replicated and no data-path collective (weak scaling).
+
+  value  : droplets/s with the CSR store, genotype matrix and tiles resident in HBM
+           (K1 tile + compaction + K2s singlet + K2 score + K3 finalize), CUDA events, max over ranks.
+  e2e    : droplets/s through the host-buffer C-ABI calls a patched cmdCramDemuxlet makes per run
+           (ccu_demux_set_genotypes + ccu_demux_score: pinned host -> device copies, all kernels,
+           result copy back), wall clock around synchronised calls, max over ranks.
+  roofline: the scoring kernel K2 against the FP64 pipe (the path is FP64-FMA bound).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "droplets/sec (all sample-pair x alpha LLKs)"
+UNIT = "droplets/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", help="BASELINE config shape (C1..C5); default C2")
+    ap.add_argument("--nbcs", type=int, default=None, help="override barcodes per GPU (debugging)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def config_dict(d, n_gpus):
+    cfg = d["cfg"]
+    return {"workload": "%s demuxlet: %d samples, %d SNPs, %d barcodes per GPU, %d alphas, ~%d SNP-reads/cell "
+                        "(r-bar is our assumption), %.0f%% doublets" %
+                        (d["name"], cfg["nv"], cfg["nsnps"], cfg["nbcs"], len(cfg["alphas"]), cfg["rbar"],
+                         100 * cfg["doublet_rate"]),
+            "samples": cfg["nv"], "snps": cfg["nsnps"], "barcodes_per_gpu": cfg["nbcs"],
+            "alphas": len(cfg["alphas"]), "reads_per_cell": cfg["rbar"], "entries_per_gpu": int(d["cell_ptr"][-1]),
+            "seed": d["seed"], "parallelism": "barcode-shard x%d, genotypes replicated" % n_gpus,
+            "l2_policy": "inputs larger than L2 (FP64 genotype matrix + tiles >> 126 MB); no explicit flush"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe):
+    one long-running `nvidia-smi -lms 100` whose rows are cut to the timed window."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.t0, self.t1 = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) >= 7:
+                self.rows.append((time.perf_counter(), f))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
+
+    def summary(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [f for (t, f) in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e30) + 0.1]
+        if not rows:
+            rows = [f for (_, f) in self.rows[-3:]]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no nvidia-smi sample"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": float(rows[0][1]), "samples": len(sm),
+                "power_w_max": max(float(r[2]) for r in rows), "reasons": reasons}
+
+
+def cpu_oracle_rate(d, seconds, threads):
+    """Reference algorithm (oracle port of cmd_cram_demuxlet.cpp:636-906) on the host: droplets/s over
+    a bounded barcode prefix, `threads` workers over disjoint barcode ranges (--group-list recipe)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle
+    gps = pyoracle.mix_genotypes(d["gp"], d["snp_err"])
+    args = (d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], gps, d["alphas"], 0.5)
+    t0 = time.perf_counter()
+    pyoracle.demux_score(*args, cell_begin=0, cell_end=2)
+    per_cell = max((time.perf_counter() - t0) / 2, 1e-6)
+    per_thread = int(max(2, min(d["nbcs"] // threads, seconds / per_cell)))
+    ranges = [(i * per_thread, (i + 1) * per_thread) for i in range(threads)]
+    t0 = time.perf_counter()
+    if threads == 1:
+        pyoracle.demux_score(*args, cell_begin=ranges[0][0], cell_end=ranges[0][1])
+    else:
+        with ThreadPoolExecutor(threads) as ex:  # ctypes releases the GIL during the foreign call
+            list(ex.map(lambda r: pyoracle.demux_score(*args, cell_begin=r[0], cell_end=r[1]), ranges))
+    dt = time.perf_counter() - t0
+    n = per_thread * threads
+    return n / dt, n, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm timed on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from cramore_b200.synth import make_dataset
+    d = make_dataset(args.workload, nbcs=args.nbcs)
+    threads = os.cpu_count() or 1
+    per_step = max(1.0, min(8.0, 150.0 / max(1, args.steps + args.warmup)))
+    rates, n_last = [], 0
+    for i in range(args.warmup + args.steps):
+        r, n_last, dt = cpu_oracle_rate(d, per_step, threads)
+        if i >= args.warmup:
+            rates.append((n_last, dt))
+    tot_n = sum(n for n, _ in rates)
+    tot_t = sum(t for _, t in rates)
+    value = tot_n / tot_t
+    sample = "%d barcodes per step (%d per thread) of the same %s workload" % (n_last, n_last // threads, d["name"])
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(d, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference binary not buildable here (htslib absent): oracle port of cmd_cram_demuxlet.cpp:636-906"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from cramore_b200 import RESULT_DTYPE, DemuxEngine
+    from cramore_b200.synth import algorithmic_flops_per_entry, make_dataset
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- synthetic workload: same genotypes on every rank, rank-specific droplets (weak scaling)
+    d = make_dataset(args.workload, nbcs=args.nbcs, droplet_seed_offset=rank)
+    nbcs, nnz = d["nbcs"], int(d["cell_ptr"][-1])
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+
+    keep = []
+    host = {}
+    for k in ("gp", "snp_err", "cell_ptr", "snp_idx", "read_ptr", "al", "bq"):
+        t, host[k] = pinned(d[k])
+        keep.append(t)
+    out_t = torch.empty(nbcs * RESULT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    out = out_t.numpy().view(RESULT_DTYPE)
+    h2d = sum(host[k].nbytes for k in host)
+    d2h = out.nbytes
+
+    eng = DemuxEngine(local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.configure(d["nv"], d["alphas"], 0.5)
+
+    def e2e_step():
+        eng.set_genotypes(host["gp"], host["snp_err"])
+        eng.score(host["cell_ptr"], host["snp_idx"], host["read_ptr"], host["al"], host["bq"], out)
+
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    fp64_peak = eng.fp64_peak_tflops(300.0)
+
+    # ---- leg 1: HBM-resident inputs, device time
+    eng.set_genotypes(host["gp"], host["snp_err"])
+    eng.upload(host["cell_ptr"], host["snp_idx"], host["read_ptr"], host["al"], host["bq"])
+    eng.run()
+    eng.wait()
+    sampler = ClockSampler(local)
+    time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k2_ms, k1_ms, launches = [], [], 0
+    barrier()
+    sampler.begin()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        eng.run()
+        eng.wait()  # per-step event readout; the stream stays busy, the host sync is ~10 us per step
+        t = eng.timings()
+        k2_ms.append(t["ms_score"])
+        k1_ms.append(t["ms_tile"])
+        launches += t["launches"]
+    ev1.record(stream)
+    barrier()
+    sampler.end()
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.summary()
+    dev_ms_max = max_over_ranks(dev_ms)
+    total_droplets = sum_over_ranks(nbcs) * args.steps
+    value = total_droplets / (dev_ms_max * 1e-3)
+
+    # ---- leg 2: end to end through the host-buffer C ABI
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+        launches += eng.timings()["launches"] + 2
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = total_droplets / e2e_s
+    res_check = np.array(out[:4])
+
+    # ---- roofline of the dominant kernel (K2 scoring, FP64 pipe)
+    flops_launch = algorithmic_flops_per_entry(d["nv"], list(d["alphas"])) * nnz
+    k2_avg = float(np.mean(k2_ms))
+    achieved = flops_launch / (k2_avg * 1e-3) / 1e12
+    roofline = {"bound": "fp64", "kernel": "demux_score_kernel (K2)", "achieved": achieved, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                "peak_source": "DFMA microkernel measured in this run (MEASURED_PEAKS.json has no FP64 entry; "
+                               "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
+                "algorithmic_flops_per_launch": flops_launch, "k2_ms_avg": k2_avg,
+                "k2_share_of_step": k2_avg * args.steps / dev_ms}
+    tile_bytes = 2 * int(d["read_ptr"][-1]) + 8 * nnz + 72 * len(d["alphas"]) * nnz
+    k1_avg = float(np.mean(k1_ms))
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        hbm_peak = 6650.0
+    roofline_k1 = {"bound": "hbm", "kernel": "demux_tile_kernel (K1)", "achieved": tile_bytes / (k1_avg * 1e-3) / 1e9,
+                   "peak": hbm_peak, "unit": "GB/s", "frac": tile_bytes / (k1_avg * 1e-3) / 1e9 / hbm_peak,
+                   "k1_ms_avg": k1_avg}
+
+    line = None
+    if rank == 0:
+        cpu_rate, cpu_n, cpu_dt = cpu_oracle_rate(d, args.cpu_seconds, 1)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(d, world), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": 1e3 * e2e_s / args.steps,
+                        "includes": "genotype matrix upload + mixing, CSR upload, all kernels, result download"},
+                "gpu_launches": launches, "roofline": roofline, "roofline_k1": roofline_k1,
+                "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
+                                 "sample": "first %d barcodes of the same workload, %.1f s, single thread "
+                                           "(the reference is single-threaded)" % (cpu_n, cpu_dt)},
+                "kernel_ms": eng.timings(), "sample_result": [float(res_check["sngBestLLK"][0]),
+                                                              float(res_check["dblBestLLK"][0])]}
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,490 @@
+// ccu_api.cu -- host side of libcramore_cuda.so: the C ABI declared in include/cramore_cuda.h.
+// Owns device memory, the stream and the event timers; every kernel lives in demux_kernels.cu /
+// fmx_kernels.cu.  There is deliberately no CPU implementation behind any entry point: if no
+// sm_100 device is usable, ccu_create() fails and nothing else can be called.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "cramore_cuda.h"
+#include "demux_internal.h"
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+enum { EV_RUN0, EV_TILE, EV_COMPACT, EV_SNG, EV_SCORE, EV_FIN, EV_GP0, EV_GP1, EV_X0, EV_X1, EV_COUNT };
+
+}  // namespace
+
+struct ccu_handle {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[EV_COUNT] = {};
+  std::string err;
+  ccu_timings tm = {};
+
+  // configuration
+  bool configured = false;
+  int nv = 0, nvp = 0, nA = 0;
+  double doublet_prior = 0.5;
+  std::vector<double> alpha;
+  DevBuf d_alpha, d_ptab, d_half, d_phred;
+
+  // genotypes
+  int64_t nsnps = -1;
+  bool has_gp_flags = false;
+  DevBuf d_gpf, d_err, d_hasgp, d_avg, d_G;
+
+  // droplets
+  int64_t nbcs = -1, nnz = 0, nreads = 0;
+  bool ran = false;
+  DevBuf d_cell_ptr, d_snp_idx, d_read_ptr, d_al, d_bq;
+  DevBuf d_tiles, d_vent, d_vsnp, d_vcnt, d_sng, d_partials, d_results, d_dbg, d_sink;
+};
+
+namespace {
+
+int fail(ccu_handle* h, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h)
+    h->err = buf;
+  else
+    g_create_error = buf;
+  return 1;
+}
+
+#define CCU_CUDA(h, call)                                                                       \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+ccu::DemuxDev dev_view(const ccu_handle* h) {
+  ccu::DemuxDev d;
+  memset(&d, 0, sizeof(d));
+  d.nv = h->nv;
+  d.nvp = h->nvp;
+  d.nA = h->nA;
+  d.doublet_prior = h->doublet_prior;
+  d.alpha = h->d_alpha.as<double>();
+  d.ptab = h->d_ptab.as<double>();
+  d.is_half = h->d_half.as<uint8_t>();
+  d.phred = h->d_phred.as<double>();
+  d.nsnps = h->nsnps;
+  d.G = h->d_G.as<double>();
+  d.has_gp = h->has_gp_flags ? h->d_hasgp.as<uint8_t>() : nullptr;
+  d.nbcs = h->nbcs;
+  d.nnz = h->nnz;
+  d.nreads = h->nreads;
+  d.cell_ptr = h->d_cell_ptr.as<int64_t>();
+  d.snp_idx = h->d_snp_idx.as<int32_t>();
+  d.read_ptr = h->d_read_ptr.as<int64_t>();
+  d.al = h->d_al.as<uint8_t>();
+  d.bq = h->d_bq.as<uint8_t>();
+  d.tiles = h->d_tiles.as<double>();
+  d.vent = h->d_vent.as<int64_t>();
+  d.vsnp = h->d_vsnp.as<int32_t>();
+  d.vcnt = h->d_vcnt.as<int32_t>();
+  d.sng_llk = h->d_sng.as<double>();
+  d.partials = h->d_partials.as<ccu::ItemPartial>();
+  d.results = h->d_results.as<ccu_demux_result>();
+  return d;
+}
+
+float ev_ms(ccu_handle* h, int a, int b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) != cudaSuccess) {
+    cudaGetLastError();
+    return 0.f;
+  }
+  return ms;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ccu_create(int32_t device, ccu_handle** out) {
+  if (!out) return fail(nullptr, "ccu_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, "ccu_create: no CUDA device available (%s); this engine has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, "ccu_create: device %d out of range [0,%d)", device, ndev);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return fail(nullptr, "ccu_create: cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, "ccu_create: device %d is sm_%d%d; libcramore_cuda is built for sm_100a only", device,
+                prop.major, prop.minor);
+  if ((e = cudaSetDevice(device)) != cudaSuccess)
+    return fail(nullptr, "ccu_create: cudaSetDevice: %s", cudaGetErrorString(e));
+  ccu_handle* h = new ccu_handle();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, "ccu_create: cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  h->stream = h->own_stream;
+  for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&h->ev[i]);
+
+  // Phred tables, PhredHelper.cpp:29-33, computed with the host libm exactly like the reference
+  std::vector<double> ph(512);
+  for (int q = 0; q < 256; ++q) {
+    ph[q] = (q > 1) ? pow(0.1, q * 0.1) : 0.75;
+    ph[256 + q] = 1. - ph[q];
+  }
+  if (h->d_phred.reserve(512 * sizeof(double)) != cudaSuccess ||
+      cudaMemcpy(h->d_phred.p, ph.data(), 512 * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+      h->d_sink.reserve(64) != cudaSuccess) {
+    ccu_destroy(h);
+    return fail(nullptr, "ccu_create: device allocation failed");
+  }
+  *out = h;
+  return 0;
+}
+
+int ccu_destroy(ccu_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  DevBuf* bufs[] = {&h->d_alpha, &h->d_ptab, &h->d_half, &h->d_phred, &h->d_gpf, &h->d_err, &h->d_hasgp,
+                    &h->d_avg, &h->d_G, &h->d_cell_ptr, &h->d_snp_idx, &h->d_read_ptr, &h->d_al, &h->d_bq,
+                    &h->d_tiles, &h->d_vent, &h->d_vsnp, &h->d_vcnt, &h->d_sng, &h->d_partials, &h->d_results, &h->d_dbg,
+                    &h->d_sink};
+  for (DevBuf* b : bufs) b->release();
+  for (int i = 0; i < EV_COUNT; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return 0;
+}
+
+const char* ccu_last_error(const ccu_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ccu_set_stream(ccu_handle* h, void* cuda_stream) {
+  if (!h) return 1;
+  h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return 0;
+}
+
+int ccu_synchronize(ccu_handle* h) {
+  if (!h) return 1;
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ccu_get_timings(const ccu_handle* h, ccu_timings* t) {
+  if (!h || !t) return 1;
+  *t = h->tm;
+  return 0;
+}
+
+int ccu_demux_configure(ccu_handle* h, int32_t nv, int32_t nalpha, const double* alpha, double doublet_prior) {
+  if (!h) return 1;
+  if (nv < 2) return fail(h, "ccu_demux_configure: need at least 2 samples (nv=%d)", nv);
+  if (nalpha < 2 || nalpha > CCU_MAX_ALPHA)
+    return fail(h, "ccu_demux_configure: alpha grid size %d outside [2,%d]", nalpha, CCU_MAX_ALPHA);
+  if (!alpha || alpha[0] != 0.0)
+    return fail(h, "ccu_demux_configure: the first --alpha must be 0 (singlets are read from it)");
+  if ((double)nv * nv * nalpha >= 2147483647.0) return fail(h, "ccu_demux_configure: nv*nv*nalpha overflows int32");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  h->nv = nv;
+  h->nvp = (nv + 31) / 32 * 32;
+  h->nA = nalpha;
+  h->doublet_prior = doublet_prior;
+  h->alpha.assign(alpha, alpha + nalpha);
+  // allele-fraction table, cmd_cram_demuxlet.cpp:673: p = 0.5*l + (m-l)*0.5*alpha ; and 1.0-p (:685)
+  std::vector<double> ptab(nalpha * 18);
+  std::vector<uint8_t> half(nalpha);
+  for (int k = 0; k < nalpha; ++k) {
+    half[k] = (alpha[k] == 0.5) ? 1 : 0;
+    for (int l = 0; l < 3; ++l)
+      for (int m = 0; m < 3; ++m) {
+        volatile double t1 = 0.5 * l;
+        volatile double t2 = (m - l) * 0.5;
+        volatile double t3 = t2 * alpha[k];
+        volatile double p = t1 + t3;
+        volatile double omp = 1.0 - p;
+        ptab[k * 9 + l * 3 + m] = p;
+        ptab[nalpha * 9 + k * 9 + l * 3 + m] = omp;
+      }
+  }
+  CCU_CUDA(h, h->d_alpha.reserve(nalpha * sizeof(double)));
+  CCU_CUDA(h, h->d_ptab.reserve(ptab.size() * sizeof(double)));
+  CCU_CUDA(h, h->d_half.reserve(nalpha));
+  CCU_CUDA(h, cudaMemcpyAsync(h->d_alpha.p, alpha, nalpha * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CCU_CUDA(h, cudaMemcpyAsync(h->d_ptab.p, ptab.data(), ptab.size() * sizeof(double), cudaMemcpyHostToDevice,
+                              h->stream));
+  CCU_CUDA(h, cudaMemcpyAsync(h->d_half.p, half.data(), nalpha, cudaMemcpyHostToDevice, h->stream));
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->configured = true;
+  h->nsnps = -1;
+  h->nbcs = -1;
+  h->ran = false;
+  return 0;
+}
+
+int ccu_demux_set_genotypes(ccu_handle* h, int64_t nsnps, const float* gp, const double* snp_err,
+                            const uint8_t* has_gp) {
+  if (!h) return 1;
+  if (!h->configured) return fail(h, "ccu_demux_set_genotypes: call ccu_demux_configure first");
+  if (nsnps < 0 || (nsnps > 0 && (!gp || !snp_err))) return fail(h, "ccu_demux_set_genotypes: bad arguments");
+  if (nsnps > 2147483647LL) return fail(h, "ccu_demux_set_genotypes: more than 2^31-1 SNPs");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  const size_t nf = (size_t)nsnps * h->nv * 3;
+  CCU_CUDA(h, h->d_gpf.reserve(nf * sizeof(float) + 16));
+  CCU_CUDA(h, h->d_err.reserve(nsnps * sizeof(double) + 16));
+  CCU_CUDA(h, h->d_avg.reserve(nsnps * 4 * sizeof(double) + 16));
+  CCU_CUDA(h, h->d_G.reserve((size_t)nsnps * h->nvp * 3 * sizeof(double) + 16));
+  h->has_gp_flags = has_gp != nullptr;
+  if (has_gp) CCU_CUDA(h, h->d_hasgp.reserve(nsnps + 16));
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_X0], h->stream));
+  if (nsnps > 0) {
+    CCU_CUDA(h, cudaMemcpyAsync(h->d_gpf.p, gp, nf * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CCU_CUDA(h, cudaMemcpyAsync(h->d_err.p, snp_err, nsnps * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (has_gp) CCU_CUDA(h, cudaMemcpyAsync(h->d_hasgp.p, has_gp, nsnps, cudaMemcpyHostToDevice, h->stream));
+  }
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_GP0], h->stream));
+  CCU_CUDA(h, ccu::launch_gp_prepare(h->d_gpf.as<float>(), h->d_err.as<double>(),
+                                     has_gp ? h->d_hasgp.as<uint8_t>() : nullptr, nsnps, h->nv, h->nvp,
+                                     h->d_avg.as<double>(), h->d_G.as<double>(), h->stream));
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_GP1], h->stream));
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->tm.ms_genotypes = ev_ms(h, EV_GP0, EV_GP1);
+  h->nsnps = nsnps;
+  return 0;
+}
+
+int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx,
+                     const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq) {
+  if (!h) return 1;
+  if (!h->configured) return fail(h, "ccu_demux_upload: call ccu_demux_configure first");
+  if (nbcs < 0 || !cell_ptr) return fail(h, "ccu_demux_upload: bad arguments");
+  const int64_t nnz = cell_ptr[nbcs] - cell_ptr[0];
+  if (cell_ptr[0] != 0) return fail(h, "ccu_demux_upload: cell_ptr[0] must be 0");
+  if (nnz < 0 || (nnz > 0 && (!snp_idx || !read_ptr))) return fail(h, "ccu_demux_upload: bad CSR arrays");
+  const int64_t nreads = nnz > 0 ? read_ptr[nnz] - read_ptr[0] : 0;
+  if (nnz > 0 && read_ptr[0] != 0) return fail(h, "ccu_demux_upload: read_ptr[0] must be 0");
+  if (nreads < 0 || (nreads > 0 && (!al || !bq))) return fail(h, "ccu_demux_upload: bad read arrays");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  const ccu::ScorePlan plan = ccu::make_score_plan(h->nv, h->nA);
+  CCU_CUDA(h, h->d_cell_ptr.reserve((nbcs + 1) * sizeof(int64_t)));
+  CCU_CUDA(h, h->d_snp_idx.reserve(nnz * sizeof(int32_t) + 16));
+  CCU_CUDA(h, h->d_read_ptr.reserve((nnz + 1) * sizeof(int64_t)));
+  CCU_CUDA(h, h->d_al.reserve(nreads + 16));
+  CCU_CUDA(h, h->d_bq.reserve(nreads + 16));
+  CCU_CUDA(h, h->d_tiles.reserve((size_t)nnz * h->nA * ccu::kTileStride * sizeof(double) + 16));
+  CCU_CUDA(h, h->d_vent.reserve(nnz * sizeof(int64_t) + 16));
+  CCU_CUDA(h, h->d_vsnp.reserve(nnz * sizeof(int32_t) + 16));
+  CCU_CUDA(h, h->d_vcnt.reserve(nbcs * sizeof(int32_t) + 16));
+  CCU_CUDA(h, h->d_sng.reserve((size_t)nbcs * h->nv * sizeof(double) + 16));
+  CCU_CUDA(h, h->d_partials.reserve((size_t)nbcs * plan.items_per_cell * sizeof(ccu::ItemPartial) + 16));
+  CCU_CUDA(h, h->d_results.reserve(nbcs * sizeof(ccu_demux_result) + 16));
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_X0], h->stream));
+  CCU_CUDA(h, cudaMemcpyAsync(h->d_cell_ptr.p, cell_ptr, (nbcs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                              h->stream));
+  if (nnz > 0) {
+    CCU_CUDA(h, cudaMemcpyAsync(h->d_snp_idx.p, snp_idx, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CCU_CUDA(h, cudaMemcpyAsync(h->d_read_ptr.p, read_ptr, (nnz + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                                h->stream));
+  }
+  if (nreads > 0) {
+    CCU_CUDA(h, cudaMemcpyAsync(h->d_al.p, al, nreads, cudaMemcpyHostToDevice, h->stream));
+    CCU_CUDA(h, cudaMemcpyAsync(h->d_bq.p, bq, nreads, cudaMemcpyHostToDevice, h->stream));
+  }
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_X1], h->stream));
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->tm.ms_h2d = ev_ms(h, EV_X0, EV_X1);
+  h->nbcs = nbcs;
+  h->nnz = nnz;
+  h->nreads = nreads;
+  h->ran = false;
+  return 0;
+}
+
+int ccu_demux_run(ccu_handle* h) {
+  if (!h) return 1;
+  if (!h->configured || h->nsnps < 0 || h->nbcs < 0)
+    return fail(h, "ccu_demux_run: configure, set_genotypes and upload must precede run");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  const ccu::DemuxDev d = dev_view(h);
+  const ccu::ScorePlan plan = ccu::make_score_plan(h->nv, h->nA);
+  int grid = 0;
+  cudaStream_t st = h->stream;
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_RUN0], st));
+  CCU_CUDA(h, ccu::launch_tile(d, st));
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_TILE], st));
+  CCU_CUDA(h, ccu::launch_compact(d, st));
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_COMPACT], st));
+  CCU_CUDA(h, ccu::launch_singlet(d, st));
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_SNG], st));
+  CCU_CUDA(h, ccu::launch_score(d, plan, h->num_sms, nullptr, 0, 0, &grid, st));
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_SCORE], st));
+  CCU_CUDA(h, ccu::launch_finalize(d, plan, st));
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_FIN], st));
+  h->tm.launches = (h->nbcs > 0 ? 4 : 0) + (h->nnz > 0 ? 1 : 0);
+  h->tm.score_ctas = grid;
+  h->tm.score_items = h->nbcs * plan.items_per_cell;
+  h->ran = true;
+  return 0;
+}
+
+static int collect_run_timings(ccu_handle* h) {
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->tm.ms_tile = ev_ms(h, EV_RUN0, EV_TILE);
+  h->tm.ms_singlet = ev_ms(h, EV_COMPACT, EV_SNG);
+  h->tm.ms_score = ev_ms(h, EV_SNG, EV_SCORE);
+  h->tm.ms_finalize = ev_ms(h, EV_SCORE, EV_FIN);
+  h->tm.ms_run = ev_ms(h, EV_RUN0, EV_FIN);
+  return 0;
+}
+
+int ccu_demux_wait(ccu_handle* h) {
+  if (!h) return 1;
+  if (!h->ran) return fail(h, "ccu_demux_wait: nothing has been run");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  return collect_run_timings(h);
+}
+
+int ccu_demux_download(ccu_handle* h, ccu_demux_result* out) {
+  if (!h) return 1;
+  if (!h->ran) return fail(h, "ccu_demux_download: nothing has been run");
+  if (h->nbcs > 0 && !out) return fail(h, "ccu_demux_download: out is NULL");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  if (collect_run_timings(h)) return 1;
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_X0], h->stream));
+  if (h->nbcs > 0)
+    CCU_CUDA(h, cudaMemcpyAsync(out, h->d_results.p, h->nbcs * sizeof(ccu_demux_result), cudaMemcpyDeviceToHost,
+                                h->stream));
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_X1], h->stream));
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->tm.ms_d2h = ev_ms(h, EV_X0, EV_X1);
+  return 0;
+}
+
+int ccu_demux_score(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx,
+                    const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq, ccu_demux_result* out) {
+  if (int rc = ccu_demux_upload(h, nbcs, cell_ptr, snp_idx, read_ptr, al, bq)) return rc;
+  if (int rc = ccu_demux_run(h)) return rc;
+  return ccu_demux_download(h, out);
+}
+
+int ccu_demux_get_tiles(ccu_handle* h, double* tiles) {
+  if (!h) return 1;
+  if (!h->ran) return fail(h, "ccu_demux_get_tiles: nothing has been run");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  const size_t rowp = (size_t)h->nA * ccu::kTileStride;
+  std::vector<double> tmp((size_t)h->nnz * rowp);
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->nnz > 0) CCU_CUDA(h, cudaMemcpy(tmp.data(), h->d_tiles.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int64_t e = 0; e < h->nnz; ++e)
+    for (int n = 0; n < h->nA; ++n)
+      memcpy(tiles + ((size_t)e * h->nA + n) * 9, tmp.data() + e * rowp + n * ccu::kTileStride, 9 * sizeof(double));
+  return 0;
+}
+
+int ccu_demux_get_genotypes(ccu_handle* h, int64_t snp_begin, int64_t snp_end, double* gps) {
+  if (!h) return 1;
+  if (h->nsnps < 0) return fail(h, "ccu_demux_get_genotypes: no genotypes set");
+  if (snp_begin < 0 || snp_end > h->nsnps || snp_begin > snp_end) return fail(h, "ccu_demux_get_genotypes: bad range");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  const int64_t n = snp_end - snp_begin;
+  if (n == 0) return 0;
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  CCU_CUDA(h, cudaMemcpy2D(gps, (size_t)h->nv * 24, h->d_G.as<double>() + snp_begin * h->nvp * 3, (size_t)h->nvp * 24,
+                           (size_t)h->nv * 24, n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int ccu_demux_get_llk(ccu_handle* h, int64_t cell_begin, int64_t cell_end, double* llk) {
+  if (!h) return 1;
+  if (!h->ran) return fail(h, "ccu_demux_get_llk: run the engine first");
+  if (cell_begin < 0 || cell_end > h->nbcs || cell_begin > cell_end) return fail(h, "ccu_demux_get_llk: bad range");
+  const int64_t nc = cell_end - cell_begin;
+  if (nc == 0) return 0;
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  const size_t n = (size_t)nc * h->nv * h->nv * h->nA;
+  // d_dbg: n double2 (mantissa, exponent) followed by n doubles of converted log-likelihoods
+  CCU_CUDA(h, h->d_dbg.reserve(n * 3 * sizeof(double)));
+  double2* raw2 = h->d_dbg.as<double2>();
+  double* llk_dev = h->d_dbg.as<double>() + 2 * n;
+  CCU_CUDA(h, cudaMemsetAsync(raw2, 0xff, n * sizeof(double2), h->stream));  // all-ones = NaN marker
+  const ccu::DemuxDev d = dev_view(h);
+  const ccu::ScorePlan plan = ccu::make_score_plan(h->nv, h->nA);
+  CCU_CUDA(h, ccu::launch_score(d, plan, h->num_sms, raw2, cell_begin, cell_end, nullptr, h->stream));
+  CCU_CUDA(h, ccu::launch_dbg_convert(raw2, llk_dev, (int64_t)n, h->stream));
+  CCU_CUDA(h, ccu::launch_singlet_to_dbg(d, llk_dev, cell_begin, cell_end, h->stream));
+  CCU_CUDA(h, cudaMemcpyAsync(llk, llk_dev, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ccu_measure_fp64_peak(ccu_handle* h, float ms, double* tflops) {
+  if (!h || !tflops) return 1;
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  int iters = 2000;
+  double best = 0;
+  float total = 0;
+  for (int rep = 0; rep < 64 && (rep < 3 || total < ms); ++rep) {
+    CCU_CUDA(h, cudaEventRecord(h->ev[EV_X0], h->stream));
+    CCU_CUDA(h, ccu::launch_fp64_peak(h->d_sink.as<double>(), iters, h->num_sms, h->stream));
+    CCU_CUDA(h, cudaEventRecord(h->ev[EV_X1], h->stream));
+    CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+    float t = ev_ms(h, EV_X0, EV_X1);
+    total += t;
+    const double flops = (double)h->num_sms * 4 * 256 * (double)iters * 64 * 2;
+    if (rep > 0 && t > 0) best = fmax(best, flops / (t * 1e-3) / 1e12);
+    if (t < 2.f) iters *= 2;
+  }
+  *tflops = best;
+  return 0;
+}
+
+}  // extern "C"

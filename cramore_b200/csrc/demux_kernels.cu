@@ -1,0 +1,975 @@
+// demux_kernels.cu -- sm_100a kernels of the demuxlet droplet-likelihood engine.
+//
+//   gp_avg / gp_mix   genotype-error mixing of the float GP matrix   (sc_drop_seq.cpp:287-315)
+//   K1 tile           per-(cell,SNP) read-product tile, 9 x nAlpha   (cmd_cram_demuxlet.cpp:655-725)
+//   compact           per-cell list of entries whose SNP has GPs     (cmd_cram_demuxlet.cpp:733)
+//   K2s singlet       llksAB[j][0][0] for every sample j              (:733-747 at k=0,n=0; :806,:828)
+//   K2 score          llksAB[j][k][n>=1] for every ordered pair x alpha, reduced in-kernel to
+//                     log-sum-exp partials + top-2 candidates        (:733-747, :809-821, :883-906)
+//   K3 finalize       per-droplet merge -> ccu_demux_result           (:788-906)
+//
+// Arithmetic notes.  K1 and gp_* reproduce the reference's operation order with explicit
+// round-to-nearest intrinsics (no FMA contraction), so their outputs are bit-identical to the CPU
+// loop.  K2 uses the exact factorisation  S[j,k,n] = sum_l g_j[l] * T[k,n,l],
+// T[k,n,l] = sum_m g_k[m] * pG[n,l,m]  and accumulates  prod_snp S  as (mantissa, exponent)
+// instead of  sum_snp log S : every factor lies in [~1e-10, ~1], the mantissa is renormalised
+// into [1,2) every 16 SNPs by integer exponent extraction, and a single log per reported value
+// is taken at the very end.  This is the same real number as the reference's sum of logs to
+// ~1e-13 relative (FP64 throughout).
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "demux_internal.h"
+
+namespace ccu {
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// 2^d for d <= 0 (0 below the normal range)
+__device__ __forceinline__ double pow2_nonpos(int d) {
+  return (d < -1022) ? 0.0 : __hiloint2double((1023 + d) << 20, 0);
+}
+
+// Renormalise a positive product into [1,2), moving its binary exponent into e.
+// Zero / subnormal products (possible only when a genotype row sums to ~0) become exactly 0.
+__device__ __forceinline__ void renorm(double& m, int& e) {
+  int hi = __double2hiint(m);
+  int ex = (hi >> 20) & 0x7ff;
+  if (ex == 0) {
+    m = 0.0;
+  } else {
+    e += ex - 1023;
+    m = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(m));
+  }
+}
+
+__device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {
+  if (a.e != b.e) return a.e > b.e;
+  if (a.m != b.m) return a.m > b.m;
+  return (uint32_t)a.pos < (uint32_t)b.pos;  // empty (-1) sorts last
+}
+__device__ __forceinline__ void cand_insert(Cand& b1, Cand& b2, const Cand& x) {
+  if (cand_better(x, b1)) {
+    b2 = b1;
+    b1 = x;
+  } else if (cand_better(x, b2)) {
+    b2 = x;
+  }
+}
+__device__ __forceinline__ Cand cand_empty() {
+  Cand c;
+  c.m = 0.0;
+  c.e = INT_MIN;
+  c.pos = -1;
+  return c;
+}
+__device__ __forceinline__ Cand cand_shfl_xor(const Cand& c, int d) {
+  Cand r;
+  r.m = __shfl_xor_sync(0xffffffffu, c.m, d);
+  r.e = __shfl_xor_sync(0xffffffffu, c.e, d);
+  r.pos = __shfl_xor_sync(0xffffffffu, c.pos, d);
+  return r;
+}
+// running sum  A * 2^E  of non-negative terms
+__device__ __forceinline__ void lse_add(double& A, int& E, double m, int e) {
+  if (m <= 0.0) return;
+  if (e > E) {
+    A = A * pow2_nonpos(E - e) + m;
+    E = e;
+  } else {
+    A += m * pow2_nonpos(e - E);
+  }
+}
+constexpr int kLseEmpty = INT_MIN / 2;
+
+// ------------------------------------------------------------------------------------------
+// genotype preparation (sc_drop_seq.cpp:287-315)
+// ------------------------------------------------------------------------------------------
+// avg_out[s] = {avg0, avg1, avg2, err_clamped}; one thread per SNP because the reference's
+// running sums over samples are sequential (bit-exactness).
+__global__ void gp_avg_kernel(const float* __restrict__ gp, const double* __restrict__ snp_err,
+                              const uint8_t* __restrict__ has_gp, int64_t nsnps, int nv,
+                              double* __restrict__ avg_out) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nsnps) return;
+  double a0 = 1e-10, a1 = 1e-10, a2 = 1e-10;
+  double err = 0;
+  if (has_gp == nullptr || has_gp[s]) {
+    const float* f = gp + s * (int64_t)nv * 3;
+    for (int i = 0; i < nv; ++i) {
+      a0 = __dadd_rn(a0, (double)f[3 * i]);
+      a1 = __dadd_rn(a1, (double)f[3 * i + 1]);
+      a2 = __dadd_rn(a2, (double)f[3 * i + 2]);
+    }
+    double sum = __dadd_rn(__dadd_rn(a0, a1), a2);
+    a0 = a0 / sum;
+    a1 = a1 / sum;
+    a2 = a2 / sum;
+    err = snp_err[s];
+    if (err > 0.999) err = 0.999;
+    if (err < 0) err = 0;
+  }
+  avg_out[s * 4 + 0] = a0;
+  avg_out[s * 4 + 1] = a1;
+  avg_out[s * 4 + 2] = a2;
+  avg_out[s * 4 + 3] = err;
+}
+
+// G[s][i][g] = (1-err)*gp + err*avg[g]   (padded samples and SNPs without GP: 0)
+__global__ void gp_mix_kernel(const float* __restrict__ gp, const double* __restrict__ avg,
+                              const uint8_t* __restrict__ has_gp, int64_t nsnps, int nv, int nvp,
+                              double* __restrict__ G) {
+  const int64_t row = (int64_t)nvp * 3;
+  const int64_t total = nsnps * row;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s = idx / row;
+    int r = (int)(idx - s * row);
+    int i = r / 3, g = r - 3 * i;
+    double v = 0.0;
+    if (i < nv && (has_gp == nullptr || has_gp[s])) {
+      v = (double)gp[s * (int64_t)nv * 3 + r];
+      double err = avg[s * 4 + 3];
+      if (err > 0) v = __dadd_rn(__dmul_rn(1 - err, v), __dmul_rn(err, avg[s * 4 + g]));
+    }
+    G[idx] = v;
+  }
+}
+
+cudaError_t launch_gp_prepare(const float* gp_f32, const double* snp_err, const uint8_t* has_gp,
+                              int64_t nsnps, int nv, int nvp, double* avg_tmp, double* G,
+                              cudaStream_t st) {
+  if (nsnps == 0) return cudaSuccess;
+  gp_avg_kernel<<<(unsigned)((nsnps + 127) / 128), 128, 0, st>>>(gp_f32, snp_err, has_gp, nsnps, nv,
+                                                                avg_tmp);
+  int64_t total = nsnps * (int64_t)nvp * 3;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  gp_mix_kernel<<<(unsigned)blocks, 256, 0, st>>>(gp_f32, avg_tmp, has_gp, nsnps, nv, nvp, G);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: per-(cell,SNP) tile (cmd_cram_demuxlet.cpp:655-725)
+// ------------------------------------------------------------------------------------------
+// GL lanes cooperate on one entry, lane n owning the 9 values of alpha[n]; the running maximum
+// over all 9*nA values (:686-687, :711-712) is a group shuffle reduction.  The Phred tables sit
+// in shared memory.  Results are staged through shared memory so that each warp writes one
+// contiguous run of global memory.
+constexpr int kTileWarps = 8;
+
+template <int GL>
+__global__ void __launch_bounds__(kTileWarps * 32)
+    demux_tile_kernel(int64_t nnz, const int64_t* __restrict__ read_ptr, const uint8_t* __restrict__ al,
+                      const uint8_t* __restrict__ bq, int nA, const double* __restrict__ ptab,
+                      const double* __restrict__ phred, double* __restrict__ tiles) {
+  constexpr int EPW = 32 / GL;  // entries per warp per pass
+  __shared__ double s_err[256];
+  __shared__ double s_mat[256];
+  __shared__ double s_out[kTileWarps][EPW * GL * kTileStride];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    s_err[i] = phred[i];
+    s_mat[i] = phred[256 + i];
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = lane % GL;   // alpha index
+  const int sub = lane / GL; // entry within the warp pass
+  const bool has_alpha = n < nA;
+  double p[9], omp[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    p[t] = has_alpha ? ptab[n * 9 + t] : 0.0;
+    omp[t] = has_alpha ? ptab[nA * 9 + n * 9 + t] : 0.0;
+  }
+  const int rowlen = nA * kTileStride;
+
+  const int64_t warps_total = (int64_t)gridDim.x * kTileWarps;
+  for (int64_t e0 = ((int64_t)blockIdx.x * kTileWarps + warp) * EPW; e0 < nnz; e0 += warps_total * EPW) {
+    const int64_t e = e0 + sub;
+    const bool valid = e < nnz;
+    int64_t r0 = 0;
+    int cnt = 0;
+    if (valid) {
+      r0 = read_ptr[e];
+      cnt = (int)(read_ptr[e + 1] - r0);
+    }
+    int maxcnt = cnt;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, d));
+
+    double v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v[t] = 1.0;  // :657
+
+    for (int i = 0; i < maxcnt; ++i) {
+      const bool act = i < cnt;
+      const int a = act ? al[r0 + i] : 2;
+      const int q = act ? bq[r0 + i] : 0;
+      const bool use = (a != 2);  // :664
+      double mx = 0.0;
+      if (use && has_alpha) {
+        const double pR = (a == 0) ? s_mat[q] : s_err[q] / 3.0;  // :666
+        const double pA = (a == 1) ? s_mat[q] : s_err[q] / 3.0;  // :667
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          v[t] = __dmul_rn(v[t], __dadd_rn(__dmul_rn(pR, omp[t]), __dmul_rn(pA, p[t])));  // :685
+          mx = fmax(mx, v[t]);
+        }
+      }
+#pragma unroll
+      for (int d = GL / 2; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      if (use && has_alpha) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] = v[t] / mx;  // :696
+      }
+    }
+    // :704-725
+    double mx = 0.0;
+    if (has_alpha) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        v[t] = __dadd_rn(v[t], 1e-10);
+        mx = fmax(mx, v[t]);
+      }
+    }
+#pragma unroll
+    for (int d = GL / 2; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if (has_alpha) {
+      double* o = &s_out[warp][sub * rowlen + n * kTileStride];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) o[t] = v[t] / mx;
+      o[9] = 0.0;
+    }
+    __syncwarp();
+    int64_t nvalid = nnz - e0;
+    if (nvalid > EPW) nvalid = EPW;
+    const int ndbl = (int)nvalid * rowlen;
+    double* dst = tiles + e0 * rowlen;
+    for (int i = lane; i < ndbl; i += 32) dst[i] = s_out[warp][i];
+    __syncwarp();
+  }
+}
+
+cudaError_t launch_tile(const DemuxDev& d, cudaStream_t st) {
+  if (d.nnz == 0) return cudaSuccess;
+  int gl = 2;
+  while (gl < d.nA) gl <<= 1;
+  int64_t per_block = (int64_t)kTileWarps * (32 / gl);
+  int64_t blocks = (d.nnz + per_block - 1) / per_block;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+#define CCU_TILE(GL)                                                                              \
+  demux_tile_kernel<GL><<<(unsigned)blocks, kTileWarps * 32, 0, st>>>(d.nnz, d.read_ptr, d.al, d.bq, \
+                                                                       d.nA, d.ptab, d.phred, d.tiles)
+  switch (gl) {
+    case 2: CCU_TILE(2); break;
+    case 4: CCU_TILE(4); break;
+    case 8: CCU_TILE(8); break;
+    case 16: CCU_TILE(16); break;
+    default: CCU_TILE(32); break;
+  }
+#undef CCU_TILE
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// compaction: vent[cell_ptr[c] + r] = r-th entry of cell c whose SNP has genotypes (:733)
+// ------------------------------------------------------------------------------------------
+__global__ void compact_kernel(int64_t nbcs, const int64_t* __restrict__ cell_ptr,
+                               const int32_t* __restrict__ snp_idx, const uint8_t* __restrict__ has_gp,
+                               int64_t* __restrict__ vent, int32_t* __restrict__ vsnp,
+                               int32_t* __restrict__ vcnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= nbcs) return;
+  const int64_t b = cell_ptr[c], e = cell_ptr[c + 1];
+  int run = 0;
+  for (int64_t i = b; i < e; i += 32) {
+    const int64_t idx = i + lane;
+    bool ok = false;
+    int32_t snp = 0;
+    if (idx < e) {
+      snp = snp_idx[idx];
+      ok = (has_gp == nullptr) || has_gp[snp];
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const int64_t o = b + run + __popc(mask & ((1u << lane) - 1u));
+      vent[o] = idx;
+      vsnp[o] = snp;
+    }
+    run += __popc(mask);
+  }
+  if (lane == 0) vcnt[c] = run;
+}
+
+cudaError_t launch_compact(const DemuxDev& d, cudaStream_t st) {
+  if (d.nbcs == 0) return cudaSuccess;
+  int64_t blocks = (d.nbcs * 32 + 255) / 256;
+  compact_kernel<<<(unsigned)blocks, 256, 0, st>>>(d.nbcs, d.cell_ptr, d.snp_idx, d.has_gp, d.vent, d.vsnp, d.vcnt);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K2s: singlet likelihoods llksAB[j][0][0] (cmd_cram_demuxlet.cpp:733-747 at k=0, n=0)
+// ------------------------------------------------------------------------------------------
+// One warp per droplet, lanes over samples.  alpha[0]==0 makes the tile independent of m, but the
+// reference still multiplies by sample 0's genotype row, so T0 uses g_0.
+__global__ void __launch_bounds__(256)
+    demux_singlet_kernel(DemuxDev d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= d.nbcs) return;
+  const int64_t base = d.cell_ptr[c];
+  const int cnt = d.vcnt[c];
+  const int64_t rowlen = (int64_t)d.nA * kTileStride;
+  const int64_t grow = (int64_t)d.nvp * 3;
+  for (int jb = 0; jb < d.nvp; jb += 32) {
+    const int j = jb + lane;
+    double m = 1.0;
+    int ex = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const int64_t e = d.vent[base + i];
+      const double* pg = d.tiles + e * rowlen;  // alpha index 0
+      const double* g = d.G + (int64_t)d.vsnp[base + i] * grow;
+      const double g00 = g[0], g01 = g[1], g02 = g[2];
+      const double t0 = fma(g02, pg[2], fma(g01, pg[1], g00 * pg[0]));
+      const double t1 = fma(g02, pg[5], fma(g01, pg[4], g00 * pg[3]));
+      const double t2 = fma(g02, pg[8], fma(g01, pg[7], g00 * pg[6]));
+      const double* gj = g + 3 * j;
+      m *= fma(gj[2], t2, fma(gj[1], t1, gj[0] * t0));
+      if ((i & 15) == 15) renorm(m, ex);
+    }
+    renorm(m, ex);
+    if (j < d.nv)
+      d.sng_llk[c * d.nv + j] = (m > 0.0) ? (log(m) + (double)ex * 0.6931471805599453094) : -CUDART_INF;
+  }
+}
+
+cudaError_t launch_singlet(const DemuxDev& d, cudaStream_t st) {
+  if (d.nbcs == 0) return cudaSuccess;
+  int64_t blocks = (d.nbcs * 32 + 255) / 256;
+  demux_singlet_kernel<<<(unsigned)blocks, 256, 0, st>>>(d);
+  return cudaGetLastError();
+}
+
+__global__ void singlet_to_dbg_kernel(DemuxDev d, double* __restrict__ llk, int64_t c0, int64_t c1) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t n = (c1 - c0) * d.nv;
+  if (idx >= n) return;
+  int64_t c = idx / d.nv;
+  int j = (int)(idx - c * d.nv);
+  llk[((c * d.nv + j) * d.nv + 0) * d.nA + 0] = d.sng_llk[(c0 + c) * d.nv + j];
+}
+
+cudaError_t launch_singlet_to_dbg(const DemuxDev& d, double* llk_dbg, int64_t c0, int64_t c1,
+                                  cudaStream_t st) {
+  int64_t n = (c1 - c0) * d.nv;
+  if (n <= 0) return cudaSuccess;
+  singlet_to_dbg_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, llk_dbg, c0, c1);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: pair x alpha scoring (cmd_cram_demuxlet.cpp:733-747, reduced per :809-821 and :883-906)
+// ------------------------------------------------------------------------------------------
+// Work item = (droplet, j-tile of 32 samples, k-tile of 32*TK samples, chunk of AC doublet
+// alphas).  A persistent CTA (one per SM) walks its items as ONE stream of 8-SNP chunks:
+//   * warp 8 (producer) streams, per SNP of a chunk, the j-rows and k-rows of the FP64 genotype
+//     matrix and the alpha block of the droplet's tile into a shared-memory ring with TMA bulk
+//     copies (cp.async.bulk, completion on "full" mbarriers); consumer warps hand stages back
+//     through "empty" mbarriers, so the ring never drains across item boundaries;
+//   * warps 0-7 (consumers) turn the k-rows x tile block into T[k][n][l] (double-buffered smem),
+//     then each thread owns 4 samples j x (TK x AC) columns = 40 running products in registers
+//     and spends 2 DFMA + 2 DMUL per (SNP, j, k, alpha);
+//   * at the end of an item the products become log-sum-exp / top-2 partials (no log needed:
+//     ordering by (exponent, mantissa) is ordering by LLK).
+constexpr int kNS = 3;   // raw ring stages
+constexpr int kTJ = 4;   // samples j per thread
+constexpr int kConsumers = kScoreThreads;        // 8 consumer warps
+constexpr int kScoreBlock = kScoreThreads + 128;  // + the producer warpgroup (1 working warp)
+// Register budget: the kernel launches with 168 registers/thread (65536 / 384); the producer
+// warpgroup shrinks to 24 and the two consumer warpgroups grow to 240 (8*32*240 + 4*32*24 = 64512).
+constexpr int kRegsProducer = 24;
+constexpr int kRegsConsumer = 240;
+
+__device__ __forceinline__ void consumer_bar() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int AC, int TK>
+struct ScoreCfg {
+  static constexpr int SC = (TK >= 8) ? 4 : 8;  // SNPs per chunk (bounded by shared memory)
+  static constexpr int RS = 16 / SC;            // renormalise every RS chunks (= 16 SNPs; factors >= ~2^-40)
+  static constexpr int NCOL = AC * TK;
+  static constexpr int TROW0 = NCOL * 3;
+  // row stride (doubles) of a thread's T block: even, and (stride/2) odd => the 8 distinct
+  // 16-byte segments a warp reads per LDS.128 fall into distinct bank groups
+  static constexpr int TROW = ((TROW0 / 2) % 2 == 1) ? TROW0 : TROW0 + 2;
+  static constexpr int KT = 32 * TK;
+  static constexpr int GJ_BYTES = kJT * 24;
+  static constexpr int GK_BYTES = KT * 24;
+  static constexpr int PG_BYTES = AC * kTileStride * 8;
+  static constexpr int SLOT_BYTES = GJ_BYTES + GK_BYTES + PG_BYTES;
+  static constexpr int STAGE_BYTES = SC * SLOT_BYTES;
+  static constexpr int T_BYTES = SC * 32 * TROW * 8;
+  static constexpr int RED_BYTES = 8 * 64;
+  static constexpr int SMEM_BYTES = kNS * STAGE_BYTES + 2 * T_BYTES + RED_BYTES + 2 * kNS * 8 + 16;
+  // T-compute task split: NG alpha groups per (SNP slot, k) pair, APT alphas per task
+  static constexpr int PAIRS = SC * KT;
+  static constexpr int NG = (PAIRS >= kConsumers) ? 1 : (kConsumers / PAIRS);
+  static constexpr int APT = AC / NG;
+  static_assert(NCOL % 2 == 0, "columns are processed in pairs");
+  static_assert(TROW % 2 == 0, "16-byte aligned T rows");
+  static_assert(AC % NG == 0, "alpha groups must divide the chunk");
+  static_assert((KT & (KT - 1)) == 0 && (NG & (NG - 1)) == 0, "power-of-two task decode");
+};
+
+struct ItemCursor {
+  int64_t item;   // global item id
+  int64_t ent0;   // cell_ptr[cell]
+  int32_t cell, nent, nch, chunk;
+  int32_t j0, k0, n0;
+  bool valid;
+};
+
+struct WarpRed {
+  double lse_a;
+  int32_t lse_e, _pad;
+  Cand b1, b2;
+};
+
+template <int AC, int TK>
+__global__ void __launch_bounds__(kScoreBlock, 1)
+    demux_score_kernel(DemuxDev d, int njt, int nkt, int nac, int64_t nitems, double2* __restrict__ dbg,
+                       int64_t dbg_c0, int64_t dbg_c1) {
+  using Cfg = ScoreCfg<AC, TK>;
+  constexpr int kSC = Cfg::SC;
+  constexpr int kRS = Cfg::RS;
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* raw = smem;
+  double* Tbuf = reinterpret_cast<double*>(smem + kNS * Cfg::STAGE_BYTES);
+  WarpRed* red = reinterpret_cast<WarpRed*>(smem + kNS * Cfg::STAGE_BYTES + 2 * Cfg::T_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kNS * Cfg::STAGE_BYTES + 2 * Cfg::T_BYTES + Cfg::RED_BYTES);
+  uint64_t* empty = full + kNS;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ipc = njt * nkt * nac;
+
+  // zero the ring once (partial k-tiles / alpha chunks leave their tail untouched)
+  for (int i = tid; i < kNS * Cfg::STAGE_BYTES / 8; i += kScoreBlock) reinterpret_cast<double*>(raw)[i] = 0.0;
+  if (tid == 0) {
+    for (int s = 0; s < kNS; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), kConsumers / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_proxy_async();
+  __syncthreads();
+
+  auto load_item = [&](ItemCursor& c, int64_t item) {
+    c.item = item;
+    c.valid = item < nitems;
+    c.chunk = 0;
+    if (!c.valid) return;
+    const int64_t cell = item / ipc;
+    int t = (int)(item - cell * ipc);
+    const int ac = t % nac;
+    t /= nac;
+    const int kt = t % nkt;
+    const int jt = t / nkt;
+    c.cell = (int32_t)cell;
+    c.ent0 = d.cell_ptr[cell];
+    c.nent = d.vcnt[cell];
+    c.nch = max(1, (c.nent + kSC - 1) / kSC);
+    c.j0 = jt * kJT;
+    c.k0 = kt * Cfg::KT;
+    c.n0 = 1 + ac * AC;
+  };
+  auto advance = [&](ItemCursor& c) {
+    if (++c.chunk >= c.nch) load_item(c, c.item + gridDim.x);
+  };
+
+  if (warp >= kConsumers / 32) {
+    // ======================= producer warp: TMA bulk copies =======================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+    if (warp != kConsumers / 32) return;
+    ItemCursor pc;
+    load_item(pc, blockIdx.x);
+    for (uint32_t g = 0; pc.valid; ++g) {
+      const int stage = g % kNS;
+      if (g >= (uint32_t)kNS) mbar_wait(smem_u32(&empty[stage]), ((g / kNS) - 1) & 1);
+      const int cnt = min(kSC, pc.nent - pc.chunk * kSC);
+      const int krows = min(Cfg::KT, d.nvp - pc.k0);
+      const int nal = min(AC, d.nA - pc.n0);
+      const uint32_t kbytes = (uint32_t)krows * 24u, pbytes = (uint32_t)nal * (kTileStride * 8);
+      const uint32_t bar = smem_u32(&full[stage]);
+      int64_t e = 0, snp = 0;
+      if (lane < cnt) {
+        const int64_t idx = pc.ent0 + (int64_t)pc.chunk * kSC + lane;
+        e = d.vent[idx];
+        snp = d.vsnp[idx];
+      }
+      if (lane == 0) mbar_expect_tx(bar, (uint32_t)max(cnt, 0) * (Cfg::GJ_BYTES + kbytes + pbytes));
+      __syncwarp();
+      if (lane < cnt) {
+        const uint32_t slot = smem_u32(raw + stage * Cfg::STAGE_BYTES + lane * Cfg::SLOT_BYTES);
+        const double* grow = d.G + snp * (int64_t)d.nvp * 3;
+        bulk_g2s(slot, grow + (int64_t)pc.j0 * 3, Cfg::GJ_BYTES, bar);
+        bulk_g2s(slot + Cfg::GJ_BYTES, grow + (int64_t)pc.k0 * 3, kbytes, bar);
+        bulk_g2s(slot + Cfg::GJ_BYTES + Cfg::GK_BYTES, d.tiles + (e * d.nA + pc.n0) * kTileStride, pbytes, bar);
+      }
+      advance(pc);
+    }
+    return;
+  }
+
+  // ======================= consumer warps =======================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
+  const int kidx = (warp & 3) * 8 + (lane & 7);  // k-lane 0..31
+  const int jg = (warp >> 2) * 4 + (lane >> 3);  // j-group 0..7
+
+  // T[s][klane][(kk*AC + a)*3 + l] = sum_m g_k[m] * pG[a][l][m]
+  auto compute_T = [&](const ItemCursor& c, int stage, int tb) {
+    const int cnt = min(kSC, c.nent - c.chunk * kSC);
+    double* T = Tbuf + tb * (Cfg::T_BYTES / 8);
+    const unsigned char* st = raw + stage * Cfg::STAGE_BYTES;
+#pragma unroll
+    for (int u0 = 0; u0 < Cfg::PAIRS * Cfg::NG; u0 += kConsumers) {
+      const int u = u0 + tid;
+      const int grp = u & (Cfg::NG - 1);
+      const int pr = u / Cfg::NG;
+      const int kabs = pr & (Cfg::KT - 1);
+      const int s = pr / Cfg::KT;
+      if (s < cnt) {
+        const unsigned char* slot = st + s * Cfg::SLOT_BYTES;
+        const double* gk = reinterpret_cast<const double*>(slot + Cfg::GJ_BYTES) + kabs * 3;
+        const double g0 = gk[0], g1 = gk[1], g2 = gk[2];
+        const double* pgb = reinterpret_cast<const double*>(slot + Cfg::GJ_BYTES + Cfg::GK_BYTES);
+        double* ob = T + (s * 32 + kabs / TK) * Cfg::TROW + ((kabs % TK) * AC) * 3;
+#pragma unroll
+        for (int i = 0; i < Cfg::APT; ++i) {
+          const int a = grp * Cfg::APT + i;
+          const double2* p2 = reinterpret_cast<const double2*>(pgb + a * kTileStride);
+          const double2 q0 = p2[0], q1 = p2[1], q2 = p2[2], q3 = p2[3];
+          const double q8 = pgb[a * kTileStride + 8];
+          double* o = ob + a * 3;
+          o[0] = fma(g2, q1.x, fma(g1, q0.y, g0 * q0.x));
+          o[1] = fma(g2, q2.y, fma(g1, q2.x, g0 * q1.y));
+          o[2] = fma(g2, q8, fma(g1, q3.y, g0 * q3.x));
+        }
+      }
+    }
+  };
+
+  double acc[kTJ][Cfg::NCOL];
+  int aex[kTJ][Cfg::NCOL];
+  auto reset_acc = [&]() {
+#pragma unroll
+    for (int jj = 0; jj < kTJ; ++jj)
+#pragma unroll
+      for (int cc = 0; cc < Cfg::NCOL; ++cc) {
+        acc[jj][cc] = 1.0;
+        aex[jj][cc] = 0;
+      }
+  };
+  auto renorm_all = [&]() {
+#pragma unroll
+    for (int jj = 0; jj < kTJ; ++jj)
+#pragma unroll
+      for (int cc = 0; cc < Cfg::NCOL; ++cc) renorm(acc[jj][cc], aex[jj][cc]);
+  };
+
+  // item epilogue: products -> partial log-sum-exp + top-2 candidates for this item
+  auto epilogue = [&](const ItemCursor& c) {
+    renorm_all();
+    double la = 0.0;
+    int le = kLseEmpty;
+    Cand b1 = cand_empty(), b2 = cand_empty();
+    const int64_t cell = c.cell;
+    const bool want_dbg = (dbg != nullptr) && cell >= dbg_c0 && cell < dbg_c1;
+#pragma unroll
+    for (int jj = 0; jj < kTJ; ++jj) {
+      const int j = c.j0 + jg * kTJ + jj;
+#pragma unroll
+      for (int cc = 0; cc < Cfg::NCOL; ++cc) {
+        const int k = c.k0 + kidx * TK + cc / AC;
+        const int n = c.n0 + cc % AC;
+        if (j < d.nv && k < d.nv && n < d.nA) {
+          const double m = acc[jj][cc];
+          const int e = aex[jj][cc];
+          if (want_dbg) dbg[(((cell - dbg_c0) * d.nv + j) * d.nv + k) * d.nA + n] = make_double2(m, (double)e);
+          if (j != k && m > 0.0) {
+            // :812-817  alpha == 0.5 is counted once (k <= j) with twice the prior
+            const double w = d.is_half[n] ? ((k < j) ? 2.0 : 0.0) : 1.0;
+            lse_add(la, le, w * m, e);
+            Cand x;
+            x.m = m;
+            x.e = e;
+            x.pos = (j * d.nv + k) * d.nA + n;
+            cand_insert(b1, b2, x);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int dd = 16; dd >= 1; dd >>= 1) {
+      const double oa = __shfl_xor_sync(0xffffffffu, la, dd);
+      const int oe = __shfl_xor_sync(0xffffffffu, le, dd);
+      lse_add(la, le, oa, oe);
+      const Cand o1 = cand_shfl_xor(b1, dd), o2 = cand_shfl_xor(b2, dd);
+      cand_insert(b1, b2, o1);
+      cand_insert(b1, b2, o2);
+    }
+    if (lane == 0) {
+      red[warp].lse_a = la;
+      red[warp].lse_e = le;
+      red[warp].b1 = b1;
+      red[warp].b2 = b2;
+    }
+    consumer_bar();
+    if (tid == 0) {
+      for (int w = 1; w < kConsumers / 32; ++w) {
+        lse_add(la, le, red[w].lse_a, red[w].lse_e);
+        cand_insert(b1, b2, red[w].b1);
+        cand_insert(b1, b2, red[w].b2);
+      }
+      ItemPartial p;
+      p.lse_a = la;
+      p.lse_e = le;
+      p._pad = 0;
+      p.best = b1;
+      p.next = b2;
+      d.partials[c.item] = p;
+    }
+    reset_acc();
+  };
+
+  // ---------------- chunk stream ----------------
+  ItemCursor cur;
+  load_item(cur, blockIdx.x);
+  if (!cur.valid) return;
+  reset_acc();
+  mbar_wait(smem_u32(&full[0]), 0);
+  compute_T(cur, 0, 0);
+  consumer_bar();
+
+  for (uint32_t g = 0; cur.valid; ++g) {
+    const int stage = g % kNS, tb = g & 1;
+    // ---- main: 4 x NCOL running products over the chunk's SNPs
+    {
+      const int cnt = min(kSC, cur.nent - cur.chunk * kSC);
+      const unsigned char* st = raw + stage * Cfg::STAGE_BYTES;
+      const double* T = Tbuf + tb * (Cfg::T_BYTES / 8) + kidx * Cfg::TROW;
+      for (int s = 0; s < cnt; ++s) {
+        const double2* gp2 = reinterpret_cast<const double2*>(st + s * Cfg::SLOT_BYTES) + jg * (kTJ * 3 / 2);
+        double gv[kTJ * 3];
+#pragma unroll
+        for (int i = 0; i < kTJ * 3 / 2; ++i) {
+          const double2 v = gp2[i];
+          gv[2 * i] = v.x;
+          gv[2 * i + 1] = v.y;
+        }
+        const double2* t2 = reinterpret_cast<const double2*>(T + s * 32 * Cfg::TROW);
+#pragma unroll
+        for (int c2 = 0; c2 < Cfg::NCOL / 2; ++c2) {
+          const double2 u0 = t2[3 * c2], u1 = t2[3 * c2 + 1], u2 = t2[3 * c2 + 2];
+#pragma unroll
+          for (int jj = 0; jj < kTJ; ++jj) {
+            const double da = fma(gv[jj * 3 + 2], u1.x, fma(gv[jj * 3 + 1], u0.y, gv[jj * 3] * u0.x));
+            const double db = fma(gv[jj * 3 + 2], u2.y, fma(gv[jj * 3 + 1], u2.x, gv[jj * 3] * u1.y));
+            acc[jj][2 * c2] *= da;
+            acc[jj][2 * c2 + 1] *= db;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&empty[stage]));  // this warp is done with ring stage `stage`
+    // ---- look ahead: T of the next chunk (possibly of the next item)
+    ItemCursor nxt = cur;
+    advance(nxt);
+    if (nxt.valid) {
+      const uint32_t g1 = g + 1;
+      mbar_wait(smem_u32(&full[g1 % kNS]), (g1 / kNS) & 1);
+      compute_T(nxt, g1 % kNS, g1 & 1);
+    }
+    if (cur.chunk + 1 >= cur.nch)
+      epilogue(cur);
+    else if ((cur.chunk % kRS) == kRS - 1)
+      renorm_all();
+    consumer_bar();
+    cur = nxt;
+  }
+}
+
+// dbg[i] = (mantissa, exponent) -> llk = log(m) + e*ln2, in place (first double of each pair)
+__global__ void dbg_convert_kernel(double2* __restrict__ dbg, double* __restrict__ llk, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2 v = dbg[i];
+  double r;
+  if (v.x != v.x) r = v.x;  // NaN marker: entry not computed by the engine
+  else r = (v.x > 0.0) ? (log(v.x) + v.y * 0.6931471805599453094) : -CUDART_INF;
+  llk[i] = r;
+}
+
+cudaError_t launch_dbg_convert(double2* dbg, double* llk, int64_t n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  dbg_convert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dbg, llk, n);
+  return cudaGetLastError();
+}
+
+ScorePlan make_score_plan(int nv, int nA) {
+  ScorePlan p;
+  const int nd = nA - 1;
+  // alphas per chunk: minimise padded work, prefer larger chunks on ties
+  const int cand[4] = {10, 5, 2, 1};
+  int best = 1, best_cost = 1 << 30;
+  for (int i = 0; i < 4; ++i) {
+    int ac = cand[i];
+    int cost = ((nd + ac - 1) / ac) * ac;
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = ac;
+    }
+  }
+  p.ac = best;
+  p.tk = (best == 10) ? 1 : (best == 5) ? 2 : (best == 2) ? 4 : 8;
+  p.kt = 32 * p.tk;
+  const int nvp = (nv + 31) / 32 * 32;
+  p.njt = nvp / kJT;
+  p.nkt = (nvp + p.kt - 1) / p.kt;
+  p.nac = (nd + p.ac - 1) / p.ac;
+  p.items_per_cell = p.njt * p.nkt * p.nac;
+  switch (p.ac) {
+    case 10: p.smem_bytes = ScoreCfg<10, 1>::SMEM_BYTES; break;
+    case 5: p.smem_bytes = ScoreCfg<5, 2>::SMEM_BYTES; break;
+    case 2: p.smem_bytes = ScoreCfg<2, 4>::SMEM_BYTES; break;
+    default: p.smem_bytes = ScoreCfg<1, 8>::SMEM_BYTES; break;
+  }
+  return p;
+}
+
+template <int AC, int TK>
+static cudaError_t launch_score_t(const DemuxDev& d, const ScorePlan& plan, int num_sms, double2* llk_dbg,
+                                  int64_t c0, int64_t c1, int* grid_out, cudaStream_t st) {
+  using Cfg = ScoreCfg<AC, TK>;
+  cudaError_t err = cudaFuncSetAttribute(demux_score_kernel<AC, TK>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  if (err != cudaSuccess) return err;
+  const int64_t nitems = d.nbcs * plan.items_per_cell;
+  int grid = (int)((nitems < num_sms) ? nitems : num_sms);
+  if (grid_out) *grid_out = grid;
+  demux_score_kernel<AC, TK><<<grid, kScoreBlock, Cfg::SMEM_BYTES, st>>>(d, plan.njt, plan.nkt, plan.nac,
+                                                                          nitems, llk_dbg, c0, c1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_score(const DemuxDev& d, const ScorePlan& plan, int num_sms, double2* llk_dbg,
+                         int64_t dbg_c0, int64_t dbg_c1, int* grid_out, cudaStream_t st) {
+  if (d.nbcs == 0) return cudaSuccess;
+  switch (plan.ac) {
+    case 10: return launch_score_t<10, 1>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
+    case 5: return launch_score_t<5, 2>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
+    case 2: return launch_score_t<2, 4>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
+    default: return launch_score_t<1, 8>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: per-droplet merge (cmd_cram_demuxlet.cpp:788-906)
+// ------------------------------------------------------------------------------------------
+struct SngCand {
+  double v;
+  int32_t j;
+};
+__device__ __forceinline__ bool sng_better(const SngCand& a, const SngCand& b) {
+  if (a.v != b.v) return a.v > b.v;
+  return (uint32_t)a.j < (uint32_t)b.j;
+}
+__device__ __forceinline__ void sng_insert(SngCand& b1, SngCand& b2, const SngCand& x) {
+  if (sng_better(x, b1)) {
+    b2 = b1;
+    b1 = x;
+  } else if (sng_better(x, b2)) {
+    b2 = x;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    demux_finalize_kernel(DemuxDev d, int ipc, double log_single_prior, double log_doublet_prior1) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= d.nbcs) return;
+  const double LN2 = 0.6931471805599453094;
+
+  // ---- singlets (:804-807, :827-837)
+  SngCand s1 = {-1e300, -1}, s2 = {-1e300, -1};
+  double smax = 0.0;  // the -1e-300 seed of :791 is exp(.) == 1, i.e. a term at 0
+  for (int j = lane; j < d.nv; j += 32) {
+    const double v = d.sng_llk[c * d.nv + j];
+    SngCand x = {v, j};
+    if (v > -1e300) sng_insert(s1, s2, x);
+    smax = fmax(smax, v + log_single_prior);
+  }
+#pragma unroll
+  for (int dd = 16; dd >= 1; dd >>= 1) {
+    SngCand o1, o2;
+    o1.v = __shfl_xor_sync(0xffffffffu, s1.v, dd);
+    o1.j = __shfl_xor_sync(0xffffffffu, s1.j, dd);
+    o2.v = __shfl_xor_sync(0xffffffffu, s2.v, dd);
+    o2.j = __shfl_xor_sync(0xffffffffu, s2.j, dd);
+    if (o1.j >= 0) sng_insert(s1, s2, o1);
+    if (o2.j >= 0) sng_insert(s1, s2, o2);
+    smax = fmax(smax, __shfl_xor_sync(0xffffffffu, smax, dd));
+  }
+
+  // ---- doublet partials of this droplet's items
+  double la = 0.0;
+  int le = kLseEmpty;
+  Cand b1 = cand_empty(), b2 = cand_empty();
+  for (int i = lane; i < ipc; i += 32) {
+    const ItemPartial p = d.partials[c * ipc + i];
+    lse_add(la, le, p.lse_a, p.lse_e);
+    cand_insert(b1, b2, p.best);
+    cand_insert(b1, b2, p.next);
+  }
+#pragma unroll
+  for (int dd = 16; dd >= 1; dd >>= 1) {
+    const double oa = __shfl_xor_sync(0xffffffffu, la, dd);
+    const int oe = __shfl_xor_sync(0xffffffffu, le, dd);
+    lse_add(la, le, oa, oe);
+    const Cand o1 = cand_shfl_xor(b1, dd), o2 = cand_shfl_xor(b2, dd);
+    cand_insert(b1, b2, o1);
+    cand_insert(b1, b2, o2);
+  }
+  const double td = (la > 0.0) ? (log_doublet_prior1 + log(la) + (double)le * LN2) : -CUDART_INF;
+
+  // ---- posterior normalisers (:804-821): log(1 + sum exp(term))
+  const double msng = smax;
+  const double mall = fmax(msng, td);
+  double ssng = 0.0, sall = 0.0;
+  for (int j = lane; j < d.nv; j += 32) {
+    const double t = d.sng_llk[c * d.nv + j] + log_single_prior;
+    ssng += exp(t - msng);
+    sall += exp(t - mall);
+  }
+#pragma unroll
+  for (int dd = 16; dd >= 1; dd >>= 1) {
+    ssng += __shfl_xor_sync(0xffffffffu, ssng, dd);
+    sall += __shfl_xor_sync(0xffffffffu, sall, dd);
+  }
+  if (lane == 0) {
+    ccu_demux_result r;
+    r.sBest = s1.j;
+    r.sNext = s2.j;
+    r.sngBestLLK = s1.v;
+    r.sngNextLLK = s2.v;
+    r.sngLLK = msng + log(exp(-msng) + ssng);
+    r.sumLLK = mall + log(exp(-mall) + sall + exp(td - mall));
+    const int nvA = d.nv * d.nA;
+    if (b1.pos >= 0) {
+      r.dBest1 = b1.pos / nvA;
+      r.dBest2 = (b1.pos % nvA) / d.nA;
+      r.dBestA = b1.pos % d.nA;
+      r.dblBestLLK = log(b1.m) + (double)b1.e * LN2;
+    } else {
+      r.dBest1 = r.dBest2 = r.dBestA = -1;
+      r.dblBestLLK = -1e300;
+    }
+    if (b2.pos >= 0) {
+      r.dNext1 = b2.pos / nvA;
+      r.dNext2 = (b2.pos % nvA) / d.nA;
+      r.dNextA = b2.pos % d.nA;
+      r.dblNextLLK = log(b2.m) + (double)b2.e * LN2;
+    } else {
+      r.dNext1 = r.dNext2 = r.dNextA = -1;
+      r.dblNextLLK = -1e300;
+    }
+    d.results[c] = r;
+  }
+}
+
+cudaError_t launch_finalize(const DemuxDev& d, const ScorePlan& plan, cudaStream_t st) {
+  if (d.nbcs == 0) return cudaSuccess;
+  const double nv = d.nv, nA = d.nA;
+  // cmd_cram_demuxlet.cpp:793-794
+  const double lsp = log((1.0 - d.doublet_prior) / nv);
+  const double ldp1 = log(d.doublet_prior / nv / (nv - 1.) / (nA - 1.));
+  int64_t blocks = (d.nbcs * 32 + 255) / 256;
+  demux_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(d, plan.items_per_cell, lsp, ldp1);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 roofline denominator: 8 independent DFMA chains per thread
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters) {
+  double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+  double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+  const double x = 0.999999, y = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, x, y);
+      a1 = fma(a1, x, y);
+      a2 = fma(a2, x, y);
+      a3 = fma(a3, x, y);
+      a4 = fma(a4, x, y);
+      a5 = fma(a5, x, y);
+      a6 = fma(a6, x, y);
+      a7 = fma(a7, x, y);
+    }
+  }
+  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 123.456) sink[0] = s;
+}
+
+cudaError_t launch_fp64_peak(double* sink, int iters, int num_sms, cudaStream_t st) {
+  fp64_peak_kernel<<<num_sms * 4, 256, 0, st>>>(sink, iters);
+  return cudaGetLastError();
+}
+
+}  // namespace ccu

@@ -1,0 +1,218 @@
+"""ctypes binding of libcramore_cuda.so -- the C ABI in include/cramore_cuda.h.
+
+This is the only compute path of the package: there is no Python or CPU implementation behind
+it.  If the shared library is missing or no sm_100 GPU is usable, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libcramore_cuda.so")
+_lib = None
+
+RESULT_DTYPE = np.dtype([
+    ("sBest", "<i4"), ("sNext", "<i4"), ("dBest1", "<i4"), ("dBest2", "<i4"), ("dBestA", "<i4"),
+    ("dNext1", "<i4"), ("dNext2", "<i4"), ("dNextA", "<i4"),
+    ("sngBestLLK", "<f8"), ("sngNextLLK", "<f8"), ("dblBestLLK", "<f8"), ("dblNextLLK", "<f8"),
+    ("sumLLK", "<f8"), ("sngLLK", "<f8")])
+
+CALL_DTYPE = np.dtype([
+    ("type", "<i4"), ("jBest", "<i4"), ("kBest", "<i4"), ("alphaBest", "<i4"),
+    ("jNext", "<i4"), ("kNext", "<i4"), ("alphaNext", "<i4"), ("_pad", "<i4"),
+    ("bestLLK", "<f8"), ("nextLLK", "<f8"), ("bestPP", "<f8"), ("sngPP", "<f8"), ("sngOnlyPP", "<f8")])
+
+
+class Timings(C.Structure):
+    _fields_ = [("ms_genotypes", C.c_float), ("ms_tile", C.c_float), ("ms_singlet", C.c_float),
+                ("ms_score", C.c_float), ("ms_finalize", C.c_float), ("ms_run", C.c_float),
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("launches", C.c_int32),
+                ("score_ctas", C.c_int32), ("score_items", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# every symbol include/cramore_cuda.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "ccu_create", "ccu_destroy", "ccu_last_error", "ccu_set_stream", "ccu_synchronize", "ccu_get_timings",
+    "ccu_demux_configure", "ccu_demux_set_genotypes", "ccu_demux_score", "ccu_demux_upload",
+    "ccu_demux_run", "ccu_demux_wait", "ccu_demux_download", "ccu_demux_classify", "ccu_demux_best_row",
+    "ccu_demux_best_header", "ccu_demux_get_tiles", "ccu_demux_get_genotypes", "ccu_demux_get_llk",
+    "ccu_measure_fp64_peak",
+]
+
+
+def load_library():
+    """dlopen libcramore_cuda.so (no GPU needed for this step)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C cramore_b200/csrc). There is no CPU fallback." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        lib.ccu_last_error.restype = C.c_char_p
+        lib.ccu_last_error.argtypes = [C.c_void_p]
+        lib.ccu_demux_best_header.restype = C.c_char_p
+        for name in ABI_SYMBOLS:
+            fn = getattr(lib, name)
+            if name not in ("ccu_last_error", "ccu_demux_best_header"):
+                fn.restype = C.c_int
+        _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class DemuxEngine:
+    """One GPU's demuxlet engine (mirrors the call sequence a patched cmdCramDemuxlet makes)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.h = C.c_void_p(0)
+        rc = self.lib.ccu_create(C.c_int32(device), C.byref(self.h))
+        if rc != 0:
+            raise EngineError(self.lib.ccu_last_error(None).decode())
+        self.nv = self.nA = 0
+        self.nbcs = 0
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.lib.ccu_destroy(self.h)
+            self.h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(self.lib.ccu_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.ccu_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._check(self.lib.ccu_synchronize(self.h))
+
+    def configure(self, nv, alphas, doublet_prior=0.5):
+        a = np.ascontiguousarray(alphas, np.float64)
+        self._check(self.lib.ccu_demux_configure(self.h, C.c_int32(nv), C.c_int32(len(a)), _ptr(a),
+                                                 C.c_double(doublet_prior)))
+        self.nv, self.nA, self.alphas, self.doublet_prior = nv, len(a), a, doublet_prior
+
+    def set_genotypes(self, gp_f32, snp_err, has_gp=None):
+        gp = np.ascontiguousarray(gp_f32, np.float32)
+        nsnps = gp.shape[0]
+        assert gp.shape == (nsnps, self.nv, 3)
+        err = np.ascontiguousarray(np.broadcast_to(np.asarray(snp_err, np.float64), (nsnps,)))
+        hg = None if has_gp is None else np.ascontiguousarray(has_gp, np.uint8)
+        self._check(self.lib.ccu_demux_set_genotypes(self.h, C.c_int64(nsnps), _ptr(gp), _ptr(err), _ptr(hg)))
+        self.nsnps = nsnps
+
+    @staticmethod
+    def _csr(cell_ptr, snp_idx, read_ptr, al, bq):
+        return (np.ascontiguousarray(cell_ptr, np.int64), np.ascontiguousarray(snp_idx, np.int32),
+                np.ascontiguousarray(read_ptr, np.int64), np.ascontiguousarray(al, np.uint8),
+                np.ascontiguousarray(bq, np.uint8))
+
+    def score(self, cell_ptr, snp_idx, read_ptr, al, bq, out=None):
+        """ccu_demux_score: host buffers in, results out (H2D + kernels + D2H)."""
+        cp, si, rp, a, q = self._csr(cell_ptr, snp_idx, read_ptr, al, bq)
+        nbcs = len(cp) - 1
+        if out is None:
+            out = np.zeros(nbcs, RESULT_DTYPE)
+        self._check(self.lib.ccu_demux_score(self.h, C.c_int64(nbcs), _ptr(cp), _ptr(si), _ptr(rp), _ptr(a),
+                                             _ptr(q), _ptr(out)))
+        self.nbcs = nbcs
+        self.nnz = int(cp[-1])
+        return out
+
+    def upload(self, cell_ptr, snp_idx, read_ptr, al, bq):
+        cp, si, rp, a, q = self._csr(cell_ptr, snp_idx, read_ptr, al, bq)
+        self.nbcs = len(cp) - 1
+        self.nnz = int(cp[-1])
+        self._check(self.lib.ccu_demux_upload(self.h, C.c_int64(self.nbcs), _ptr(cp), _ptr(si), _ptr(rp),
+                                              _ptr(a), _ptr(q)))
+
+    def run(self):
+        self._check(self.lib.ccu_demux_run(self.h))
+
+    def wait(self):
+        self._check(self.lib.ccu_demux_wait(self.h))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.zeros(self.nbcs, RESULT_DTYPE)
+        self._check(self.lib.ccu_demux_download(self.h, _ptr(out)))
+        return out
+
+    def timings(self):
+        t = Timings()
+        self._check(self.lib.ccu_get_timings(self.h, C.byref(t)))
+        return t.as_dict()
+
+    def tiles(self):
+        out = np.zeros((self.nnz, self.nA * 9), np.float64)
+        self._check(self.lib.ccu_demux_get_tiles(self.h, _ptr(out)))
+        return out
+
+    def genotypes(self, snp_begin=0, snp_end=None):
+        snp_end = self.nsnps if snp_end is None else snp_end
+        out = np.zeros((snp_end - snp_begin, self.nv, 3), np.float64)
+        self._check(self.lib.ccu_demux_get_genotypes(self.h, C.c_int64(snp_begin), C.c_int64(snp_end), _ptr(out)))
+        return out
+
+    def llk(self, cell_begin=0, cell_end=None):
+        cell_end = self.nbcs if cell_end is None else cell_end
+        out = np.zeros((cell_end - cell_begin, self.nv, self.nv, self.nA), np.float64)
+        self._check(self.lib.ccu_demux_get_llk(self.h, C.c_int64(cell_begin), C.c_int64(cell_end), _ptr(out)))
+        return out
+
+    def fp64_peak_tflops(self, ms=200.0):
+        v = C.c_double(0)
+        self._check(self.lib.ccu_measure_fp64_peak(self.h, C.c_float(ms), C.byref(v)))
+        return v.value
+
+
+def classify(results, nv, alphas, doublet_prior=0.5):
+    """Host decision of cmd_cram_demuxlet.cpp:921-991 for an array of results."""
+    lib = load_library()
+    a = np.ascontiguousarray(alphas, np.float64)
+    res = np.ascontiguousarray(results)
+    calls = np.zeros(len(res), CALL_DTYPE)
+    for i in range(len(res)):
+        rc = lib.ccu_demux_classify(C.c_void_p(res[i:i + 1].ctypes.data), C.c_int32(nv), C.c_int32(len(a)),
+                                    _ptr(a), C.c_double(doublet_prior), C.c_void_p(calls[i:i + 1].ctypes.data))
+        if rc != 0:
+            raise EngineError("ccu_demux_classify failed")
+    return calls
+
+
+def best_header():
+    return load_library().ccu_demux_best_header().decode()
+
+
+def best_row(int_id, barcode, nsnps_cell, nreads_cell, result, nv, alphas, doublet_prior, sample_ids):
+    lib = load_library()
+    a = np.ascontiguousarray(alphas, np.float64)
+    buf = C.create_string_buffer(4096)
+    ids = (C.c_char_p * nv)(*[s.encode() for s in sample_ids])
+    res = np.ascontiguousarray(result).reshape(1)
+    n = lib.ccu_demux_best_row(buf, C.c_int32(4096), C.c_int32(int_id), barcode.encode(), C.c_uint32(nsnps_cell),
+                               C.c_int32(nreads_cell), C.c_void_p(res.ctypes.data), C.c_int32(nv),
+                               C.c_int32(len(a)), _ptr(a), C.c_double(doublet_prior), ids)
+    if n < 0:
+        raise EngineError("ccu_demux_best_row: result has undefined indices")
+    return buf.raw[:n].decode()

@@ -1,0 +1,144 @@
+"""Synthetic "simuxlet-style" demuxlet / freemuxlet inputs.
+
+Random genotypes, simulated singlet / doublet droplets, reads drawn from the droplet's sample(s),
+emitted directly as the float GP matrix plus the CSR droplet store that
+`sc_dropseq_lib_t::load_from_plp` (sc_drop_seq.cpp:103-384) would build.  Counter-based PRNG
+(numpy Philox), seed = 1000 + config index.  Reads per cell r-bar is OUR assumption for C2..C4
+(BASELINE.json does not fix it) and is recorded in every config dict.
+"""
+import numpy as np
+
+# name -> BASELINE.json configs[i]
+CONFIGS = {
+    "C1": dict(index=0, nv=8, nsnps=20_000, nbcs=1_000, rbar=50, alphas=[0.0, 0.5], doublet_rate=0.10),
+    "C2": dict(index=1, nv=64, nsnps=200_000, nbcs=20_000, rbar=200,
+               alphas=[round(0.05 * i, 2) for i in range(11)], doublet_rate=0.10),
+    "C3": dict(index=2, nv=256, nsnps=500_000, nbcs=100_000, rbar=200,
+               alphas=[round(0.05 * i, 2) for i in range(11)], doublet_rate=0.10),
+    "C4": dict(index=3, nv=16, nsnps=300_000, nbcs=50_000, rbar=200, alphas=[0.0, 0.5], doublet_rate=0.10),
+    "C5": dict(index=4, nv=128, nsnps=200_000, nbcs=5_000, rbar=2000,
+               alphas=[round(0.05 * i, 2) for i in range(11)], doublet_rate=0.20),
+}
+
+
+def _hex_order_key(counter):
+    """Sort key reproducing lexicographic order of sprintf("%x", counter) (sc_drop_seq.cpp:365:
+    UMIs in the plp path are hex strings of a global counter kept in a std::map<std::string,..>)."""
+    c = counter.astype(np.uint64)
+    nd = np.ones(c.shape, np.int64)
+    t = c >> np.uint64(4)
+    while np.any(t > 0):
+        nd += (t > 0)
+        t = t >> np.uint64(4)
+    left = c << ((16 - nd) * 4).astype(np.uint64)
+    return left, nd
+
+
+def make_genotypes(rng, nsnps, nv):
+    """float32 GP [nsnps][nv][3], normalised in float like bcf_filtered_reader.cpp:474-485."""
+    af = rng.uniform(0.05, 0.5, nsnps)
+    geno = rng.binomial(2, af[:, None], size=(nsnps, nv)).astype(np.int8)
+    gp = np.full((nsnps, nv, 3), np.float32(0.01), np.float32)
+    np.put_along_axis(gp, geno[:, :, None].astype(np.int64), np.float32(0.98), axis=2)
+    s = (gp[:, :, 0] + gp[:, :, 1]) + gp[:, :, 2]  # float accumulation order of :478-480
+    gp /= s[:, :, None]
+    return af, geno, gp
+
+
+def make_droplets(rng, geno, nbcs, rbar, doublet_rate, min_bq=13, cap_bq=20, chunk=2_000_000):
+    """Simulated droplets -> CSR (cell_ptr, snp_idx, read_ptr, al, bq) + truth."""
+    nsnps, nv = geno.shape
+    is_dbl = rng.random(nbcs) < doublet_rate
+    s1 = rng.integers(0, nv, nbcs)
+    s2 = (s1 + 1 + rng.integers(0, nv - 1, nbcs)) % nv
+    s2 = np.where(is_dbl, s2, s1)
+    nreads = rng.poisson(rbar, nbcs).astype(np.int64)
+    R = int(nreads.sum())
+    cell = np.repeat(np.arange(nbcs, dtype=np.int64), nreads)
+    snp = rng.integers(0, nsnps, R).astype(np.int64)
+    src = np.where(rng.random(R) < 0.5, s1[cell], s2[cell])
+    g = np.empty(R, np.int8)
+    for a in range(0, R, chunk):  # gather in chunks to bound temporaries
+        b = min(R, a + chunk)
+        g[a:b] = geno[snp[a:b], src[a:b]]
+    raw_bq = rng.integers(min_bq, 41, R)
+    allele = (rng.random(R) < g * 0.5).astype(np.uint8)
+    flip = rng.random(R) < np.power(10.0, -raw_bq / 10.0)
+    allele = np.where(flip, 1 - allele, allele).astype(np.uint8)
+    allele = np.where(rng.random(R) < 0.001, 2, allele).astype(np.uint8)
+    bq = np.minimum(raw_bq, cap_bq).astype(np.uint8)
+
+    # plp order: by droplet, then SNP; the global hex counter follows that order
+    order = np.lexsort((np.arange(R), snp, cell))
+    cell, snp, allele, bq = cell[order], snp[order], allele[order], bq[order]
+    counter = np.arange(R, dtype=np.int64)
+    newgrp = np.ones(R, bool)
+    if R > 1:
+        newgrp[1:] = (cell[1:] != cell[:-1]) | (snp[1:] != snp[:-1])
+    grp = np.cumsum(newgrp) - 1
+    nnz = int(grp[-1] + 1) if R else 0
+    gsize = np.bincount(grp, minlength=nnz)
+    multi = gsize[grp] > 1
+    if np.any(multi):  # reads of one (cell,SNP) iterate in lexicographic UMI order
+        idx = np.nonzero(multi)[0]
+        left, nd = _hex_order_key(counter[idx])
+        sub = np.lexsort((nd, left, grp[idx]))
+        allele[idx] = allele[idx][sub]
+        bq[idx] = bq[idx][sub]
+    read_ptr = np.zeros(nnz + 1, np.int64)
+    np.cumsum(gsize, out=read_ptr[1:])
+    first = np.nonzero(newgrp)[0]
+    snp_idx = snp[first].astype(np.int32)
+    ent_cell = cell[first]
+    cell_ptr = np.zeros(nbcs + 1, np.int64)
+    np.cumsum(np.bincount(ent_cell, minlength=nbcs), out=cell_ptr[1:])
+    return dict(cell_ptr=cell_ptr, snp_idx=snp_idx, read_ptr=read_ptr, al=allele, bq=bq,
+                is_dbl=is_dbl, s1=s1, s2=s2, nreads=nreads)
+
+
+def make_barcodes(rng, nbcs):
+    out, seen = [], set()
+    letters = np.array(list("ACGT"))
+    while len(out) < nbcs:
+        for row in letters[rng.integers(0, 4, (nbcs, 16))]:
+            b = "".join(row) + "-1"
+            if b not in seen:
+                seen.add(b)
+                out.append(b)
+                if len(out) == nbcs:
+                    break
+    return out
+
+
+def make_dataset(name="C1", nbcs=None, nsnps=None, nv=None, rbar=None, seed=None, droplet_seed_offset=0,
+                 geno_error_offset=0.10, with_barcodes=False):
+    """Dataset of a named BASELINE config (any size field can be overridden for tests)."""
+    cfg = dict(CONFIGS[name])
+    if nbcs is not None:
+        cfg["nbcs"] = nbcs
+    if nsnps is not None:
+        cfg["nsnps"] = nsnps
+    if nv is not None:
+        cfg["nv"] = nv
+    if rbar is not None:
+        cfg["rbar"] = rbar
+    seed = 1000 + cfg["index"] if seed is None else seed
+    rng_g = np.random.Generator(np.random.Philox(key=seed))
+    af, geno, gp = make_genotypes(rng_g, cfg["nsnps"], cfg["nv"])
+    rng_d = np.random.Generator(np.random.Philox(key=seed + 7919 * (1 + droplet_seed_offset)))
+    d = make_droplets(rng_d, geno, cfg["nbcs"], cfg["rbar"], cfg["doublet_rate"])
+    d.update(name=name, cfg=cfg, seed=seed, gp=gp, af=af,
+             snp_err=np.full(cfg["nsnps"], geno_error_offset, np.float64),
+             alphas=np.asarray(cfg["alphas"], np.float64), nv=cfg["nv"], nsnps=cfg["nsnps"], nbcs=cfg["nbcs"],
+             sample_ids=["SM%03d" % i for i in range(cfg["nv"])])
+    if with_barcodes:
+        d["barcodes"] = make_barcodes(rng_d, cfg["nbcs"])
+    return d
+
+
+def algorithmic_flops_per_entry(nv, alphas):
+    """FP64 flops per (cell,SNP) = 8*N_llk + 18*nv*nA."""
+    nA = len(alphas)
+    has_half = any(a == 0.5 for a in alphas)
+    n_llk = nv + nv * (nv - 1) * (nA - 1) - (nv * (nv - 1) // 2 if has_half else 0)
+    return 8 * n_llk + 18 * nv * nA

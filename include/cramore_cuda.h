@@ -1,0 +1,142 @@
+/*
+ * cramore_cuda.h -- C ABI of libcramore_cuda.so, the B200 (sm_100a) droplet-likelihood engine
+ * behind `cramore demuxlet` / `cramore freemuxlet`.
+ *
+ * The reference (hyunminkang/cramore) has no plugin or FFI seam: the engine is inline in
+ * cmdCramDemuxlet (cmd_cram_demuxlet.cpp:427-1060) and cmdCramFreemuxlet
+ * (cmd_cram_freemuxlet.cpp:116-164, 359-370, 456-653).  This header defines the seam a patched
+ * command driver calls once its sc_dropseq_lib_t is populated (cmd_cram_demuxlet.cpp:425,
+ * cmd_cram_freemuxlet.cpp:83).  Each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, non-zero on error; the message is
+ *     available from ccu_last_error().  No exceptions cross the boundary, no CPU fallback exists:
+ *     without an sm_100 device ccu_create() fails.
+ *   - one handle drives ONE GPU.  Multi-GPU = one process (or handle) per GPU over disjoint
+ *     barcode shards, the reference's own --group-list recipe (cmd_cram_demuxlet.cpp:75).
+ *   - all array arguments are HOST pointers borrowed for the duration of the call unless the
+ *     name says _dev.  The engine owns all device memory.
+ *
+ * CSR layout of the droplet store (flattened sc_dropseq_lib_t::cell_umis, sc_drop_seq.h:165):
+ *   cell_ptr[nbcs+1]  -> first (cell,SNP) entry of each barcode (entries ascend by SNP id)
+ *   snp_idx[nnz]      -> SNP id of each entry
+ *   read_ptr[nnz+1]   -> first read of each entry (reads in lexicographic UMI order)
+ *   al[R], bq[R]      -> allele code {0 ref, 1 alt, 2 other} and capped base quality per unique read
+ */
+#ifndef CRAMORE_CUDA_H
+#define CRAMORE_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCU_MAX_ALPHA 32 /* size of the --alpha grid the engine accepts */
+
+typedef struct ccu_handle ccu_handle;
+
+/* Exactly the per-droplet values consumed by the decision + row code
+ * (cmd_cram_demuxlet.cpp:788-791 declarations, :921-1013 consumers). */
+typedef struct {
+  int32_t sBest, sNext;            /* :827-837 */
+  int32_t dBest1, dBest2, dBestA;  /* :883-906 (dBestA indexes the alpha grid) */
+  int32_t dNext1, dNext2, dNextA;
+  double sngBestLLK, sngNextLLK;
+  double dblBestLLK, dblNextLLK;
+  double sumLLK, sngLLK;           /* :804-821 */
+} ccu_demux_result;
+
+/* Decision of cmd_cram_demuxlet.cpp:921-991.  type: 0 SNG, 1 DBL, 2 AMB. */
+typedef struct {
+  int32_t type;
+  int32_t jBest, kBest, alphaBest;
+  int32_t jNext, kNext, alphaNext;
+  int32_t _pad;
+  double bestLLK, nextLLK;
+  double bestPP, sngPP, sngOnlyPP;
+} ccu_demux_call;
+
+/* Device timings of the last ccu_demux_run()/ccu_demux_score(), CUDA events on the engine's
+ * stream (milliseconds), and the number of kernels it launched. */
+typedef struct {
+  float ms_genotypes;  /* ccu_demux_set_genotypes kernels (last call) */
+  float ms_tile;       /* K1  per-(cell,SNP) tile kernel */
+  float ms_singlet;    /* K2s singlet scoring kernel */
+  float ms_score;      /* K2  pair x alpha scoring kernel */
+  float ms_finalize;   /* K3  per-droplet reduction */
+  float ms_run;        /* all kernels of one run, first launch to last completion */
+  float ms_h2d, ms_d2h;
+  int32_t launches;    /* kernels launched by the last run */
+  int32_t score_ctas;  /* grid size of K2 */
+  int64_t score_items; /* (barcode x pair-tile x alpha-chunk) work items of K2 */
+} ccu_timings;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+int ccu_create(int32_t device, ccu_handle** out);
+int ccu_destroy(ccu_handle* h);
+/* Message of the last failed call on h (h == NULL: last failed ccu_create). */
+const char* ccu_last_error(const ccu_handle* h);
+/* Run on the caller's CUDA stream (cudaStream_t passed as void*); NULL = engine-owned stream. */
+int ccu_set_stream(ccu_handle* h, void* cuda_stream);
+int ccu_synchronize(ccu_handle* h);
+int ccu_get_timings(const ccu_handle* h, ccu_timings* t);
+
+/* ---- demuxlet -------------------------------------------------------------------------- */
+
+/* --alpha grid / --doublet-prior / sample count (cmd_cram_demuxlet.cpp:62-63,85-89,103).
+ * alpha[0] must be 0, nalpha in [2, CCU_MAX_ALPHA], nv >= 2 (the reference is
+ * undefined otherwise). */
+int ccu_demux_configure(ccu_handle* h, int32_t nv, int32_t nalpha, const double* alpha,
+                        double doublet_prior);
+
+/* Genotype posteriors, replaces the host loop sc_drop_seq.cpp:287-315
+ * (== cmd_cram_demuxlet.cpp:241-268): gp is BCFFilteredReader::get_posterior_at output (float,
+ * bcf_filtered_reader.h:168-170) as [nsnps][nv][3]; snp_err[s] = offset + (1-offset)*(1-R2)*coeff
+ * (clamped to [0,0.999] by the engine like :308-309); has_gp[s]==0 marks sc_snp_t::gps==NULL
+ * (NULL pointer = every SNP has genotypes).  The engine forms the per-SNP average and the mixed
+ * FP64 matrix on the device, bit-identical to the host loop. */
+int ccu_demux_set_genotypes(ccu_handle* h, int64_t nsnps, const float* gp, const double* snp_err,
+                            const uint8_t* has_gp);
+
+/* The whole engine for nbcs droplets, replaces cmd_cram_demuxlet.cpp:636-906 (tile :655-725,
+ * pairwise accumulation :733-747, posterior normaliser :804-821, top-2 scans :827-906).
+ * out[nbcs] in CSR barcode order.  Equivalent to upload + run + download. */
+int ccu_demux_score(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx,
+                    const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq,
+                    ccu_demux_result* out);
+
+/* Staged form of the same call (inputs stay resident in HBM between runs). */
+int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx,
+                     const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq);
+int ccu_demux_run(ccu_handle* h);  /* asynchronous on the stream */
+int ccu_demux_wait(ccu_handle* h); /* wait for the last run and refresh ccu_get_timings() */
+int ccu_demux_download(ccu_handle* h, ccu_demux_result* out);
+
+/* Decision + row formatting (host code, cmd_cram_demuxlet.cpp:921-1013). */
+int ccu_demux_classify(const ccu_demux_result* r, int32_t nv, int32_t nalpha, const double* alpha,
+                       double doublet_prior, ccu_demux_call* call);
+/* snprintf semantics; header line is ccu_demux_best_header(). */
+int ccu_demux_best_row(char* buf, int32_t buflen, int32_t int_id, const char* barcode,
+                       uint32_t nsnps_cell, int32_t nreads_cell, const ccu_demux_result* r, int32_t nv,
+                       int32_t nalpha, const double* alpha, double doublet_prior,
+                       const char* const* sample_ids);
+const char* ccu_demux_best_header(void);
+
+/* Inspection (parity tests): copy device intermediates of the last upload/run back.
+ * tiles: [nnz][nalpha*9] (cmd_cram_demuxlet.cpp:655-725); gps: [snp_end-snp_begin][nv][3]
+ * (sc_snp_t::gps); llk: [cell_end-cell_begin][nv][nv][nalpha] = llksAB (:746) where the engine
+ * computes it ([j][0][0] and every [j][k][n>=1]); other entries are NaN.  ccu_demux_get_llk
+ * re-runs the scoring kernel for that barcode range. */
+int ccu_demux_get_tiles(ccu_handle* h, double* tiles);
+int ccu_demux_get_genotypes(ccu_handle* h, int64_t snp_begin, int64_t snp_end, double* gps);
+int ccu_demux_get_llk(ccu_handle* h, int64_t cell_begin, int64_t cell_end, double* llk);
+
+/* Measured FP64 roofline denominator: runs a DFMA-saturating microkernel for about `ms`
+ * milliseconds on the handle's device and returns TFLOP/s (2 flops per DFMA). */
+int ccu_measure_fp64_peak(ccu_handle* h, float ms, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
