@@ -314,7 +314,7 @@ int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const
   if (nnz > 0 && read_ptr[0] != 0) return fail(h, "ccu_demux_upload: read_ptr[0] must be 0");
   if (nreads < 0 || (nreads > 0 && (!al || !bq))) return fail(h, "ccu_demux_upload: bad read arrays");
   CCU_CUDA(h, cudaSetDevice(h->device));
-  const ccu::ScorePlan plan = ccu::make_score_plan(h->nv, h->nA);
+  const ccu::ScorePlan plan = ccu::make_score_plan(h->nv, h->nA, h->alpha.data());
   CCU_CUDA(h, h->d_cell_ptr.reserve((nbcs + 1) * sizeof(int64_t)));
   CCU_CUDA(h, h->d_snp_idx.reserve(nnz * sizeof(int32_t) + 16));
   CCU_CUDA(h, h->d_read_ptr.reserve((nnz + 1) * sizeof(int64_t)));
@@ -355,7 +355,7 @@ int ccu_demux_run(ccu_handle* h) {
     return fail(h, "ccu_demux_run: configure, set_genotypes and upload must precede run");
   CCU_CUDA(h, cudaSetDevice(h->device));
   const ccu::DemuxDev d = dev_view(h);
-  const ccu::ScorePlan plan = ccu::make_score_plan(h->nv, h->nA);
+  const ccu::ScorePlan plan = ccu::make_score_plan(h->nv, h->nA, h->alpha.data());
   int grid = 0;
   cudaStream_t st = h->stream;
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_RUN0], st));
@@ -457,7 +457,7 @@ int ccu_demux_get_llk(ccu_handle* h, int64_t cell_begin, int64_t cell_end, doubl
   double* llk_dev = h->d_dbg.as<double>() + 2 * n;
   CCU_CUDA(h, cudaMemsetAsync(raw2, 0xff, n * sizeof(double2), h->stream));  // all-ones = NaN marker
   const ccu::DemuxDev d = dev_view(h);
-  const ccu::ScorePlan plan = ccu::make_score_plan(h->nv, h->nA);
+  const ccu::ScorePlan plan = ccu::make_score_plan(h->nv, h->nA, h->alpha.data());
   CCU_CUDA(h, ccu::launch_score(d, plan, h->num_sms, raw2, cell_begin, cell_end, nullptr, h->stream));
   CCU_CUDA(h, ccu::launch_dbg_convert(raw2, llk_dev, (int64_t)n, h->stream));
   CCU_CUDA(h, ccu::launch_singlet_to_dbg(d, llk_dev, cell_begin, cell_end, h->stream));

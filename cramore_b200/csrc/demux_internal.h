@@ -11,7 +11,7 @@ namespace ccu {
 constexpr int kTileStride = 10;  // doubles per alpha in the device tile ([nnz][nA][10]; 9 used, 80 B
                                  // keeps every alpha block 16-byte aligned for cp.async.bulk)
 constexpr int kJT = 32;          // samples j per scoring CTA tile
-constexpr int kScoreThreads = 256;
+constexpr int kScoreThreads = 512;  // consumer threads of the scoring CTA
 
 // One (best or next) candidate of the doublet scan in the product domain:
 // LLK = log(m) + e*ln2, pos = (j*nv + k)*nA + n  (scan order of cmd_cram_demuxlet.cpp:883-906).
@@ -65,8 +65,9 @@ struct ScorePlan {
   int njt, nkt, nac;   // tiles per cell
   int items_per_cell;
   size_t smem_bytes;
+  uint8_t is_half[CCU_MAX_ALPHA];  // alpha[n] == 0.5
 };
-ScorePlan make_score_plan(int nv, int nA);
+ScorePlan make_score_plan(int nv, int nA, const double* alpha);
 
 // launch wrappers (all asynchronous on `st`); return cudaGetLastError()
 cudaError_t launch_gp_prepare(const float* gp_f32, const double* snp_err, const uint8_t* has_gp,

@@ -410,24 +410,28 @@ cudaError_t launch_singlet_to_dbg(const DemuxDev& d, double* llk_dbg, int64_t c0
 // K2: pair x alpha scoring (cmd_cram_demuxlet.cpp:733-747, reduced per :809-821 and :883-906)
 // ------------------------------------------------------------------------------------------
 // Work item = (droplet, j-tile of 32 samples, k-tile of 32*TK samples, chunk of AC doublet
-// alphas).  A persistent CTA (one per SM) walks its items as ONE stream of 8-SNP chunks:
-//   * warp 8 (producer) streams, per SNP of a chunk, the j-rows and k-rows of the FP64 genotype
+// alphas).  A persistent CTA (one per SM) walks its items as ONE stream of SNP chunks:
+//   * the producer warp streams, per SNP of a chunk, the j-rows and k-rows of the FP64 genotype
 //     matrix and the alpha block of the droplet's tile into a shared-memory ring with TMA bulk
-//     copies (cp.async.bulk, completion on "full" mbarriers); consumer warps hand stages back
-//     through "empty" mbarriers, so the ring never drains across item boundaries;
-//   * warps 0-7 (consumers) turn the k-rows x tile block into T[k][n][l] (double-buffered smem),
-//     then each thread owns 4 samples j x (TK x AC) columns = 40 running products in registers
-//     and spends 2 DFMA + 2 DMUL per (SNP, j, k, alpha);
+//     copies (cp.async.bulk, completion on "full" mbarriers) and publishes the chunk's metadata
+//     next to it; consumers hand stages back through "empty" mbarriers, so the ring never drains
+//     across item boundaries and consumer warps never touch global memory for control flow;
+//   * 16 consumer warps turn the k-rows x tile block into T[k][n][l] (double-buffered smem), then
+//     each thread owns 2 samples j x (TK x AC) columns = 20 running products in registers and
+//     spends 2 DFMA + 2 DMUL per (SNP, j, k, alpha).  Four warps per scheduler hide the FP64
+//     dependent-issue latency that two warps could not (ncu: "wait" stalls, profiles/);
 //   * at the end of an item the products become log-sum-exp / top-2 partials (no log needed:
 //     ordering by (exponent, mantissa) is ordering by LLK).
-constexpr int kNS = 3;   // raw ring stages
-constexpr int kTJ = 4;   // samples j per thread
-constexpr int kConsumers = kScoreThreads;        // 8 consumer warps
-constexpr int kScoreBlock = kScoreThreads + 128;  // + the producer warpgroup (1 working warp)
-// Register budget: the kernel launches with 168 registers/thread (65536 / 384); the producer
-// warpgroup shrinks to 24 and the two consumer warpgroups grow to 240 (8*32*240 + 4*32*24 = 64512).
+constexpr int kNS = 3;                              // raw ring stages
+constexpr int kTJ = 2;                              // samples j per thread
+constexpr int kConsumers = kScoreThreads;           // 16 consumer warps
+constexpr int kScoreBlock = kScoreThreads + 128;    // + the producer warpgroup (1 working warp)
+// Register budget: the kernel launches with 96 registers/thread (65536 / 640 rounded down to the
+// allocation unit); the producer warpgroup shrinks to 24 and the four consumer warpgroups grow
+// to 112 out of the CTA's own pool (16*32*112 + 4*32*24 = 60416 <= 640*96 = 61440).
 constexpr int kRegsProducer = 24;
-constexpr int kRegsConsumer = 240;
+constexpr int kRegsConsumer = 112;
+static_assert(kScoreThreads == 512, "thread mapping below assumes 16 consumer warps");
 
 __device__ __forceinline__ void consumer_bar() {
   asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
@@ -435,6 +439,17 @@ __device__ __forceinline__ void consumer_bar() {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+
+struct ChunkMeta {   // published by the producer with each ring stage
+  int32_t cnt;       // SNPs in this chunk (0..SC)
+  int32_t flags;     // bit0 valid (0 = end of stream), bit1 last chunk of its item
+  int32_t chunk;     // chunk index within the item
+  int32_t cell;
+  int32_t j0, k0, n0;
+  int32_t _pad;
+  int64_t item;
+  int64_t _pad2;
+};
 
 template <int AC, int TK>
 struct ScoreCfg {
@@ -452,8 +467,13 @@ struct ScoreCfg {
   static constexpr int SLOT_BYTES = GJ_BYTES + GK_BYTES + PG_BYTES;
   static constexpr int STAGE_BYTES = SC * SLOT_BYTES;
   static constexpr int T_BYTES = SC * 32 * TROW * 8;
-  static constexpr int RED_BYTES = 8 * 64;
-  static constexpr int SMEM_BYTES = kNS * STAGE_BYTES + 2 * T_BYTES + RED_BYTES + 2 * kNS * 8 + 16;
+  static constexpr int RED_BYTES = (kConsumers / 32) * 64;
+  static constexpr int META_BYTES = kNS * (int)sizeof(ChunkMeta);
+  static constexpr int OFF_T = kNS * STAGE_BYTES;
+  static constexpr int OFF_RED = OFF_T + 2 * T_BYTES;
+  static constexpr int OFF_META = OFF_RED + RED_BYTES;
+  static constexpr int OFF_BAR = OFF_META + META_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 2 * kNS * 8 + 16;
   // T-compute task split: NG alpha groups per (SNP slot, k) pair, APT alphas per task
   static constexpr int PAIRS = SC * KT;
   static constexpr int NG = (PAIRS >= kConsumers) ? 1 : (kConsumers / PAIRS);
@@ -462,14 +482,7 @@ struct ScoreCfg {
   static_assert(TROW % 2 == 0, "16-byte aligned T rows");
   static_assert(AC % NG == 0, "alpha groups must divide the chunk");
   static_assert((KT & (KT - 1)) == 0 && (NG & (NG - 1)) == 0, "power-of-two task decode");
-};
-
-struct ItemCursor {
-  int64_t item;   // global item id
-  int64_t ent0;   // cell_ptr[cell]
-  int32_t cell, nent, nch, chunk;
-  int32_t j0, k0, n0;
-  bool valid;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 struct WarpRed {
@@ -477,24 +490,24 @@ struct WarpRed {
   int32_t lse_e, _pad;
   Cand b1, b2;
 };
+static_assert(sizeof(WarpRed) <= 64, "WarpRed slot");
 
 template <int AC, int TK>
 __global__ void __launch_bounds__(kScoreBlock, 1)
-    demux_score_kernel(DemuxDev d, int njt, int nkt, int nac, int64_t nitems, double2* __restrict__ dbg,
-                       int64_t dbg_c0, int64_t dbg_c1) {
+    demux_score_kernel(DemuxDev d, int njt, int nkt, int nac, int64_t nitems, uint32_t half_mask,
+                       double2* __restrict__ dbg, int64_t dbg_c0, int64_t dbg_c1) {
   using Cfg = ScoreCfg<AC, TK>;
   constexpr int kSC = Cfg::SC;
   constexpr int kRS = Cfg::RS;
-  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "shared memory budget");
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* raw = smem;
-  double* Tbuf = reinterpret_cast<double*>(smem + kNS * Cfg::STAGE_BYTES);
-  WarpRed* red = reinterpret_cast<WarpRed*>(smem + kNS * Cfg::STAGE_BYTES + 2 * Cfg::T_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kNS * Cfg::STAGE_BYTES + 2 * Cfg::T_BYTES + Cfg::RED_BYTES);
+  double* Tbuf = reinterpret_cast<double*>(smem + Cfg::OFF_T);
+  WarpRed* red = reinterpret_cast<WarpRed*>(smem + Cfg::OFF_RED);
+  ChunkMeta* meta = reinterpret_cast<ChunkMeta*>(smem + Cfg::OFF_META);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* empty = full + kNS;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ipc = njt * nkt * nac;
 
   // zero the ring once (partial k-tiles / alpha chunks leave their tail untouched)
   for (int i = tid; i < kNS * Cfg::STAGE_BYTES / 8; i += kScoreBlock) reinterpret_cast<double*>(raw)[i] = 0.0;
@@ -508,59 +521,70 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
   fence_proxy_async();
   __syncthreads();
 
-  auto load_item = [&](ItemCursor& c, int64_t item) {
-    c.item = item;
-    c.valid = item < nitems;
-    c.chunk = 0;
-    if (!c.valid) return;
-    const int64_t cell = item / ipc;
-    int t = (int)(item - cell * ipc);
-    const int ac = t % nac;
-    t /= nac;
-    const int kt = t % nkt;
-    const int jt = t / nkt;
-    c.cell = (int32_t)cell;
-    c.ent0 = d.cell_ptr[cell];
-    c.nent = d.vcnt[cell];
-    c.nch = max(1, (c.nent + kSC - 1) / kSC);
-    c.j0 = jt * kJT;
-    c.k0 = kt * Cfg::KT;
-    c.n0 = 1 + ac * AC;
-  };
-  auto advance = [&](ItemCursor& c) {
-    if (++c.chunk >= c.nch) load_item(c, c.item + gridDim.x);
-  };
-
   if (warp >= kConsumers / 32) {
-    // ======================= producer warp: TMA bulk copies =======================
+    // ======================= producer warp: TMA bulk copies + chunk metadata =======================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
     if (warp != kConsumers / 32) return;
-    ItemCursor pc;
-    load_item(pc, blockIdx.x);
-    for (uint32_t g = 0; pc.valid; ++g) {
-      const int stage = g % kNS;
-      if (g >= (uint32_t)kNS) mbar_wait(smem_u32(&empty[stage]), ((g / kNS) - 1) & 1);
-      const int cnt = min(kSC, pc.nent - pc.chunk * kSC);
-      const int krows = min(Cfg::KT, d.nvp - pc.k0);
-      const int nal = min(AC, d.nA - pc.n0);
+    const int ipc = njt * nkt * nac;
+    int64_t item = blockIdx.x;
+    uint32_t g = 0;
+    while (true) {
+      const bool valid = item < nitems;
+      int32_t cell = 0, nent = 0, nch = 1, j0 = 0, k0 = 0, n0 = 1;
+      int64_t ent0 = 0;
+      if (valid) {
+        const int64_t c64 = item / ipc;
+        int t = (int)(item - c64 * ipc);
+        const int ac = t % nac;
+        t /= nac;
+        cell = (int32_t)c64;
+        ent0 = d.cell_ptr[c64];
+        nent = d.vcnt[c64];
+        nch = max(1, (nent + kSC - 1) / kSC);
+        j0 = (t / nkt) * kJT;
+        k0 = (t % nkt) * Cfg::KT;
+        n0 = 1 + ac * AC;
+      }
+      const int krows = min(Cfg::KT, d.nvp - k0);
+      const int nal = min(AC, d.nA - n0);
       const uint32_t kbytes = (uint32_t)krows * 24u, pbytes = (uint32_t)nal * (kTileStride * 8);
-      const uint32_t bar = smem_u32(&full[stage]);
-      int64_t e = 0, snp = 0;
-      if (lane < cnt) {
-        const int64_t idx = pc.ent0 + (int64_t)pc.chunk * kSC + lane;
-        e = d.vent[idx];
-        snp = d.vsnp[idx];
+      for (int chunk = 0; chunk < nch; ++chunk, ++g) {
+        const int stage = g % kNS;
+        if (g >= (uint32_t)kNS) mbar_wait(smem_u32(&empty[stage]), ((g / kNS) - 1) & 1);
+        const uint32_t bar = smem_u32(&full[stage]);
+        const int cnt = valid ? max(0, min(kSC, nent - chunk * kSC)) : 0;
+        int64_t e = 0, snp = 0;
+        if (lane < cnt) {
+          const int64_t idx = ent0 + (int64_t)chunk * kSC + lane;
+          e = d.vent[idx];
+          snp = d.vsnp[idx];
+        }
+        if (lane == 0) {
+          ChunkMeta m;
+          m.cnt = cnt;
+          m.flags = (valid ? 1 : 0) | ((chunk + 1 >= nch) ? 2 : 0);
+          m.chunk = chunk;
+          m.cell = cell;
+          m.j0 = j0;
+          m.k0 = k0;
+          m.n0 = n0;
+          m._pad = 0;
+          m.item = item;
+          m._pad2 = 0;
+          meta[stage] = m;
+          mbar_expect_tx(bar, (uint32_t)cnt * (Cfg::GJ_BYTES + kbytes + pbytes));  // release: meta visible
+        }
+        __syncwarp();
+        if (lane < cnt) {
+          const uint32_t slot = smem_u32(raw + stage * Cfg::STAGE_BYTES + lane * Cfg::SLOT_BYTES);
+          const double* grow = d.G + snp * (int64_t)d.nvp * 3;
+          bulk_g2s(slot, grow + (int64_t)j0 * 3, Cfg::GJ_BYTES, bar);
+          bulk_g2s(slot + Cfg::GJ_BYTES, grow + (int64_t)k0 * 3, kbytes, bar);
+          bulk_g2s(slot + Cfg::GJ_BYTES + Cfg::GK_BYTES, d.tiles + (e * d.nA + n0) * kTileStride, pbytes, bar);
+        }
       }
-      if (lane == 0) mbar_expect_tx(bar, (uint32_t)max(cnt, 0) * (Cfg::GJ_BYTES + kbytes + pbytes));
-      __syncwarp();
-      if (lane < cnt) {
-        const uint32_t slot = smem_u32(raw + stage * Cfg::STAGE_BYTES + lane * Cfg::SLOT_BYTES);
-        const double* grow = d.G + snp * (int64_t)d.nvp * 3;
-        bulk_g2s(slot, grow + (int64_t)pc.j0 * 3, Cfg::GJ_BYTES, bar);
-        bulk_g2s(slot + Cfg::GJ_BYTES, grow + (int64_t)pc.k0 * 3, kbytes, bar);
-        bulk_g2s(slot + Cfg::GJ_BYTES + Cfg::GK_BYTES, d.tiles + (e * d.nA + pc.n0) * kTileStride, pbytes, bar);
-      }
-      advance(pc);
+      if (!valid) break;  // the chunk just published was the end-of-stream sentinel
+      item += gridDim.x;
     }
     return;
   }
@@ -568,11 +592,10 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
   // ======================= consumer warps =======================
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
   const int kidx = (warp & 3) * 8 + (lane & 7);  // k-lane 0..31
-  const int jg = (warp >> 2) * 4 + (lane >> 3);  // j-group 0..7
+  const int jg = (warp >> 2) * 4 + (lane >> 3);  // j-group 0..15
 
   // T[s][klane][(kk*AC + a)*3 + l] = sum_m g_k[m] * pG[a][l][m]
-  auto compute_T = [&](const ItemCursor& c, int stage, int tb) {
-    const int cnt = min(kSC, c.nent - c.chunk * kSC);
+  auto compute_T = [&](int cnt, int stage, int tb) {
     double* T = Tbuf + tb * (Cfg::T_BYTES / 8);
     const unsigned char* st = raw + stage * Cfg::STAGE_BYTES;
 #pragma unroll
@@ -622,27 +645,29 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
   };
 
   // item epilogue: products -> partial log-sum-exp + top-2 candidates for this item
-  auto epilogue = [&](const ItemCursor& c) {
+  auto epilogue = [&](const ChunkMeta* mt) {
     renorm_all();
+    const int j0 = mt->j0, k0 = mt->k0, n0 = mt->n0;
+    const int64_t cell = mt->cell;
+    const int64_t item = mt->item;
     double la = 0.0;
     int le = kLseEmpty;
     Cand b1 = cand_empty(), b2 = cand_empty();
-    const int64_t cell = c.cell;
     const bool want_dbg = (dbg != nullptr) && cell >= dbg_c0 && cell < dbg_c1;
 #pragma unroll
     for (int jj = 0; jj < kTJ; ++jj) {
-      const int j = c.j0 + jg * kTJ + jj;
+      const int j = j0 + jg * kTJ + jj;
 #pragma unroll
       for (int cc = 0; cc < Cfg::NCOL; ++cc) {
-        const int k = c.k0 + kidx * TK + cc / AC;
-        const int n = c.n0 + cc % AC;
+        const int k = k0 + kidx * TK + cc / AC;
+        const int n = n0 + cc % AC;
         if (j < d.nv && k < d.nv && n < d.nA) {
           const double m = acc[jj][cc];
           const int e = aex[jj][cc];
           if (want_dbg) dbg[(((cell - dbg_c0) * d.nv + j) * d.nv + k) * d.nA + n] = make_double2(m, (double)e);
           if (j != k && m > 0.0) {
             // :812-817  alpha == 0.5 is counted once (k <= j) with twice the prior
-            const double w = d.is_half[n] ? ((k < j) ? 2.0 : 0.0) : 1.0;
+            const double w = ((half_mask >> n) & 1u) ? ((k < j) ? 2.0 : 0.0) : 1.0;
             lse_add(la, le, w * m, e);
             Cand x;
             x.m = m;
@@ -681,25 +706,25 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
       p._pad = 0;
       p.best = b1;
       p.next = b2;
-      d.partials[c.item] = p;
+      d.partials[item] = p;
     }
     reset_acc();
   };
 
   // ---------------- chunk stream ----------------
-  ItemCursor cur;
-  load_item(cur, blockIdx.x);
-  if (!cur.valid) return;
   reset_acc();
   mbar_wait(smem_u32(&full[0]), 0);
-  compute_T(cur, 0, 0);
+  int cnt = meta[0].cnt;
+  int flags = meta[0].flags;
+  int chunk = meta[0].chunk;
+  if (!(flags & 1)) return;
+  compute_T(cnt, 0, 0);
   consumer_bar();
 
-  for (uint32_t g = 0; cur.valid; ++g) {
+  for (uint32_t g = 0;; ++g) {
     const int stage = g % kNS, tb = g & 1;
-    // ---- main: 4 x NCOL running products over the chunk's SNPs
+    // ---- main: kTJ x NCOL running products over the chunk's SNPs
     {
-      const int cnt = min(kSC, cur.nent - cur.chunk * kSC);
       const unsigned char* st = raw + stage * Cfg::STAGE_BYTES;
       const double* T = Tbuf + tb * (Cfg::T_BYTES / 8) + kidx * Cfg::TROW;
       for (int s = 0; s < cnt; ++s) {
@@ -725,22 +750,23 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
         }
       }
     }
+    // ---- look ahead: T of the next chunk (possibly of the next item)
+    const uint32_t g1 = g + 1;
+    const int nstage = g1 % kNS;
+    mbar_wait(smem_u32(&full[nstage]), (g1 / kNS) & 1);
+    const int ncnt = meta[nstage].cnt, nflags = meta[nstage].flags, nchunk = meta[nstage].chunk;
+    if (nflags & 1) compute_T(ncnt, nstage, g1 & 1);
+    if (flags & 2)
+      epilogue(&meta[stage]);
+    else if ((chunk % kRS) == kRS - 1)
+      renorm_all();
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&empty[stage]));  // this warp is done with ring stage `stage`
-    // ---- look ahead: T of the next chunk (possibly of the next item)
-    ItemCursor nxt = cur;
-    advance(nxt);
-    if (nxt.valid) {
-      const uint32_t g1 = g + 1;
-      mbar_wait(smem_u32(&full[g1 % kNS]), (g1 / kNS) & 1);
-      compute_T(nxt, g1 % kNS, g1 & 1);
-    }
-    if (cur.chunk + 1 >= cur.nch)
-      epilogue(cur);
-    else if ((cur.chunk % kRS) == kRS - 1)
-      renorm_all();
     consumer_bar();
-    cur = nxt;
+    if (!(nflags & 1)) break;
+    cnt = ncnt;
+    flags = nflags;
+    chunk = nchunk;
   }
 }
 
@@ -761,8 +787,9 @@ cudaError_t launch_dbg_convert(double2* dbg, double* llk, int64_t n, cudaStream_
   return cudaGetLastError();
 }
 
-ScorePlan make_score_plan(int nv, int nA) {
+ScorePlan make_score_plan(int nv, int nA, const double* alpha) {
   ScorePlan p;
+  for (int n = 0; n < CCU_MAX_ALPHA; ++n) p.is_half[n] = (n < nA && alpha[n] == 0.5) ? 1 : 0;
   const int nd = nA - 1;
   // alphas per chunk: minimise padded work, prefer larger chunks on ties
   const int cand[4] = {10, 5, 2, 1};
@@ -802,8 +829,11 @@ static cudaError_t launch_score_t(const DemuxDev& d, const ScorePlan& plan, int 
   const int64_t nitems = d.nbcs * plan.items_per_cell;
   int grid = (int)((nitems < num_sms) ? nitems : num_sms);
   if (grid_out) *grid_out = grid;
-  demux_score_kernel<AC, TK><<<grid, kScoreBlock, Cfg::SMEM_BYTES, st>>>(d, plan.njt, plan.nkt, plan.nac,
-                                                                          nitems, llk_dbg, c0, c1);
+  uint32_t half_mask = 0;
+  for (int n = 0; n < d.nA && n < 32; ++n)
+    if (plan.is_half[n]) half_mask |= 1u << n;
+  demux_score_kernel<AC, TK><<<grid, kScoreBlock, Cfg::SMEM_BYTES, st>>>(d, plan.njt, plan.nkt, plan.nac, nitems,
+                                                                        half_mask, llk_dbg, c0, c1);
   return cudaGetLastError();
 }
 
