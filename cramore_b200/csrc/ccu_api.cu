@@ -76,7 +76,7 @@ struct ccu_handle {
   int64_t nbcs = -1, nnz = 0, nreads = 0;
   bool ran = false;
   DevBuf d_cell_ptr, d_snp_idx, d_read_ptr, d_al, d_bq;
-  DevBuf d_tiles, d_vent, d_vsnp, d_vcnt, d_sng, d_partials, d_results, d_dbg, d_sink;
+  DevBuf d_tiles, d_eclass, d_vent, d_vsnp, d_vcnt, d_sng, d_fmat, d_pm, d_pe, d_partials, d_results, d_dbg, d_sink;
 };
 
 namespace {
@@ -126,8 +126,13 @@ ccu::DemuxDev dev_view(const ccu_handle* h) {
   d.tiles = h->d_tiles.as<double>();
   d.vent = h->d_vent.as<int64_t>();
   d.vsnp = h->d_vsnp.as<int32_t>();
-  d.vcnt = h->d_vcnt.as<int32_t>();
+  d.eclass = h->d_eclass.as<uint8_t>();
+  d.vcnt_g = h->d_vcnt.as<int32_t>();
+  d.vcnt_a = h->d_vcnt.as<int32_t>() + (h->nbcs > 0 ? h->nbcs : 0);
   d.sng_llk = h->d_sng.as<double>();
+  d.fmat = h->d_fmat.as<double>();
+  d.pm = h->d_pm.as<double>();
+  d.pe = h->d_pe.as<int32_t>();
   d.partials = h->d_partials.as<ccu::ItemPartial>();
   d.results = h->d_results.as<ccu_demux_result>();
   return d;
@@ -195,7 +200,7 @@ int ccu_destroy(ccu_handle* h) {
   cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->d_alpha, &h->d_ptab, &h->d_half, &h->d_phred, &h->d_gpf, &h->d_err, &h->d_hasgp,
                     &h->d_avg, &h->d_G, &h->d_cell_ptr, &h->d_snp_idx, &h->d_read_ptr, &h->d_al, &h->d_bq,
-                    &h->d_tiles, &h->d_vent, &h->d_vsnp, &h->d_vcnt, &h->d_sng, &h->d_partials, &h->d_results, &h->d_dbg,
+                    &h->d_tiles, &h->d_eclass, &h->d_vent, &h->d_vsnp, &h->d_vcnt, &h->d_sng, &h->d_fmat, &h->d_pm, &h->d_pe, &h->d_partials, &h->d_results, &h->d_dbg,
                     &h->d_sink};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < EV_COUNT; ++i)
@@ -323,8 +328,12 @@ int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const
   CCU_CUDA(h, h->d_tiles.reserve((size_t)nnz * h->nA * ccu::kTileStride * sizeof(double) + 16));
   CCU_CUDA(h, h->d_vent.reserve(nnz * sizeof(int64_t) + 16));
   CCU_CUDA(h, h->d_vsnp.reserve(nnz * sizeof(int32_t) + 16));
-  CCU_CUDA(h, h->d_vcnt.reserve(nbcs * sizeof(int32_t) + 16));
+  CCU_CUDA(h, h->d_vcnt.reserve(2 * nbcs * sizeof(int32_t) + 16));
   CCU_CUDA(h, h->d_sng.reserve((size_t)nbcs * h->nv * sizeof(double) + 16));
+  CCU_CUDA(h, h->d_eclass.reserve(nnz + 16));
+  CCU_CUDA(h, h->d_fmat.reserve((size_t)nnz * h->nvp * sizeof(double) + 16));
+  CCU_CUDA(h, h->d_pm.reserve((size_t)nbcs * h->nvp * sizeof(double) + 16));
+  CCU_CUDA(h, h->d_pe.reserve((size_t)nbcs * h->nvp * sizeof(int32_t) + 16));
   CCU_CUDA(h, h->d_partials.reserve((size_t)nbcs * plan.items_per_cell * sizeof(ccu::ItemPartial) + 16));
   CCU_CUDA(h, h->d_results.reserve(nbcs * sizeof(ccu_demux_result) + 16));
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_X0], h->stream));
@@ -363,7 +372,7 @@ int ccu_demux_run(ccu_handle* h) {
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_TILE], st));
   CCU_CUDA(h, ccu::launch_compact(d, st));
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_COMPACT], st));
-  CCU_CUDA(h, ccu::launch_singlet(d, st));
+  CCU_CUDA(h, ccu::launch_sample(d, st));
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_SNG], st));
   CCU_CUDA(h, ccu::launch_score(d, plan, h->num_sms, nullptr, 0, 0, &grid, st));
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_SCORE], st));

@@ -50,10 +50,18 @@ struct DemuxDev {
   const uint8_t* bq;
   // intermediates
   double* tiles;           // [nnz][nA][kTileStride]
-  int64_t* vent;           // [nnz] per-cell compacted entry ids with genotypes
+  uint8_t* eclass;         // [nnz] 0 = at most one informative read (tile affine in the allele
+                           //       fraction), 1 = general
+  int64_t* vent;           // [nnz] per-cell compacted entry ids with genotypes: general entries
+                           //       first, then the affine ones
   int32_t* vsnp;           // [nnz] SNP id of each compacted entry
-  int32_t* vcnt;           // [nbcs]
+  int32_t* vcnt_g;         // [nbcs] general entries of the cell
+  int32_t* vcnt_a;         // [nbcs] affine entries of the cell
   double* sng_llk;         // [nbcs][nv]
+  double* fmat;            // per cell at cell_ptr[c]*nvp: [nvp/32][vcnt_a][32] normalised single-read
+                           //       likelihoods f = (sum_l g[l]*pG[0][l][0]) / (sum_l g[l])
+  double* pm;              // [nbcs][nvp] mantissa of prod over affine entries of sum_l g[l]
+  int32_t* pe;             // [nbcs][nvp] its binary exponent
   ItemPartial* partials;   // [nbcs * items_per_cell]
   ccu_demux_result* results;  // [nbcs]
 };
@@ -75,7 +83,7 @@ cudaError_t launch_gp_prepare(const float* gp_f32, const double* snp_err, const 
                               cudaStream_t st);
 cudaError_t launch_tile(const DemuxDev& d, cudaStream_t st);
 cudaError_t launch_compact(const DemuxDev& d, cudaStream_t st);
-cudaError_t launch_singlet(const DemuxDev& d, cudaStream_t st);
+cudaError_t launch_sample(const DemuxDev& d, cudaStream_t st);
 // dbg != NULL: also dump (mantissa, exponent) of every computed llksAB entry of cells [dbg_c0, dbg_c1)
 // into [cells][nv][nv][nA] double2; launch_dbg_convert turns them into log-likelihoods
 cudaError_t launch_score(const DemuxDev& d, const ScorePlan& plan, int num_sms, double2* dbg,

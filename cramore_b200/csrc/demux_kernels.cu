@@ -197,7 +197,8 @@ template <int GL>
 __global__ void __launch_bounds__(kTileWarps * 32)
     demux_tile_kernel(int64_t nnz, const int64_t* __restrict__ read_ptr, const uint8_t* __restrict__ al,
                       const uint8_t* __restrict__ bq, int nA, const double* __restrict__ ptab,
-                      const double* __restrict__ phred, double* __restrict__ tiles) {
+                      const double* __restrict__ phred, double* __restrict__ tiles,
+                      uint8_t* __restrict__ eclass) {
   constexpr int EPW = 32 / GL;  // entries per warp per pass
   __shared__ double s_err[256];
   __shared__ double s_mat[256];
@@ -237,12 +238,14 @@ __global__ void __launch_bounds__(kTileWarps * 32)
     double v[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) v[t] = 1.0;  // :657
+    int nuse = 0;  // informative reads of this entry
 
     for (int i = 0; i < maxcnt; ++i) {
       const bool act = i < cnt;
       const int a = act ? al[r0 + i] : 2;
       const int q = act ? bq[r0 + i] : 0;
       const bool use = (a != 2);  // :664
+      nuse += use ? 1 : 0;
       double mx = 0.0;
       if (use && has_alpha) {
         const double pR = (a == 0) ? s_mat[q] : s_err[q] / 3.0;  // :666
@@ -277,6 +280,9 @@ __global__ void __launch_bounds__(kTileWarps * 32)
       for (int t = 0; t < 9; ++t) o[t] = v[t] / mx;
       o[9] = 0.0;
     }
+    // With at most one informative read the tile is an affine function of the allele fraction
+    // p = (1-alpha)*l/2 + alpha*m/2, i.e. pG[n][l][m] = (1-alpha)*pG[0][l][.] + alpha*pG[0][m][.]
+    if (valid && n == 0) eclass[e] = (nuse > 1) ? 1 : 0;
     __syncwarp();
     int64_t nvalid = nnz - e0;
     if (nvalid > EPW) nvalid = EPW;
@@ -296,7 +302,7 @@ cudaError_t launch_tile(const DemuxDev& d, cudaStream_t st) {
   if (blocks > 148 * 16) blocks = 148 * 16;
 #define CCU_TILE(GL)                                                                              \
   demux_tile_kernel<GL><<<(unsigned)blocks, kTileWarps * 32, 0, st>>>(d.nnz, d.read_ptr, d.al, d.bq, \
-                                                                       d.nA, d.ptab, d.phred, d.tiles)
+                                                                       d.nA, d.ptab, d.phred, d.tiles, d.eclass)
   switch (gl) {
     case 2: CCU_TILE(2); break;
     case 4: CCU_TILE(4); break;
@@ -309,83 +315,118 @@ cudaError_t launch_tile(const DemuxDev& d, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------
-// compaction: vent[cell_ptr[c] + r] = r-th entry of cell c whose SNP has genotypes (:733)
+// compaction: per cell, the entries whose SNP has genotypes (:733), general entries first and
+// the affine (<= 1 informative read) entries after them:
+//   vent[cell_ptr[c] + r], r in [0, vcnt_g[c])                    general
+//   vent[cell_ptr[c] + vcnt_g[c] + r], r in [0, vcnt_a[c])        affine
 // ------------------------------------------------------------------------------------------
 __global__ void compact_kernel(int64_t nbcs, const int64_t* __restrict__ cell_ptr,
                                const int32_t* __restrict__ snp_idx, const uint8_t* __restrict__ has_gp,
-                               int64_t* __restrict__ vent, int32_t* __restrict__ vsnp,
-                               int32_t* __restrict__ vcnt) {
+                               const uint8_t* __restrict__ eclass, int64_t* __restrict__ vent,
+                               int32_t* __restrict__ vsnp, int32_t* __restrict__ vcnt_g,
+                               int32_t* __restrict__ vcnt_a) {
   const int lane = threadIdx.x & 31;
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= nbcs) return;
   const int64_t b = cell_ptr[c], e = cell_ptr[c + 1];
-  int run = 0;
-  for (int64_t i = b; i < e; i += 32) {
-    const int64_t idx = i + lane;
-    bool ok = false;
-    int32_t snp = 0;
-    if (idx < e) {
-      snp = snp_idx[idx];
-      ok = (has_gp == nullptr) || has_gp[snp];
+  int run = 0, ngen = 0;
+  for (int pass = 0; pass < 2; ++pass) {  // pass 0: general, pass 1: affine
+    for (int64_t i = b; i < e; i += 32) {
+      const int64_t idx = i + lane;
+      bool ok = false;
+      int32_t snp = 0;
+      if (idx < e) {
+        snp = snp_idx[idx];
+        ok = ((has_gp == nullptr) || has_gp[snp]) && ((eclass[idx] != 0) == (pass == 0));
+      }
+      const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int64_t o = b + run + __popc(mask & ((1u << lane) - 1u));
+        vent[o] = idx;
+        vsnp[o] = snp;
+      }
+      run += __popc(mask);
     }
-    const uint32_t mask = __ballot_sync(0xffffffffu, ok);
-    if (ok) {
-      const int64_t o = b + run + __popc(mask & ((1u << lane) - 1u));
-      vent[o] = idx;
-      vsnp[o] = snp;
-    }
-    run += __popc(mask);
+    if (pass == 0) ngen = run;
   }
-  if (lane == 0) vcnt[c] = run;
+  if (lane == 0) {
+    vcnt_g[c] = ngen;
+    vcnt_a[c] = run - ngen;
+  }
 }
 
 cudaError_t launch_compact(const DemuxDev& d, cudaStream_t st) {
   if (d.nbcs == 0) return cudaSuccess;
   int64_t blocks = (d.nbcs * 32 + 255) / 256;
-  compact_kernel<<<(unsigned)blocks, 256, 0, st>>>(d.nbcs, d.cell_ptr, d.snp_idx, d.has_gp, d.vent, d.vsnp, d.vcnt);
+  compact_kernel<<<(unsigned)blocks, 256, 0, st>>>(d.nbcs, d.cell_ptr, d.snp_idx, d.has_gp, d.eclass, d.vent,
+                                                   d.vsnp, d.vcnt_g, d.vcnt_a);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
-// K2s: singlet likelihoods llksAB[j][0][0] (cmd_cram_demuxlet.cpp:733-747 at k=0, n=0)
+// K2s: per-(droplet, sample) prepass
+//   * singlet likelihoods llksAB[j][0][0] (cmd_cram_demuxlet.cpp:733-747 at k=0, n=0).  alpha[0]==0
+//     makes the tile independent of m, but the reference still multiplies by sample 0's genotype
+//     row, so T0 uses g_0;
+//   * for the affine entries: f_j = F_j / s_j with F_j = sum_l g_j[l]*pG[0][l][0] and
+//     s_j = sum_l g_j[l], written as [32-sample tile][entry][32] so that the scoring kernel streams
+//     a (tile x entry chunk) block with one bulk copy, and the per-droplet product of the s_j.
+//     For such an entry sum_{l,m} g_j[l] g_k[m] pG[n][l][m] = s_j s_k ((1-alpha_n) f_j + alpha_n f_k).
+// One warp per (droplet, 32-sample tile), lanes over samples.
 // ------------------------------------------------------------------------------------------
-// One warp per droplet, lanes over samples.  alpha[0]==0 makes the tile independent of m, but the
-// reference still multiplies by sample 0's genotype row, so T0 uses g_0.
 __global__ void __launch_bounds__(256)
-    demux_singlet_kernel(DemuxDev d) {
+    demux_sample_kernel(DemuxDev d) {
   const int lane = threadIdx.x & 31;
-  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int ntile = d.nvp >> 5;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t c = w / ntile;
   if (c >= d.nbcs) return;
+  const int tile = (int)(w - c * ntile);
+  const int j = tile * 32 + lane;
   const int64_t base = d.cell_ptr[c];
-  const int cnt = d.vcnt[c];
+  const int ng = d.vcnt_g[c], na = d.vcnt_a[c];
   const int64_t rowlen = (int64_t)d.nA * kTileStride;
   const int64_t grow = (int64_t)d.nvp * 3;
-  for (int jb = 0; jb < d.nvp; jb += 32) {
-    const int j = jb + lane;
-    double m = 1.0;
-    int ex = 0;
-    for (int i = 0; i < cnt; ++i) {
-      const int64_t e = d.vent[base + i];
-      const double* pg = d.tiles + e * rowlen;  // alpha index 0
-      const double* g = d.G + (int64_t)d.vsnp[base + i] * grow;
-      const double g00 = g[0], g01 = g[1], g02 = g[2];
-      const double t0 = fma(g02, pg[2], fma(g01, pg[1], g00 * pg[0]));
-      const double t1 = fma(g02, pg[5], fma(g01, pg[4], g00 * pg[3]));
-      const double t2 = fma(g02, pg[8], fma(g01, pg[7], g00 * pg[6]));
-      const double* gj = g + 3 * j;
-      m *= fma(gj[2], t2, fma(gj[1], t1, gj[0] * t0));
-      if ((i & 15) == 15) renorm(m, ex);
+  double* fdst = d.fmat + base * d.nvp + (int64_t)tile * 32 * na + lane;
+  double m = 1.0, pm = 1.0;
+  int ex = 0, pe = 0;
+  const int cnt = ng + na;
+#pragma unroll 2
+  for (int i = 0; i < cnt; ++i) {
+    const int64_t e = d.vent[base + i];
+    const double* pg = d.tiles + e * rowlen;  // alpha index 0
+    const double* g = d.G + (int64_t)d.vsnp[base + i] * grow;
+    const double g00 = g[0], g01 = g[1], g02 = g[2];
+    const double t0 = fma(g02, pg[2], fma(g01, pg[1], g00 * pg[0]));
+    const double t1 = fma(g02, pg[5], fma(g01, pg[4], g00 * pg[3]));
+    const double t2 = fma(g02, pg[8], fma(g01, pg[7], g00 * pg[6]));
+    const double* gj = g + 3 * j;
+    const double gj0 = gj[0], gj1 = gj[1], gj2 = gj[2];
+    m *= fma(gj2, t2, fma(gj1, t1, gj0 * t0));
+    if (i >= ng) {
+      const double F = fma(gj2, pg[6], fma(gj1, pg[3], gj0 * pg[0]));
+      const double sj = (gj0 + gj1) + gj2;
+      const bool live = (j < d.nv) && (sj > 0.0);
+      fdst[(int64_t)(i - ng) * 32] = live ? F / sj : ((j < d.nv) ? 0.0 : 1.0);
+      pm *= (j < d.nv) ? sj : 1.0;
     }
-    renorm(m, ex);
-    if (j < d.nv)
-      d.sng_llk[c * d.nv + j] = (m > 0.0) ? (log(m) + (double)ex * 0.6931471805599453094) : -CUDART_INF;
+    if ((i & 15) == 15) {
+      renorm(m, ex);
+      renorm(pm, pe);
+    }
   }
+  renorm(m, ex);
+  renorm(pm, pe);
+  if (j < d.nv)
+    d.sng_llk[c * d.nv + j] = (m > 0.0) ? (log(m) + (double)ex * 0.6931471805599453094) : -CUDART_INF;
+  d.pm[c * d.nvp + j] = pm;
+  d.pe[c * d.nvp + j] = pe;
 }
 
-cudaError_t launch_singlet(const DemuxDev& d, cudaStream_t st) {
+cudaError_t launch_sample(const DemuxDev& d, cudaStream_t st) {
   if (d.nbcs == 0) return cudaSuccess;
-  int64_t blocks = (d.nbcs * 32 + 255) / 256;
-  demux_singlet_kernel<<<(unsigned)blocks, 256, 0, st>>>(d);
+  int64_t blocks = (d.nbcs * (d.nvp >> 5) * 32 + 255) / 256;
+  demux_sample_kernel<<<(unsigned)blocks, 256, 0, st>>>(d);
   return cudaGetLastError();
 }
 
@@ -410,16 +451,23 @@ cudaError_t launch_singlet_to_dbg(const DemuxDev& d, double* llk_dbg, int64_t c0
 // K2: pair x alpha scoring (cmd_cram_demuxlet.cpp:733-747, reduced per :809-821 and :883-906)
 // ------------------------------------------------------------------------------------------
 // Work item = (droplet, j-tile of 32 samples, k-tile of 32*TK samples, chunk of AC doublet
-// alphas).  A persistent CTA (one per SM) walks its items as ONE stream of SNP chunks:
-//   * the producer warp streams, per SNP of a chunk, the j-rows and k-rows of the FP64 genotype
-//     matrix and the alpha block of the droplet's tile into a shared-memory ring with TMA bulk
-//     copies (cp.async.bulk, completion on "full" mbarriers) and publishes the chunk's metadata
-//     next to it; consumers hand stages back through "empty" mbarriers, so the ring never drains
-//     across item boundaries and consumer warps never touch global memory for control flow;
-//   * 16 consumer warps turn the k-rows x tile block into T[k][n][l] (double-buffered smem), then
-//     each thread owns 2 samples j x (TK x AC) columns = 20 running products in registers and
-//     spends 2 DFMA + 2 DMUL per (SNP, j, k, alpha).  Four warps per scheduler hide the FP64
-//     dependent-issue latency that two warps could not (ncu: "wait" stalls, profiles/);
+// alphas).  A persistent CTA (one per SM) walks its items as ONE stream of entry chunks:
+//   * the producer warp streams the chunks into a shared-memory ring with TMA bulk copies
+//     (cp.async.bulk, completion on "full" mbarriers) and publishes each chunk's metadata next to
+//     it; consumers hand stages back through "empty" mbarriers, so the ring never drains across
+//     item boundaries and consumer warps never touch global memory for control flow;
+//   * 16 consumer warps; each thread owns 2 samples j x (TK x AC) columns = 20 running products
+//     in registers.  Two kinds of chunk feed them:
+//       general  (entries with >= 2 informative reads): per SNP the j-rows and k-rows of the FP64
+//                genotype matrix and the alpha block of the droplet's tile; the k-rows x tile
+//                block becomes T[k][n][l] (double-buffered smem), then 2 DFMA + 2 DMUL per
+//                (SNP, j, k, alpha);
+//       affine   (<= 1 informative read, the bulk of sparse single-cell data): the tile is affine
+//                in the allele fraction, so the term is s_j s_k ((1-alpha) f_j + alpha f_k).  The
+//                chunk is two (sample tile x entries) blocks of the prepass' f matrix, and the
+//                inner loop is 1 DFMA + 1 DMUL per (SNP, j, k, alpha) plus one DADD per (j, k):
+//                f_j + alpha (f_k - f_j).  The s_j s_k products are per-droplet constants applied
+//                in the item epilogue;
 //   * at the end of an item the products become log-sum-exp / top-2 partials (no log needed:
 //     ordering by (exponent, mantissa) is ordering by LLK).
 constexpr int kNS = 3;                              // raw ring stages
@@ -431,6 +479,8 @@ constexpr int kScoreBlock = kScoreThreads + 128;    // + the producer warpgroup 
 // to 112 out of the CTA's own pool (16*32*112 + 4*32*24 = 60416 <= 640*96 = 61440).
 constexpr int kRegsProducer = 24;
 constexpr int kRegsConsumer = 112;
+constexpr int kRenormAfter = 14;  // renormalise once this many SNPs are pending (factors >= ~2^-34:
+                                  // at most 13 + 16 SNPs ever accumulate between renormalisations)
 static_assert(kScoreThreads == 512, "thread mapping below assumes 16 consumer warps");
 
 __device__ __forceinline__ void consumer_bar() {
@@ -441,20 +491,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 struct ChunkMeta {   // published by the producer with each ring stage
-  int32_t cnt;       // SNPs in this chunk (0..SC)
-  int32_t flags;     // bit0 valid (0 = end of stream), bit1 last chunk of its item
-  int32_t chunk;     // chunk index within the item
+  int32_t cnt;       // entries in this chunk
+  int32_t flags;     // bit0 valid (0 = end of stream), bit1 last chunk of its item, bit2 affine
   int32_t cell;
   int32_t j0, k0, n0;
-  int32_t _pad;
   int64_t item;
-  int64_t _pad2;
 };
 
 template <int AC, int TK>
 struct ScoreCfg {
-  static constexpr int SC = (TK >= 8) ? 4 : 8;  // SNPs per chunk (bounded by shared memory)
-  static constexpr int RS = 16 / SC;            // renormalise every RS chunks (= 16 SNPs; factors >= ~2^-40)
+  static constexpr int SC = (TK >= 8) ? 4 : 8;  // SNPs per general chunk (bounded by shared memory)
+  static constexpr int SCA = (TK == 1) ? 32 : (TK <= 4) ? 16 : 8;  // entries per affine chunk
   static constexpr int NCOL = AC * TK;
   static constexpr int TROW0 = NCOL * 3;
   // row stride (doubles) of a thread's T block: even, and (stride/2) odd => the 8 distinct
@@ -465,14 +512,19 @@ struct ScoreCfg {
   static constexpr int GK_BYTES = KT * 24;
   static constexpr int PG_BYTES = AC * kTileStride * 8;
   static constexpr int SLOT_BYTES = GJ_BYTES + GK_BYTES + PG_BYTES;
-  static constexpr int STAGE_BYTES = SC * SLOT_BYTES;
+  static constexpr int PART_BYTES = SCA * 32 * 8;          // one (32-sample tile x SCA entries) block
+  static constexpr int STAGE_G = SC * SLOT_BYTES;
+  static constexpr int STAGE_A = (1 + TK) * PART_BYTES;
+  static constexpr int STAGE_BYTES = (STAGE_G > STAGE_A) ? STAGE_G : STAGE_A;
   static constexpr int T_BYTES = SC * 32 * TROW * 8;
   static constexpr int RED_BYTES = (kConsumers / 32) * 64;
   static constexpr int META_BYTES = kNS * (int)sizeof(ChunkMeta);
+  static constexpr int ALPHA_BYTES = 48 * 8;
   static constexpr int OFF_T = kNS * STAGE_BYTES;
   static constexpr int OFF_RED = OFF_T + 2 * T_BYTES;
   static constexpr int OFF_META = OFF_RED + RED_BYTES;
-  static constexpr int OFF_BAR = OFF_META + META_BYTES;
+  static constexpr int OFF_ALPHA = OFF_META + META_BYTES;
+  static constexpr int OFF_BAR = OFF_ALPHA + ALPHA_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 2 * kNS * 8 + 16;
   // T-compute task split: NG alpha groups per (SNP slot, k) pair, APT alphas per task
   static constexpr int PAIRS = SC * KT;
@@ -482,6 +534,8 @@ struct ScoreCfg {
   static_assert(TROW % 2 == 0, "16-byte aligned T rows");
   static_assert(AC % NG == 0, "alpha groups must divide the chunk");
   static_assert((KT & (KT - 1)) == 0 && (NG & (NG - 1)) == 0, "power-of-two task decode");
+  static_assert(STAGE_BYTES % 16 == 0 && OFF_T % 16 == 0, "bulk copy alignment");
+  static_assert(sizeof(ChunkMeta) == 32, "ChunkMeta layout");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -498,12 +552,13 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
                        double2* __restrict__ dbg, int64_t dbg_c0, int64_t dbg_c1) {
   using Cfg = ScoreCfg<AC, TK>;
   constexpr int kSC = Cfg::SC;
-  constexpr int kRS = Cfg::RS;
+  constexpr int kSCA = Cfg::SCA;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* raw = smem;
   double* Tbuf = reinterpret_cast<double*>(smem + Cfg::OFF_T);
   WarpRed* red = reinterpret_cast<WarpRed*>(smem + Cfg::OFF_RED);
   ChunkMeta* meta = reinterpret_cast<ChunkMeta*>(smem + Cfg::OFF_META);
+  double* s_alpha = reinterpret_cast<double*>(smem + Cfg::OFF_ALPHA);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* empty = full + kNS;
 
@@ -511,6 +566,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
 
   // zero the ring once (partial k-tiles / alpha chunks leave their tail untouched)
   for (int i = tid; i < kNS * Cfg::STAGE_BYTES / 8; i += kScoreBlock) reinterpret_cast<double*>(raw)[i] = 0.0;
+  if (tid < 48) s_alpha[tid] = (tid < d.nA) ? d.alpha[tid] : 0.0;
   if (tid == 0) {
     for (int s = 0; s < kNS; ++s) {
       mbar_init(smem_u32(&full[s]), 1);
@@ -530,7 +586,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
     uint32_t g = 0;
     while (true) {
       const bool valid = item < nitems;
-      int32_t cell = 0, nent = 0, nch = 1, j0 = 0, k0 = 0, n0 = 1;
+      int32_t cell = 0, ng = 0, na = 0, nchg = 0, nch = 1, j0 = 0, k0 = 0, n0 = 1;
       int64_t ent0 = 0;
       if (valid) {
         const int64_t c64 = item / ipc;
@@ -539,8 +595,10 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
         t /= nac;
         cell = (int32_t)c64;
         ent0 = d.cell_ptr[c64];
-        nent = d.vcnt[c64];
-        nch = max(1, (nent + kSC - 1) / kSC);
+        ng = d.vcnt_g[c64];
+        na = d.vcnt_a[c64];
+        nchg = (ng + kSC - 1) / kSC;
+        nch = max(1, nchg + (na + kSCA - 1) / kSCA);
         j0 = (t / nkt) * kJT;
         k0 = (t % nkt) * Cfg::KT;
         n0 = 1 + ac * AC;
@@ -552,9 +610,18 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
         const int stage = g % kNS;
         if (g >= (uint32_t)kNS) mbar_wait(smem_u32(&empty[stage]), ((g / kNS) - 1) & 1);
         const uint32_t bar = smem_u32(&full[stage]);
-        const int cnt = valid ? max(0, min(kSC, nent - chunk * kSC)) : 0;
+        const bool affine = chunk >= nchg;
+        int cnt;
+        uint32_t tx;
+        if (!affine) {
+          cnt = valid ? max(0, min(kSC, ng - chunk * kSC)) : 0;
+          tx = (uint32_t)cnt * (Cfg::GJ_BYTES + kbytes + pbytes);
+        } else {
+          cnt = valid ? max(0, min(kSCA, na - (chunk - nchg) * kSCA)) : 0;
+          tx = (uint32_t)cnt * 256u * (uint32_t)(1 + krows / 32);
+        }
         int64_t e = 0, snp = 0;
-        if (lane < cnt) {
+        if (!affine && lane < cnt) {
           const int64_t idx = ent0 + (int64_t)chunk * kSC + lane;
           e = d.vent[idx];
           snp = d.vsnp[idx];
@@ -562,25 +629,29 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
         if (lane == 0) {
           ChunkMeta m;
           m.cnt = cnt;
-          m.flags = (valid ? 1 : 0) | ((chunk + 1 >= nch) ? 2 : 0);
-          m.chunk = chunk;
+          m.flags = (valid ? 1 : 0) | ((chunk + 1 >= nch) ? 2 : 0) | (affine ? 4 : 0);
           m.cell = cell;
           m.j0 = j0;
           m.k0 = k0;
           m.n0 = n0;
-          m._pad = 0;
           m.item = item;
-          m._pad2 = 0;
           meta[stage] = m;
-          mbar_expect_tx(bar, (uint32_t)cnt * (Cfg::GJ_BYTES + kbytes + pbytes));  // release: meta visible
+          mbar_expect_tx(bar, tx);  // release: meta visible
         }
         __syncwarp();
-        if (lane < cnt) {
-          const uint32_t slot = smem_u32(raw + stage * Cfg::STAGE_BYTES + lane * Cfg::SLOT_BYTES);
-          const double* grow = d.G + snp * (int64_t)d.nvp * 3;
-          bulk_g2s(slot, grow + (int64_t)j0 * 3, Cfg::GJ_BYTES, bar);
-          bulk_g2s(slot + Cfg::GJ_BYTES, grow + (int64_t)k0 * 3, kbytes, bar);
-          bulk_g2s(slot + Cfg::GJ_BYTES + Cfg::GK_BYTES, d.tiles + (e * d.nA + n0) * kTileStride, pbytes, bar);
+        if (!affine) {
+          if (lane < cnt) {
+            const uint32_t slot = smem_u32(raw + stage * Cfg::STAGE_BYTES + lane * Cfg::SLOT_BYTES);
+            const double* grow = d.G + snp * (int64_t)d.nvp * 3;
+            bulk_g2s(slot, grow + (int64_t)j0 * 3, Cfg::GJ_BYTES, bar);
+            bulk_g2s(slot + Cfg::GJ_BYTES, grow + (int64_t)k0 * 3, kbytes, bar);
+            bulk_g2s(slot + Cfg::GJ_BYTES + Cfg::GK_BYTES, d.tiles + (e * d.nA + n0) * kTileStride, pbytes, bar);
+          }
+        } else if (cnt > 0 && lane <= krows / 32) {
+          // part 0: the j tile; parts 1..: the 32-sample tiles of the k tile
+          const int tile = (lane == 0) ? (j0 >> 5) : ((k0 >> 5) + lane - 1);
+          const double* src = d.fmat + ent0 * d.nvp + ((int64_t)tile * na + (int64_t)(chunk - nchg) * kSCA) * 32;
+          bulk_g2s(smem_u32(raw + stage * Cfg::STAGE_BYTES + lane * Cfg::PART_BYTES), src, (uint32_t)cnt * 256u, bar);
         }
       }
       if (!valid) break;  // the chunk just published was the end-of-stream sentinel
@@ -644,12 +715,91 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
       for (int cc = 0; cc < Cfg::NCOL; ++cc) renorm(acc[jj][cc], aex[jj][cc]);
   };
 
+  // ---- general chunk: kTJ x NCOL running products over the chunk's SNPs through T
+  auto main_general = [&](int cnt, int stage, int tb) {
+    const unsigned char* st = raw + stage * Cfg::STAGE_BYTES;
+    const double* T = Tbuf + tb * (Cfg::T_BYTES / 8) + kidx * Cfg::TROW;
+    for (int s = 0; s < cnt; ++s) {
+      const double2* gp2 = reinterpret_cast<const double2*>(st + s * Cfg::SLOT_BYTES) + jg * (kTJ * 3 / 2);
+      double gv[kTJ * 3];
+#pragma unroll
+      for (int i = 0; i < kTJ * 3 / 2; ++i) {
+        const double2 v = gp2[i];
+        gv[2 * i] = v.x;
+        gv[2 * i + 1] = v.y;
+      }
+      const double2* t2 = reinterpret_cast<const double2*>(T + s * 32 * Cfg::TROW);
+#pragma unroll
+      for (int c2 = 0; c2 < Cfg::NCOL / 2; ++c2) {
+        const double2 u0 = t2[3 * c2], u1 = t2[3 * c2 + 1], u2 = t2[3 * c2 + 2];
+#pragma unroll
+        for (int jj = 0; jj < kTJ; ++jj) {
+          const double da = fma(gv[jj * 3 + 2], u1.x, fma(gv[jj * 3 + 1], u0.y, gv[jj * 3] * u0.x));
+          const double db = fma(gv[jj * 3 + 2], u2.y, fma(gv[jj * 3 + 1], u2.x, gv[jj * 3] * u1.y));
+          acc[jj][2 * c2] *= da;
+          acc[jj][2 * c2 + 1] *= db;
+        }
+      }
+    }
+  };
+
+  // ---- affine chunk: acc[j][k][n] *= f_j + alpha_n (f_k - f_j)
+  auto main_affine = [&](int cnt, int stage, int n0) {
+    const double* fj_base = reinterpret_cast<const double*>(raw + stage * Cfg::STAGE_BYTES) + jg * kTJ;
+    // the thread's TK consecutive samples k sit inside one 32-sample part
+    const double* fk_base = reinterpret_cast<const double*>(raw + stage * Cfg::STAGE_BYTES + Cfg::PART_BYTES) +
+                            ((kidx * TK) >> 5) * (Cfg::PART_BYTES / 8) + ((kidx * TK) & 31);
+    double al[AC];
+#pragma unroll
+    for (int a = 0; a < AC; ++a) al[a] = s_alpha[n0 + a];
+#pragma unroll 2
+    for (int s = 0; s < cnt; ++s) {
+      const double2 fj = *reinterpret_cast<const double2*>(fj_base + s * 32);
+      double fk[TK];
+      if constexpr (TK == 1) {
+        fk[0] = fk_base[s * 32];
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < TK; kk += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(fk_base + s * 32 + kk);
+          fk[kk] = v.x;
+          fk[kk + 1] = v.y;
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < TK; ++kk) {
+        const double d0 = fk[kk] - fj.x, d1 = fk[kk] - fj.y;
+#pragma unroll
+        for (int a = 0; a < AC; ++a) {
+          acc[0][kk * AC + a] *= fma(al[a], d0, fj.x);
+          acc[1][kk * AC + a] *= fma(al[a], d1, fj.y);
+        }
+      }
+      if ((s & 15) == 15) renorm_all();
+    }
+  };
+
   // item epilogue: products -> partial log-sum-exp + top-2 candidates for this item
   auto epilogue = [&](const ChunkMeta* mt) {
     renorm_all();
     const int j0 = mt->j0, k0 = mt->k0, n0 = mt->n0;
     const int64_t cell = mt->cell;
     const int64_t item = mt->item;
+    // per-droplet constants of the affine entries: prod s_j and prod s_k
+    double pmj[kTJ], pmk[TK];
+    int pej[kTJ], pek[TK];
+#pragma unroll
+    for (int jj = 0; jj < kTJ; ++jj) {
+      const int j = j0 + jg * kTJ + jj;
+      pmj[jj] = d.pm[cell * d.nvp + j];
+      pej[jj] = d.pe[cell * d.nvp + j];
+    }
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      const int k = min(k0 + kidx * TK + kk, d.nvp - 1);
+      pmk[kk] = d.pm[cell * d.nvp + k];
+      pek[kk] = d.pe[cell * d.nvp + k];
+    }
     double la = 0.0;
     int le = kLseEmpty;
     Cand b1 = cand_empty(), b2 = cand_empty();
@@ -662,8 +812,9 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
         const int k = k0 + kidx * TK + cc / AC;
         const int n = n0 + cc % AC;
         if (j < d.nv && k < d.nv && n < d.nA) {
-          const double m = acc[jj][cc];
-          const int e = aex[jj][cc];
+          double m = acc[jj][cc] * (pmj[jj] * pmk[cc / AC]);
+          int e = aex[jj][cc] + pej[jj] + pek[cc / AC];
+          renorm(m, e);
           if (want_dbg) dbg[(((cell - dbg_c0) * d.nv + j) * d.nv + k) * d.nA + n] = make_double2(m, (double)e);
           if (j != k && m > 0.0) {
             // :812-817  alpha == 0.5 is counted once (k <= j) with twice the prior
@@ -716,57 +867,39 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
   mbar_wait(smem_u32(&full[0]), 0);
   int cnt = meta[0].cnt;
   int flags = meta[0].flags;
-  int chunk = meta[0].chunk;
   if (!(flags & 1)) return;
-  compute_T(cnt, 0, 0);
+  if (!(flags & 4)) compute_T(cnt, 0, 0);
   consumer_bar();
+  int pending = 0;  // SNPs multiplied in since the last renormalisation
 
   for (uint32_t g = 0;; ++g) {
     const int stage = g % kNS, tb = g & 1;
-    // ---- main: kTJ x NCOL running products over the chunk's SNPs
-    {
-      const unsigned char* st = raw + stage * Cfg::STAGE_BYTES;
-      const double* T = Tbuf + tb * (Cfg::T_BYTES / 8) + kidx * Cfg::TROW;
-      for (int s = 0; s < cnt; ++s) {
-        const double2* gp2 = reinterpret_cast<const double2*>(st + s * Cfg::SLOT_BYTES) + jg * (kTJ * 3 / 2);
-        double gv[kTJ * 3];
-#pragma unroll
-        for (int i = 0; i < kTJ * 3 / 2; ++i) {
-          const double2 v = gp2[i];
-          gv[2 * i] = v.x;
-          gv[2 * i + 1] = v.y;
-        }
-        const double2* t2 = reinterpret_cast<const double2*>(T + s * 32 * Cfg::TROW);
-#pragma unroll
-        for (int c2 = 0; c2 < Cfg::NCOL / 2; ++c2) {
-          const double2 u0 = t2[3 * c2], u1 = t2[3 * c2 + 1], u2 = t2[3 * c2 + 2];
-#pragma unroll
-          for (int jj = 0; jj < kTJ; ++jj) {
-            const double da = fma(gv[jj * 3 + 2], u1.x, fma(gv[jj * 3 + 1], u0.y, gv[jj * 3] * u0.x));
-            const double db = fma(gv[jj * 3 + 2], u2.y, fma(gv[jj * 3 + 1], u2.x, gv[jj * 3] * u1.y));
-            acc[jj][2 * c2] *= da;
-            acc[jj][2 * c2 + 1] *= db;
-          }
-        }
-      }
+    if (flags & 4) {
+      main_affine(cnt, stage, meta[stage].n0);
+      pending = (cnt >= 16) ? (cnt & 15) : pending + cnt;
+    } else {
+      main_general(cnt, stage, tb);
+      pending += cnt;
     }
     // ---- look ahead: T of the next chunk (possibly of the next item)
     const uint32_t g1 = g + 1;
     const int nstage = g1 % kNS;
     mbar_wait(smem_u32(&full[nstage]), (g1 / kNS) & 1);
-    const int ncnt = meta[nstage].cnt, nflags = meta[nstage].flags, nchunk = meta[nstage].chunk;
-    if (nflags & 1) compute_T(ncnt, nstage, g1 & 1);
-    if (flags & 2)
+    const int ncnt = meta[nstage].cnt, nflags = meta[nstage].flags;
+    if ((nflags & 5) == 1) compute_T(ncnt, nstage, g1 & 1);
+    if (flags & 2) {
       epilogue(&meta[stage]);
-    else if ((chunk % kRS) == kRS - 1)
+      pending = 0;
+    } else if (pending >= kRenormAfter) {
       renorm_all();
+      pending = 0;
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&empty[stage]));  // this warp is done with ring stage `stage`
     consumer_bar();
     if (!(nflags & 1)) break;
     cnt = ncnt;
     flags = nflags;
-    chunk = nchunk;
   }
 }
 
