@@ -1,0 +1,157 @@
+"""CPU tests of the host-side logic: the C-ABI library loads and exports every symbol
+include/cramore_cuda.h declares, the engine refuses to run without a GPU (no CPU fallback), the
+host decision/row code matches the oracle, barcode sharding and the world_size-2 gather over gloo."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = []
+    for fn in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if fn.endswith(".h"):
+            src = open(os.path.join(ROOT, "include", fn)).read()
+            src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+            names += re.findall(r"\b(ccu_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_abi_exports_every_declared_symbol(built):
+    from cramore_b200 import ABI_SYMBOLS, load_library
+    lib = load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "libcramore_cuda.so does not export %s" % name
+    assert sorted(ABI_SYMBOLS) == declared, "engine.py ABI_SYMBOLS out of sync with include/*.h"
+
+
+def test_no_cpu_fallback(built):
+    """Without an sm_100 device ccu_create must fail loudly and the product never touches oracle/."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cramore_b200 import DemuxEngine, EngineError
+    with pytest.raises(EngineError) as ei:
+        DemuxEngine(0)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+    pkg = os.path.join(ROOT, "cramore_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in txt and "liboracle" not in txt, "%s references the oracle" % f
+
+
+def test_host_classify_and_row_match_oracle(built):
+    from cramore_b200 import RESULT_DTYPE, best_header, best_row, classify
+    from oracle import pyoracle
+    rng = np.random.default_rng(3)
+    alphas = [0.0, 0.25, 0.5]
+    res = np.zeros(200, RESULT_DTYPE)
+    res["sBest"], res["sNext"] = 1, 2
+    res["dBest1"], res["dBest2"], res["dBestA"] = 0, 3, rng.integers(1, 3, 200)
+    res["dNext1"], res["dNext2"], res["dNextA"] = 3, 0, rng.integers(1, 3, 200)
+    res["sngBestLLK"] = -rng.uniform(10, 30, 200)
+    res["sngNextLLK"] = res["sngBestLLK"] - rng.uniform(0, 5, 200)
+    res["dblBestLLK"] = res["sngBestLLK"] + rng.uniform(-5, 5, 200)
+    res["dblNextLLK"] = res["dblBestLLK"] - rng.uniform(0, 5, 200)
+    res["sngLLK"] = res["sngBestLLK"] + 0.1
+    res["sumLLK"] = np.maximum(res["sngLLK"], res["dblBestLLK"]) + 0.2
+    mine = classify(res, 4, alphas, 0.5)
+    theirs = pyoracle.demux_classify(res.view(pyoracle.DEMUX_RESULT_DTYPE), 4, alphas, 0.5)
+    for f in mine.dtype.names:
+        if f != "_pad":
+            assert np.array_equal(mine[f], theirs[f]), f
+    assert set(np.unique(mine["type"])) == {0, 1, 2}
+    ids = ["S0", "S1", "S2", "S3"]
+    for i in range(0, 200, 17):
+        a = best_row(i, "BC%d-1" % i, 12, 15, res[i], 4, alphas, 0.5, ids)
+        b = pyoracle.demux_best_row(i, "BC%d-1" % i, 12, 15, res[i:i + 1].view(pyoracle.DEMUX_RESULT_DTYPE)[0], 4,
+                                    alphas, 0.5, ids)
+        assert a == b
+    # cmd_cram_demuxlet.cpp:629
+    assert best_header() == ("INT_ID\tBARCODE\tNUM.SNPS\tNUM.READS\tDROPLET.TYPE\tBEST.GUESS\tBEST.LLK\tNEXT.GUESS\t"
+                             "NEXT.LLK\tDIFF.LLK.BEST.NEXT\tBEST.POSTERIOR\tSNG.POSTERIOR\tSNG.BEST.GUESS\t"
+                             "SNG.BEST.LLK\tSNG.NEXT.GUESS\tSNG.NEXT.LLK\tSNG.ONLY.POSTERIOR\tDBL.BEST.GUESS\t"
+                             "DBL.BEST.LLK\tDIFF.LLK.SNG.DBL\n")
+
+
+def test_balanced_ranges_and_slices():
+    from cramore_b200.shard import balanced_ranges, slice_csr
+    from cramore_b200.synth import make_dataset
+    d = make_dataset("C1", nbcs=301, nsnps=500)
+    for world in (1, 2, 3, 8):
+        rs = balanced_ranges(d["cell_ptr"], world)
+        assert rs[0][0] == 0 and rs[-1][1] == 301 and all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+        nnz = [int(d["cell_ptr"][e] - d["cell_ptr"][b]) for b, e in rs]
+        assert max(nnz) - min(nnz) <= 2 * int(np.diff(d["cell_ptr"]).max())
+        tot_reads = 0
+        for b, e in rs:
+            cp, si, rp, al, bq = slice_csr(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], b, e)
+            assert cp[0] == 0 and rp[0] == 0 and len(si) == cp[-1] and len(al) == rp[-1] == len(bq)
+            tot_reads += len(al)
+        assert tot_reads == len(d["al"])
+    assert balanced_ranges(np.zeros(1, np.int64), 4) == [(0, 0)] * 4  # empty store
+
+
+def test_synth_is_deterministic_and_hex_ordered():
+    from cramore_b200.synth import _hex_order_key, make_dataset
+    a = make_dataset("C1", nbcs=50, nsnps=300)
+    b = make_dataset("C1", nbcs=50, nsnps=300)
+    for k in ("gp", "cell_ptr", "snp_idx", "read_ptr", "al", "bq"):
+        assert np.array_equal(a[k], b[k])
+    assert np.all(np.diff(a["cell_ptr"]) >= 0) and np.all(np.diff(a["read_ptr"]) >= 1)
+    for c in range(50):  # SNP ids ascend inside a droplet (std::map order, sc_drop_seq.h:165)
+        s = a["snp_idx"][a["cell_ptr"][c]:a["cell_ptr"][c + 1]]
+        assert np.all(np.diff(s) > 0)
+    cnt = np.asarray([9, 10, 15, 16, 255, 256, 4095, 4096])
+    left, nd = _hex_order_key(cnt)
+    order = np.lexsort((nd, left))
+    assert [format(int(x), "x") for x in cnt[order]] == sorted(format(int(x), "x") for x in cnt)
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from cramore_b200.shard import score_sharded
+from cramore_b200.synth import make_dataset
+dist.init_process_group("gloo")
+d = make_dataset("C1", nbcs=97, nsnps=400)
+DT = np.dtype([("cell", "<i8"), ("nent", "<i4"), ("nread", "<i4"), ("x", "<f8")])
+calls = []
+def fake_score(cp, si, rp, al, bq):   # stand-in for DemuxEngine.score on a CPU box: per-droplet digests
+    calls.append(len(cp) - 1)
+    out = np.zeros(len(cp) - 1, DT)
+    out["nent"] = np.diff(cp)
+    out["nread"] = rp[cp[1:]] - rp[cp[:-1]]
+    out["x"] = [float(np.sum(si[cp[i]:cp[i + 1]].astype(np.float64))) for i in range(len(cp) - 1)]
+    return out
+full = score_sharded(fake_score, d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"])
+want = fake_score(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"])
+assert len(full) == 97 and np.array_equal(full, want), "gathered shards differ from the single-process result"
+assert 0 < calls[0] < 97
+dist.barrier()
+dist.destroy_process_group()
+print("rank", dist.get_rank() if dist.is_initialized() else os.environ["RANK"], "ok")
+"""
+
+
+def test_world_size_2_gloo_shard_and_gather(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29713", str(script)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
