@@ -76,7 +76,7 @@ struct ccu_handle {
   int64_t nbcs = -1, nnz = 0, nreads = 0;
   bool ran = false;
   DevBuf d_cell_ptr, d_snp_idx, d_read_ptr, d_al, d_bq;
-  DevBuf d_tiles, d_eclass, d_vent, d_vsnp, d_vcnt, d_sng, d_fmat, d_pm, d_pe, d_partials, d_results, d_dbg, d_sink;
+  DevBuf d_tiles, d_eclass, d_vent, d_vsnp, d_vcnt, d_sng, d_fmat, d_pm, d_pe, d_maxbq, d_partials, d_results, d_dbg, d_sink;
 };
 
 namespace {
@@ -133,6 +133,7 @@ ccu::DemuxDev dev_view(const ccu_handle* h) {
   d.fmat = h->d_fmat.as<double>();
   d.pm = h->d_pm.as<double>();
   d.pe = h->d_pe.as<int32_t>();
+  d.maxbq = h->d_maxbq.as<int32_t>();
   d.partials = h->d_partials.as<ccu::ItemPartial>();
   d.results = h->d_results.as<ccu_demux_result>();
   return d;
@@ -200,7 +201,7 @@ int ccu_destroy(ccu_handle* h) {
   cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->d_alpha, &h->d_ptab, &h->d_half, &h->d_phred, &h->d_gpf, &h->d_err, &h->d_hasgp,
                     &h->d_avg, &h->d_G, &h->d_cell_ptr, &h->d_snp_idx, &h->d_read_ptr, &h->d_al, &h->d_bq,
-                    &h->d_tiles, &h->d_eclass, &h->d_vent, &h->d_vsnp, &h->d_vcnt, &h->d_sng, &h->d_fmat, &h->d_pm, &h->d_pe, &h->d_partials, &h->d_results, &h->d_dbg,
+                    &h->d_tiles, &h->d_eclass, &h->d_vent, &h->d_vsnp, &h->d_vcnt, &h->d_sng, &h->d_fmat, &h->d_pm, &h->d_pe, &h->d_maxbq, &h->d_partials, &h->d_results, &h->d_dbg,
                     &h->d_sink};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < EV_COUNT; ++i)
@@ -334,7 +335,8 @@ int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const
   CCU_CUDA(h, h->d_fmat.reserve((size_t)nnz * h->nvp * sizeof(double) + 16));
   CCU_CUDA(h, h->d_pm.reserve((size_t)nbcs * h->nvp * sizeof(double) + 16));
   CCU_CUDA(h, h->d_pe.reserve((size_t)nbcs * h->nvp * sizeof(int32_t) + 16));
-  CCU_CUDA(h, h->d_partials.reserve((size_t)nbcs * plan.items_per_cell * sizeof(ccu::ItemPartial) + 16));
+  CCU_CUDA(h, h->d_maxbq.reserve(16));
+  CCU_CUDA(h, h->d_partials.reserve((size_t)nbcs * plan.items_per_cell * ccu::kScoreWarps * sizeof(ccu::ItemPartial) + 16));
   CCU_CUDA(h, h->d_results.reserve(nbcs * sizeof(ccu_demux_result) + 16));
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_X0], h->stream));
   CCU_CUDA(h, cudaMemcpyAsync(h->d_cell_ptr.p, cell_ptr, (nbcs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,

@@ -21,7 +21,9 @@ struct Cand {
   int32_t pos;  // -1 = empty
 };
 
-// Partial reduction of one scoring work item (barcode x pair tile x alpha chunk).
+constexpr int kScoreWarps = kScoreThreads / 32;  // partial records per work item (one per consumer warp)
+
+// Partial reduction of one consumer warp over one scoring work item (barcode x pair tile x alpha chunk).
 struct ItemPartial {
   double lse_a;    // sum over the item's doublet terms of w * m * 2^(e - lse_e), w per :812-817
   int32_t lse_e;   // INT_MIN/2 when the item has no term
@@ -62,7 +64,8 @@ struct DemuxDev {
                            //       likelihoods f = (sum_l g[l]*pG[0][l][0]) / (sum_l g[l])
   double* pm;              // [nbcs][nvp] mantissa of prod over affine entries of sum_l g[l]
   int32_t* pe;             // [nbcs][nvp] its binary exponent
-  ItemPartial* partials;   // [nbcs * items_per_cell]
+  int32_t* maxbq;          // [1] largest base quality among informative reads (set by K1)
+  ItemPartial* partials;   // [nbcs * items_per_cell * kScoreWarps]
   ccu_demux_result* results;  // [nbcs]
 };
 

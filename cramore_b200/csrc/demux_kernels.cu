@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kTileWarps * 32)
     demux_tile_kernel(int64_t nnz, const int64_t* __restrict__ read_ptr, const uint8_t* __restrict__ al,
                       const uint8_t* __restrict__ bq, int nA, const double* __restrict__ ptab,
                       const double* __restrict__ phred, double* __restrict__ tiles,
-                      uint8_t* __restrict__ eclass) {
+                      uint8_t* __restrict__ eclass, int32_t* __restrict__ maxbq) {
   constexpr int EPW = 32 / GL;  // entries per warp per pass
   __shared__ double s_err[256];
   __shared__ double s_mat[256];
@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(kTileWarps * 32)
     omp[t] = has_alpha ? ptab[nA * 9 + n * 9 + t] : 0.0;
   }
   const int rowlen = nA * kTileStride;
+  int wqmax = 0;  // largest base quality of an informative read seen by this thread
 
   const int64_t warps_total = (int64_t)gridDim.x * kTileWarps;
   for (int64_t e0 = ((int64_t)blockIdx.x * kTileWarps + warp) * EPW; e0 < nnz; e0 += warps_total * EPW) {
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(kTileWarps * 32)
 #pragma unroll
     for (int t = 0; t < 9; ++t) v[t] = 1.0;  // :657
     int nuse = 0;  // informative reads of this entry
+    int qmax = 0;
 
     for (int i = 0; i < maxcnt; ++i) {
       const bool act = i < cnt;
@@ -246,6 +248,7 @@ __global__ void __launch_bounds__(kTileWarps * 32)
       const int q = act ? bq[r0 + i] : 0;
       const bool use = (a != 2);  // :664
       nuse += use ? 1 : 0;
+      qmax = use ? max(qmax, q) : qmax;
       double mx = 0.0;
       if (use && has_alpha) {
         const double pR = (a == 0) ? s_mat[q] : s_err[q] / 3.0;  // :666
@@ -283,6 +286,7 @@ __global__ void __launch_bounds__(kTileWarps * 32)
     // With at most one informative read the tile is an affine function of the allele fraction
     // p = (1-alpha)*l/2 + alpha*m/2, i.e. pG[n][l][m] = (1-alpha)*pG[0][l][.] + alpha*pG[0][m][.]
     if (valid && n == 0) eclass[e] = (nuse > 1) ? 1 : 0;
+    wqmax = max(wqmax, qmax);
     __syncwarp();
     int64_t nvalid = nnz - e0;
     if (nvalid > EPW) nvalid = EPW;
@@ -291,9 +295,14 @@ __global__ void __launch_bounds__(kTileWarps * 32)
     for (int i = lane; i < ndbl; i += 32) dst[i] = s_out[warp][i];
     __syncwarp();
   }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) wqmax = max(wqmax, __shfl_xor_sync(0xffffffffu, wqmax, d));
+  if (lane == 0 && wqmax > 0) atomicMax(maxbq, wqmax);  // bounds the smallest single-read factor for K2
 }
 
 cudaError_t launch_tile(const DemuxDev& d, cudaStream_t st) {
+  cudaError_t e0 = cudaMemsetAsync(d.maxbq, 0, sizeof(int32_t), st);
+  if (e0 != cudaSuccess) return e0;
   if (d.nnz == 0) return cudaSuccess;
   int gl = 2;
   while (gl < d.nA) gl <<= 1;
@@ -302,7 +311,7 @@ cudaError_t launch_tile(const DemuxDev& d, cudaStream_t st) {
   if (blocks > 148 * 16) blocks = 148 * 16;
 #define CCU_TILE(GL)                                                                              \
   demux_tile_kernel<GL><<<(unsigned)blocks, kTileWarps * 32, 0, st>>>(d.nnz, d.read_ptr, d.al, d.bq, \
-                                                                       d.nA, d.ptab, d.phred, d.tiles, d.eclass)
+                                                                       d.nA, d.ptab, d.phred, d.tiles, d.eclass, d.maxbq)
   switch (gl) {
     case 2: CCU_TILE(2); break;
     case 4: CCU_TILE(4); break;
@@ -475,9 +484,9 @@ constexpr int kTJ = 2;                              // samples j per thread
 constexpr int kConsumers = kScoreThreads;           // 16 consumer warps
 constexpr int kScoreBlock = kScoreThreads + 128;    // + the producer warpgroup (1 working warp)
 // Register budget: the kernel launches with 96 registers/thread (65536 / 640 rounded down to the
-// allocation unit); the producer warpgroup shrinks to 24 and the four consumer warpgroups grow
-// to 112 out of the CTA's own pool (16*32*112 + 4*32*24 = 60416 <= 640*96 = 61440).
-constexpr int kRegsProducer = 24;
+// allocation unit); the producer warpgroup shrinks to 32 and the four consumer warpgroups grow
+// to 112 out of the CTA's own pool (16*32*112 + 4*32*32 = 61440 = 640*96).
+constexpr int kRegsProducer = 32;
 constexpr int kRegsConsumer = 112;
 constexpr int kRenormAfter = 14;  // renormalise once this many SNPs are pending (factors >= ~2^-34:
                                   // at most 13 + 16 SNPs ever accumulate between renormalisations)
@@ -556,7 +565,6 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* raw = smem;
   double* Tbuf = reinterpret_cast<double*>(smem + Cfg::OFF_T);
-  WarpRed* red = reinterpret_cast<WarpRed*>(smem + Cfg::OFF_RED);
   ChunkMeta* meta = reinterpret_cast<ChunkMeta*>(smem + Cfg::OFF_META);
   double* s_alpha = reinterpret_cast<double*>(smem + Cfg::OFF_ALPHA);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -714,6 +722,12 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
 #pragma unroll
       for (int cc = 0; cc < Cfg::NCOL; ++cc) renorm(acc[jj][cc], aex[jj][cc]);
   };
+  // Underflow budget (binary orders of magnitude a running product may still lose before it must
+  // be renormalised).  A general factor is >= ~1e-10 (the +1e-10 floor of :704-725) = 34 bits; an
+  // affine factor is >= err(maxbq)/3, i.e. abits = ceil(0.3322*maxbq + 1.585) + 1, at most 34.
+  constexpr int kBudget = 960, kGenBits = 34;
+  const int abits = min(kGenBits, (int)(0.33220 * (double)d.maxbq[0] + 3.585));
+  int budget = kBudget;
 
   // ---- general chunk: kTJ x NCOL running products over the chunk's SNPs through T
   auto main_general = [&](int cnt, int stage, int tb) {
@@ -752,57 +766,74 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
     double al[AC];
 #pragma unroll
     for (int a = 0; a < AC; ++a) al[a] = s_alpha[n0 + a];
+    int s = 0;
+    while (s < cnt) {
+      if (budget < abits) {
+        renorm_all();
+        budget = kBudget;
+      }
+      const int run = min(cnt - s, budget / abits);  // SNPs that fit into the budget
+      budget -= run * abits;
+      const int s_end = s + run;
 #pragma unroll 2
-    for (int s = 0; s < cnt; ++s) {
-      const double2 fj = *reinterpret_cast<const double2*>(fj_base + s * 32);
-      double fk[TK];
-      if constexpr (TK == 1) {
-        fk[0] = fk_base[s * 32];
-      } else {
+      for (; s < s_end; ++s) {
+        const double2 fj = *reinterpret_cast<const double2*>(fj_base + s * 32);
+        double fk[TK];
+        if constexpr (TK == 1) {
+          fk[0] = fk_base[s * 32];
+        } else {
 #pragma unroll
-        for (int kk = 0; kk < TK; kk += 2) {
-          const double2 v = *reinterpret_cast<const double2*>(fk_base + s * 32 + kk);
-          fk[kk] = v.x;
-          fk[kk + 1] = v.y;
+          for (int kk = 0; kk < TK; kk += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(fk_base + s * 32 + kk);
+            fk[kk] = v.x;
+            fk[kk + 1] = v.y;
+          }
+        }
+#pragma unroll
+        for (int kk = 0; kk < TK; ++kk) {
+          const double d0 = fk[kk] - fj.x, d1 = fk[kk] - fj.y;
+#pragma unroll
+          for (int a = 0; a < AC; ++a) {
+            acc[0][kk * AC + a] *= fma(al[a], d0, fj.x);
+            acc[1][kk * AC + a] *= fma(al[a], d1, fj.y);
+          }
         }
       }
-#pragma unroll
-      for (int kk = 0; kk < TK; ++kk) {
-        const double d0 = fk[kk] - fj.x, d1 = fk[kk] - fj.y;
-#pragma unroll
-        for (int a = 0; a < AC; ++a) {
-          acc[0][kk * AC + a] *= fma(al[a], d0, fj.x);
-          acc[1][kk * AC + a] *= fma(al[a], d1, fj.y);
-        }
-      }
-      if ((s & 15) == 15) renorm_all();
     }
   };
 
-  // item epilogue: products -> partial log-sum-exp + top-2 candidates for this item
-  auto epilogue = [&](const ChunkMeta* mt) {
-    renorm_all();
-    const int j0 = mt->j0, k0 = mt->k0, n0 = mt->n0;
-    const int64_t cell = mt->cell;
-    const int64_t item = mt->item;
+  // ---- item epilogue: this warp's products -> log-sum-exp partial + top-2 candidates.  Each
+  // consumer warp writes its own record (K3 merges them), so no cross-warp synchronisation.
+  auto epilogue = [&](int cell32, int j0, int k0, int n0, int64_t item) {
+    const int64_t cell = cell32;
     // per-droplet constants of the affine entries: prod s_j and prod s_k
-    double pmj[kTJ], pmk[TK];
-    int pej[kTJ], pek[TK];
+    double pjk[kTJ][TK];
+    int ejk[kTJ][TK];
+    {
+      double pmj[kTJ], pmk[TK];
+      int pej[kTJ], pek[TK];
 #pragma unroll
-    for (int jj = 0; jj < kTJ; ++jj) {
-      const int j = j0 + jg * kTJ + jj;
-      pmj[jj] = d.pm[cell * d.nvp + j];
-      pej[jj] = d.pe[cell * d.nvp + j];
-    }
+      for (int jj = 0; jj < kTJ; ++jj) {
+        const int j = j0 + jg * kTJ + jj;
+        pmj[jj] = d.pm[cell * d.nvp + j];
+        pej[jj] = d.pe[cell * d.nvp + j];
+      }
 #pragma unroll
-    for (int kk = 0; kk < TK; ++kk) {
-      const int k = min(k0 + kidx * TK + kk, d.nvp - 1);
-      pmk[kk] = d.pm[cell * d.nvp + k];
-      pek[kk] = d.pe[cell * d.nvp + k];
+      for (int kk = 0; kk < TK; ++kk) {
+        const int k = min(k0 + kidx * TK + kk, d.nvp - 1);
+        pmk[kk] = d.pm[cell * d.nvp + k];
+        pek[kk] = d.pe[cell * d.nvp + k];
+      }
+#pragma unroll
+      for (int jj = 0; jj < kTJ; ++jj)
+#pragma unroll
+        for (int kk = 0; kk < TK; ++kk) {
+          pjk[jj][kk] = pmj[jj] * pmk[kk];  // in [1,4) or 0
+          ejk[jj][kk] = pej[jj] + pek[kk];
+        }
     }
-    double la = 0.0;
-    int le = kLseEmpty;
-    Cand b1 = cand_empty(), b2 = cand_empty();
+    // pass 1: final (mantissa, exponent) of every product; largest exponent among the doublet terms
+    int emax = kLseEmpty;
     const bool want_dbg = (dbg != nullptr) && cell >= dbg_c0 && cell < dbg_c1;
 #pragma unroll
     for (int jj = 0; jj < kTJ; ++jj) {
@@ -811,24 +842,54 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
       for (int cc = 0; cc < Cfg::NCOL; ++cc) {
         const int k = k0 + kidx * TK + cc / AC;
         const int n = n0 + cc % AC;
-        if (j < d.nv && k < d.nv && n < d.nA) {
-          double m = acc[jj][cc] * (pmj[jj] * pmk[cc / AC]);
-          int e = aex[jj][cc] + pej[jj] + pek[cc / AC];
-          renorm(m, e);
-          if (want_dbg) dbg[(((cell - dbg_c0) * d.nv + j) * d.nv + k) * d.nA + n] = make_double2(m, (double)e);
-          if (j != k && m > 0.0) {
-            // :812-817  alpha == 0.5 is counted once (k <= j) with twice the prior
-            const double w = ((half_mask >> n) & 1u) ? ((k < j) ? 2.0 : 0.0) : 1.0;
-            lse_add(la, le, w * m, e);
-            Cand x;
-            x.m = m;
-            x.e = e;
-            x.pos = (j * d.nv + k) * d.nA + n;
-            cand_insert(b1, b2, x);
-          }
+        double m = acc[jj][cc] * pjk[jj][cc / AC];
+        int e = aex[jj][cc] + ejk[jj][cc / AC];
+        renorm(m, e);
+        const bool inside = (j < d.nv) && (k < d.nv) && (n < d.nA);
+        if (want_dbg && inside) dbg[(((cell - dbg_c0) * d.nv + j) * d.nv + k) * d.nA + n] = make_double2(m, (double)e);
+        if (!inside || j == k || !(m > 0.0)) {
+          m = 0.0;
+          e = kLseEmpty;
         }
+        acc[jj][cc] = m;
+        aex[jj][cc] = e;
+        emax = max(emax, e);
       }
     }
+    // pass 2: sum of w * m * 2^(e - emax) and the thread's top-2 (scan order = increasing pos)
+    double la = 0.0;
+    double bm1 = 0.0, bm2 = 0.0;
+    int be1 = INT_MIN, be2 = INT_MIN, bp1 = -1, bp2 = -1;
+#pragma unroll
+    for (int jj = 0; jj < kTJ; ++jj) {
+      const int j = j0 + jg * kTJ + jj;
+#pragma unroll
+      for (int cc = 0; cc < Cfg::NCOL; ++cc) {
+        const int k = k0 + kidx * TK + cc / AC;
+        const int n = n0 + cc % AC;
+        const double m = acc[jj][cc];
+        const int e = aex[jj][cc];
+        // :812-817  alpha == 0.5 is counted once (k <= j) with twice the prior
+        const double w = ((half_mask >> n) & 1u) ? ((k < j) ? 2.0 : 0.0) : 1.0;
+        la = fma(w * m, pow2_nonpos(e - emax), la);
+        const bool valid = m > 0.0;
+        const bool gt1 = valid && ((e > be1) || (e == be1 && m > bm1));
+        const bool gt2 = valid && ((e > be2) || (e == be2 && m > bm2));
+        const int pos = (j * d.nv + k) * d.nA + n;
+        // second = gt1 ? old first : (gt2 ? x : second)
+        bm2 = gt1 ? bm1 : (gt2 ? m : bm2);
+        be2 = gt1 ? be1 : (gt2 ? e : be2);
+        bp2 = gt1 ? bp1 : (gt2 ? pos : bp2);
+        bm1 = gt1 ? m : bm1;
+        be1 = gt1 ? e : be1;
+        bp1 = gt1 ? pos : bp1;
+      }
+    }
+    int le = emax;
+    if (!(la > 0.0)) le = kLseEmpty;
+    Cand b1, b2;
+    b1.m = bm1; b1.e = be1; b1.pos = bp1;
+    b2.m = bm2; b2.e = be2; b2.pos = bp2;
 #pragma unroll
     for (int dd = 16; dd >= 1; dd >>= 1) {
       const double oa = __shfl_xor_sync(0xffffffffu, la, dd);
@@ -839,67 +900,46 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
       cand_insert(b1, b2, o2);
     }
     if (lane == 0) {
-      red[warp].lse_a = la;
-      red[warp].lse_e = le;
-      red[warp].b1 = b1;
-      red[warp].b2 = b2;
-    }
-    consumer_bar();
-    if (tid == 0) {
-      for (int w = 1; w < kConsumers / 32; ++w) {
-        lse_add(la, le, red[w].lse_a, red[w].lse_e);
-        cand_insert(b1, b2, red[w].b1);
-        cand_insert(b1, b2, red[w].b2);
-      }
       ItemPartial p;
       p.lse_a = la;
       p.lse_e = le;
       p._pad = 0;
       p.best = b1;
       p.next = b2;
-      d.partials[item] = p;
+      d.partials[item * kScoreWarps + warp] = p;
     }
     reset_acc();
+    budget = kBudget;
   };
 
-  // ---------------- chunk stream ----------------
+  // ---------------- chunk stream: every warp walks the ring on its own; the only block-level
+  // synchronisation is the one barrier between writing and reading T in a general chunk ----------------
   reset_acc();
-  mbar_wait(smem_u32(&full[0]), 0);
-  int cnt = meta[0].cnt;
-  int flags = meta[0].flags;
-  if (!(flags & 1)) return;
-  if (!(flags & 4)) compute_T(cnt, 0, 0);
-  consumer_bar();
-  int pending = 0;  // SNPs multiplied in since the last renormalisation
-
+  uint32_t gt = 0;  // general chunks seen so far (T double buffer)
   for (uint32_t g = 0;; ++g) {
-    const int stage = g % kNS, tb = g & 1;
+    const int stage = g % kNS;
+    mbar_wait(smem_u32(&full[stage]), (g / kNS) & 1);
+    const ChunkMeta* mt = &meta[stage];
+    const int cnt = mt->cnt, flags = mt->flags;
+    if (!(flags & 1)) break;
+    const int m_cell = mt->cell, m_j0 = mt->j0, m_k0 = mt->k0, m_n0 = mt->n0;
+    const int64_t m_item = mt->item;
     if (flags & 4) {
-      main_affine(cnt, stage, meta[stage].n0);
-      pending = (cnt >= 16) ? (cnt & 15) : pending + cnt;
+      main_affine(cnt, stage, m_n0);
     } else {
-      main_general(cnt, stage, tb);
-      pending += cnt;
+      if (budget < kGenBits * cnt) {
+        renorm_all();
+        budget = kBudget;
+      }
+      budget -= kGenBits * cnt;
+      compute_T(cnt, stage, gt & 1);
+      consumer_bar();
+      main_general(cnt, stage, gt & 1);
+      ++gt;
     }
-    // ---- look ahead: T of the next chunk (possibly of the next item)
-    const uint32_t g1 = g + 1;
-    const int nstage = g1 % kNS;
-    mbar_wait(smem_u32(&full[nstage]), (g1 / kNS) & 1);
-    const int ncnt = meta[nstage].cnt, nflags = meta[nstage].flags;
-    if ((nflags & 5) == 1) compute_T(ncnt, nstage, g1 & 1);
-    if (flags & 2) {
-      epilogue(&meta[stage]);
-      pending = 0;
-    } else if (pending >= kRenormAfter) {
-      renorm_all();
-      pending = 0;
-    }
+    if (flags & 2) epilogue(m_cell, m_j0, m_k0, m_n0, m_item);
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&empty[stage]));  // this warp is done with ring stage `stage`
-    consumer_bar();
-    if (!(nflags & 1)) break;
-    cnt = ncnt;
-    flags = nflags;
   }
 }
 
@@ -1033,8 +1073,8 @@ __global__ void __launch_bounds__(256)
   double la = 0.0;
   int le = kLseEmpty;
   Cand b1 = cand_empty(), b2 = cand_empty();
-  for (int i = lane; i < ipc; i += 32) {
-    const ItemPartial p = d.partials[c * ipc + i];
+  for (int i = lane; i < ipc * kScoreWarps; i += 32) {
+    const ItemPartial p = d.partials[c * ipc * kScoreWarps + i];
     lse_add(la, le, p.lse_a, p.lse_e);
     cand_insert(b1, b2, p.best);
     cand_insert(b1, b2, p.next);
