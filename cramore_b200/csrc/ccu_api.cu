@@ -76,7 +76,7 @@ struct ccu_handle {
   int64_t nbcs = -1, nnz = 0, nreads = 0;
   bool ran = false;
   DevBuf d_cell_ptr, d_snp_idx, d_read_ptr, d_al, d_bq;
-  DevBuf d_tiles, d_eclass, d_vent, d_vsnp, d_vcnt, d_sng, d_fmat, d_pm, d_pe, d_maxbq, d_partials, d_results, d_dbg, d_sink;
+  DevBuf d_tiles, d_vaff, d_eclass, d_vent, d_vsnp, d_vcnt, d_sng, d_fmat, d_pm, d_pe, d_maxbq, d_partials, d_results, d_dbg, d_sink;
 };
 
 namespace {
@@ -124,6 +124,7 @@ ccu::DemuxDev dev_view(const ccu_handle* h) {
   d.al = h->d_al.as<uint8_t>();
   d.bq = h->d_bq.as<uint8_t>();
   d.tiles = h->d_tiles.as<double>();
+  d.vaff = h->d_vaff.as<double>();
   d.vent = h->d_vent.as<int64_t>();
   d.vsnp = h->d_vsnp.as<int32_t>();
   d.eclass = h->d_eclass.as<uint8_t>();
@@ -201,7 +202,7 @@ int ccu_destroy(ccu_handle* h) {
   cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->d_alpha, &h->d_ptab, &h->d_half, &h->d_phred, &h->d_gpf, &h->d_err, &h->d_hasgp,
                     &h->d_avg, &h->d_G, &h->d_cell_ptr, &h->d_snp_idx, &h->d_read_ptr, &h->d_al, &h->d_bq,
-                    &h->d_tiles, &h->d_eclass, &h->d_vent, &h->d_vsnp, &h->d_vcnt, &h->d_sng, &h->d_fmat, &h->d_pm, &h->d_pe, &h->d_maxbq, &h->d_partials, &h->d_results, &h->d_dbg,
+                    &h->d_tiles, &h->d_vaff, &h->d_eclass, &h->d_vent, &h->d_vsnp, &h->d_vcnt, &h->d_sng, &h->d_fmat, &h->d_pm, &h->d_pe, &h->d_maxbq, &h->d_partials, &h->d_results, &h->d_dbg,
                     &h->d_sink};
   for (DevBuf* b : bufs) b->release();
   for (int i = 0; i < EV_COUNT; ++i)
@@ -332,6 +333,7 @@ int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const
   CCU_CUDA(h, h->d_vcnt.reserve(2 * nbcs * sizeof(int32_t) + 16));
   CCU_CUDA(h, h->d_sng.reserve((size_t)nbcs * h->nv * sizeof(double) + 16));
   CCU_CUDA(h, h->d_eclass.reserve(nnz + 16));
+  CCU_CUDA(h, h->d_vaff.reserve((size_t)nnz * 4 * sizeof(double) + 32));
   CCU_CUDA(h, h->d_fmat.reserve((size_t)nnz * h->nvp * sizeof(double) + 16));
   CCU_CUDA(h, h->d_pm.reserve((size_t)nbcs * h->nvp * sizeof(double) + 16));
   CCU_CUDA(h, h->d_pe.reserve((size_t)nbcs * h->nvp * sizeof(int32_t) + 16));
@@ -370,7 +372,7 @@ int ccu_demux_run(ccu_handle* h) {
   int grid = 0;
   cudaStream_t st = h->stream;
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_RUN0], st));
-  CCU_CUDA(h, ccu::launch_tile(d, st));
+  CCU_CUDA(h, ccu::launch_tile(d, false, st));
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_TILE], st));
   CCU_CUDA(h, ccu::launch_compact(d, st));
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_COMPACT], st));
@@ -380,7 +382,7 @@ int ccu_demux_run(ccu_handle* h) {
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_SCORE], st));
   CCU_CUDA(h, ccu::launch_finalize(d, plan, st));
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_FIN], st));
-  h->tm.launches = (h->nbcs > 0 ? 4 : 0) + (h->nnz > 0 ? 1 : 0);
+  h->tm.launches = (h->nbcs > 0 ? 4 : 0) + (h->nnz > 0 ? 2 : 0);
   h->tm.score_ctas = grid;
   h->tm.score_items = h->nbcs * plan.items_per_cell;
   h->ran = true;
@@ -433,6 +435,7 @@ int ccu_demux_get_tiles(ccu_handle* h, double* tiles) {
   CCU_CUDA(h, cudaSetDevice(h->device));
   const size_t rowp = (size_t)h->nA * ccu::kTileStride;
   std::vector<double> tmp((size_t)h->nnz * rowp);
+  CCU_CUDA(h, ccu::launch_tile(dev_view(h), true, h->stream));  // materialise the affine entries' tiles too
   CCU_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->nnz > 0) CCU_CUDA(h, cudaMemcpy(tmp.data(), h->d_tiles.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
   for (int64_t e = 0; e < h->nnz; ++e)

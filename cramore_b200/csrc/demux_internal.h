@@ -51,7 +51,9 @@ struct DemuxDev {
   const uint8_t* al;
   const uint8_t* bq;
   // intermediates
-  double* tiles;           // [nnz][nA][kTileStride]
+  double* tiles;           // [nnz][nA][kTileStride]; rows of general entries only, unless materialised
+                           //       for ccu_demux_get_tiles
+  double* vaff;            // [nnz][4] {pG[0][0][.], pG[0][1][.], pG[0][2][.], 0} of every entry
   uint8_t* eclass;         // [nnz] 0 = at most one informative read (tile affine in the allele
                            //       fraction), 1 = general
   int64_t* vent;           // [nnz] per-cell compacted entry ids with genotypes: general entries
@@ -84,7 +86,7 @@ ScorePlan make_score_plan(int nv, int nA, const double* alpha);
 cudaError_t launch_gp_prepare(const float* gp_f32, const double* snp_err, const uint8_t* has_gp,
                               int64_t nsnps, int nv, int nvp, double* avg_tmp, double* G,
                               cudaStream_t st);
-cudaError_t launch_tile(const DemuxDev& d, cudaStream_t st);
+cudaError_t launch_tile(const DemuxDev& d, bool all_entries, cudaStream_t st);
 cudaError_t launch_compact(const DemuxDev& d, cudaStream_t st);
 cudaError_t launch_sample(const DemuxDev& d, cudaStream_t st);
 // dbg != NULL: also dump (mantissa, exponent) of every computed llksAB entry of cells [dbg_c0, dbg_c1)

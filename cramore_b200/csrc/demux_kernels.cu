@@ -187,18 +187,80 @@ cudaError_t launch_gp_prepare(const float* gp_f32, const double* snp_err, const 
 // ------------------------------------------------------------------------------------------
 // K1: per-(cell,SNP) tile (cmd_cram_demuxlet.cpp:655-725)
 // ------------------------------------------------------------------------------------------
-// GL lanes cooperate on one entry, lane n owning the 9 values of alpha[n]; the running maximum
-// over all 9*nA values (:686-687, :711-712) is a group shuffle reduction.  The Phred tables sit
-// in shared memory.  Results are staged through shared memory so that each warp writes one
-// contiguous run of global memory.
+// K1a (thread per entry) scans the entry's reads and classifies it.  With at most one informative
+// read (allele code != 2) the tile is an affine function of the allele fraction
+// p = (1-alpha)*l/2 + alpha*m/2, i.e. pG[n][l][m] = (1-alpha)*v(l) + alpha*v(m) with
+// v(l) = pG[0][l][.], so only v is needed downstream: K1a computes it with the reference's own
+// operation order (the running maximum of :686-687 over all 9*nA values is attained at p = 0 or
+// p = 1, both of which are in the alpha[0] block) and stores it as vaff[e] = {v0, v1, v2, 0}.
+// Entries with two or more informative reads are left to K1b.
+__global__ void __launch_bounds__(256)
+    demux_entry_kernel(int64_t nnz, const int64_t* __restrict__ read_ptr, const uint8_t* __restrict__ al,
+                       const uint8_t* __restrict__ bq, const double* __restrict__ phred,
+                       double* __restrict__ vaff, uint8_t* __restrict__ eclass, int32_t* __restrict__ maxbq) {
+  const int lane = threadIdx.x & 31;
+  int qmax = 0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r0 = read_ptr[e], r1 = read_ptr[e + 1];
+    int nuse = 0, a1 = 2, q1 = 0;
+    for (int64_t r = r0; r < r1; ++r) {
+      const int a = al[r];
+      if (a != 2) {  // :664
+        const int q = bq[r];
+        if (nuse == 0) {
+          a1 = a;
+          q1 = q;
+        }
+        ++nuse;
+        qmax = max(qmax, q);
+      }
+    }
+    eclass[e] = (nuse > 1) ? 1 : 0;
+    if (nuse <= 1) {
+      double v0 = 1.0, v1 = 1.0, v2 = 1.0;  // :657
+      if (nuse == 1) {
+        const double er = phred[q1], mt = phred[256 + q1];
+        const double pR = (a1 == 0) ? mt : er / 3.0;  // :666
+        const double pA = (a1 == 1) ? mt : er / 3.0;  // :667
+        // :673 at alpha[0] = 0: p = 0.5*l, 1-p
+        v0 = __dmul_rn(v0, __dadd_rn(__dmul_rn(pR, 1.0), __dmul_rn(pA, 0.0)));  // :685
+        v1 = __dmul_rn(v1, __dadd_rn(__dmul_rn(pR, 0.5), __dmul_rn(pA, 0.5)));
+        v2 = __dmul_rn(v2, __dadd_rn(__dmul_rn(pR, 0.0), __dmul_rn(pA, 1.0)));
+        const double mx = fmax(v0, fmax(v1, v2));
+        v0 = v0 / mx;  // :696
+        v1 = v1 / mx;
+        v2 = v2 / mx;
+      }
+      v0 = __dadd_rn(v0, 1e-10);  // :704-725
+      v1 = __dadd_rn(v1, 1e-10);
+      v2 = __dadd_rn(v2, 1e-10);
+      const double mx = fmax(v0, fmax(v1, v2));
+      double4 o;
+      o.x = v0 / mx;
+      o.y = v1 / mx;
+      o.z = v2 / mx;
+      o.w = 0.0;
+      reinterpret_cast<double4*>(vaff)[e] = o;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) qmax = max(qmax, __shfl_xor_sync(0xffffffffu, qmax, d));
+  if (lane == 0 && qmax > 0) atomicMax(maxbq, qmax);  // bounds the smallest single-read factor for K2
+}
+
+// K1b: the full 9 x nAlpha tile.  GL lanes cooperate on one entry, lane n owning the 9 values of
+// alpha[n]; the running maximum over all 9*nA values (:686-687, :711-712) is a group shuffle
+// reduction.  The Phred tables sit in shared memory.  Rows are staged through shared memory so
+// that the warp writes each one as a contiguous run.  Only general entries are processed unless
+// `all_entries` is set (ccu_demux_get_tiles).
 constexpr int kTileWarps = 8;
 
 template <int GL>
 __global__ void __launch_bounds__(kTileWarps * 32)
     demux_tile_kernel(int64_t nnz, const int64_t* __restrict__ read_ptr, const uint8_t* __restrict__ al,
                       const uint8_t* __restrict__ bq, int nA, const double* __restrict__ ptab,
-                      const double* __restrict__ phred, double* __restrict__ tiles,
-                      uint8_t* __restrict__ eclass, int32_t* __restrict__ maxbq) {
+                      const double* __restrict__ phred, const uint8_t* __restrict__ eclass, int all_entries,
+                      double* __restrict__ tiles, double* __restrict__ vaff) {
   constexpr int EPW = 32 / GL;  // entries per warp per pass
   __shared__ double s_err[256];
   __shared__ double s_mat[256];
@@ -220,12 +282,12 @@ __global__ void __launch_bounds__(kTileWarps * 32)
     omp[t] = has_alpha ? ptab[nA * 9 + n * 9 + t] : 0.0;
   }
   const int rowlen = nA * kTileStride;
-  int wqmax = 0;  // largest base quality of an informative read seen by this thread
 
   const int64_t warps_total = (int64_t)gridDim.x * kTileWarps;
   for (int64_t e0 = ((int64_t)blockIdx.x * kTileWarps + warp) * EPW; e0 < nnz; e0 += warps_total * EPW) {
     const int64_t e = e0 + sub;
-    const bool valid = e < nnz;
+    const bool valid = (e < nnz) && (all_entries || eclass[e] != 0);
+    if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
     int64_t r0 = 0;
     int cnt = 0;
     if (valid) {
@@ -239,16 +301,12 @@ __global__ void __launch_bounds__(kTileWarps * 32)
     double v[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) v[t] = 1.0;  // :657
-    int nuse = 0;  // informative reads of this entry
-    int qmax = 0;
 
     for (int i = 0; i < maxcnt; ++i) {
       const bool act = i < cnt;
       const int a = act ? al[r0 + i] : 2;
       const int q = act ? bq[r0 + i] : 0;
       const bool use = (a != 2);  // :664
-      nuse += use ? 1 : 0;
-      qmax = use ? max(qmax, q) : qmax;
       double mx = 0.0;
       if (use && has_alpha) {
         const double pR = (a == 0) ? s_mat[q] : s_err[q] / 3.0;  // :666
@@ -282,36 +340,46 @@ __global__ void __launch_bounds__(kTileWarps * 32)
 #pragma unroll
       for (int t = 0; t < 9; ++t) o[t] = v[t] / mx;
       o[9] = 0.0;
+      if (valid && n == 0) {
+        double4 w;
+        w.x = o[0];
+        w.y = o[3];
+        w.z = o[6];
+        w.w = 0.0;
+        reinterpret_cast<double4*>(vaff)[e] = w;
+      }
     }
-    // With at most one informative read the tile is an affine function of the allele fraction
-    // p = (1-alpha)*l/2 + alpha*m/2, i.e. pG[n][l][m] = (1-alpha)*pG[0][l][.] + alpha*pG[0][m][.]
-    if (valid && n == 0) eclass[e] = (nuse > 1) ? 1 : 0;
-    wqmax = max(wqmax, qmax);
     __syncwarp();
-    int64_t nvalid = nnz - e0;
-    if (nvalid > EPW) nvalid = EPW;
-    const int ndbl = (int)nvalid * rowlen;
-    double* dst = tiles + e0 * rowlen;
-    for (int i = lane; i < ndbl; i += 32) dst[i] = s_out[warp][i];
+#pragma unroll
+    for (int sb = 0; sb < EPW; ++sb) {
+      if (__shfl_sync(0xffffffffu, (int)valid, sb * GL)) {
+        double* dst = tiles + (e0 + sb) * rowlen;
+        for (int i = lane; i < rowlen; i += 32) dst[i] = s_out[warp][sb * rowlen + i];
+      }
+    }
     __syncwarp();
   }
-#pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) wqmax = max(wqmax, __shfl_xor_sync(0xffffffffu, wqmax, d));
-  if (lane == 0 && wqmax > 0) atomicMax(maxbq, wqmax);  // bounds the smallest single-read factor for K2
 }
 
-cudaError_t launch_tile(const DemuxDev& d, cudaStream_t st) {
+cudaError_t launch_tile(const DemuxDev& d, bool all_entries, cudaStream_t st) {
   cudaError_t e0 = cudaMemsetAsync(d.maxbq, 0, sizeof(int32_t), st);
   if (e0 != cudaSuccess) return e0;
   if (d.nnz == 0) return cudaSuccess;
+  {
+    int64_t blocks = (d.nnz + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    demux_entry_kernel<<<(unsigned)blocks, 256, 0, st>>>(d.nnz, d.read_ptr, d.al, d.bq, d.phred, d.vaff, d.eclass,
+                                                         d.maxbq);
+  }
   int gl = 2;
   while (gl < d.nA) gl <<= 1;
   int64_t per_block = (int64_t)kTileWarps * (32 / gl);
   int64_t blocks = (d.nnz + per_block - 1) / per_block;
   if (blocks > 148 * 16) blocks = 148 * 16;
-#define CCU_TILE(GL)                                                                              \
-  demux_tile_kernel<GL><<<(unsigned)blocks, kTileWarps * 32, 0, st>>>(d.nnz, d.read_ptr, d.al, d.bq, \
-                                                                       d.nA, d.ptab, d.phred, d.tiles, d.eclass, d.maxbq)
+#define CCU_TILE(GL)                                                                                 \
+  demux_tile_kernel<GL><<<(unsigned)blocks, kTileWarps * 32, 0, st>>>(d.nnz, d.read_ptr, d.al, d.bq, d.nA, d.ptab, \
+                                                                       d.phred, d.eclass, all_entries ? 1 : 0,      \
+                                                                       d.tiles, d.vaff)
   switch (gl) {
     case 2: CCU_TILE(2); break;
     case 4: CCU_TILE(4); break;
@@ -394,7 +462,6 @@ __global__ void __launch_bounds__(256)
   const int j = tile * 32 + lane;
   const int64_t base = d.cell_ptr[c];
   const int ng = d.vcnt_g[c], na = d.vcnt_a[c];
-  const int64_t rowlen = (int64_t)d.nA * kTileStride;
   const int64_t grow = (int64_t)d.nvp * 3;
   double* fdst = d.fmat + base * d.nvp + (int64_t)tile * 32 * na + lane;
   double m = 1.0, pm = 1.0;
@@ -403,17 +470,19 @@ __global__ void __launch_bounds__(256)
 #pragma unroll 2
   for (int i = 0; i < cnt; ++i) {
     const int64_t e = d.vent[base + i];
-    const double* pg = d.tiles + e * rowlen;  // alpha index 0
+    // alpha[0] == 0 makes pG[0][l][m] independent of m (bitwise: the same p = 0.5*l), so the three
+    // values v(l) = pG[0][l][.] stand for the whole alpha[0] block
+    const double4 v = reinterpret_cast<const double4*>(d.vaff)[e];
     const double* g = d.G + (int64_t)d.vsnp[base + i] * grow;
     const double g00 = g[0], g01 = g[1], g02 = g[2];
-    const double t0 = fma(g02, pg[2], fma(g01, pg[1], g00 * pg[0]));
-    const double t1 = fma(g02, pg[5], fma(g01, pg[4], g00 * pg[3]));
-    const double t2 = fma(g02, pg[8], fma(g01, pg[7], g00 * pg[6]));
+    const double t0 = fma(g02, v.x, fma(g01, v.x, g00 * v.x));
+    const double t1 = fma(g02, v.y, fma(g01, v.y, g00 * v.y));
+    const double t2 = fma(g02, v.z, fma(g01, v.z, g00 * v.z));
     const double* gj = g + 3 * j;
     const double gj0 = gj[0], gj1 = gj[1], gj2 = gj[2];
     m *= fma(gj2, t2, fma(gj1, t1, gj0 * t0));
     if (i >= ng) {
-      const double F = fma(gj2, pg[6], fma(gj1, pg[3], gj0 * pg[0]));
+      const double F = fma(gj2, v.z, fma(gj1, v.y, gj0 * v.x));
       const double sj = (gj0 + gj1) + gj2;
       const bool live = (j < d.nv) && (sj > 0.0);
       fdst[(int64_t)(i - ng) * 32] = live ? F / sj : ((j < d.nv) ? 0.0 : 1.0);
@@ -488,8 +557,6 @@ constexpr int kScoreBlock = kScoreThreads + 128;    // + the producer warpgroup 
 // to 112 out of the CTA's own pool (16*32*112 + 4*32*32 = 61440 = 640*96).
 constexpr int kRegsProducer = 32;
 constexpr int kRegsConsumer = 112;
-constexpr int kRenormAfter = 14;  // renormalise once this many SNPs are pending (factors >= ~2^-34:
-                                  // at most 13 + 16 SNPs ever accumulate between renormalisations)
 static_assert(kScoreThreads == 512, "thread mapping below assumes 16 consumer warps");
 
 __device__ __forceinline__ void consumer_bar() {
