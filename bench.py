@@ -268,23 +268,56 @@ def main():
     res_check = np.array(out[:4])
 
     # ---- roofline of the dominant kernel (K2 scoring, FP64 pipe)
-    flops_launch = algorithmic_flops_per_entry(d["nv"], list(d["alphas"])) * nnz
+    nv, nA = d["nv"], len(d["alphas"])
+    flops_launch = algorithmic_flops_per_entry(nv, list(d["alphas"])) * nnz
     k2_avg = float(np.mean(k2_ms))
     achieved = flops_launch / (k2_avg * 1e-3) / 1e12
+    # FP64 instructions the kernel really issues: every ordered pair of the padded sample
+    # tiles; affine entries (<= 1 informative read) cost 1 DADD per (j,k) + 2 per (j,k,alpha), general
+    # entries 4 per (j,k,alpha) + 9 per (k,alpha) per j-tile for T
+    al_ne2 = (np.asarray(d["al"]) != 2).astype(np.int64)
+    csum = np.concatenate([[0], np.cumsum(al_ne2)])
+    neff = csum[np.asarray(d["read_ptr"][1:])] - csum[np.asarray(d["read_ptr"][:-1])]
+    n_gen = int((neff > 1).sum())
+    n_aff = nnz - n_gen
+    nvp = (nv + 31) // 32 * 32
+    nd = nA - 1
+    ac = min((10, 5, 2, 1), key=lambda a: ((nd + a - 1) // a * a, -a))
+    nd_pad = (nd + ac - 1) // ac * ac
+    nac = nd_pad // ac
+    instr_aff = nvp * nvp * (nac + 2 * nd_pad)
+    instr_gen = nvp * nvp * 4 * nd_pad + (nvp // 32) * nvp * nd_pad * 9
+    executed = 2.0 * (n_aff * instr_aff + n_gen * instr_gen)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k2_traffic.json")))
+        if d["name"] == "C2" and nbcs == 20000:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "fp64", "kernel": "demux_score_kernel (K2)", "achieved": achieved, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
+                "traffic_note": "dram__bytes_read+write of one K2 launch at this workload, ncu --set full capture "
+                                "summarised in profiles/r01_k2_score_ncu_full.csv (bytes; the kernel is FP64-pipe "
+                                "bound, HBM is at ~1% of peak)",
                 "peak_source": "DFMA microkernel measured in this run (MEASURED_PEAKS.json has no FP64 entry; "
                                "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
-                "algorithmic_flops_per_launch": flops_launch, "k2_ms_avg": k2_avg,
-                "k2_share_of_step": k2_avg * args.steps / dev_ms}
-    tile_bytes = 2 * int(d["read_ptr"][-1]) + 8 * nnz + 72 * len(d["alphas"]) * nnz
+                "note": "achieved = SURVEY 8(d) algorithmic flops (8 per needed LLK + 18*nv*nA per entry) / K2 event "
+                        "time. The affine fast path needs ~half of those instructions, so frac can exceed 1; "
+                        "executed_frac counts the FP64 instructions actually issued (x2 flops) and is the pipe "
+                        "utilisation ncu reports as sm__pipe_fp64_cycles_active",
+                "algorithmic_flops_per_launch": flops_launch, "executed_flops_per_launch": executed,
+                "executed_frac": executed / (k2_avg * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None,
+                "entries_affine": n_aff, "entries_general": n_gen,
+                "k2_ms_avg": k2_avg, "k2_share_of_step": k2_avg * args.steps / dev_ms}
+    tile_bytes = 2 * int(d["read_ptr"][-1]) + 8 * nnz + 33 * nnz + 80 * len(d["alphas"]) * n_gen  # reads + read_ptr + vaff/eclass + general tiles
     k1_avg = float(np.mean(k1_ms))
     hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         hbm_peak = 6650.0
-    roofline_k1 = {"bound": "hbm", "kernel": "demux_tile_kernel (K1)", "achieved": tile_bytes / (k1_avg * 1e-3) / 1e9,
+    roofline_k1 = {"bound": "hbm", "kernel": "demux_entry_kernel + demux_tile_kernel (K1)", "achieved": tile_bytes / (k1_avg * 1e-3) / 1e9,
                    "peak": hbm_peak, "unit": "GB/s", "frac": tile_bytes / (k1_avg * 1e-3) / 1e9 / hbm_peak,
                    "k1_ms_avg": k1_avg}
 
