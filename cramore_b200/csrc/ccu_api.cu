@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "ccu_handle.h"
 #include "cramore_cuda.h"
 #include "demux_internal.h"
 
@@ -19,69 +20,9 @@ namespace {
 
 std::string g_create_error;
 
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) {
-      e = cudaMalloc(&p, bytes);
-      want = bytes;
-    }
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-  template <typename T>
-  T* as() const {
-    return reinterpret_cast<T*>(p);
-  }
-};
-
-enum { EV_RUN0, EV_TILE, EV_COMPACT, EV_SNG, EV_SCORE, EV_FIN, EV_GP0, EV_GP1, EV_X0, EV_X1, EV_COUNT };
-
 }  // namespace
 
-struct ccu_handle {
-  int device = 0;
-  int num_sms = 0;
-  cudaStream_t own_stream = nullptr;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[EV_COUNT] = {};
-  std::string err;
-  ccu_timings tm = {};
-
-  // configuration
-  bool configured = false;
-  int nv = 0, nvp = 0, nA = 0;
-  double doublet_prior = 0.5;
-  std::vector<double> alpha;
-  DevBuf d_alpha, d_ptab, d_half, d_phred;
-
-  // genotypes
-  int64_t nsnps = -1;
-  bool has_gp_flags = false;
-  DevBuf d_gpf, d_err, d_hasgp, d_avg, d_G;
-
-  // droplets
-  int64_t nbcs = -1, nnz = 0, nreads = 0;
-  bool ran = false;
-  DevBuf d_cell_ptr, d_snp_idx, d_read_ptr, d_al, d_bq;
-  DevBuf d_tiles, d_vaff, d_eclass, d_vent, d_vsnp, d_vcnt, d_sng, d_fmat, d_pm, d_pe, d_maxbq, d_partials, d_results, d_dbg, d_sink;
-};
-
-namespace {
-
-int fail(ccu_handle* h, const char* fmt, ...) {
+int ccu_fail(ccu_handle* h, const char* fmt, ...) {
   char buf[1024];
   va_list ap;
   va_start(ap, fmt);
@@ -94,12 +35,10 @@ int fail(ccu_handle* h, const char* fmt, ...) {
   return 1;
 }
 
-#define CCU_CUDA(h, call)                                                                       \
-  do {                                                                                          \
-    cudaError_t e__ = (call);                                                                   \
-    if (e__ != cudaSuccess)                                                                     \
-      return fail(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
-  } while (0)
+namespace {
+
+#define fail ccu_fail
+#define ev_ms ccu_ev_ms
 
 ccu::DemuxDev dev_view(const ccu_handle* h) {
   ccu::DemuxDev d;
@@ -138,15 +77,6 @@ ccu::DemuxDev dev_view(const ccu_handle* h) {
   d.partials = h->d_partials.as<ccu::ItemPartial>();
   d.results = h->d_results.as<ccu_demux_result>();
   return d;
-}
-
-float ev_ms(ccu_handle* h, int a, int b) {
-  float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) != cudaSuccess) {
-    cudaGetLastError();
-    return 0.f;
-  }
-  return ms;
 }
 
 }  // namespace
@@ -205,6 +135,7 @@ int ccu_destroy(ccu_handle* h) {
                     &h->d_tiles, &h->d_vaff, &h->d_eclass, &h->d_vent, &h->d_vsnp, &h->d_vcnt, &h->d_sng, &h->d_fmat, &h->d_pm, &h->d_pe, &h->d_maxbq, &h->d_partials, &h->d_results, &h->d_dbg,
                     &h->d_sink};
   for (DevBuf* b : bufs) b->release();
+  ccu_fmx_release(h);
   for (int i = 0; i < EV_COUNT; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);

@@ -1,0 +1,439 @@
+// ccu_fmx_api.cu -- freemuxlet half of the C ABI (include/cramore_cuda.h): device memory, the
+// SNP-major index build (CUB radix sort, once per upload) and the EM driver around the kernels of
+// fmx_kernels.cu.  No CPU implementation exists behind any entry point.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <cub/device/device_radix_sort.cuh>
+#include <vector>
+
+#include "ccu_handle.h"
+#include "fmx_internal.h"
+
+struct FmxState {
+  bool configured = false, uploaded = false, have_stats = false, have_estep = false;
+  int32_t K = 0;
+  double doublet_prior = 0.5, geno_error = 0.0;
+  int64_t nbcs = 0, nsnps = 0, nnz = 0, nreads = 0;
+  int64_t cell_begin = 0, cell_end = 0, snp_begin = 0, snp_end = 0;
+  DevBuf cell_ptr, snp_idx, read_ptr, al, bq, af;
+  DevBuf gl, cnt, logdenom, csc_ptr, csc_cell, csc_gl, csc_cnt;
+  DevBuf assign, stats, cgp, llk, results, scratch;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  ccu_fmx_timings tm = {};
+  void release() {
+    DevBuf* all[] = {&cell_ptr, &snp_idx, &read_ptr, &al, &bq, &af, &gl, &cnt, &logdenom, &csc_ptr, &csc_cell,
+                     &csc_gl, &csc_cnt, &assign, &stats, &cgp, &llk, &results, &scratch};
+    for (DevBuf* b : all) b->release();
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+  }
+};
+
+void ccu_fmx_release(ccu_handle* h) {
+  if (h && h->fmx) {
+    h->fmx->release();
+    delete h->fmx;
+    h->fmx = nullptr;
+  }
+}
+
+namespace {
+
+ccu::FmxDev fmx_view(const ccu_handle* h) {
+  const FmxState* f = h->fmx;
+  ccu::FmxDev d;
+  memset(&d, 0, sizeof(d));
+  d.K = f->K;
+  d.doublet_prior = f->doublet_prior;
+  d.geno_error = f->geno_error;
+  d.nbcs = f->nbcs;
+  d.nsnps = f->nsnps;
+  d.nnz = f->nnz;
+  d.cell_ptr = f->cell_ptr.as<int64_t>();
+  d.snp_idx = f->snp_idx.as<int32_t>();
+  d.read_ptr = f->read_ptr.as<int64_t>();
+  d.al = f->al.as<uint8_t>();
+  d.bq = f->bq.as<uint8_t>();
+  d.af = f->af.as<double>();
+  d.phred = h->d_phred.as<double>();
+  d.gl = f->gl.as<double>();
+  d.cnt = f->cnt.as<int4>();
+  d.logdenom = f->logdenom.as<double>();
+  d.csc_ptr = f->csc_ptr.as<int64_t>();
+  d.csc_cell = f->csc_cell.as<int32_t>();
+  d.csc_gl = f->csc_gl.as<double>();
+  d.csc_cnt = f->csc_cnt.as<int4>();
+  d.assign = f->assign.as<int32_t>();
+  d.stats = f->stats.as<double>();
+  d.cgp = f->cgp.as<double>();
+  d.llk = f->llk.as<double>();
+  d.results = f->results.as<ccu_fmx_result>();
+  d.cell_begin = f->cell_begin;
+  d.cell_end = f->cell_end;
+  d.snp_begin = f->snp_begin;
+  d.snp_end = f->snp_end;
+  return d;
+}
+
+struct Timer {  // CUDA-event timer on the engine stream
+  ccu_handle* h;
+  float* dst;
+  Timer(ccu_handle* h_, float* dst_) : h(h_), dst(dst_) { cudaEventRecord(h->fmx->ev[0], h->stream); }
+  void stop_sync() {
+    cudaEventRecord(h->fmx->ev[1], h->stream);
+    cudaEventSynchronize(h->fmx->ev[1]);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->fmx->ev[0], h->fmx->ev[1]) == cudaSuccess) *dst = ms;
+  }
+};
+
+int need(ccu_handle* h, bool uploaded, const char* who) {
+  if (!h) return 1;
+  if (!h->fmx || !h->fmx->configured) return ccu_fail(h, "%s: call ccu_fmx_configure first", who);
+  if (uploaded && !h->fmx->uploaded) return ccu_fail(h, "%s: call ccu_fmx_upload first", who);
+  return 0;
+}
+
+int reserve_shard_buffers(ccu_handle* h) {
+  FmxState* f = h->fmx;
+  const int64_t ncell = f->cell_end - f->cell_begin;
+  const int64_t npairs = (int64_t)f->K * (f->K + 1) / 2;
+  CCU_CUDA(h, f->llk.reserve((size_t)ncell * npairs * sizeof(double) + 16));
+  CCU_CUDA(h, f->results.reserve((size_t)ncell * sizeof(ccu_fmx_result) + 16));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ccu_fmx_configure(ccu_handle* h, int32_t nclust, double doublet_prior, double geno_error) {
+  if (!h) return 1;
+  if (nclust < 2 || nclust > ccu::kFmxMaxClust)
+    return ccu_fail(h, "ccu_fmx_configure: --nsample %d outside [2,%d]", nclust, ccu::kFmxMaxClust);
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  if (!h->fmx) {
+    h->fmx = new FmxState();
+    cudaEventCreate(&h->fmx->ev[0]);
+    cudaEventCreate(&h->fmx->ev[1]);
+  }
+  FmxState* f = h->fmx;
+  f->K = nclust;
+  f->doublet_prior = doublet_prior;
+  f->geno_error = geno_error;
+  f->configured = true;
+  f->uploaded = f->have_stats = f->have_estep = false;
+  return 0;
+}
+
+int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* cell_ptr, const int32_t* snp_idx,
+                   const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq, const double* af) {
+  if (int rc = need(h, false, "ccu_fmx_upload")) return rc;
+  if (nbcs < 0 || nsnps < 0 || !cell_ptr || (nsnps > 0 && !af)) return ccu_fail(h, "ccu_fmx_upload: bad arguments");
+  if (cell_ptr[0] != 0) return ccu_fail(h, "ccu_fmx_upload: cell_ptr[0] must be 0");
+  const int64_t nnz = cell_ptr[nbcs];
+  if (nnz < 0 || nnz > 2147483647LL) return ccu_fail(h, "ccu_fmx_upload: entry count %lld out of range", (long long)nnz);
+  if (nnz > 0 && (!snp_idx || !read_ptr || read_ptr[0] != 0)) return ccu_fail(h, "ccu_fmx_upload: bad CSR arrays");
+  const int64_t nreads = nnz > 0 ? read_ptr[nnz] : 0;
+  if (nreads < 0 || (nreads > 0 && (!al || !bq))) return ccu_fail(h, "ccu_fmx_upload: bad read arrays");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  FmxState* f = h->fmx;
+  cudaStream_t st = h->stream;
+  f->nbcs = nbcs;
+  f->nsnps = nsnps;
+  f->nnz = nnz;
+  f->nreads = nreads;
+  f->cell_begin = 0;
+  f->cell_end = nbcs;
+  f->snp_begin = 0;
+  f->snp_end = nsnps;
+  f->uploaded = f->have_stats = f->have_estep = false;
+  CCU_CUDA(h, f->cell_ptr.reserve((nbcs + 1) * sizeof(int64_t)));
+  CCU_CUDA(h, f->snp_idx.reserve(nnz * sizeof(int32_t) + 16));
+  CCU_CUDA(h, f->read_ptr.reserve((nnz + 1) * sizeof(int64_t)));
+  CCU_CUDA(h, f->al.reserve(nreads + 16));
+  CCU_CUDA(h, f->bq.reserve(nreads + 16));
+  CCU_CUDA(h, f->af.reserve(nsnps * sizeof(double) + 16));
+  CCU_CUDA(h, f->gl.reserve((size_t)nnz * 9 * sizeof(double) + 16));
+  CCU_CUDA(h, f->cnt.reserve((size_t)nnz * sizeof(int4) + 16));
+  CCU_CUDA(h, f->logdenom.reserve((size_t)nnz * sizeof(double) + 16));
+  CCU_CUDA(h, f->csc_ptr.reserve((nsnps + 1) * sizeof(int64_t)));
+  CCU_CUDA(h, f->csc_cell.reserve((size_t)nnz * sizeof(int32_t) + 16));
+  CCU_CUDA(h, f->csc_gl.reserve((size_t)nnz * 9 * sizeof(double) + 16));
+  CCU_CUDA(h, f->csc_cnt.reserve((size_t)nnz * sizeof(int4) + 16));
+  CCU_CUDA(h, f->assign.reserve(nbcs * sizeof(int32_t) + 16));
+  CCU_CUDA(h, f->stats.reserve((size_t)f->K * nsnps * ccu::kStatStride * sizeof(double) + 16));
+  CCU_CUDA(h, f->cgp.reserve((size_t)f->K * nsnps * 3 * sizeof(double) + 16));
+  if (int rc = reserve_shard_buffers(h)) return rc;
+  CCU_CUDA(h, cudaMemcpyAsync(f->cell_ptr.p, cell_ptr, (nbcs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (nnz > 0) {
+    CCU_CUDA(h, cudaMemcpyAsync(f->snp_idx.p, snp_idx, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CCU_CUDA(h, cudaMemcpyAsync(f->read_ptr.p, read_ptr, (nnz + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  }
+  if (nreads > 0) {
+    CCU_CUDA(h, cudaMemcpyAsync(f->al.p, al, nreads, cudaMemcpyHostToDevice, st));
+    CCU_CUDA(h, cudaMemcpyAsync(f->bq.p, bq, nreads, cudaMemcpyHostToDevice, st));
+  }
+  if (nsnps > 0) CCU_CUDA(h, cudaMemcpyAsync(f->af.p, af, nsnps * sizeof(double), cudaMemcpyHostToDevice, st));
+  CCU_CUDA(h, cudaMemsetAsync(f->assign.p, 0xff, nbcs * sizeof(int32_t) + 16, st));  // -1: unassigned
+
+  const ccu::FmxDev d = fmx_view(h);
+  f->tm.launches = 0;
+  {  // F1: alpha = 0.5, cmd_cram_freemuxlet.cpp:133
+    Timer t(h, &f->tm.ms_pileup);
+    CCU_CUDA(h, ccu::launch_fmx_pileup(d, 0.5, st));
+    t.stop_sync();
+    f->tm.launches += nnz > 0 ? 1 : 0;
+  }
+  {  // SNP-major index: stable radix sort of (snp, entry id); entries of one SNP stay in ascending droplet order
+    Timer t(h, &f->tm.ms_csc);
+    // scratch: ent_cell | keys_in(=snp_idx) -> keys_out | vals_in | vals_out | cub temp
+    const size_t n = (size_t)nnz;
+    size_t temp_bytes = 0;
+    int end_bit = 1;
+    while ((1LL << end_bit) < nsnps && end_bit < 31) ++end_bit;
+    cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const int32_t*)nullptr, (int32_t*)nullptr,
+                                    (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0, end_bit, st);
+    const size_t a4 = (n * sizeof(int32_t) + 255) / 256 * 256;
+    CCU_CUDA(h, f->scratch.reserve(4 * a4 + temp_bytes + 256));
+    char* base = f->scratch.as<char>();
+    int32_t* ent_cell = reinterpret_cast<int32_t*>(base);
+    int32_t* keys_out = reinterpret_cast<int32_t*>(base + a4);
+    int32_t* vals_in = reinterpret_cast<int32_t*>(base + 2 * a4);
+    int32_t* vals_out = reinterpret_cast<int32_t*>(base + 3 * a4);
+    void* temp = base + 4 * a4;
+    CCU_CUDA(h, ccu::launch_fmx_entry_cells(d, ent_cell, st));
+    if (n > 0) {
+      std::vector<int32_t> iota(n);
+      for (size_t i = 0; i < n; ++i) iota[i] = (int32_t)i;
+      CCU_CUDA(h, cudaMemcpyAsync(vals_in, iota.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      CCU_CUDA(h, cudaStreamSynchronize(st));
+      CCU_CUDA(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, d.snp_idx, keys_out, vals_in, vals_out, (int)n, 0,
+                                                  end_bit, st));
+    }
+    CCU_CUDA(h, ccu::launch_fmx_build_csc(d, keys_out, vals_out, ent_cell, st));
+    t.stop_sync();
+    f->tm.launches += 4;
+  }
+  f->uploaded = true;
+  return 0;
+}
+
+int ccu_fmx_set_shard(ccu_handle* h, int64_t cell_begin, int64_t cell_end, int64_t snp_begin, int64_t snp_end) {
+  if (int rc = need(h, true, "ccu_fmx_set_shard")) return rc;
+  FmxState* f = h->fmx;
+  if (cell_begin < 0 || cell_end > f->nbcs || cell_begin > cell_end || snp_begin < 0 || snp_end > f->nsnps ||
+      snp_begin > snp_end)
+    return ccu_fail(h, "ccu_fmx_set_shard: range out of bounds");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  f->cell_begin = cell_begin;
+  f->cell_end = cell_end;
+  f->snp_begin = snp_begin;
+  f->snp_end = snp_end;
+  f->have_estep = false;
+  return reserve_shard_buffers(h);
+}
+
+int ccu_fmx_lmix(ccu_handle* h, double* llk0, double* llk2) {
+  if (int rc = need(h, true, "ccu_fmx_lmix")) return rc;
+  FmxState* f = h->fmx;
+  if (f->nbcs > 0 && (!llk0 || !llk2)) return ccu_fail(h, "ccu_fmx_lmix: NULL output");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  CCU_CUDA(h, f->scratch.reserve(2 * f->nbcs * sizeof(double) + 16));
+  double* d0 = f->scratch.as<double>();
+  double* d2 = d0 + f->nbcs;
+  Timer t(h, &f->tm.ms_lmix);
+  CCU_CUDA(h, ccu::launch_fmx_lmix(fmx_view(h), d0, d2, h->stream));
+  t.stop_sync();
+  if (f->nbcs > 0) {
+    CCU_CUDA(h, cudaMemcpy(llk0, d0, f->nbcs * sizeof(double), cudaMemcpyDeviceToHost));
+    CCU_CUDA(h, cudaMemcpy(llk2, d2, f->nbcs * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+int ccu_fmx_get_pileups(ccu_handle* h, ccu_pileup* out) {
+  if (int rc = need(h, true, "ccu_fmx_get_pileups")) return rc;
+  FmxState* f = h->fmx;
+  if (f->nnz == 0) return 0;
+  if (!out) return ccu_fail(h, "ccu_fmx_get_pileups: NULL output");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  std::vector<double> gl((size_t)f->nnz * 9), ld(f->nnz);
+  std::vector<int4> cnt(f->nnz);
+  CCU_CUDA(h, cudaMemcpy(gl.data(), f->gl.p, gl.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CCU_CUDA(h, cudaMemcpy(ld.data(), f->logdenom.p, ld.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CCU_CUDA(h, cudaMemcpy(cnt.data(), f->cnt.p, cnt.size() * sizeof(int4), cudaMemcpyDeviceToHost));
+  for (int64_t e = 0; e < f->nnz; ++e) {
+    out[e].nreads = cnt[e].x;
+    out[e].nref = cnt[e].y;
+    out[e].nalt = cnt[e].z;
+    out[e]._pad = 0;
+    memcpy(out[e].gls, &gl[e * 9], 9 * sizeof(double));
+    out[e].logdenom = ld[e];
+  }
+  return 0;
+}
+
+int ccu_fmx_mstep_dev(ccu_handle* h) {
+  if (int rc = need(h, true, "ccu_fmx_mstep")) return rc;
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  FmxState* f = h->fmx;
+  cudaEventRecord(f->ev[0], h->stream);
+  CCU_CUDA(h, ccu::launch_fmx_mstep(fmx_view(h), h->stream));
+  cudaEventRecord(f->ev[1], h->stream);
+  f->tm.launches += 1;
+  f->have_stats = true;
+  return 0;
+}
+
+int ccu_fmx_mstep(ccu_handle* h, const int32_t* assign) {
+  if (int rc = need(h, true, "ccu_fmx_mstep")) return rc;
+  FmxState* f = h->fmx;
+  if (f->nbcs > 0 && !assign) return ccu_fail(h, "ccu_fmx_mstep: NULL assignment vector");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  for (int64_t c = 0; c < f->nbcs; ++c)
+    if (assign[c] >= f->K) return ccu_fail(h, "ccu_fmx_mstep: assign[%lld] = %d >= nclust", (long long)c, assign[c]);
+  if (f->nbcs > 0)
+    CCU_CUDA(h, cudaMemcpyAsync(f->assign.p, assign, f->nbcs * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  if (int rc = ccu_fmx_mstep_dev(h)) return rc;
+  CCU_CUDA(h, cudaEventSynchronize(f->ev[1]));
+  cudaEventElapsedTime(&f->tm.ms_mstep, f->ev[0], f->ev[1]);
+  return 0;
+}
+
+int ccu_fmx_estep_dev(ccu_handle* h, int32_t apply_geno_error) {
+  if (int rc = need(h, true, "ccu_fmx_estep")) return rc;
+  FmxState* f = h->fmx;
+  if (!f->have_stats) return ccu_fail(h, "ccu_fmx_estep: no cluster statistics yet (run ccu_fmx_mstep first)");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  const ccu::FmxDev d = fmx_view(h);
+  CCU_CUDA(h, ccu::launch_fmx_cgp(d, apply_geno_error, h->stream));
+  cudaEventRecord(f->ev[0], h->stream);
+  CCU_CUDA(h, ccu::launch_fmx_estep(d, h->stream));
+  cudaEventRecord(f->ev[1], h->stream);
+  f->tm.launches += 2;
+  f->have_estep = true;
+  return 0;
+}
+
+int ccu_fmx_download_results(ccu_handle* h, ccu_fmx_result* out) {
+  if (int rc = need(h, true, "ccu_fmx_download_results")) return rc;
+  FmxState* f = h->fmx;
+  if (!f->have_estep) return ccu_fail(h, "ccu_fmx_download_results: no E-step has run");
+  const int64_t ncell = f->cell_end - f->cell_begin;
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  if (ncell > 0) {
+    if (!out) return ccu_fail(h, "ccu_fmx_download_results: NULL output");
+    CCU_CUDA(h, cudaMemcpyAsync(out, f->results.p, ncell * sizeof(ccu_fmx_result), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ccu_fmx_estep(ccu_handle* h, int32_t apply_geno_error, ccu_fmx_result* out, int32_t* assign_out) {
+  if (int rc = ccu_fmx_estep_dev(h, apply_geno_error)) return rc;
+  FmxState* f = h->fmx;
+  CCU_CUDA(h, cudaEventSynchronize(f->ev[1]));
+  cudaEventElapsedTime(&f->tm.ms_estep, f->ev[0], f->ev[1]);
+  if (int rc = ccu_fmx_download_results(h, out)) return rc;
+  const int64_t ncell = f->cell_end - f->cell_begin;
+  if (assign_out && ncell > 0)
+    CCU_CUDA(h, cudaMemcpy(assign_out, f->assign.as<int32_t>() + f->cell_begin, ncell * sizeof(int32_t),
+                           cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int ccu_fmx_get_llk(ccu_handle* h, double* llk) {
+  if (int rc = need(h, true, "ccu_fmx_get_llk")) return rc;
+  FmxState* f = h->fmx;
+  if (!f->have_estep) return ccu_fail(h, "ccu_fmx_get_llk: no E-step has run");
+  const int64_t n = (f->cell_end - f->cell_begin) * ((int64_t)f->K * (f->K + 1) / 2);
+  if (n == 0) return 0;
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  CCU_CUDA(h, cudaMemcpy(llk, f->llk.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int ccu_fmx_get_clusters(ccu_handle* h, ccu_pileup* out) {
+  if (int rc = need(h, true, "ccu_fmx_get_clusters")) return rc;
+  FmxState* f = h->fmx;
+  if (!f->have_stats) return ccu_fail(h, "ccu_fmx_get_clusters: no M-step has run");
+  const int64_t n = (int64_t)f->K * f->nsnps;
+  if (n == 0) return 0;
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  CCU_CUDA(h, f->scratch.reserve(n * sizeof(ccu_pileup) + 16));
+  CCU_CUDA(h, ccu::launch_fmx_unpack_stats(fmx_view(h), f->scratch.as<ccu_pileup>(), h->stream));
+  CCU_CUDA(h, cudaMemcpyAsync(out, f->scratch.p, n * sizeof(ccu_pileup), cudaMemcpyDeviceToHost, h->stream));
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+void* ccu_fmx_stats_dev(ccu_handle* h, int64_t* n_doubles) {
+  if (!h || !h->fmx || !h->fmx->uploaded) return nullptr;
+  if (n_doubles) *n_doubles = (int64_t)h->fmx->K * h->fmx->nsnps * ccu::kStatStride;
+  return h->fmx->stats.p;
+}
+
+void* ccu_fmx_assign_dev(ccu_handle* h, int64_t* n_int32) {
+  if (!h || !h->fmx || !h->fmx->uploaded) return nullptr;
+  if (n_int32) *n_int32 = h->fmx->nbcs;
+  return h->fmx->assign.p;
+}
+
+int ccu_fmx_run_em(ccu_handle* h, const int32_t* init_assign, int32_t niter, int32_t geno_error_every_iter,
+                   int32_t stop_when_stable, ccu_fmx_result* out, int32_t* iters_run) {
+  if (int rc = need(h, true, "ccu_fmx_run_em")) return rc;
+  FmxState* f = h->fmx;
+  if (f->cell_begin != 0 || f->cell_end != f->nbcs || f->snp_begin != 0 || f->snp_end != f->nsnps)
+    return ccu_fail(h, "ccu_fmx_run_em: single-GPU loop needs the full shard (use the *_dev calls with collectives)");
+  if (niter < 1) return ccu_fail(h, "ccu_fmx_run_em: niter must be >= 1");
+  if (int rc = ccu_fmx_mstep(h, init_assign)) return rc;  // cmd_cram_freemuxlet.cpp:359-370
+  std::vector<ccu_fmx_result> prev, cur;
+  float ms_e = 0, ms_m = 0;
+  int it = 0;
+  for (; it < niter; ++it) {
+    const int apply = geno_error_every_iter ? 1 : (it + 1 == niter);  // :485 vs freemux2 :410
+    if (int rc = ccu_fmx_estep_dev(h, apply)) return rc;
+    cudaEvent_t e0 = f->ev[0], e1 = f->ev[1];
+    CCU_CUDA(h, cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms_e += ms;
+    if (int rc = ccu_fmx_mstep_dev(h)) return rc;  // :639-650 (assign was written by the E-step)
+    CCU_CUDA(h, cudaEventSynchronize(f->ev[1]));
+    cudaEventElapsedTime(&ms, f->ev[0], f->ev[1]);
+    ms_m += ms;
+    if (stop_when_stable) {  // cmd_cram_freemux2.cpp:518-604
+      cur.resize(f->nbcs);
+      if (int rc = ccu_fmx_download_results(h, cur.data())) return rc;
+      int64_t nchanged = 0;
+      for (int64_t c = 0; c < f->nbcs; ++c) {
+        const bool had = !prev.empty();
+        const int ptype = had ? prev[c].type : -1, pj = had ? prev[c].jBest : -1, pk = had ? prev[c].kBest : -1;
+        if (cur[c].type == 0) nchanged += (ptype != 0 || pj != cur[c].sBest || pk != cur[c].sBest);
+        else nchanged += (ptype != cur[c].type);
+      }
+      prev.swap(cur);
+      if (nchanged == 0) {
+        ++it;
+        break;
+      }
+    }
+  }
+  f->tm.ms_estep = ms_e / (it > 0 ? it : 1);
+  f->tm.ms_mstep = ms_m / (it > 0 ? it : 1);
+  if (iters_run) *iters_run = it;
+  return ccu_fmx_download_results(h, out);
+}
+
+int ccu_fmx_get_timings(const ccu_handle* h, ccu_fmx_timings* t) {
+  if (!h || !t || !h->fmx) return 1;
+  *t = h->fmx->tm;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+// fmx_internal.h -- device-side layout and launch wrappers of the freemuxlet kernels
+// (fmx_kernels.cu), shared with the C-ABI host code (ccu_fmx_api.cu).  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cramore_cuda.h"
+
+namespace ccu {
+
+constexpr int kStatStride = 12;   // doubles per (cluster,SNP): gls[9], nreads, nref, nalt
+constexpr int kFmxMaxClust = 64;  // K(K+1)/2 <= 2080 pair likelihoods per droplet
+
+struct FmxDev {
+  int32_t K;
+  double doublet_prior, geno_error;
+  int64_t nbcs, nsnps, nnz;
+  // droplet store (all droplets)
+  const int64_t* cell_ptr;   // [nbcs+1]
+  const int32_t* snp_idx;    // [nnz]
+  const int64_t* read_ptr;   // [nnz+1]
+  const uint8_t* al;
+  const uint8_t* bq;
+  const double* af;          // [nsnps]
+  const double* phred;       // [512] err, mat
+  // per-entry pileups (static over the EM loop), cell-major
+  double* gl;                // [nnz][9]
+  int4* cnt;                 // [nnz] nreads, nref, nalt, 0
+  double* logdenom;          // [nnz]
+  // SNP-major copy for the M-step
+  int64_t* csc_ptr;          // [nsnps+1]
+  int32_t* csc_cell;         // [nnz] droplet id, ascending inside a SNP
+  double* csc_gl;            // [nnz][9]
+  int4* csc_cnt;             // [nnz]
+  // EM state
+  int32_t* assign;           // [nbcs] cluster of the droplet in the next M-step, or -1
+  double* stats;             // [K][nsnps][kStatStride]
+  double* cgp;               // [nsnps][K][3] per-cluster genotype posteriors of the current iteration
+  double* llk;               // [cells of the shard][K(K+1)/2]
+  ccu_fmx_result* results;   // [cells of the shard]
+  // shard
+  int64_t cell_begin, cell_end, snp_begin, snp_end;
+};
+
+cudaError_t launch_fmx_pileup(const FmxDev& d, double alpha, cudaStream_t st);
+cudaError_t launch_fmx_lmix(const FmxDev& d, double* llk0, double* llk2, cudaStream_t st);
+// ent_cell[nnz]: droplet id of every entry
+cudaError_t launch_fmx_entry_cells(const FmxDev& d, int32_t* ent_cell, cudaStream_t st);
+// after the (snp, entry) pairs were sorted by snp: gather the SNP-major copy and the segment offsets
+cudaError_t launch_fmx_build_csc(const FmxDev& d, const int32_t* sorted_snp, const int32_t* sorted_ent,
+                                 const int32_t* ent_cell, cudaStream_t st);
+cudaError_t launch_fmx_mstep(const FmxDev& d, cudaStream_t st);
+cudaError_t launch_fmx_cgp(const FmxDev& d, int apply_geno_error, cudaStream_t st);
+cudaError_t launch_fmx_estep(const FmxDev& d, cudaStream_t st);
+// int32 count of droplets whose (type, jBest, kBest) differ between two result arrays
+cudaError_t launch_fmx_unpack_stats(const FmxDev& d, ccu_pileup* out, cudaStream_t st);
+
+}  // namespace ccu

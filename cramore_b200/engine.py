@@ -41,6 +41,10 @@ ABI_SYMBOLS = [
     "ccu_demux_run", "ccu_demux_wait", "ccu_demux_download", "ccu_demux_classify", "ccu_demux_best_row",
     "ccu_demux_best_header", "ccu_demux_get_tiles", "ccu_demux_get_genotypes", "ccu_demux_get_llk",
     "ccu_measure_fp64_peak",
+    "ccu_fmx_configure", "ccu_fmx_upload", "ccu_fmx_set_shard", "ccu_fmx_lmix", "ccu_fmx_get_pileups",
+    "ccu_fmx_mstep", "ccu_fmx_estep", "ccu_fmx_get_llk", "ccu_fmx_get_clusters", "ccu_fmx_stats_dev",
+    "ccu_fmx_assign_dev", "ccu_fmx_mstep_dev", "ccu_fmx_estep_dev", "ccu_fmx_download_results", "ccu_fmx_run_em",
+    "ccu_fmx_get_timings",
 ]
 
 
@@ -58,7 +62,9 @@ def load_library():
         lib.ccu_demux_best_header.restype = C.c_char_p
         for name in ABI_SYMBOLS:
             fn = getattr(lib, name)
-            if name not in ("ccu_last_error", "ccu_demux_best_header"):
+            if name in ("ccu_fmx_stats_dev", "ccu_fmx_assign_dev"):
+                fn.restype = C.c_void_p
+            elif name not in ("ccu_last_error", "ccu_demux_best_header"):
                 fn.restype = C.c_int
         _lib = lib
     return _lib
@@ -184,6 +190,118 @@ class DemuxEngine:
         v = C.c_double(0)
         self._check(self.lib.ccu_measure_fp64_peak(self.h, C.c_float(ms), C.byref(v)))
         return v.value
+
+
+PILEUP_DTYPE = np.dtype([
+    ("nreads", "<i4"), ("nref", "<i4"), ("nalt", "<i4"), ("_pad", "<i4"),
+    ("gls", "<f8", (9,)), ("logdenom", "<f8")])
+
+FMX_RESULT_DTYPE = np.dtype([
+    ("sBest", "<i4"), ("sNext", "<i4"), ("dBest1", "<i4"), ("dBest2", "<i4"), ("dNext1", "<i4"),
+    ("dNext2", "<i4"), ("type", "<i4"), ("jBest", "<i4"), ("kBest", "<i4"), ("jNext", "<i4"),
+    ("kNext", "<i4"), ("_pad", "<i4"),
+    ("sngBestLLK", "<f8"), ("sngNextLLK", "<f8"), ("dblBestLLK", "<f8"), ("dblNextLLK", "<f8"),
+    ("sumLLK", "<f8"), ("sngLLK", "<f8"), ("bestLLK", "<f8"), ("nextLLK", "<f8"),
+    ("bestPP", "<f8"), ("sngPP", "<f8"), ("sngOnlyPP", "<f8")])
+
+
+class FmxTimings(C.Structure):
+    _fields_ = [("ms_pileup", C.c_float), ("ms_csc", C.c_float), ("ms_lmix", C.c_float), ("ms_cgp", C.c_float),
+                ("ms_estep", C.c_float), ("ms_mstep", C.c_float), ("launches", C.c_int32), ("_pad", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "_pad"}
+
+
+class FreemuxEngine(DemuxEngine):
+    """One GPU's freemuxlet engine: the call sequence a patched cmdCramFreemuxlet makes
+    (cmd_cram_freemuxlet.cpp:83-653).  The multi-GPU driver is cramore_b200.fmx_dist."""
+
+    def configure_fmx(self, nclust, doublet_prior=0.5, geno_error=0.0):
+        self._check(self.lib.ccu_fmx_configure(self.h, C.c_int32(nclust), C.c_double(doublet_prior),
+                                               C.c_double(geno_error)))
+        self.K = nclust
+        self.npairs = nclust * (nclust + 1) // 2
+
+    def upload_fmx(self, cell_ptr, snp_idx, read_ptr, al, bq, af):
+        cp, si, rp, a, q = self._csr(cell_ptr, snp_idx, read_ptr, al, bq)
+        af = np.ascontiguousarray(af, np.float64)
+        self.nbcs, self.nnz, self.nsnps = len(cp) - 1, int(cp[-1]), len(af)
+        self.cell_begin, self.cell_end = 0, self.nbcs
+        self._check(self.lib.ccu_fmx_upload(self.h, C.c_int64(self.nbcs), C.c_int64(self.nsnps), _ptr(cp), _ptr(si),
+                                            _ptr(rp), _ptr(a), _ptr(q), _ptr(af)))
+
+    def set_shard(self, cell_begin, cell_end, snp_begin, snp_end):
+        self._check(self.lib.ccu_fmx_set_shard(self.h, C.c_int64(cell_begin), C.c_int64(cell_end),
+                                               C.c_int64(snp_begin), C.c_int64(snp_end)))
+        self.cell_begin, self.cell_end = cell_begin, cell_end
+
+    def lmix(self):
+        a, b = np.zeros(self.nbcs), np.zeros(self.nbcs)
+        self._check(self.lib.ccu_fmx_lmix(self.h, _ptr(a), _ptr(b)))
+        return a, b
+
+    def pileups(self):
+        out = np.zeros(self.nnz, PILEUP_DTYPE)
+        self._check(self.lib.ccu_fmx_get_pileups(self.h, _ptr(out)))
+        return out
+
+    def mstep(self, assign):
+        a = np.ascontiguousarray(assign, np.int32)
+        assert len(a) == self.nbcs
+        self._check(self.lib.ccu_fmx_mstep(self.h, _ptr(a)))
+
+    def estep(self, apply_geno_error=False):
+        n = self.cell_end - self.cell_begin
+        out = np.zeros(n, FMX_RESULT_DTYPE)
+        assign = np.zeros(n, np.int32)
+        self._check(self.lib.ccu_fmx_estep(self.h, C.c_int32(1 if apply_geno_error else 0), _ptr(out), _ptr(assign)))
+        return out, assign
+
+    def fmx_llk(self):
+        out = np.zeros((self.cell_end - self.cell_begin, self.npairs))
+        self._check(self.lib.ccu_fmx_get_llk(self.h, _ptr(out)))
+        return out
+
+    def clusters(self):
+        out = np.zeros((self.K, self.nsnps), PILEUP_DTYPE)
+        self._check(self.lib.ccu_fmx_get_clusters(self.h, _ptr(out)))
+        return out
+
+    def stats_dev(self):
+        """(device pointer, number of doubles) of the [K][nsnps][12] statistics array."""
+        n = C.c_int64(0)
+        p = self.lib.ccu_fmx_stats_dev(self.h, C.byref(n))
+        return p, n.value
+
+    def assign_dev(self):
+        n = C.c_int64(0)
+        p = self.lib.ccu_fmx_assign_dev(self.h, C.byref(n))
+        return p, n.value
+
+    def mstep_dev(self):
+        self._check(self.lib.ccu_fmx_mstep_dev(self.h))
+
+    def estep_dev(self, apply_geno_error=False):
+        self._check(self.lib.ccu_fmx_estep_dev(self.h, C.c_int32(1 if apply_geno_error else 0)))
+
+    def download_results(self):
+        out = np.zeros(self.cell_end - self.cell_begin, FMX_RESULT_DTYPE)
+        self._check(self.lib.ccu_fmx_download_results(self.h, _ptr(out)))
+        return out
+
+    def run_em(self, init_assign, niter=10, geno_error_every_iter=False, stop_when_stable=False):
+        a = np.ascontiguousarray(init_assign, np.int32)
+        out = np.zeros(self.nbcs, FMX_RESULT_DTYPE)
+        it = C.c_int32(0)
+        self._check(self.lib.ccu_fmx_run_em(self.h, _ptr(a), C.c_int32(niter), C.c_int32(int(geno_error_every_iter)),
+                                            C.c_int32(int(stop_when_stable)), _ptr(out), C.byref(it)))
+        return out, it.value
+
+    def fmx_timings(self):
+        t = FmxTimings()
+        self._check(self.lib.ccu_fmx_get_timings(self.h, C.byref(t)))
+        return t.as_dict()
 
 
 def classify(results, nv, alphas, doublet_prior=0.5):

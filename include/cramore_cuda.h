@@ -132,6 +132,88 @@ int ccu_demux_get_tiles(ccu_handle* h, double* tiles);
 int ccu_demux_get_genotypes(ccu_handle* h, int64_t snp_begin, int64_t snp_end, double* gps);
 int ccu_demux_get_llk(ccu_handle* h, int64_t cell_begin, int64_t cell_end, double* llk);
 
+
+/* ---- freemuxlet ------------------------------------------------------------------------ */
+
+/* snp_droplet_pileup (sc_drop_seq.h:65-75) flattened: one per (cell,SNP) entry or per
+ * (cluster,SNP).  logdenom is carried for per-entry pileups only: no live output of the reference
+ * reads it (it is dead state of snp_droplet_pileup::merge), so cluster pileups report 0. */
+typedef struct {
+  int32_t nreads, nref, nalt, _pad;
+  double gls[9];
+  double logdenom;
+} ccu_pileup;
+
+/* Per-droplet outcome of one E-step + decision pass (cmd_cram_freemuxlet.cpp:524-637): exactly the
+ * arrays the reference keeps per droplet and prints into <out>.clust1.samples.gz (:709-711).
+ * type: 0 SNG, 1 DBL, 2 AMB. */
+typedef struct {
+  int32_t sBest, sNext, dBest1, dBest2, dNext1, dNext2;
+  int32_t type;
+  int32_t jBest, kBest, jNext, kNext, _pad;
+  double sngBestLLK, sngNextLLK, dblBestLLK, dblNextLLK;
+  double sumLLK, sngLLK;
+  double bestLLK, nextLLK, bestPP, sngPP, sngOnlyPP;
+} ccu_fmx_result;
+
+/* --nsample / --doublet-prior / --geno-error (cmd_cram_freemuxlet.cpp:34-63).  2 <= nclust <= 64. */
+int ccu_fmx_configure(ccu_handle* h, int32_t nclust, double doublet_prior, double geno_error);
+
+/* The droplet store (same CSR as demuxlet, ALL droplets) plus the per-SNP allele frequency
+ * (sc_snp_t::af, .var.gz column 6).  Computes the per-(cell,SNP) pileup likelihoods at alpha = 0.5
+ * (calculate_snp_droplet_pileup, sc_drop_seq.cpp:452-509, as called at
+ * cmd_cram_freemuxlet.cpp:133) and the SNP-major copy the M-step folds over. */
+int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* cell_ptr, const int32_t* snp_idx,
+                   const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq, const double* af);
+
+/* Multi-GPU partition: this handle runs the E-step for droplets [cell_begin, cell_end)
+ * and the M-step for SNPs [snp_begin, snp_end).  Default after upload: everything. */
+int ccu_fmx_set_shard(ccu_handle* h, int64_t cell_begin, int64_t cell_end, int64_t snp_begin, int64_t snp_end);
+
+/* .lmix scores (cmd_cram_freemuxlet.cpp:116-164): llk0 = DBL.LLK, llk2 = SNG.LLK per droplet [nbcs]. */
+int ccu_fmx_lmix(ccu_handle* h, double* llk0, double* llk2);
+int ccu_fmx_get_pileups(ccu_handle* h, ccu_pileup* out /* [nnz] */);
+
+/* M-step (cmd_cram_freemuxlet.cpp:359-370 and :639-650): rebuild every cluster pileup as the ordered
+ * fold snp_droplet_pileup::merge (sc_drop_seq.h:77-101) over the droplets with assign[c] >= 0 in
+ * ascending droplet id.  assign: host int32 [nbcs] (cluster id or -1).  Fills the SNP slab of this
+ * shard and zeroes the rest of the statistics array, so that a sum-allreduce over ranks assembles the
+ * full array bit-exactly. */
+int ccu_fmx_mstep(ccu_handle* h, const int32_t* assign);
+/* E-step + decision (cmd_cram_freemuxlet.cpp:465-637) for this shard's droplets.
+ * out: host [cell_end-cell_begin]; assign_out (optional): host int32 [cell_end-cell_begin], the
+ * M-step input of the next iteration (jBest for confident singlets, else -1, :641-643). */
+int ccu_fmx_estep(ccu_handle* h, int32_t apply_geno_error, ccu_fmx_result* out, int32_t* assign_out);
+/* llks[pair] of the last E-step, [cells of the shard][K(K+1)/2], pair = j(j+1)/2+k (inspection). */
+int ccu_fmx_get_llk(ccu_handle* h, double* llk);
+int ccu_fmx_get_clusters(ccu_handle* h, ccu_pileup* out /* [K][nsnps] */);
+
+/* Device-resident form for the EM loop and its collectives.  The statistics array is
+ * double [K][nsnps][12] = {gls[9], nreads, nref, nalt}; the assignment vector is int32 [nbcs].
+ * Both pointers stay valid until the next ccu_fmx_upload / ccu_destroy.  A multi-GPU driver runs,
+ * per iteration:  ccu_fmx_estep_dev -> all-gather of the assignment vector (each rank wrote its own
+ * droplet range) -> ccu_fmx_mstep_dev -> sum-allreduce of the statistics array (NCCL, in place). */
+void* ccu_fmx_stats_dev(ccu_handle* h, int64_t* n_doubles);
+void* ccu_fmx_assign_dev(ccu_handle* h, int64_t* n_int32);
+int ccu_fmx_mstep_dev(ccu_handle* h);
+int ccu_fmx_estep_dev(ccu_handle* h, int32_t apply_geno_error);
+int ccu_fmx_download_results(ccu_handle* h, ccu_fmx_result* out);
+/* Single-GPU EM loop cmd_cram_freemuxlet.cpp:457-653: niter iterations of E-step, decision and
+ * M-step starting from init_assign (host int32 [nbcs], the clusts[] of :359-370); geno_error is
+ * applied on the last iteration only (freemuxlet, :485) or on every iteration (freemux2,
+ * cmd_cram_freemux2.cpp:410-415) as every_iter says; stop_when_stable adds freemux2's early stop
+ * (:601-604).  out: host [nbcs]; returns the number of iterations run in *iters_run. */
+int ccu_fmx_run_em(ccu_handle* h, const int32_t* init_assign, int32_t niter, int32_t geno_error_every_iter,
+                   int32_t stop_when_stable, ccu_fmx_result* out, int32_t* iters_run);
+
+/* Device timings (ms) of the last freemuxlet calls. */
+typedef struct {
+  float ms_pileup, ms_csc, ms_lmix, ms_cgp, ms_estep, ms_mstep;
+  int32_t launches;
+  int32_t _pad;
+} ccu_fmx_timings;
+int ccu_fmx_get_timings(const ccu_handle* h, ccu_fmx_timings* t);
+
 /* Measured FP64 roofline denominator: runs a DFMA-saturating microkernel for about `ms`
  * milliseconds on the handle's device and returns TFLOP/s (2 flops per DFMA). */
 int ccu_measure_fp64_peak(ccu_handle* h, float ms, double* tflops);

@@ -1,0 +1,180 @@
+"""-m gpu parity tests of the freemuxlet kernels (through the C ABI) vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from cramore_b200.synth import make_dataset
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def feng(built):
+    from cramore_b200 import FreemuxEngine
+    eng = FreemuxEngine(0)
+    yield eng
+    eng.close()
+
+
+def small_c4(nbcs=300, nsnps=3000, rbar=150, seed=None):
+    d = make_dataset("C4", nbcs=nbcs, nsnps=nsnps, rbar=rbar, seed=seed)
+    d["plp"] = pyoracle.fmx_pileup(d["read_ptr"], d["al"], d["bq"], 0.5)
+    return d
+
+
+def noisy_init(d, K, frac_unassigned=0.2, frac_wrong=0.05, seed=3):
+    rng = np.random.default_rng(seed)
+    a = (d["s1"] % K).astype(np.int32)
+    wrong = rng.random(len(a)) < frac_wrong
+    a[wrong] = rng.integers(0, K, wrong.sum())
+    a[d["is_dbl"]] = -1
+    a[rng.random(len(a)) < frac_unassigned] = -1
+    return a
+
+
+def upload(feng, d, K, geno_error=0.0, prior=0.5):
+    feng.configure_fmx(K, prior, geno_error)
+    feng.upload_fmx(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], d["af"])
+
+
+def assert_fmx_results(res, ref, ref_llk, K):
+    for f in ("sngBestLLK", "sngNextLLK", "dblBestLLK", "dblNextLLK", "sumLLK", "sngLLK", "bestLLK", "nextLLK", "bestPP"):
+        np.testing.assert_allclose(res[f], ref[f], rtol=RTOL, atol=1e-9, err_msg=f)
+    np.testing.assert_allclose(res["sngPP"], ref["sngPP"], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(res["sngOnlyPP"], ref["sngOnlyPP"], rtol=1e-6, atol=1e-12)
+
+    def pair(j, k):
+        return j * (j + 1) // 2 + k
+
+    for i in range(len(ref)):
+        for a, b in (("sBest", "sBest"), ("sNext", "sNext")):
+            x, y = int(res[a][i]), int(ref[b][i])
+            if x != y:  # acceptable only for a tie within tolerance
+                assert abs(ref_llk[i, pair(x, x)] - ref_llk[i, pair(y, y)]) <= RTOL * abs(ref_llk[i, pair(y, y)])
+        for t in ("Best", "Next"):
+            x = (int(res["d%s1" % t][i]), int(res["d%s2" % t][i]))
+            y = (int(ref["d%s1" % t][i]), int(ref["d%s2" % t][i]))
+            if x != y:
+                assert abs(ref_llk[i, pair(*x)] - ref_llk[i, pair(*y)]) <= RTOL * abs(ref_llk[i, pair(*y)])
+    assert np.array_equal(res["type"], ref["type"])
+    same = res["sBest"] == ref["sBest"]
+    assert np.array_equal(res["jBest"][same], ref["jBest"][same])
+
+
+def test_pileups_bit_exact(feng):
+    d = small_c4(nbcs=200, nsnps=500, rbar=300)  # ~300 reads over 500 SNPs: many multi-read entries
+    upload(feng, d, 4)
+    got = feng.pileups()
+    ref = d["plp"]
+    for f in ("nreads", "nref", "nalt"):
+        assert np.array_equal(got[f], ref[f]), f
+    assert np.array_equal(got["gls"], ref["gls"])
+    np.testing.assert_allclose(got["logdenom"], ref["logdenom"], rtol=1e-12, atol=1e-13)
+
+
+def test_lmix_scores(feng):
+    d = small_c4()
+    upload(feng, d, 4)
+    l0, l2 = feng.lmix()
+    r0, r2 = pyoracle.fmx_lmix(d["cell_ptr"], d["snp_idx"], d["plp"], d["af"])
+    np.testing.assert_allclose(l0, r0, rtol=RTOL)
+    np.testing.assert_allclose(l2, r2, rtol=RTOL)
+
+
+@pytest.mark.parametrize("K", [2, 5, 16])
+def test_mstep_bit_exact(feng, K):
+    d = small_c4(nbcs=400, nsnps=800, rbar=200)
+    upload(feng, d, K)
+    assign = noisy_init(d, K)
+    feng.mstep(assign)
+    got = feng.clusters()
+    ref = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], d["plp"], assign, K, d["nsnps"])
+    for f in ("nreads", "nref", "nalt"):
+        assert np.array_equal(got[f], ref[f]), f
+    assert np.array_equal(got["gls"], ref["gls"])  # ordered, clamped fold: bit-exact
+
+
+@pytest.mark.parametrize("K,geno_error", [(2, 0.0), (3, 0.1), (16, 0.0), (16, 0.1), (20, 0.05), (33, 0.0)])
+def test_estep_llk_and_decisions(feng, K, geno_error):
+    d = small_c4(nbcs=120, nsnps=2000, rbar=150)
+    upload(feng, d, K, geno_error)
+    assign = noisy_init(d, K)
+    feng.mstep(assign)
+    res, nxt = feng.estep(apply_geno_error=geno_error > 0)
+    clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], d["plp"], assign, K, d["nsnps"])
+    ref, ref_llk = pyoracle.fmx_estep(d["cell_ptr"], d["snp_idx"], d["plp"], d["af"], clust, 0.5, geno_error,
+                                      geno_error > 0, want_llk=True)
+    np.testing.assert_allclose(feng.fmx_llk(), ref_llk, rtol=RTOL, atol=1e-12)
+    assert_fmx_results(res, ref, ref_llk, K)
+    want_next = np.where(ref["type"] == 0, ref["jBest"], -1)
+    same = res["sBest"] == ref["sBest"]
+    assert np.array_equal(nxt[same], want_next[same])
+
+
+def test_em_loop_matches_oracle(feng):
+    """cmd_cram_freemuxlet.cpp:457-653: initial M-step, then E/decision/M iterations, geno_error on the
+    last iteration only; final cluster statistics are bit-identical when every assignment agrees."""
+    K, niter, ge = 16, 4, 0.1
+    d = small_c4(nbcs=600, nsnps=4000, rbar=200)
+    upload(feng, d, K, ge)
+    init = noisy_init(d, K, frac_unassigned=0.5)
+    res, iters = feng.run_em(init, niter=niter)
+    assert iters == niter
+    clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], d["plp"], init, K, d["nsnps"])
+    for it in range(niter):
+        ref, ref_llk = pyoracle.fmx_estep(d["cell_ptr"], d["snp_idx"], d["plp"], d["af"], clust, 0.5, ge,
+                                          it + 1 == niter, want_llk=True)
+        assign = np.where(ref["type"] == 0, ref["jBest"], -1).astype(np.int32)
+        clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], d["plp"], assign, K, d["nsnps"])
+    assert_fmx_results(res, ref, ref_llk, K)
+    got = feng.clusters()
+    assert np.array_equal(got["gls"], clust["gls"]) and np.array_equal(got["nreads"], clust["nreads"])
+    # the simulation is recovered: confident singlets sit in the cluster of their sample
+    sng = (res["type"] == 0) & ~d["is_dbl"]
+    assert sng.sum() > 300 and (res["jBest"][sng] == d["s1"][sng] % K).mean() > 0.98
+
+
+def test_freemux2_flavour_early_stop(feng):
+    """cmd_cram_freemux2.cpp: geno_error on every iteration and stop once no call changes."""
+    K = 8
+    d = make_dataset("C4", nbcs=300, nsnps=3000, rbar=200, nv=8)
+    upload(feng, d, K, 0.1)
+    init = noisy_init(d, K, frac_unassigned=0.3)
+    res, iters = feng.run_em(init, niter=30, geno_error_every_iter=True, stop_when_stable=True)
+    assert 2 <= iters < 30
+    res2, iters2 = feng.run_em(init, niter=iters, geno_error_every_iter=True)
+    assert np.array_equal(res, res2)
+
+
+def test_shard_invariance_and_slab_sum(feng):
+    """Multi-GPU partition emulated on one GPU: E-step over barcode shards and M-step over SNP slabs
+    reproduce the unsharded results bitwise; slab statistics are disjoint, so their sum (what the NCCL
+    all-reduce computes) is the full array exactly."""
+    import ctypes as C
+    K = 6
+    d = small_c4(nbcs=250, nsnps=1500, rbar=150)
+    upload(feng, d, K)
+    assign = noisy_init(d, K)
+    feng.mstep(assign)
+    full_stats = np.array(feng.clusters())
+    res_full, nxt_full = feng.estep()
+    parts = []
+    for b, e in ((0, 90), (90, 250)):
+        feng.set_shard(b, e, 0, d["nsnps"])
+        r, _ = feng.estep()
+        parts.append(r)
+    assert np.array_equal(np.concatenate(parts), res_full)
+    total = None
+    for b, e in ((0, 400), (400, 1100), (1100, 1500)):
+        feng.set_shard(0, d["nbcs"], b, e)
+        feng.mstep(assign)
+        c = feng.clusters()
+        outside = np.ones(d["nsnps"], bool)
+        outside[b:e] = False
+        assert np.all(c["gls"][:, outside] == 0) and np.all(c["nreads"][:, outside] == 0)
+        s = np.concatenate([c["gls"], c["nreads"][..., None].astype(float), c["nref"][..., None].astype(float),
+                            c["nalt"][..., None].astype(float)], axis=2)
+        total = s if total is None else total + s
+    assert np.array_equal(total[..., :9], full_stats["gls"])
+    assert np.array_equal(total[..., 9], full_stats["nreads"])
