@@ -216,7 +216,10 @@ def main():
     d2h = out.nbytes
 
     eng = DemuxEngine(local)
-    stream = torch.cuda.current_stream()
+    # one real stream shared by the engine and the torch events (handle 0, the legacy default stream,
+    # would mean "engine-owned stream" to ccu_set_stream)
+    stream = torch.cuda.Stream(device=torch.device("cuda", local))
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     eng.configure(d["nv"], d["alphas"], 0.5)
 

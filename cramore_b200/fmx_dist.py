@@ -1,0 +1,87 @@
+"""Multi-GPU freemuxlet EM driver: one process per GPU.
+
+  E-step  : barcode shards (droplets are independent given the cluster statistics)
+  M-step  : SNP slabs.  snp_droplet_pileup::merge (sc_drop_seq.h:77-101) clamps after every droplet, so
+            a cluster statistic is an ORDERED fold over droplets and cannot be formed by summing
+            per-shard partials.  Every rank therefore folds all droplets, in ascending id, for its own
+            SNP slab and leaves zeros elsewhere; the sum-allreduce (NCCL over NVLink, in place on the
+            engine's statistics array) then assembles the full array bit-exactly on every rank.
+  per iteration: E-step -> all-gather of the assignment vector -> M-step -> all-reduce of the statistics.
+
+The engine object only has to provide the methods used below, which lets the CPU test suite drive the
+same loop over gloo with a numpy stand-in."""
+import numpy as np
+
+from .shard import balanced_ranges, gather_results
+
+
+class _DevArray:
+    """CUDA array interface view of engine-owned device memory (no copy)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def device_views(eng, device):
+    """torch tensors aliasing the engine's statistics (float64) and assignment (int32) arrays."""
+    import torch
+    sp, sn = eng.stats_dev()
+    ap, an = eng.assign_dev()
+    stats = torch.as_tensor(_DevArray(sp, sn, "<f8"), device=device)
+    assign = torch.as_tensor(_DevArray(ap, an, "<i4"), device=device)
+    assert stats.data_ptr() == sp and assign.data_ptr() == ap
+    return stats, assign
+
+
+def snp_slabs(snp_idx, nsnps, world):
+    """Contiguous SNP ranges with ~equal numbers of (cell,SNP) entries."""
+    counts = np.bincount(np.asarray(snp_idx, np.int64), minlength=nsnps)
+    ptr = np.concatenate([[0], np.cumsum(counts)])
+    return balanced_ranges(ptr, world)
+
+
+def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign, niter=10,
+                       geno_error_every_iter=False, group=None, sync=None):
+    """cmd_cram_freemuxlet.cpp:359-370 + :457-653 across ranks.  `stats`/`assign` are torch tensors
+    aliasing the engine's arrays (device_views, or CPU tensors of a stand-in engine).  Returns this
+    rank's per-droplet results and every rank's results gathered in barcode order."""
+    import torch
+    import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    rank = dist.get_rank(group) if multi else 0
+    cb, ce = cell_ranges[rank]
+    sb, se = snp_ranges[rank]
+    eng.set_shard(cb, ce, sb, se)
+    sync = sync or (lambda: None)
+
+    def exchange_assign():
+        # each rank owns assign[cb:ce]; a sum of (value + 1) over zero-filled vectors is an all-gather
+        if not multi:
+            return
+        sync()
+        tmp = torch.zeros_like(assign)
+        tmp[cb:ce] = assign[cb:ce] + 1
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        assign.copy_(tmp - 1)
+
+    def exchange_stats():
+        if not multi:
+            return
+        sync()
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+
+    assign.copy_(torch.as_tensor(np.ascontiguousarray(init_assign, np.int32)).to(assign.device))
+    eng.mstep_dev()
+    exchange_stats()
+    for it in range(niter):
+        eng.estep_dev(bool(geno_error_every_iter) or (it + 1 == niter))
+        exchange_assign()
+        eng.mstep_dev()
+        exchange_stats()
+    sync()
+    local = eng.download_results()
+    if not multi:
+        return local, local
+    device = None if stats.device.type == "cpu" else stats.device
+    return local, gather_results(local, cell_ranges, device=device, group=group)

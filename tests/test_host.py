@@ -155,3 +155,82 @@ def test_world_size_2_gloo_shard_and_gather(tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+_FMX_WORKER = r"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from cramore_b200.fmx_dist import run_em_distributed, snp_slabs
+from cramore_b200.shard import balanced_ranges
+from cramore_b200.synth import make_dataset
+from oracle import pyoracle
+
+K, NITER, GE = 4, 3, 0.1
+d = make_dataset("C4", nbcs=80, nsnps=600, rbar=80, nv=4)
+plp = pyoracle.fmx_pileup(d["read_ptr"], d["al"], d["bq"], 0.5)
+
+
+class OracleEngine:   # numpy stand-in with the FreemuxEngine methods the driver uses (CPU box: no GPU)
+    def __init__(self):
+        self.stats = torch.zeros(K * d["nsnps"] * 12, dtype=torch.float64)
+        self.assign = torch.full((d["nbcs"],), -1, dtype=torch.int32)
+    def set_shard(self, cb, ce, sb, se):
+        self.cb, self.ce, self.sb, self.se = cb, ce, sb, se
+    def _clust(self):
+        s = self.stats.numpy().reshape(K, d["nsnps"], 12)
+        c = np.zeros((K, d["nsnps"]), pyoracle.PILEUP_DTYPE)
+        c["gls"] = s[..., :9]
+        c["nreads"], c["nref"], c["nalt"] = s[..., 9], s[..., 10], s[..., 11]
+        return c
+    def mstep_dev(self):
+        c = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], plp, self.assign.numpy(), K, d["nsnps"])
+        s = np.zeros((K, d["nsnps"], 12))
+        s[:, self.sb:self.se, :9] = c["gls"][:, self.sb:self.se]
+        for i, f in enumerate(("nreads", "nref", "nalt")):
+            s[:, self.sb:self.se, 9 + i] = c[f][:, self.sb:self.se]
+        self.stats.copy_(torch.from_numpy(s.reshape(-1)))
+    def estep_dev(self, apply):
+        res, _ = pyoracle.fmx_estep(d["cell_ptr"], d["snp_idx"], plp, d["af"], self._clust(), 0.5, GE, apply)
+        self.res = res[self.cb:self.ce]
+        a = np.where(self.res["type"] == 0, self.res["jBest"], -1).astype(np.int32)
+        self.assign[self.cb:self.ce] = torch.from_numpy(a)
+    def download_results(self):
+        return self.res
+
+
+dist.init_process_group("gloo")
+world = dist.get_world_size()
+rng = np.random.default_rng(1)
+init = (d["s1"] %% K).astype(np.int32)
+init[rng.random(len(init)) < 0.4] = -1
+eng = OracleEngine()
+local, full = run_em_distributed(eng, eng.stats, eng.assign, balanced_ranges(d["cell_ptr"], world),
+                                 snp_slabs(d["snp_idx"], d["nsnps"], world), init, niter=NITER)
+# single-process reference loop
+clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], plp, init, K, d["nsnps"])
+for it in range(NITER):
+    ref, _ = pyoracle.fmx_estep(d["cell_ptr"], d["snp_idx"], plp, d["af"], clust, 0.5, GE, it + 1 == NITER)
+    a = np.where(ref["type"] == 0, ref["jBest"], -1).astype(np.int32)
+    clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], plp, a, K, d["nsnps"])
+assert np.array_equal(full, ref), "sharded EM differs from the single-process loop"
+assert np.array_equal(eng._clust()["gls"], clust["gls"]), "all-reduced statistics differ"
+dist.barrier()
+dist.destroy_process_group()
+print("rank ok")
+"""
+
+
+def test_world_size_2_gloo_freemuxlet_em(tmp_path):
+    """The multi-GPU EM driver (barcode-sharded E-step, SNP-slab M-step, all-reduce of the statistics)
+    over gloo with an oracle-backed stand-in engine: bitwise equal to the single-process loop."""
+    script = tmp_path / "fmx_worker.py"
+    script.write_text(_FMX_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29714", str(script)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("rank ok") == 2
