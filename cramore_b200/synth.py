@@ -39,7 +39,7 @@ def make_genotypes(rng, nsnps, nv):
     af = rng.uniform(0.05, 0.5, nsnps)
     geno = rng.binomial(2, af[:, None], size=(nsnps, nv)).astype(np.int8)
     gp = np.full((nsnps, nv, 3), np.float32(0.01), np.float32)
-    np.put_along_axis(gp, geno[:, :, None].astype(np.int64), np.float32(0.98), axis=2)
+    np.put_along_axis(gp, geno[:, :, None].astype(np.int64), np.float32(0.98), axis=2)  # the VCF's GP values
     s = (gp[:, :, 0] + gp[:, :, 1]) + gp[:, :, 2]  # float accumulation order of :478-480
     gp /= s[:, :, None]
     return af, geno, gp
@@ -127,7 +127,7 @@ def make_dataset(name="C1", nbcs=None, nsnps=None, nv=None, rbar=None, seed=None
     af, geno, gp = make_genotypes(rng_g, cfg["nsnps"], cfg["nv"])
     rng_d = np.random.Generator(np.random.Philox(key=seed + 7919 * (1 + droplet_seed_offset)))
     d = make_droplets(rng_d, geno, cfg["nbcs"], cfg["rbar"], cfg["doublet_rate"])
-    d.update(name=name, cfg=cfg, seed=seed, gp=gp, af=af,
+    d.update(name=name, cfg=cfg, seed=seed, gp=gp, af=af, geno=geno,
              snp_err=np.full(cfg["nsnps"], geno_error_offset, np.float64),
              alphas=np.asarray(cfg["alphas"], np.float64), nv=cfg["nv"], nsnps=cfg["nsnps"], nbcs=cfg["nbcs"],
              sample_ids=["SM%03d" % i for i in range(cfg["nv"])])
@@ -142,3 +142,75 @@ def algorithmic_flops_per_entry(nv, alphas):
     has_half = any(a == 0.5 for a in alphas)
     n_llk = nv + nv * (nv - 1) * (nA - 1) - (nv * (nv - 1) // 2 if has_half else 0)
     return 8 * n_llk + 18 * nv * nA
+
+
+# ---------------------------------------------------------------------------------------------
+# on-disk forms of a dataset: digital pileup (.cel.gz/.var.gz/.plp.gz) + VCF
+# ---------------------------------------------------------------------------------------------
+def plp_read_order(d):
+    """Index array `o` such that reads[o] is the order in which the reads were numbered by the global
+    hex counter of load_from_plp (sc_drop_seq.cpp:365), i.e. the order they must appear in .plp.gz.
+    The CSR keeps each entry's reads in std::map order of that counter's hex string."""
+    rp = np.asarray(d["read_ptr"], np.int64)
+    R = int(rp[-1])
+    o = np.arange(R, dtype=np.int64)
+    cnt = np.diff(rp)
+    for e in np.nonzero(cnt > 1)[0]:
+        c = np.arange(rp[e], rp[e + 1], dtype=np.int64)  # counters of this entry (consecutive)
+        left, nd = _hex_order_key(c)
+        perm = np.lexsort((nd, left))                    # CSR position j holds counter c[perm[j]]
+        o[c[perm]] = c
+    return o
+
+
+def write_plp(d, prefix, chrom="1"):
+    """Writes <prefix>.cel.gz/.var.gz/.plp.gz in the dsc-pileup format read by load_from_plp
+    (sc_drop_seq.cpp:103-384; writer side: cmd_cram_dsc_pileup.cpp:438-523)."""
+    import gzip
+    cp, rp = np.asarray(d["cell_ptr"], np.int64), np.asarray(d["read_ptr"], np.int64)
+    nbcs = len(cp) - 1
+    bcs = d.get("barcodes") or ["BC%07d-1" % i for i in range(nbcs)]
+    nread_cell = rp[cp[1:]] - rp[cp[:-1]]
+    with gzip.open(prefix + ".cel.gz", "wt", compresslevel=1) as f:
+        f.write("#DROPLET_ID\tBARCODE\tNUM.READ\tNUM.UMI\tNUM.UMIwSNP\tNUM.SNP\n")
+        for i in range(nbcs):
+            f.write("%d\t%s\t%d\t%d\t%d\t%d\n" % (i, bcs[i], nread_cell[i], nread_cell[i], nread_cell[i],
+                                                   cp[i + 1] - cp[i]))
+    with gzip.open(prefix + ".var.gz", "wt", compresslevel=1) as f:
+        f.write("#SNP_ID\tCHROM\tPOS\tREF\tALT\tAF\n")
+        for s in range(d["nsnps"]):
+            f.write("%d\t%s\t%d\tA\tG\t%.5f\n" % (s, chrom, 1000 + 10 * s, d["af"][s]))
+    order = plp_read_order(d)
+    al = np.asarray(d["al"])[order]
+    bq = np.asarray(d["bq"])[order]
+    alc = (al + ord("0")).astype(np.uint8).tobytes().decode("ascii")
+    bqc = (bq + 33).astype(np.uint8).tobytes().decode("ascii")
+    si = np.asarray(d["snp_idx"])
+    with gzip.open(prefix + ".plp.gz", "wt", compresslevel=1) as f:
+        f.write("#DROPLET_ID\tSNP_ID\tALLELES\tBASEQS\n")
+        for c in range(nbcs):
+            for e in range(cp[c], cp[c + 1]):
+                f.write("%d\t%d\t%s\t%s\n" % (c, si[e], alc[rp[e]:rp[e + 1]], bqc[rp[e]:rp[e + 1]]))
+    return bcs
+
+
+def write_vcf(d, path, chrom="1", with_r2=False):
+    """Text VCF with GT:GP per sample: the un-normalised GP triple (0.98 on the genotype, 0.01 elsewhere)
+    that BCFFilteredReader::parse_posteriors (bcf_filtered_reader.cpp:457-499) float-normalises into d["gp"]."""
+    import gzip
+    opener = gzip.open if path.endswith(".gz") else open
+    gts = ["0/0", "0/1", "1/1"]
+    gps = ["0.98,0.01,0.01", "0.01,0.98,0.01", "0.01,0.01,0.98"]
+    cols = [gts[g] + ":" + gps[g] for g in range(3)]
+    with opener(path, "wt") as f:
+        f.write("##fileformat=VCFv4.2\n##contig=<ID=%s>\n" % chrom)
+        f.write('##INFO=<ID=R2,Number=1,Type=Float,Description="imputation r2">\n')
+        f.write('##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">\n')
+        f.write('##FORMAT=<ID=GP,Number=G,Type=Float,Description="Genotype posterior">\n')
+        f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(d["sample_ids"]) + "\n")
+        geno = np.asarray(d["geno"])
+        for s in range(d["nsnps"]):
+            info = "R2=0.9" if with_r2 else "."
+            f.write("%s\t%d\t.\tA\tG\t.\tPASS\t%s\tGT:GP\t" % (chrom, 1000 + 10 * s, info))
+            f.write("\t".join(cols[g] for g in geno[s]))
+            f.write("\n")

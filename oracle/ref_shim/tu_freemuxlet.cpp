@@ -1,0 +1,3 @@
+// The reference's freemuxlet driver, compiled from where it lies against the I/O shim.
+#include "shim_decls.h"
+#include "cmd_cram_freemuxlet.cpp"

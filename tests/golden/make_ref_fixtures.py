@@ -1,0 +1,142 @@
+"""Generates tests/golden/ref_*.json: outputs of the REFERENCE's own compiled likelihood code
+(oracle/_ref/ref_cramore = /root/reference/cmd_cram_demuxlet.cpp, cmd_cram_freemuxlet.cpp,
+sc_drop_seq.cpp, ... compiled unmodified against the zlib I/O shim in oracle/ref_shim/) on synthetic
+digital-pileup + VCF inputs written by cramore_b200.synth.  Runs only where /root/reference exists
+(`make -C oracle ref` first).  Inputs are not stored: every case is re-created from its seed; the
+fixture holds the case parameters and every value the reference passed to hprintf at full precision
+(REF_SHIM_RAW=1 side files)."""
+import gzip
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from cramore_b200.synth import make_dataset, write_plp, write_vcf  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_cramore")
+
+DEMUX_CASES = {
+    "demux_c1_small": dict(ds=dict(name="C1", nbcs=60, nsnps=400, rbar=60), alphas=None, args=[]),
+    "demux_grid_deep": dict(ds=dict(name="C1", nbcs=30, nsnps=200, rbar=90, nv=5, seed=77),
+                            alphas=[0, 0.1, 0.2, 0.3, 0.4, 0.5], args=["--doublet-prior", "0.3"]),
+    "demux_missing_gp_r2": dict(ds=dict(name="C1", nbcs=40, nsnps=300, rbar=50, nv=6, seed=99), alphas=[0, 0.25, 0.5],
+                                args=["--geno-error-offset", "0.05", "--geno-error-coeff", "0.5"], drop_every=7,
+                                with_r2=True),
+}
+FMX_CASES = {
+    "fmx_k4": dict(ds=dict(name="C4", nbcs=80, nsnps=600, rbar=80, nv=4), K=4, args=["--geno-error", "0.1"]),
+    "fmx_k3_noerr": dict(ds=dict(name="C4", nbcs=50, nsnps=400, rbar=60, nv=3, seed=5), K=3, args=[]),
+}
+
+
+def dataset(spec):
+    ds = dict(spec["ds"])
+    return make_dataset(ds.pop("name"), with_barcodes=True, **ds)
+
+
+def read_raw(path):
+    rows = []
+    for line in open(path):
+        line = line.rstrip("\n")
+        if line:
+            rows.append(line.split("\t"))
+    return rows
+
+
+def run(args, cwd):
+    env = dict(os.environ, REF_SHIM_RAW="1")
+    r = subprocess.run([REF] + args, capture_output=True, text=True, env=env, cwd=cwd)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr[-3000:])
+
+
+def init_clusters(d, K):
+    """Deterministic --init-cluster file content: the simulated sample for most droplets."""
+    rng = np.random.default_rng(17)
+    a = (d["s1"] % K).astype(int)
+    a[d["is_dbl"]] = -1
+    a[rng.random(len(a)) < 0.25] = -1
+    return a
+
+
+def main():
+    if not os.path.exists(REF):
+        raise SystemExit("build oracle/_ref first: make -C oracle ref (needs /root/reference)")
+    for name, spec in DEMUX_CASES.items():
+        d = dataset(spec)
+        with tempfile.TemporaryDirectory() as tmp:
+            write_plp(d, os.path.join(tmp, "in"))
+            dv = d
+            if spec.get("drop_every"):
+                keep = np.arange(d["nsnps"]) % spec["drop_every"] != 0
+                lines = open_vcf_lines(d, tmp, spec.get("with_r2", False))
+                with open(os.path.join(tmp, "in.vcf"), "w") as f:
+                    snp = 0
+                    for ln in lines:
+                        if ln.startswith("#"):
+                            f.write(ln)
+                        else:
+                            if keep[snp]:
+                                f.write(ln)
+                            snp += 1
+            else:
+                write_vcf(dv, os.path.join(tmp, "in.vcf"), with_r2=spec.get("with_r2", False))
+            args = ["demuxlet", "--plp", "in", "--vcf", "in.vcf", "--field", "GP", "--out", "out"] + spec["args"]
+            for a in (spec["alphas"] or []):
+                args += ["--alpha", repr(float(a))]
+            run(args, tmp)
+            best = open(os.path.join(tmp, "out.best")).read()
+            raw = read_raw(os.path.join(tmp, "out.best.raw"))
+        json.dump({"case": name, "spec": spec, "best_text": best, "best_raw": raw},
+                  open(os.path.join(HERE, "ref_%s.json" % name), "w"))
+        print(name, len(raw), "rows")
+    for name, spec in FMX_CASES.items():
+        d = dataset(spec)
+        K = spec["K"]
+        with tempfile.TemporaryDirectory() as tmp:
+            bcs = write_plp(d, os.path.join(tmp, "in"))
+            init = init_clusters(d, K)
+            with open(os.path.join(tmp, "init.txt"), "w") as f:
+                for b, c in zip(bcs, init):
+                    f.write("%s\t%d\n" % (b, c))
+            args = ["freemuxlet", "--plp", "in", "--out", "out", "--nsample", str(K), "--init-cluster", "init.txt",
+                    "--iter-init", "0", "--keep-init-missing"] + spec["args"]
+            run(args, tmp)
+            out = {"case": name, "spec": spec, "init": init.tolist(),
+                   "lmix_raw": read_raw(os.path.join(tmp, "out.lmix.raw")),
+                   "samples_raw": read_raw(os.path.join(tmp, "out.clust1.samples.gz.raw")),
+                   "samples_text": gzip.open(os.path.join(tmp, "out.clust1.samples.gz"), "rt").read(),
+                   "vcf_sites": vcf_sites(read_raw(os.path.join(tmp, "out.clust1.vcf.gz.raw")), K)}
+        json.dump(out, open(os.path.join(HERE, "ref_%s.json" % name), "w"))
+        print(name, len(out["samples_raw"]), "rows")
+
+
+def vcf_sites(raw, K, limit=60):
+    """clust1.vcf.gz as hprintf saw it (cmd_cram_freemuxlet.cpp:670-704): per site one call with
+    (chrom, pos, ref, alt, af) followed by K calls with (gt1, gt2, gq, dp, nref, nalt, pl0..2, gp0..2)."""
+    sites = []
+    i = 0
+    while i < len(raw) and len(sites) < limit:
+        if len(raw[i]) == 5 and all(len(r) == 12 for r in raw[i + 1:i + 1 + K]):
+            sites.append({"pos": int(raw[i][1]), "af": float(raw[i][4]),
+                          "clusters": [[float(x) for x in r] for r in raw[i + 1:i + 1 + K]]})
+            i += 1 + K
+        else:
+            i += 1
+    return sites
+
+
+def open_vcf_lines(d, tmp, with_r2):
+    p = os.path.join(tmp, "full.vcf")
+    write_vcf(d, p, with_r2=with_r2)
+    return open(p).readlines()
+
+
+if __name__ == "__main__":
+    main()
