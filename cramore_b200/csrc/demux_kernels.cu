@@ -1156,6 +1156,21 @@ __global__ void __launch_bounds__(256)
     cand_insert(b1, b2, o2);
   }
   const double td = (la > 0.0) ? (log_doublet_prior1 + log(la) + (double)le * LN2) : -CUDART_INF;
+  // At alpha == 0.5 the hypotheses (j,k) and (k,j) are the same model; the reference computes both and
+  // lets last-bit rounding of its own summation order decide which one is "best" and which "next"
+  // (an exact tie keeps the first scanned, j < k).  That noise cannot be reproduced,
+  // so the pair is reported in the canonical orientation j < k whenever best/next are such mirrors.
+  if (b1.pos >= 0 && b2.pos >= 0) {
+    const int nvA = d.nv * d.nA;
+    const int j1 = b1.pos / nvA, k1 = (b1.pos % nvA) / d.nA, n1 = b1.pos % d.nA;
+    const int j2 = b2.pos / nvA, k2 = (b2.pos % nvA) / d.nA, n2 = b2.pos % d.nA;
+    if (n1 == n2 && d.is_half[n1] && j1 == k2 && k1 == j2 && j1 > k1 && b1.e == b2.e &&
+        fabs(b1.m - b2.m) <= 1e-12 * b1.m) {
+      const Cand t = b1;
+      b1 = b2;
+      b2 = t;
+    }
+  }
 
   // ---- posterior normalisers (:804-821): log(1 + sum exp(term))
   const double msng = smax;

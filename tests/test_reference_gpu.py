@@ -43,9 +43,13 @@ def test_engine_demuxlet_equals_reference(engine, name):
         assert ids[calls["jBest"][c]] in (r["best1"], r["best2"])
         row = best_row(rank, d["barcodes"][c], int(cp[c + 1] - cp[c]), int(rp[cp[c + 1]] - rp[cp[c]]), res[c], d["nv"],
                        alphas, prior, ids)
+        if row != lines[1 + rank]:
+            # the only admissible textual difference: the reference's rounding noise chose the non-canonical
+            # orientation (j > k) of an alpha = 0.5 pair (every number was compared above)
+            assert r["dBestAlpha"] == 0.5 and mine_d == theirs_d[::-1] and \
+                d["sample_ids"].index(r["dBest1"]) > d["sample_ids"].index(r["dBest2"]), (name, c, row, lines[1 + rank])
         n_text_equal += (row == lines[1 + rank])
-    # the printed rows (2-decimal LLKs) agree with the reference's .best except for alpha=0.5 orientation noise
-    assert n_text_equal >= 0.8 * d["nbcs"], (n_text_equal, d["nbcs"])
+    assert n_text_equal >= 0.6 * d["nbcs"], (n_text_equal, d["nbcs"])
 
 
 @pytest.mark.parametrize("name", refcase.FMX_CASES)
