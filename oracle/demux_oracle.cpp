@@ -11,8 +11,8 @@
  * lines (this file must be compiled like the reference: -O3, no -march=native,
  * -ffp-contract=off, so no FMA contraction).
  *
- * PARITY: unpinned for the engine (no reference fixtures exist, reference not
- * buildable without htslib); Phred tables pinned against oracle/_ref.
+ * PARITY: pinned against oracle/_ref/ref_cramore (the reference's own sources compiled behind the
+ * oracle/ref_shim I/O stand-ins) through tests/golden/ref_*.json -- see oracle.h.
  */
 #include "oracle.h"
 

@@ -10,7 +10,8 @@
  * The reference keeps cluster pileups in std::map and default-constructs
  * missing entries (gls == 1, sc_drop_seq.h:72-75); here the K x nsnps array is
  * dense and starts in that default state, which is equivalent.
- * PARITY: unpinned (no reference fixtures, reference not buildable here).
+ * PARITY: pinned against oracle/_ref/ref_cramore (the reference's own sources compiled behind the
+ * oracle/ref_shim I/O stand-ins) through tests/golden/ref_*.json -- see oracle.h.
  */
 #include "oracle.h"
 
