@@ -1,0 +1,270 @@
+// cmd_demuxlet.cpp -- `cramore demuxlet` on the B200 engine: the command-line surface and output files of
+// cmdCramDemuxlet (cmd_cram_demuxlet.cpp:6-1060) for the --plp path.  Ingestion is host C++ (host_io.h);
+// everything between "ingestion finished" (:425) and "row printed" (:993) runs in libcramore_cuda.so.
+// The --sam path needs htslib's BAM/CRAM decoder, which this build does not link: it is rejected with an error.
+#include <thread>
+
+#include "cli_params.h"
+#include "cramore_cuda.h"
+#include "host_io.h"
+
+using namespace hostio;
+
+namespace {
+
+void dump_vec(const std::string& fn, const void* p, size_t bytes) {
+  FILE* f = fopen(fn.c_str(), "wb");
+  if (!f) fatal("Cannot write %s", fn.c_str());
+  if (bytes) fwrite(p, 1, bytes, f);
+  fclose(f);
+}
+
+std::vector<int> parse_devices(const std::string& s) {
+  std::vector<int> v;
+  size_t p = 0;
+  while (p < s.size()) {
+    size_t e = s.find(',', p);
+    if (e == std::string::npos) e = s.size();
+    v.push_back(atoi(s.substr(p, e - p).c_str()));
+    p = e + 1;
+  }
+  if (v.empty()) v.push_back(0);
+  return v;
+}
+
+}  // namespace
+
+int cmdDemuxlet(int argc, char** argv) {
+  // defaults of cmd_cram_demuxlet.cpp:7-36
+  std::string samFile, tagGroup("CB"), tagUMI("UB"), plpPrefix, vcfFile, field("GP"), r2Info("R2"), smList, outPrefix,
+      groupList, gpuDevices("0"), dumpPrefix;
+  double genoErrorOffset = 0.10, genoErrorCoeffR2 = 0.00, minCallRate = 0.5, doublet_prior = 0.5;
+  int32_t minMAC = 1, samVerbose = 1000000, vcfVerbose = 10000, capBQ = 20, minBQ = 13, minMQ = 20, minTD = 0,
+          exclFlag = 0x0f04, minTotalReads = 0, minUMIs = 0, minCoveredSNPs = 0;
+  std::vector<std::string> smIDs;
+  std::vector<double> gridAlpha;
+
+  cli::Params pl;
+  pl.group("Options for input SAM/BAM/CRAM");
+  pl.add("sam", &samFile, "Input SAM/BAM/CRAM file. Must be sorted by coordinates and indexed");
+  pl.add("tag-group", &tagGroup, "Tag representing readgroup or cell barcodes, in the case to partition the BAM file into multiple groups. For 10x genomics, use CB");
+  pl.add("tag-UMI", &tagUMI, "Tag representing UMIs. For 10x genomiucs, use UB");
+  pl.group("Options for input Pileup format");
+  pl.add("plp", &plpPrefix, "Input pileup format");
+  pl.group("Options for input VCF/BCF");
+  pl.add("vcf", &vcfFile, "Input VCF/BCF file, containing the individual genotypes (GT), posterior probability (GP), or genotype likelihood (PL)");
+  pl.add("field", &field, "FORMAT field to extract the genotype, likelihood, or posterior from");
+  pl.add("geno-error-offset", &genoErrorOffset, "Offset of genotype error rate. [error] = [offset] + [1-offset]*[coeff]*[1-r2]");
+  pl.add("geno-error-coeff", &genoErrorCoeffR2, "Slope of genotype error rate. [error] = [offset] + [1-offset]*[coeff]*[1-r2]");
+  pl.add("r2-info", &r2Info, "INFO field name representing R2 value. Used for representing imputation quality");
+  pl.add("min-mac", &minMAC, "Minimum minor allele frequency");
+  pl.add("min-callrate", &minCallRate, "Minimum call rate");
+  pl.add("sm", &smIDs, "List of sample IDs to compare to (default: use all)");
+  pl.add("sm-list", &smList, "File containing the list of sample IDs to compare");
+  pl.group("Output Options");
+  pl.add("out", &outPrefix, "Output file prefix");
+  pl.add("alpha", &gridAlpha, "Grid of alpha to search for (default is 0.1, 0.2, 0.3, 0.4, 0.5)");
+  pl.add("doublet-prior", &doublet_prior, "Prior of doublet");
+  pl.add("sam-verbose", &samVerbose, "Verbose message frequency for SAM/BAM/CRAM");
+  pl.add("vcf-verbose", &vcfVerbose, "Verbose message frequency for VCF/BCF");
+  pl.group("Read filtering Options");
+  pl.add("cap-BQ", &capBQ, "Maximum base quality (higher BQ will be capped)");
+  pl.add("min-BQ", &minBQ, "Minimum base quality to consider (lower BQ will be skipped)");
+  pl.add("min-MQ", &minMQ, "Minimum mapping quality to consider (lower MQ will be ignored)");
+  pl.add("min-TD", &minTD, "Minimum distance to the tail (lower will be ignored)");
+  pl.add("excl-flag", &exclFlag, "SAM/BAM FLAGs to be excluded");
+  pl.group("Cell/droplet filtering options");
+  pl.add("group-list", &groupList, "List of tag readgroup/cell barcode to consider in this run. All other barcodes will be ignored. This is useful for parallelized run");
+  pl.add("min-total", &minTotalReads, "Minimum number of total reads for a droplet/cell to be considered");
+  pl.add("min-umi", &minUMIs, "Minimum number of UMIs for a droplet/cell to be considered");
+  pl.add("min-snp", &minCoveredSNPs, "Minimum number of SNPs with coverage for a droplet/cell to be considered");
+  pl.group("GPU engine options (additions of this build)");
+  pl.add("gpu-devices", &gpuDevices, "Comma-separated CUDA device ids; droplets are sharded across them");
+  pl.add("gpu-dump-inputs", &dumpPrefix, "Write the flattened engine inputs to PREFIX.* and exit without touching a GPU");
+  if (!pl.read(argc, argv)) return 1;
+
+  if (gridAlpha.empty()) {  // :85-89
+    gridAlpha.push_back(0);
+    gridAlpha.push_back(0.5);
+  }
+  const int32_t nAlpha = (int32_t)gridAlpha.size();
+  if (!samFile.empty()) {
+    if (!plpPrefix.empty()) fatal("with --plp option, neither --sam option cannot be used");
+    fatal("--sam needs htslib's BAM/CRAM reader, which this build does not include; run `cramore dsc-pileup` "
+          "once and pass its output with --plp");
+  }
+  if (plpPrefix.empty() || vcfFile.empty() || outPrefix.empty()) fatal("Missing required option(s) : --plp, --vcf, --out");
+
+  std::set<std::string> sm_ids(smIDs.begin(), smIDs.end());
+  if (!smList.empty()) {
+    LineReader lr(smList);
+    while (lr.read_fields() > 0) sm_ids.insert(lr.fields[0]);
+  }
+  VcfReader vr(vcfFile, sm_ids);
+  vr.minMAC = minMAC;
+  vr.minCallRate = minCallRate;
+  vr.maxAlleles = 2;
+  const int32_t nv = vr.nsamples();
+
+  PlpFilters flt;
+  flt.minRead = minTotalReads;
+  flt.minUMI = minUMIs;
+  flt.minSNP = minCoveredSNPs;
+  flt.capBQ = capBQ;
+  flt.minBQ = minBQ;
+  if (!groupList.empty()) {
+    LineReader lr(groupList);
+    while (lr.read_fields() > 0) flt.valid_bcs.insert(lr.fields[0]);
+    notice("Loaded %zu valid barcodes from %s", flt.valid_bcs.size(), groupList.c_str());
+  }
+
+  // ---- .var.gz x VCF join, sc_drop_seq.cpp:108-116 and :226-330 ----
+  if (!vr.read()) fatal("Cannot read any single variant from %s", vcfFile.c_str());
+  std::vector<float> gp_f32;
+  std::vector<double> snp_err;
+  std::vector<uint8_t> has_gp;
+  std::vector<float> tmp_gp(nv * 3);
+  DropletStore st;
+  load_plp(plpPrefix, flt, st, [&](int32_t /*idx*/, const char* chr, const SnpInfo& s) {
+    bool found = false, passed = false;
+    while (!(found || passed)) {
+      if (vr.eof) passed = true;
+      else if (vr.cur.rid > s.rid) passed = true;
+      else if (vr.cur.rid == s.rid) {
+        if (vr.cur.pos1 > s.pos) passed = true;
+        else if (vr.cur.pos1 == s.pos) {
+          if (vr.cur.ref[0] != s.ref || vr.cur.alt[0] != s.alt) passed = true;
+          else found = true;
+        }
+      }
+      if (passed || found) break;
+      vr.read();
+    }
+    gp_f32.resize(gp_f32.size() + (size_t)nv * 3, 0.0f);
+    if (found) {
+      if (!vr.parse_posteriors(field.c_str(), 0, tmp_gp.data()))
+        fatal("Cannot parse posterior probability at %s:%d", chr, s.pos);
+      memcpy(&gp_f32[gp_f32.size() - (size_t)nv * 3], tmp_gp.data(), sizeof(float) * nv * 3);
+      double err = genoErrorOffset;  // :298-306
+      if (genoErrorCoeffR2 > 0) {
+        float r2;
+        if (!vr.info_float(r2Info.c_str(), &r2))
+          fatal("Cannot extract %s (1 float value) from INFO field at %s:%d. Cannot use --geno-error-coeff", r2Info.c_str(), chr, s.pos);
+        err += (1 - genoErrorOffset) * (1 - r2) * genoErrorCoeffR2;
+      }
+      snp_err.push_back(err);  // clamped to [0, 0.999] by the engine (:308-309)
+      has_gp.push_back(1);
+    } else {
+      snp_err.push_back(0.0);
+      has_gp.push_back(0);  // SNP kept without genotypes: sc_snp_t::gps == NULL (:278-282)
+    }
+  });
+  notice("Finished reading %lld variants from %s (%lld skipped by the variant filter)", (long long)vr.nRead, vcfFile.c_str(),
+         (long long)vr.nSkip);
+
+  // ---- droplets that produce a row, in std::map barcode order (:636-653) ----
+  const int32_t nbcs = st.nbcs();
+  std::vector<int32_t> order(nbcs);
+  for (int32_t i = 0; i < nbcs; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return st.bcs[a] < st.bcs[b]; });
+  std::vector<int32_t> row_cell, row_int_id;
+  for (int32_t rank = 0; rank < nbcs; ++rank) {
+    const int32_t i = order[rank];
+    const int32_t ns = (int32_t)(st.cell_ptr[i + 1] - st.cell_ptr[i]);
+    if (st.totl_reads[i] < minTotalReads || st.uniq_reads[i] < minUMIs || ns < minCoveredSNPs) continue;
+    if (ns == 0) continue;
+    row_cell.push_back(i);
+    row_int_id.push_back(rank);
+  }
+  // CSR of those droplets, in row order
+  std::vector<int64_t> cell_ptr(1, 0), read_ptr(1, 0);
+  std::vector<int32_t> snp_idx;
+  std::vector<uint8_t> al, bq;
+  for (int32_t i : row_cell) {
+    for (int64_t e = st.cell_ptr[i]; e < st.cell_ptr[i + 1]; ++e) {
+      snp_idx.push_back(st.snp_idx[e]);
+      al.insert(al.end(), st.al.begin() + st.read_ptr[e], st.al.begin() + st.read_ptr[e + 1]);
+      bq.insert(bq.end(), st.bq.begin() + st.read_ptr[e], st.bq.begin() + st.read_ptr[e + 1]);
+      read_ptr.push_back((int64_t)al.size());
+    }
+    cell_ptr.push_back((int64_t)snp_idx.size());
+  }
+  const int64_t nrows = (int64_t)row_cell.size();
+
+  if (!dumpPrefix.empty()) {  // test hook: the flattened inputs, bit for bit
+    dump_vec(dumpPrefix + ".cell_ptr.i64", cell_ptr.data(), cell_ptr.size() * 8);
+    dump_vec(dumpPrefix + ".snp_idx.i32", snp_idx.data(), snp_idx.size() * 4);
+    dump_vec(dumpPrefix + ".read_ptr.i64", read_ptr.data(), read_ptr.size() * 8);
+    dump_vec(dumpPrefix + ".al.u8", al.data(), al.size());
+    dump_vec(dumpPrefix + ".bq.u8", bq.data(), bq.size());
+    dump_vec(dumpPrefix + ".gp.f32", gp_f32.data(), gp_f32.size() * 4);
+    dump_vec(dumpPrefix + ".snp_err.f64", snp_err.data(), snp_err.size() * 8);
+    dump_vec(dumpPrefix + ".has_gp.u8", has_gp.data(), has_gp.size());
+    dump_vec(dumpPrefix + ".row_int_id.i32", row_int_id.data(), row_int_id.size() * 4);
+    Writer w(dumpPrefix + ".barcodes.txt", false);
+    for (int32_t i : row_cell) w.printf("%s\n", st.bcs[i].c_str());
+    notice("Wrote engine inputs for %lld droplets to %s.*", (long long)nrows, dumpPrefix.c_str());
+    return 0;
+  }
+
+  // ---- engine: one handle per GPU, contiguous row ranges balanced by entry count ----
+  notice("Starting to identify best matching individual IDs");
+  const std::vector<int> devs = parse_devices(gpuDevices);
+  const int ndev = (int)devs.size();
+  std::vector<ccu_demux_result> res(nrows);
+  std::vector<int64_t> cut(ndev + 1, nrows);
+  cut[0] = 0;
+  for (int d = 1; d < ndev; ++d) {
+    const int64_t target = cell_ptr[nrows] * d / ndev;
+    cut[d] = std::lower_bound(cell_ptr.begin(), cell_ptr.end(), target) - cell_ptr.begin();
+    cut[d] = std::min<int64_t>(std::max(cut[d], cut[d - 1]), nrows);
+  }
+  std::vector<std::string> errs(ndev);
+  auto work = [&](int d) {
+    ccu_handle* h = NULL;
+    if (ccu_create(devs[d], &h)) {
+      errs[d] = ccu_last_error(NULL);
+      return;
+    }
+    const int64_t b = cut[d], e = cut[d + 1];
+    std::vector<int64_t> cp(cell_ptr.begin() + b, cell_ptr.begin() + e + 1), rp;
+    const int64_t e0 = cp.front(), e1 = cp.back();
+    for (auto& x : cp) x -= e0;
+    rp.assign(read_ptr.begin() + e0, read_ptr.begin() + e1 + 1);
+    const int64_t r0 = rp.front();
+    for (auto& x : rp) x -= r0;
+    if (ccu_demux_configure(h, nv, nAlpha, gridAlpha.data(), doublet_prior) ||
+        ccu_demux_set_genotypes(h, st.nsnps(), gp_f32.data(), snp_err.data(), has_gp.data()) ||
+        ccu_demux_score(h, e - b, cp.data(), snp_idx.data() + e0, rp.data(), al.data() + r0, bq.data() + r0, res.data() + b))
+      errs[d] = ccu_last_error(h);
+    ccu_destroy(h);
+  };
+  if (ndev == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int d = 0; d < ndev; ++d) th.emplace_back(work, d);
+    for (auto& t : th) t.join();
+  }
+  for (int d = 0; d < ndev; ++d)
+    if (!errs[d].empty()) fatal("%s", errs[d].c_str());
+
+  // ---- <out>.best: header :629, rows :993 ----
+  Writer wbest(outPrefix + ".best", false);
+  const char* hdr = ccu_demux_best_header();
+  wbest.write(hdr, (int)strlen(hdr));
+  std::vector<const char*> ids(nv);
+  for (int32_t j = 0; j < nv; ++j) ids[j] = vr.sample_id(j);
+  char row[8192];
+  for (int64_t r = 0; r < nrows; ++r) {
+    const int32_t i = row_cell[r];
+    const int n = ccu_demux_best_row(row, sizeof(row), row_int_id[r], st.bcs[i].c_str(),
+                                     (uint32_t)(st.cell_ptr[i + 1] - st.cell_ptr[i]), st.uniq_reads[i], &res[r], nv, nAlpha,
+                                     gridAlpha.data(), doublet_prior, ids.data());
+    if (n < 0) fatal("cannot format the row of droplet %s", st.bcs[i].c_str());
+    wbest.write(row, n);
+  }
+  wbest.close();
+  notice("Finished writing output files");
+  return 0;
+}

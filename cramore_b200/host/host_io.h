@@ -1,0 +1,540 @@
+// host_io.h -- host-side ingestion of the `--plp` path, flat and allocation-light: the digital pileup
+// (.cel.gz/.var.gz/.plp.gz, format of cmd_cram_dsc_pileup.cpp:438-523) and a text VCF are turned directly
+// into the CSR droplet store + float genotype matrix the C ABI takes, with the semantics of
+// sc_dropseq_lib_t::load_from_plp (sc_drop_seq.cpp:103-384) and BCFFilteredReader
+// (bcf_filtered_reader.cpp:406-500, 571-647, 744-870).  No map-of-maps: reads are collected as flat records
+// and sorted once into the reference's iteration order.
+#pragma once
+#include <stdint.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace hostio {
+
+[[noreturn]] inline void fatal(const char* fmt, ...) {  // Error.cpp:29-43: "FATAL ERROR -" then abort
+  char buf[2048];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  fprintf(stderr, "\nFATAL ERROR - \n%s\n\n", buf);
+  throw std::runtime_error(buf);
+}
+inline void notice(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  fprintf(stderr, "NOTICE - ");
+  vfprintf(stderr, fmt, ap);
+  fprintf(stderr, "\n");
+  va_end(ap);
+}
+
+// ---- line reader over plain or gzip text, fields split on white space (tsv_reader.cpp:27-55) ----
+class LineReader {
+ public:
+  explicit LineReader(const std::string& fn) : nlines(0), fn_(fn) {
+    gz_ = gzopen(fn.c_str(), "rb");
+    if (!gz_) fatal("Cannot open file %s for reading", fn.c_str());
+    gzbuffer(gz_, 1 << 20);
+  }
+  ~LineReader() {
+    if (gz_) gzclose(gz_);
+  }
+  bool next_line() {
+    line.clear();
+    char buf[1 << 16];
+    while (gzgets(gz_, buf, sizeof(buf)) != NULL) {
+      size_t n = strlen(buf);
+      line.append(buf, n);
+      if (n > 0 && buf[n - 1] == '\n') break;
+    }
+    if (line.empty()) return false;
+    while (!line.empty() && (line.back() == '\n' || line.back() == '\r')) line.pop_back();
+    ++nlines;
+    return true;
+  }
+  // number of white-space separated fields of the next line, 0 at EOF
+  int read_fields() {
+    fields.clear();
+    if (!next_line()) return 0;
+    char* p = &line[0];
+    char* end = p + line.size();
+    while (p < end) {
+      while (p < end && isspace((unsigned char)*p)) ++p;
+      if (p >= end) break;
+      fields.push_back(p);
+      while (p < end && !isspace((unsigned char)*p)) ++p;
+      if (p < end) *p++ = '\0';
+    }
+    return (int)fields.size();
+  }
+  std::string line;
+  std::vector<char*> fields;
+  int64_t nlines;
+
+ private:
+  std::string fn_;
+  gzFile gz_;
+};
+
+// ---- gz / plain writer with printf (hts_utils.cpp:1018-1038) ----
+class Writer {
+ public:
+  Writer(const std::string& fn, bool gz) : fp_(NULL), gz_(NULL) {
+    if (gz) gz_ = gzopen(fn.c_str(), "wb");
+    else fp_ = fopen(fn.c_str(), "w");
+    if (!fp_ && !gz_) fatal("Cannot open file %s for writing", fn.c_str());
+  }
+  ~Writer() { close(); }
+  void close() {
+    if (fp_) fclose(fp_);
+    if (gz_) gzclose(gz_);
+    fp_ = NULL;
+    gz_ = NULL;
+  }
+  void printf(const char* fmt, ...) {
+    char buf[8192];
+    va_list ap;
+    va_start(ap, fmt);
+    int n = vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (n >= (int)sizeof(buf)) n = (int)sizeof(buf) - 1;
+    write(buf, n);
+  }
+  void write(const char* s, int n) {
+    if (fp_) fwrite(s, 1, n, fp_);
+    else gzwrite(gz_, s, n);
+  }
+
+ private:
+  FILE* fp_;
+  gzFile gz_;
+};
+
+// ---- text VCF reader: sequential cursor with the variant filter of cmdCramDemuxlet ----
+struct VcfRecord {
+  int32_t rid = -1, pos1 = 0;  // 1-based position
+  std::string ref, alt;
+  int32_t n_allele = 0;
+  std::string info;
+  std::vector<std::string> fmt;
+  std::vector<char*> cols;  // sample columns (pointers into line)
+  std::string line;
+};
+
+class VcfReader {
+ public:
+  std::vector<std::string> chroms, samples;
+  std::vector<int32_t> sm_icols;  // selected sample columns, in VCF order
+  int32_t minMAC = 1, maxAlleles = 2;
+  double minCallRate = 0.5;
+  int64_t nRead = 0, nSkip = 0;
+  bool eof = false;
+  VcfRecord cur;
+  std::vector<double> acs;
+  int32_t an = 0;
+
+  VcfReader(const std::string& fn, const std::set<std::string>& sm_ids) : lr_(fn) {
+    while (lr_.next_line()) {
+      const std::string& l = lr_.line;
+      if (l.compare(0, 2, "##") == 0) {
+        if (l.compare(0, 13, "##contig=<ID=") == 0) chroms.push_back(l.substr(13, l.find_first_of(",>", 13) - 13));
+        continue;
+      }
+      if (l.compare(0, 6, "#CHROM") == 0) {
+        size_t p = 0;
+        int col = 0;
+        while (p <= l.size()) {
+          size_t e = l.find('\t', p);
+          if (e == std::string::npos) e = l.size();
+          if (col >= 9) samples.push_back(l.substr(p, e - p));
+          ++col;
+          p = e + 1;
+        }
+        break;
+      }
+      fatal("Malformed VCF header in %s", fn.c_str());
+    }
+    for (int32_t i = 0; i < (int32_t)samples.size(); ++i)
+      if (sm_ids.empty() || sm_ids.count(samples[i])) sm_icols.push_back(i);
+    if (sm_icols.empty()) fatal("No sample to read from %s", fn.c_str());
+  }
+
+  int32_t nsamples() const { return (int32_t)sm_icols.size(); }
+  const char* sample_id(int32_t i) const { return samples[sm_icols[i]].c_str(); }
+
+  int chrom_id(const std::string& name) {
+    for (size_t i = 0; i < chroms.size(); ++i)
+      if (chroms[i] == name) return (int)i;
+    chroms.push_back(name);
+    return (int)chroms.size() - 1;
+  }
+
+  // BCFFilteredReader::read(): advance to the next variant passing the filter; false at EOF
+  bool read() {
+    while (lr_.next_line()) {
+      if (lr_.line.empty() || lr_.line[0] == '#') continue;
+      parse_line();
+      ++nRead;
+      bool pass = cur.n_allele <= maxAlleles;
+      if (pass && (minMAC > 0 || minCallRate > 0)) {  // vfilt.require_GT, bcf_filtered_reader.cpp:613-645
+        if (!parse_genotypes()) fatal("Cannot find the field GT from the VCF file at position %s:%d", chroms[cur.rid].c_str(), cur.pos1);
+        if (minCallRate > (double)an / (2.0 * (double)sm_icols.size())) pass = false;
+        const int32_t ac = an - (int32_t)acs[0];
+        if (ac < minMAC || an - ac < minMAC) pass = false;
+      }
+      if (pass) return true;
+      ++nSkip;
+    }
+    eof = true;
+    return false;
+  }
+
+  // posteriors of the selected samples for the current record: out[nv*3] (float, bcf_filtered_reader.h:168-170)
+  bool parse_posteriors(const char* field, double gt_error, float* out) {
+    const int32_t nv = nsamples();
+    if (cur.n_allele != 2) fatal("parse_posteriors: only biallelic sites are supported (%s:%d)", chroms[cur.rid].c_str(), cur.pos1);
+    if (strcmp(field, "GT") == 0) {  // :414-452
+      if (!parse_genotypes()) return false;
+      for (int32_t i = 0; i < nv; ++i) {
+        const int32_t a1 = gts_[2 * i], a2 = gts_[2 * i + 1];
+        const int32_t g = (a1 < 0 || a2 < 0) ? -1 : (a1 > a2 ? a1 * (a1 + 1) / 2 + a2 : a2 * (a2 + 1) / 2 + a1);
+        if (g < 0) {
+          for (int32_t j = 0, l = 0; j < 2; ++j)
+            for (int32_t k = 0; k <= j; ++k, ++l)
+              out[i * 3 + l] = (float)((j == k ? 1.0 : 2.0) * (acs[j] + 1.0 / 2) / (an + 1.0) * (acs[k] + 1.0 / 2) / (an + 1.0));
+        } else {
+          for (int32_t j = 0; j < 3; ++j) out[i * 3 + j] = (g == j) ? 1.0 - gt_error : gt_error / (3 - 1.0);
+        }
+      }
+      return true;
+    }
+    if (strcmp(field, "PL") == 0) fatal("--field PL is not supported by the text VCF reader yet (use GP or GT)");
+    const int fi = fmt_index(field);
+    if (fi < 0) return false;
+    float gpSums[3] = {1.0f / 4.0f, 2.0f / 4.0f, 1.0f / 4.0f};  // :462-468 (nalleles = 2)
+    for (int32_t i = 0; i < nv; ++i) {  // :474-485
+      const char* p = sample_field(sm_icols[i], fi);
+      float g[3];
+      for (int j = 0; j < 3; ++j) {
+        char* e;
+        g[j] = strtof(p, &e);
+        p = (*e == ',') ? e + 1 : e;
+      }
+      float sumgp = 0;
+      for (int j = 0; j < 3; ++j) sumgp += g[j];
+      for (int j = 0; j < 3; ++j) {
+        g[j] /= sumgp;
+        gpSums[j] += g[j];
+        out[i * 3 + j] = g[j];
+      }
+    }
+    for (int j = 0; j < 3; ++j) gpSums[j] /= (int32_t)(nv + 1.0);
+    for (int32_t i = 0; i < nv; ++i)  // :490-496
+      for (int j = 0; j < 3; ++j) out[i * 3 + j] = ((1.0 - gt_error) * out[i * 3 + j] + gt_error * gpSums[j]);
+    return true;
+  }
+
+  // one float INFO value; false if absent
+  bool info_float(const char* tag, float* v) const {
+    const std::string key = std::string(tag) + "=";
+    size_t p = 0;
+    while (p < cur.info.size()) {
+      size_t e = cur.info.find(';', p);
+      if (e == std::string::npos) e = cur.info.size();
+      if (cur.info.compare(p, key.size(), key) == 0) {
+        *v = strtof(cur.info.c_str() + p + key.size(), NULL);
+        return true;
+      }
+      p = e + 1;
+    }
+    return false;
+  }
+
+ private:
+  void parse_line() {
+    cur.line.swap(lr_.line);
+    std::vector<char*> f;
+    char* p = &cur.line[0];
+    f.push_back(p);
+    for (; *p; ++p)
+      if (*p == '\t') {
+        *p = '\0';
+        f.push_back(p + 1);
+      }
+    if (f.size() < 8) fatal("Malformed VCF record (%zu columns)", f.size());
+    cur.rid = chrom_id(f[0]);
+    cur.pos1 = atoi(f[1]);
+    cur.ref = f[3];
+    cur.alt = f[4];
+    cur.n_allele = (cur.alt == ".") ? 1 : 2 + (int32_t)std::count(cur.alt.begin(), cur.alt.end(), ',');
+    cur.info = f[7];
+    cur.fmt.clear();
+    cur.cols.clear();
+    if (f.size() > 9) {
+      const char* q = f[8];
+      while (true) {
+        const char* e = strchr(q, ':');
+        if (!e) {
+          cur.fmt.push_back(q);
+          break;
+        }
+        cur.fmt.push_back(std::string(q, e - q));
+        q = e + 1;
+      }
+      cur.cols.assign(f.begin() + 9, f.end());
+    }
+  }
+  int fmt_index(const char* key) const {
+    for (size_t i = 0; i < cur.fmt.size(); ++i)
+      if (cur.fmt[i] == key) return (int)i;
+    return -1;
+  }
+  const char* sample_field(int col, int idx) const {
+    const char* p = cur.cols[col];
+    for (int i = 0; i < idx; ++i) {
+      p = strchr(p, ':');
+      if (!p) return ".";
+      ++p;
+    }
+    return p;
+  }
+  // bcf_filtered_reader.cpp:198-254: allele counts over the selected samples
+  bool parse_genotypes() {
+    const int gi = fmt_index("GT");
+    if (gi < 0) return false;
+    const int32_t nv = nsamples();
+    gts_.resize(2 * nv);
+    acs.assign(cur.n_allele, 0.0);
+    an = 0;
+    for (int32_t i = 0; i < nv; ++i) {
+      const char* p = sample_field(sm_icols[i], gi);
+      int a[2] = {-1, -1};
+      int k = 0;
+      while (*p && *p != ':' && k < 2) {
+        if (*p == '.') {
+          ++p;
+        } else if (isdigit((unsigned char)*p)) {
+          a[k] = (int)strtol(p, (char**)&p, 10);
+        } else {
+          break;
+        }
+        ++k;
+        if (*p == '/' || *p == '|') ++p;
+      }
+      gts_[2 * i] = a[0];
+      gts_[2 * i + 1] = a[1];
+      for (int j = 0; j < 2; ++j)
+        if (a[j] >= 0 && a[j] < cur.n_allele) {
+          ++an;
+          ++acs[a[j]];
+        }
+    }
+    return true;
+  }
+  LineReader lr_;
+  std::vector<int32_t> gts_;
+};
+
+// ---- droplet store flattened to CSR ----
+struct SnpInfo {
+  int32_t rid, pos;
+  char ref, alt;
+  double af;
+};
+
+struct DropletStore {
+  // droplets in id order (= .cel.gz row order minus skipped rows, sc_drop_seq.cpp:182-185)
+  std::vector<std::string> bcs;
+  std::vector<int32_t> totl_reads, uniq_reads;  // cell_totl_reads / cell_uniq_reads
+  std::vector<std::string> rid2chr;
+  std::vector<SnpInfo> snps;
+  // CSR
+  std::vector<int64_t> cell_ptr, read_ptr;
+  std::vector<int32_t> snp_idx;
+  std::vector<uint8_t> al, bq;
+  int64_t numi = 0;
+
+  int32_t nbcs() const { return (int32_t)bcs.size(); }
+  int32_t nsnps() const { return (int32_t)snps.size(); }
+};
+
+// hexadecimal-string order of the global read counter: the reference keys reads by sprintf("%x", numi++) in a
+// std::map<std::string,...> (sc_drop_seq.cpp:365, sc_drop_seq.h:26), so "100" < "ff"
+inline uint64_t hex_lex_key(uint32_t c, int* ndigits) {
+  int nd = 1;
+  for (uint32_t t = c >> 4; t; t >>= 4) ++nd;
+  *ndigits = nd;
+  return (uint64_t)c << (4 * (16 - nd));
+}
+
+struct ReadRec {
+  int32_t cell, snp;
+  uint64_t key;  // left-aligned hex digits
+  uint8_t nd, al, bq;
+};
+
+struct PlpFilters {
+  int32_t minRead = 0, minUMI = 0, minSNP = 0, minBQ = 1, capBQ = 60;
+  std::set<std::string> valid_bcs;  // --group-list
+};
+
+// Loads <prefix>.cel.gz and <prefix>.var.gz; `on_snp(idx, chrom, SnpInfo)` is called per .var row in order
+// (demuxlet joins the VCF there).  Then <prefix>.plp.gz -> CSR.
+template <class OnSnp>
+inline void load_plp(const std::string& prefix, const PlpFilters& flt, DropletStore& st, OnSnp on_snp) {
+  notice("Loading pileup information with prefix %s", prefix.c_str());
+  std::vector<int32_t> index_bcs;
+  std::vector<int32_t> tmp_totl, tmp_uniq, tmp_nsnp;
+  {
+    LineReader lr(prefix + ".cel.gz");
+    if (lr.read_fields() != 6 || strcmp(lr.fields[0], "#DROPLET_ID") || strcmp(lr.fields[1], "BARCODE") ||
+        strcmp(lr.fields[2], "NUM.READ") || strcmp(lr.fields[3], "NUM.UMI") || strcmp(lr.fields[4], "NUM.UMIwSNP") ||
+        strcmp(lr.fields[5], "NUM.SNP"))
+      fatal("The header line of %s.cel.gz is malformed or outdated. Expecting #DROPLET_ID BARCODE NUM.READ NUM.UMI NUM.UMIwSNP NUM.SNP", prefix.c_str());
+    int32_t nskip = 0;
+    std::map<std::string, int32_t> bc_map;
+    while (lr.read_fields() > 0) {
+      if (lr.fields.size() < 6) fatal("Malformed row in %s.cel.gz", prefix.c_str());
+      if (!flt.valid_bcs.empty() && !flt.valid_bcs.count(lr.fields[1])) {
+        ++nskip;
+        index_bcs.push_back(-1);
+        continue;
+      }
+      const int32_t n_reads = atoi(lr.fields[2]), n_umis = atoi(lr.fields[3]), n_umi_w = atoi(lr.fields[4]),
+                    n_snps = atoi(lr.fields[5]);
+      if (n_reads < flt.minRead || n_umis < flt.minUMI || n_snps < flt.minSNP) {
+        index_bcs.push_back(-1);
+        ++nskip;
+        continue;
+      }
+      auto it = bc_map.find(lr.fields[1]);
+      int32_t id;
+      if (it == bc_map.end()) {
+        id = (int32_t)st.bcs.size();
+        bc_map[lr.fields[1]] = id;
+        st.bcs.push_back(lr.fields[1]);
+      } else {
+        id = it->second;
+      }
+      index_bcs.push_back(id);
+      if (id + nskip != atoi(lr.fields[0]))
+        fatal("Observed DROPLET_ID %d is different from expected DROPLET_ID. Did you modify the digital pileup files by yourself?", atoi(lr.fields[0]));
+      tmp_totl.push_back(n_reads);
+      tmp_uniq.push_back(n_umi_w);
+      tmp_nsnp.push_back(n_snps);
+    }
+    notice("Finished loading %d droplets, skipping %d", st.nbcs(), nskip);
+  }
+  {
+    LineReader lr(prefix + ".var.gz");
+    if (lr.read_fields() != 6 || strcmp(lr.fields[0], "#SNP_ID") || strcmp(lr.fields[1], "CHROM") ||
+        strcmp(lr.fields[2], "POS") || strcmp(lr.fields[3], "REF") || strcmp(lr.fields[4], "ALT") || strcmp(lr.fields[5], "AF"))
+      fatal("The header line of %s.var.gz is malformed or outdated. Expecting #SNP_ID CHROM POS REF ALT AF", prefix.c_str());
+    std::map<std::string, int32_t> chr2rid;
+    while (lr.read_fields() > 0) {
+      if (lr.fields.size() < 6) fatal("Malformed row in %s.var.gz", prefix.c_str());
+      const char* chr = lr.fields[1];
+      auto it = chr2rid.find(chr);
+      if (it == chr2rid.end()) {
+        it = chr2rid.emplace(chr, (int32_t)chr2rid.size()).first;
+        st.rid2chr.push_back(chr);
+      }
+      SnpInfo s;
+      s.rid = it->second;
+      s.pos = atoi(lr.fields[2]);
+      s.ref = lr.fields[3][0];
+      s.alt = lr.fields[4][0];
+      s.af = atof(lr.fields[5]);
+      if ((int64_t)st.snps.size() + 2 != lr.nlines) fatal("Expected SNP nID = %lld but observed %d", (long long)lr.nlines - 2, st.nsnps());
+      on_snp(st.nsnps(), chr, s);
+      st.snps.push_back(s);
+    }
+    notice("Finished loading %d variants..", st.nsnps());
+  }
+  std::vector<ReadRec> recs;
+  std::vector<int32_t> pass_totl(st.nbcs(), 0);
+  {
+    LineReader lr(prefix + ".plp.gz");
+    if (lr.read_fields() != 4 || strcmp(lr.fields[0], "#DROPLET_ID") || strcmp(lr.fields[1], "SNP_ID") ||
+        strcmp(lr.fields[2], "ALLELES") || strcmp(lr.fields[3], "BASEQS"))
+      fatal("THe header line of %s.cel.gz is malformed or outdated. Expecting #DROPLET_ID SNP_ID ALLELES BASEQS", prefix.c_str());
+    uint32_t numi = 0;
+    while (lr.read_fields() > 0) {
+      if (lr.fields.size() < 4) fatal("Malformed row in %s.plp.gz", prefix.c_str());
+      const int32_t did = atoi(lr.fields[0]);
+      if (did < 0 || did >= (int32_t)index_bcs.size()) fatal("DROPLET_ID %d out of range in %s.plp.gz", did, prefix.c_str());
+      const int32_t ibc = index_bcs[did];
+      if (ibc < 0) continue;
+      const int32_t snp = atoi(lr.fields[1]);
+      if (snp < 0 || snp >= st.nsnps()) fatal("SNP_ID %d out of range in %s.plp.gz", snp, prefix.c_str());
+      const char* pa = lr.fields[2];
+      const char* pq = lr.fields[3];
+      const int32_t l = (int32_t)strlen(pq);
+      if ((int32_t)strlen(pa) < l) fatal("Length are different between %s and %s", pa, pq);
+      for (int32_t i = 0; i < l; ++i) {
+        char q = (char)(pq[i] - (char)33);
+        if (q >= flt.minBQ) {  // sc_drop_seq.cpp:362-364
+          if (q > flt.capBQ) q = (char)flt.capBQ;
+          ReadRec r;
+          r.cell = ibc;
+          r.snp = snp;
+          int nd;
+          r.key = hex_lex_key(numi++, &nd);
+          r.nd = (uint8_t)nd;
+          r.al = (uint8_t)(pa[i] - '0');
+          r.bq = (uint8_t)q;
+          recs.push_back(r);
+          ++pass_totl[ibc];
+        }
+      }
+    }
+    st.numi = numi;
+    notice("Finished loading %u UMIs in total..", numi);
+  }
+  // reference iteration order: droplet id, SNP id (std::map<int32_t,...>), UMI string (std::map<std::string,...>)
+  std::sort(recs.begin(), recs.end(), [](const ReadRec& a, const ReadRec& b) {
+    if (a.cell != b.cell) return a.cell < b.cell;
+    if (a.snp != b.snp) return a.snp < b.snp;
+    if (a.key != b.key) return a.key < b.key;
+    return a.nd < b.nd;
+  });
+  const int32_t nb = st.nbcs();
+  st.cell_ptr.assign(nb + 1, 0);
+  st.uniq_reads.assign(nb, 0);
+  st.read_ptr.assign(1, 0);
+  st.al.reserve(recs.size());
+  st.bq.reserve(recs.size());
+  for (size_t i = 0; i < recs.size(); ++i) {
+    const ReadRec& r = recs[i];
+    if (i == 0 || r.cell != recs[i - 1].cell || r.snp != recs[i - 1].snp) {
+      if (i > 0) st.read_ptr.push_back((int64_t)st.al.size());
+      st.snp_idx.push_back(r.snp);
+      ++st.cell_ptr[r.cell + 1];
+    }
+    st.al.push_back(r.al);
+    st.bq.push_back(r.bq);
+    ++st.uniq_reads[r.cell];  // every plp read has its own UMI string (sc_drop_seq.cpp:365)
+  }
+  if (!recs.empty()) st.read_ptr.push_back((int64_t)st.al.size());
+  for (int32_t c = 0; c < nb; ++c) st.cell_ptr[c + 1] += st.cell_ptr[c];
+  // cell_totl_reads: counted reads, overwritten by the .cel.gz value when the other counts agree (:375-380)
+  st.totl_reads.assign(nb, 0);
+  for (int32_t c = 0; c < nb; ++c) {
+    st.totl_reads[c] = pass_totl[c];
+    if (st.uniq_reads[c] == tmp_uniq[c] && tmp_nsnp[c] == (int32_t)(st.cell_ptr[c + 1] - st.cell_ptr[c])) st.totl_reads[c] = tmp_totl[c];
+  }
+}
+
+}  // namespace hostio

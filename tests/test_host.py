@@ -234,3 +234,105 @@ def test_world_size_2_gloo_freemuxlet_em(tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("rank ok") == 2
+
+
+# ---------------------------------------------------------------------------------------------
+# the `cramore` command line (cramore_b200/host): flag surface and bit-exact CSR construction
+# ---------------------------------------------------------------------------------------------
+CRAMORE = os.path.join(ROOT, "cramore_b200", "host", "cramore")
+
+REF_DEMUX_FLAGS = ["sam", "tag-group", "tag-UMI", "plp", "vcf", "field", "geno-error-offset", "geno-error-coeff", "r2-info",
+                   "min-mac", "min-callrate", "sm", "sm-list", "out", "alpha", "doublet-prior", "sam-verbose",
+                   "vcf-verbose", "cap-BQ", "min-BQ", "min-MQ", "min-TD", "excl-flag", "group-list", "min-total",
+                   "min-umi", "min-snp"]  # cmd_cram_demuxlet.cpp:40-79, in order
+REF_FMX_FLAGS = ["plp", "init-cluster", "out", "nsample", "aux-files", "verbose", "doublet-prior", "geno-error",
+                 "bf-thres", "frac-init-clust", "iter-init", "keep-init-missing", "cap-BQ", "min-BQ", "group-list",
+                 "min-total", "min-uniq", "min-snp"]  # cmd_cram_freemuxlet.cpp:34-63
+
+
+def _help_flags(cmd):
+    r = subprocess.run([CRAMORE, cmd, "--help"], capture_output=True, text=True)
+    return re.findall(r"^\s+--([A-Za-z0-9-]+)\s+:", r.stderr, flags=re.M)
+
+
+def test_cli_flag_surface(built):
+    d = _help_flags("demuxlet")
+    assert d[:len(REF_DEMUX_FLAGS)] == REF_DEMUX_FLAGS and all(f.startswith("gpu-") for f in d[len(REF_DEMUX_FLAGS):])
+    f = _help_flags("freemuxlet")
+    assert f[:len(REF_FMX_FLAGS)] == REF_FMX_FLAGS and all(x.startswith("gpu-") for x in f[len(REF_FMX_FLAGS):])
+    f2 = _help_flags("freemux2")
+    assert "seed" in f2 and "randomize-singlet-score" in f2 and "min-umi" in f2 and "min-uniq" not in f2
+    # unknown flags and a repeated scalar flag are errors, like paramList::Read (params.cpp:140-177, 478-480)
+    r = subprocess.run([CRAMORE, "demuxlet", "--no-such-flag", "1"], capture_output=True, text=True)
+    assert r.returncode != 0 and "ignored" in r.stderr
+    r = subprocess.run([CRAMORE, "demuxlet", "--out", "a", "--out", "b"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Redundant" in r.stderr
+
+
+@pytest.mark.parametrize("case", ["plain", "filters"])
+def test_cli_csr_construction_bit_exact(built, tmp_path, case):
+    """plp + VCF text -> the engine's flat inputs, without a GPU (--gpu-dump-inputs): CSR, read order, float GP,
+    has_gp and per-SNP error must equal what load_from_plp / parse_posteriors build (bit-exact)."""
+    from cramore_b200.synth import make_dataset, write_plp, write_vcf
+    d = make_dataset("C1", nbcs=70, nsnps=150, rbar=160, nv=6, seed=31, with_barcodes=True)  # many multi-read entries
+    pre = str(tmp_path / "in")
+    write_plp(d, pre)
+    write_vcf(d, pre + ".vcf", with_r2=True)
+    args = [CRAMORE, "demuxlet", "--plp", pre, "--vcf", pre + ".vcf", "--out", str(tmp_path / "o"),
+            "--gpu-dump-inputs", str(tmp_path / "dump")]
+    keep = np.ones(d["nbcs"], bool)
+    err = 0.10
+    if case == "filters":
+        grp = tmp_path / "grp.txt"
+        sel = [b for i, b in enumerate(d["barcodes"]) if i % 3 != 1]
+        grp.write_text("\n".join(sel) + "\n")
+        keep = np.asarray([i % 3 != 1 for i in range(d["nbcs"])])
+        args += ["--group-list", str(grp), "--geno-error-offset", "0.05", "--geno-error-coeff", "0.5", "--min-snp", "100"]
+        err = 0.05 + (1 - 0.05) * (1 - float(np.float32(0.9))) * 0.5
+        keep &= np.diff(d["cell_ptr"]) >= 100
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+    def load(name, dt):
+        return np.fromfile(str(tmp_path / ("dump." + name)), dtype=dt)
+
+    # rows come in std::map barcode order, restricted to the droplets that pass the filters
+    cells = [i for i in sorted(range(d["nbcs"]), key=lambda i: d["barcodes"][i]) if keep[i]]
+    bcs = (tmp_path / "dump.barcodes.txt").read_text().split()
+    assert bcs == [d["barcodes"][i] for i in cells]
+    from cramore_b200.synth import _hex_order_key, plp_read_order
+    from tests.parity import permute_cells
+    # reads are numbered by a global counter over the KEPT droplets' .plp rows and iterate in the hex-string order
+    # of that number (sc_drop_seq.cpp:365): re-derive the order for the surviving droplets
+    o = plp_read_order(d)
+    d2 = dict(d, al=np.asarray(d["al"])[o], bq=np.asarray(d["bq"])[o])      # file (counter) order
+    kept_ids = [i for i in range(d["nbcs"]) if keep[i]]  # droplets surviving --group-list / --min-snp, id order
+    counter = np.full(len(d["al"]), -1, np.int64)
+    n = 0
+    for i in kept_ids:
+        r0, r1 = d["read_ptr"][d["cell_ptr"][i]], d["read_ptr"][d["cell_ptr"][i + 1]]
+        counter[r0:r1] = np.arange(n, n + r1 - r0)
+        n += r1 - r0
+    al_f, bq_f = d2["al"].copy(), d2["bq"].copy()
+    rp0 = np.asarray(d["read_ptr"])
+    for e in np.nonzero(np.diff(rp0) > 1)[0]:
+        c = counter[rp0[e]:rp0[e + 1]]
+        if c[0] < 0:
+            continue
+        left, nd = _hex_order_key(c)
+        perm = np.lexsort((nd, left))
+        al_f[rp0[e]:rp0[e + 1]] = d2["al"][rp0[e]:rp0[e + 1]][perm]
+        bq_f[rp0[e]:rp0[e + 1]] = d2["bq"][rp0[e]:rp0[e + 1]][perm]
+    cp, si, rp, al, bq = permute_cells(dict(d, al=al_f, bq=bq_f), cells)
+    assert np.array_equal(load("cell_ptr.i64", "<i8"), cp) and np.array_equal(load("snp_idx.i32", "<i4"), si)
+    assert np.array_equal(load("read_ptr.i64", "<i8"), rp)
+    assert np.array_equal(load("al.u8", "u1"), al) and np.array_equal(load("bq.u8", "u1"), bq)
+    ac = np.asarray(d["geno"], np.int64).sum(axis=1)
+    has = ((ac >= 1) & (2 * d["nv"] - ac >= 1)).astype(np.uint8)  # --min-mac 1 (bcf_filtered_reader.cpp:638)
+    assert np.array_equal(load("has_gp.u8", "u1"), has)
+    gp = load("gp.f32", "<f4").reshape(d["nsnps"], d["nv"], 3)
+    assert np.array_equal(gp[has == 1], d["gp"][has == 1]) and np.all(gp[has == 0] == 0)
+    assert np.array_equal(load("snp_err.f64", "<f8"), np.where(has == 1, err, 0.0))
+    if case == "plain":
+        ranks = {b: k for k, b in enumerate(sorted(d["barcodes"]))}
+        assert np.array_equal(load("row_int_id.i32", "<i4"), [ranks[b] for b in bcs])
