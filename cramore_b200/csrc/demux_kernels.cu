@@ -548,7 +548,14 @@ cudaError_t launch_singlet_to_dbg(const DemuxDev& d, double* llk_dbg, int64_t c0
 //                in the item epilogue;
 //   * at the end of an item the products become log-sum-exp / top-2 partials (no log needed:
 //     ordering by (exponent, mantissa) is ordering by LLK).
-constexpr int kNS = 3;                              // raw ring stages
+#ifndef CCU_NS
+#define CCU_NS 3
+#endif
+#ifndef CCU_AFF_UNROLL
+#define CCU_AFF_UNROLL 2
+#endif
+constexpr int kNSWanted = CCU_NS;                   // raw ring stages (fewer where shared memory is short)
+constexpr int kAffUnroll = CCU_AFF_UNROLL;
 constexpr int kTJ = 2;                              // samples j per thread
 constexpr int kConsumers = kScoreThreads;           // 16 consumer warps
 constexpr int kScoreBlock = kScoreThreads + 128;    // + the producer warpgroup (1 working warp)
@@ -594,14 +601,16 @@ struct ScoreCfg {
   static constexpr int STAGE_BYTES = (STAGE_G > STAGE_A) ? STAGE_G : STAGE_A;
   static constexpr int T_BYTES = SC * 32 * TROW * 8;
   static constexpr int RED_BYTES = (kConsumers / 32) * 64;
-  static constexpr int META_BYTES = kNS * (int)sizeof(ChunkMeta);
+  static constexpr int FIXED_BYTES = 2 * T_BYTES + RED_BYTES + 48 * 8 + 64;
+  static constexpr int NS = ((kNSWanted * (STAGE_BYTES + 32 + 16) + FIXED_BYTES) <= 227 * 1024) ? kNSWanted : 3;
+  static constexpr int META_BYTES = NS * (int)sizeof(ChunkMeta);
   static constexpr int ALPHA_BYTES = 48 * 8;
-  static constexpr int OFF_T = kNS * STAGE_BYTES;
+  static constexpr int OFF_T = NS * STAGE_BYTES;
   static constexpr int OFF_RED = OFF_T + 2 * T_BYTES;
   static constexpr int OFF_META = OFF_RED + RED_BYTES;
   static constexpr int OFF_ALPHA = OFF_META + META_BYTES;
   static constexpr int OFF_BAR = OFF_ALPHA + ALPHA_BYTES;
-  static constexpr int SMEM_BYTES = OFF_BAR + 2 * kNS * 8 + 16;
+  static constexpr int SMEM_BYTES = OFF_BAR + 2 * NS * 8 + 16;
   // T-compute task split: NG alpha groups per (SNP slot, k) pair, APT alphas per task
   static constexpr int PAIRS = SC * KT;
   static constexpr int NG = (PAIRS >= kConsumers) ? 1 : (kConsumers / PAIRS);
@@ -629,6 +638,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
   using Cfg = ScoreCfg<AC, TK>;
   constexpr int kSC = Cfg::SC;
   constexpr int kSCA = Cfg::SCA;
+  constexpr int kNS = Cfg::NS;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* raw = smem;
   double* Tbuf = reinterpret_cast<double*>(smem + Cfg::OFF_T);
@@ -795,6 +805,8 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
   constexpr int kBudget = 960, kGenBits = 34;
   const int abits = min(kGenBits, (int)(0.33220 * (double)d.maxbq[0] + 3.585));
   int budget = kBudget;
+  bool pair_ok = true;  // every alpha within [0, 0.5]
+  for (int n = 0; n < d.nA; ++n) pair_ok = pair_ok && (s_alpha[n] >= 0.0) && (s_alpha[n] <= 0.5);
 
   // ---- general chunk: kTJ x NCOL running products over the chunk's SNPs through T
   auto main_general = [&](int cnt, int stage, int tb) {
@@ -824,45 +836,78 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
     }
   };
 
-  // ---- affine chunk: acc[j][k][n] *= f_j + alpha_n (f_k - f_j)
+  // ---- affine chunk: acc[j][k][n] *= f_j + alpha_n (f_k - f_j).
+  // Two SNPs are taken at a time: (a1 + alpha d1)(a2 + alpha d2) = c0 + alpha (c1 + alpha c2) costs 6 FP64
+  // instructions per (j,k) for the coefficients plus 2 DFMA + 1 DMUL per alpha, i.e. 1.8 instead of 2.1 per
+  // likelihood and SNP.  With every alpha in [0, 0.5] each factor is >= half its f_j, so the expanded form has
+  // no cancellation to speak of (terms / value <= ~4); grids reaching beyond 0.5 use the one-SNP form.
+  // The alphas are re-read from shared memory inside the loop (broadcast LDS.128) to keep 20 registers free.
   auto main_affine = [&](int cnt, int stage, int n0) {
     const double* fj_base = reinterpret_cast<const double*>(raw + stage * Cfg::STAGE_BYTES) + jg * kTJ;
     // the thread's TK consecutive samples k sit inside one 32-sample part
     const double* fk_base = reinterpret_cast<const double*>(raw + stage * Cfg::STAGE_BYTES + Cfg::PART_BYTES) +
                             ((kidx * TK) >> 5) * (Cfg::PART_BYTES / 8) + ((kidx * TK) & 31);
-    double al[AC];
+    const double* sal = s_alpha + n0;
+    auto load_fk = [&](int s, double* fk) {
+      if constexpr (TK == 1) {
+        fk[0] = fk_base[s * 32];
+      } else {
 #pragma unroll
-    for (int a = 0; a < AC; ++a) al[a] = s_alpha[n0 + a];
+        for (int kk = 0; kk < TK; kk += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(fk_base + s * 32 + kk);
+          fk[kk] = v.x;
+          fk[kk + 1] = v.y;
+        }
+      }
+    };
     int s = 0;
+#ifdef CCU_EXPERIMENT_SKIP_MATH  // timing experiment only: the data pipeline without the multiplications
+    if (cnt > 0) acc[0][0] *= fj_base[0] + fk_base[0] + sal[0];
+    s = cnt;
+#endif
     while (s < cnt) {
-      if (budget < abits) {
+      if (budget < 2 * abits) {
         renorm_all();
         budget = kBudget;
       }
       const int run = min(cnt - s, budget / abits);  // SNPs that fit into the budget
       budget -= run * abits;
       const int s_end = s + run;
-#pragma unroll 2
+      if (pair_ok) {
+        for (; s + 1 < s_end; s += 2) {
+          const double2 fa = *reinterpret_cast<const double2*>(fj_base + s * 32);
+          const double2 fb = *reinterpret_cast<const double2*>(fj_base + (s + 1) * 32);
+          double ka[TK], kb[TK];
+          load_fk(s, ka);
+          load_fk(s + 1, kb);
+          const double c00 = fa.x * fb.x, c01 = fa.y * fb.y;
+#pragma unroll
+          for (int kk = 0; kk < TK; ++kk) {
+            const double da0 = ka[kk] - fa.x, da1 = ka[kk] - fa.y, db0 = kb[kk] - fb.x, db1 = kb[kk] - fb.y;
+            const double c20 = da0 * db0, c21 = da1 * db1;
+            const double c10 = fma(fa.x, db0, fb.x * da0), c11 = fma(fa.y, db1, fb.y * da1);
+#pragma unroll
+            for (int a = 0; a < AC; ++a) {
+              const double al = sal[a];
+              acc[0][kk * AC + a] *= fma(al, fma(al, c20, c10), c00);
+              acc[1][kk * AC + a] *= fma(al, fma(al, c21, c11), c01);
+            }
+          }
+        }
+      }
+#pragma unroll 1
       for (; s < s_end; ++s) {
         const double2 fj = *reinterpret_cast<const double2*>(fj_base + s * 32);
         double fk[TK];
-        if constexpr (TK == 1) {
-          fk[0] = fk_base[s * 32];
-        } else {
-#pragma unroll
-          for (int kk = 0; kk < TK; kk += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(fk_base + s * 32 + kk);
-            fk[kk] = v.x;
-            fk[kk + 1] = v.y;
-          }
-        }
+        load_fk(s, fk);
 #pragma unroll
         for (int kk = 0; kk < TK; ++kk) {
           const double d0 = fk[kk] - fj.x, d1 = fk[kk] - fj.y;
 #pragma unroll
           for (int a = 0; a < AC; ++a) {
-            acc[0][kk * AC + a] *= fma(al[a], d0, fj.x);
-            acc[1][kk * AC + a] *= fma(al[a], d1, fj.y);
+            const double al = sal[a];
+            acc[0][kk * AC + a] *= fma(al, d0, fj.x);
+            acc[1][kk * AC + a] *= fma(al, d1, fj.y);
           }
         }
       }
@@ -871,96 +916,122 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
 
   // ---- item epilogue: this warp's products -> log-sum-exp partial + top-2 candidates.  Each
   // consumer warp writes its own record (K3 merges them), so no cross-warp synchronisation.
+  // Cost matters (it is paid per likelihood, not per SNP): validity is folded into the per-(j,k)
+  // multiplier, and the warp-wide largest exponent is found first so that the log-sum-exp and the
+  // top-2 scans touch only the handful of products that can matter; whole-warp votes skip the rest.
+  double pjk[kTJ][TK];  // prod s_j * prod s_k of the affine entries, or 0 where (j,k) is not a doublet pair
+  int ejk[kTJ][TK];
+  auto load_item_consts = [&](int cell32, int j0, int k0) {  // issued before the item's last chunk
+    const int64_t cell = cell32;
+    double pmj[kTJ], pmk[TK];
+    int pej[kTJ], pek[TK];
+#pragma unroll
+    for (int jj = 0; jj < kTJ; ++jj) {
+      const int j = j0 + jg * kTJ + jj;
+      pmj[jj] = d.pm[cell * d.nvp + j];
+      pej[jj] = d.pe[cell * d.nvp + j];
+    }
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      const int k = min(k0 + kidx * TK + kk, d.nvp - 1);
+      pmk[kk] = d.pm[cell * d.nvp + k];
+      pek[kk] = d.pe[cell * d.nvp + k];
+    }
+#pragma unroll
+    for (int jj = 0; jj < kTJ; ++jj)
+#pragma unroll
+      for (int kk = 0; kk < TK; ++kk) {
+        pjk[jj][kk] = pmj[jj] * pmk[kk];  // in [1,4) or 0
+        ejk[jj][kk] = pej[jj] + pek[kk];
+      }
+  };
+
   auto epilogue = [&](int cell32, int j0, int k0, int n0, int64_t item) {
     const int64_t cell = cell32;
-    // per-droplet constants of the affine entries: prod s_j and prod s_k
-    double pjk[kTJ][TK];
-    int ejk[kTJ][TK];
-    {
-      double pmj[kTJ], pmk[TK];
-      int pej[kTJ], pek[TK];
+    constexpr uint32_t kFull = 0xffffffffu;
+    if constexpr (TK > 2) load_item_consts(cell32, j0, k0);
+    if ((dbg != nullptr) && cell >= dbg_c0 && cell < dbg_c1) {  // inspection path (ccu_demux_get_llk)
 #pragma unroll
       for (int jj = 0; jj < kTJ; ++jj) {
         const int j = j0 + jg * kTJ + jj;
-        pmj[jj] = d.pm[cell * d.nvp + j];
-        pej[jj] = d.pe[cell * d.nvp + j];
-      }
 #pragma unroll
-      for (int kk = 0; kk < TK; ++kk) {
-        const int k = min(k0 + kidx * TK + kk, d.nvp - 1);
-        pmk[kk] = d.pm[cell * d.nvp + k];
-        pek[kk] = d.pe[cell * d.nvp + k];
-      }
-#pragma unroll
-      for (int jj = 0; jj < kTJ; ++jj)
-#pragma unroll
-        for (int kk = 0; kk < TK; ++kk) {
-          pjk[jj][kk] = pmj[jj] * pmk[kk];  // in [1,4) or 0
-          ejk[jj][kk] = pej[jj] + pek[kk];
+        for (int cc = 0; cc < Cfg::NCOL; ++cc) {
+          const int k = k0 + kidx * TK + cc / AC, n = n0 + cc % AC;
+          double m = acc[jj][cc] * pjk[jj][cc / AC];
+          int e = aex[jj][cc] + ejk[jj][cc / AC];
+          renorm(m, e);
+          if (j < d.nv && k < d.nv && n < d.nA)
+            dbg[(((cell - dbg_c0) * d.nv + j) * d.nv + k) * d.nA + n] = make_double2(m, (double)e);
         }
+      }
     }
-    // pass 1: final (mantissa, exponent) of every product; largest exponent among the doublet terms
-    int emax = kLseEmpty;
-    const bool want_dbg = (dbg != nullptr) && cell >= dbg_c0 && cell < dbg_c1;
+    // (j,k) that are not doublet pairs contribute nothing: zero multiplier; alpha == 0.5 weights (:812-817:
+    // counted once, k < j, with twice the prior)
+    double whalf[kTJ][TK];
 #pragma unroll
     for (int jj = 0; jj < kTJ; ++jj) {
       const int j = j0 + jg * kTJ + jj;
 #pragma unroll
+      for (int kk = 0; kk < TK; ++kk) {
+        const int k = k0 + kidx * TK + kk;
+        if (j >= d.nv || k >= d.nv || j == k) pjk[jj][kk] = 0.0;
+        whalf[jj][kk] = (k < j) ? 2.0 : 0.0;
+      }
+    }
+    const int nal = d.nA - n0;  // valid alphas of this chunk (>= AC unless the grid was padded)
+    // pass 1: final (mantissa, exponent) of every product and the largest exponent (branch-free)
+    int emax = kLseEmpty;
+#pragma unroll
+    for (int jj = 0; jj < kTJ; ++jj) {
+#pragma unroll
       for (int cc = 0; cc < Cfg::NCOL; ++cc) {
-        const int k = k0 + kidx * TK + cc / AC;
-        const int n = n0 + cc % AC;
         double m = acc[jj][cc] * pjk[jj][cc / AC];
         int e = aex[jj][cc] + ejk[jj][cc / AC];
         renorm(m, e);
-        const bool inside = (j < d.nv) && (k < d.nv) && (n < d.nA);
-        if (want_dbg && inside) dbg[(((cell - dbg_c0) * d.nv + j) * d.nv + k) * d.nA + n] = make_double2(m, (double)e);
-        if (!inside || j == k || !(m > 0.0)) {
-          m = 0.0;
-          e = kLseEmpty;
-        }
+        if ((cc % AC) >= nal) m = 0.0;
+        e = (m > 0.0) ? e : kLseEmpty;
         acc[jj][cc] = m;
         aex[jj][cc] = e;
         emax = max(emax, e);
       }
     }
-    // pass 2: sum of w * m * 2^(e - emax) and the thread's top-2 (scan order = increasing pos)
-    double la = 0.0;
+    // pass 2: sum of w * m * 2^(e - emax) and the thread's top-2 (scan order = increasing pos); branch-free,
+    // two interleaved partial sums
+    double la0 = 0.0, la1 = 0.0;
     double bm1 = 0.0, bm2 = 0.0;
-    int be1 = INT_MIN, be2 = INT_MIN, bp1 = -1, bp2 = -1;
+    int be1 = INT_MIN, be2 = INT_MIN, bt1 = -1, bt2 = -1;  // t = jj*NCOL + cc
 #pragma unroll
     for (int jj = 0; jj < kTJ; ++jj) {
-      const int j = j0 + jg * kTJ + jj;
 #pragma unroll
       for (int cc = 0; cc < Cfg::NCOL; ++cc) {
-        const int k = k0 + kidx * TK + cc / AC;
-        const int n = n0 + cc % AC;
         const double m = acc[jj][cc];
         const int e = aex[jj][cc];
-        // :812-817  alpha == 0.5 is counted once (k <= j) with twice the prior
-        const double w = ((half_mask >> n) & 1u) ? ((k < j) ? 2.0 : 0.0) : 1.0;
-        la = fma(w * m, pow2_nonpos(e - emax), la);
-        const bool valid = m > 0.0;
-        const bool gt1 = valid && ((e > be1) || (e == be1 && m > bm1));
-        const bool gt2 = valid && ((e > be2) || (e == be2 && m > bm2));
-        const int pos = (j * d.nv + k) * d.nA + n;
-        // second = gt1 ? old first : (gt2 ? x : second)
+        const double w = ((half_mask >> (n0 + cc % AC)) & 1u) ? whalf[jj][cc / AC] : 1.0;
+        if (cc & 1) la1 = fma(w * m, pow2_nonpos(e - emax), la1);
+        else la0 = fma(w * m, pow2_nonpos(e - emax), la0);
+        const bool gt1 = (e > be1) || (e == be1 && m > bm1);  // empty products carry e = kLseEmpty > INT_MIN
+        const bool gt2 = (e > be2) || (e == be2 && m > bm2);
         bm2 = gt1 ? bm1 : (gt2 ? m : bm2);
         be2 = gt1 ? be1 : (gt2 ? e : be2);
-        bp2 = gt1 ? bp1 : (gt2 ? pos : bp2);
+        bt2 = gt1 ? bt1 : (gt2 ? (jj * Cfg::NCOL + cc) : bt2);
         bm1 = gt1 ? m : bm1;
         be1 = gt1 ? e : be1;
-        bp1 = gt1 ? pos : bp1;
+        bt1 = gt1 ? (jj * Cfg::NCOL + cc) : bt1;
       }
     }
-    int le = emax;
-    if (!(la > 0.0)) le = kLseEmpty;
+    double la = la0 + la1;
+    int le = (la > 0.0) ? emax : kLseEmpty;
+    auto pos_of = [&](int t) {
+      const int jj = t / Cfg::NCOL, cc = t - jj * Cfg::NCOL;
+      return ((j0 + jg * kTJ + jj) * d.nv + (k0 + kidx * TK + cc / AC)) * d.nA + n0 + cc % AC;
+    };
     Cand b1, b2;
-    b1.m = bm1; b1.e = be1; b1.pos = bp1;
-    b2.m = bm2; b2.e = be2; b2.pos = bp2;
+    b1.m = bm1; b1.e = (bm1 > 0.0) ? be1 : INT_MIN; b1.pos = (bm1 > 0.0) ? pos_of(bt1) : -1;
+    b2.m = bm2; b2.e = (bm2 > 0.0) ? be2 : INT_MIN; b2.pos = (bm2 > 0.0) ? pos_of(bt2) : -1;
 #pragma unroll
     for (int dd = 16; dd >= 1; dd >>= 1) {
-      const double oa = __shfl_xor_sync(0xffffffffu, la, dd);
-      const int oe = __shfl_xor_sync(0xffffffffu, le, dd);
+      const double oa = __shfl_xor_sync(kFull, la, dd);
+      const int oe = __shfl_xor_sync(kFull, le, dd);
       lse_add(la, le, oa, oe);
       const Cand o1 = cand_shfl_xor(b1, dd), o2 = cand_shfl_xor(b2, dd);
       cand_insert(b1, b2, o1);
@@ -991,6 +1062,11 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
     if (!(flags & 1)) break;
     const int m_cell = mt->cell, m_j0 = mt->j0, m_k0 = mt->k0, m_n0 = mt->n0;
     const int64_t m_item = mt->item;
+    // the item's global constants are fetched before its last chunk so the loads fly while it is multiplied in
+    // (only where the 2*TK extra registers are affordable)
+    if constexpr (TK <= 2) {
+      if (flags & 2) load_item_consts(m_cell, m_j0, m_k0);
+    }
     if (flags & 4) {
       main_affine(cnt, stage, m_n0);
     } else {

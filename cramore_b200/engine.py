@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libcramore_cuda.so")
+LIB_PATH = os.environ.get("CCU_LIB") or os.path.join(_PKG, "libcramore_cuda.so")  # CCU_LIB: A/B builds of the same ABI
 _lib = None
 
 RESULT_DTYPE = np.dtype([
