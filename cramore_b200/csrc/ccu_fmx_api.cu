@@ -18,13 +18,13 @@ struct FmxState {
   int64_t nbcs = 0, nsnps = 0, nnz = 0, nreads = 0;
   int64_t cell_begin = 0, cell_end = 0, snp_begin = 0, snp_end = 0;
   DevBuf cell_ptr, snp_idx, read_ptr, al, bq, af;
-  DevBuf gl, cnt, logdenom, csc_ptr, csc_cell, csc_gl, csc_cnt;
+  DevBuf gl, cnt, logdenom, csc_ptr, csc_cell, csc_gl, csc_cnt, csc_lab;
   DevBuf assign, stats, cgp, llk, results, scratch;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   ccu_fmx_timings tm = {};
   void release() {
     DevBuf* all[] = {&cell_ptr, &snp_idx, &read_ptr, &al, &bq, &af, &gl, &cnt, &logdenom, &csc_ptr, &csc_cell,
-                     &csc_gl, &csc_cnt, &assign, &stats, &cgp, &llk, &results, &scratch};
+                     &csc_gl, &csc_cnt, &csc_lab, &assign, &stats, &cgp, &llk, &results, &scratch};
     for (DevBuf* b : all) b->release();
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
@@ -65,6 +65,7 @@ ccu::FmxDev fmx_view(const ccu_handle* h) {
   d.csc_cell = f->csc_cell.as<int32_t>();
   d.csc_gl = f->csc_gl.as<double>();
   d.csc_cnt = f->csc_cnt.as<int4>();
+  d.csc_lab = f->csc_lab.as<int8_t>();
   d.assign = f->assign.as<int32_t>();
   d.stats = f->stats.as<double>();
   d.cgp = f->cgp.as<double>();
@@ -163,6 +164,7 @@ int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* ce
   CCU_CUDA(h, f->csc_cell.reserve((size_t)nnz * sizeof(int32_t) + 16));
   CCU_CUDA(h, f->csc_gl.reserve((size_t)nnz * 9 * sizeof(double) + 16));
   CCU_CUDA(h, f->csc_cnt.reserve((size_t)nnz * sizeof(int4) + 16));
+  CCU_CUDA(h, f->csc_lab.reserve((size_t)nnz + 16));
   CCU_CUDA(h, f->assign.reserve(nbcs * sizeof(int32_t) + 16));
   CCU_CUDA(h, f->stats.reserve((size_t)f->K * nsnps * ccu::kStatStride * sizeof(double) + 16));
   CCU_CUDA(h, f->cgp.reserve((size_t)f->K * nsnps * 3 * sizeof(double) + 16));
@@ -284,7 +286,7 @@ int ccu_fmx_mstep_dev(ccu_handle* h) {
   cudaEventRecord(f->ev[0], h->stream);
   CCU_CUDA(h, ccu::launch_fmx_mstep(fmx_view(h), h->stream));
   cudaEventRecord(f->ev[1], h->stream);
-  f->tm.launches += 1;
+  f->tm.launches += 2;  // label pass + fold
   f->have_stats = true;
   return 0;
 }
@@ -428,6 +430,23 @@ int ccu_fmx_run_em(ccu_handle* h, const int32_t* init_assign, int32_t niter, int
   f->tm.ms_mstep = ms_m / (it > 0 ? it : 1);
   if (iters_run) *iters_run = it;
   return ccu_fmx_download_results(h, out);
+}
+
+int ccu_fmx_selftest_division(ccu_handle* h, int64_t nsets, uint64_t seed, int64_t* mismatches) {
+  if (!h) return 1;
+  if (!mismatches || nsets < 0) return ccu_fail(h, "ccu_fmx_selftest_division: bad arguments");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  unsigned long long* d = nullptr;
+  CCU_CUDA(h, cudaMalloc(&d, sizeof(unsigned long long)));
+  cudaError_t e = cudaMemsetAsync(d, 0, sizeof(unsigned long long), h->stream);
+  if (e == cudaSuccess) e = ccu::launch_fmx_div_selftest(seed, nsets, d, h->stream);
+  unsigned long long v = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&v, d, sizeof(v), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  CCU_CUDA(h, e);
+  *mismatches = (int64_t)v;
+  return 0;
 }
 
 int ccu_fmx_get_timings(const ccu_handle* h, ccu_fmx_timings* t) {

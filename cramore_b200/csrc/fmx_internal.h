@@ -32,6 +32,7 @@ struct FmxDev {
   int32_t* csc_cell;         // [nnz] droplet id, ascending inside a SNP
   double* csc_gl;            // [nnz][9]
   int4* csc_cnt;             // [nnz]
+  int8_t* csc_lab;           // [nnz] cluster label of the entry's droplet in the current M-step (-1: none)
   // EM state
   int32_t* assign;           // [nbcs] cluster of the droplet in the next M-step, or -1
   double* stats;             // [K][nsnps][kStatStride]
@@ -53,6 +54,8 @@ cudaError_t launch_fmx_mstep(const FmxDev& d, cudaStream_t st);
 cudaError_t launch_fmx_cgp(const FmxDev& d, int apply_geno_error, cudaStream_t st);
 cudaError_t launch_fmx_estep(const FmxDev& d, cudaStream_t st);
 // int32 count of droplets whose (type, jBest, kBest) differ between two result arrays
+// counts bitwise differences between the shared-reciprocal division of the pileup kernels and __ddiv_rn
+cudaError_t launch_fmx_div_selftest(uint64_t seed, int64_t n, unsigned long long* mismatches, cudaStream_t st);
 cudaError_t launch_fmx_unpack_stats(const FmxDev& d, ccu_pileup* out, cudaStream_t st);
 
 }  // namespace ccu

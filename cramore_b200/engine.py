@@ -44,7 +44,7 @@ ABI_SYMBOLS = [
     "ccu_fmx_configure", "ccu_fmx_upload", "ccu_fmx_set_shard", "ccu_fmx_lmix", "ccu_fmx_get_pileups",
     "ccu_fmx_mstep", "ccu_fmx_estep", "ccu_fmx_get_llk", "ccu_fmx_get_clusters", "ccu_fmx_stats_dev",
     "ccu_fmx_assign_dev", "ccu_fmx_mstep_dev", "ccu_fmx_estep_dev", "ccu_fmx_download_results", "ccu_fmx_run_em",
-    "ccu_fmx_get_timings",
+    "ccu_fmx_get_timings", "ccu_fmx_selftest_division",
 ]
 
 
@@ -297,6 +297,11 @@ class FreemuxEngine(DemuxEngine):
         self._check(self.lib.ccu_fmx_run_em(self.h, _ptr(a), C.c_int32(niter), C.c_int32(int(geno_error_every_iter)),
                                             C.c_int32(int(stop_when_stable)), _ptr(out), C.byref(it)))
         return out, it.value
+
+    def selftest_division(self, nsets=1 << 22, seed=1):
+        v = C.c_int64(-1)
+        self._check(self.lib.ccu_fmx_selftest_division(self.h, C.c_int64(nsets), C.c_uint64(seed), C.byref(v)))
+        return v.value
 
     def fmx_timings(self):
         t = FmxTimings()

@@ -214,6 +214,12 @@ typedef struct {
 } ccu_fmx_timings;
 int ccu_fmx_get_timings(const ccu_handle* h, ccu_fmx_timings* t);
 
+/* Diagnostic: the pileup kernels divide the nine likelihoods of a pileup by one sum with a shared refined
+ * reciprocal (sc_drop_seq.cpp:492-506 and sc_drop_seq.h:85-100 do nine divisions).  Runs `nsets` random
+ * operand sets on the device and returns how many of the 9*nsets quotients differ bitwise from IEEE
+ * division (must be 0). */
+int ccu_fmx_selftest_division(ccu_handle* h, int64_t nsets, uint64_t seed, int64_t* mismatches);
+
 /* Measured FP64 roofline denominator: runs a DFMA-saturating microkernel for about `ms`
  * milliseconds on the handle's device and returns TFLOP/s (2 flops per DFMA). */
 int ccu_measure_fp64_peak(ccu_handle* h, float ms, double* tflops);

@@ -62,6 +62,13 @@ def assert_fmx_results(res, ref, ref_llk, K):
     assert np.array_equal(res["jBest"][same], ref["jBest"][same])
 
 
+def test_shared_reciprocal_division_is_ieee(feng):
+    """F1/F3 divide nine likelihoods by one sum through a shared refined reciprocal: 9 * 2^26 quotients
+    must equal __ddiv_rn bit for bit (including the operand ranges that take the guarded slow path)."""
+    assert feng.selftest_division(1 << 26, seed=12345) == 0
+    assert feng.selftest_division(1 << 20, seed=7) == 0
+
+
 def test_pileups_bit_exact(feng):
     d = small_c4(nbcs=200, nsnps=500, rbar=300)  # ~300 reads over 500 SNPs: many multi-read entries
     upload(feng, d, 4)
