@@ -48,6 +48,8 @@ ccu::FmxDev fmx_view(const ccu_handle* h) {
   d.K = f->K;
   d.doublet_prior = f->doublet_prior;
   d.geno_error = f->geno_error;
+  d.log_sng_prior = std::log((1.0 - f->doublet_prior) / f->K);
+  d.log_dbl_prior = std::log(f->doublet_prior / f->K / (f->K - 1) * 2.0);
   d.nbcs = f->nbcs;
   d.nsnps = f->nsnps;
   d.nnz = f->nnz;

@@ -14,6 +14,7 @@ constexpr int kFmxMaxClust = 64;  // K(K+1)/2 <= 2080 pair likelihoods per dropl
 struct FmxDev {
   int32_t K;
   double doublet_prior, geno_error;
+  double log_sng_prior, log_dbl_prior;  // log((1-prior)/K), log(prior/K/(K-1)*2)  (cmd_cram_freemuxlet.cpp:462-463)
   int64_t nbcs, nsnps, nnz;
   // droplet store (all droplets)
   const int64_t* cell_ptr;   // [nbcs+1]
