@@ -19,12 +19,12 @@ struct FmxState {
   int64_t cell_begin = 0, cell_end = 0, snp_begin = 0, snp_end = 0;
   DevBuf cell_ptr, snp_idx, read_ptr, al, bq, af;
   DevBuf gl, cnt, logdenom, csc_ptr, csc_cell, csc_gl, csc_cnt, csc_lab;
-  DevBuf assign, stats, cgp, llk, results, scratch;
+  DevBuf assign, stats, cgp, llk, results, scan, scratch;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   ccu_fmx_timings tm = {};
   void release() {
     DevBuf* all[] = {&cell_ptr, &snp_idx, &read_ptr, &al, &bq, &af, &gl, &cnt, &logdenom, &csc_ptr, &csc_cell,
-                     &csc_gl, &csc_cnt, &csc_lab, &assign, &stats, &cgp, &llk, &results, &scratch};
+                     &csc_gl, &csc_cnt, &csc_lab, &assign, &stats, &cgp, &llk, &results, &scan, &scratch};
     for (DevBuf* b : all) b->release();
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
@@ -73,6 +73,7 @@ ccu::FmxDev fmx_view(const ccu_handle* h) {
   d.cgp = f->cgp.as<double>();
   d.llk = f->llk.as<double>();
   d.results = f->results.as<ccu_fmx_result>();
+  d.scan = f->scan.as<ccu::FmxScan>();
   d.cell_begin = f->cell_begin;
   d.cell_end = f->cell_end;
   d.snp_begin = f->snp_begin;
@@ -105,6 +106,7 @@ int reserve_shard_buffers(ccu_handle* h) {
   const int64_t npairs = (int64_t)f->K * (f->K + 1) / 2;
   CCU_CUDA(h, f->llk.reserve((size_t)ncell * npairs * sizeof(double) + 16));
   CCU_CUDA(h, f->results.reserve((size_t)ncell * sizeof(ccu_fmx_result) + 16));
+  CCU_CUDA(h, f->scan.reserve((size_t)ncell * sizeof(ccu::FmxScan) + 16));
   return 0;
 }
 
@@ -318,7 +320,7 @@ int ccu_fmx_estep_dev(ccu_handle* h, int32_t apply_geno_error) {
   cudaEventRecord(f->ev[0], h->stream);
   CCU_CUDA(h, ccu::launch_fmx_estep(d, h->stream));
   cudaEventRecord(f->ev[1], h->stream);
-  f->tm.launches += 2;
+  f->tm.launches += 3;  // posteriors, E-step, decision
   f->have_estep = true;
   return 0;
 }

@@ -11,6 +11,13 @@ namespace ccu {
 constexpr int kStatStride = 12;   // doubles per (cluster,SNP): gls[9], nreads, nref, nalt
 constexpr int kFmxMaxClust = 64;  // K(K+1)/2 <= 2080 pair likelihoods per droplet
 
+// Reduced scans of one droplet's pair likelihoods (E-step kernel -> decision kernel)
+struct FmxScan {
+  double sv1, sv2, dv1, dv2;      // best / next singlet and doublet log-likelihood
+  int32_t si1, si2, di1, di2;     // cluster of the singlets, pair index j(j+1)/2+k of the doublets (INT_MAX: none)
+  double ssum, asum, smax, vmax;  // sum exp(llk + prior - max) over singlets / all, and the two maxima
+};
+
 struct FmxDev {
   int32_t K;
   double doublet_prior, geno_error;
@@ -40,6 +47,7 @@ struct FmxDev {
   double* cgp;               // [nsnps][K][3] per-cluster genotype posteriors of the current iteration
   double* llk;               // [cells of the shard][K(K+1)/2]
   ccu_fmx_result* results;   // [cells of the shard]
+  FmxScan* scan;             // [cells of the shard]
   // shard
   int64_t cell_begin, cell_end, snp_begin, snp_end;
 };
