@@ -18,13 +18,13 @@ struct FmxState {
   int64_t nbcs = 0, nsnps = 0, nnz = 0, nreads = 0;
   int64_t cell_begin = 0, cell_end = 0, snp_begin = 0, snp_end = 0;
   DevBuf cell_ptr, snp_idx, read_ptr, al, bq, af;
-  DevBuf gl, cnt, logdenom, csc_ptr, csc_cell, csc_gl, csc_cnt, csc_lab;
+  DevBuf gl, cnt, logdenom, csc_ptr, csc_cell, csc_gl, csc_cnt;
   DevBuf assign, stats, cgp, llk, results, scan, scratch;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   ccu_fmx_timings tm = {};
   void release() {
     DevBuf* all[] = {&cell_ptr, &snp_idx, &read_ptr, &al, &bq, &af, &gl, &cnt, &logdenom, &csc_ptr, &csc_cell,
-                     &csc_gl, &csc_cnt, &csc_lab, &assign, &stats, &cgp, &llk, &results, &scan, &scratch};
+                     &csc_gl, &csc_cnt, &assign, &stats, &cgp, &llk, &results, &scan, &scratch};
     for (DevBuf* b : all) b->release();
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
@@ -67,7 +67,6 @@ ccu::FmxDev fmx_view(const ccu_handle* h) {
   d.csc_cell = f->csc_cell.as<int32_t>();
   d.csc_gl = f->csc_gl.as<double>();
   d.csc_cnt = f->csc_cnt.as<int4>();
-  d.csc_lab = f->csc_lab.as<int8_t>();
   d.assign = f->assign.as<int32_t>();
   d.stats = f->stats.as<double>();
   d.cgp = f->cgp.as<double>();
@@ -168,7 +167,6 @@ int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* ce
   CCU_CUDA(h, f->csc_cell.reserve((size_t)nnz * sizeof(int32_t) + 16));
   CCU_CUDA(h, f->csc_gl.reserve((size_t)nnz * 9 * sizeof(double) + 16));
   CCU_CUDA(h, f->csc_cnt.reserve((size_t)nnz * sizeof(int4) + 16));
-  CCU_CUDA(h, f->csc_lab.reserve((size_t)nnz + 16));
   CCU_CUDA(h, f->assign.reserve(nbcs * sizeof(int32_t) + 16));
   CCU_CUDA(h, f->stats.reserve((size_t)f->K * nsnps * ccu::kStatStride * sizeof(double) + 16));
   CCU_CUDA(h, f->cgp.reserve((size_t)f->K * nsnps * 3 * sizeof(double) + 16));
@@ -290,7 +288,7 @@ int ccu_fmx_mstep_dev(ccu_handle* h) {
   cudaEventRecord(f->ev[0], h->stream);
   CCU_CUDA(h, ccu::launch_fmx_mstep(fmx_view(h), h->stream));
   cudaEventRecord(f->ev[1], h->stream);
-  f->tm.launches += 2;  // label pass + fold
+  f->tm.launches += 1;
   f->have_stats = true;
   return 0;
 }

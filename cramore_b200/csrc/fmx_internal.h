@@ -40,7 +40,6 @@ struct FmxDev {
   int32_t* csc_cell;         // [nnz] droplet id, ascending inside a SNP
   double* csc_gl;            // [nnz][9]
   int4* csc_cnt;             // [nnz]
-  int8_t* csc_lab;           // [nnz] cluster label of the entry's droplet in the current M-step (-1: none)
   // EM state
   int32_t* assign;           // [nbcs] cluster of the droplet in the next M-step, or -1
   double* stats;             // [K][nsnps][kStatStride]
