@@ -12,7 +12,7 @@
 #include "fmx_internal.h"
 
 struct FmxState {
-  bool configured = false, uploaded = false, have_stats = false, have_estep = false;
+  bool configured = false, uploaded = false, have_stats = false, have_estep = false, have_post = false;
   int32_t K = 0;
   double doublet_prior = 0.5, geno_error = 0.0;
   int64_t nbcs = 0, nsnps = 0, nnz = 0, nreads = 0;
@@ -128,7 +128,7 @@ int ccu_fmx_configure(ccu_handle* h, int32_t nclust, double doublet_prior, doubl
   f->doublet_prior = doublet_prior;
   f->geno_error = geno_error;
   f->configured = true;
-  f->uploaded = f->have_stats = f->have_estep = false;
+  f->uploaded = f->have_stats = f->have_estep = f->have_post = false;
   return 0;
 }
 
@@ -153,7 +153,7 @@ int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* ce
   f->cell_end = nbcs;
   f->snp_begin = 0;
   f->snp_end = nsnps;
-  f->uploaded = f->have_stats = f->have_estep = false;
+  f->uploaded = f->have_stats = f->have_estep = f->have_post = false;
   CCU_CUDA(h, f->cell_ptr.reserve((nbcs + 1) * sizeof(int64_t)));
   CCU_CUDA(h, f->snp_idx.reserve(nnz * sizeof(int32_t) + 16));
   CCU_CUDA(h, f->read_ptr.reserve((nnz + 1) * sizeof(int64_t)));
@@ -314,13 +314,43 @@ int ccu_fmx_estep_dev(ccu_handle* h, int32_t apply_geno_error) {
   if (!f->have_stats) return ccu_fail(h, "ccu_fmx_estep: no cluster statistics yet (run ccu_fmx_mstep first)");
   CCU_CUDA(h, cudaSetDevice(h->device));
   const ccu::FmxDev d = fmx_view(h);
-  CCU_CUDA(h, ccu::launch_fmx_cgp(d, apply_geno_error, h->stream));
+  CCU_CUDA(h, ccu::launch_fmx_cgp(d, apply_geno_error, false, h->stream));
   cudaEventRecord(f->ev[0], h->stream);
   CCU_CUDA(h, ccu::launch_fmx_estep(d, h->stream));
   cudaEventRecord(f->ev[1], h->stream);
   f->tm.launches += 3;  // posteriors, E-step, decision
   f->have_estep = true;
   return 0;
+}
+
+int ccu_fmx_posteriors_dev(ccu_handle* h, int32_t apply_geno_error) {
+  if (int rc = need(h, true, "ccu_fmx_posteriors")) return rc;
+  FmxState* f = h->fmx;
+  if (!f->have_stats) return ccu_fail(h, "ccu_fmx_posteriors: no cluster statistics yet (run ccu_fmx_mstep first)");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  CCU_CUDA(h, ccu::launch_fmx_cgp(fmx_view(h), apply_geno_error, true, h->stream));
+  f->tm.launches += 1;
+  f->have_post = true;
+  return 0;
+}
+
+int ccu_fmx_estep_post_dev(ccu_handle* h) {
+  if (int rc = need(h, true, "ccu_fmx_estep_post")) return rc;
+  FmxState* f = h->fmx;
+  if (!f->have_post) return ccu_fail(h, "ccu_fmx_estep_post: no posteriors yet (run ccu_fmx_posteriors_dev first)");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  cudaEventRecord(f->ev[0], h->stream);
+  CCU_CUDA(h, ccu::launch_fmx_estep(fmx_view(h), h->stream));
+  cudaEventRecord(f->ev[1], h->stream);
+  f->tm.launches += 2;  // E-step, decision
+  f->have_estep = true;
+  return 0;
+}
+
+void* ccu_fmx_post_dev(ccu_handle* h, int64_t* n_doubles) {
+  if (!h || !h->fmx || !h->fmx->uploaded) return nullptr;
+  if (n_doubles) *n_doubles = (int64_t)h->fmx->K * h->fmx->nsnps * 3;
+  return h->fmx->cgp.p;
 }
 
 int ccu_fmx_download_results(ccu_handle* h, ccu_fmx_result* out) {

@@ -59,7 +59,7 @@ cudaError_t launch_fmx_entry_cells(const FmxDev& d, int32_t* ent_cell, cudaStrea
 cudaError_t launch_fmx_build_csc(const FmxDev& d, const int32_t* sorted_snp, const int32_t* sorted_ent,
                                  const int32_t* ent_cell, cudaStream_t st);
 cudaError_t launch_fmx_mstep(const FmxDev& d, cudaStream_t st);
-cudaError_t launch_fmx_cgp(const FmxDev& d, int apply_geno_error, cudaStream_t st);
+cudaError_t launch_fmx_cgp(const FmxDev& d, int apply_geno_error, bool slab_only, cudaStream_t st);
 cudaError_t launch_fmx_estep(const FmxDev& d, cudaStream_t st);
 // int32 count of droplets whose (type, jBest, kBest) differ between two result arrays
 // counts bitwise differences between the shared-reciprocal division of the pileup kernels and __ddiv_rn

@@ -44,7 +44,8 @@ ABI_SYMBOLS = [
     "ccu_fmx_configure", "ccu_fmx_upload", "ccu_fmx_set_shard", "ccu_fmx_lmix", "ccu_fmx_get_pileups",
     "ccu_fmx_mstep", "ccu_fmx_estep", "ccu_fmx_get_llk", "ccu_fmx_get_clusters", "ccu_fmx_stats_dev",
     "ccu_fmx_assign_dev", "ccu_fmx_mstep_dev", "ccu_fmx_estep_dev", "ccu_fmx_download_results", "ccu_fmx_run_em",
-    "ccu_fmx_get_timings", "ccu_fmx_selftest_division",
+    "ccu_fmx_get_timings", "ccu_fmx_selftest_division", "ccu_fmx_post_dev", "ccu_fmx_posteriors_dev",
+    "ccu_fmx_estep_post_dev",
 ]
 
 
@@ -62,7 +63,7 @@ def load_library():
         lib.ccu_demux_best_header.restype = C.c_char_p
         for name in ABI_SYMBOLS:
             fn = getattr(lib, name)
-            if name in ("ccu_fmx_stats_dev", "ccu_fmx_assign_dev"):
+            if name in ("ccu_fmx_stats_dev", "ccu_fmx_assign_dev", "ccu_fmx_post_dev"):
                 fn.restype = C.c_void_p
             elif name not in ("ccu_last_error", "ccu_demux_best_header"):
                 fn.restype = C.c_int
@@ -278,6 +279,17 @@ class FreemuxEngine(DemuxEngine):
         n = C.c_int64(0)
         p = self.lib.ccu_fmx_assign_dev(self.h, C.byref(n))
         return p, n.value
+
+    def post_dev(self):
+        n = C.c_int64(0)
+        p = self.lib.ccu_fmx_post_dev(self.h, C.byref(n))
+        return p, n.value
+
+    def posteriors_dev(self, apply_geno_error=False):
+        self._check(self.lib.ccu_fmx_posteriors_dev(self.h, C.c_int32(1 if apply_geno_error else 0)))
+
+    def estep_post_dev(self):
+        self._check(self.lib.ccu_fmx_estep_post_dev(self.h))
 
     def mstep_dev(self):
         self._check(self.lib.ccu_fmx_mstep_dev(self.h))

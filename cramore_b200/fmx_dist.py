@@ -4,9 +4,14 @@
   M-step  : SNP slabs.  snp_droplet_pileup::merge (sc_drop_seq.h:77-101) clamps after every droplet, so
             a cluster statistic is an ORDERED fold over droplets and cannot be formed by summing
             per-shard partials.  Every rank therefore folds all droplets, in ascending id, for its own
-            SNP slab and leaves zeros elsewhere; the sum-allreduce (NCCL over NVLink, in place on the
-            engine's statistics array) then assembles the full array bit-exactly on every rank.
-  per iteration: E-step -> all-gather of the assignment vector -> M-step -> all-reduce of the statistics.
+            SNP slab and leaves zeros elsewhere; a sum-allreduce (NCCL over NVLink, in place on the
+            engine's array) then assembles the full array bit-exactly on every rank.
+  exchange: the E-step reads the statistics only through the per-(SNP, cluster) genotype posteriors
+            (cmd_cram_freemuxlet.cpp:476-489; 3 doubles where the statistics have 12), so each rank derives
+            the posteriors of its slab and THAT array is all-reduced every iteration; the statistics array
+            itself is all-reduced once, after the last M-step (it is only needed for the cluster VCF).
+  per iteration: posteriors of the slab -> all-reduce -> E-step -> all-gather of the assignment vector -> M-step.
+  exchange="stats" keeps the heavier form (all-reduce of the 12-double statistics every iteration).
 
 The engine object only has to provide the methods used below, which lets the CPU test suite drive the
 same loop over gloo with a numpy stand-in."""
@@ -34,6 +39,15 @@ def device_views(eng, device):
     return stats, assign
 
 
+def posterior_view(eng, device):
+    """torch tensor aliasing the engine's per-(SNP, cluster) posterior array [nsnps][K][3] (float64)."""
+    import torch
+    pp, pn = eng.post_dev()
+    post = torch.as_tensor(_DevArray(pp, pn, "<f8"), device=device)
+    assert post.data_ptr() == pp
+    return post
+
+
 def snp_slabs(snp_idx, nsnps, world):
     """Contiguous SNP ranges with ~equal numbers of (cell,SNP) entries."""
     counts = np.bincount(np.asarray(snp_idx, np.int64), minlength=nsnps)
@@ -42,10 +56,11 @@ def snp_slabs(snp_idx, nsnps, world):
 
 
 def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign, niter=10,
-                       geno_error_every_iter=False, group=None, sync=None):
-    """cmd_cram_freemuxlet.cpp:359-370 + :457-653 across ranks.  `stats`/`assign` are torch tensors
-    aliasing the engine's arrays (device_views, or CPU tensors of a stand-in engine).  Returns this
-    rank's per-droplet results and every rank's results gathered in barcode order."""
+                       geno_error_every_iter=False, group=None, sync=None, post=None, exchange=None):
+    """cmd_cram_freemuxlet.cpp:359-370 + :457-653 across ranks.  `stats`/`assign` (and `post`) are torch
+    tensors aliasing the engine's arrays (device_views / posterior_view, or CPU tensors of a stand-in
+    engine).  exchange: "posteriors" (default when `post` is given) or "stats".  Returns this rank's
+    per-droplet results and every rank's results gathered in barcode order."""
     import torch
     import torch.distributed as dist
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -54,6 +69,10 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
     sb, se = snp_ranges[rank]
     eng.set_shard(cb, ce, sb, se)
     sync = sync or (lambda: None)
+    if exchange is None:
+        exchange = "posteriors" if post is not None else "stats"
+    if exchange not in ("posteriors", "stats") or (exchange == "posteriors" and post is None):
+        raise ValueError("exchange must be 'stats' or 'posteriors' (the latter needs the posterior tensor)")
 
     def exchange_assign():
         # each rank owns assign[cb:ce]; a sum of (value + 1) over zero-filled vectors is an all-gather
@@ -71,14 +90,30 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
         sync()
         dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
 
+    def exchange_post():
+        if not multi:
+            return
+        sync()
+        dist.all_reduce(post, op=dist.ReduceOp.SUM, group=group)
+
     assign.copy_(torch.as_tensor(np.ascontiguousarray(init_assign, np.int32)).to(assign.device))
     eng.mstep_dev()
-    exchange_stats()
+    if exchange == "stats":
+        exchange_stats()
     for it in range(niter):
-        eng.estep_dev(bool(geno_error_every_iter) or (it + 1 == niter))
+        apply = bool(geno_error_every_iter) or (it + 1 == niter)
+        if exchange == "stats":
+            eng.estep_dev(apply)
+        else:
+            eng.posteriors_dev(apply)
+            exchange_post()
+            eng.estep_post_dev()
         exchange_assign()
         eng.mstep_dev()
-        exchange_stats()
+        if exchange == "stats":
+            exchange_stats()
+    if exchange != "stats":
+        exchange_stats()  # once: the full statistics are only needed for the output
     sync()
     local = eng.download_results()
     if not multi:

@@ -194,6 +194,16 @@ int ccu_fmx_get_clusters(ccu_handle* h, ccu_pileup* out /* [K][nsnps] */);
  * per iteration:  ccu_fmx_estep_dev -> all-gather of the assignment vector (each rank wrote its own
  * droplet range) -> ccu_fmx_mstep_dev -> sum-allreduce of the statistics array (NCCL, in place). */
 void* ccu_fmx_stats_dev(ccu_handle* h, int64_t* n_doubles);
+/* Lighter per-iteration exchange: the E-step reads the statistics only through the per-(SNP, cluster) genotype
+ * posteriors of cmd_cram_freemuxlet.cpp:476-489 (3 doubles instead of 12).  ccu_fmx_posteriors_dev computes
+ * them for this shard's SNP slab from its slab of the statistics and zeroes the rest of the array
+ * double [nsnps][K][3] returned by ccu_fmx_post_dev; after a sum-allreduce of that array
+ * ccu_fmx_estep_post_dev runs the E-step + decision from it.  Per iteration:
+ * ccu_fmx_posteriors_dev -> allreduce(post) -> ccu_fmx_estep_post_dev -> all-gather(assign) -> ccu_fmx_mstep_dev;
+ * the statistics array itself is all-reduced once, after the last iteration (cluster VCF output). */
+void* ccu_fmx_post_dev(ccu_handle* h, int64_t* n_doubles);
+int ccu_fmx_posteriors_dev(ccu_handle* h, int32_t apply_geno_error);
+int ccu_fmx_estep_post_dev(ccu_handle* h);
 void* ccu_fmx_assign_dev(ccu_handle* h, int64_t* n_int32);
 int ccu_fmx_mstep_dev(ccu_handle* h);
 int ccu_fmx_estep_dev(ccu_handle* h, int32_t apply_geno_error);

@@ -218,3 +218,38 @@ np.save(sys.argv[2], e.fmx_llk()); np.save(sys.argv[3], nxt)
                 out[mode] = (np.load(f1), np.load(f2))
             np.testing.assert_allclose(out["mma"][0], out["rows"][0], rtol=1e-12, atol=1e-12)
             assert np.array_equal(out["mma"][1], out["rows"][1])
+
+
+def test_posterior_exchange_path_is_bitwise_equal(feng):
+    """ccu_fmx_posteriors_dev + ccu_fmx_estep_post_dev (the multi-GPU per-iteration form) give the results of
+    ccu_fmx_estep_dev bitwise; slab posteriors are disjoint, so their sum over slabs is the full array."""
+    K = 7
+    d = small_c4(nbcs=200, nsnps=1200, rbar=150)
+    upload(feng, d, K, 0.1)
+    assign = noisy_init(d, K)
+    feng.mstep(assign)
+    feng.estep_dev(True)
+    ref = feng.download_results()
+    feng.posteriors_dev(True)
+    feng.estep_post_dev()
+    assert np.array_equal(feng.download_results(), ref)
+    ptr, n = feng.post_dev()
+    assert n == d["nsnps"] * K * 3
+
+    def post_host():
+        import torch
+        from cramore_b200.fmx_dist import posterior_view
+        feng.synchronize()
+        return posterior_view(feng, torch.device("cuda", 0)).cpu().numpy().reshape(d["nsnps"], K, 3).copy()
+
+    full = post_host()
+    total = np.zeros_like(full)
+    for b, e in ((0, 500), (500, 1200)):
+        feng.set_shard(0, d["nbcs"], b, e)
+        feng.mstep(assign)
+        feng.posteriors_dev(True)
+        part = post_host()
+        assert np.all(part[:b] == 0) and np.all(part[e:] == 0)
+        total += part
+    assert np.array_equal(total, full)
+    feng.set_shard(0, d["nbcs"], 0, d["nsnps"])

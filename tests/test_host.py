@@ -177,6 +177,7 @@ class OracleEngine:   # numpy stand-in with the FreemuxEngine methods the driver
     def __init__(self):
         self.stats = torch.zeros(K * d["nsnps"] * 12, dtype=torch.float64)
         self.assign = torch.full((d["nbcs"],), -1, dtype=torch.int32)
+        self.post = torch.zeros(d["nsnps"] * K * 3, dtype=torch.float64)
     def set_shard(self, cb, ce, sb, se):
         self.cb, self.ce, self.sb, self.se = cb, ce, sb, se
     def _clust(self):
@@ -197,6 +198,22 @@ class OracleEngine:   # numpy stand-in with the FreemuxEngine methods the driver
         self.res = res[self.cb:self.ce]
         a = np.where(self.res["type"] == 0, self.res["jBest"], -1).astype(np.int32)
         self.assign[self.cb:self.ce] = torch.from_numpy(a)
+    # posterior exchange: the oracle's E-step reads the statistics only through gls[0], gls[4], gls[8], so the
+    # stand-in's "posterior" array carries exactly those three numbers per (SNP, cluster); slab only, zeros elsewhere
+    def posteriors_dev(self, apply):
+        self.apply = apply
+        s = self.stats.numpy().reshape(K, d["nsnps"], 12)
+        p = np.zeros((d["nsnps"], K, 3))
+        p[self.sb:self.se] = s[:, self.sb:self.se][..., [0, 4, 8]].transpose(1, 0, 2)
+        self.post.copy_(torch.from_numpy(p.reshape(-1)))
+    def estep_post_dev(self):
+        p = self.post.numpy().reshape(d["nsnps"], K, 3)
+        c = np.zeros((K, d["nsnps"]), pyoracle.PILEUP_DTYPE)
+        c["gls"][..., [0, 4, 8]] = p.transpose(1, 0, 2)
+        res, _ = pyoracle.fmx_estep(d["cell_ptr"], d["snp_idx"], plp, d["af"], c, 0.5, GE, self.apply)
+        self.res = res[self.cb:self.ce]
+        a = np.where(self.res["type"] == 0, self.res["jBest"], -1).astype(np.int32)
+        self.assign[self.cb:self.ce] = torch.from_numpy(a)
     def download_results(self):
         return self.res
 
@@ -206,9 +223,17 @@ world = dist.get_world_size()
 rng = np.random.default_rng(1)
 init = (d["s1"] %% K).astype(np.int32)
 init[rng.random(len(init)) < 0.4] = -1
-eng = OracleEngine()
-local, full = run_em_distributed(eng, eng.stats, eng.assign, balanced_ranges(d["cell_ptr"], world),
-                                 snp_slabs(d["snp_idx"], d["nsnps"], world), init, niter=NITER)
+for mode in ("stats", "posteriors"):
+    eng = OracleEngine()
+    local, full = run_em_distributed(eng, eng.stats, eng.assign, balanced_ranges(d["cell_ptr"], world),
+                                     snp_slabs(d["snp_idx"], d["nsnps"], world), init, niter=NITER,
+                                     post=eng.post, exchange=mode)
+    results = full if mode == "stats" else results
+    assert np.array_equal(full, results), "the two exchange forms differ"
+    if mode == "stats":
+        stats_first = eng.stats.clone()
+    else:
+        assert torch.equal(eng.stats, stats_first), "final statistics differ between the exchange forms"
 # single-process reference loop
 clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], plp, init, K, d["nsnps"])
 for it in range(NITER):

@@ -27,11 +27,12 @@ def main():
     ap.add_argument("--nsnps", type=int, default=None)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--exchange", default="posteriors", choices=["posteriors", "stats"])
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
     from cramore_b200 import FreemuxEngine
-    from cramore_b200.fmx_dist import device_views, run_em_distributed, snp_slabs
+    from cramore_b200.fmx_dist import device_views, posterior_view, run_em_distributed, snp_slabs
     from cramore_b200.shard import balanced_ranges
     from cramore_b200.synth import make_dataset
 
@@ -61,6 +62,7 @@ def main():
     t_upload = time.perf_counter() - t0
     setup = eng.fmx_timings()
     stats, assign = device_views(eng, dev)
+    post = posterior_view(eng, dev)
     cell_ranges = balanced_ranges(d["cell_ptr"], world)
     slabs = snp_slabs(d["snp_idx"], d["nsnps"], world)
 
@@ -70,7 +72,8 @@ def main():
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        loc, full = run_em_distributed(eng, stats, assign, cell_ranges, slabs, init, niter=args.iters)
+        loc, full = run_em_distributed(eng, stats, assign, cell_ranges, slabs, init, niter=args.iters, post=post,
+                                       exchange=args.exchange)
         e1.record()
         torch.cuda.synchronize()
         return loc, full, e0.elapsed_time(e1)
@@ -90,6 +93,7 @@ def main():
         timed("mstep_ms", lambda: eng.mstep_dev())
         if world > 1:
             timed("allreduce_stats_ms", lambda: dist.all_reduce(stats))
+            timed("allreduce_posteriors_ms", lambda: dist.all_reduce(post))
         return out
 
     run()  # warm-up (NCCL channels, allocations)
@@ -109,11 +113,29 @@ def main():
         ref_eng.close()
     if rank == 0:
         nnz = int(d["cell_ptr"][-1])
+        # HBM roofline of the two per-iteration kernels, algorithmic bytes of SURVEY 8(d):
+        #   E-step: 84 B pileup + 24*K B gathered cluster posteriors per entry
+        #   M-step: 84 B pileup per entry in, 84 B per (cluster, observed SNP) out
+        try:
+            hbm_peak, peak_src = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
+        nobs = int(np.unique(d["snp_idx"]).size)
+        e_bytes = (84 + 24 * K) * nnz / world
+        m_bytes = (84 * nnz + 84 * K * nobs) / world
+        roof = []
+        for name, key, nbytes in (("fmx_estep_rows_kernel (F2)", "estep_ms", e_bytes),
+                                  ("fmx_mstep_kernel (F3)", "mstep_ms", m_bytes)):
+            gbs = nbytes / (phases[key] * 1e-3) / 1e9
+            roof.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": gbs / hbm_peak, "algorithmic_bytes_per_launch": int(nbytes), "ms": phases[key],
+                         "peak_source": peak_src})
         line = {"metric": "freemuxlet EM iterations/s", "value": args.iters / (ms * 1e-3), "unit": "iter/s",
                 "n_gpus": world, "iters": args.iters, "ms_per_iter": ms / args.iters,
                 "config": {"workload": "C4 freemuxlet: K=%d, %d barcodes, %d SNPs, %d entries" %
                                        (K, d["nbcs"], d["nsnps"], nnz)},
-                "stats_allreduce_bytes": int(stats.numel() * 8), "setup": setup, "upload_s": t_upload, "phase_ms": phases,
+                "exchange": args.exchange, "stats_allreduce_bytes": int(stats.numel() * 8),
+                "posterior_allreduce_bytes": int(post.numel() * 8), "setup": setup, "upload_s": t_upload, "phase_ms": phases, "roofline": roof,
                 "singlets": int((full["type"] == 0).sum()), "doublets": int((full["type"] == 1).sum()),
                 "matches_single_gpu": ok}
         print(json.dumps(line), flush=True)
