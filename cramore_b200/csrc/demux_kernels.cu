@@ -804,6 +804,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
   // affine factor is >= err(maxbq)/3, i.e. abits = ceil(0.3322*maxbq + 1.585) + 1, at most 34.
   constexpr int kBudget = 960, kGenBits = 34;
   const int abits = min(kGenBits, (int)(0.33220 * (double)d.maxbq[0] + 3.585));
+  const int inv_abits = 65536 / abits;  // floor: (budget * inv_abits) >> 16 never exceeds budget / abits
   int budget = kBudget;
   bool pair_ok = true;  // every alpha within [0, 0.5]
   for (int n = 0; n < d.nA; ++n) pair_ok = pair_ok && (s_alpha[n] >= 0.0) && (s_alpha[n] <= 0.5);
@@ -847,7 +848,9 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
     // the thread's TK consecutive samples k sit inside one 32-sample part
     const double* fk_base = reinterpret_cast<const double*>(raw + stage * Cfg::STAGE_BYTES + Cfg::PART_BYTES) +
                             ((kidx * TK) >> 5) * (Cfg::PART_BYTES / 8) + ((kidx * TK) & 31);
-    const double* sal = s_alpha + n0;
+    // volatile: the alphas must be re-read from shared memory (broadcast LDS) inside the loop; hoisted into
+    // registers they cost 2*AC of the 112 and ptxas then funnels every product through one temporary
+    const volatile double* sal = s_alpha + n0;
     auto load_fk = [&](int s, double* fk) {
       if constexpr (TK == 1) {
         fk[0] = fk_base[s * 32];
@@ -870,7 +873,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
         renorm_all();
         budget = kBudget;
       }
-      const int run = min(cnt - s, budget / abits);  // SNPs that fit into the budget
+      const int run = min(cnt - s, (budget * inv_abits) >> 16);  // SNPs that fit into the budget (>= 1 here)
       budget -= run * abits;
       const int s_end = s + run;
       if (pair_ok) {
