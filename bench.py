@@ -345,8 +345,10 @@ def main():
     k2_avg = float(np.mean(k2_ms))
     achieved = flops_launch / (k2_avg * 1e-3) / 1e12
     # FP64 instructions the kernel really issues: every ordered pair of the padded sample
-    # tiles; affine entries (<= 1 informative read) cost 1 DADD per (j,k) + 2 per (j,k,alpha), general
-    # entries 4 per (j,k,alpha) + 9 per (k,alpha) per j-tile for T
+    # tiles.  Affine entries (<= 1 informative read) go two SNPs at a time: a thread tile of 2 j x TK k x AC
+    # alphas costs 2 + TK*(10 + 6*AC) instructions per SNP pair (1.8 per likelihood and SNP at AC=10, TK=1;
+    # the odd SNP of a run costs 2.1, not counted); general entries 4 per (j,k,alpha) + 9 per (k,alpha) per
+    # j-tile for T
     al_ne2 = (np.asarray(d["al"]) != 2).astype(np.int64)
     csum = np.concatenate([[0], np.cumsum(al_ne2)])
     neff = csum[np.asarray(d["read_ptr"][1:])] - csum[np.asarray(d["read_ptr"][:-1])]
@@ -357,7 +359,8 @@ def main():
     ac = min((10, 5, 2, 1), key=lambda a: ((nd + a - 1) // a * a, -a))
     nd_pad = (nd + ac - 1) // ac * ac
     nac = nd_pad // ac
-    instr_aff = nvp * nvp * (nac + 2 * nd_pad)
+    tk = {10: 1, 5: 2, 2: 4, 1: 8}[ac]
+    instr_aff = (nvp // 2) * (nvp // tk) * nac * (1 + tk * (5 + 3 * ac))
     instr_gen = nvp * nvp * 4 * nd_pad + (nvp // 32) * nvp * nd_pad * 9
     executed = 2.0 * (n_aff * instr_aff + n_gen * instr_gen)
     traffic = None

@@ -11,6 +11,13 @@
 #include "ccu_handle.h"
 #include "fmx_internal.h"
 
+struct FmxPairs;  // fmx_init.cu
+void ccu_fmx_pairs_release(FmxPairs*& p);
+int ccu_fmx_pairs_build(ccu_handle* h, const ccu::FmxDev& d, FmxPairs*& ps, int64_t* npairs_out);
+int ccu_fmx_pairs_download(ccu_handle* h, FmxPairs* ps, ccu_pair_dist* out);
+float ccu_fmx_pairs_ms(const FmxPairs* ps);
+int64_t ccu_fmx_pairs_records(const FmxPairs* ps);
+
 struct FmxState {
   bool configured = false, uploaded = false, have_stats = false, have_estep = false, have_post = false;
   int32_t K = 0;
@@ -22,7 +29,9 @@ struct FmxState {
   DevBuf assign, stats, cgp, llk, results, scan, scratch;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   ccu_fmx_timings tm = {};
+  FmxPairs* pairs = nullptr;
   void release() {
+    ccu_fmx_pairs_release(pairs);
     DevBuf* all[] = {&cell_ptr, &snp_idx, &read_ptr, &al, &bq, &af, &gl, &cnt, &logdenom, &csc_ptr, &csc_cell,
                      &csc_gl, &csc_cnt, &assign, &stats, &cgp, &llk, &results, &scan, &scratch};
     for (DevBuf* b : all) b->release();
@@ -462,6 +471,23 @@ int ccu_fmx_run_em(ccu_handle* h, const int32_t* init_assign, int32_t niter, int
   f->tm.ms_mstep = ms_m / (it > 0 ? it : 1);
   if (iters_run) *iters_run = it;
   return ccu_fmx_download_results(h, out);
+}
+
+int ccu_fmx_pair_distances(ccu_handle* h, int64_t* npairs, int64_t* nrecords, float* ms) {
+  if (int rc = need(h, true, "ccu_fmx_pair_distances")) return rc;
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  FmxState* f = h->fmx;
+  if (int rc = ccu_fmx_pairs_build(h, fmx_view(h), f->pairs, npairs)) return rc;
+  if (nrecords) *nrecords = ccu_fmx_pairs_records(f->pairs);
+  if (ms) *ms = ccu_fmx_pairs_ms(f->pairs);
+  f->tm.launches += 6;
+  return 0;
+}
+
+int ccu_fmx_get_pair_distances(ccu_handle* h, ccu_pair_dist* out) {
+  if (int rc = need(h, true, "ccu_fmx_get_pair_distances")) return rc;
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  return ccu_fmx_pairs_download(h, h->fmx->pairs, out);
 }
 
 int ccu_fmx_selftest_division(ccu_handle* h, int64_t nsets, uint64_t seed, int64_t* mismatches) {

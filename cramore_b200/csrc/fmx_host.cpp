@@ -1,0 +1,122 @@
+// fmx_host.cpp -- host half of freemuxlet's initial clustering (cmd_cram_freemuxlet.cpp:166-346) on the
+// sparse pair list that ccu_fmx_pair_distances produces.  No GPU, no handle.
+//
+// The reference walks a dense nbcs x nbcs matrix; a pair of droplets without a common SNP has llk0 = llk2 = 0
+// there and casts no vote, so walking only the recorded pairs gives the same votes.  What has to be kept is the
+// ORDER in which the +-1 votes are added to the (tiny random) starting values, because the sums are doubles:
+// ascending position in the score order for the greedy pass (:262), ascending droplet id for the sweeps (:311).
+// Random numbers are libc rand() in the reference's call order: nclust per visited droplet, and the
+// libstdc++ std::random_shuffle of every sweep (rand() % (i + 1) for i = 1 .. n - 1, swap when different).
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <numeric>
+#include <vector>
+
+#include "cramore_cuda.h"
+
+namespace {
+
+struct Nbr {
+  int32_t other;
+  double bf;  // llk2 - llk0
+};
+
+}  // namespace
+
+extern "C" int ccu_fmx_initial_clusters(int64_t nbcs, int32_t nclust, const double* cell_scores, int64_t npairs,
+                                        const ccu_pair_dist* pairs, double bf_thres, double frac_init_clust,
+                                        int32_t iter_init, int32_t keep_init_missing, int32_t have_init,
+                                        int32_t seed, int32_t* clusts) {
+  if (nbcs < 0 || nclust < 1 || npairs < 0 || (nbcs > 0 && (!cell_scores || !clusts)) || (npairs > 0 && !pairs)) return 1;
+  for (int64_t p = 0; p < npairs; ++p)
+    if (pairs[p].id1 <= pairs[p].id2 || pairs[p].id2 < 0 || pairs[p].id1 >= nbcs) return 1;
+  if (seed >= 0) srand((unsigned)seed);
+  const int64_t n = nbcs;
+
+  // symmetric adjacency, every row in ascending id of the other droplet (pairs are sorted by (id1, id2): a
+  // counting pass keeps that order on both sides)
+  std::vector<int64_t> ptr(n + 1, 0);
+  for (int64_t p = 0; p < npairs; ++p) {
+    ++ptr[pairs[p].id1 + 1];
+    ++ptr[pairs[p].id2 + 1];
+  }
+  for (int64_t i = 0; i < n; ++i) ptr[i + 1] += ptr[i];
+  std::vector<Nbr> adj(ptr[n]);
+  {
+    std::vector<int64_t> fill(ptr.begin(), ptr.end() - 1);
+    // first the smaller ids (id2 of row id1), then the larger ones: two passes keep each row ascending
+    for (int64_t p = 0; p < npairs; ++p) adj[fill[pairs[p].id1]++] = {pairs[p].id2, pairs[p].llk2 - pairs[p].llk0};
+    for (int64_t p = 0; p < npairs; ++p) adj[fill[pairs[p].id2]++] = {pairs[p].id1, pairs[p].llk2 - pairs[p].llk0};
+  }
+  for (int64_t i = 0; i < n; ++i)
+    if (!std::is_sorted(adj.begin() + ptr[i], adj.begin() + ptr[i + 1], [](const Nbr& a, const Nbr& b) { return a.other < b.other; }))
+      std::sort(adj.begin() + ptr[i], adj.begin() + ptr[i + 1], [](const Nbr& a, const Nbr& b) { return a.other < b.other; });
+
+  std::vector<double> votes(nclust);
+  auto elect = [&]() {  // :279-287, :322-330: first maximum
+    int32_t elected = 0;
+    double maxvote = votes[0];
+    for (int32_t j = 1; j < nclust; ++j)
+      if (maxvote < votes[j]) {
+        elected = j;
+        maxvote = votes[j];
+      }
+    return elected;
+  };
+
+  if (!have_init) {
+    // droplets by singlet score, larger id first on ties (sc_drop_comp_t)
+    std::vector<int32_t> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+      const double cmp = cell_scores[a] - cell_scores[b];
+      if (cmp != 0) return cmp > 0;
+      return a > b;
+    });
+    std::vector<int32_t> rank(n);
+    for (int64_t i = 0; i < n; ++i) rank[order[i]] = (int32_t)i;
+    for (int64_t i = 0; i < n; ++i) clusts[i] = -1;
+    std::vector<std::pair<int32_t, double>> earlier;  // (rank, bf) of the droplets voted on
+    for (int64_t i = 0; i < n; ++i) {
+      if ((double)i > (double)n * frac_init_clust) continue;  // :249
+      const int32_t si = order[i];
+      for (int32_t j = 0; j < nclust; ++j) votes[j] = rand() / (RAND_MAX + 1.) / 1000.;  // :258-260
+      earlier.clear();
+      for (int64_t t = ptr[si]; t < ptr[si + 1]; ++t)
+        if (rank[adj[t].other] < (int32_t)i) earlier.emplace_back(rank[adj[t].other], adj[t].bf);
+      std::sort(earlier.begin(), earlier.end(), [](const std::pair<int32_t, double>& a, const std::pair<int32_t, double>& b) { return a.first < b.first; });
+      for (const auto& e : earlier) {  // :262-278 in the order j = 0 .. i-1
+        const int32_t c = clusts[order[e.first]];
+        if (-e.second > bf_thres) votes[c] -= 1.0;
+        else if (e.second > bf_thres) votes[c] += 1.0;
+      }
+      clusts[si] = elect();
+    }
+  }
+
+  if (iter_init > 0) {
+    std::vector<int32_t> orand(n);
+    for (int iter = 0; iter < 10; ++iter) {  // :296 (the count is a literal 10)
+      std::iota(orand.begin(), orand.end(), 0);
+      for (int64_t i = 1; i < n; ++i) {  // std::random_shuffle(orand.begin(), orand.end()) of libstdc++
+        const int64_t j = rand() % (i + 1);
+        if (i != j) std::swap(orand[i], orand[j]);
+      }
+      for (int64_t i = 0; i < n; ++i) {
+        const int32_t si = orand[i];
+        for (int32_t j = 0; j < nclust; ++j) votes[j] = rand() / (RAND_MAX + 1.) / 1000.;
+        for (int64_t t = ptr[si]; t < ptr[si + 1]; ++t) {  // :311-320, j ascending
+          const int32_t c = clusts[adj[t].other];
+          if (c >= 0) {
+            if (adj[t].bf > bf_thres) ++votes[c];
+            else if (adj[t].bf < 0 - bf_thres) --votes[c];
+          }
+        }
+        const int32_t elected = elect();
+        if (clusts[si] >= 0 || !keep_init_missing) clusts[si] = elected;  // :332-336
+      }
+    }
+  }
+  return 0;
+}

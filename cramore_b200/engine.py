@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "ccu_fmx_mstep", "ccu_fmx_estep", "ccu_fmx_get_llk", "ccu_fmx_get_clusters", "ccu_fmx_stats_dev",
     "ccu_fmx_assign_dev", "ccu_fmx_mstep_dev", "ccu_fmx_estep_dev", "ccu_fmx_download_results", "ccu_fmx_run_em",
     "ccu_fmx_get_timings", "ccu_fmx_selftest_division", "ccu_fmx_post_dev", "ccu_fmx_posteriors_dev",
-    "ccu_fmx_estep_post_dev",
+    "ccu_fmx_estep_post_dev", "ccu_fmx_pair_distances", "ccu_fmx_get_pair_distances", "ccu_fmx_initial_clusters",
 ]
 
 
@@ -197,6 +197,10 @@ PILEUP_DTYPE = np.dtype([
     ("nreads", "<i4"), ("nref", "<i4"), ("nalt", "<i4"), ("_pad", "<i4"),
     ("gls", "<f8", (9,)), ("logdenom", "<f8")])
 
+PAIR_DIST_DTYPE = np.dtype([
+    ("id1", "<i4"), ("id2", "<i4"), ("nsnps", "<i4"), ("nread1", "<i4"), ("nread2", "<i4"), ("_pad", "<i4"),
+    ("llk0", "<f8"), ("llk2", "<f8")])
+
 FMX_RESULT_DTYPE = np.dtype([
     ("sBest", "<i4"), ("sNext", "<i4"), ("dBest1", "<i4"), ("dBest2", "<i4"), ("dNext1", "<i4"),
     ("dNext2", "<i4"), ("type", "<i4"), ("jBest", "<i4"), ("kBest", "<i4"), ("jNext", "<i4"),
@@ -310,6 +314,15 @@ class FreemuxEngine(DemuxEngine):
                                             C.c_int32(int(stop_when_stable)), _ptr(out), C.byref(it)))
         return out, it.value
 
+    def pair_distances(self):
+        """Sparse dropDs matrix of cmd_cram_freemuxlet.cpp:172-221: records sorted by (id1 > id2)."""
+        n, nrec, ms = C.c_int64(0), C.c_int64(0), C.c_float(0)
+        self._check(self.lib.ccu_fmx_pair_distances(self.h, C.byref(n), C.byref(nrec), C.byref(ms)))
+        out = np.zeros(n.value, PAIR_DIST_DTYPE)
+        self._check(self.lib.ccu_fmx_get_pair_distances(self.h, _ptr(out)))
+        self.pair_stats = {"pairs": n.value, "records": nrec.value, "ms": ms.value}
+        return out
+
     def selftest_division(self, nsets=1 << 22, seed=1):
         v = C.c_int64(-1)
         self._check(self.lib.ccu_fmx_selftest_division(self.h, C.c_int64(nsets), C.c_uint64(seed), C.byref(v)))
@@ -319,6 +332,23 @@ class FreemuxEngine(DemuxEngine):
         t = FmxTimings()
         self._check(self.lib.ccu_fmx_get_timings(self.h, C.byref(t)))
         return t.as_dict()
+
+
+def initial_clusters(cell_scores, pairs, nclust, bf_thres=5.41, frac_init_clust=1.0, iter_init=10,
+                     keep_init_missing=False, init=None, seed=1):
+    """cmd_cram_freemuxlet.cpp:223-346 on the sparse pair list (host code of libcramore_cuda.so; uses rand())."""
+    lib = load_library()
+    scores = np.ascontiguousarray(cell_scores, np.float64)
+    pairs = np.ascontiguousarray(pairs, PAIR_DIST_DTYPE)
+    n = len(scores)
+    clusts = np.full(n, -1, np.int32) if init is None else np.ascontiguousarray(init, np.int32).copy()
+    rc = lib.ccu_fmx_initial_clusters(C.c_int64(n), C.c_int32(nclust), _ptr(scores), C.c_int64(len(pairs)), _ptr(pairs),
+                                      C.c_double(bf_thres), C.c_double(frac_init_clust), C.c_int32(iter_init),
+                                      C.c_int32(int(keep_init_missing)), C.c_int32(0 if init is None else 1),
+                                      C.c_int32(seed), _ptr(clusts))
+    if rc:
+        raise ValueError("ccu_fmx_initial_clusters: bad arguments")
+    return clusts
 
 
 def classify(results, nv, alphas, doublet_prior=0.5):

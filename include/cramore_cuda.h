@@ -224,6 +224,33 @@ typedef struct {
 } ccu_fmx_timings;
 int ccu_fmx_get_timings(const ccu_handle* h, ccu_fmx_timings* t);
 
+/* ---- initial clustering of freemuxlet (cmd_cram_freemuxlet.cpp:166-346) ------------------------------------
+ * One record per pair of droplets that share at least one SNP = the non-zero entries of the reference's dense
+ * lower-triangular dropDs[id1][id2] matrix (sc_drop_seq.h:45-52), id1 > id2, sorted by (id1, id2). */
+typedef struct {
+  int32_t id1, id2;       /* droplets, id1 > id2 */
+  int32_t nsnps;          /* SNPs covered by both */
+  int32_t nread1, nread2; /* reads of id1 / id2 over those SNPs */
+  int32_t _pad;
+  double llk0, llk2;      /* sum_snp log lk0 (different individuals), log lk2 (same individual), :202-214 */
+} ccu_pair_dist;
+
+/* Pairwise distances (:186-221) from the uploaded droplet store, on the device.  Returns the number of pairs,
+ * the number of (pair, SNP) records they were folded from and the device time. */
+int ccu_fmx_pair_distances(ccu_handle* h, int64_t* npairs, int64_t* nrecords, float* ms);
+int ccu_fmx_get_pair_distances(ccu_handle* h, ccu_pair_dist* out /* [npairs] */);
+
+/* Host part of the initial clustering (:223-346): greedy assignment in the order of the singlet scores
+ * (cell_scores[i] = SNG.LLK - DBL.LLK of .lmix, ties by larger id first, sc_drop_seq.h:190-198) by votes of the
+ * already assigned droplets whose Bayes factor against the candidate passes bf_thres, then -- if iter_init > 0 --
+ * ten sweeps in std::random_shuffle order.  Every random number comes from rand(), in the reference's call
+ * order; seed >= 0 calls srand(seed) first (the reference never seeds: seed 1).  clusts: int32 [nbcs]; with
+ * have_init != 0 it holds the --init-cluster assignment (-1: none) and the greedy pass is skipped.  Needs no GPU
+ * and no handle. */
+int ccu_fmx_initial_clusters(int64_t nbcs, int32_t nclust, const double* cell_scores, int64_t npairs,
+                             const ccu_pair_dist* pairs, double bf_thres, double frac_init_clust, int32_t iter_init,
+                             int32_t keep_init_missing, int32_t have_init, int32_t seed, int32_t* clusts);
+
 /* Diagnostic: the pileup kernels divide the nine likelihoods of a pileup by one sum with a shared refined
  * reciprocal (sc_drop_seq.cpp:492-506 and sc_drop_seq.h:85-100 do nine divisions).  Runs `nsets` random
  * operand sets on the device and returns how many of the 9*nsets quotients differ bitwise from IEEE

@@ -280,3 +280,42 @@ void orc_fmx_estep(int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx
 }
 
 }  // extern "C"
+
+// cmd_cram_freemuxlet.cpp:186-221: SNP by SNP, every pair of droplets covering the SNP (the larger id owns the
+// row) accumulates log lk0 / log lk2 of the diagonal pileup likelihoods under HWE
+void orc_fmx_pair_dist(int64_t nbcs, int64_t nsnps, const int64_t* cell_ptr, const int32_t* snp_idx,
+                       const orc_pileup* plp, const double* af_arr, orc_dropd* out) {
+  for (int64_t i = 0; i < nbcs * nbcs; ++i) {
+    out[i].nsnps = out[i].nread1 = out[i].nread2 = out[i]._pad = 0;
+    out[i].llk0 = out[i].llk2 = 0;
+  }
+  // snp_cell_plps[v]: cells of SNP v in ascending cell id (std::map order)
+  std::vector<std::vector<std::pair<int32_t, int64_t>>> by_snp(nsnps);
+  for (int64_t c = 0; c < nbcs; ++c)
+    for (int64_t e = cell_ptr[c]; e < cell_ptr[c + 1]; ++e) by_snp[snp_idx[e]].push_back({(int32_t)c, e});
+  for (int64_t v = 0; v < nsnps; ++v) {
+    const auto& cells = by_snp[v];
+    for (size_t a = 0; a < cells.size(); ++a) {
+      const double* glis = plp[cells[a].second].gls;
+      for (size_t b = 0; b < a; ++b) {
+        const double* gljs = plp[cells[b].second].gls;
+        double af = af_arr[v];
+        double lk0 = 0, lk2 = 0;
+        double gps[3];
+        gps[0] = (1.0 - af) * (1.0 - af);
+        gps[1] = 2.0 * af * (1.0 - af);
+        gps[2] = af * af;
+        for (int gi = 0; gi < 3; ++gi) {
+          lk2 += (glis[gi * 3 + gi] * gljs[gi * 3 + gi] * gps[gi]);
+          for (int gj = 0; gj < 3; ++gj) lk0 += (glis[gi * 3 + gi] * gljs[gj * 3 + gj] * gps[gi] * gps[gj]);
+        }
+        orc_dropd& dd = out[(int64_t)cells[a].first * nbcs + cells[b].first];
+        ++dd.nsnps;
+        dd.nread1 += plp[cells[a].second].nreads;
+        dd.nread2 += plp[cells[b].second].nreads;
+        dd.llk2 += log(lk2);
+        dd.llk0 += log(lk0);
+      }
+    }
+  }
+}

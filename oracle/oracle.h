@@ -133,6 +133,16 @@ void orc_fmx_estep(int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx
                    const orc_pileup* clust, double doublet_prior, double geno_error,
                    int32_t apply_geno_error, orc_fmx_result* out, double* llk_out);
 
+/* dropD (sc_drop_seq.h:45-52); dense lower-triangular matrix of cmd_cram_freemuxlet.cpp:172-221 as
+ * out[i * nbcs + j], j < i (the other entries stay zero): nsnps, nread1 (droplet i), nread2 (droplet j),
+ * llk0, llk2.  Small nbcs only -- this is the reference's own quadratic layout. */
+typedef struct {
+  int32_t nsnps, nread1, nread2, _pad;
+  double llk0, llk2;
+} orc_dropd;
+void orc_fmx_pair_dist(int64_t nbcs, int64_t nsnps, const int64_t* cell_ptr, const int32_t* snp_idx,
+                       const orc_pileup* plp, const double* af, orc_dropd* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -238,3 +238,19 @@ def fmx_estep(cell_ptr, snp_idx, plp, af, clust, doublet_prior=0.5, geno_error=0
                         C.c_int32(1 if apply_geno_error else 0), C.c_void_p(out.ctypes.data),
                         _p(llk, C.c_double))
     return out, llk
+
+
+DROPD_DTYPE = np.dtype([("nsnps", "<i4"), ("nread1", "<i4"), ("nread2", "<i4"), ("_pad", "<i4"),
+                        ("llk0", "<f8"), ("llk2", "<f8")])
+
+
+def fmx_pair_dist(cell_ptr, snp_idx, plp, af, nsnps):
+    """Dense dropDs matrix [nbcs][nbcs] (rows = the larger droplet id), cmd_cram_freemuxlet.cpp:172-221."""
+    cell_ptr = np.ascontiguousarray(cell_ptr, np.int64)
+    snp_idx = np.ascontiguousarray(snp_idx, np.int32)
+    af = np.ascontiguousarray(af, np.float64)
+    nbcs = len(cell_ptr) - 1
+    out = np.zeros((nbcs, nbcs), DROPD_DTYPE)
+    lib().orc_fmx_pair_dist(C.c_int64(nbcs), C.c_int64(nsnps), _p(cell_ptr, C.c_int64), _p(snp_idx, C.c_int32),
+                            C.c_void_p(plp.ctypes.data), _p(af, C.c_double), C.c_void_p(out.ctypes.data))
+    return out

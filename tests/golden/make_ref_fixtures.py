@@ -35,6 +35,16 @@ FMX_CASES = {
 }
 
 
+# initial clustering (cmd_cram_freemuxlet.cpp:166-346): no --init-cluster, or --init-cluster with the sweeps on
+FMX_INIT_CASES = {
+    "fmx_init_k3": dict(ds=dict(name="C4", nbcs=60, nsnps=300, rbar=80, nv=3, seed=21), K=3, args=[]),
+    "fmx_init_k4_partial": dict(ds=dict(name="C4", nbcs=48, nsnps=260, rbar=90, nv=4, seed=31), K=4,
+                                args=["--frac-init-clust", "0.7", "--bf-thres", "3.0", "--geno-error", "0.05"]),
+    "fmx_init_k3_fromfile": dict(ds=dict(name="C4", nbcs=40, nsnps=240, rbar=80, nv=3, seed=41), K=3,
+                                 args=["--keep-init-missing"], init_file=True),
+}
+
+
 def dataset(spec):
     ds = dict(spec["ds"])
     return make_dataset(ds.pop("name"), with_barcodes=True, **ds)
@@ -115,6 +125,32 @@ def main():
                    "vcf_sites": vcf_sites(read_raw(os.path.join(tmp, "out.clust1.vcf.gz.raw")), K)}
         json.dump(out, open(os.path.join(HERE, "ref_%s.json" % name), "w"))
         print(name, len(out["samples_raw"]), "rows")
+    for name, spec in FMX_INIT_CASES.items():
+        d = dataset(spec)
+        K = spec["K"]
+        with tempfile.TemporaryDirectory() as tmp:
+            bcs = write_plp(d, os.path.join(tmp, "in"))
+            args = ["freemuxlet", "--plp", "in", "--out", "out", "--nsample", str(K), "--aux-files"] + spec["args"]
+            init = None
+            if spec.get("init_file"):
+                init = init_clusters(d, K)
+                with open(os.path.join(tmp, "init.txt"), "w") as f:
+                    for b, c in zip(bcs, init):
+                        if c >= 0:
+                            f.write("%s\t%d\n" % (b, c))
+                args += ["--init-cluster", "init.txt"]
+            run(args, tmp)
+            ldist = read_raw(os.path.join(tmp, "out.ldist.gz.raw")) if init is None else []
+            clust0 = [int(r[2]) for r in read_raw(os.path.join(tmp, "out.clust0.samples.gz.raw")) if len(r) == 3
+                      and r[0].lstrip("-").isdigit()]
+            out = {"case": name, "spec": spec, "init": None if init is None else init.tolist(),
+                   "lmix_raw": read_raw(os.path.join(tmp, "out.lmix.raw")),
+                   "ldist_raw": [r for r in ldist if r[0].isdigit()],
+                   "clust0": clust0,
+                   "samples_raw": read_raw(os.path.join(tmp, "out.clust1.samples.gz.raw")),
+                   "samples_text": gzip.open(os.path.join(tmp, "out.clust1.samples.gz"), "rt").read()}
+        json.dump(out, open(os.path.join(HERE, "ref_%s.json" % name), "w"))
+        print(name, len(out["clust0"]), "droplets,", len(out["ldist_raw"]), "pair rows")
 
 
 def vcf_sites(raw, K, limit=60):

@@ -10,6 +10,7 @@ from cramore_b200.synth import make_dataset
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEMUX_CASES = ["demux_c1_small", "demux_grid_deep", "demux_missing_gp_r2"]
 FMX_CASES = ["fmx_k4", "fmx_k3_noerr"]
+FMX_INIT_CASES = ["fmx_init_k3", "fmx_init_k4_partial", "fmx_init_k3_fromfile"]
 
 # columns of one .best row as passed to hprintf (cmd_cram_demuxlet.cpp:993-1013)
 BEST_COLS = ["int_id", "barcode", "nsnps", "nreads", "type", "best1", "best2", "bestA", "bestLLK", "next1", "next2",
@@ -84,3 +85,30 @@ def fmx_rows(fx):
             row[k] = int(row[k])
         rows.append(row)
     return rows
+
+
+def fmx_init_inputs(fx):
+    """Inputs of the initial clustering as cmdCramFreemuxlet sees them: dataset, pileups, AF, singlet scores."""
+    from oracle import pyoracle
+    d = dataset(fx)
+    plp = pyoracle.fmx_pileup(d["read_ptr"], d["al"], d["bq"], 0.5)
+    af = np.asarray(["%.5f" % a for a in d["af"]], np.float64)  # AF as it round-trips through .var.gz
+    args = fx["spec"]["args"]
+
+    def opt(flag, default):
+        return float(args[args.index(flag) + 1]) if flag in args else default
+
+    params = dict(bf_thres=opt("--bf-thres", 5.41), frac_init_clust=opt("--frac-init-clust", 1.0),
+                  geno_error=opt("--geno-error", 0.0), keep_init_missing="--keep-init-missing" in args)
+    return d, plp, af, params
+
+
+def sparse_pairs(dense):
+    """orc_dropd matrix [nbcs][nbcs] -> the engine's record list (id1 > id2, sorted)."""
+    from cramore_b200.engine import PAIR_DIST_DTYPE
+    i, j = np.nonzero(dense["nsnps"])
+    out = np.zeros(len(i), PAIR_DIST_DTYPE)
+    out["id1"], out["id2"] = i, j
+    for f in ("nsnps", "nread1", "nread2", "llk0", "llk2"):
+        out[f] = dense[f][i, j]
+    return out

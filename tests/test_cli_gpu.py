@@ -118,3 +118,33 @@ def test_cli_freemuxlet_files(built, tmp_path, name):
             gt, gq, dp, ad, pl, gp = f[9 + k].split(":")
             c = site["clusters"][k]
             assert int(dp) == c[3] and ad == "%d,%d" % (c[4], c[5]) and pl == "%d,%d,%d" % (c[6], c[7], c[8])
+
+
+@pytest.mark.parametrize("name", refcase.FMX_INIT_CASES)
+def test_cli_freemuxlet_initial_clustering(built, tmp_path, name):
+    """`cramore freemuxlet` without --init-cluster (or with it and the sweeps on): the GPU pair distances and the
+    host votes give the reference's own .clust0.samples.gz, and the EM ends in the reference's .clust1.samples.gz."""
+    fx = refcase.load(name)
+    d = refcase.dataset(fx)
+    K = fx["spec"]["K"]
+    pre = str(tmp_path / "in")
+    bcs = write_plp(d, pre)
+    args = [CRAMORE, "freemuxlet", "--plp", pre, "--out", str(tmp_path / "out"), "--nsample", str(K), "--aux-files"] + \
+        fx["spec"]["args"]
+    if fx["init"] is not None:
+        with open(str(tmp_path / "init.txt"), "w") as f:
+            for b, c in zip(bcs, fx["init"]):
+                if c >= 0:
+                    f.write("%s\t%d\n" % (b, c))
+        args += ["--init-cluster", str(tmp_path / "init.txt")]
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    c0 = gzip.open(str(tmp_path / "out.clust0.samples.gz"), "rt").read().splitlines()
+    assert c0[0] == "INT_ID\tBARCODE\tCLUST0"
+    assert [int(ln.split("\t")[2]) for ln in c0[1:]] == fx["clust0"]
+    mine = gzip.open(str(tmp_path / "out.clust1.samples.gz"), "rt").read().splitlines(keepends=True)
+    ref = fx["samples_text"].splitlines(keepends=True)
+    assert len(mine) == len(ref) and mine[0] == ref[0]
+    for a, b in zip(mine[1:], ref[1:]):
+        assert a == b or _numeric_row_match(a, b), (a, b)
+    assert sum(a == b for a, b in zip(mine, ref)) >= 0.95 * len(ref)

@@ -253,3 +253,36 @@ def test_posterior_exchange_path_is_bitwise_equal(feng):
         total += part
     assert np.array_equal(total, full)
     feng.set_shard(0, d["nbcs"], 0, d["nsnps"])
+
+
+def test_pair_distances_match_oracle(feng):
+    """ccu_fmx_pair_distances (sparse, sorted) against the dense dropDs matrix of the oracle
+    (cmd_cram_freemuxlet.cpp:172-221): same pairs, exact counts, log-likelihood sums to 1e-12."""
+    from tests.refcase import sparse_pairs
+    d = small_c4(nbcs=180, nsnps=900, rbar=120)
+    upload(feng, d, 4)
+    got = feng.pair_distances()
+    ref = sparse_pairs(pyoracle.fmx_pair_dist(d["cell_ptr"], d["snp_idx"], d["plp"], d["af"], d["nsnps"]))
+    assert len(got) == len(ref) and feng.pair_stats["records"] == int(ref["nsnps"].sum())
+    for f in ("id1", "id2", "nsnps", "nread1", "nread2"):
+        assert np.array_equal(got[f], ref[f]), f
+    np.testing.assert_allclose(got["llk0"], ref["llk0"], rtol=1e-12)
+    np.testing.assert_allclose(got["llk2"], ref["llk2"], rtol=1e-12)
+    assert np.all(np.diff(got["id1"].astype(np.int64) * d["nbcs"] + got["id2"]) > 0)
+
+
+@pytest.mark.parametrize("name", ["fmx_init_k3", "fmx_init_k4_partial"])
+def test_initial_clustering_from_gpu_distances_equals_reference(feng, name):
+    """GPU pair distances + host votes reproduce the reference's own .clust0 (its rand() sequence included)."""
+    from cramore_b200.engine import initial_clusters
+    from tests import refcase
+    fx = refcase.load(name)
+    d, plp, af, prm = refcase.fmx_init_inputs(fx)
+    K = fx["spec"]["K"]
+    feng.configure_fmx(K, 0.5, prm["geno_error"])
+    feng.upload_fmx(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], af)
+    l0, l2 = feng.lmix()
+    pairs = feng.pair_distances()
+    clusts = initial_clusters(l2 - l0, pairs, K, bf_thres=prm["bf_thres"], frac_init_clust=prm["frac_init_clust"],
+                              iter_init=10, keep_init_missing=prm["keep_init_missing"], seed=1)
+    assert clusts.tolist() == fx["clust0"]

@@ -98,3 +98,40 @@ def test_oracle_freemuxlet_equals_reference(name):
             pp /= pp.sum()
             np.testing.assert_allclose(pp, [pp0, pp1, pp2], rtol=1e-11, atol=1e-300)
             assert [int(-10.0 * np.log10(g[i] / mx)) for i in range(3)] == [pl0, pl1, pl2]
+
+
+@pytest.mark.parametrize("name", refcase.FMX_INIT_CASES)
+def test_initial_clustering_equals_reference(name, built):
+    """cmd_cram_freemuxlet.cpp:166-346 against the reference's own run (no --init-cluster, or --init-cluster plus
+    the ten sweeps): the oracle's pairwise distances equal every row of .ldist.gz, and the host clustering
+    (ccu_fmx_initial_clusters: same rand() call sequence, same vote order) reproduces .clust0 exactly."""
+    from cramore_b200.engine import initial_clusters
+    fx = refcase.load(name)
+    d, plp, af, prm = refcase.fmx_init_inputs(fx)
+    K = fx["spec"]["K"]
+    l0, l2 = pyoracle.fmx_lmix(d["cell_ptr"], d["snp_idx"], plp, af)
+    dense = pyoracle.fmx_pair_dist(d["cell_ptr"], d["snp_idx"], plp, af, d["nsnps"])
+    for r in fx["ldist_raw"]:
+        a, b = int(r[0]), int(r[1])
+        dd = dense[max(a, b), min(a, b)]
+        assert (dd["nsnps"], dd["nread1"], dd["nread2"]) == (int(r[2]), int(r[3]), int(r[4])), (a, b)
+        for mine, theirs in ((dd["llk0"], float(r[6])), (dd["llk2"], float(r[7]))):
+            assert mine == theirs or abs(mine - theirs) <= TIGHT * abs(theirs), (a, b, mine, theirs)
+    if fx["init"] is None:
+        assert len(fx["ldist_raw"]) > 500
+    init = None if fx["init"] is None else np.asarray(fx["init"], np.int32)
+    clusts = initial_clusters(l2 - l0, refcase.sparse_pairs(dense), K, bf_thres=prm["bf_thres"],
+                              frac_init_clust=prm["frac_init_clust"], iter_init=10,
+                              keep_init_missing=prm["keep_init_missing"], init=init, seed=1)
+    assert clusts.tolist() == fx["clust0"]
+    # and the EM that follows, started from those clusters, ends where the reference ended
+    clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], plp, clusts, K, d["nsnps"])
+    for it in range(10):
+        res, _ = pyoracle.fmx_estep(d["cell_ptr"], d["snp_idx"], plp, af, clust, 0.5, prm["geno_error"], it + 1 == 10)
+        assign = np.where(res["type"] == 0, res["jBest"], -1).astype(np.int32)
+        clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], plp, assign, K, d["nsnps"])
+    rows = refcase.fmx_rows(fx)
+    assert len(rows) == d["nbcs"]
+    for c, r in enumerate(rows):
+        assert TYPES[r["type"]] == res["type"][c] and (r["jBest"], r["kBest"]) == (res["jBest"][c], res["kBest"][c])
+        assert abs(res["bestLLK"][c] - r["bestLLK"]) <= TIGHT * abs(r["bestLLK"])
