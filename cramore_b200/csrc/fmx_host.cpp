@@ -8,6 +8,7 @@
 // Random numbers are libc rand() in the reference's call order: nclust per visited droplet, and the
 // libstdc++ std::random_shuffle of every sweep (rand() % (i + 1) for i = 1 .. n - 1, swap when different).
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <numeric>
@@ -116,6 +117,85 @@ extern "C" int ccu_fmx_initial_clusters(int64_t nbcs, int32_t nclust, const doub
         const int32_t elected = elect();
         if (clusts[si] >= 0 || !keep_init_missing) clusts[si] = elected;  // :332-336
       }
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// freemux2's greedy initialisation (cmd_cram_freemux2.cpp:217-261): droplets in the order of their singlet
+// scores; each goes to the cluster whose running pileup it fits best (largest llk2 - llk0 of
+// sc_dropseq_lib_t::calculate_droplet_clust_distance, sc_drop_seq.cpp:544-578, first maximum; a cluster without
+// any of the droplet's SNPs scores 0) and is then merged into that cluster's pileup
+// (snp_droplet_pileup::merge, sc_drop_seq.h:77-101).  Strictly sequential and O(entries x nclust): host code.
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int ccu_fmx_greedy_clusters(int64_t nbcs, int64_t nsnps, int32_t nclust, const int64_t* cell_ptr,
+                                       const int32_t* snp_idx, const ccu_pileup* plp, const double* af,
+                                       const double* cell_scores, double frac_init_clust, double singlet_score_thres,
+                                       int32_t* clusts) {
+  if (nbcs < 0 || nsnps < 0 || nclust < 1 || !cell_ptr || !clusts || (nbcs > 0 && !cell_scores)) return 1;
+  const int64_t n = nbcs;
+  if (n > 0 && cell_ptr[n] > 0 && (!snp_idx || !plp || !af)) return 1;
+  std::vector<int32_t> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {  // sc_drop_comp_t
+    const double cmp = cell_scores[a] - cell_scores[b];
+    if (cmp != 0) return cmp > 0;
+    return a > b;
+  });
+  // cluster pileups: gls[9] per (cluster, SNP), allocated on first use (a std::map entry of the reference)
+  std::vector<double> cgl((size_t)nclust * nsnps * 9);
+  std::vector<uint8_t> present((size_t)nclust * nsnps, 0);
+  for (int64_t i = 0; i < n; ++i) clusts[i] = -1;
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t si = order[i];
+    if ((double)i > (double)n * frac_init_clust) continue;    // :225
+    if (cell_scores[si] < singlet_score_thres) continue;      // :226
+    int32_t maxClust = 0;
+    double maxScore = 0;
+    for (int32_t j = 0; j < nclust; ++j) {
+      double llk0 = 0, llk2 = 0;
+      for (int64_t e = cell_ptr[si]; e < cell_ptr[si + 1]; ++e) {
+        const int64_t v = snp_idx[e];
+        if (!present[(size_t)j * nsnps + v]) continue;
+        const double a = af[v];
+        double lk0 = 0, lk2 = 0;
+        double gps[3];
+        gps[0] = (1.0 - a) * (1.0 - a);
+        gps[1] = 2.0 * a * (1.0 - a);
+        gps[2] = a * a;
+        const double* glis = plp[e].gls;
+        const double* gljs = &cgl[((size_t)j * nsnps + v) * 9];
+        for (int gi = 0; gi < 3; ++gi) {
+          lk2 += (glis[gi * 3 + gi] * gljs[gi * 3 + gi] * gps[gi]);
+          for (int gj = 0; gj < 3; ++gj) lk0 += (glis[gi * 3 + gi] * gljs[gj * 3 + gj] * gps[gi] * gps[gj]);
+        }
+        llk2 += std::log(lk2);
+        llk0 += std::log(lk0);
+      }
+      const double score = llk2 - llk0;
+      if (j == 0 || score > maxScore) {  // :236-243: seeded with cluster 0, then strict '>'
+        maxClust = j;
+        maxScore = score;
+      }
+    }
+    clusts[si] = maxClust;
+    for (int64_t e = cell_ptr[si]; e < cell_ptr[si + 1]; ++e) {  // :249-252
+      const size_t at = (size_t)maxClust * nsnps + snp_idx[e];
+      double* gls = &cgl[at * 9];
+      if (!present[at]) {
+        present[at] = 1;
+        for (int t = 0; t < 9; ++t) gls[t] = 1.0;
+      }
+      for (int t = 0; t < 9; ++t) gls[t] *= plp[e].gls[t];
+      double tmp = 0;
+      for (int t = 0; t < 9; ++t) tmp += gls[t];
+      for (int t = 0; t < 9; ++t) gls[t] /= tmp;
+      for (int t = 0; t < 9; ++t)
+        if (gls[t] < 1e-6) gls[t] = 1e-6;  // MIN_NORM_GL
+      tmp = 0;
+      for (int t = 0; t < 9; ++t) tmp += gls[t];
+      for (int t = 0; t < 9; ++t) gls[t] /= tmp;
     }
   }
   return 0;

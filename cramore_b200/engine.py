@@ -46,6 +46,7 @@ ABI_SYMBOLS = [
     "ccu_fmx_assign_dev", "ccu_fmx_mstep_dev", "ccu_fmx_estep_dev", "ccu_fmx_download_results", "ccu_fmx_run_em",
     "ccu_fmx_get_timings", "ccu_fmx_selftest_division", "ccu_fmx_post_dev", "ccu_fmx_posteriors_dev",
     "ccu_fmx_estep_post_dev", "ccu_fmx_pair_distances", "ccu_fmx_get_pair_distances", "ccu_fmx_initial_clusters",
+    "ccu_fmx_greedy_clusters",
 ]
 
 
@@ -348,6 +349,25 @@ def initial_clusters(cell_scores, pairs, nclust, bf_thres=5.41, frac_init_clust=
                                       C.c_int32(seed), _ptr(clusts))
     if rc:
         raise ValueError("ccu_fmx_initial_clusters: bad arguments")
+    return clusts
+
+
+def greedy_clusters(cell_ptr, snp_idx, plp, af, cell_scores, nclust, nsnps, frac_init_clust=1.0,
+                    singlet_score_thres=-1e300):
+    """cmd_cram_freemux2.cpp:217-261 (host code of libcramore_cuda.so)."""
+    lib = load_library()
+    cell_ptr = np.ascontiguousarray(cell_ptr, np.int64)
+    snp_idx = np.ascontiguousarray(snp_idx, np.int32)
+    plp = np.ascontiguousarray(plp, PILEUP_DTYPE)
+    af = np.ascontiguousarray(af, np.float64)
+    scores = np.ascontiguousarray(cell_scores, np.float64)
+    n = len(cell_ptr) - 1
+    clusts = np.full(n, -1, np.int32)
+    rc = lib.ccu_fmx_greedy_clusters(C.c_int64(n), C.c_int64(nsnps), C.c_int32(nclust), _ptr(cell_ptr), _ptr(snp_idx),
+                                     _ptr(plp), _ptr(af), _ptr(scores), C.c_double(frac_init_clust),
+                                     C.c_double(singlet_score_thres), _ptr(clusts))
+    if rc:
+        raise ValueError("ccu_fmx_greedy_clusters: bad arguments")
     return clusts
 
 

@@ -251,6 +251,13 @@ int ccu_fmx_initial_clusters(int64_t nbcs, int32_t nclust, const double* cell_sc
                              const ccu_pair_dist* pairs, double bf_thres, double frac_init_clust, int32_t iter_init,
                              int32_t keep_init_missing, int32_t have_init, int32_t seed, int32_t* clusts);
 
+/* freemux2's greedy initialisation (cmd_cram_freemux2.cpp:217-261): droplets in singlet-score order, each assigned to
+ * the cluster whose running pileup it fits best (sc_drop_seq.cpp:544-578) and merged into it (sc_drop_seq.h:77-101).
+ * plp: the per-entry pileups of ccu_fmx_get_pileups.  Sequential and cheap (entries x nclust): host code, no GPU. */
+int ccu_fmx_greedy_clusters(int64_t nbcs, int64_t nsnps, int32_t nclust, const int64_t* cell_ptr, const int32_t* snp_idx,
+                            const ccu_pileup* plp, const double* af, const double* cell_scores, double frac_init_clust,
+                            double singlet_score_thres, int32_t* clusts);
+
 /* Diagnostic: the pileup kernels divide the nine likelihoods of a pileup by one sum with a shared refined
  * reciprocal (sc_drop_seq.cpp:492-506 and sc_drop_seq.h:85-100 do nine divisions).  Runs `nsets` random
  * operand sets on the device and returns how many of the 9*nsets quotients differ bitwise from IEEE

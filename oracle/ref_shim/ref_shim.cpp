@@ -12,6 +12,7 @@
 
 int32_t cmdCramDemuxlet(int32_t argc, char** argv);
 int32_t cmdCramFreemuxlet(int32_t argc, char** argv);
+int32_t cmdCramFreemux2(int32_t argc, char** argv);
 
 /* ------------------------------------------------------------------ output (hts_utils.cpp:1018-1038) */
 struct htsFile {
@@ -423,11 +424,12 @@ void SAMFilteredReader::close() {}
 /* ------------------------------------------------------------------ command dispatch (cramore.cpp:89-182) */
 int main(int argc, char** argv) {
   if (argc < 2) {
-    fprintf(stderr, "usage: ref_cramore {demuxlet|freemuxlet} [options]\n");
+    fprintf(stderr, "usage: ref_cramore {demuxlet|freemuxlet|freemux2} [options]\n");
     return 1;
   }
   if (strcmp(argv[1], "demuxlet") == 0) return cmdCramDemuxlet(argc - 1, argv + 1);
   if (strcmp(argv[1], "freemuxlet") == 0) return cmdCramFreemuxlet(argc - 1, argv + 1);
-  fprintf(stderr, "ref_cramore: only demuxlet and freemuxlet are built\n");
+  if (strcmp(argv[1], "freemux2") == 0) return cmdCramFreemux2(argc - 1, argv + 1);
+  fprintf(stderr, "ref_cramore: only demuxlet, freemuxlet and freemux2 are built\n");
   return 1;
 }

@@ -45,6 +45,15 @@ FMX_INIT_CASES = {
 }
 
 
+# freemux2 (cmd_cram_freemux2.cpp): greedy cluster-pileup initialisation, geno_error on every iteration, early stop
+FMX2_CASES = {
+    "fmx2_k3_greedy": dict(ds=dict(name="C4", nbcs=60, nsnps=300, rbar=80, nv=3, seed=21), K=3, args=[]),
+    "fmx2_k4_greedy_partial": dict(ds=dict(name="C4", nbcs=50, nsnps=280, rbar=90, nv=4, seed=33), K=4,
+                                   args=["--frac-init-clust", "0.6", "--geno-error", "0.05", "--doublet-prior", "0.3"]),
+    "fmx2_k3_fromfile": dict(ds=dict(name="C4", nbcs=40, nsnps=240, rbar=80, nv=3, seed=41), K=3, args=[], init_file=True),
+}
+
+
 def dataset(spec):
     ds = dict(spec["ds"])
     return make_dataset(ds.pop("name"), with_barcodes=True, **ds)
@@ -151,6 +160,35 @@ def main():
                    "samples_text": gzip.open(os.path.join(tmp, "out.clust1.samples.gz"), "rt").read()}
         json.dump(out, open(os.path.join(HERE, "ref_%s.json" % name), "w"))
         print(name, len(out["clust0"]), "droplets,", len(out["ldist_raw"]), "pair rows")
+    freemux2_cases()
+
+
+def freemux2_cases():
+    for name, spec in FMX2_CASES.items():
+        d = dataset(spec)
+        K = spec["K"]
+        with tempfile.TemporaryDirectory() as tmp:
+            bcs = write_plp(d, os.path.join(tmp, "in"))
+            args = ["freemux2", "--plp", "in", "--out", "out", "--nsample", str(K), "--aux-files", "--seed", "7"] + spec["args"]
+            init = None
+            if spec.get("init_file"):
+                init = init_clusters(d, K)
+                with open(os.path.join(tmp, "init.txt"), "w") as f:
+                    for b, c in zip(bcs, init):
+                        if c >= 0:
+                            f.write("%s\t%d\n" % (b, c))
+                args += ["--init-cluster", "init.txt"]
+            run(args, tmp)
+            clust0 = [int(r[2]) for r in read_raw(os.path.join(tmp, "out.clust0.samples.gz.raw")) if len(r) == 3
+                      and r[0].lstrip("-").isdigit()]
+            out = {"case": name, "spec": spec, "init": None if init is None else init.tolist(),
+                   "lmix_raw": read_raw(os.path.join(tmp, "out.lmix.raw")),
+                   "lmix_text": open(os.path.join(tmp, "out.lmix")).read(),
+                   "clust0": clust0,
+                   "samples_raw": read_raw(os.path.join(tmp, "out.clust1.samples.gz.raw")),
+                   "samples_text": gzip.open(os.path.join(tmp, "out.clust1.samples.gz"), "rt").read()}
+        json.dump(out, open(os.path.join(HERE, "ref_%s.json" % name), "w"))
+        print(name, len(out["clust0"]), "droplets")
 
 
 def vcf_sites(raw, K, limit=60):

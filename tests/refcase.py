@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 DEMUX_CASES = ["demux_c1_small", "demux_grid_deep", "demux_missing_gp_r2"]
 FMX_CASES = ["fmx_k4", "fmx_k3_noerr"]
 FMX_INIT_CASES = ["fmx_init_k3", "fmx_init_k4_partial", "fmx_init_k3_fromfile"]
+FMX2_CASES = ["fmx2_k3_greedy", "fmx2_k4_greedy_partial", "fmx2_k3_fromfile"]
 
 # columns of one .best row as passed to hprintf (cmd_cram_demuxlet.cpp:993-1013)
 BEST_COLS = ["int_id", "barcode", "nsnps", "nreads", "type", "best1", "best2", "bestA", "bestLLK", "next1", "next2",
@@ -98,8 +99,10 @@ def fmx_init_inputs(fx):
     def opt(flag, default):
         return float(args[args.index(flag) + 1]) if flag in args else default
 
+    v2 = fx["case"].startswith("fmx2")
     params = dict(bf_thres=opt("--bf-thres", 5.41), frac_init_clust=opt("--frac-init-clust", 1.0),
-                  geno_error=opt("--geno-error", 0.0), keep_init_missing="--keep-init-missing" in args)
+                  geno_error=opt("--geno-error", 0.1 if v2 else 0.0), keep_init_missing="--keep-init-missing" in args,
+                  doublet_prior=opt("--doublet-prior", 0.5))
     return d, plp, af, params
 
 

@@ -148,3 +148,36 @@ def test_cli_freemuxlet_initial_clustering(built, tmp_path, name):
     for a, b in zip(mine[1:], ref[1:]):
         assert a == b or _numeric_row_match(a, b), (a, b)
     assert sum(a == b for a, b in zip(mine, ref)) >= 0.95 * len(ref)
+
+
+@pytest.mark.parametrize("name", refcase.FMX2_CASES)
+def test_cli_freemux2_files(built, tmp_path, name):
+    """`cramore freemux2` against the reference's own freemux2 run: greedy initial clusters (.clust0), .lmix and the
+    final .clust1.samples.gz (geno_error on every iteration, early stop)."""
+    fx = refcase.load(name)
+    d = refcase.dataset(fx)
+    K = fx["spec"]["K"]
+    pre = str(tmp_path / "in")
+    bcs = write_plp(d, pre)
+    args = [CRAMORE, "freemux2", "--plp", pre, "--out", str(tmp_path / "out"), "--nsample", str(K), "--aux-files",
+            "--seed", "7"] + fx["spec"]["args"]
+    if fx["init"] is not None:
+        with open(str(tmp_path / "init.txt"), "w") as f:
+            for b, c in zip(bcs, fx["init"]):
+                if c >= 0:
+                    f.write("%s\t%d\n" % (b, c))
+        args += ["--init-cluster", str(tmp_path / "init.txt")]
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    c0 = gzip.open(str(tmp_path / "out.clust0.samples.gz"), "rt").read().splitlines()
+    assert [int(ln.split("\t")[2]) for ln in c0[1:]] == fx["clust0"]
+    mine = gzip.open(str(tmp_path / "out.clust1.samples.gz"), "rt").read().splitlines(keepends=True)
+    ref = fx["samples_text"].splitlines(keepends=True)
+    assert len(mine) == len(ref) and mine[0] == ref[0]
+    for a, b in zip(mine[1:], ref[1:]):
+        assert a == b or _numeric_row_match(a, b), (a, b)
+    assert sum(a == b for a, b in zip(mine, ref)) >= 0.95 * len(ref)
+    lm, rlm = open(str(tmp_path / "out.lmix")).read().splitlines(), fx["lmix_text"].splitlines()
+    assert len(lm) == len(rlm) and lm[0] == rlm[0]
+    for a, b in zip(lm[1:], rlm[1:]):
+        assert a == b or _numeric_row_match(a, b), (a, b)

@@ -135,3 +135,37 @@ def test_initial_clustering_equals_reference(name, built):
     for c, r in enumerate(rows):
         assert TYPES[r["type"]] == res["type"][c] and (r["jBest"], r["kBest"]) == (res["jBest"][c], res["kBest"][c])
         assert abs(res["bestLLK"][c] - r["bestLLK"]) <= TIGHT * abs(r["bestLLK"])
+
+
+@pytest.mark.parametrize("name", refcase.FMX2_CASES)
+def test_freemux2_equals_reference(name, built):
+    """cmd_cram_freemux2.cpp against the reference's own run: the greedy cluster-pileup initialisation
+    (ccu_fmx_greedy_clusters, :217-261) reproduces .clust0 exactly, and the oracle's EM in the freemux2 flavour
+    (geno_error on every iteration, stop once no call changes, :374-605) ends in the reference's rows."""
+    from cramore_b200.engine import greedy_clusters
+    fx = refcase.load(name)
+    d, plp, af, prm = refcase.fmx_init_inputs(fx)
+    K = fx["spec"]["K"]
+    l0, l2 = pyoracle.fmx_lmix(d["cell_ptr"], d["snp_idx"], plp, af)
+    if fx["init"] is None:
+        clusts = greedy_clusters(d["cell_ptr"], d["snp_idx"], plp, af, l2 - l0, K, d["nsnps"],
+                                 frac_init_clust=prm["frac_init_clust"])
+    else:
+        clusts = np.asarray(fx["init"], np.int32)
+    assert clusts.tolist() == fx["clust0"]
+    clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], plp, clusts, K, d["nsnps"])
+    prev = None
+    for it in range(10):
+        res, _ = pyoracle.fmx_estep(d["cell_ptr"], d["snp_idx"], plp, af, clust, prm["doublet_prior"], prm["geno_error"], True)
+        assign = np.where(res["type"] == 0, res["jBest"], -1).astype(np.int32)
+        clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], plp, assign, K, d["nsnps"])
+        key = np.where(res["type"] == 0, res["sBest"], -1 - res["type"])
+        if prev is not None and np.array_equal(key, prev):
+            break
+        prev = key
+    rows = refcase.fmx_rows(fx)
+    assert len(rows) == d["nbcs"]
+    for c, r in enumerate(rows):
+        assert TYPES[r["type"]] == res["type"][c], (c, r["type"], res["type"][c])
+        assert (r["jBest"], r["kBest"]) == (res["jBest"][c], res["kBest"][c])
+        assert abs(res["bestLLK"][c] - r["bestLLK"]) <= TIGHT * abs(r["bestLLK"]), (c, res["bestLLK"][c], r["bestLLK"])
