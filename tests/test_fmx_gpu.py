@@ -187,9 +187,10 @@ def test_shard_invariance_and_slab_sum(feng):
     assert np.array_equal(total[..., 9], full_stats["nreads"])
 
 
-def test_estep_tensor_path_matches_default(built):
-    """CCU_FMX_ESTEP=mma selects the DMMA (FP64 tensor) E-step kernel; it must give the default kernel's
-    likelihoods to 1e-12 and identical decisions (run in a subprocess: the switch is read once per process)."""
+def test_estep_alternative_kernels_match_default(built):
+    """CCU_FMX_ESTEP=mma selects the DMMA (FP64 tensor) E-step kernel and CCU_FMX_ESTEP=rows1 the one-row-per-lane
+    kernel for K <= 16; both must give the default kernel's likelihoods to 1e-12 and identical decisions (run in
+    subprocesses: the switch is read once per process)."""
     import os
     import subprocess
     import sys
@@ -211,13 +212,14 @@ np.save(sys.argv[2], e.fmx_llk()); np.save(sys.argv[3], nxt)
     with tempfile.TemporaryDirectory() as tmp:
         for K in (7, 16, 21):
             out = {}
-            for mode in ("rows", "mma"):
+            for mode in ("rows", "rows1", "mma"):
                 env = dict(os.environ, CCU_FMX_ESTEP=mode, PYTHONPATH=root)
                 f1, f2 = os.path.join(tmp, "llk_%s.npy" % mode), os.path.join(tmp, "nxt_%s.npy" % mode)
                 subprocess.check_call([sys.executable, "-c", code, str(K), f1, f2], env=env, cwd=root)
                 out[mode] = (np.load(f1), np.load(f2))
-            np.testing.assert_allclose(out["mma"][0], out["rows"][0], rtol=1e-12, atol=1e-12)
-            assert np.array_equal(out["mma"][1], out["rows"][1])
+            for mode in ("rows1", "mma"):
+                np.testing.assert_allclose(out[mode][0], out["rows"][0], rtol=1e-12, atol=1e-12)
+                assert np.array_equal(out[mode][1], out["rows"][1])
 
 
 def test_posterior_exchange_path_is_bitwise_equal(feng):
