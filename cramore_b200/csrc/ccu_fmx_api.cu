@@ -3,6 +3,7 @@
 // fmx_kernels.cu.  No CPU implementation exists behind any entry point.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
@@ -22,7 +23,7 @@ struct FmxState {
   bool configured = false, uploaded = false, have_stats = false, have_estep = false, have_post = false;
   int32_t K = 0;
   double doublet_prior = 0.5, geno_error = 0.0;
-  int64_t nbcs = 0, nsnps = 0, nnz = 0, nreads = 0;
+  int64_t nbcs = 0, nsnps = 0, nnz = 0, nreads = 0, max_segment = 0;
   int64_t cell_begin = 0, cell_end = 0, snp_begin = 0, snp_end = 0;
   DevBuf cell_ptr, snp_idx, read_ptr, al, bq, af;
   DevBuf gl, cnt, logdenom, csc_ptr, csc_cell, csc_gl, csc_cnt;
@@ -62,6 +63,7 @@ ccu::FmxDev fmx_view(const ccu_handle* h) {
   d.nbcs = f->nbcs;
   d.nsnps = f->nsnps;
   d.nnz = f->nnz;
+  d.max_segment = f->max_segment;
   d.cell_ptr = f->cell_ptr.as<int64_t>();
   d.snp_idx = f->snp_idx.as<int32_t>();
   d.read_ptr = f->read_ptr.as<int64_t>();
@@ -158,6 +160,16 @@ int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* ce
   f->nsnps = nsnps;
   f->nnz = nnz;
   f->nreads = nreads;
+  {  // most droplets per SNP
+    std::vector<int32_t> per_snp(nsnps, 0);
+    int32_t mx = 0;
+    for (int64_t e = 0; e < nnz; ++e) {
+      const int32_t s = snp_idx[e];
+      if (s < 0 || s >= nsnps) return ccu_fail(h, "ccu_fmx_upload: snp_idx[%lld] = %d out of range", (long long)e, s);
+      mx = std::max(mx, ++per_snp[s]);
+    }
+    f->max_segment = mx;
+  }
   f->cell_begin = 0;
   f->cell_end = nbcs;
   f->snp_begin = 0;

@@ -23,6 +23,7 @@ struct FmxDev {
   double doublet_prior, geno_error;
   double log_sng_prior, log_dbl_prior;  // log((1-prior)/K), log(prior/K/(K-1)*2)  (cmd_cram_freemuxlet.cpp:462-463)
   int64_t nbcs, nsnps, nnz;
+  int64_t max_segment;       // most droplets any SNP has (selects the M-step kernel)
   // droplet store (all droplets)
   const int64_t* cell_ptr;   // [nbcs+1]
   const int32_t* snp_idx;    // [nnz]
