@@ -48,6 +48,7 @@ ccu::DemuxDev dev_view(const ccu_handle* h) {
   d.nA = h->nA;
   d.doublet_prior = h->doublet_prior;
   d.alpha = h->d_alpha.as<double>();
+  for (int n = 0; n < CCU_MAX_ALPHA; ++n) d.alpha_c[n] = (n < (int)h->alpha.size()) ? h->alpha[n] : 0.0;
   d.ptab = h->d_ptab.as<double>();
   d.is_half = h->d_half.as<uint8_t>();
   d.phred = h->d_phred.as<double>();

@@ -36,6 +36,7 @@ struct DemuxDev {
   int32_t nv, nvp, nA;
   double doublet_prior;
   const double* alpha;     // [nA]
+  double alpha_c[CCU_MAX_ALPHA];  // the same grid by value: lands in the kernel's constant bank
   const double* ptab;      // [nA*9*2]: p then (1-p), cmd_cram_demuxlet.cpp:673,685
   const uint8_t* is_half;  // [nA] alpha[n] == 0.5
   const double* phred;     // [512]: err[256], mat[256]

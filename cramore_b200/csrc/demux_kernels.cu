@@ -631,7 +631,7 @@ struct WarpRed {
 };
 static_assert(sizeof(WarpRed) <= 64, "WarpRed slot");
 
-template <int AC, int TK>
+template <int AC, int TK, bool CA>
 __global__ void __launch_bounds__(kScoreBlock, 1)
     demux_score_kernel(DemuxDev d, int njt, int nkt, int nac, int64_t nitems, uint32_t half_mask,
                        double2* __restrict__ dbg, int64_t dbg_c0, int64_t dbg_c1) {
@@ -848,8 +848,10 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
     // the thread's TK consecutive samples k sit inside one 32-sample part
     const double* fk_base = reinterpret_cast<const double*>(raw + stage * Cfg::STAGE_BYTES + Cfg::PART_BYTES) +
                             ((kidx * TK) >> 5) * (Cfg::PART_BYTES / 8) + ((kidx * TK) & 31);
-    // volatile: the alphas must be re-read from shared memory (broadcast LDS) inside the loop; hoisted into
-    // registers they cost 2*AC of the 112 and ptxas then funnels every product through one temporary
+    // The alphas must not sit in registers: hoisted out of the loop they cost 2*AC of the 112 and ptxas then
+    // funnels every product through one temporary.  With a single alpha chunk (CA: n0 == 1, the usual case) they
+    // are read as constant-bank operands of the FP64 instructions themselves (the grid travels by value in the
+    // kernel parameters); otherwise they are re-read from shared memory (volatile broadcast LDS).
     const volatile double* sal = s_alpha + n0;
     auto load_fk = [&](int s, double* fk) {
       if constexpr (TK == 1) {
@@ -891,7 +893,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
             const double c10 = fma(fa.x, db0, fb.x * da0), c11 = fma(fa.y, db1, fb.y * da1);
 #pragma unroll
             for (int a = 0; a < AC; ++a) {
-              const double al = sal[a];
+              const double al = CA ? d.alpha_c[1 + a] : sal[a];
               acc[0][kk * AC + a] *= fma(al, fma(al, c20, c10), c00);
               acc[1][kk * AC + a] *= fma(al, fma(al, c21, c11), c01);
             }
@@ -908,7 +910,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
           const double d0 = fk[kk] - fj.x, d1 = fk[kk] - fj.y;
 #pragma unroll
           for (int a = 0; a < AC; ++a) {
-            const double al = sal[a];
+            const double al = CA ? d.alpha_c[1 + a] : sal[a];
             acc[0][kk * AC + a] *= fma(al, d0, fj.x);
             acc[1][kk * AC + a] *= fma(al, d1, fj.y);
           }
@@ -1142,8 +1144,11 @@ template <int AC, int TK>
 static cudaError_t launch_score_t(const DemuxDev& d, const ScorePlan& plan, int num_sms, double2* llk_dbg,
                                   int64_t c0, int64_t c1, int* grid_out, cudaStream_t st) {
   using Cfg = ScoreCfg<AC, TK>;
-  cudaError_t err = cudaFuncSetAttribute(demux_score_kernel<AC, TK>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  const bool ca = plan.nac == 1;  // one alpha chunk: n0 == 1 in every item
+  cudaError_t err = ca ? cudaFuncSetAttribute(demux_score_kernel<AC, TK, true>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)
+                       : cudaFuncSetAttribute(demux_score_kernel<AC, TK, false>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (err != cudaSuccess) return err;
   const int64_t nitems = d.nbcs * plan.items_per_cell;
   int grid = (int)((nitems < num_sms) ? nitems : num_sms);
@@ -1151,8 +1156,12 @@ static cudaError_t launch_score_t(const DemuxDev& d, const ScorePlan& plan, int 
   uint32_t half_mask = 0;
   for (int n = 0; n < d.nA && n < 32; ++n)
     if (plan.is_half[n]) half_mask |= 1u << n;
-  demux_score_kernel<AC, TK><<<grid, kScoreBlock, Cfg::SMEM_BYTES, st>>>(d, plan.njt, plan.nkt, plan.nac, nitems,
-                                                                        half_mask, llk_dbg, c0, c1);
+  if (ca)
+    demux_score_kernel<AC, TK, true><<<grid, kScoreBlock, Cfg::SMEM_BYTES, st>>>(d, plan.njt, plan.nkt, plan.nac, nitems,
+                                                                                half_mask, llk_dbg, c0, c1);
+  else
+    demux_score_kernel<AC, TK, false><<<grid, kScoreBlock, Cfg::SMEM_BYTES, st>>>(d, plan.njt, plan.nkt, plan.nac, nitems,
+                                                                                 half_mask, llk_dbg, c0, c1);
   return cudaGetLastError();
 }
 
