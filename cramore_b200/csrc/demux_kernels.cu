@@ -551,11 +551,7 @@ cudaError_t launch_singlet_to_dbg(const DemuxDev& d, double* llk_dbg, int64_t c0
 #ifndef CCU_NS
 #define CCU_NS 3
 #endif
-#ifndef CCU_AFF_UNROLL
-#define CCU_AFF_UNROLL 2
-#endif
 constexpr int kNSWanted = CCU_NS;                   // raw ring stages (fewer where shared memory is short)
-constexpr int kAffUnroll = CCU_AFF_UNROLL;
 constexpr int kTJ = 2;                              // samples j per thread
 constexpr int kConsumers = kScoreThreads;           // 16 consumer warps
 constexpr int kScoreBlock = kScoreThreads + 128;    // + the producer warpgroup (1 working warp)
@@ -631,7 +627,7 @@ struct WarpRed {
 };
 static_assert(sizeof(WarpRed) <= 64, "WarpRed slot");
 
-template <int AC, int TK, bool CA>
+template <int AC, int TK>
 __global__ void __launch_bounds__(kScoreBlock, 1)
     demux_score_kernel(DemuxDev d, int njt, int nkt, int nac, int64_t nitems, uint32_t half_mask,
                        double2* __restrict__ dbg, int64_t dbg_c0, int64_t dbg_c1) {
@@ -848,11 +844,11 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
     // the thread's TK consecutive samples k sit inside one 32-sample part
     const double* fk_base = reinterpret_cast<const double*>(raw + stage * Cfg::STAGE_BYTES + Cfg::PART_BYTES) +
                             ((kidx * TK) >> 5) * (Cfg::PART_BYTES / 8) + ((kidx * TK) & 31);
-    // The alphas must not sit in registers: hoisted out of the loop they cost 2*AC of the 112 and ptxas then
-    // funnels every product through one temporary.  With a single alpha chunk (CA: n0 == 1, the usual case) they
-    // are read as constant-bank operands of the FP64 instructions themselves (the grid travels by value in the
-    // kernel parameters); otherwise they are re-read from shared memory (volatile broadcast LDS).
-    const volatile double* sal = s_alpha + n0;
+    // The alphas must not sit in ordinary registers: hoisted out of the loop they cost 2*AC of the 112 and ptxas
+    // then funnels every product through one temporary.  The grid travels by value in the kernel parameters
+    // (d.alpha_c, constant bank) and n0 is warp-uniform, so the compiler keeps the chunk's alphas in UNIFORM
+    // registers and feeds them to the FP64 instructions as uniform operands: no vector registers, no loads in
+    // the loop, ten independent products in flight.
     auto load_fk = [&](int s, double* fk) {
       if constexpr (TK == 1) {
         fk[0] = fk_base[s * 32];
@@ -867,7 +863,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
     };
     int s = 0;
 #ifdef CCU_EXPERIMENT_SKIP_MATH  // timing experiment only: the data pipeline without the multiplications
-    if (cnt > 0) acc[0][0] *= fj_base[0] + fk_base[0] + sal[0];
+    if (cnt > 0) acc[0][0] *= fj_base[0] + fk_base[0] + d.alpha_c[n0];
     s = cnt;
 #endif
     while (s < cnt) {
@@ -893,7 +889,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
             const double c10 = fma(fa.x, db0, fb.x * da0), c11 = fma(fa.y, db1, fb.y * da1);
 #pragma unroll
             for (int a = 0; a < AC; ++a) {
-              const double al = CA ? d.alpha_c[1 + a] : sal[a];
+              const double al = d.alpha_c[n0 + a];
               acc[0][kk * AC + a] *= fma(al, fma(al, c20, c10), c00);
               acc[1][kk * AC + a] *= fma(al, fma(al, c21, c11), c01);
             }
@@ -910,7 +906,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
           const double d0 = fk[kk] - fj.x, d1 = fk[kk] - fj.y;
 #pragma unroll
           for (int a = 0; a < AC; ++a) {
-            const double al = CA ? d.alpha_c[1 + a] : sal[a];
+            const double al = d.alpha_c[n0 + a];
             acc[0][kk * AC + a] *= fma(al, d0, fj.x);
             acc[1][kk * AC + a] *= fma(al, d1, fj.y);
           }
@@ -1144,11 +1140,8 @@ template <int AC, int TK>
 static cudaError_t launch_score_t(const DemuxDev& d, const ScorePlan& plan, int num_sms, double2* llk_dbg,
                                   int64_t c0, int64_t c1, int* grid_out, cudaStream_t st) {
   using Cfg = ScoreCfg<AC, TK>;
-  const bool ca = plan.nac == 1;  // one alpha chunk: n0 == 1 in every item
-  cudaError_t err = ca ? cudaFuncSetAttribute(demux_score_kernel<AC, TK, true>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)
-                       : cudaFuncSetAttribute(demux_score_kernel<AC, TK, false>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  cudaError_t err = cudaFuncSetAttribute(demux_score_kernel<AC, TK>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (err != cudaSuccess) return err;
   const int64_t nitems = d.nbcs * plan.items_per_cell;
   int grid = (int)((nitems < num_sms) ? nitems : num_sms);
@@ -1156,12 +1149,8 @@ static cudaError_t launch_score_t(const DemuxDev& d, const ScorePlan& plan, int 
   uint32_t half_mask = 0;
   for (int n = 0; n < d.nA && n < 32; ++n)
     if (plan.is_half[n]) half_mask |= 1u << n;
-  if (ca)
-    demux_score_kernel<AC, TK, true><<<grid, kScoreBlock, Cfg::SMEM_BYTES, st>>>(d, plan.njt, plan.nkt, plan.nac, nitems,
-                                                                                half_mask, llk_dbg, c0, c1);
-  else
-    demux_score_kernel<AC, TK, false><<<grid, kScoreBlock, Cfg::SMEM_BYTES, st>>>(d, plan.njt, plan.nkt, plan.nac, nitems,
-                                                                                 half_mask, llk_dbg, c0, c1);
+  demux_score_kernel<AC, TK><<<grid, kScoreBlock, Cfg::SMEM_BYTES, st>>>(d, plan.njt, plan.nkt, plan.nac, nitems,
+                                                                        half_mask, llk_dbg, c0, c1);
   return cudaGetLastError();
 }
 
