@@ -283,11 +283,18 @@ __global__ void __launch_bounds__(kTileWarps * 32)
   }
   const int rowlen = nA * kTileStride;
 
+  // A warp looks at 32 entries at a time (one coalesced read of their classes) and works only on those that need
+  // a full tile, EPW of them per pass: with sparse single-cell data that is one entry in two thousand.
   const int64_t warps_total = (int64_t)gridDim.x * kTileWarps;
-  for (int64_t e0 = ((int64_t)blockIdx.x * kTileWarps + warp) * EPW; e0 < nnz; e0 += warps_total * EPW) {
-    const int64_t e = e0 + sub;
-    const bool valid = (e < nnz) && (all_entries || eclass[e] != 0);
-    if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
+  for (int64_t base = ((int64_t)blockIdx.x * kTileWarps + warp) * 32; base < nnz; base += warps_total * 32) {
+    const int64_t el = base + lane;
+    unsigned todo = __ballot_sync(0xffffffffu, (el < nnz) && (all_entries || eclass[el] != 0));
+    while (todo != 0u) {
+    const unsigned bit = __fns(todo, 0, sub + 1);  // the sub-th entry still to do (0xffffffff: none)
+    const bool valid = bit != 0xffffffffu;
+    const int64_t e = base + (valid ? (int)bit : 0);
+#pragma unroll
+    for (int i = 0; i < EPW; ++i) todo &= todo - 1;
     int64_t r0 = 0;
     int cnt = 0;
     if (valid) {
@@ -352,12 +359,14 @@ __global__ void __launch_bounds__(kTileWarps * 32)
     __syncwarp();
 #pragma unroll
     for (int sb = 0; sb < EPW; ++sb) {
+      const int64_t es = __shfl_sync(0xffffffffu, e, sb * GL);
       if (__shfl_sync(0xffffffffu, (int)valid, sb * GL)) {
-        double* dst = tiles + (e0 + sb) * rowlen;
+        double* dst = tiles + es * rowlen;
         for (int i = lane; i < rowlen; i += 32) dst[i] = s_out[warp][sb * rowlen + i];
       }
     }
     __syncwarp();
+    }
   }
 }
 
@@ -373,7 +382,7 @@ cudaError_t launch_tile(const DemuxDev& d, bool all_entries, cudaStream_t st) {
   }
   int gl = 2;
   while (gl < d.nA) gl <<= 1;
-  int64_t per_block = (int64_t)kTileWarps * (32 / gl);
+  int64_t per_block = (int64_t)kTileWarps * 32;
   int64_t blocks = (d.nnz + per_block - 1) / per_block;
   if (blocks > 148 * 16) blocks = 148 * 16;
 #define CCU_TILE(GL)                                                                                 \
@@ -551,6 +560,9 @@ cudaError_t launch_singlet_to_dbg(const DemuxDev& d, double* llk_dbg, int64_t c0
 #ifndef CCU_NS
 #define CCU_NS 3
 #endif
+#ifndef CCU_SCA1
+#define CCU_SCA1 32
+#endif
 constexpr int kNSWanted = CCU_NS;                   // raw ring stages (fewer where shared memory is short)
 constexpr int kTJ = 2;                              // samples j per thread
 constexpr int kConsumers = kScoreThreads;           // 16 consumer warps
@@ -580,7 +592,7 @@ struct ChunkMeta {   // published by the producer with each ring stage
 template <int AC, int TK>
 struct ScoreCfg {
   static constexpr int SC = (TK >= 8) ? 4 : 8;  // SNPs per general chunk (bounded by shared memory)
-  static constexpr int SCA = (TK == 1) ? 32 : (TK <= 4) ? 16 : 8;  // entries per affine chunk
+  static constexpr int SCA = (TK == 1) ? CCU_SCA1 : (TK <= 4) ? 16 : 8;  // entries per affine chunk
   static constexpr int NCOL = AC * TK;
   static constexpr int TROW0 = NCOL * 3;
   // row stride (doubles) of a thread's T block: even, and (stride/2) odd => the 8 distinct
