@@ -16,6 +16,7 @@ struct FmxPairs;  // fmx_init.cu
 void ccu_fmx_pairs_release(FmxPairs*& p);
 int ccu_fmx_pairs_build(ccu_handle* h, const ccu::FmxDev& d, FmxPairs*& ps, int64_t* npairs_out);
 int ccu_fmx_pairs_download(ccu_handle* h, FmxPairs* ps, ccu_pair_dist* out);
+int ccu_fmx_pairs_download_voting(ccu_handle* h, FmxPairs* ps, double bf_thres, int64_t* nvoting, ccu_pair_dist* out);
 float ccu_fmx_pairs_ms(const FmxPairs* ps);
 int64_t ccu_fmx_pairs_records(const FmxPairs* ps);
 
@@ -500,6 +501,12 @@ int ccu_fmx_get_pair_distances(ccu_handle* h, ccu_pair_dist* out) {
   if (int rc = need(h, true, "ccu_fmx_get_pair_distances")) return rc;
   CCU_CUDA(h, cudaSetDevice(h->device));
   return ccu_fmx_pairs_download(h, h->fmx->pairs, out);
+}
+
+int ccu_fmx_get_voting_pairs(ccu_handle* h, double bf_thres, int64_t* nvoting, ccu_pair_dist* out) {
+  if (int rc = need(h, true, "ccu_fmx_get_voting_pairs")) return rc;
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  return ccu_fmx_pairs_download_voting(h, h->fmx->pairs, bf_thres, nvoting, out);
 }
 
 int ccu_fmx_selftest_division(ccu_handle* h, int64_t nsets, uint64_t seed, int64_t* mismatches) {

@@ -37,18 +37,26 @@ extern "C" int ccu_fmx_initial_clusters(int64_t nbcs, int32_t nclust, const doub
 
   // symmetric adjacency, every row in ascending id of the other droplet (pairs are sorted by (id1, id2): a
   // counting pass keeps that order on both sides)
+  // (a pair whose Bayes factor passes the threshold in neither direction never touches a vote: left out)
+  auto votes_at_all = [&](const ccu_pair_dist& p) {
+    const double bf = p.llk2 - p.llk0;
+    return (bf > bf_thres) || (-bf > bf_thres);
+  };
   std::vector<int64_t> ptr(n + 1, 0);
-  for (int64_t p = 0; p < npairs; ++p) {
-    ++ptr[pairs[p].id1 + 1];
-    ++ptr[pairs[p].id2 + 1];
-  }
+  for (int64_t p = 0; p < npairs; ++p)
+    if (votes_at_all(pairs[p])) {
+      ++ptr[pairs[p].id1 + 1];
+      ++ptr[pairs[p].id2 + 1];
+    }
   for (int64_t i = 0; i < n; ++i) ptr[i + 1] += ptr[i];
   std::vector<Nbr> adj(ptr[n]);
   {
     std::vector<int64_t> fill(ptr.begin(), ptr.end() - 1);
     // first the smaller ids (id2 of row id1), then the larger ones: two passes keep each row ascending
-    for (int64_t p = 0; p < npairs; ++p) adj[fill[pairs[p].id1]++] = {pairs[p].id2, pairs[p].llk2 - pairs[p].llk0};
-    for (int64_t p = 0; p < npairs; ++p) adj[fill[pairs[p].id2]++] = {pairs[p].id1, pairs[p].llk2 - pairs[p].llk0};
+    for (int64_t p = 0; p < npairs; ++p)
+      if (votes_at_all(pairs[p])) adj[fill[pairs[p].id1]++] = {pairs[p].id2, pairs[p].llk2 - pairs[p].llk0};
+    for (int64_t p = 0; p < npairs; ++p)
+      if (votes_at_all(pairs[p])) adj[fill[pairs[p].id2]++] = {pairs[p].id1, pairs[p].llk2 - pairs[p].llk0};
   }
   for (int64_t i = 0; i < n; ++i)
     if (!std::is_sorted(adj.begin() + ptr[i], adj.begin() + ptr[i + 1], [](const Nbr& a, const Nbr& b) { return a.other < b.other; }))

@@ -24,6 +24,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 
 #include "ccu_handle.h"
 #include "fmx_internal.h"
@@ -104,17 +105,25 @@ __global__ void fmx_pair_reduce_kernel(int64_t npairs, int64_t nbcs, const uint6
   out[u] = o;
 }
 
+struct PairVotes {  // a pair casts a vote iff its Bayes factor passes the threshold in either direction
+  double thres;
+  __host__ __device__ bool operator()(const ccu_pair_dist& p) const {
+    const double bf = p.llk2 - p.llk0;
+    return (bf > thres) || (-bf > thres);
+  }
+};
+
 }  // namespace ccu
 
 namespace {
 
 struct PairState {
-  DevBuf cnt, rec_ptr, keys, keys_alt, ids, ids_alt, llk, reads, ukeys, ucnt, run_ptr, nruns, temp, out;
+  DevBuf cnt, rec_ptr, keys, keys_alt, ids, ids_alt, llk, reads, ukeys, ucnt, run_ptr, nruns, temp, out, sel;
   int64_t npairs = -1, nrecords = 0;
   float ms = 0;
   void release() {
     DevBuf* all[] = {&cnt, &rec_ptr, &keys, &keys_alt, &ids, &ids_alt, &llk, &reads, &ukeys, &ucnt, &run_ptr, &nruns,
-                     &temp, &out};
+                     &temp, &out, &sel};
     for (DevBuf* b : all) b->release();
     npairs = -1;
   }
@@ -222,3 +231,31 @@ int ccu_fmx_pairs_download(ccu_handle* h, FmxPairs* ps, ccu_pair_dist* out) {
 
 float ccu_fmx_pairs_ms(const FmxPairs* ps) { return ps ? ps->ms : 0.f; }
 int64_t ccu_fmx_pairs_records(const FmxPairs* ps) { return ps ? ps->nrecords : 0; }
+
+// the pairs whose |llk2 - llk0| passes bf_thres (the only ones the votes of :262-278 / :311-320 look at),
+// compacted on the device in (id1, id2) order; out == NULL only counts them
+int ccu_fmx_pairs_download_voting(ccu_handle* h, FmxPairs* ps, double bf_thres, int64_t* nvoting, ccu_pair_dist* out) {
+  if (!ps || ps->npairs < 0) return ccu_fail(h, "ccu_fmx_get_voting_pairs: call ccu_fmx_pair_distances first");
+  if (!nvoting) return ccu_fail(h, "ccu_fmx_get_voting_pairs: NULL count");
+  *nvoting = 0;
+  if (ps->npairs == 0) return 0;
+  cudaStream_t st = h->stream;
+  CCU_CUDA(h, ps->sel.reserve(ps->npairs * sizeof(ccu_pair_dist) + 16));
+  CCU_CUDA(h, ps->nruns.reserve(sizeof(int64_t)));
+  size_t tb = 0;
+  ccu::PairVotes pred{bf_thres};
+  CCU_CUDA(h, cub::DeviceSelect::If(nullptr, tb, ps->out.as<ccu_pair_dist>(), ps->sel.as<ccu_pair_dist>(),
+                                    ps->nruns.as<int64_t>(), (int)ps->npairs, pred, st));
+  CCU_CUDA(h, ps->temp.reserve(tb + 16));
+  CCU_CUDA(h, cub::DeviceSelect::If(ps->temp.p, tb, ps->out.as<ccu_pair_dist>(), ps->sel.as<ccu_pair_dist>(),
+                                    ps->nruns.as<int64_t>(), (int)ps->npairs, pred, st));
+  int64_t n = 0;
+  CCU_CUDA(h, cudaMemcpyAsync(&n, ps->nruns.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CCU_CUDA(h, cudaStreamSynchronize(st));
+  *nvoting = n;
+  if (out && n > 0) {
+    CCU_CUDA(h, cudaMemcpyAsync(out, ps->sel.p, n * sizeof(ccu_pair_dist), cudaMemcpyDeviceToHost, st));
+    CCU_CUDA(h, cudaStreamSynchronize(st));
+  }
+  return 0;
+}

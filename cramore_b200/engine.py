@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "ccu_fmx_assign_dev", "ccu_fmx_mstep_dev", "ccu_fmx_estep_dev", "ccu_fmx_download_results", "ccu_fmx_run_em",
     "ccu_fmx_get_timings", "ccu_fmx_selftest_division", "ccu_fmx_post_dev", "ccu_fmx_posteriors_dev",
     "ccu_fmx_estep_post_dev", "ccu_fmx_pair_distances", "ccu_fmx_get_pair_distances", "ccu_fmx_initial_clusters",
-    "ccu_fmx_greedy_clusters",
+    "ccu_fmx_greedy_clusters", "ccu_fmx_get_voting_pairs",
 ]
 
 
@@ -315,13 +315,24 @@ class FreemuxEngine(DemuxEngine):
                                             C.c_int32(int(stop_when_stable)), _ptr(out), C.byref(it)))
         return out, it.value
 
-    def pair_distances(self):
+    def pair_distances(self, download=True):
         """Sparse dropDs matrix of cmd_cram_freemuxlet.cpp:172-221: records sorted by (id1 > id2)."""
         n, nrec, ms = C.c_int64(0), C.c_int64(0), C.c_float(0)
         self._check(self.lib.ccu_fmx_pair_distances(self.h, C.byref(n), C.byref(nrec), C.byref(ms)))
+        self.pair_stats = {"pairs": n.value, "records": nrec.value, "ms": ms.value}
+        if not download:
+            return None
         out = np.zeros(n.value, PAIR_DIST_DTYPE)
         self._check(self.lib.ccu_fmx_get_pair_distances(self.h, _ptr(out)))
-        self.pair_stats = {"pairs": n.value, "records": nrec.value, "ms": ms.value}
+        return out
+
+    def voting_pairs(self, bf_thres=5.41):
+        """After pair_distances(): only the pairs with |llk2 - llk0| > bf_thres (device-side compaction)."""
+        n = C.c_int64(0)
+        self._check(self.lib.ccu_fmx_get_voting_pairs(self.h, C.c_double(bf_thres), C.byref(n), None))
+        out = np.zeros(n.value, PAIR_DIST_DTYPE)
+        if n.value:
+            self._check(self.lib.ccu_fmx_get_voting_pairs(self.h, C.c_double(bf_thres), C.byref(n), _ptr(out)))
         return out
 
     def selftest_division(self, nsets=1 << 22, seed=1):

@@ -239,6 +239,10 @@ typedef struct {
  * the number of (pair, SNP) records they were folded from and the device time. */
 int ccu_fmx_pair_distances(ccu_handle* h, int64_t* npairs, int64_t* nrecords, float* ms);
 int ccu_fmx_get_pair_distances(ccu_handle* h, ccu_pair_dist* out /* [npairs] */);
+/* Only the pairs that can cast a vote in the clustering below, |llk2 - llk0| > bf_thres (compacted on the device,
+ * same order): call once with out == NULL for the count, then with a buffer of that many records.  The votes they
+ * give are identical to those of the full list -- the other pairs never touch a vote (:270-277, :313-318). */
+int ccu_fmx_get_voting_pairs(ccu_handle* h, double bf_thres, int64_t* nvoting, ccu_pair_dist* out);
 
 /* Host part of the initial clustering (:223-346): greedy assignment in the order of the singlet scores
  * (cell_scores[i] = SNG.LLK - DBL.LLK of .lmix, ties by larger id first, sc_drop_seq.h:190-198) by votes of the

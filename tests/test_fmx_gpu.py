@@ -271,6 +271,11 @@ def test_pair_distances_match_oracle(feng):
     np.testing.assert_allclose(got["llk0"], ref["llk0"], rtol=1e-12)
     np.testing.assert_allclose(got["llk2"], ref["llk2"], rtol=1e-12)
     assert np.all(np.diff(got["id1"].astype(np.int64) * d["nbcs"] + got["id2"]) > 0)
+    # device-side compaction of the pairs that can vote
+    for thres in (5.41, 1.0):
+        sel = feng.voting_pairs(thres)
+        want = got[np.abs(got["llk2"] - got["llk0"]) > thres]
+        assert np.array_equal(sel, want) and (thres > 2 or len(sel) > 0)
 
 
 @pytest.mark.parametrize("name", ["fmx_init_k3", "fmx_init_k4_partial"])
@@ -285,6 +290,7 @@ def test_initial_clustering_from_gpu_distances_equals_reference(feng, name):
     feng.upload_fmx(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], af)
     l0, l2 = feng.lmix()
     pairs = feng.pair_distances()
-    clusts = initial_clusters(l2 - l0, pairs, K, bf_thres=prm["bf_thres"], frac_init_clust=prm["frac_init_clust"],
-                              iter_init=10, keep_init_missing=prm["keep_init_missing"], seed=1)
-    assert clusts.tolist() == fx["clust0"]
+    for plist in (pairs, feng.voting_pairs(prm["bf_thres"])):  # the full list and the compacted one vote alike
+        clusts = initial_clusters(l2 - l0, plist, K, bf_thres=prm["bf_thres"], frac_init_clust=prm["frac_init_clust"],
+                                  iter_init=10, keep_init_missing=prm["keep_init_missing"], seed=1)
+        assert clusts.tolist() == fx["clust0"]

@@ -32,14 +32,14 @@ def main():
     eng.upload_fmx(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], d["af"])
     l0, l2 = eng.lmix()
     t0 = time.perf_counter()
-    pairs = eng.pair_distances()
+    eng.pair_distances(download=False)
+    pairs = eng.voting_pairs(5.41)  # the pairs that can cast a vote (|llk2 - llk0| > --bf-thres), compacted on the device
     t_pairs = time.perf_counter() - t0
     st = eng.pair_stats
     t0 = time.perf_counter()
     clusts = initial_clusters(l2 - l0, pairs, K, iter_init=args.iter_init)
     t_votes = time.perf_counter() - t0
-    bf = pairs["llk2"] - pairs["llk0"]
-    voting = int((np.abs(bf) > 5.41).sum())  # pairs whose Bayes factor passes --bf-thres and so cast a vote
+    voting = len(pairs)
     # bytes the device path moves at least once: pileup diagonals + counts in, 32-byte records out and back in
     nrec = st["records"]
     line = {"metric": "freemuxlet initial clustering", "config": {"workload": "C4: K=%d, %d barcodes, %d SNPs, %d entries" %
@@ -48,7 +48,7 @@ def main():
             "gpu_records_per_s": nrec / (st["ms"] * 1e-3) if st["ms"] > 0 else None,
             "pair_distances_s_incl_download": t_pairs, "host_votes_s": t_votes, "iter_init": args.iter_init,
             "dense_matrix_bytes_of_the_reference": int(d["nbcs"]) * int(d["nbcs"]) // 2 * 32,
-            "sparse_bytes": int(pairs.nbytes), "pairs_passing_bf_thres": voting,
+            "sparse_bytes_on_device": int(st["pairs"]) * 40, "pairs_passing_bf_thres": voting, "bytes_downloaded": int(pairs.nbytes),
             "clusters_used": int(len(np.unique(clusts[clusts >= 0])))}
     print(json.dumps(line), flush=True)
     eng.close()
