@@ -50,6 +50,8 @@ def test_appendix_c_known_answer(engine):
 @pytest.mark.parametrize("nv,alphas", [
     (2, [0, 0.5]), (3, [0, 0.3]), (8, [0, 0.5]), (33, [0, 0.25, 0.5]), (64, [0, 0.1, 0.2, 0.3, 0.4, 0.5]),
     (65, [round(0.05 * i, 2) for i in range(11)]), (40, [0, 0.1, 0.2, 0.3, 0.35, 0.4, 0.45, 0.5]),
+    (5, [0, 0.25, 0.75, 1.0]),                      # grid beyond 0.5: the one-SNP form of the affine path
+    (34, [round(0.025 * i, 3) for i in range(21)]),  # two chunks of ten alphas: runtime chunk offset
 ])
 def test_llk_matrix_and_calls(engine, nv, alphas):
     d = make_dataset("C1", nbcs=12, nsnps=500, nv=nv, rbar=60)
