@@ -232,10 +232,7 @@ int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* ce
     void* temp = base + 4 * a4;
     CCU_CUDA(h, ccu::launch_fmx_entry_cells(d, ent_cell, st));
     if (n > 0) {
-      std::vector<int32_t> iota(n);
-      for (size_t i = 0; i < n; ++i) iota[i] = (int32_t)i;
-      CCU_CUDA(h, cudaMemcpyAsync(vals_in, iota.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-      CCU_CUDA(h, cudaStreamSynchronize(st));
+      CCU_CUDA(h, ccu::launch_fmx_iota(vals_in, (int64_t)n, st));
       CCU_CUDA(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, d.snp_idx, keys_out, vals_in, vals_out, (int)n, 0,
                                                   end_bit, st));
     }

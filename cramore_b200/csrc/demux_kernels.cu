@@ -13,8 +13,9 @@
 // loop.  K2 uses the exact factorisation  S[j,k,n] = sum_l g_j[l] * T[k,n,l],
 // T[k,n,l] = sum_m g_k[m] * pG[n,l,m]  and accumulates  prod_snp S  as (mantissa, exponent)
 // instead of  sum_snp log S : every factor lies in [~1e-10, ~1], the mantissa is renormalised
-// into [1,2) every 16 SNPs by integer exponent extraction, and a single log per reported value
-// is taken at the very end.  This is the same real number as the reference's sum of logs to
+// into [1,2) by integer exponent extraction whenever an underflow budget of 960 binary orders of
+// magnitude is used up (about every 29 general or 96 single-read SNPs), and a single log per
+// reported value is taken at the very end.  This is the same real number as the reference's sum of logs to
 // ~1e-13 relative (FP64 throughout).
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -874,10 +875,6 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
       }
     };
     int s = 0;
-#ifdef CCU_EXPERIMENT_SKIP_MATH  // timing experiment only: the data pipeline without the multiplications
-    if (cnt > 0) acc[0][0] *= fj_base[0] + fk_base[0] + d.alpha_c[n0];
-    s = cnt;
-#endif
     while (s < cnt) {
       if (budget < 2 * abits) {
         renorm_all();

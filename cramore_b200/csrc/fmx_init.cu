@@ -121,7 +121,11 @@ struct PairState {
   DevBuf cnt, rec_ptr, keys, keys_alt, ids, ids_alt, llk, reads, ukeys, ucnt, run_ptr, nruns, temp, out, sel;
   int64_t npairs = -1, nrecords = 0;
   float ms = 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
   void release() {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    e0 = e1 = nullptr;
     DevBuf* all[] = {&cnt, &rec_ptr, &keys, &keys_alt, &ids, &ids_alt, &llk, &reads, &ukeys, &ucnt, &run_ptr, &nruns,
                      &temp, &out, &sel};
     for (DevBuf* b : all) b->release();
@@ -147,9 +151,10 @@ int ccu_fmx_pairs_build(ccu_handle* h, const ccu::FmxDev& d, FmxPairs*& ps, int6
   cudaStream_t st = h->stream;
   const int64_t nsnps = d.nsnps;
   if ((double)d.nbcs * (double)d.nbcs >= 1.8e19) return ccu_fail(h, "ccu_fmx_pair_distances: too many droplets");
-  cudaEvent_t e0, e1;
-  CCU_CUDA(h, cudaEventCreate(&e0));
-  CCU_CUDA(h, cudaEventCreate(&e1));
+  if (!ps->e0) CCU_CUDA(h, cudaEventCreate(&ps->e0));
+  if (!ps->e1) CCU_CUDA(h, cudaEventCreate(&ps->e1));
+  cudaEvent_t e0 = ps->e0, e1 = ps->e1;
+  ps->npairs = -1;
   CCU_CUDA(h, cudaEventRecord(e0, st));
   CCU_CUDA(h, ps->cnt.reserve((nsnps + 1) * sizeof(int64_t)));
   CCU_CUDA(h, ps->rec_ptr.reserve((nsnps + 1) * sizeof(int64_t)));
@@ -213,8 +218,6 @@ int ccu_fmx_pairs_build(ccu_handle* h, const ccu::FmxDev& d, FmxPairs*& ps, int6
   CCU_CUDA(h, cudaEventRecord(e1, st));
   CCU_CUDA(h, cudaEventSynchronize(e1));
   cudaEventElapsedTime(&ps->ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   ps->npairs = nruns;
   if (npairs_out) *npairs_out = nruns;
   return 0;

@@ -54,6 +54,8 @@ struct FmxDev {
 
 cudaError_t launch_fmx_pileup(const FmxDev& d, double alpha, cudaStream_t st);
 cudaError_t launch_fmx_lmix(const FmxDev& d, double* llk0, double* llk2, cudaStream_t st);
+// out[i] = i
+cudaError_t launch_fmx_iota(int32_t* out, int64_t n, cudaStream_t st);
 // ent_cell[nnz]: droplet id of every entry
 cudaError_t launch_fmx_entry_cells(const FmxDev& d, int32_t* ent_cell, cudaStream_t st);
 // after the (snp, entry) pairs were sorted by snp: gather the SNP-major copy and the segment offsets
