@@ -19,6 +19,24 @@ void dump_vec(const std::string& fn, const void* p, size_t bytes) {
   fclose(f);
 }
 
+template <typename T>
+void load_vec(const std::string& fn, std::vector<T>& v) {
+  FILE* f = fopen(fn.c_str(), "rb");
+  if (!f) fatal("Cannot read %s (written by --gpu-dump-inputs)", fn.c_str());
+  fseek(f, 0, SEEK_END);
+  const long bytes = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  if (bytes < 0 || bytes % (long)sizeof(T) != 0) fatal("%s: unexpected size", fn.c_str());
+  v.resize((size_t)bytes / sizeof(T));
+  if (bytes > 0 && fread(v.data(), 1, (size_t)bytes, f) != (size_t)bytes) fatal("%s: short read", fn.c_str());
+  fclose(f);
+}
+
+void load_lines(const std::string& fn, std::vector<std::string>& v) {
+  LineReader lr(fn);
+  while (lr.next_line()) v.push_back(lr.line);
+}
+
 std::vector<int> parse_devices(const std::string& s) {
   std::vector<int> v;
   size_t p = 0;
@@ -37,7 +55,7 @@ std::vector<int> parse_devices(const std::string& s) {
 int cmdDemuxlet(int argc, char** argv) {
   // defaults of cmd_cram_demuxlet.cpp:7-36
   std::string samFile, tagGroup("CB"), tagUMI("UB"), plpPrefix, vcfFile, field("GP"), r2Info("R2"), smList, outPrefix,
-      groupList, gpuDevices("0"), dumpPrefix;
+      groupList, gpuDevices("0"), dumpPrefix, loadPrefix;
   double genoErrorOffset = 0.10, genoErrorCoeffR2 = 0.00, minCallRate = 0.5, doublet_prior = 0.5;
   int32_t minMAC = 1, samVerbose = 1000000, vcfVerbose = 10000, capBQ = 20, minBQ = 13, minMQ = 20, minTD = 0,
           exclFlag = 0x0f04, minTotalReads = 0, minUMIs = 0, minCoveredSNPs = 0;
@@ -81,6 +99,7 @@ int cmdDemuxlet(int argc, char** argv) {
   pl.group("GPU engine options (additions of this build)");
   pl.add("gpu-devices", &gpuDevices, "Comma-separated CUDA device ids; droplets are sharded across them");
   pl.add("gpu-dump-inputs", &dumpPrefix, "Write the flattened engine inputs to PREFIX.* and exit without touching a GPU");
+  pl.add("gpu-load-inputs", &loadPrefix, "Binary sidecar cache: read the engine inputs written by --gpu-dump-inputs instead of parsing --plp/--vcf (droplet and variant filters are those of the dump)");
   if (!pl.read(argc, argv)) return 1;
 
   if (gridAlpha.empty()) {  // :85-89
@@ -93,119 +112,157 @@ int cmdDemuxlet(int argc, char** argv) {
     fatal("--sam needs htslib's BAM/CRAM reader, which this build does not include; run `cramore dsc-pileup` "
           "once and pass its output with --plp");
   }
-  if (plpPrefix.empty() || vcfFile.empty() || outPrefix.empty()) fatal("Missing required option(s) : --plp, --vcf, --out");
+  if (outPrefix.empty()) fatal("Missing required option(s) : --out");
+  if (loadPrefix.empty() && (plpPrefix.empty() || vcfFile.empty())) fatal("Missing required option(s) : --plp, --vcf, --out");
 
-  std::set<std::string> sm_ids(smIDs.begin(), smIDs.end());
-  if (!smList.empty()) {
-    LineReader lr(smList);
-    while (lr.read_fields() > 0) sm_ids.insert(lr.fields[0]);
-  }
-  VcfReader vr(vcfFile, sm_ids);
-  vr.minMAC = minMAC;
-  vr.minCallRate = minCallRate;
-  vr.maxAlleles = 2;
-  const int32_t nv = vr.nsamples();
-
-  PlpFilters flt;
-  flt.minRead = minTotalReads;
-  flt.minUMI = minUMIs;
-  flt.minSNP = minCoveredSNPs;
-  flt.capBQ = capBQ;
-  flt.minBQ = minBQ;
-  if (!groupList.empty()) {
-    LineReader lr(groupList);
-    while (lr.read_fields() > 0) flt.valid_bcs.insert(lr.fields[0]);
-    notice("Loaded %zu valid barcodes from %s", flt.valid_bcs.size(), groupList.c_str());
-  }
-
-  // ---- .var.gz x VCF join, sc_drop_seq.cpp:108-116 and :226-330 ----
-  if (!vr.read()) fatal("Cannot read any single variant from %s", vcfFile.c_str());
+  // what the engine and the .best writer need: filled by ingestion, or by the binary sidecar cache
+  std::vector<int64_t> cell_ptr, read_ptr;
+  std::vector<int32_t> snp_idx, row_int_id;
+  std::vector<uint8_t> al, bq, has_gp;
   std::vector<float> gp_f32;
   std::vector<double> snp_err;
-  std::vector<uint8_t> has_gp;
-  std::vector<float> tmp_gp(nv * 3);
-  DropletStore st;
-  load_plp(plpPrefix, flt, st, [&](int32_t /*idx*/, const char* chr, const SnpInfo& s) {
-    bool found = false, passed = false;
-    while (!(found || passed)) {
-      if (vr.eof) passed = true;
-      else if (vr.cur.rid > s.rid) passed = true;
-      else if (vr.cur.rid == s.rid) {
-        if (vr.cur.pos1 > s.pos) passed = true;
-        else if (vr.cur.pos1 == s.pos) {
-          if (vr.cur.ref[0] != s.ref || vr.cur.alt[0] != s.alt) passed = true;
-          else found = true;
+  std::vector<std::string> row_bcs, sample_ids;
+  int32_t nv_total = 0;
+  int64_t nsnps_total = 0;
+  if (!loadPrefix.empty()) {
+    load_vec(loadPrefix + ".cell_ptr.i64", cell_ptr);
+    load_vec(loadPrefix + ".snp_idx.i32", snp_idx);
+    load_vec(loadPrefix + ".read_ptr.i64", read_ptr);
+    load_vec(loadPrefix + ".al.u8", al);
+    load_vec(loadPrefix + ".bq.u8", bq);
+    load_vec(loadPrefix + ".gp.f32", gp_f32);
+    load_vec(loadPrefix + ".snp_err.f64", snp_err);
+    load_vec(loadPrefix + ".has_gp.u8", has_gp);
+    load_vec(loadPrefix + ".row_int_id.i32", row_int_id);
+    load_lines(loadPrefix + ".barcodes.txt", row_bcs);
+    load_lines(loadPrefix + ".samples.txt", sample_ids);
+    nv_total = (int32_t)sample_ids.size();
+    nsnps_total = (int64_t)snp_err.size();
+    if (cell_ptr.empty() || cell_ptr.size() != row_bcs.size() + 1 || row_int_id.size() != row_bcs.size() ||
+        read_ptr.size() != snp_idx.size() + 1 || (int64_t)snp_idx.size() != cell_ptr.back() || al.size() != bq.size() ||
+        (int64_t)al.size() != read_ptr.back() || has_gp.size() != snp_err.size() || nv_total < 1 ||
+        gp_f32.size() != (size_t)nsnps_total * nv_total * 3)
+      fatal("--gpu-load-inputs %s: the files do not belong together", loadPrefix.c_str());
+    notice("Loaded engine inputs for %zu droplets, %lld variants, %d samples from %s.*", row_bcs.size(),
+           (long long)nsnps_total, nv_total, loadPrefix.c_str());
+  } else {
+
+    std::set<std::string> sm_ids(smIDs.begin(), smIDs.end());
+    if (!smList.empty()) {
+      LineReader lr(smList);
+      while (lr.read_fields() > 0) sm_ids.insert(lr.fields[0]);
+    }
+    VcfReader vr(vcfFile, sm_ids);
+    vr.minMAC = minMAC;
+    vr.minCallRate = minCallRate;
+    vr.maxAlleles = 2;
+    const int32_t nv = vr.nsamples();
+
+    PlpFilters flt;
+    flt.minRead = minTotalReads;
+    flt.minUMI = minUMIs;
+    flt.minSNP = minCoveredSNPs;
+    flt.capBQ = capBQ;
+    flt.minBQ = minBQ;
+    if (!groupList.empty()) {
+      LineReader lr(groupList);
+      while (lr.read_fields() > 0) flt.valid_bcs.insert(lr.fields[0]);
+      notice("Loaded %zu valid barcodes from %s", flt.valid_bcs.size(), groupList.c_str());
+    }
+
+    // ---- .var.gz x VCF join, sc_drop_seq.cpp:108-116 and :226-330 ----
+    if (!vr.read()) fatal("Cannot read any single variant from %s", vcfFile.c_str());
+    std::vector<float> tmp_gp(nv * 3);
+    DropletStore st;
+    load_plp(plpPrefix, flt, st, [&](int32_t /*idx*/, const char* chr, const SnpInfo& s) {
+      bool found = false, passed = false;
+      while (!(found || passed)) {
+        if (vr.eof) passed = true;
+        else if (vr.cur.rid > s.rid) passed = true;
+        else if (vr.cur.rid == s.rid) {
+          if (vr.cur.pos1 > s.pos) passed = true;
+          else if (vr.cur.pos1 == s.pos) {
+            if (vr.cur.ref[0] != s.ref || vr.cur.alt[0] != s.alt) passed = true;
+            else found = true;
+          }
         }
+        if (passed || found) break;
+        vr.read();
       }
-      if (passed || found) break;
-      vr.read();
-    }
-    gp_f32.resize(gp_f32.size() + (size_t)nv * 3, 0.0f);
-    if (found) {
-      if (!vr.parse_posteriors(field.c_str(), 0, tmp_gp.data()))
-        fatal("Cannot parse posterior probability at %s:%d", chr, s.pos);
-      memcpy(&gp_f32[gp_f32.size() - (size_t)nv * 3], tmp_gp.data(), sizeof(float) * nv * 3);
-      double err = genoErrorOffset;  // :298-306
-      if (genoErrorCoeffR2 > 0) {
-        float r2;
-        if (!vr.info_float(r2Info.c_str(), &r2))
-          fatal("Cannot extract %s (1 float value) from INFO field at %s:%d. Cannot use --geno-error-coeff", r2Info.c_str(), chr, s.pos);
-        err += (1 - genoErrorOffset) * (1 - r2) * genoErrorCoeffR2;
+      gp_f32.resize(gp_f32.size() + (size_t)nv * 3, 0.0f);
+      if (found) {
+        if (!vr.parse_posteriors(field.c_str(), 0, tmp_gp.data()))
+          fatal("Cannot parse posterior probability at %s:%d", chr, s.pos);
+        memcpy(&gp_f32[gp_f32.size() - (size_t)nv * 3], tmp_gp.data(), sizeof(float) * nv * 3);
+        double err = genoErrorOffset;  // :298-306
+        if (genoErrorCoeffR2 > 0) {
+          float r2;
+          if (!vr.info_float(r2Info.c_str(), &r2))
+            fatal("Cannot extract %s (1 float value) from INFO field at %s:%d. Cannot use --geno-error-coeff", r2Info.c_str(), chr, s.pos);
+          err += (1 - genoErrorOffset) * (1 - r2) * genoErrorCoeffR2;
+        }
+        snp_err.push_back(err);  // clamped to [0, 0.999] by the engine (:308-309)
+        has_gp.push_back(1);
+      } else {
+        snp_err.push_back(0.0);
+        has_gp.push_back(0);  // SNP kept without genotypes: sc_snp_t::gps == NULL (:278-282)
       }
-      snp_err.push_back(err);  // clamped to [0, 0.999] by the engine (:308-309)
-      has_gp.push_back(1);
-    } else {
-      snp_err.push_back(0.0);
-      has_gp.push_back(0);  // SNP kept without genotypes: sc_snp_t::gps == NULL (:278-282)
-    }
-  });
-  notice("Finished reading %lld variants from %s (%lld skipped by the variant filter)", (long long)vr.nRead, vcfFile.c_str(),
-         (long long)vr.nSkip);
+    });
+    notice("Finished reading %lld variants from %s (%lld skipped by the variant filter)", (long long)vr.nRead, vcfFile.c_str(),
+           (long long)vr.nSkip);
 
-  // ---- droplets that produce a row, in std::map barcode order (:636-653) ----
-  const int32_t nbcs = st.nbcs();
-  std::vector<int32_t> order(nbcs);
-  for (int32_t i = 0; i < nbcs; ++i) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return st.bcs[a] < st.bcs[b]; });
-  std::vector<int32_t> row_cell, row_int_id;
-  for (int32_t rank = 0; rank < nbcs; ++rank) {
-    const int32_t i = order[rank];
-    const int32_t ns = (int32_t)(st.cell_ptr[i + 1] - st.cell_ptr[i]);
-    if (st.totl_reads[i] < minTotalReads || st.uniq_reads[i] < minUMIs || ns < minCoveredSNPs) continue;
-    if (ns == 0) continue;
-    row_cell.push_back(i);
-    row_int_id.push_back(rank);
-  }
-  // CSR of those droplets, in row order
-  std::vector<int64_t> cell_ptr(1, 0), read_ptr(1, 0);
-  std::vector<int32_t> snp_idx;
-  std::vector<uint8_t> al, bq;
-  for (int32_t i : row_cell) {
-    for (int64_t e = st.cell_ptr[i]; e < st.cell_ptr[i + 1]; ++e) {
-      snp_idx.push_back(st.snp_idx[e]);
-      al.insert(al.end(), st.al.begin() + st.read_ptr[e], st.al.begin() + st.read_ptr[e + 1]);
-      bq.insert(bq.end(), st.bq.begin() + st.read_ptr[e], st.bq.begin() + st.read_ptr[e + 1]);
-      read_ptr.push_back((int64_t)al.size());
+    // ---- droplets that produce a row, in std::map barcode order (:636-653) ----
+    const int32_t nbcs = st.nbcs();
+    std::vector<int32_t> order(nbcs);
+    for (int32_t i = 0; i < nbcs; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return st.bcs[a] < st.bcs[b]; });
+    std::vector<int32_t> row_cell;
+    for (int32_t rank = 0; rank < nbcs; ++rank) {
+      const int32_t i = order[rank];
+      const int32_t ns = (int32_t)(st.cell_ptr[i + 1] - st.cell_ptr[i]);
+      if (st.totl_reads[i] < minTotalReads || st.uniq_reads[i] < minUMIs || ns < minCoveredSNPs) continue;
+      if (ns == 0) continue;
+      row_cell.push_back(i);
+      row_int_id.push_back(rank);
     }
-    cell_ptr.push_back((int64_t)snp_idx.size());
-  }
-  const int64_t nrows = (int64_t)row_cell.size();
+    // CSR of those droplets, in row order
+    cell_ptr.assign(1, 0);
+    read_ptr.assign(1, 0);
+    for (int32_t i : row_cell) {
+      for (int64_t e = st.cell_ptr[i]; e < st.cell_ptr[i + 1]; ++e) {
+        snp_idx.push_back(st.snp_idx[e]);
+        al.insert(al.end(), st.al.begin() + st.read_ptr[e], st.al.begin() + st.read_ptr[e + 1]);
+        bq.insert(bq.end(), st.bq.begin() + st.read_ptr[e], st.bq.begin() + st.read_ptr[e + 1]);
+        read_ptr.push_back((int64_t)al.size());
+      }
+      cell_ptr.push_back((int64_t)snp_idx.size());
+    }
+    for (int32_t i : row_cell) row_bcs.push_back(st.bcs[i]);
+    for (int32_t j = 0; j < nv; ++j) sample_ids.push_back(vr.sample_id(j));
+    nv_total = nv;
+    nsnps_total = st.nsnps();
 
-  if (!dumpPrefix.empty()) {  // test hook: the flattened inputs, bit for bit
-    dump_vec(dumpPrefix + ".cell_ptr.i64", cell_ptr.data(), cell_ptr.size() * 8);
-    dump_vec(dumpPrefix + ".snp_idx.i32", snp_idx.data(), snp_idx.size() * 4);
-    dump_vec(dumpPrefix + ".read_ptr.i64", read_ptr.data(), read_ptr.size() * 8);
-    dump_vec(dumpPrefix + ".al.u8", al.data(), al.size());
-    dump_vec(dumpPrefix + ".bq.u8", bq.data(), bq.size());
-    dump_vec(dumpPrefix + ".gp.f32", gp_f32.data(), gp_f32.size() * 4);
-    dump_vec(dumpPrefix + ".snp_err.f64", snp_err.data(), snp_err.size() * 8);
-    dump_vec(dumpPrefix + ".has_gp.u8", has_gp.data(), has_gp.size());
-    dump_vec(dumpPrefix + ".row_int_id.i32", row_int_id.data(), row_int_id.size() * 4);
-    Writer w(dumpPrefix + ".barcodes.txt", false);
-    for (int32_t i : row_cell) w.printf("%s\n", st.bcs[i].c_str());
-    notice("Wrote engine inputs for %lld droplets to %s.*", (long long)nrows, dumpPrefix.c_str());
-    return 0;
+    if (!dumpPrefix.empty()) {  // test hook: the flattened inputs, bit for bit
+      dump_vec(dumpPrefix + ".cell_ptr.i64", cell_ptr.data(), cell_ptr.size() * 8);
+      dump_vec(dumpPrefix + ".snp_idx.i32", snp_idx.data(), snp_idx.size() * 4);
+      dump_vec(dumpPrefix + ".read_ptr.i64", read_ptr.data(), read_ptr.size() * 8);
+      dump_vec(dumpPrefix + ".al.u8", al.data(), al.size());
+      dump_vec(dumpPrefix + ".bq.u8", bq.data(), bq.size());
+      dump_vec(dumpPrefix + ".gp.f32", gp_f32.data(), gp_f32.size() * 4);
+      dump_vec(dumpPrefix + ".snp_err.f64", snp_err.data(), snp_err.size() * 8);
+      dump_vec(dumpPrefix + ".has_gp.u8", has_gp.data(), has_gp.size());
+      dump_vec(dumpPrefix + ".row_int_id.i32", row_int_id.data(), row_int_id.size() * 4);
+      Writer w(dumpPrefix + ".barcodes.txt", false);
+      for (const std::string& b : row_bcs) w.printf("%s\n", b.c_str());
+      Writer ws(dumpPrefix + ".samples.txt", false);
+      for (const std::string& b : sample_ids) ws.printf("%s\n", b.c_str());
+      notice("Wrote engine inputs for %lld droplets to %s.*", (long long)row_bcs.size(), dumpPrefix.c_str());
+      return 0;
+    }
+
   }
+  const int32_t nv = nv_total;
+  const int64_t nrows = (int64_t)row_bcs.size();
 
   // ---- engine: one handle per GPU, contiguous row ranges balanced by entry count ----
   notice("Starting to identify best matching individual IDs");
@@ -234,7 +291,7 @@ int cmdDemuxlet(int argc, char** argv) {
     const int64_t r0 = rp.front();
     for (auto& x : rp) x -= r0;
     if (ccu_demux_configure(h, nv, nAlpha, gridAlpha.data(), doublet_prior) ||
-        ccu_demux_set_genotypes(h, st.nsnps(), gp_f32.data(), snp_err.data(), has_gp.data()) ||
+        ccu_demux_set_genotypes(h, nsnps_total, gp_f32.data(), snp_err.data(), has_gp.data()) ||
         ccu_demux_score(h, e - b, cp.data(), snp_idx.data() + e0, rp.data(), al.data() + r0, bq.data() + r0, res.data() + b))
       errs[d] = ccu_last_error(h);
     ccu_destroy(h);
@@ -254,14 +311,14 @@ int cmdDemuxlet(int argc, char** argv) {
   const char* hdr = ccu_demux_best_header();
   wbest.write(hdr, (int)strlen(hdr));
   std::vector<const char*> ids(nv);
-  for (int32_t j = 0; j < nv; ++j) ids[j] = vr.sample_id(j);
+  for (int32_t j = 0; j < nv; ++j) ids[j] = sample_ids[j].c_str();
   char row[8192];
   for (int64_t r = 0; r < nrows; ++r) {
-    const int32_t i = row_cell[r];
-    const int n = ccu_demux_best_row(row, sizeof(row), row_int_id[r], st.bcs[i].c_str(),
-                                     (uint32_t)(st.cell_ptr[i + 1] - st.cell_ptr[i]), st.uniq_reads[i], &res[r], nv, nAlpha,
+    const int n = ccu_demux_best_row(row, sizeof(row), row_int_id[r], row_bcs[r].c_str(),
+                                     (uint32_t)(cell_ptr[r + 1] - cell_ptr[r]),
+                                     (uint32_t)(read_ptr[cell_ptr[r + 1]] - read_ptr[cell_ptr[r]]), &res[r], nv, nAlpha,
                                      gridAlpha.data(), doublet_prior, ids.data());
-    if (n < 0) fatal("cannot format the row of droplet %s", st.bcs[i].c_str());
+    if (n < 0) fatal("cannot format the row of droplet %s", row_bcs[r].c_str());
     wbest.write(row, n);
   }
   wbest.close();

@@ -123,6 +123,77 @@ class Writer {
 };
 
 // ---- text VCF reader: sequential cursor with the variant filter of cmdCramDemuxlet ----
+// strtof for the plain decimals a VCF holds ("0.97", "1", "3.3e-05"), bit-identical to strtof: up to 15 digits
+// and a small power of ten go through Clinger's exact double path (double(m) * or / 10^k is the correctly rounded
+// double) and one cast; a value whose double sits within 2 ulp of a float rounding boundary, or anything else
+// (long mantissas, inf/nan, hex, large exponents), is handed to strtof itself.
+inline float fast_strtof(const char* s, const char** end) {
+  static const double p10[] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11,
+                               1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+  const char* p = s;
+  bool neg = false;
+  if (*p == '-' || *p == '+') neg = (*p++ == '-');
+  uint64_t m = 0;
+  int nd = 0, dexp = 0;
+  bool any = false;
+  while (*p >= '0' && *p <= '9') {
+    any = true;
+    if (nd < 15) {
+      m = m * 10 + (uint64_t)(*p - '0');
+      if (m) ++nd;
+    } else {
+      ++dexp;
+    }
+    ++p;
+  }
+  bool lossy = dexp > 0;
+  if (*p == '.') {
+    ++p;
+    while (*p >= '0' && *p <= '9') {
+      any = true;
+      if (nd < 15) {
+        m = m * 10 + (uint64_t)(*p - '0');
+        if (m) ++nd;
+        --dexp;
+      } else if (*p != '0') {
+        lossy = true;
+      }
+      ++p;
+    }
+  }
+  if (any && (*p == 'e' || *p == 'E')) {
+    const char* q = p + 1;
+    bool eneg = false;
+    if (*q == '-' || *q == '+') eneg = (*q++ == '-');
+    if (*q >= '0' && *q <= '9') {
+      int ev = 0;
+      while (*q >= '0' && *q <= '9' && ev < 10000) ev = ev * 10 + (*q++ - '0');
+      dexp += eneg ? -ev : ev;
+      p = q;
+    }
+  }
+  if (any && !lossy && dexp >= -22 && dexp <= 22) {
+    const double v = (dexp < 0) ? (double)m / p10[-dexp] : (double)m * p10[dexp];
+    uint64_t bits;
+    memcpy(&bits, &v, 8);
+    const int64_t low = (int64_t)(bits & 0x1FFFFFFFull) - 0x10000000ll;  // distance to the float rounding boundary
+    const int ex = (int)((bits >> 52) & 0x7ff);
+    if ((low > 2 || low < -2) && ex > 1023 - 120 && ex < 1023 + 120) {  // normal float range, unambiguous cast
+      *end = p;
+      const float f = (float)v;
+      return neg ? -f : f;
+    }
+    if (m == 0) {
+      *end = p;
+      return neg ? -0.0f : 0.0f;
+    }
+  }
+  char* e;
+  const float f = strtof(s, &e);
+  *end = e;
+  return f;
+}
+
 struct VcfRecord {
   int32_t rid = -1, pos1 = 0;  // 1-based position
   std::string ref, alt;
@@ -228,8 +299,8 @@ class VcfReader {
       const char* p = sample_field(sm_icols[i], fi);
       float g[3];
       for (int j = 0; j < 3; ++j) {
-        char* e;
-        g[j] = strtof(p, &e);
+        const char* e;
+        g[j] = fast_strtof(p, &e);
         p = (*e == ',') ? e + 1 : e;
       }
       float sumgp = 0;

@@ -55,6 +55,15 @@ def test_cli_demuxlet_best_file(built, tmp_path, name):
         args += ["--alpha", repr(float(a))]
     r = subprocess.run(args, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
+    # binary sidecar cache: --gpu-dump-inputs once, then --gpu-load-inputs without --plp/--vcf gives the same file
+    dump = str(tmp_path / "cache")
+    r2 = subprocess.run(args + ["--gpu-dump-inputs", dump], capture_output=True, text=True)
+    assert r2.returncode == 0, r2.stderr[-3000:]
+    keep = [a for a in args if a not in ("--plp", pre, "--vcf", vcf)]
+    keep[keep.index(str(tmp_path / "out"))] = str(tmp_path / "out_cached")
+    r3 = subprocess.run(keep + ["--gpu-load-inputs", dump], capture_output=True, text=True)
+    assert r3.returncode == 0, r3.stderr[-3000:]
+    assert open(str(tmp_path / "out_cached.best")).read() == open(str(tmp_path / "out.best")).read()
     mine = open(str(tmp_path / "out.best")).read().splitlines(keepends=True)
     ref = fx["best_text"].splitlines(keepends=True)
     assert mine[0] == ref[0] and len(mine) == len(ref)
