@@ -291,7 +291,50 @@ class VcfReader {
       }
       return true;
     }
-    if (strcmp(field, "PL") == 0) fatal("--field PL is not supported by the text VCF reader yet (use GP or GT)");
+    if (strcmp(field, "PL") == 0) {  // parse_likelihoods, bcf_filtered_reader.cpp:289-365 (diploid samples)
+      // ten EM iterations for the allele frequency under HWE; the posteriors of the last one are the output.
+      // toProb(pl) = pow(0.1, pl * 0.1), capped at pl = 255 (PhredHelper.cpp:31, PhredHelper.h:40).
+      // Parity unpinned: the reference's own reader is htslib-bound and not buildable here.
+      const int fi = fmt_index("PL");
+      if (fi < 0) return false;
+      pls_.resize((size_t)nv * 3);
+      for (int32_t i = 0; i < nv; ++i) {
+        const char* p = sample_field(sm_icols[i], fi);
+        for (int j = 0; j < 3; ++j) {
+          char* e;
+          long v = (*p == '.') ? 255 : strtol(p, &e, 10);  // a missing value carries no information either way
+          if (*p == '.') e = const_cast<char*>(p) + 1;
+          pls_[(size_t)i * 3 + j] = (uint32_t)(v < 0 ? 0 : v);
+          p = (*e == ',') ? e + 1 : e;
+        }
+      }
+      acs.assign(2, 0.5);
+      double gp[3];
+      for (int it = 0; it < 10; ++it) {
+        double newacs[2] = {0, 0};
+        an = 0;
+        for (int32_t i = 0; i < nv; ++i) {
+          double sumgp = 0;
+          for (int j = 0, l = 0; j < 2; ++j)
+            for (int k = 0; k <= j; ++k, ++l) {
+              const uint32_t pl = pls_[(size_t)i * 3 + l];
+              sumgp += (gp[l] = (j == k ? 1 : 2) * acs[j] * acs[k] * pow(0.1, (pl > 255 ? 255 : pl) * 0.1));
+            }
+          for (int j = 0, l = 0; j < 2; ++j)
+            for (int k = 0; k <= j; ++k, ++l) {
+              gp[l] /= sumgp;
+              newacs[j] += gp[l];
+              newacs[k] += gp[l];
+            }
+          an += 2;
+          if (it + 1 == 10)
+            for (int l = 0; l < 3; ++l) out[i * 3 + l] = (float)gp[l];
+        }
+        for (int j = 0; j < 2; ++j) acs[j] = newacs[j] / an;
+      }
+      for (int j = 0; j < 2; ++j) acs[j] *= an;
+      return true;
+    }
     const int fi = fmt_index(field);
     if (fi < 0) return false;
     float gpSums[3] = {1.0f / 4.0f, 2.0f / 4.0f, 1.0f / 4.0f};  // :462-468 (nalleles = 2)
@@ -416,6 +459,7 @@ class VcfReader {
   }
   LineReader lr_;
   std::vector<int32_t> gts_;
+  std::vector<uint32_t> pls_;
 };
 
 // ---- droplet store flattened to CSR ----

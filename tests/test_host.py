@@ -361,3 +361,46 @@ def test_cli_csr_construction_bit_exact(built, tmp_path, case):
     if case == "plain":
         ranks = {b: k for k, b in enumerate(sorted(d["barcodes"]))}
         assert np.array_equal(load("row_int_id.i32", "<i4"), [ranks[b] for b in bcs])
+
+
+def test_cli_field_pl_posteriors(built, tmp_path):
+    """--field PL: genotype posteriors from Phred-scaled likelihoods by ten EM iterations on the allele frequency
+    (BCFFilteredReader::parse_likelihoods, bcf_filtered_reader.cpp:289-365), checked against a Python restatement of
+    those lines through --gpu-dump-inputs (no GPU).  Parity unpinned: the reference's reader is htslib-bound."""
+    from cramore_b200.synth import make_dataset, write_plp
+    d = make_dataset("C1", nbcs=20, nsnps=60, rbar=40, nv=5, seed=9, with_barcodes=True)
+    pre = str(tmp_path / "in")
+    write_plp(d, pre)
+    rng = np.random.default_rng(4)
+    geno = np.asarray(d["geno"])
+    pls = np.zeros((d["nsnps"], d["nv"], 3), np.int64)
+    with open(pre + ".vcf", "w") as f:
+        f.write("##fileformat=VCFv4.2\n##contig=<ID=1>\n")
+        f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(d["sample_ids"]) + "\n")
+        for s in range(d["nsnps"]):
+            cols = []
+            for j in range(d["nv"]):
+                pl = rng.integers(5, 300, 3)  # above 255 is capped (PhredHelper.h:40)
+                pl[geno[s, j]] = 0
+                pls[s, j] = pl
+                cols.append("%s:%d,%d,%d" % (["0/0", "0/1", "1/1"][geno[s, j]], *pl))
+            f.write("1\t%d\t.\tA\tG\t.\tPASS\t.\tGT:PL\t%s\n" % (1000 + 10 * s, "\t".join(cols)))
+    r = subprocess.run([CRAMORE, "demuxlet", "--plp", pre, "--vcf", pre + ".vcf", "--field", "PL", "--out",
+                        str(tmp_path / "o"), "--gpu-dump-inputs", str(tmp_path / "dump")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    gp = np.fromfile(str(tmp_path / "dump.gp.f32"), np.float32).reshape(d["nsnps"], d["nv"], 3)
+    has = np.fromfile(str(tmp_path / "dump.has_gp.u8"), np.uint8)
+    w = np.array([1.0, 2.0, 1.0])
+    for s in range(d["nsnps"]):
+        if not has[s]:
+            continue  # dropped by --min-mac 1
+        acs = np.array([0.5, 0.5])
+        prob = np.power(0.1, np.minimum(pls[s], 255) * 0.1)
+        for it in range(10):
+            pri = np.array([acs[0] * acs[0], acs[1] * acs[0], acs[1] * acs[1]]) * w
+            g = pri * prob
+            g /= g.sum(axis=1, keepdims=True)
+            new = np.array([(2 * g[:, 0] + g[:, 1]).sum(), (g[:, 1] + 2 * g[:, 2]).sum()])
+            acs = new / (2 * d["nv"])
+        np.testing.assert_allclose(gp[s], g.astype(np.float32), rtol=2e-6)
+    assert has.sum() > 30
