@@ -7,6 +7,8 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -354,11 +356,75 @@ int ccu_demux_download(ccu_handle* h, ccu_demux_result* out) {
   return 0;
 }
 
+// Device scratch one droplet range needs (the per-entry tiles and single-read likelihood rows dominate).
+static double demux_scratch_bytes(const ccu_handle* h, int64_t ncell, int64_t nnz, int64_t nreads) {
+  const ccu::ScorePlan plan = ccu::make_score_plan(h->nv, h->nA, h->alpha.data());
+  const double per_entry = (double)h->nA * ccu::kTileStride * 8 + (double)h->nvp * 8 + 8 + 4 + 1 + 32 + 4 + 8;
+  const double per_cell = (double)h->nv * 8 + (double)h->nvp * 12 + 16 + sizeof(ccu_demux_result) +
+                          (double)plan.items_per_cell * ccu::kScoreWarps * sizeof(ccu::ItemPartial);
+  return per_entry * (double)nnz + per_cell * (double)ncell + 2.0 * (double)nreads;
+}
+
 int ccu_demux_score(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx,
                     const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq, ccu_demux_result* out) {
-  if (int rc = ccu_demux_upload(h, nbcs, cell_ptr, snp_idx, read_ptr, al, bq)) return rc;
-  if (int rc = ccu_demux_run(h)) return rc;
-  return ccu_demux_download(h, out);
+  if (!h) return 1;
+  if (!h->configured) return fail(h, "ccu_demux_score: call ccu_demux_configure first");
+  if (nbcs < 0 || !cell_ptr) return fail(h, "ccu_demux_score: bad arguments");
+  // Droplets are independent: when the scratch of the whole store does not fit into the device memory that is
+  // free right now, the store is scored in contiguous droplet ranges that do (CCU_DEMUX_MAX_SCRATCH_MB caps the
+  // budget, for tests).
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  size_t free_b = 0, total_b = 0;
+  CCU_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
+  const size_t held = h->d_tiles.cap + h->d_fmat.cap + h->d_vaff.cap + h->d_vent.cap + h->d_partials.cap;  // reusable
+  double budget = 0.85 * ((double)free_b + (double)held);
+  if (const char* cap = getenv("CCU_DEMUX_MAX_SCRATCH_MB")) budget = std::min(budget, atof(cap) * 1048576.0);
+  const int64_t nnz = cell_ptr[nbcs] - cell_ptr[0];
+  const int64_t nreads = (nnz > 0 && read_ptr) ? read_ptr[nnz] - read_ptr[0] : 0;
+  if (nbcs == 0 || demux_scratch_bytes(h, nbcs, nnz, nreads) <= budget) {
+    if (int rc = ccu_demux_upload(h, nbcs, cell_ptr, snp_idx, read_ptr, al, bq)) return rc;
+    if (int rc = ccu_demux_run(h)) return rc;
+    return ccu_demux_download(h, out);
+  }
+  if (cell_ptr[0] != 0 || (nnz > 0 && (!snp_idx || !read_ptr || read_ptr[0] != 0)))
+    return fail(h, "ccu_demux_score: bad CSR arrays");
+  ccu_timings sum = {};
+  std::vector<int64_t> cp, rp;
+  int64_t b = 0, nbatch = 0;
+  while (b < nbcs) {
+    int64_t e = b + 1;  // at least one droplet per range; grow while the range still fits
+    while (e < nbcs && demux_scratch_bytes(h, e + 1 - b, cell_ptr[e + 1] - cell_ptr[b],
+                                           read_ptr[cell_ptr[e + 1]] - read_ptr[cell_ptr[b]]) <= budget) {
+      // grow geometrically, then settle with the linear test above
+      const int64_t step = std::max<int64_t>(1, (e - b) / 2);
+      const int64_t e2 = std::min(nbcs, e + step);
+      if (demux_scratch_bytes(h, e2 - b, cell_ptr[e2] - cell_ptr[b], read_ptr[cell_ptr[e2]] - read_ptr[cell_ptr[b]]) <= budget) e = e2;
+      else ++e;
+    }
+    const int64_t e0 = cell_ptr[b], e1 = cell_ptr[e], r0 = read_ptr[e0];
+    cp.assign(cell_ptr + b, cell_ptr + e + 1);
+    for (auto& x : cp) x -= e0;
+    rp.assign(read_ptr + e0, read_ptr + e1 + 1);
+    for (auto& x : rp) x -= r0;
+    if (int rc = ccu_demux_upload(h, e - b, cp.data(), snp_idx + e0, rp.data(), al + r0, bq + r0)) return rc;
+    if (int rc = ccu_demux_run(h)) return rc;
+    if (int rc = ccu_demux_download(h, out + b)) return rc;
+    sum.ms_tile += h->tm.ms_tile;
+    sum.ms_singlet += h->tm.ms_singlet;
+    sum.ms_score += h->tm.ms_score;
+    sum.ms_finalize += h->tm.ms_finalize;
+    sum.ms_run += h->tm.ms_run;
+    sum.ms_h2d += h->tm.ms_h2d;
+    sum.ms_d2h += h->tm.ms_d2h;
+    sum.launches += h->tm.launches;
+    sum.score_items += h->tm.score_items;
+    sum.score_ctas = h->tm.score_ctas;
+    b = e;
+    ++nbatch;
+  }
+  sum.ms_genotypes = h->tm.ms_genotypes;
+  h->tm = sum;
+  return 0;
 }
 
 int ccu_demux_get_tiles(ccu_handle* h, double* tiles) {

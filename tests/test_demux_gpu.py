@@ -155,3 +155,16 @@ def test_full_size_properties(engine):
     truth = np.stack([np.minimum(d["s1"], d["s2"]), np.maximum(d["s1"], d["s2"])], 1)[dbl]
     got = np.stack([np.minimum(calls["jBest"], calls["kBest"]), np.maximum(calls["jBest"], calls["kBest"])], 1)[dbl]
     assert (truth == got).all(1).mean() > 0.95
+
+
+def test_scoring_in_memory_bounded_ranges(engine, monkeypatch):
+    """ccu_demux_score splits the droplet store into ranges whose scratch fits the device memory budget
+    (CCU_DEMUX_MAX_SCRATCH_MB forces it here): results are bitwise those of the single pass."""
+    d = make_dataset("C2", nbcs=300, nsnps=20000)
+    whole = engine_run(engine, d)
+    launches_whole = engine.timings()["launches"]
+    monkeypatch.setenv("CCU_DEMUX_MAX_SCRATCH_MB", "8")  # ~1.4 KB per entry at 64 samples x 11 alphas
+    parts = engine_run(engine, d)
+    assert engine.timings()["launches"] > 3 * launches_whole  # several ranges were run
+    monkeypatch.delenv("CCU_DEMUX_MAX_SCRATCH_MB")
+    assert np.array_equal(whole, parts)
