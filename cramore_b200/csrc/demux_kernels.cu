@@ -1163,9 +1163,168 @@ static cudaError_t launch_score_t(const DemuxDev& d, const ScorePlan& plan, int 
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// K2 for small pools (nv <= 16 and nv*nv*(nA-1) <= 512 products per droplet -- the classic demuxlet run: 8 or 16
+// pooled samples, 1..4 doublet alphas).  The tiled kernel above pads the samples to 32 x 32 per alpha chunk and
+// pays its per-item machinery (ring, epilogue of 20 products per thread) for a handful of live products: at 8
+// samples and alpha {0, 0.5} it ran at 0.3 % of its own arithmetic.  Here a warp owns a droplet and a lane owns
+// the products p = lane, lane + 32, ... of the list p = (j*nv + k)*(nA-1) + (n-1), i.e. the reference's scan
+// order.  Per entry the lane needs f_j, f_k (single-read entries: one 32-double row of `fmat`, staged in shared
+// memory) or the genotype rows and the alpha block of the tile (entries with >= 2 informative reads, read
+// straight from global memory); same running products, same epilogue rules and the same partial record
+// (one per droplet) as the tiled kernel, so K3 is shared.
+// ------------------------------------------------------------------------------------------
+constexpr int kSmallWarps = 8;
+
+template <int PPL>
+__global__ void __launch_bounds__(kSmallWarps * 32)
+    demux_score_small_kernel(DemuxDev d, uint32_t half_mask, double2* __restrict__ dbg, int64_t dbg_c0, int64_t dbg_c1) {
+  __shared__ double s_f[kSmallWarps][2][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * kSmallWarps + warp;
+  if (c >= d.nbcs) return;
+  const int nv = d.nv, nd = d.nA - 1, P = nv * nv * nd;
+  constexpr uint32_t kFull = 0xffffffffu;
+
+  int pj[PPL], pk[PPL], pn[PPL];  // sample j, sample k, alpha index n >= 1 of each product (pn = 0: no product)
+  double acc[PPL];
+  int aex[PPL];
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    const int p = lane + 32 * i;
+    const bool ok = p < P;
+    const int jk = ok ? p / nd : 0;
+    pj[i] = jk / nv;
+    pk[i] = jk - pj[i] * nv;
+    pn[i] = ok ? 1 + (p - jk * nd) : 0;
+    acc[i] = 1.0;
+    aex[i] = 0;
+  }
+
+  const int64_t base = d.cell_ptr[c];
+  const int ng = d.vcnt_g[c], na = d.vcnt_a[c];
+  const int64_t grow = (int64_t)d.nvp * 3;
+  // ---- entries with >= 2 informative reads: sum_l g_j[l] * (sum_m g_k[m] * pG[n][l][m])
+  for (int i = 0; i < ng; ++i) {
+    const int64_t e = d.vent[base + i];
+    const double* g = d.G + (int64_t)d.vsnp[base + i] * grow;
+    const double* tile = d.tiles + e * d.nA * kTileStride;
+#pragma unroll
+    for (int q = 0; q < PPL; ++q)
+      if (pn[q] > 0) {
+        const double* gj = g + 3 * pj[q];
+        const double* gk = g + 3 * pk[q];
+        const double* pg = tile + pn[q] * kTileStride;
+        const double k0 = gk[0], k1 = gk[1], k2 = gk[2];
+        const double t0 = fma(k2, pg[2], fma(k1, pg[1], k0 * pg[0]));
+        const double t1 = fma(k2, pg[5], fma(k1, pg[4], k0 * pg[3]));
+        const double t2 = fma(k2, pg[8], fma(k1, pg[7], k0 * pg[6]));
+        acc[q] *= fma(gj[2], t2, fma(gj[1], t1, gj[0] * t0));
+      }
+    if ((i & 15) == 15) {  // a general factor is >= ~2^-34: 16 of them cannot underflow
+#pragma unroll
+      for (int q = 0; q < PPL; ++q) renorm(acc[q], aex[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < PPL; ++q) renorm(acc[q], aex[q]);
+  // ---- single-read entries: f_j + alpha_n (f_k - f_j); the s_j s_k factors come in at the end
+  const double* frow = d.fmat + base * d.nvp + lane;  // nvp == 32 here: one 32-sample tile, [entry][32]
+  double fnext = (na > 0) ? frow[0] : 0.0;
+  for (int i = 0; i < na; ++i) {
+    double* S = s_f[warp][i & 1];
+    S[lane] = fnext;
+    __syncwarp();
+    if (i + 1 < na) fnext = frow[(int64_t)(i + 1) * 32];
+#pragma unroll
+    for (int q = 0; q < PPL; ++q)
+      if (pn[q] > 0) {
+        const double fj = S[pj[q]], fk = S[pk[q]];
+        acc[q] *= fma(d.alpha_c[pn[q]], fk - fj, fj);
+      }
+    if ((i & 15) == 15) {  // a single-read factor is >= err/3 >= ~2^-34 as well
+#pragma unroll
+      for (int q = 0; q < PPL; ++q) renorm(acc[q], aex[q]);
+    }
+  }
+
+  // ---- epilogue: the rules of the tiled kernel's item epilogue, for this droplet's whole product list
+  const bool want_dbg = (dbg != nullptr) && c >= dbg_c0 && c < dbg_c1;
+  double la = 0.0;
+  int le = kLseEmpty;
+  Cand b1 = cand_empty(), b2 = cand_empty();
+#pragma unroll
+  for (int q = 0; q < PPL; ++q)
+    if (pn[q] > 0) {
+      const int j = pj[q], k = pk[q], n = pn[q];
+      double m = acc[q] * (d.pm[c * d.nvp + j] * d.pm[c * d.nvp + k]);
+      int e = aex[q] + d.pe[c * d.nvp + j] + d.pe[c * d.nvp + k];
+      renorm(m, e);
+      if (want_dbg) dbg[(((c - dbg_c0) * nv + j) * nv + k) * d.nA + n] = make_double2(m, (double)e);
+      if (j != k && m > 0.0) {
+        // alpha == 0.5 is counted once, k < j, with twice the prior (:812-817)
+        const double w = ((half_mask >> n) & 1u) ? ((k < j) ? 2.0 : 0.0) : 1.0;
+        lse_add(la, le, w * m, e);
+        Cand x;
+        x.m = m;
+        x.e = e;
+        x.pos = (j * nv + k) * d.nA + n;
+        cand_insert(b1, b2, x);
+      }
+    }
+#pragma unroll
+  for (int dd = 16; dd >= 1; dd >>= 1) {
+    const double oa = __shfl_xor_sync(kFull, la, dd);
+    const int oe = __shfl_xor_sync(kFull, le, dd);
+    lse_add(la, le, oa, oe);
+    const Cand o1 = cand_shfl_xor(b1, dd), o2 = cand_shfl_xor(b2, dd);
+    cand_insert(b1, b2, o1);
+    cand_insert(b1, b2, o2);
+  }
+  if (lane == 0) {
+    ItemPartial p;
+    p.lse_a = la;
+    p.lse_e = (la > 0.0) ? le : kLseEmpty;
+    p._pad = 0;
+    p.best = b1;
+    p.next = b2;
+    d.partials[c] = p;
+  }
+}
+
+// products per droplet the small-pool kernel takes (0: use the tiled kernel)
+static int small_pool_ppl(const DemuxDev& d) {
+  if (d.nv > 16 || d.nvp != 32) return 0;
+  const int P = d.nv * d.nv * (d.nA - 1);
+  if (P <= 0 || P > 512) return 0;  // 16 products per lane; beyond that the register file is the limit
+  int ppl = 2;
+  while (ppl * 32 < P) ppl *= 2;
+  return ppl;
+}
+
+int score_partials_per_cell(const DemuxDev& d, const ScorePlan& plan) {
+  return small_pool_ppl(d) ? 1 : plan.items_per_cell * kScoreWarps;
+}
+
 cudaError_t launch_score(const DemuxDev& d, const ScorePlan& plan, int num_sms, double2* llk_dbg,
                          int64_t dbg_c0, int64_t dbg_c1, int* grid_out, cudaStream_t st) {
   if (d.nbcs == 0) return cudaSuccess;
+  if (const int ppl = small_pool_ppl(d)) {
+    uint32_t half_mask = 0;
+    for (int n = 0; n < d.nA && n < 32; ++n)
+      if (plan.is_half[n]) half_mask |= 1u << n;
+    const unsigned blocks = (unsigned)((d.nbcs + kSmallWarps - 1) / kSmallWarps);
+    if (grid_out) *grid_out = (int)blocks;
+#define CCU_SMALL(N) demux_score_small_kernel<N><<<blocks, kSmallWarps * 32, 0, st>>>(d, half_mask, llk_dbg, dbg_c0, dbg_c1)
+    switch (ppl) {
+      case 2: CCU_SMALL(2); break;
+      case 4: CCU_SMALL(4); break;
+      case 8: CCU_SMALL(8); break;
+      default: CCU_SMALL(16); break;
+    }
+#undef CCU_SMALL
+    return cudaGetLastError();
+  }
   switch (plan.ac) {
     case 10: return launch_score_t<10, 1>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
     case 5: return launch_score_t<5, 2>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
@@ -1195,7 +1354,7 @@ __device__ __forceinline__ void sng_insert(SngCand& b1, SngCand& b2, const SngCa
 }
 
 __global__ void __launch_bounds__(256)
-    demux_finalize_kernel(DemuxDev d, int ipc, double log_single_prior, double log_doublet_prior1) {
+    demux_finalize_kernel(DemuxDev d, int nrec, double log_single_prior, double log_doublet_prior1) {
   const int lane = threadIdx.x & 31;
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= d.nbcs) return;
@@ -1226,8 +1385,8 @@ __global__ void __launch_bounds__(256)
   double la = 0.0;
   int le = kLseEmpty;
   Cand b1 = cand_empty(), b2 = cand_empty();
-  for (int i = lane; i < ipc * kScoreWarps; i += 32) {
-    const ItemPartial p = d.partials[c * ipc * kScoreWarps + i];
+  for (int i = lane; i < nrec; i += 32) {  // nrec partial records per droplet
+    const ItemPartial p = d.partials[c * (int64_t)nrec + i];
     lse_add(la, le, p.lse_a, p.lse_e);
     cand_insert(b1, b2, p.best);
     cand_insert(b1, b2, p.next);
@@ -1310,7 +1469,7 @@ cudaError_t launch_finalize(const DemuxDev& d, const ScorePlan& plan, cudaStream
   const double lsp = log((1.0 - d.doublet_prior) / nv);
   const double ldp1 = log(d.doublet_prior / nv / (nv - 1.) / (nA - 1.));
   int64_t blocks = (d.nbcs * 32 + 255) / 256;
-  demux_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(d, plan.items_per_cell, lsp, ldp1);
+  demux_finalize_kernel<<<(unsigned)blocks, 256, 0, st>>>(d, score_partials_per_cell(d, plan), lsp, ldp1);
   return cudaGetLastError();
 }
 
