@@ -1164,24 +1164,26 @@ static cudaError_t launch_score_t(const DemuxDev& d, const ScorePlan& plan, int 
 }
 
 // ------------------------------------------------------------------------------------------
-// K2 for small pools (nv <= 16 and nv*nv*(nA-1) <= 512 products per droplet -- the classic demuxlet run: 8 or 16
-// pooled samples, 1..4 doublet alphas).  The tiled kernel above pads the samples to 32 x 32 per alpha chunk and
+// K2 for small pools (nv <= 32 and nv*nv*(nA-1) <= 1024 products per droplet -- the classic demuxlet run: 8 or 16
+// pooled samples, a few doublet alphas).  The tiled kernel above pads the samples to 32 x 32 per alpha chunk and
 // pays its per-item machinery (ring, epilogue of 20 products per thread) for a handful of live products: at 8
-// samples and alpha {0, 0.5} it ran at 0.3 % of its own arithmetic.  Here a warp owns a droplet and a lane owns
-// the products p = lane, lane + 32, ... of the list p = (j*nv + k)*(nA-1) + (n-1), i.e. the reference's scan
-// order.  Per entry the lane needs f_j, f_k (single-read entries: one 32-double row of `fmat`, staged in shared
+// samples and alpha {0, 0.5} it ran at 0.3 % of its own arithmetic.  Here wpc warps (1, 2, 4 or 8) own a droplet
+// and a lane owns every (32*wpc)-th product of the list p = (j*nv + k)*(nA-1) + (n-1), i.e. the reference's
+// scan order.  Per entry the lane needs f_j, f_k (single-read entries: one 32-double row of `fmat`, staged in shared
 // memory) or the genotype rows and the alpha block of the tile (entries with >= 2 informative reads, read
 // straight from global memory); same running products, same epilogue rules and the same partial record
-// (one per droplet) as the tiled kernel, so K3 is shared.
+// (one per warp, wpc per droplet) as the tiled kernel, so K3 is shared.
 // ------------------------------------------------------------------------------------------
 constexpr int kSmallWarps = 8;
 
 template <int PPL>
 __global__ void __launch_bounds__(kSmallWarps * 32)
-    demux_score_small_kernel(DemuxDev d, uint32_t half_mask, double2* __restrict__ dbg, int64_t dbg_c0, int64_t dbg_c1) {
+    demux_score_small_kernel(DemuxDev d, int wpc, uint32_t half_mask, double2* __restrict__ dbg, int64_t dbg_c0,
+                             int64_t dbg_c1) {
   __shared__ double s_f[kSmallWarps][2][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t c = (int64_t)blockIdx.x * kSmallWarps + warp;
+  const int wsub = warp % wpc;  // this warp's share of the droplet's products
+  const int64_t c = (int64_t)blockIdx.x * (kSmallWarps / wpc) + warp / wpc;
   if (c >= d.nbcs) return;
   const int nv = d.nv, nd = d.nA - 1, P = nv * nv * nd;
   constexpr uint32_t kFull = 0xffffffffu;
@@ -1191,7 +1193,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
   int aex[PPL];
 #pragma unroll
   for (int i = 0; i < PPL; ++i) {
-    const int p = lane + 32 * i;
+    const int p = wsub * 32 + lane + 32 * wpc * i;
     const bool ok = p < P;
     const int jk = ok ? p / nd : 0;
     pj[i] = jk / nv;
@@ -1288,34 +1290,42 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
     p._pad = 0;
     p.best = b1;
     p.next = b2;
-    d.partials[c] = p;
+    d.partials[c * wpc + wsub] = p;
   }
 }
 
 // products per droplet the small-pool kernel takes (0: use the tiled kernel)
-static int small_pool_ppl(const DemuxDev& d) {
-  if (d.nv > 16 || d.nvp != 32) return 0;
+static int small_pool_ppl(const DemuxDev& d, int* wpc_out) {
+  if (d.nvp != 32) return 0;
   const int P = d.nv * d.nv * (d.nA - 1);
-  if (P <= 0 || P > 512) return 0;  // 16 products per lane; beyond that the register file is the limit
+  if (P <= 0 || P > 1024) return 0;  // beyond that the tiled kernel wins (it needs 1.8 instructions per product and
+                                     // SNP where this one needs ~8)
+  int wpc = 1;
+  while (wpc < kSmallWarps && P > 256 * wpc) wpc *= 2;  // at most 8 products per lane
   int ppl = 2;
-  while (ppl * 32 < P) ppl *= 2;
+  while (ppl * 32 * wpc < P) ppl *= 2;
+  if (wpc_out) *wpc_out = wpc;
   return ppl;
 }
 
 int score_partials_per_cell(const DemuxDev& d, const ScorePlan& plan) {
-  return small_pool_ppl(d) ? 1 : plan.items_per_cell * kScoreWarps;
+  int wpc = 1;
+  return small_pool_ppl(d, &wpc) ? wpc : plan.items_per_cell * kScoreWarps;
 }
 
 cudaError_t launch_score(const DemuxDev& d, const ScorePlan& plan, int num_sms, double2* llk_dbg,
                          int64_t dbg_c0, int64_t dbg_c1, int* grid_out, cudaStream_t st) {
   if (d.nbcs == 0) return cudaSuccess;
-  if (const int ppl = small_pool_ppl(d)) {
+  int wpc = 1;
+  if (const int ppl = small_pool_ppl(d, &wpc)) {
     uint32_t half_mask = 0;
     for (int n = 0; n < d.nA && n < 32; ++n)
       if (plan.is_half[n]) half_mask |= 1u << n;
-    const unsigned blocks = (unsigned)((d.nbcs + kSmallWarps - 1) / kSmallWarps);
+    const int cpb = kSmallWarps / wpc;  // droplets per CTA
+    const unsigned blocks = (unsigned)((d.nbcs + cpb - 1) / cpb);
     if (grid_out) *grid_out = (int)blocks;
-#define CCU_SMALL(N) demux_score_small_kernel<N><<<blocks, kSmallWarps * 32, 0, st>>>(d, half_mask, llk_dbg, dbg_c0, dbg_c1)
+#define CCU_SMALL(N) \
+  demux_score_small_kernel<N><<<blocks, kSmallWarps * 32, 0, st>>>(d, wpc, half_mask, llk_dbg, dbg_c0, dbg_c1)
     switch (ppl) {
       case 2: CCU_SMALL(2); break;
       case 4: CCU_SMALL(4); break;
