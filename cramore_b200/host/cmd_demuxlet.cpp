@@ -1,11 +1,13 @@
 // cmd_demuxlet.cpp -- `cramore demuxlet` on the B200 engine: the command-line surface and output files of
 // cmdCramDemuxlet (cmd_cram_demuxlet.cpp:6-1060) for the --plp path.  Ingestion is host C++ (host_io.h);
 // everything between "ingestion finished" (:425) and "row printed" (:993) runs in libcramore_cuda.so.
-// The --sam path needs htslib's BAM/CRAM decoder, which this build does not link: it is rejected with an error.
+// --sam reads BAM through the built-in reader of bam_io.h (SAM text and CRAM need htslib, which this build does not
+// link: they are rejected with an error).
 #include <thread>
 
 #include "cli_params.h"
 #include "cramore_cuda.h"
+#include "bam_io.h"
 #include "host_io.h"
 
 using namespace hostio;
@@ -107,13 +109,10 @@ int cmdDemuxlet(int argc, char** argv) {
     gridAlpha.push_back(0.5);
   }
   const int32_t nAlpha = (int32_t)gridAlpha.size();
-  if (!samFile.empty()) {
-    if (!plpPrefix.empty()) fatal("with --plp option, neither --sam option cannot be used");
-    fatal("--sam needs htslib's BAM/CRAM reader, which this build does not include; run `cramore dsc-pileup` "
-          "once and pass its output with --plp");
-  }
+  if (!samFile.empty() && !plpPrefix.empty()) fatal("with --plp option, neither --sam option cannot be used");
   if (outPrefix.empty()) fatal("Missing required option(s) : --out");
-  if (loadPrefix.empty() && (plpPrefix.empty() || vcfFile.empty())) fatal("Missing required option(s) : --plp, --vcf, --out");
+  if (loadPrefix.empty() && ((plpPrefix.empty() && samFile.empty()) || vcfFile.empty()))
+    fatal("Missing required option(s) : --sam (or --plp), --vcf, --out");
 
   // what the engine and the .best writer need: filled by ingestion, or by the binary sidecar cache
   std::vector<int64_t> cell_ptr, read_ptr;
@@ -170,10 +169,42 @@ int cmdDemuxlet(int argc, char** argv) {
       notice("Loaded %zu valid barcodes from %s", flt.valid_bcs.size(), groupList.c_str());
     }
 
-    // ---- .var.gz x VCF join, sc_drop_seq.cpp:108-116 and :226-330 ----
     if (!vr.read()) fatal("Cannot read any single variant from %s", vcfFile.c_str());
     std::vector<float> tmp_gp(nv * 3);
     DropletStore st;
+    if (!samFile.empty()) {
+      // ---- BAM x VCF join, cmd_cram_demuxlet.cpp:126-395: every variant passing the filter becomes a SNP with
+      // genotypes (the reference adds them as the reads reach them; a SNP no read reaches changes nothing) ----
+      std::vector<SamVariant> vars;
+      while (!vr.eof) {
+        if (!vr.parse_posteriors(field.c_str(), 0, tmp_gp.data()))
+          fatal("Cannot parse posterior probability at %s:%d", vr.chroms[vr.cur.rid].c_str(), vr.cur.pos1);
+        gp_f32.insert(gp_f32.end(), tmp_gp.begin(), tmp_gp.end());
+        double err = genoErrorOffset;  // :256-262
+        if (genoErrorCoeffR2 > 0) {
+          float r2;
+          if (!vr.info_float(r2Info.c_str(), &r2))
+            fatal("Cannot extract %s (1 float value) from INFO field at %s:%d. Cannot use --geno-error-coeff", r2Info.c_str(),
+                  vr.chroms[vr.cur.rid].c_str(), vr.cur.pos1);
+          err += (1 - genoErrorOffset) * (1 - r2) * genoErrorCoeffR2;
+        }
+        snp_err.push_back(err);
+        has_gp.push_back(1);
+        vars.push_back({vr.cur.rid, vr.cur.pos1, vr.cur.ref[0], vr.cur.alt[0]});
+        vr.read();
+      }
+      SamOptions so;
+      so.tagGroup = tagGroup;
+      so.tagUMI = tagUMI;
+      so.capBQ = capBQ;
+      so.minBQ = minBQ;
+      so.minMQ = minMQ;
+      so.minTD = minTD;
+      so.exclFlag = (uint32_t)exclFlag;
+      so.valid_bcs = flt.valid_bcs;
+      load_sam(samFile, so, vr.chroms, vars, st);
+    } else
+    // ---- .var.gz x VCF join, sc_drop_seq.cpp:108-116 and :226-330 ----
     load_plp(plpPrefix, flt, st, [&](int32_t /*idx*/, const char* chr, const SnpInfo& s) {
       bool found = false, passed = false;
       while (!(found || passed)) {

@@ -214,3 +214,96 @@ def write_vcf(d, path, chrom="1", with_r2=False):
             f.write("%s\t%d\t.\tA\tG\t.\tPASS\t%s\tGT:GP\t" % (chrom, 1000 + 10 * s, info))
             f.write("\t".join(cols[g] for g in geno[s]))
             f.write("\n")
+
+
+# ---------------------------------------------------------------------------------------------
+# BAM writer (SAM spec section 4: BGZF blocks around little-endian records) for the --sam tests
+# ---------------------------------------------------------------------------------------------
+_CIGAR_OPS = "MIDNSHP=X"
+_NT16 = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
+
+
+def _bgzf_block(data):
+    import struct
+    import zlib
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = co.compress(data) + co.flush()
+    bsize = len(comp) + 25  # total block size - 1
+    return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize) + comp +
+            struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
+
+
+def encode_bam_record(tid, pos, mapq, flag, cigar, seq, qual, qname="r", tags=()):
+    """One alignment record.  cigar: [(op char, length)]; qual: raw Phred values; tags: [(two-letter tag, str)]."""
+    import struct
+    name = qname.encode() + b"\0"
+    cig = b"".join(struct.pack("<I", (n << 4) | _CIGAR_OPS.index(op)) for op, n in cigar)
+    packed = bytearray((len(seq) + 1) // 2)
+    for i, c in enumerate(seq):
+        packed[i >> 1] |= _NT16[c] << (4 if i % 2 == 0 else 0)
+    aux = b"".join(t.encode() + b"Z" + v.encode() + b"\0" for t, v in tags)
+    body = struct.pack("<iiBBHHHiiii", tid, pos, len(name), mapq, 4680, len(cigar), flag, len(seq), -1, -1, 0)
+    body += name + cig + bytes(packed) + bytes(bytearray(qual)) + aux
+    return struct.pack("<i", len(body)) + body
+
+
+def write_bam_records(path, refs, records):
+    """refs: [(name, length)]; records: encoded alignment records in coordinate order."""
+    import struct
+    text = b"@HD\tVN:1.6\tSO:coordinate\n" + b"".join(b"@SQ\tSN:%s\tLN:%d\n" % (n.encode(), ln) for n, ln in refs)
+    hdr = b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs))
+    for n, ln in refs:
+        hdr += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", ln)
+    blob = hdr + b"".join(records)
+    with open(path, "wb") as f:
+        for i in range(0, len(blob), 60000):
+            f.write(_bgzf_block(blob[i:i + 60000]))
+        f.write(_bgzf_block(b""))  # BGZF EOF marker
+
+
+def write_bam(d, path, chrom="1", seed=0, duplicate_every=0):
+    """The reads of the synthetic droplet store as a coordinate-sorted BAM with CB/UB tags: one short alignment per
+    read, covering only its own SNP (SNPs of write_vcf / write_plp sit 10 bp apart at 1000 + 10*s, REF A, ALT G), with
+    a CIGAR drawn from a few shapes (soft clip, insertion, deletion, reference skip) so that the read coordinate of
+    the SNP base differs from its reference offset.  duplicate_every > 0 appends, after every such read, a second
+    alignment with the same droplet, SNP and UMI but another base: the reference keeps the first one."""
+    rng = np.random.default_rng(seed)
+    cp, rp = np.asarray(d["cell_ptr"], np.int64), np.asarray(d["read_ptr"], np.int64)
+    si, al, bq = np.asarray(d["snp_idx"]), np.asarray(d["al"]), np.asarray(d["bq"])
+    bcs = d["barcodes"]
+    base_of = {0: "A", 1: "G", 2: "C"}
+    # (cigar, reference offset of the first aligned base relative to the SNP, read index of the SNP base)
+    shapes = [
+        ([("M", 5)], -2, 2),
+        ([("S", 2), ("M", 5)], -3, 5),
+        ([("M", 2), ("I", 1), ("M", 3)], -3, 4),
+        ([("M", 2), ("D", 2), ("M", 3)], -5, 3),
+        ([("M", 1), ("N", 3), ("M", 4), ("S", 1)], -4, 1),
+        ([("H", 3), ("M", 4)], 0, 0),
+    ]
+    recs = []
+    n = 0
+    for c in range(len(cp) - 1):
+        for e in range(cp[c], cp[c + 1]):
+            for r in range(rp[e], rp[e + 1]):
+                cigar, off, ridx = shapes[int(rng.integers(len(shapes)))]
+                snp_pos0 = 1000 + 10 * int(si[e]) - 1
+                rlen = sum(k for op, k in cigar if op in "MIS=X")
+                seq = ["T"] * rlen
+                qual = [30] * rlen
+                seq[ridx] = base_of[int(al[r])]
+                qual[ridx] = int(bq[r])
+                umi = "%x" % n
+                recs.append((snp_pos0 + off, n, encode_bam_record(0, snp_pos0 + off, 60, 0, cigar, "".join(seq), qual,
+                                                                  "q%d" % n, (("CB", bcs[c]), ("UB", umi)))))
+                if duplicate_every and n % duplicate_every == 0:
+                    seq2 = list(seq)
+                    seq2[ridx] = "G" if seq[ridx] != "G" else "A"
+                    recs.append((snp_pos0 + off, n + 0.5, encode_bam_record(0, snp_pos0 + off, 60, 0, cigar, "".join(seq2),
+                                                                            qual, "d%d" % n, (("CB", bcs[c]), ("UB", umi)))))
+                n += 1
+    recs.sort(key=lambda t: (t[0], t[1]))
+    # reads the filter must drop: low mapping quality, duplicate flag, unmapped
+    junk = [encode_bam_record(0, 1000, 5, 0, [("M", 5)], "GGGGG", [30] * 5, "lowmq", (("CB", bcs[0]), ("UB", "zz1"))),
+            encode_bam_record(0, 1000, 60, 0x400, [("M", 5)], "GGGGG", [30] * 5, "dup", (("CB", bcs[0]), ("UB", "zz2")))]
+    write_bam_records(path, [(chrom, 1000 + 10 * d["nsnps"] + 100)], junk + [t[2] for t in recs])

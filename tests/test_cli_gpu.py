@@ -190,3 +190,27 @@ def test_cli_freemux2_files(built, tmp_path, name):
     assert len(lm) == len(rlm) and lm[0] == rlm[0]
     for a, b in zip(lm[1:], rlm[1:]):
         assert a == b or _numeric_row_match(a, b), (a, b)
+
+
+def test_cli_demuxlet_sam_input_matches_plp_input(built, tmp_path):
+    """`--sam` (BGZF/BAM read by cramore_b200/host/bam_io.h, joined to the VCF on the host) scores the same droplets
+    as `--plp` on the same reads.  NUM.SNPS / NUM.READS count the SNPs the VCF filter dropped on the --plp path only
+    (the reference keeps them in the pileup store, cmd_cram_demuxlet.cpp:337-455, but never loads them from a BAM)."""
+    from cramore_b200.synth import make_dataset, write_bam
+    d = make_dataset("C1", nbcs=60, nsnps=300, rbar=150, nv=6, seed=29, with_barcodes=True)
+    pre = str(tmp_path / "in")
+    write_plp(d, pre)
+    write_vcf(d, pre + ".vcf", with_r2=True)
+    write_bam(d, pre + ".bam", duplicate_every=7)
+    rows = {}
+    for mode, src in (("sam", ["--sam", pre + ".bam"]), ("plp", ["--plp", pre])):
+        out = str(tmp_path / mode)
+        r = subprocess.run([CRAMORE, "demuxlet"] + src + ["--vcf", pre + ".vcf", "--out", out, "--alpha", "0", "--alpha", "0.5"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        rows[mode] = open(out + ".best").read().splitlines()
+    assert rows["sam"][0] == rows["plp"][0] and len(rows["sam"]) == len(rows["plp"]) == 61
+    for a, b in zip(rows["sam"][1:], rows["plp"][1:]):
+        fa, fb = a.split("\t"), b.split("\t")
+        assert fa[:2] == fb[:2] and int(fa[2]) <= int(fb[2]) and int(fa[3]) <= int(fb[3])
+        assert _numeric_row_match("\t".join(fa[4:]), "\t".join(fb[4:])), (a, b)

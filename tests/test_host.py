@@ -404,3 +404,82 @@ def test_cli_field_pl_posteriors(built, tmp_path):
             acs = new / (2 * d["nv"])
         np.testing.assert_allclose(gp[s], g.astype(np.float32), rtol=2e-6)
     assert has.sum() > 30
+
+
+def test_cli_sam_path_matches_plp_path(built, tmp_path):
+    """--sam (built-in BAM reader, bam_io.h) against --plp on the same reads: the BAM holds one short alignment per
+    read of the synthetic store (CIGARs with soft/hard clips, an insertion, a deletion, a reference skip), duplicates
+    of (droplet, SNP, UMI) that must lose to the first read, and reads the filter must drop.  The flattened engine
+    inputs (--gpu-dump-inputs, no GPU) must agree entry by entry; the reference drops SNPs failing --min-mac on the
+    --sam path and keeps them without genotypes on the --plp path, which is accounted for."""
+    from cramore_b200.synth import make_dataset, write_bam, write_plp, write_vcf
+    d = make_dataset("C1", nbcs=40, nsnps=150, rbar=90, nv=5, seed=13, with_barcodes=True)
+    pre = str(tmp_path / "in")
+    write_plp(d, pre)
+    write_vcf(d, pre + ".vcf", with_r2=True)
+    write_bam(d, pre + ".bam", duplicate_every=5)
+    common = ["--vcf", pre + ".vcf", "--out", str(tmp_path / "o"), "--geno-error-coeff", "0.5"]
+    for mode, src in (("sam", ["--sam", pre + ".bam"]), ("plp", ["--plp", pre])):
+        r = subprocess.run([CRAMORE, "demuxlet"] + src + common + ["--gpu-dump-inputs", str(tmp_path / mode)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+
+    def load(mode, name, dt):
+        return np.fromfile(str(tmp_path / (mode + "." + name)), dtype=dt)
+
+    has = load("plp", "has_gp.u8", np.uint8).astype(bool)
+    assert has.sum() < len(has) and load("sam", "has_gp.u8", np.uint8).all()
+    remap = np.cumsum(has) - 1  # SNP id on the --sam path
+    assert (tmp_path / "sam.barcodes.txt").read_text() == (tmp_path / "plp.barcodes.txt").read_text()
+    assert np.array_equal(load("sam", "row_int_id.i32", np.int32), load("plp", "row_int_id.i32", np.int32))
+    nv = 5
+    gp_p = load("plp", "gp.f32", np.float32).reshape(-1, nv * 3)[has]
+    assert np.array_equal(load("sam", "gp.f32", np.float32).reshape(-1, nv * 3), gp_p)
+    assert np.array_equal(load("sam", "snp_err.f64", np.float64), load("plp", "snp_err.f64", np.float64)[has])
+    cps, cpp = load("sam", "cell_ptr.i64", np.int64), load("plp", "cell_ptr.i64", np.int64)
+    sis, sip = load("sam", "snp_idx.i32", np.int32), load("plp", "snp_idx.i32", np.int32)
+    rps, rpp = load("sam", "read_ptr.i64", np.int64), load("plp", "read_ptr.i64", np.int64)
+    als, alp = load("sam", "al.u8", np.uint8), load("plp", "al.u8", np.uint8)
+    bqs, bqp = load("sam", "bq.u8", np.uint8), load("plp", "bq.u8", np.uint8)
+    nent = 0
+    for c in range(len(cpp) - 1):
+        want = [(remap[sip[e]], sorted(zip(alp[rpp[e]:rpp[e + 1]], bqp[rpp[e]:rpp[e + 1]])))
+                for e in range(cpp[c], cpp[c + 1]) if has[sip[e]]]
+        got = [(sis[e], sorted(zip(als[rps[e]:rps[e + 1]], bqs[rps[e]:rps[e + 1]]))) for e in range(cps[c], cps[c + 1])]
+        assert got == want, c
+        nent += len(got)
+    assert nent > 2000
+
+
+def test_bam_base_extraction_follows_the_reference_cigar_walk(built, tmp_path):
+    """bam_get_base_and_qual_and_read_and_qual (hts_utils.cpp:279-358) through the CLI: hand-made alignments whose
+    SNP base sits behind clips / insertions / deletions, inside a deletion (no observation), or behind '=' / 'X'
+    operations, which that function ignores."""
+    from cramore_b200.synth import encode_bam_record, write_bam_records
+    pre = str(tmp_path / "x")
+    with open(pre + ".vcf", "w") as f:
+        f.write("##fileformat=VCFv4.2\n##contig=<ID=1>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\tS2\n")
+        for pos in (101, 121, 141, 161, 181, 201):
+            f.write("1\t%d\t.\tA\tG\t.\tPASS\t.\tGT:GP\t0/1:0.01,0.98,0.01\t0/0:0.98,0.01,0.01\n" % pos)
+    q = [30] * 12
+
+    def rec(pos0, cigar, seq, name, cb="AAAC-1", umi=None, qual=None):
+        return encode_bam_record(0, pos0, 60, 0, cigar, seq, (qual or q)[:len(seq)], name, (("CB", cb), ("UB", umi or name)))
+
+    records = [
+        rec(98, [("M", 6)], "TTGTTT", "u1"),                         # SNP 101 (0-based 100) = read index 2: G -> alt
+        rec(117, [("S", 3), ("M", 6)], "CCCTTTATT", "u2"),           # SNP 121: 3 clipped + offset 3 -> index 6: A -> ref
+        rec(138, [("M", 2), ("D", 3), ("M", 4)], "TTTTTT", "u3"),    # SNP 141 (140) lies in the deletion 140..142: no read
+        rec(158, [("M", 1), ("I", 2), ("M", 5)], "TCCTGTTT", "u4"),  # SNP 161 (160): index 1+2+1 = 4: G -> alt
+        rec(178, [("=", 3), ("M", 6)], "TTTCTTTTT", "u5"),           # '=' is ignored by the walk: M starts at 178, SNP
+                                                                      # 181 (180) -> index 2: T -> neither allele (code 2)
+        rec(199, [("M", 6)], "TAGTTT", "u6", qual=[30, 5, 30, 30, 30, 30]),  # SNP 201 (200): index 1, BQ 5 < --min-BQ
+    ]
+    write_bam_records(pre + ".bam", [("1", 1000)], records)
+    r = subprocess.run([CRAMORE, "demuxlet", "--sam", pre + ".bam", "--vcf", pre + ".vcf", "--out", str(tmp_path / "o"),
+                        "--gpu-dump-inputs", str(tmp_path / "d")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    snp = np.fromfile(str(tmp_path / "d.snp_idx.i32"), np.int32)
+    al = np.fromfile(str(tmp_path / "d.al.u8"), np.uint8)
+    bq = np.fromfile(str(tmp_path / "d.bq.u8"), np.uint8)
+    assert snp.tolist() == [0, 1, 3, 4] and al.tolist() == [1, 0, 1, 2] and bq.tolist() == [20, 20, 20, 20]
