@@ -12,6 +12,7 @@
 // reader against BAM files written by an independent Python encoder and against the --plp path on the same reads.
 #pragma once
 #include <unordered_map>
+#include <unordered_set>
 
 #include "host_io.h"
 
@@ -220,72 +221,217 @@ struct SamOptions {
   int32_t capBQ = 20, minBQ = 13, minMQ = 20, minTD = 0;
   uint32_t exclFlag = 0x0f04;
   std::set<std::string> valid_bcs;  // --group-list
+  // dsc-pileup only (cmd_cram_dsc_pileup.cpp): a second flag mask applied in the loop, reads on contigs the VCF does
+  // not have still count towards the droplet's totals, and the regions covered per (droplet, UMI) are collected
+  bool pileup_mode = false;
+  uint32_t excludeFlag2 = 0;
+  bool collect_umi_loci = false;
 };
+
+// one aligned block of a read: genomeLocus (genomeLoci.h:17-75), positions 1-based and closed
+struct UmiLocus {
+  int32_t tid, beg1, end0;
+};
+// (droplet, UMI) -> covered regions, forward and reverse strand (umiLoci of cmd_cram_dsc_pileup.cpp:195)
+struct UmiLoci {
+  int32_t cell, umi;
+  std::vector<UmiLocus> strand[2];
+};
+
+// ordering of genomeLocus::operator< (genomeLoci.h:53-75): contigs by their leading number when both have one,
+// numbered contigs before the others, otherwise by name.  Two different contigs with the same leading number are
+// EQUIVALENT under it -- a std::set then refuses the second locus; insert_locus below keeps that.
+struct UmiLocusLess {
+  const std::vector<std::string>* names;
+  bool operator()(const UmiLocus& a, const UmiLocus& b) const {
+    if (a.tid == b.tid) return (a.beg1 == b.beg1) ? (a.end0 < b.end0) : (a.beg1 < b.beg1);
+    const std::string& ca = (*names)[(size_t)a.tid];
+    const std::string& cb = (*names)[(size_t)b.tid];
+    const int32_t n1 = atoi(ca.c_str()), n2 = atoi(cb.c_str());
+    if (n1 == 0 && n2 == 0) return ca < cb;
+    if (n1 > 0 && n2 > 0) return n1 < n2;
+    return n1 > 0;
+  }
+};
+
+// genomeLoci::add (genomeLoci.h:227-237) on a sorted vector standing in for the std::set
+inline void insert_locus(std::vector<UmiLocus>& v, const UmiLocus& x, const UmiLocusLess& less) {
+  auto it = std::lower_bound(v.begin(), v.end(), x, less);
+  if (it != v.end() && !less(x, *it)) return;  // an equivalent element is there already
+  v.insert(it, x);
+}
+// genomeLoci::resolveOverlaps (genomeLoci.h:255-287): neighbours sharing a base are merged (touching ones are not)
+inline void resolve_overlaps(std::vector<UmiLocus>& v, const UmiLocusLess& less) {
+  size_t i = 1;
+  while (i < v.size()) {
+    UmiLocus& p = v[i - 1];
+    const UmiLocus& c = v[i];
+    if (p.tid == c.tid && p.beg1 <= c.end0 && c.beg1 <= p.end0) {
+      UmiLocus m = p;
+      if (c.beg1 < m.beg1) m.beg1 = c.beg1;
+      if (c.end0 > m.end0) m.end0 = c.end0;
+      v.erase(v.begin() + (i - 1), v.begin() + (i + 1));
+      auto it = std::lower_bound(v.begin(), v.end(), m, less);
+      if (it != v.end() && !less(m, *it)) {
+        i = (size_t)(it - v.begin()) + 1;  // std::set::insert returned the equivalent element
+      } else {
+        i = (size_t)(v.insert(it, m) - v.begin()) + 1;
+      }
+    } else {
+      ++i;
+    }
+  }
+}
 
 struct SamVariant {
   int32_t rid, pos1;  // VCF contig id, 1-based position
   char ref, alt;
+  int32_t rlen;  // length of the REF allele (bcf1_t::rlen)
 };
 
-// cmd_cram_demuxlet.cpp:222-395 on preloaded variants (`vars`, in VCF order, positions ascending inside a contig;
-// `chroms` = the VCF's contig names): reads stream by, every SNP a read overlaps is looked at, and the droplet store
-// comes out in the reference's iteration order (droplet id = order of first appearance, SNP id, UMI string).
-inline void load_sam(const std::string& fn, const SamOptions& opt, const std::vector<std::string>& chroms,
-                     const std::vector<SamVariant>& vars, DropletStore& st) {
-  if (opt.tagUMI.empty()) fatal("--tag-UMI '' (random UMIs) is not supported by this build");
+struct SamJoinStats {
+  int64_t nReadsMultiSNPs = 0, nReadsSkipBCD = 0, nReadsPass = 0, nReadsRedundant = 0, nReadsN = 0, nReadsLQ = 0,
+          nReadsTMP = 0, nReadsFilt = 0, n_read = 0, n_skip = 0;
+};
+
+// The streaming BAM x VCF join of cmd_cram_demuxlet.cpp:222-395 and cmd_cram_dsc_pileup.cpp:199-372, restated on
+// this build's readers.  The VCF cursor runs ahead of the coordinate-sorted reads; a window [ibeg, nsnps) of the
+// SNPs added so far is examined per read.  Kept as the reference has it, quirks included:
+//   * a SNP becomes known only when a read's end passes the previous one, so the SNP list ends one variant past the
+//     last read;
+//   * the window is trimmed against the contig of the VCF CURSOR and the start of the read
+//     (clear_buffer_before, bcf_filtered_reader.cpp:722-742): once the cursor has moved on to the next contig, the
+//     remaining reads of the current one lose the SNPs still in the window;
+//   * a SNP in the window is matched to the read by position alone.
+// `vr` must stand on its first variant (read() already called once); on_snp(id, first) is called for every SNP
+// right after it is appended to st.snps -- demuxlet parses genotypes there, dsc-pileup the allele frequency.
+// The store comes out in the reference's iteration order (droplet id = order of first appearance, SNP id, UMI string).
+template <class OnSnp>
+inline void join_sam_vcf(const std::string& fn, const SamOptions& opt, VcfReader& vr, DropletStore& st, OnSnp on_snp,
+                         SamJoinStats& js, std::vector<std::string>* bam_refs = NULL,
+                         std::vector<UmiLoci>* umi_loci = NULL, std::vector<std::string>* umi_names = NULL,
+                         std::vector<int32_t>* cell_numi = NULL) {
+  if (!opt.tagGroup.empty() && opt.tagGroup.size() != 2)
+    fatal("Cannot recognize group tag %s. It is suppose to be a length 2 string", opt.tagGroup.c_str());
+  if (!opt.tagUMI.empty() && opt.tagUMI.size() != 2)
+    fatal("Cannot recognize UMI tag %s. It is suppose to be a length 2 string", opt.tagUMI.c_str());
   BamReader br(fn);
   br.minMQ = opt.minMQ;
   br.exclude_flag = opt.exclFlag;
-  std::unordered_map<std::string, int32_t> chrom_id;
-  for (size_t i = 0; i < chroms.size(); ++i) chrom_id.emplace(chroms[i], (int32_t)i);
-  std::vector<int32_t> tid2rid(br.refs.size(), -1);
-  bool any = false;
-  for (size_t t = 0; t < br.refs.size(); ++t) {
-    auto it = chrom_id.find(br.refs[t]);
-    if (it != chrom_id.end()) {
-      tid2rid[t] = it->second;
-      any = true;
+  if (bam_refs) *bam_refs = br.refs;
+  auto name2rid = [&](const std::string& name) {  // bcf_hdr_name2id
+    for (size_t i = 0; i < vr.chroms.size(); ++i)
+      if (vr.chroms[i] == name) return (int32_t)i;
+    return (int32_t)-1;
+  };
+  // contig order check (:181-199 / dsc-pileup :145-169)
+  int32_t prevrid = -1, nmatch = 0, rchroms_size = 0;
+  {
+    std::set<int32_t> rids;
+    for (size_t t = 0; t < br.refs.size(); ++t) {
+      const int32_t rid = name2rid(br.refs[t]);
+      if (rid >= 0) {
+        if (prevrid >= rid)
+          fatal("Your VCF/BCF files and SAM/BAM/CRAM files have different ordering of chromosomes. SAM/BAM/CRAM file has %s before %s, but VCF/BCF file has %s after %s",
+                vr.chroms[(size_t)prevrid].c_str(), br.refs[t].c_str(), vr.chroms[(size_t)prevrid].c_str(), br.refs[t].c_str());
+        rids.insert(rid);
+        ++nmatch;
+        rchroms_size = rid + 1;
+        prevrid = rid;
+      }
     }
+    if (nmatch == 0 || (int32_t)rids.size() != nmatch)
+      fatal("Your VCF/BCF files and SAM/BAM/CRAM files does not have any matching chromosomes, or some chromosome names are duplicated");
   }
-  if (!any) fatal("Your VCF/BCF files and SAM/BAM/CRAM files does not have any matching chromosomes, or some chromosome names are duplicated");
-  // per contig: [first, last) range of `vars`
-  std::vector<std::pair<int64_t, int64_t>> vrange(chroms.size(), {0, 0});
-  for (int64_t i = 0; i < (int64_t)vars.size(); ++i) {
-    auto& pr = vrange[(size_t)vars[i].rid];
-    if (pr.second == 0 && pr.first == 0) pr.first = i;
-    else if (pr.second != i) fatal("the VCF is not sorted: contig %s appears in more than one block", chroms[(size_t)vars[i].rid].c_str());
-    if (i > pr.first && vars[i].pos1 < vars[i - 1].pos1) fatal("the VCF is not sorted by position on contig %s", chroms[(size_t)vars[i].rid].c_str());
-    pr.second = i + 1;
-  }
-  st.rid2chr = chroms;
+  if (opt.pileup_mode) notice("Identified %d overlapping chromosomes between VCF and BAM", nmatch);
+
+  std::vector<SamVariant> vars;  // parallel to st.snps
+  auto add_cursor = [&](bool first) {
+    vars.push_back({vr.cur.rid, vr.cur.pos1, vr.cur.ref[0], vr.cur.alt[0], (int32_t)vr.cur.ref.size()});
+    st.snps.push_back({vr.cur.rid, vr.cur.pos1, vr.cur.ref[0], vr.cur.alt[0], 0.0});
+    on_snp((int32_t)vars.size() - 1, first);
+  };
   st.snps.clear();
-  for (const SamVariant& v : vars) st.snps.push_back({v.rid, v.pos1, v.ref, v.alt, 0.0});
+  add_cursor(true);
+  bool vcf_eof = false;
+  int64_t ibeg = 0;  // window [ibeg, vars.size())
 
   struct Rec {
     int32_t cell, snp, umi;
     uint8_t al, bq;
     int64_t seq;
   };
+  struct Key {
+    int32_t cell, snp, umi;
+    bool operator==(const Key& o) const { return cell == o.cell && snp == o.snp && umi == o.umi; }
+  };
+  struct KeyHash {
+    size_t operator()(const Key& k) const {
+      uint64_t h = (uint64_t)(uint32_t)k.cell * 0x9e3779b97f4a7c15ull;
+      h ^= ((uint64_t)(uint32_t)k.snp + 0x7f4a7c15ull) * 0xbf58476d1ce4e5b9ull;
+      h ^= ((uint64_t)(uint32_t)k.umi + 0x1ce4e5b9ull) * 0x94d049bb133111ebull;
+      return (size_t)(h ^ (h >> 29));
+    }
+  };
   std::vector<Rec> recs;
+  std::unordered_set<Key, KeyHash> seen;
   std::unordered_map<std::string, int32_t> cell_id, umi_id;
   std::vector<std::string> umis;
+  std::unordered_map<uint64_t, size_t> loci_at;  // (cell, umi) -> index into *umi_loci
+  const UmiLocusLess less{&br.refs};
   const char* gtag = opt.tagGroup.c_str();
   const char* utag = opt.tagUMI.c_str();
   BamRecord r;
-  int64_t n_no_gtag = 0, n_no_utag = 0, nReadsSkipBCD = 0, nReadsPass = 0;
+  int64_t n_no_gtag = 0, n_no_utag = 0;
+  std::vector<int32_t> tid_rid;  // cache of name2rid per BAM contig, refreshed when the VCF meets a new contig
+  size_t tid_rid_for = 0;
+  char numbuf[32];
   while (br.read(r)) {
-    if (r.tid < 0 || r.tid >= (int32_t)tid2rid.size()) continue;
-    const int32_t rid = tid2rid[(size_t)r.tid];
-    if (rid < 0) continue;  // no matching VCF contig (:225-228)
+    const int32_t endpos = r.endpos();
+    if (tid_rid_for != vr.chroms.size()) {
+      tid_rid.assign(br.refs.size(), -1);
+      for (size_t t = 0; t < br.refs.size(); ++t) tid_rid[t] = name2rid(br.refs[t]);
+      tid_rid_for = vr.chroms.size();
+    }
+    const int32_t tid2rid = (r.tid >= 0 && r.tid < (int32_t)tid_rid.size()) ? tid_rid[(size_t)r.tid] : -1;
+    bool noBCF = false;
+    if (opt.pileup_mode) {
+      if (r.flag & opt.excludeFlag2) {  // dsc-pileup :208-212
+        ++js.nReadsFilt;
+        continue;
+      }
+      if (tid2rid < 0) noBCF = true;
+      if (vars.back().rid >= rchroms_size)
+        fatal("The contig %s was absent in the VCF header. This happens when contigs in VCF header do not match to actual records. Run 'bcftools reheader -f [ref.fasta.fai] [in.vcf.gz] > [out.vcf.gz] to resolve this problem",
+              (r.tid >= 0 && r.tid < (int32_t)br.refs.size()) ? br.refs[(size_t)r.tid].c_str() : "*");
+    } else if (tid2rid < 0) {
+      continue;  // demuxlet :225-228
+    }
+    {  // clear_buffer_before(contig of the cursor, start of the read)
+      const int32_t crid = vars.back().rid;
+      while (ibeg < (int64_t)vars.size()) {
+        const SamVariant& v = vars[(size_t)ibeg];
+        if (v.rid < crid) ++ibeg;
+        else if (v.rid == crid && (v.pos1 - 1) + v.rlen < r.pos) ++ibeg;
+        else break;
+      }
+    }
+    if (!noBCF) {
+      while (!vcf_eof && (vars.back().rid < tid2rid || (vars.back().rid == tid2rid && vars.back().pos1 - 1 < endpos))) {
+        if (vr.read()) add_cursor(false);
+        else vcf_eof = true;
+      }
+    }
+    // droplet
     int32_t ibcd;
     {
       const char* sbcd = ".";
       if (!opt.tagGroup.empty()) {
-        const char* z = (gtag[0] && gtag[1]) ? r.tag_z(gtag) : NULL;
+        const char* z = r.tag_z(gtag);
         if (z) sbcd = z;
         else ++n_no_gtag;
         if (!opt.valid_bcs.empty() && !opt.valid_bcs.count(sbcd)) {
-          ++nReadsSkipBCD;
+          ++js.nReadsSkipBCD;
           continue;
         }
       }
@@ -293,46 +439,87 @@ inline void load_sam(const std::string& fn, const SamOptions& opt, const std::ve
       if (ins.second) {
         st.bcs.push_back(sbcd);
         st.totl_reads.push_back(0);
+        if (cell_numi) cell_numi->push_back(0);
       }
       ibcd = ins.first->second;
     }
+    ++js.nReadsTMP;
+    // UMI
     int32_t iumi;
     {
-      const char* z = (utag[0] && utag[1]) ? r.tag_z(utag) : NULL;
-      if (!z) ++n_no_utag;
-      auto ins = umi_id.emplace(z ? z : ".", (int32_t)umis.size());
+      const char* z = ".";
+      if (opt.tagUMI.empty()) {
+        snprintf(numbuf, sizeof(numbuf), "%x", rand());  // a random UMI (:298-301)
+        z = numbuf;
+      } else {
+        const char* t = r.tag_z(utag);
+        if (t) z = t;
+        else ++n_no_utag;
+      }
+      auto ins = umi_id.emplace(z, (int32_t)umis.size());
       if (ins.second) umis.push_back(ins.first->first);
       iumi = ins.first->second;
     }
-    ++st.totl_reads[(size_t)ibcd];  // :325
-    // SNPs from the read's start to its end (:340-367)
-    const auto& pr = vrange[(size_t)rid];
-    const int32_t endpos = r.endpos();
-    auto lo = std::lower_bound(vars.begin() + pr.first, vars.begin() + pr.second, r.pos + 1,
-                               [](const SamVariant& v, int32_t p1) { return v.pos1 < p1; });
-    bool passed = false;
-    for (auto it = lo; it != vars.begin() + pr.second && it->pos1 - 1 < endpos; ++it) {
+    ++st.totl_reads[(size_t)ibcd];
+    if (opt.collect_umi_loci && umi_loci) {  // dsc-pileup :296-331
+      const uint64_t key = ((uint64_t)(uint32_t)ibcd << 32) | (uint32_t)iumi;
+      auto ins = loci_at.emplace(key, umi_loci->size());
+      if (ins.second) {
+        umi_loci->push_back({ibcd, iumi, {}});
+        if (cell_numi) ++(*cell_numi)[(size_t)ibcd];
+      }
+      std::vector<UmiLocus>& loci = (*umi_loci)[ins.first->second].strand[(r.flag & 0x10) ? 1 : 0];
+      if (!r.cigar.empty()) {
+        int32_t cpos = r.pos;
+        for (uint32_t c : r.cigar) {
+          const char op = "MIDNSHP=XB??????"[c & 15];
+          const int32_t len = (int32_t)(c >> 4);
+          if (op == 'M') {
+            insert_locus(loci, {r.tid, cpos + 1, cpos + len}, less);
+            cpos += len;
+          } else if (op == 'D' || op == 'N') {
+            cpos += len;
+          }
+        }
+        resolve_overlaps(loci, less);
+      }
+    }
+    if (noBCF) continue;
+    // SNPs of the window (:340-367)
+    int32_t nv_pass = 0, nv_redundant = 0, nv_valid = 0;
+    for (int64_t i = ibeg; i < (int64_t)vars.size(); ++i) {
+      const SamVariant& v = vars[(size_t)i];
       char base, qual;
       int32_t rpos;
-      bam_base_at(r, (uint32_t)(it->pos1 - 1), base, qual, rpos);
+      bam_base_at(r, (uint32_t)(v.pos1 - 1), base, qual, rpos);
       if (rpos == kBamReadIndexNA) continue;
       if (base == 'N') continue;
+      ++nv_valid;
       if (qual - 33 < opt.minBQ) continue;
       if (rpos < opt.minTD - 1) continue;
       if (rpos + opt.minTD > r.l_seq) continue;
-      const uint8_t allele = (base == it->ref) ? 0 : ((base == it->alt) ? 1 : 2);
+      const uint8_t allele = (base == v.ref) ? 0 : ((base == v.alt) ? 1 : 2);
       const int bq = qual - 33 > opt.capBQ ? opt.capBQ : qual - 33;
-      recs.push_back({ibcd, (int32_t)(it - vars.begin()), iumi, allele, (uint8_t)bq, (int64_t)recs.size()});
-      passed = true;
+      if (seen.insert({ibcd, (int32_t)i, iumi}).second) {  // sc_dropseq_lib_t::add_read: the first read wins
+        recs.push_back({ibcd, (int32_t)i, iumi, allele, (uint8_t)bq, (int64_t)recs.size()});
+        ++nv_pass;
+      } else {
+        ++nv_redundant;
+      }
     }
-    if (passed) ++nReadsPass;
+    if (nv_pass > 1) ++js.nReadsMultiSNPs;
+    if (nv_pass > 0) ++js.nReadsPass;
+    else if (nv_redundant > 0) ++js.nReadsRedundant;
+    else if (nv_valid > 0) ++js.nReadsLQ;
+    else ++js.nReadsN;
   }
-  if (n_no_gtag) notice("WARNING: %lld reads carry no droplet/cell tag %s and were treated as a single group", (long long)n_no_gtag, gtag);
+  js.n_read = br.n_read;
+  js.n_skip = br.n_skip;
   if (n_no_utag) notice("WARNING: %lld reads carry no UMI tag %s and were treated as a single UMI", (long long)n_no_utag, utag);
-  notice("Finished reading %lld reads from %s (%lld skipped by the read filter, %lld outside --group-list, %lld overlapping SNPs)",
-         (long long)br.n_read, fn.c_str(), (long long)br.n_skip, (long long)nReadsSkipBCD, (long long)nReadsPass);
+  if (n_no_gtag) notice("WARNING: %lld reads carry no droplet/cell tag %s and were treated as a single group", (long long)n_no_gtag, gtag);
+  if (umi_names) *umi_names = umis;
 
-  // reference iteration order: droplet id, SNP id, UMI string; of equal (droplet, SNP, UMI) the first read wins
+  // reference iteration order: droplet id, SNP id, UMI string
   std::sort(recs.begin(), recs.end(), [&](const Rec& a, const Rec& b) {
     if (a.cell != b.cell) return a.cell < b.cell;
     if (a.snp != b.snp) return a.snp < b.snp;
@@ -349,7 +536,6 @@ inline void load_sam(const std::string& fn, const SamOptions& opt, const std::ve
   bool open = false;
   for (size_t i = 0; i < recs.size(); ++i) {
     const Rec& x = recs[i];
-    if (i > 0 && x.cell == recs[i - 1].cell && x.snp == recs[i - 1].snp && x.umi == recs[i - 1].umi) continue;  // duplicate
     if (i == 0 || x.cell != recs[i - 1].cell || x.snp != recs[i - 1].snp) {
       if (open) st.read_ptr.push_back((int64_t)st.al.size());
       st.snp_idx.push_back(x.snp);

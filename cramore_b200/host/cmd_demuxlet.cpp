@@ -173,26 +173,7 @@ int cmdDemuxlet(int argc, char** argv) {
     std::vector<float> tmp_gp(nv * 3);
     DropletStore st;
     if (!samFile.empty()) {
-      // ---- BAM x VCF join, cmd_cram_demuxlet.cpp:126-395: every variant passing the filter becomes a SNP with
-      // genotypes (the reference adds them as the reads reach them; a SNP no read reaches changes nothing) ----
-      std::vector<SamVariant> vars;
-      while (!vr.eof) {
-        if (!vr.parse_posteriors(field.c_str(), 0, tmp_gp.data()))
-          fatal("Cannot parse posterior probability at %s:%d", vr.chroms[vr.cur.rid].c_str(), vr.cur.pos1);
-        gp_f32.insert(gp_f32.end(), tmp_gp.begin(), tmp_gp.end());
-        double err = genoErrorOffset;  // :256-262
-        if (genoErrorCoeffR2 > 0) {
-          float r2;
-          if (!vr.info_float(r2Info.c_str(), &r2))
-            fatal("Cannot extract %s (1 float value) from INFO field at %s:%d. Cannot use --geno-error-coeff", r2Info.c_str(),
-                  vr.chroms[vr.cur.rid].c_str(), vr.cur.pos1);
-          err += (1 - genoErrorOffset) * (1 - r2) * genoErrorCoeffR2;
-        }
-        snp_err.push_back(err);
-        has_gp.push_back(1);
-        vars.push_back({vr.cur.rid, vr.cur.pos1, vr.cur.ref[0], vr.cur.alt[0]});
-        vr.read();
-      }
+      // ---- BAM x VCF join, cmd_cram_demuxlet.cpp:126-395 (join_sam_vcf keeps the reference's streaming order) ----
       SamOptions so;
       so.tagGroup = tagGroup;
       so.tagUMI = tagUMI;
@@ -202,7 +183,30 @@ int cmdDemuxlet(int argc, char** argv) {
       so.minTD = minTD;
       so.exclFlag = (uint32_t)exclFlag;
       so.valid_bcs = flt.valid_bcs;
-      load_sam(samFile, so, vr.chroms, vars, st);
+      SamJoinStats js;
+      join_sam_vcf(samFile, so, vr, st, [&](int32_t /*snp*/, bool first) {
+        // the first SNP is added before the loop with the default genotype-error offset of parse_posteriors and
+        // without the error mix (:177, :204-209); the others at :238-268
+        if (!vr.parse_posteriors(field.c_str(), first ? 1e-4 : 0, tmp_gp.data()))
+          fatal("Cannot parse posterior probability at %s:%d", vr.chroms[vr.cur.rid].c_str(), vr.cur.pos1);
+        gp_f32.insert(gp_f32.end(), tmp_gp.begin(), tmp_gp.end());
+        double err = 0;
+        if (!first) {
+          err = genoErrorOffset;  // :256-262
+          if (genoErrorCoeffR2 > 0) {
+            float r2;
+            if (!vr.info_float(r2Info.c_str(), &r2))
+              fatal("Cannot extract %s (1 float value) from INFO field at %s:%d. Cannot use --geno-error-coeff", r2Info.c_str(),
+                    vr.chroms[vr.cur.rid].c_str(), vr.cur.pos1);
+            err += (1 - genoErrorOffset) * (1 - r2) * genoErrorCoeffR2;
+          }
+        }
+        snp_err.push_back(err);
+        has_gp.push_back(1);
+      }, js);
+      notice("Finished reading %lld reads from %s (%lld skipped by the read filter, %lld outside --group-list, %lld overlapping SNPs, %lld redundant)",
+             (long long)js.n_read, samFile.c_str(), (long long)js.n_skip, (long long)js.nReadsSkipBCD, (long long)js.nReadsPass,
+             (long long)js.nReadsRedundant);
     } else
     // ---- .var.gz x VCF join, sc_drop_seq.cpp:108-116 and :226-330 ----
     load_plp(plpPrefix, flt, st, [&](int32_t /*idx*/, const char* chr, const SnpInfo& s) {

@@ -216,7 +216,7 @@ class VcfReader {
   std::vector<double> acs;
   int32_t an = 0;
 
-  VcfReader(const std::string& fn, const std::set<std::string>& sm_ids) : lr_(fn) {
+  VcfReader(const std::string& fn, const std::set<std::string>& sm_ids, bool allow_no_samples = false) : lr_(fn) {
     while (lr_.next_line()) {
       const std::string& l = lr_.line;
       if (l.compare(0, 2, "##") == 0) {
@@ -239,7 +239,7 @@ class VcfReader {
     }
     for (int32_t i = 0; i < (int32_t)samples.size(); ++i)
       if (sm_ids.empty() || sm_ids.count(samples[i])) sm_icols.push_back(i);
-    if (sm_icols.empty()) fatal("No sample to read from %s", fn.c_str());
+    if (sm_icols.empty() && !allow_no_samples) fatal("No sample to read from %s", fn.c_str());
   }
 
   int32_t nsamples() const { return (int32_t)sm_icols.size(); }
@@ -258,8 +258,11 @@ class VcfReader {
       if (lr_.line.empty() || lr_.line[0] == '#') continue;
       parse_line();
       ++nRead;
-      bool pass = cur.n_allele <= maxAlleles;
-      if (pass && (minMAC > 0 || minCallRate > 0)) {  // vfilt.require_GT, bcf_filtered_reader.cpp:613-645
+      // passed_vfilter (bcf_filtered_reader.cpp:571-645): with no genotype-based threshold set (require_GT false,
+      // bcf_filter_arg.h:109-113) it returns true before it ever looks at the allele count
+      const bool require_GT = minMAC > 0 || minCallRate > 0;
+      bool pass = !require_GT || cur.n_allele <= maxAlleles;
+      if (pass && require_GT) {
         if (!parse_genotypes()) fatal("Cannot find the field GT from the VCF file at position %s:%d", chroms[cur.rid].c_str(), cur.pos1);
         if (minCallRate > (double)an / (2.0 * (double)sm_icols.size())) pass = false;
         const int32_t ac = an - (int32_t)acs[0];
@@ -362,18 +365,37 @@ class VcfReader {
 
   // one float INFO value; false if absent
   bool info_float(const char* tag, float* v) const {
+    const char* s = info_value(tag);
+    if (s) *v = strtof(s, NULL);
+    return s != NULL;
+  }
+  // start of the value of an INFO key, or NULL
+  const char* info_value(const char* tag) const {
     const std::string key = std::string(tag) + "=";
     size_t p = 0;
     while (p < cur.info.size()) {
       size_t e = cur.info.find(';', p);
       if (e == std::string::npos) e = cur.info.size();
-      if (cur.info.compare(p, key.size(), key) == 0) {
-        *v = strtof(cur.info.c_str() + p + key.size(), NULL);
-        return true;
-      }
+      if (cur.info.compare(p, key.size(), key) == 0) return cur.info.c_str() + p + key.size();
       p = e + 1;
     }
-    return false;
+    return NULL;
+  }
+
+  // BCFFilteredReader::calculate_af (bcf_filtered_reader.cpp:845-879): INFO/AF, else INFO/AC / INFO/AN, when all
+  // samples of the file are in use; otherwise the alternate allele's share among the selected samples' genotypes
+  double calculate_af(bool use_info_field) {
+    if (use_info_field && sm_icols.size() == samples.size()) {
+      float af;
+      if (info_float("AF", &af)) return af;
+      const char* ac = info_value("AC");
+      const char* an_ = info_value("AN");
+      if (!ac) fatal("Cannot find AC field from INFO field at %s:%d", chroms[cur.rid].c_str(), cur.pos1);
+      if (!an_) fatal("Cannot find AN field from INFO field at %s:%d", chroms[cur.rid].c_str(), cur.pos1);
+      return (double)strtol(ac, NULL, 10) / (double)strtol(an_, NULL, 10);
+    }
+    parse_genotypes();
+    return (double)acs[1] / (double)an;
   }
 
  private:

@@ -6,22 +6,25 @@
 int cmdDemuxlet(int argc, char** argv);
 int cmdFreemuxlet(int argc, char** argv);
 int cmdFreemux2(int argc, char** argv);
+int cmdDscPileup(int argc, char** argv);
 
 int main(int argc, char** argv) {
   if (argc < 2 || strcmp(argv[1], "--help") == 0) {
     fprintf(stderr, "cramore (B200 engine build) -- available commands:\n"
                     "  demuxlet    Deconvolute sample identify of droplet-based sc-RNAseq\n"
                     "  freemuxlet  Genotype-free deconvolution of scRNA-seq\n"
-                    "  freemux2    Genotype-free deconvolution of scRNA-seq (v2)\n");
+                    "  freemux2    Genotype-free deconvolution of scRNA-seq (v2)\n"
+                    "  dsc-pileup  Produce pileup of dsc-RNAseq\n");
     return argc < 2 ? 1 : 0;
   }
   try {
     if (strcmp(argv[1], "demuxlet") == 0) return cmdDemuxlet(argc - 1, argv + 1);
     if (strcmp(argv[1], "freemuxlet") == 0) return cmdFreemuxlet(argc - 1, argv + 1);
     if (strcmp(argv[1], "freemux2") == 0) return cmdFreemux2(argc - 1, argv + 1);
+    if (strcmp(argv[1], "dsc-pileup") == 0) return cmdDscPileup(argc - 1, argv + 1);
   } catch (const std::exception&) {
     return 134;  // the reference aborts on error() (uncaught pexception, Error.cpp:29-43)
   }
-  fprintf(stderr, "cramore: unknown command %s (this build provides demuxlet, freemuxlet and freemux2)\n", argv[1]);
+  fprintf(stderr, "cramore: unknown command %s (this build provides demuxlet, freemuxlet, freemux2 and dsc-pileup)\n", argv[1]);
   return 1;
 }

@@ -194,9 +194,12 @@ def write_plp(d, prefix, chrom="1"):
     return bcs
 
 
-def write_vcf(d, path, chrom="1", with_r2=False):
+def write_vcf(d, path, chrom="1", with_r2=False, lead_decoy=False):
     """Text VCF with GT:GP per sample: the un-normalised GP triple (0.98 on the genotype, 0.01 elsewhere)
-    that BCFFilteredReader::parse_posteriors (bcf_filtered_reader.cpp:457-499) float-normalises into d["gp"]."""
+    that BCFFilteredReader::parse_posteriors (bcf_filtered_reader.cpp:457-499) float-normalises into d["gp"].
+    lead_decoy: one extra heterozygous record in front of every read (position 500).  The reference's --sam path
+    treats the FIRST variant of the file differently from the others (cmd_cram_demuxlet.cpp:177, 204-209: default
+    genotype-error offset, no error mix); with the decoy in that role the real SNPs are handled like on --plp."""
     import gzip
     opener = gzip.open if path.endswith(".gz") else open
     gts = ["0/0", "0/1", "1/1"]
@@ -209,6 +212,9 @@ def write_vcf(d, path, chrom="1", with_r2=False):
         f.write('##FORMAT=<ID=GP,Number=G,Type=Float,Description="Genotype posterior">\n')
         f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(d["sample_ids"]) + "\n")
         geno = np.asarray(d["geno"])
+        if lead_decoy:
+            f.write("%s\t500\t.\tA\tC\t.\tPASS\t%s\tGT:GP\t" % (chrom, "R2=0.9" if with_r2 else "."))
+            f.write("\t".join(cols[1] for _ in d["sample_ids"]) + "\n")
         for s in range(d["nsnps"]):
             info = "R2=0.9" if with_r2 else "."
             f.write("%s\t%d\t.\tA\tG\t.\tPASS\t%s\tGT:GP\t" % (chrom, 1000 + 10 * s, info))

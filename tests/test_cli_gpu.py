@@ -200,7 +200,7 @@ def test_cli_demuxlet_sam_input_matches_plp_input(built, tmp_path):
     d = make_dataset("C1", nbcs=60, nsnps=300, rbar=150, nv=6, seed=29, with_barcodes=True)
     pre = str(tmp_path / "in")
     write_plp(d, pre)
-    write_vcf(d, pre + ".vcf", with_r2=True)
+    write_vcf(d, pre + ".vcf", with_r2=True, lead_decoy=True)
     write_bam(d, pre + ".bam", duplicate_every=7)
     rows = {}
     for mode, src in (("sam", ["--sam", pre + ".bam"]), ("plp", ["--plp", pre])):

@@ -273,6 +273,9 @@ REF_DEMUX_FLAGS = ["sam", "tag-group", "tag-UMI", "plp", "vcf", "field", "geno-e
 REF_FMX_FLAGS = ["plp", "init-cluster", "out", "nsample", "aux-files", "verbose", "doublet-prior", "geno-error",
                  "bf-thres", "frac-init-clust", "iter-init", "keep-init-missing", "cap-BQ", "min-BQ", "group-list",
                  "min-total", "min-uniq", "min-snp"]  # cmd_cram_freemuxlet.cpp:34-63
+REF_DSC_FLAGS = ["sam", "tag-group", "tag-UMI", "exclude-flag", "vcf", "sm", "sm-list", "out", "sam-verbose", "vcf-verbose",
+                 "skip-umi", "cap-BQ", "min-BQ", "min-MQ", "min-TD", "excl-flag", "group-list", "min-total", "min-uniq",
+                 "min-snp"]  # cmd_cram_dsc_pileup.cpp:39-71
 
 
 def _help_flags(cmd):
@@ -285,6 +288,7 @@ def test_cli_flag_surface(built):
     assert d[:len(REF_DEMUX_FLAGS)] == REF_DEMUX_FLAGS and all(f.startswith("gpu-") for f in d[len(REF_DEMUX_FLAGS):])
     f = _help_flags("freemuxlet")
     assert f[:len(REF_FMX_FLAGS)] == REF_FMX_FLAGS and all(x.startswith("gpu-") for x in f[len(REF_FMX_FLAGS):])
+    assert _help_flags("dsc-pileup") == REF_DSC_FLAGS
     f2 = _help_flags("freemux2")
     assert "seed" in f2 and "randomize-singlet-score" in f2 and "min-umi" in f2 and "min-uniq" not in f2
     # unknown flags and a repeated scalar flag are errors, like paramList::Read (params.cpp:140-177, 478-480)
@@ -416,7 +420,7 @@ def test_cli_sam_path_matches_plp_path(built, tmp_path):
     d = make_dataset("C1", nbcs=40, nsnps=150, rbar=90, nv=5, seed=13, with_barcodes=True)
     pre = str(tmp_path / "in")
     write_plp(d, pre)
-    write_vcf(d, pre + ".vcf", with_r2=True)
+    write_vcf(d, pre + ".vcf", with_r2=True, lead_decoy=True)
     write_bam(d, pre + ".bam", duplicate_every=5)
     common = ["--vcf", pre + ".vcf", "--out", str(tmp_path / "o"), "--geno-error-coeff", "0.5"]
     for mode, src in (("sam", ["--sam", pre + ".bam"]), ("plp", ["--plp", pre])):
@@ -429,13 +433,17 @@ def test_cli_sam_path_matches_plp_path(built, tmp_path):
 
     has = load("plp", "has_gp.u8", np.uint8).astype(bool)
     assert has.sum() < len(has) and load("sam", "has_gp.u8", np.uint8).all()
-    remap = np.cumsum(has) - 1  # SNP id on the --sam path
+    remap = np.cumsum(has)  # SNP id on the --sam path, whose SNP 0 is the decoy record
     assert (tmp_path / "sam.barcodes.txt").read_text() == (tmp_path / "plp.barcodes.txt").read_text()
     assert np.array_equal(load("sam", "row_int_id.i32", np.int32), load("plp", "row_int_id.i32", np.int32))
     nv = 5
     gp_p = load("plp", "gp.f32", np.float32).reshape(-1, nv * 3)[has]
-    assert np.array_equal(load("sam", "gp.f32", np.float32).reshape(-1, nv * 3), gp_p)
-    assert np.array_equal(load("sam", "snp_err.f64", np.float64), load("plp", "snp_err.f64", np.float64)[has])
+    gp_s = load("sam", "gp.f32", np.float32).reshape(-1, nv * 3)
+    err_s = load("sam", "snp_err.f64", np.float64)
+    assert np.array_equal(gp_s[1:], gp_p)
+    assert np.array_equal(err_s[1:], load("plp", "snp_err.f64", np.float64)[has])
+    # the first variant of the file: genotype-error offset 1e-4 inside parse_posteriors, no error mix (:177, :204-209)
+    assert err_s[0] == 0.0 and np.allclose(gp_s[0], np.tile([0.01, 0.98, 0.01], nv), atol=2e-4) and gp_s[0, 1] != np.float32(0.98)
     cps, cpp = load("sam", "cell_ptr.i64", np.int64), load("plp", "cell_ptr.i64", np.int64)
     sis, sip = load("sam", "snp_idx.i32", np.int32), load("plp", "snp_idx.i32", np.int32)
     rps, rpp = load("sam", "read_ptr.i64", np.int64), load("plp", "read_ptr.i64", np.int64)
@@ -482,4 +490,193 @@ def test_bam_base_extraction_follows_the_reference_cigar_walk(built, tmp_path):
     snp = np.fromfile(str(tmp_path / "d.snp_idx.i32"), np.int32)
     al = np.fromfile(str(tmp_path / "d.al.u8"), np.uint8)
     bq = np.fromfile(str(tmp_path / "d.bq.u8"), np.uint8)
-    assert snp.tolist() == [0, 1, 3, 4] and al.tolist() == [1, 0, 1, 2] and bq.tolist() == [20, 20, 20, 20]
+    # SNP 5 (position 201): u6 fails --min-BQ there, but u5 does produce an observation.  Its '=' bases are not
+    # counted, so the walk ends at read index 6 < read length without having met position 200 and the function
+    # hands out that base ('T', neither allele) for every later SNP in the window -- as the reference does
+    assert snp.tolist() == [0, 1, 3, 4, 5] and al.tolist() == [1, 0, 1, 2, 2] and bq.tolist() == [20, 20, 20, 20, 20]
+
+
+def _random_alignments(tmp_path, seed, with_samples=False):
+    """A coordinate-sorted BAM over several contigs (one of them unknown to the VCF) with long gapped reads that
+    span several SNPs, both strands, flags and mapping qualities on either side of the filters, missing tags, a small
+    UMI alphabet (so that droplet/SNP/UMI collisions happen) -- and a VCF with an indel, a multi-allelic record and a
+    contig the BAM lacks."""
+    from cramore_b200.synth import encode_bam_record, write_bam_records
+    rng = np.random.default_rng(seed)
+    refs = [("1", 3000), ("2", 2500), ("GL7", 900), ("10", 2000), ("X", 1500)]   # GL7: not in the VCF
+    vcf_contigs = ["1", "2", "10", "11", "X"]                                     # 11: not in the BAM
+    pre = str(tmp_path / ("r%d" % seed))
+    samples = ["S%d" % i for i in range(4)] if with_samples else []
+    with open(pre + ".vcf", "w") as f:
+        f.write("##fileformat=VCFv4.2\n" + "".join("##contig=<ID=%s>\n" % c for c in vcf_contigs))
+        f.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO" + ("\tFORMAT\t" + "\t".join(samples) if samples else "") + "\n")
+        for c in vcf_contigs:
+            length = dict(refs).get(c, 800)
+            pos = 40
+            while pos < length - 40:
+                kind = rng.integers(20)
+                ref, alt = "ACGT"[rng.integers(4)], "ACGT"[rng.integers(4)]
+                if alt == ref:
+                    alt = "ACGT"[("ACGT".index(ref) + 1) % 4]
+                if kind == 0:
+                    ref += "TT"          # a deletion: rlen 3
+                elif kind == 1 and not samples:
+                    alt += ",N"          # three alleles
+                info = "AF=%.4f" % rng.uniform(0.01, 0.99) if rng.integers(2) else "AC=%d;AN=%d" % (rng.integers(1, 50), 200)
+                line = "%s\t%d\t.\t%s\t%s\t.\tPASS\t%s" % (c, pos, ref, alt, info)
+                if samples:
+                    gts = rng.integers(0, 3, len(samples))
+                    line += "\tGT:GP\t" + "\t".join(["0/0:0.98,0.01,0.01", "0/1:0.01,0.98,0.01", "1/1:0.01,0.01,0.98"][g] for g in gts)
+                f.write(line + "\n")
+                pos += int(rng.integers(3, 60))
+    bcs = ["%s-1" % "".join("ACGT"[i] for i in rng.integers(0, 4, 8)) for _ in range(12)]
+    records = []
+    for tid, (name, length) in enumerate(refs):
+        starts = np.sort(rng.integers(0, length - 120, 500 if name != "GL7" else 60))
+        for k, pos in enumerate(starts):
+            cigar, rlen = [], 0
+            if rng.integers(6) == 0:
+                cigar.append(("H", int(rng.integers(1, 5))))
+            if rng.integers(4) == 0:
+                n = int(rng.integers(1, 6))
+                cigar.append(("S", n))
+                rlen += n
+            for blk in range(int(rng.integers(1, 4))):
+                n = int(rng.integers(5, 30))
+                cigar.append(("M" if rng.integers(12) else "=X"[rng.integers(2)], n))
+                rlen += n
+                if blk < 2 and rng.integers(2):
+                    op = "IDN"[rng.integers(3)]
+                    n = int(rng.integers(1, 12))
+                    cigar.append((op, n))
+                    if op == "I":
+                        rlen += n
+            while cigar[-1][0] in "IDN":
+                op, n = cigar.pop()
+                if op == "I":
+                    rlen -= n
+            if rng.integers(5) == 0:
+                n = int(rng.integers(1, 4))
+                cigar.append(("S", n))
+                rlen += n
+            seq = "".join("ACGTN"[i] for i in rng.choice(5, rlen, p=[0.24, 0.24, 0.24, 0.24, 0.04]))
+            qual = [int(q) for q in rng.integers(2, 42, rlen)]
+            flag = (0x10 if rng.integers(2) else 0) | int(rng.choice([0, 0, 0, 0, 0, 0x400, 0x100, 0x4, 0x200, 0x800]))
+            tags = []
+            if rng.integers(25):
+                tags.append(("CB", bcs[rng.integers(len(bcs))]))
+            if rng.integers(25):
+                tags.append(("UB", "".join("ACGT"[i] for i in rng.integers(0, 4, 2))))
+            mapq = int(rng.choice([0, 3, 19, 20, 60, 255]))
+            records.append(encode_bam_record(tid, int(pos), mapq, flag, cigar, seq, qual, "q%d_%d" % (tid, k), tuple(tags)))
+    write_bam_records(pre + ".bam", refs, records)
+    return pre, bcs
+
+
+def _gunzip(path):
+    import gzip
+    with gzip.open(path, "rt") as f:
+        return f.read()
+
+
+@pytest.mark.parametrize("seed,extra", [(1, {}), (2, dict(min_td=3, cap_bq=30, min_bq=20)), (3, dict(skip_umi=True)),
+                                        (4, dict(group=True, exclude_flag=0x10)), (5, dict(min_mq=0, excl_flag=0))])
+def test_dsc_pileup_files_match_the_python_restatement(built, tmp_path, seed, extra):
+    """`cramore dsc-pileup` (cmd_dsc_pileup.cpp + the streaming join of bam_io.h) against oracle/dsc_pileup_py.py, an
+    independent reading of cmd_cram_dsc_pileup.cpp: the four output files byte for byte."""
+    from oracle import dsc_pileup_py
+    pre, bcs = _random_alignments(tmp_path, seed)
+    args = [CRAMORE, "dsc-pileup", "--sam", pre + ".bam", "--vcf", pre + ".vcf", "--out", pre + ".out"]
+    kw = {}
+    for key, flag in (("min_td", "--min-TD"), ("cap_bq", "--cap-BQ"), ("min_bq", "--min-BQ"), ("min_mq", "--min-MQ"),
+                      ("excl_flag", "--excl-flag"), ("exclude_flag", "--exclude-flag")):
+        if key in extra:
+            args += [flag, str(extra[key])]
+            kw[key] = extra[key]
+    if extra.get("skip_umi"):
+        args.append("--skip-umi")
+        kw["skip_umi"] = True
+    if extra.get("group"):
+        with open(pre + ".grp", "w") as f:
+            f.write("\n".join(bcs[::2] + ["."]) + "\n")
+        args += ["--group-list", pre + ".grp"]
+        kw["group_list"] = set(bcs[::2] + ["."])
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    want = dsc_pileup_py.dsc_pileup(pre + ".bam", pre + ".vcf", **kw)
+    assert len(want["plp"].splitlines()) > 150 // (2 if extra.get("group") else 1)
+    for ext in ("cel", "var", "plp"):
+        assert _gunzip(pre + ".out.%s.gz" % ext) == want[ext], ext
+    if extra.get("skip_umi"):
+        assert not os.path.exists(pre + ".out.umi.gz")
+    else:
+        assert _gunzip(pre + ".out.umi.gz") == want["umi"]
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_demuxlet_sam_join_matches_the_python_restatement(built, tmp_path, seed):
+    """The droplet store `cramore demuxlet --sam` hands to the engine (--gpu-dump-inputs, no GPU) against the Python
+    restatement of cmd_cram_demuxlet.cpp:222-395 on multi-contig gapped alignments: rows in barcode order, SNP ids in
+    the order the VCF cursor met them, reads of an entry in UMI string order, first read of a UMI wins."""
+    from oracle import dsc_pileup_py
+    pre, bcs = _random_alignments(tmp_path, seed, with_samples=True)
+    r = subprocess.run([CRAMORE, "demuxlet", "--sam", pre + ".bam", "--vcf", pre + ".vcf", "--out", pre + ".o", "--min-mac", "0",
+                        "--min-callrate", "0", "--gpu-dump-inputs", pre + ".d"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    want = dsc_pileup_py.dsc_pileup(pre + ".bam", pre + ".vcf", cap_bq=20, demuxlet_mode=True)
+    per_cell = {}
+    for snp, cells in want["snp_umis"].items():
+        for c, umis in cells.items():
+            per_cell.setdefault(c, {})[snp] = [umis[u] for u in sorted(umis)]
+    rows = sorted((b, i) for i, b in enumerate(want["barcodes"]) if i in per_cell)
+    assert (tmp_path / ("r%d.d.barcodes.txt" % seed)).read_text().split() == [b for b, _ in rows]
+    snp_idx, als, bqs, cell_ptr, read_ptr = [], [], [], [0], [0]
+    for _, i in rows:
+        for snp in sorted(per_cell[i]):
+            snp_idx.append(snp)
+            als += [a for a, _ in per_cell[i][snp]]
+            bqs += [q for _, q in per_cell[i][snp]]
+            read_ptr.append(len(als))
+        cell_ptr.append(len(snp_idx))
+    assert len(snp_idx) > 200
+    for name, dt, exp in (("cell_ptr.i64", np.int64, cell_ptr), ("snp_idx.i32", np.int32, snp_idx), ("read_ptr.i64", np.int64, read_ptr),
+                          ("al.u8", np.uint8, als), ("bq.u8", np.uint8, bqs)):
+        assert np.fromfile(pre + ".d." + name, dt).tolist() == exp, name
+    assert len(np.fromfile(pre + ".d.has_gp.u8", np.uint8)) == len(want["snps"])
+
+
+def test_dsc_pileup_output_feeds_demuxlet_plp(built, tmp_path):
+    """BAM -> `cramore dsc-pileup` -> `cramore demuxlet --plp`: the same engine inputs as from the digital pileup the
+    generator writes directly (reads of an entry compared as multisets: the UMI strings, hence the read order inside
+    an entry, are not the generator's).  --sm restricts the VCF to one sample, which switches the allele frequency
+    of the .var.gz file from INFO/AF to that sample's genotype (bcf_filtered_reader.cpp:875-878)."""
+    from cramore_b200.synth import make_dataset, write_bam, write_plp, write_vcf
+    d = make_dataset("C1", nbcs=30, nsnps=120, rbar=80, nv=4, seed=5, with_barcodes=True)
+    pre = str(tmp_path / "in")
+    write_plp(d, pre)
+    write_vcf(d, pre + ".vcf")
+    write_bam(d, pre + ".bam", duplicate_every=4)
+    r = subprocess.run([CRAMORE, "dsc-pileup", "--sam", pre + ".bam", "--vcf", pre + ".vcf", "--out", pre + ".dsc", "--sm",
+                        d["sample_ids"][0]], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    var = _gunzip(pre + ".dsc.var.gz").splitlines()[1:]
+    geno0 = np.asarray(d["geno"])[:, 0]
+    assert [ln.split("\t")[5] for ln in var[:len(geno0)]] == ["%.5f" % (g / 2.0) for g in geno0[:len(var)]]
+    assert len(var) == d["nsnps"]
+    dumps = {}
+    for mode, prefix in (("dsc", pre + ".dsc"), ("gen", pre)):
+        r = subprocess.run([CRAMORE, "demuxlet", "--plp", prefix, "--vcf", pre + ".vcf", "--out", str(tmp_path / "o"),
+                            "--gpu-dump-inputs", str(tmp_path / mode)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        dumps[mode] = {n: np.fromfile(str(tmp_path / (mode + "." + n)), dt) for n, dt in (
+            ("cell_ptr.i64", np.int64), ("snp_idx.i32", np.int32), ("read_ptr.i64", np.int64), ("al.u8", np.uint8),
+            ("bq.u8", np.uint8), ("gp.f32", np.float32), ("snp_err.f64", np.float64), ("has_gp.u8", np.uint8),
+            ("row_int_id.i32", np.int32))}
+        dumps[mode]["bcs"] = (tmp_path / (mode + ".barcodes.txt")).read_text()
+    a, b = dumps["dsc"], dumps["gen"]
+    for n in ("cell_ptr.i64", "snp_idx.i32", "read_ptr.i64", "gp.f32", "snp_err.f64", "has_gp.u8", "row_int_id.i32", "bcs"):
+        assert np.array_equal(a[n], b[n]), n
+    rp = a["read_ptr.i64"]
+    for e in range(len(rp) - 1):
+        assert sorted(zip(a["al.u8"][rp[e]:rp[e + 1]], a["bq.u8"][rp[e]:rp[e + 1]])) == \
+               sorted(zip(b["al.u8"][rp[e]:rp[e + 1]], b["bq.u8"][rp[e]:rp[e + 1]])), e
