@@ -135,7 +135,7 @@ int ccu_destroy(ccu_handle* h) {
   cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->d_alpha, &h->d_ptab, &h->d_half, &h->d_phred, &h->d_gpf, &h->d_err, &h->d_hasgp,
                     &h->d_avg, &h->d_G, &h->d_cell_ptr, &h->d_snp_idx, &h->d_read_ptr, &h->d_al, &h->d_bq,
-                    &h->d_tiles, &h->d_vaff, &h->d_eclass, &h->d_vent, &h->d_vsnp, &h->d_vcnt, &h->d_sng, &h->d_fmat, &h->d_pm, &h->d_pe, &h->d_maxbq, &h->d_partials, &h->d_results, &h->d_dbg,
+                    &h->d_tiles, &h->d_vaff, &h->d_eclass, &h->d_vent, &h->d_vsnp, &h->d_vcnt, &h->d_sng, &h->d_fmat, &h->d_pm, &h->d_pe, &h->d_maxbq, &h->d_partials, &h->d_results, &h->d_dbg, &h->d_flag,
                     &h->d_sink};
   for (DevBuf* b : bufs) b->release();
   ccu_fmx_release(h);
@@ -293,6 +293,7 @@ int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const
   h->nnz = nnz;
   h->nreads = nreads;
   h->ran = false;
+  h->validated = false;
   return 0;
 }
 
@@ -305,6 +306,23 @@ int ccu_demux_run(ccu_handle* h) {
   const ccu::ScorePlan plan = ccu::make_score_plan(h->nv, h->nA, h->alpha.data());
   int grid = 0;
   cudaStream_t st = h->stream;
+  int nvalidate = 0;
+  if (!h->validated) {
+    nvalidate = (h->nbcs > 0 || h->nnz > 0) ? 1 : 0;
+    // The kernels index the genotype matrix and the read arrays with what the caller handed in: check it on the
+    // device first (pointer arrays non-decreasing and closed, SNP ids inside the genotype matrix) and refuse to run
+    // rather than read out of bounds.  One pass over the index arrays and one 4-byte read-back per upload.
+    uint32_t bad = 0;
+    CCU_CUDA(h, h->d_flag.reserve(16));
+    CCU_CUDA(h, cudaMemsetAsync(h->d_flag.p, 0, 4, st));
+    CCU_CUDA(h, ccu::launch_validate(d, h->nreads, h->d_flag.as<uint32_t>(), st));
+    CCU_CUDA(h, cudaMemcpyAsync(&bad, h->d_flag.p, 4, cudaMemcpyDeviceToHost, st));
+    CCU_CUDA(h, cudaStreamSynchronize(st));
+    if (bad)
+      return fail(h, "ccu_demux_run: malformed droplet store (%s%s%s)", (bad & 1) ? "cell_ptr not non-decreasing from 0 to nnz; " : "",
+                  (bad & 2) ? "SNP id outside [0, nsnps); " : "", (bad & 4) ? "read_ptr not non-decreasing from 0 to the number of reads" : "");
+    h->validated = true;
+  }
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_RUN0], st));
   CCU_CUDA(h, ccu::launch_tile(d, false, st));
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_TILE], st));
@@ -316,7 +334,7 @@ int ccu_demux_run(ccu_handle* h) {
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_SCORE], st));
   CCU_CUDA(h, ccu::launch_finalize(d, plan, st));
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_FIN], st));
-  h->tm.launches = (h->nbcs > 0 ? 4 : 0) + (h->nnz > 0 ? 2 : 0);
+  h->tm.launches = (h->nbcs > 0 ? 4 : 0) + (h->nnz > 0 ? 2 : 0) + nvalidate;
   h->tm.score_ctas = grid;
   h->tm.score_items = h->nbcs * plan.items_per_cell;
   h->ran = true;

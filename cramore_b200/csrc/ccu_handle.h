@@ -69,7 +69,8 @@ struct ccu_handle {
   bool ran = false;
   DevBuf d_cell_ptr, d_snp_idx, d_read_ptr, d_al, d_bq;
   DevBuf d_tiles, d_vaff, d_eclass, d_vent, d_vsnp, d_vcnt, d_sng, d_fmat, d_pm, d_pe, d_maxbq, d_partials, d_results,
-      d_dbg, d_sink;
+      d_dbg, d_sink, d_flag;
+  bool validated = false;  // the uploaded CSR passed demux_validate_kernel
 
   // freemuxlet (owned by ccu_fmx_api.cu)
   FmxState* fmx = nullptr;

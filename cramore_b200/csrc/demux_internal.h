@@ -87,6 +87,7 @@ ScorePlan make_score_plan(int nv, int nA, const double* alpha);
 cudaError_t launch_gp_prepare(const float* gp_f32, const double* snp_err, const uint8_t* has_gp,
                               int64_t nsnps, int nv, int nvp, double* avg_tmp, double* G,
                               cudaStream_t st);
+cudaError_t launch_validate(const DemuxDev& d, int64_t nreads, uint32_t* flag, cudaStream_t st);
 cudaError_t launch_tile(const DemuxDev& d, bool all_entries, cudaStream_t st);
 cudaError_t launch_compact(const DemuxDev& d, cudaStream_t st);
 cudaError_t launch_sample(const DemuxDev& d, cudaStream_t st);

@@ -371,6 +371,38 @@ __global__ void __launch_bounds__(kTileWarps * 32)
   }
 }
 
+// ---- input check: the droplet store is caller data and every later kernel indexes with it.  bit 0: cell_ptr is
+// not a non-decreasing walk from 0 to nnz; bit 1: a SNP id outside the genotype matrix; bit 2: read_ptr is not a
+// non-decreasing walk from 0 to nreads.  Pure streaming over the three index arrays.
+__global__ void __launch_bounds__(256)
+    demux_validate_kernel(int64_t nbcs, int64_t nnz, int64_t nreads, int64_t nsnps, const int64_t* __restrict__ cell_ptr,
+                          const int32_t* __restrict__ snp_idx, const int64_t* __restrict__ read_ptr,
+                          uint32_t* __restrict__ flag) {
+  uint32_t bad = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbcs; i += stride) {
+    const int64_t a = cell_ptr[i], b = cell_ptr[i + 1];
+    if (a > b || a < 0 || b > nnz || (i == 0 && a != 0) || (i == nbcs - 1 && b != nnz)) bad |= 1u;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+    const int32_t s = snp_idx[i];
+    if (s < 0 || s >= nsnps) bad |= 2u;
+    const int64_t a = read_ptr[i], b = read_ptr[i + 1];
+    if (a > b || a < 0 || b > nreads || (i == 0 && a != 0) || (i == nnz - 1 && b != nreads)) bad |= 4u;
+  }
+  bad = __reduce_or_sync(0xffffffffu, bad);
+  if (bad && (threadIdx.x & 31) == 0) atomicOr(flag, bad);
+}
+
+cudaError_t launch_validate(const DemuxDev& d, int64_t nreads, uint32_t* flag, cudaStream_t st) {
+  const int64_t n = d.nbcs > d.nnz ? d.nbcs : d.nnz;
+  if (n == 0) return cudaSuccess;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  demux_validate_kernel<<<(unsigned)blocks, 256, 0, st>>>(d.nbcs, d.nnz, nreads, d.nsnps, d.cell_ptr, d.snp_idx, d.read_ptr, flag);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_tile(const DemuxDev& d, bool all_entries, cudaStream_t st) {
   cudaError_t e0 = cudaMemsetAsync(d.maxbq, 0, sizeof(int32_t), st);
   if (e0 != cudaSuccess) return e0;

@@ -151,6 +151,16 @@ def test_cli_freemuxlet_initial_clustering(built, tmp_path, name):
     c0 = gzip.open(str(tmp_path / "out.clust0.samples.gz"), "rt").read().splitlines()
     assert c0[0] == "INT_ID\tBARCODE\tCLUST0"
     assert [int(ln.split("\t")[2]) for ln in c0[1:]] == fx["clust0"]
+    if fx["init"] is None:
+        # <out>.ldist.gz: the pair rows of the greedy pass in the reference's order (dense, zero rows included)
+        ld = gzip.open(str(tmp_path / "out.ldist.gz"), "rt").read().splitlines()
+        assert ld[0] == "ID1\tID2\tNSNP\tREAD1\tREAD2\tREADMIN\tLLK0\tLLK2\tLDIFF\tDIFF.SNP"
+        want = ["%d\t%d\t%d\t%d\t%d\t%d\t%.2f\t%.2f\t%.2f\t%.4f" % (tuple(int(x) for x in r[:6]) + tuple(float(x) for x in r[6:]))
+                for r in fx["ldist_raw"]]
+        assert len(ld) - 1 == len(want) > 500
+        for a, b in zip(ld[1:], want):
+            assert a == b or _numeric_row_match(a, b), (a, b)
+        assert sum(a == b for a, b in zip(ld[1:], want)) >= 0.99 * len(want)
     mine = gzip.open(str(tmp_path / "out.clust1.samples.gz"), "rt").read().splitlines(keepends=True)
     ref = fx["samples_text"].splitlines(keepends=True)
     assert len(mine) == len(ref) and mine[0] == ref[0]

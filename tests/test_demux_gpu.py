@@ -168,3 +168,84 @@ def test_scoring_in_memory_bounded_ranges(engine, monkeypatch):
     assert engine.timings()["launches"] > 3 * launches_whole  # several ranges were run
     monkeypatch.delenv("CCU_DEMUX_MAX_SCRATCH_MB")
     assert np.array_equal(whole, parts)
+
+
+def test_single_sample_and_widest_pool(engine):
+    """nv = 1 (no doublet hypothesis exists: every doublet field keeps the reference's start values) and the C3 shape
+    (256 samples, 11 alphas: 65,280 ordered pairs per alpha) on two droplets."""
+    d = make_dataset("C1", nbcs=6, nsnps=300, nv=1, rbar=40)
+    res = engine_run(engine, d)
+    _, ref, ref_llk, _ = oracle_run(d, want_llk=True)
+    assert_results_match(res, ref, d["alphas"], ref_llk)
+    for f in ("dBest1", "dBest2", "dBestA", "dNext1", "dNext2", "dNextA"):
+        assert np.array_equal(res[f], ref[f]), f
+    d = make_dataset("C3", nbcs=2, nsnps=5000)
+    assert d["nv"] == 256 and len(d["alphas"]) == 11
+    res = engine_run(engine, d)
+    _, ref, ref_llk, _ = oracle_run(d, want_llk=True)
+    assert_llk_match(engine.llk(), ref_llk)
+    assert_results_match(res, ref, d["alphas"], ref_llk)
+    assert_calls_match(res, ref, d["nv"], d["alphas"])
+
+
+def test_exact_ties_follow_the_scan_order(engine):
+    """Samples with identical genotypes tie EXACTLY in every likelihood: best / next must be the ones the reference's
+    strict '<' scans keep (cmd_cram_demuxlet.cpp:827-837, :883-906) -- the first in scan order wins, the runner-up
+    is the next one met -- for singlets and for doublets, with and without alpha = 0.5 in the grid."""
+    for alphas in ([0, 0.5], [0, 0.2, 0.4]):
+        d = make_dataset("C1", nbcs=10, nsnps=400, nv=6, rbar=80, seed=77)
+        gp = np.array(d["gp"], np.float32).reshape(-1, 6, 3)
+        gp[:, 3] = gp[:, 1]   # sample 3 == sample 1
+        gp[:, 5] = gp[:, 1]   # sample 5 == sample 1
+        gp[:, 4] = gp[:, 0]   # sample 4 == sample 0
+        d["gp"] = gp.reshape(np.asarray(d["gp"]).shape)
+        d["alphas"] = np.asarray(alphas, np.float64)
+        res = engine_run(engine, d)
+        _, ref, ref_llk, _ = oracle_run(d, want_llk=True)
+        assert_llk_match(engine.llk(), ref_llk)
+        for f in ("sBest", "sNext"):
+            assert np.array_equal(res[f], ref[f]), (alphas, f)
+        mirror = 0
+        for i in range(len(ref)):
+            for tag in ("Best", "Next"):
+                a = tuple(int(res["d%s%s" % (tag, x)][i]) for x in "12A")
+                b = tuple(int(ref["d%s%s" % (tag, x)][i]) for x in "12A")
+                if a != b:  # only the mirror orientation of an alpha = 0.5 pair, which the reference picks by rounding
+                    assert d["alphas"][a[2]] == 0.5 and a[2] == b[2] and (a[0], a[1]) == (b[1], b[0]), (alphas, i, tag, a, b)
+                    mirror += 1
+        assert mirror == 0 or 0.5 in alphas
+        np.testing.assert_allclose(res["dblBestLLK"], ref["dblBestLLK"], rtol=1e-9)
+        np.testing.assert_allclose(res["dblNextLLK"], ref["dblNextLLK"], rtol=1e-9)
+
+
+def test_twenty_thousand_reads_on_one_snp(engine):
+    """One (droplet, SNP) entry with 20,000 reads: the per-read product of cmd_cram_demuxlet.cpp:655-700 is renormalised
+    by its running maximum in the reference; the tile kernel must survive the same depth without underflow."""
+    rng = np.random.default_rng(3)
+    d = make_dataset("C1", nbcs=1, nsnps=50, nv=4, rbar=5)
+    n = 20000
+    al = (rng.random(n) < 0.5).astype(np.uint8)
+    d.update(cell_ptr=np.asarray([0, 2]), snp_idx=np.asarray([7, 9], np.int32), read_ptr=np.asarray([0, n, n + 1]),
+             al=np.concatenate([al, [1]]).astype(np.uint8), bq=np.concatenate([rng.integers(13, 21, n), [20]]).astype(np.uint8))
+    res = engine_run(engine, d)
+    _, ref, ref_llk, tiles = oracle_run(d, want_llk=True, want_tiles=True)
+    assert np.array_equal(engine.tiles(), tiles)
+    assert_llk_match(engine.llk(), ref_llk)
+    assert_results_match(res, ref, d["alphas"], ref_llk)
+
+
+def test_argument_errors_are_reported_not_computed(engine):
+    from cramore_b200.engine import EngineError
+    d = make_dataset("C1", nbcs=2, nsnps=50, nv=3, rbar=10)
+    with pytest.raises(EngineError):
+        engine.configure(3, [0.5], 0.5)          # one alpha: the prior divides by nA - 1 (:794)
+    with pytest.raises(EngineError):
+        engine.configure(3, [0.1, 0.5], 0.5)     # element 0 must be 0 (SURVEY 8b)
+    engine.configure(3, [0, 0.5], 0.5)
+    engine.set_genotypes(d["gp"], d["snp_err"], None)
+    bad = np.asarray(d["snp_idx"]).copy()
+    bad[0] = 50                                   # SNP id out of range
+    with pytest.raises(EngineError):
+        engine.score(d["cell_ptr"], bad, d["read_ptr"], d["al"], d["bq"])
+    res = engine.score(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"])   # the handle is still usable
+    assert len(res) == 2
