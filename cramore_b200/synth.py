@@ -50,7 +50,7 @@ def make_droplets(rng, geno, nbcs, rbar, doublet_rate, min_bq=13, cap_bq=20, chu
     nsnps, nv = geno.shape
     is_dbl = rng.random(nbcs) < doublet_rate
     s1 = rng.integers(0, nv, nbcs)
-    s2 = (s1 + 1 + rng.integers(0, nv - 1, nbcs)) % nv
+    s2 = (s1 + 1 + rng.integers(0, max(nv - 1, 1), nbcs)) % nv
     s2 = np.where(is_dbl, s2, s1)
     nreads = rng.poisson(rbar, nbcs).astype(np.int64)
     R = int(nreads.sum())

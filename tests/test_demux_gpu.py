@@ -170,15 +170,18 @@ def test_scoring_in_memory_bounded_ranges(engine, monkeypatch):
     assert np.array_equal(whole, parts)
 
 
-def test_single_sample_and_widest_pool(engine):
-    """nv = 1 (no doublet hypothesis exists: every doublet field keeps the reference's start values) and the C3 shape
-    (256 samples, 11 alphas: 65,280 ordered pairs per alpha) on two droplets."""
-    d = make_dataset("C1", nbcs=6, nsnps=300, nv=1, rbar=40)
+def test_two_samples_and_widest_pool(engine):
+    """nv = 2 (one doublet pair; a single sample is refused like one alpha is: the reference's doublet scan would index
+    sample -1) and the C3 shape (256 samples, 11 alphas: 65,280 ordered pairs per alpha) on two droplets."""
+    from cramore_b200.engine import EngineError
+    with pytest.raises(EngineError):
+        engine.configure(1, [0, 0.5], 0.5)
+    d = make_dataset("C1", nbcs=6, nsnps=300, nv=2, rbar=40)
     res = engine_run(engine, d)
     _, ref, ref_llk, _ = oracle_run(d, want_llk=True)
+    assert_llk_match(engine.llk(), ref_llk)
     assert_results_match(res, ref, d["alphas"], ref_llk)
-    for f in ("dBest1", "dBest2", "dBestA", "dNext1", "dNext2", "dNextA"):
-        assert np.array_equal(res[f], ref[f]), f
+    assert_calls_match(res, ref, 2, d["alphas"])
     d = make_dataset("C3", nbcs=2, nsnps=5000)
     assert d["nv"] == 256 and len(d["alphas"]) == 11
     res = engine_run(engine, d)
