@@ -230,6 +230,41 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local):
+    """Run this process (and therefore place the pinned host buffers it allocates next) on the CPUs of the NUMA node
+    the GPU hangs off: host->device copies from the far socket run at about half the PCIe rate.  Returns a short
+    description for the JSON line; a no-op where sysfs / NVML do not say (or BENCH_NO_NUMA_BIND=1)."""
+    if os.environ.get("BENCH_NO_NUMA_BIND") == "1":
+        return "off (BENCH_NO_NUMA_BIND=1)"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local < len(ids) and ids[local].isdigit():
+                idx = int(ids[local])
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s" % (dom[-4:].lower(), rest.lower())
+        node = int(open(path + "/numa_node").read().strip())
+        if node < 0:
+            return "single node (numa_node=-1)"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "node %d has no allowed CPU" % node
+        os.sched_setaffinity(0, cpus)
+        return "numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:  # noqa: BLE001 -- placement is an optimisation, never a reason to fail the bench
+        return "unavailable (%s)" % type(e).__name__
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -246,6 +281,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the engine has no CPU fallback")
     torch.cuda.set_device(local)
+    host_affinity = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -292,9 +328,19 @@ def main():
     eng.set_stream(stream.cuda_stream)
     eng.configure(d["nv"], d["alphas"], 0.5)
 
+    e2e_parts = [0.0, 0.0]  # seconds inside set_genotypes / score (host wall clock)
+    e2e_dev = [0.0, 0.0, 0.0, 0.0]  # the engine's own CUDA-event times of the same calls (ms)
+
     def e2e_step():
+        t_a = time.perf_counter()
         eng.set_genotypes(host["gp"], host["snp_err"])
+        t_b = time.perf_counter()
         eng.score(host["cell_ptr"], host["snp_idx"], host["read_ptr"], host["al"], host["bq"], out)
+        e2e_parts[0] += t_b - t_a
+        e2e_parts[1] += time.perf_counter() - t_b
+        tm = eng.timings()
+        for i, k in enumerate(("ms_genotypes", "ms_h2d", "ms_run", "ms_d2h")):
+            e2e_dev[i] += tm[k]
 
     for _ in range(max(args.warmup, 3)):
         e2e_step()
@@ -330,6 +376,8 @@ def main():
 
     # ---- leg 2: end to end through the host-buffer C ABI
     barrier()
+    e2e_parts[0] = e2e_parts[1] = 0.0
+    e2e_dev[:] = [0.0, 0.0, 0.0, 0.0]
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
@@ -405,6 +453,10 @@ def main():
                 "config": config_dict(d, world), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * e2e_s / args.steps,
+                        "ms_set_genotypes_call": 1e3 * e2e_parts[0] / args.steps,
+                        "ms_score_call": 1e3 * e2e_parts[1] / args.steps, "host_affinity": host_affinity,
+                        "device_ms_inside": {k: v / args.steps for k, v in zip(
+                            ("genotype_mix_kernels", "csr_h2d", "kernels", "result_d2h"), e2e_dev)},
                         "includes": "genotype matrix upload + mixing, CSR upload, all kernels, result download"},
                 "gpu_launches": launches, "roofline": roofline, "roofline_k1": roofline_k1,
                 "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": 1, "kind": cpu_kind,

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "ccu_handle.h"
@@ -177,6 +178,7 @@ int ccu_demux_configure(ccu_handle* h, int32_t nv, int32_t nalpha, const double*
   if ((double)nv * nv * nalpha >= 2147483647.0) return fail(h, "ccu_demux_configure: nv*nv*nalpha overflows int32");
   CCU_CUDA(h, cudaSetDevice(h->device));
   h->nv = nv;
+  h->scratch_fits = 0.0;
   h->nvp = (nv + 31) / 32 * 32;
   h->nA = nalpha;
   h->doublet_prior = doublet_prior;
@@ -388,21 +390,41 @@ int ccu_demux_score(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const 
   if (!h) return 1;
   if (!h->configured) return fail(h, "ccu_demux_score: call ccu_demux_configure first");
   if (nbcs < 0 || !cell_ptr) return fail(h, "ccu_demux_score: bad arguments");
+  const auto t_enter = std::chrono::steady_clock::now();
   // Droplets are independent: when the scratch of the whole store does not fit into the device memory that is
   // free right now, the store is scored in contiguous droplet ranges that do (CCU_DEMUX_MAX_SCRATCH_MB caps the
   // budget, for tests).
   CCU_CUDA(h, cudaSetDevice(h->device));
-  size_t free_b = 0, total_b = 0;
-  CCU_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
-  const size_t held = h->d_tiles.cap + h->d_fmat.cap + h->d_vaff.cap + h->d_vent.cap + h->d_partials.cap;  // reusable
-  double budget = 0.85 * ((double)free_b + (double)held);
-  if (const char* cap = getenv("CCU_DEMUX_MAX_SCRATCH_MB")) budget = std::min(budget, atof(cap) * 1048576.0);
   const int64_t nnz = cell_ptr[nbcs] - cell_ptr[0];
   const int64_t nreads = (nnz > 0 && read_ptr) ? read_ptr[nnz] - read_ptr[0] : 0;
-  if (nbcs == 0 || demux_scratch_bytes(h, nbcs, nnz, nreads) <= budget) {
+  const double need = (nbcs == 0) ? 0.0 : demux_scratch_bytes(h, nbcs, nnz, nreads);
+  const char* cap = getenv("CCU_DEMUX_MAX_SCRATCH_MB");
+  // A store no larger than one that already ran in one piece on this handle fits again (its buffers are still
+  // held): the free-memory query -- a driver call whose latency is not ours to bound -- is skipped for it.
+  double budget = h->scratch_fits;
+  if (cap || need > budget) {
+    size_t free_b = 0, total_b = 0;
+    CCU_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
+    const size_t held = h->d_tiles.cap + h->d_fmat.cap + h->d_vaff.cap + h->d_vent.cap + h->d_partials.cap;  // reusable
+    budget = 0.85 * ((double)free_b + (double)held);
+    if (cap) budget = std::min(budget, atof(cap) * 1048576.0);
+  }
+  if (nbcs == 0 || need <= budget) {
+    const bool trace = getenv("CCU_TRACE") != nullptr;  // host wall clock of the phases, to stderr
+    const auto t0 = std::chrono::steady_clock::now();
     if (int rc = ccu_demux_upload(h, nbcs, cell_ptr, snp_idx, read_ptr, al, bq)) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     if (int rc = ccu_demux_run(h)) return rc;
-    return ccu_demux_download(h, out);
+    const auto t2 = std::chrono::steady_clock::now();
+    const int rc = ccu_demux_download(h, out);
+    if (rc == 0 && !cap && need > h->scratch_fits) h->scratch_fits = need;
+    if (trace) {
+      const auto t3 = std::chrono::steady_clock::now();
+      auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+      fprintf(stderr, "[ccu] score: mem-info %.3f ms, upload %.3f ms, run (launch) %.3f ms, wait+download %.3f ms\n",
+              ms(t_enter, t0), ms(t0, t1), ms(t1, t2), ms(t2, t3));
+    }
+    return rc;
   }
   if (cell_ptr[0] != 0 || (nnz > 0 && (!snp_idx || !read_ptr || read_ptr[0] != 0)))
     return fail(h, "ccu_demux_score: bad CSR arrays");
