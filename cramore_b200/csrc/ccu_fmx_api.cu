@@ -32,7 +32,20 @@ struct FmxState {
   cudaEvent_t ev[2] = {nullptr, nullptr};
   ccu_fmx_timings tm = {};
   FmxPairs* pairs = nullptr;
+  // peer-memory exchange: every rank's posterior / assignment array (CUDA IPC mappings; [peer_rank] is our own)
+  ccu::FmxPeers peers = {};
+  int32_t peer_rank = -1;
+  void close_peers() {
+    for (int r = 0; r < peers.n; ++r)
+      if (r != peer_rank) {
+        if (peers.post[r]) cudaIpcCloseMemHandle(peers.post[r]);
+        if (peers.assign[r]) cudaIpcCloseMemHandle(peers.assign[r]);
+      }
+    peers = {};
+    peer_rank = -1;
+  }
   void release() {
+    close_peers();
     ccu_fmx_pairs_release(pairs);
     DevBuf* all[] = {&cell_ptr, &snp_idx, &read_ptr, &al, &bq, &af, &gl, &cnt, &logdenom, &csc_ptr, &csc_cell,
                      &csc_gl, &csc_cnt, &assign, &stats, &cgp, &llk, &results, &scan, &scratch};
@@ -156,6 +169,7 @@ int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* ce
   if (nreads < 0 || (nreads > 0 && (!al || !bq))) return ccu_fail(h, "ccu_fmx_upload: bad read arrays");
   CCU_CUDA(h, cudaSetDevice(h->device));
   FmxState* f = h->fmx;
+  f->close_peers();  // the mapped arrays may be re-allocated below
   cudaStream_t st = h->stream;
   f->nbcs = nbcs;
   f->nsnps = nsnps;
@@ -363,6 +377,83 @@ int ccu_fmx_estep_post_dev(ccu_handle* h) {
   cudaEventRecord(f->ev[1], h->stream);
   f->tm.launches += 2;  // E-step, decision
   f->have_estep = true;
+  return 0;
+}
+
+// ---- peer-memory exchange over NVLink (one process per GPU) ----
+int ccu_fmx_peer_handles(ccu_handle* h, void* out) {
+  if (int rc = need(h, true, "ccu_fmx_peer_handles")) return rc;
+  FmxState* f = h->fmx;
+  if (!out) return ccu_fail(h, "ccu_fmx_peer_handles: NULL output");
+  if (!f->cgp.p || !f->assign.p) return ccu_fail(h, "ccu_fmx_peer_handles: call ccu_fmx_set_shard first");
+  static_assert(sizeof(cudaIpcMemHandle_t) == CCU_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  cudaIpcMemHandle_t hd[2];
+  CCU_CUDA(h, cudaIpcGetMemHandle(&hd[0], f->cgp.p));
+  CCU_CUDA(h, cudaIpcGetMemHandle(&hd[1], f->assign.p));
+  memcpy(out, hd, sizeof(hd));
+  return 0;
+}
+
+int ccu_fmx_peer_open(ccu_handle* h, int32_t nranks, int32_t rank, const void* handles) {
+  if (int rc = need(h, true, "ccu_fmx_peer_open")) return rc;
+  FmxState* f = h->fmx;
+  if (nranks < 1 || nranks > ccu::kMaxPeers || rank < 0 || rank >= nranks || !handles)
+    return ccu_fail(h, "ccu_fmx_peer_open: bad arguments (at most %d ranks)", ccu::kMaxPeers);
+  if (!f->cgp.p || !f->assign.p) return ccu_fail(h, "ccu_fmx_peer_open: call ccu_fmx_set_shard first");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  f->close_peers();
+  const cudaIpcMemHandle_t* hd = static_cast<const cudaIpcMemHandle_t*>(handles);
+  f->peer_rank = rank;
+  f->peers.n = nranks;
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) {
+      f->peers.post[r] = f->cgp.as<double>();
+      f->peers.assign[r] = f->assign.as<int32_t>();
+      continue;
+    }
+    void *pp = nullptr, *pa = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&pp, hd[2 * r], cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pa, hd[2 * r + 1], cudaIpcMemLazyEnablePeerAccess);
+    f->peers.post[r] = static_cast<double*>(pp);
+    f->peers.assign[r] = static_cast<int32_t*>(pa);
+    if (e != cudaSuccess) {
+      f->peers.n = r + 1;
+      f->close_peers();
+      return ccu_fail(h, "ccu_fmx_peer_open: cannot map the arrays of rank %d: %s", r, cudaGetErrorString(e));
+    }
+  }
+  return 0;
+}
+
+int ccu_fmx_peer_close(ccu_handle* h) {
+  if (!h || !h->fmx) return 1;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->fmx->close_peers();
+  return 0;
+}
+
+int ccu_fmx_posteriors_push_dev(ccu_handle* h, int32_t apply_geno_error) {
+  if (int rc = need(h, true, "ccu_fmx_posteriors_push")) return rc;
+  FmxState* f = h->fmx;
+  if (!f->have_stats) return ccu_fail(h, "ccu_fmx_posteriors_push: no cluster statistics yet (run ccu_fmx_mstep first)");
+  if (f->peers.n < 1) return ccu_fail(h, "ccu_fmx_posteriors_push: call ccu_fmx_peer_open first");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  CCU_CUDA(h, ccu::launch_fmx_cgp_push(fmx_view(h), apply_geno_error, f->peers, h->stream));
+  f->tm.launches += 1;
+  f->have_post = true;
+  return 0;
+}
+
+int ccu_fmx_assign_push_dev(ccu_handle* h) {
+  if (int rc = need(h, true, "ccu_fmx_assign_push")) return rc;
+  FmxState* f = h->fmx;
+  if (!f->have_estep) return ccu_fail(h, "ccu_fmx_assign_push: no E-step has run");
+  if (f->peers.n < 1) return ccu_fail(h, "ccu_fmx_assign_push: call ccu_fmx_peer_open first");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  CCU_CUDA(h, ccu::launch_fmx_assign_push(fmx_view(h), f->peers, h->stream));
+  f->tm.launches += 1;
   return 0;
 }
 

@@ -63,6 +63,18 @@ cudaError_t launch_fmx_build_csc(const FmxDev& d, const int32_t* sorted_snp, con
                                  const int32_t* ent_cell, cudaStream_t st);
 cudaError_t launch_fmx_mstep(const FmxDev& d, cudaStream_t st);
 cudaError_t launch_fmx_cgp(const FmxDev& d, int apply_geno_error, bool slab_only, cudaStream_t st);
+// Peer-memory exchange (one process per GPU, NVLink / NVSwitch): the posterior and assignment arrays of every rank,
+// opened through CUDA IPC.  launch_fmx_cgp_push computes this rank's SNP slab of the posteriors and stores every
+// value straight into all ranks' arrays (its own included) -- the all-gather happens inside the producing kernel;
+// launch_fmx_assign_push copies this rank's droplet range of the assignment vector to all ranks.
+constexpr int kMaxPeers = 16;
+struct FmxPeers {
+  double* post[kMaxPeers];
+  int32_t* assign[kMaxPeers];
+  int32_t n;
+};
+cudaError_t launch_fmx_cgp_push(const FmxDev& d, int apply_geno_error, const FmxPeers& peers, cudaStream_t st);
+cudaError_t launch_fmx_assign_push(const FmxDev& d, const FmxPeers& peers, cudaStream_t st);
 cudaError_t launch_fmx_estep(const FmxDev& d, cudaStream_t st);
 // int32 count of droplets whose (type, jBest, kBest) differ between two result arrays
 // counts bitwise differences between the shared-reciprocal division of the pileup kernels and __ddiv_rn

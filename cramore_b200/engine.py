@@ -46,7 +46,8 @@ ABI_SYMBOLS = [
     "ccu_fmx_assign_dev", "ccu_fmx_mstep_dev", "ccu_fmx_estep_dev", "ccu_fmx_download_results", "ccu_fmx_run_em",
     "ccu_fmx_get_timings", "ccu_fmx_selftest_division", "ccu_fmx_post_dev", "ccu_fmx_posteriors_dev",
     "ccu_fmx_estep_post_dev", "ccu_fmx_pair_distances", "ccu_fmx_get_pair_distances", "ccu_fmx_initial_clusters",
-    "ccu_fmx_greedy_clusters", "ccu_fmx_get_voting_pairs",
+    "ccu_fmx_greedy_clusters", "ccu_fmx_get_voting_pairs", "ccu_fmx_peer_handles", "ccu_fmx_peer_open",
+    "ccu_fmx_peer_close", "ccu_fmx_posteriors_push_dev", "ccu_fmx_assign_push_dev",
 ]
 
 
@@ -234,6 +235,7 @@ class FreemuxEngine(DemuxEngine):
         af = np.ascontiguousarray(af, np.float64)
         self.nbcs, self.nnz, self.nsnps = len(cp) - 1, int(cp[-1]), len(af)
         self.cell_begin, self.cell_end = 0, self.nbcs
+        self._peer_world = None  # peer mappings belong to the arrays of one upload
         self._check(self.lib.ccu_fmx_upload(self.h, C.c_int64(self.nbcs), C.c_int64(self.nsnps), _ptr(cp), _ptr(si),
                                             _ptr(rp), _ptr(a), _ptr(q), _ptr(af)))
 
@@ -295,6 +297,30 @@ class FreemuxEngine(DemuxEngine):
 
     def estep_post_dev(self):
         self._check(self.lib.ccu_fmx_estep_post_dev(self.h))
+
+    # ---- peer-memory exchange (CUDA IPC over NVLink), see include/cramore_cuda.h ----
+    IPC_BYTES = 2 * 64
+
+    def peer_handles(self):
+        buf = C.create_string_buffer(self.IPC_BYTES)
+        self._check(self.lib.ccu_fmx_peer_handles(self.h, buf))
+        return buf.raw
+
+    def peer_open(self, rank, all_handles):
+        """all_handles: the peer_handles() bytes of every rank, in rank order."""
+        blob = b"".join(all_handles)
+        if len(blob) != self.IPC_BYTES * len(all_handles):
+            raise ValueError("peer_open: every rank contributes %d bytes" % self.IPC_BYTES)
+        self._check(self.lib.ccu_fmx_peer_open(self.h, C.c_int32(len(all_handles)), C.c_int32(rank), blob))
+
+    def peer_close(self):
+        self._check(self.lib.ccu_fmx_peer_close(self.h))
+
+    def posteriors_push_dev(self, apply_geno_error=False):
+        self._check(self.lib.ccu_fmx_posteriors_push_dev(self.h, C.c_int32(1 if apply_geno_error else 0)))
+
+    def assign_push_dev(self):
+        self._check(self.lib.ccu_fmx_assign_push_dev(self.h))
 
     def mstep_dev(self):
         self._check(self.lib.ccu_fmx_mstep_dev(self.h))

@@ -71,8 +71,25 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
     sync = sync or (lambda: None)
     if exchange is None:
         exchange = "posteriors" if post is not None else "stats"
-    if exchange not in ("posteriors", "stats") or (exchange == "posteriors" and post is None):
-        raise ValueError("exchange must be 'stats' or 'posteriors' (the latter needs the posterior tensor)")
+    if exchange not in ("posteriors", "stats", "push") or (exchange == "posteriors" and post is None):
+        raise ValueError("exchange must be 'stats', 'posteriors' (needs the posterior tensor) or 'push'")
+    if exchange == "push" and not multi:
+        exchange = "posteriors" if post is not None else "stats"
+    if exchange == "push":
+        # the mappings persist on the engine (they are tied to its arrays, not to one EM run)
+        key = (dist.get_world_size(group), rank)
+        if getattr(eng, "_peer_world", None) != key:
+            mine = eng.peer_handles()
+            everyone = [None] * key[0]
+            dist.all_gather_object(everyone, mine, group=group)
+            eng.peer_open(rank, everyone)
+            eng._peer_world = key
+        token = torch.zeros(1, dtype=torch.int32, device=assign.device)
+
+    def rank_barrier():
+        # stream-ordered: completes here only after every rank's stream has reached it, i.e. after their push kernels
+        sync()
+        dist.all_reduce(token, op=dist.ReduceOp.SUM, group=group)
 
     def exchange_assign():
         # each rank owns assign[cb:ce]; a sum of (value + 1) over zero-filled vectors is an all-gather
@@ -104,11 +121,19 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
         apply = bool(geno_error_every_iter) or (it + 1 == niter)
         if exchange == "stats":
             eng.estep_dev(apply)
+        elif exchange == "push":
+            eng.posteriors_push_dev(apply)
+            rank_barrier()
+            eng.estep_post_dev()
         else:
             eng.posteriors_dev(apply)
             exchange_post()
             eng.estep_post_dev()
-        exchange_assign()
+        if exchange == "push":
+            eng.assign_push_dev()
+            rank_barrier()
+        else:
+            exchange_assign()
         eng.mstep_dev()
         if exchange == "stats":
             exchange_stats()

@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--nsnps", type=int, default=None)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--check", action="store_true")
-    ap.add_argument("--exchange", default="posteriors", choices=["posteriors", "stats"])
+    ap.add_argument("--exchange", default="posteriors", choices=["posteriors", "stats", "push"])
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -94,6 +94,11 @@ def main():
         if world > 1:
             timed("allreduce_stats_ms", lambda: dist.all_reduce(stats))
             timed("allreduce_posteriors_ms", lambda: dist.all_reduce(post))
+            if args.exchange == "push":
+                tok = torch.zeros(1, dtype=torch.int32, device=dev)
+                timed("posteriors_push_ms", lambda: eng.posteriors_push_dev(False))
+                timed("assign_push_ms", lambda: eng.assign_push_dev())
+                timed("rank_barrier_ms", lambda: dist.all_reduce(tok))
         return out
 
     run()  # warm-up (NCCL channels, allocations)
