@@ -265,6 +265,9 @@ int ccu_fmx_set_shard(ccu_handle* h, int64_t cell_begin, int64_t cell_end, int64
       snp_begin > snp_end)
     return ccu_fail(h, "ccu_fmx_set_shard: range out of bounds");
   CCU_CUDA(h, cudaSetDevice(h->device));
+  if (f->cell_begin == cell_begin && f->cell_end == cell_end && f->snp_begin == snp_begin && f->snp_end == snp_end &&
+      f->results.p)
+    return 0;  // same shard: keep what has been computed for it (a replayed CUDA graph makes no host-side calls)
   f->cell_begin = cell_begin;
   f->cell_end = cell_end;
   f->snp_begin = snp_begin;

@@ -56,7 +56,7 @@ def snp_slabs(snp_idx, nsnps, world):
 
 
 def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign, niter=10,
-                       geno_error_every_iter=False, group=None, sync=None, post=None, exchange=None):
+                       geno_error_every_iter=False, group=None, sync=None, post=None, exchange=None, graphs=None):
     """cmd_cram_freemuxlet.cpp:359-370 + :457-653 across ranks.  `stats`/`assign` (and `post`) are torch
     tensors aliasing the engine's arrays (device_views / posterior_view, or CPU tensors of a stand-in
     engine).  exchange: "posteriors" (default when `post` is given) or "stats".  Returns this rank's
@@ -84,7 +84,10 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
             dist.all_gather_object(everyone, mine, group=group)
             eng.peer_open(rank, everyone)
             eng._peer_world = key
+        # the 4-byte token of the rank barrier; a captured graph keeps pointing at it, so it lives with the graphs
         token = torch.zeros(1, dtype=torch.int32, device=assign.device)
+        if graphs is not None:
+            token = graphs.setdefault("_barrier_token", token)
 
     def rank_barrier():
         # stream-ordered: completes here only after every rank's stream has reached it, i.e. after their push kernels
@@ -113,32 +116,50 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
         sync()
         dist.all_reduce(post, op=dist.ReduceOp.SUM, group=group)
 
-    assign.copy_(torch.as_tensor(np.ascontiguousarray(init_assign, np.int32)).to(assign.device))
-    eng.mstep_dev()
-    if exchange == "stats":
-        exchange_stats()
-    for it in range(niter):
-        apply = bool(geno_error_every_iter) or (it + 1 == niter)
-        if exchange == "stats":
-            eng.estep_dev(apply)
-        elif exchange == "push":
-            eng.posteriors_push_dev(apply)
-            rank_barrier()
-            eng.estep_post_dev()
-        else:
-            eng.posteriors_dev(apply)
-            exchange_post()
-            eng.estep_post_dev()
-        if exchange == "push":
-            eng.assign_push_dev()
-            rank_barrier()
-        else:
-            exchange_assign()
+    def em_loop():
         eng.mstep_dev()
         if exchange == "stats":
             exchange_stats()
-    if exchange != "stats":
-        exchange_stats()  # once: the full statistics are only needed for the output
+        for it in range(niter):
+            apply = bool(geno_error_every_iter) or (it + 1 == niter)
+            if exchange == "stats":
+                eng.estep_dev(apply)
+            elif exchange == "push":
+                eng.posteriors_push_dev(apply)
+                rank_barrier()
+                eng.estep_post_dev()
+            else:
+                eng.posteriors_dev(apply)
+                exchange_post()
+                eng.estep_post_dev()
+            if exchange == "push":
+                eng.assign_push_dev()
+                rank_barrier()
+            else:
+                exchange_assign()
+            eng.mstep_dev()
+            if exchange == "stats":
+                exchange_stats()
+        if exchange != "stats":
+            exchange_stats()  # once: the full statistics are only needed for the output
+
+    assign.copy_(torch.as_tensor(np.ascontiguousarray(init_assign, np.int32)).to(assign.device))
+    key = (exchange, niter, bool(geno_error_every_iter), cb, ce, sb, se)
+    if graphs is None or stats.device.type == "cpu":
+        em_loop()
+    elif key not in graphs:
+        graphs[key] = None  # warm-up: eager
+        em_loop()
+    else:
+        if graphs[key] is None:
+            g = torch.cuda.CUDAGraph()
+            outer = torch.cuda.current_stream()
+            with torch.cuda.graph(g):
+                eng.set_stream(torch.cuda.current_stream().cuda_stream)  # the capture stream
+                em_loop()
+            eng.set_stream(outer.cuda_stream)
+            graphs[key] = g
+        graphs[key].replay()
     sync()
     local = eng.download_results()
     if not multi:

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--exchange", default="posteriors", choices=["posteriors", "stats", "push"])
+    ap.add_argument("--graph", action="store_true", help="run the whole EM loop as one CUDA graph (captured on the second run)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -66,6 +67,8 @@ def main():
     cell_ranges = balanced_ranges(d["cell_ptr"], world)
     slabs = snp_slabs(d["snp_idx"], d["nsnps"], world)
 
+    graphs = {} if args.graph else None
+
     def run():
         torch.cuda.synchronize()
         if world > 1:
@@ -73,7 +76,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         loc, full = run_em_distributed(eng, stats, assign, cell_ranges, slabs, init, niter=args.iters, post=post,
-                                       exchange=args.exchange)
+                                       exchange=args.exchange, graphs=graphs)
         e1.record()
         torch.cuda.synchronize()
         return loc, full, e0.elapsed_time(e1)
@@ -102,6 +105,8 @@ def main():
         return out
 
     run()  # warm-up (NCCL channels, allocations)
+    if args.graph:
+        run()  # captures the loop, then replays it once
     loc, full, ms = run()
     phases = breakdown()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -139,14 +144,25 @@ def main():
                 "n_gpus": world, "iters": args.iters, "ms_per_iter": ms / args.iters,
                 "config": {"workload": "C4 freemuxlet: K=%d, %d barcodes, %d SNPs, %d entries" %
                                        (K, d["nbcs"], d["nsnps"], nnz)},
-                "exchange": args.exchange, "stats_allreduce_bytes": int(stats.numel() * 8),
+                "exchange": args.exchange, "cuda_graph": bool(args.graph), "stats_allreduce_bytes": int(stats.numel() * 8),
                 "posterior_allreduce_bytes": int(post.numel() * 8), "setup": setup, "upload_s": t_upload, "phase_ms": phases, "roofline": roof,
                 "singlets": int((full["type"] == 0).sum()), "doublets": int((full["type"] == 1).sum()),
                 "matches_single_gpu": ok}
         print(json.dumps(line), flush=True)
-    eng.close()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    if graphs:
+        # a captured graph holds NCCL work of the process group: tearing the group down under it has been seen to
+        # hang, so the graphs go first and the process leaves without the group's destructor
+        graphs.clear()
+        torch.cuda.synchronize()
+        eng.close()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+    eng.close()
+    if world > 1:
         dist.destroy_process_group()
 
 
