@@ -28,7 +28,7 @@ struct FmxState {
   int64_t cell_begin = 0, cell_end = 0, snp_begin = 0, snp_end = 0;
   DevBuf cell_ptr, snp_idx, read_ptr, al, bq, af;
   DevBuf gl, cnt, logdenom, csc_ptr, csc_cell, csc_gl, csc_cnt;
-  DevBuf assign, stats, cgp, llk, results, scan, scratch;
+  DevBuf assign, stats, cgp, llk, results, scan, scratch, flags;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   ccu_fmx_timings tm = {};
   FmxPairs* pairs = nullptr;
@@ -40,6 +40,7 @@ struct FmxState {
       if (r != peer_rank) {
         if (peers.post[r]) cudaIpcCloseMemHandle(peers.post[r]);
         if (peers.assign[r]) cudaIpcCloseMemHandle(peers.assign[r]);
+        if (peers.flags[r]) cudaIpcCloseMemHandle(peers.flags[r]);
       }
     peers = {};
     peer_rank = -1;
@@ -48,7 +49,7 @@ struct FmxState {
     close_peers();
     ccu_fmx_pairs_release(pairs);
     DevBuf* all[] = {&cell_ptr, &snp_idx, &read_ptr, &al, &bq, &af, &gl, &cnt, &logdenom, &csc_ptr, &csc_cell,
-                     &csc_gl, &csc_cnt, &assign, &stats, &cgp, &llk, &results, &scan, &scratch};
+                     &csc_gl, &csc_cnt, &assign, &stats, &cgp, &llk, &results, &scan, &scratch, &flags};
     for (DevBuf* b : all) b->release();
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
@@ -391,9 +392,14 @@ int ccu_fmx_peer_handles(ccu_handle* h, void* out) {
   if (!f->cgp.p || !f->assign.p) return ccu_fail(h, "ccu_fmx_peer_handles: call ccu_fmx_set_shard first");
   static_assert(sizeof(cudaIpcMemHandle_t) == CCU_IPC_HANDLE_BYTES, "CUDA IPC handle size");
   CCU_CUDA(h, cudaSetDevice(h->device));
-  cudaIpcMemHandle_t hd[2];
+  // the flag array of the peer-memory barrier: zeroed here, i.e. before any peer can learn its address
+  CCU_CUDA(h, f->flags.reserve((ccu::kMaxPeers + 2) * sizeof(uint32_t)));
+  CCU_CUDA(h, cudaMemsetAsync(f->flags.p, 0, (ccu::kMaxPeers + 2) * sizeof(uint32_t), h->stream));
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaIpcMemHandle_t hd[3];
   CCU_CUDA(h, cudaIpcGetMemHandle(&hd[0], f->cgp.p));
   CCU_CUDA(h, cudaIpcGetMemHandle(&hd[1], f->assign.p));
+  CCU_CUDA(h, cudaIpcGetMemHandle(&hd[2], f->flags.p));
   memcpy(out, hd, sizeof(hd));
   return 0;
 }
@@ -403,7 +409,7 @@ int ccu_fmx_peer_open(ccu_handle* h, int32_t nranks, int32_t rank, const void* h
   FmxState* f = h->fmx;
   if (nranks < 1 || nranks > ccu::kMaxPeers || rank < 0 || rank >= nranks || !handles)
     return ccu_fail(h, "ccu_fmx_peer_open: bad arguments (at most %d ranks)", ccu::kMaxPeers);
-  if (!f->cgp.p || !f->assign.p) return ccu_fail(h, "ccu_fmx_peer_open: call ccu_fmx_set_shard first");
+  if (!f->cgp.p || !f->assign.p || !f->flags.p) return ccu_fail(h, "ccu_fmx_peer_open: call ccu_fmx_peer_handles first");
   CCU_CUDA(h, cudaSetDevice(h->device));
   f->close_peers();
   const cudaIpcMemHandle_t* hd = static_cast<const cudaIpcMemHandle_t*>(handles);
@@ -413,13 +419,16 @@ int ccu_fmx_peer_open(ccu_handle* h, int32_t nranks, int32_t rank, const void* h
     if (r == rank) {
       f->peers.post[r] = f->cgp.as<double>();
       f->peers.assign[r] = f->assign.as<int32_t>();
+      f->peers.flags[r] = f->flags.as<uint32_t>();
       continue;
     }
-    void *pp = nullptr, *pa = nullptr;
-    cudaError_t e = cudaIpcOpenMemHandle(&pp, hd[2 * r], cudaIpcMemLazyEnablePeerAccess);
-    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pa, hd[2 * r + 1], cudaIpcMemLazyEnablePeerAccess);
+    void *pp = nullptr, *pa = nullptr, *pf = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&pp, hd[3 * r], cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pa, hd[3 * r + 1], cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pf, hd[3 * r + 2], cudaIpcMemLazyEnablePeerAccess);
     f->peers.post[r] = static_cast<double*>(pp);
     f->peers.assign[r] = static_cast<int32_t*>(pa);
+    f->peers.flags[r] = static_cast<uint32_t*>(pf);
     if (e != cudaSuccess) {
       f->peers.n = r + 1;
       f->close_peers();
@@ -446,6 +455,30 @@ int ccu_fmx_posteriors_push_dev(ccu_handle* h, int32_t apply_geno_error) {
   CCU_CUDA(h, ccu::launch_fmx_cgp_push(fmx_view(h), apply_geno_error, f->peers, h->stream));
   f->tm.launches += 1;
   f->have_post = true;
+  return 0;
+}
+
+int ccu_fmx_rank_barrier_dev(ccu_handle* h) {
+  if (int rc = need(h, true, "ccu_fmx_rank_barrier")) return rc;
+  FmxState* f = h->fmx;
+  if (f->peers.n < 1) return ccu_fail(h, "ccu_fmx_rank_barrier: call ccu_fmx_peer_open first");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  CCU_CUDA(h, ccu::launch_fmx_rank_barrier(f->peers, f->peer_rank, h->stream));
+  f->tm.launches += (f->peers.n > 1) ? 1 : 0;
+  return 0;
+}
+
+int ccu_fmx_rank_barrier_failed(ccu_handle* h, int32_t* failed) {
+  if (int rc = need(h, true, "ccu_fmx_rank_barrier_failed")) return rc;
+  FmxState* f = h->fmx;
+  if (!failed) return ccu_fail(h, "ccu_fmx_rank_barrier_failed: NULL output");
+  *failed = 0;
+  if (!f->flags.p) return 0;
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  uint32_t v = 0;
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  CCU_CUDA(h, cudaMemcpy(&v, f->flags.as<uint32_t>() + ccu::kMaxPeers + 1, sizeof(v), cudaMemcpyDeviceToHost));
+  *failed = v ? 1 : 0;
   return 0;
 }
 

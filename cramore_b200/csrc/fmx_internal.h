@@ -71,10 +71,16 @@ constexpr int kMaxPeers = 16;
 struct FmxPeers {
   double* post[kMaxPeers];
   int32_t* assign[kMaxPeers];
+  uint32_t* flags[kMaxPeers];  // [kMaxPeers + 2]: arrival epochs written by the peers, own epoch, error flag
   int32_t n;
 };
 cudaError_t launch_fmx_cgp_push(const FmxDev& d, int apply_geno_error, const FmxPeers& peers, cudaStream_t st);
 cudaError_t launch_fmx_assign_push(const FmxDev& d, const FmxPeers& peers, cudaStream_t st);
+// Stream-ordered barrier across the ranks through the mapped flag arrays: every rank stores its next epoch into its
+// slot of every peer's array (release, system scope) and waits until all slots of its own array have reached it.
+// The epoch lives in device memory, so the launch can sit in a replayed CUDA graph.  A rank that waits longer than
+// ~2 s gives up and raises the error flag (flags[kMaxPeers + 1]) instead of hanging the GPU.
+cudaError_t launch_fmx_rank_barrier(const FmxPeers& peers, int rank, cudaStream_t st);
 cudaError_t launch_fmx_estep(const FmxDev& d, cudaStream_t st);
 // int32 count of droplets whose (type, jBest, kBest) differ between two result arrays
 // counts bitwise differences between the shared-reciprocal division of the pileup kernels and __ddiv_rn

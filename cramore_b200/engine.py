@@ -47,7 +47,8 @@ ABI_SYMBOLS = [
     "ccu_fmx_get_timings", "ccu_fmx_selftest_division", "ccu_fmx_post_dev", "ccu_fmx_posteriors_dev",
     "ccu_fmx_estep_post_dev", "ccu_fmx_pair_distances", "ccu_fmx_get_pair_distances", "ccu_fmx_initial_clusters",
     "ccu_fmx_greedy_clusters", "ccu_fmx_get_voting_pairs", "ccu_fmx_peer_handles", "ccu_fmx_peer_open",
-    "ccu_fmx_peer_close", "ccu_fmx_posteriors_push_dev", "ccu_fmx_assign_push_dev",
+    "ccu_fmx_peer_close", "ccu_fmx_posteriors_push_dev", "ccu_fmx_assign_push_dev", "ccu_fmx_rank_barrier_dev",
+    "ccu_fmx_rank_barrier_failed",
 ]
 
 
@@ -299,7 +300,7 @@ class FreemuxEngine(DemuxEngine):
         self._check(self.lib.ccu_fmx_estep_post_dev(self.h))
 
     # ---- peer-memory exchange (CUDA IPC over NVLink), see include/cramore_cuda.h ----
-    IPC_BYTES = 2 * 64
+    IPC_BYTES = 3 * 64
 
     def peer_handles(self):
         buf = C.create_string_buffer(self.IPC_BYTES)
@@ -321,6 +322,14 @@ class FreemuxEngine(DemuxEngine):
 
     def assign_push_dev(self):
         self._check(self.lib.ccu_fmx_assign_push_dev(self.h))
+
+    def rank_barrier_dev(self):
+        self._check(self.lib.ccu_fmx_rank_barrier_dev(self.h))
+
+    def rank_barrier_failed(self):
+        v = C.c_int32(0)
+        self._check(self.lib.ccu_fmx_rank_barrier_failed(self.h, C.byref(v)))
+        return bool(v.value)
 
     def mstep_dev(self):
         self._check(self.lib.ccu_fmx_mstep_dev(self.h))

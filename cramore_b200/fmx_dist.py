@@ -56,7 +56,8 @@ def snp_slabs(snp_idx, nsnps, world):
 
 
 def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign, niter=10,
-                       geno_error_every_iter=False, group=None, sync=None, post=None, exchange=None, graphs=None):
+                       geno_error_every_iter=False, group=None, sync=None, post=None, exchange=None, graphs=None,
+                       push_barrier="kernel"):
     """cmd_cram_freemuxlet.cpp:359-370 + :457-653 across ranks.  `stats`/`assign` (and `post`) are torch
     tensors aliasing the engine's arrays (device_views / posterior_view, or CPU tensors of a stand-in
     engine).  exchange: "posteriors" (default when `post` is given) or "stats".  Returns this rank's
@@ -91,8 +92,11 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
 
     def rank_barrier():
         # stream-ordered: completes here only after every rank's stream has reached it, i.e. after their push kernels
-        sync()
-        dist.all_reduce(token, op=dist.ReduceOp.SUM, group=group)
+        if push_barrier == "kernel":
+            eng.rank_barrier_dev()  # one-warp kernel over mapped flag arrays (no collective at all)
+        else:
+            sync()
+            dist.all_reduce(token, op=dist.ReduceOp.SUM, group=group)
 
     def exchange_assign():
         # each rank owns assign[cb:ce]; a sum of (value + 1) over zero-filled vectors is an all-gather
@@ -162,6 +166,8 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
         graphs[key].replay()
     sync()
     local = eng.download_results()
+    if exchange == "push" and push_barrier == "kernel" and eng.rank_barrier_failed():
+        raise RuntimeError("freemuxlet peer-memory exchange: a rank did not reach the barrier within its time-out")
     if not multi:
         return local, local
     device = None if stats.device.type == "cpu" else stats.device

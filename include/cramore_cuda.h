@@ -207,17 +207,21 @@ int ccu_fmx_estep_post_dev(ccu_handle* h);
 /* Peer-memory exchange (no reference counterpart: the reference is one process).  With one process per GPU on an
  * NVLink / NVSwitch box the two per-iteration exchanges need no collective on the payload: every rank maps the
  * posterior and assignment arrays of all ranks (CUDA IPC) and the producing kernels store straight into them.
- *   setup, after ccu_fmx_set_shard: ccu_fmx_peer_handles(h, mine) -> all-gather of the CCU_IPC_HANDLE_BYTES*2 bytes
+ *   setup, after ccu_fmx_set_shard: ccu_fmx_peer_handles(h, mine) -> all-gather of the CCU_IPC_HANDLE_BYTES*3 bytes
  *          (any host channel) -> ccu_fmx_peer_open(h, nranks, rank, all)
  *   per iteration: ccu_fmx_posteriors_push_dev -> barrier -> ccu_fmx_estep_post_dev -> ccu_fmx_assign_push_dev ->
  *          barrier -> ccu_fmx_mstep_dev
- * where "barrier" is any stream-ordered cross-rank synchronisation (a 4-byte ncclAllReduce on the engine's stream):
- * a rank may read its arrays only after every rank's push kernel has completed, and may push again only after every
- * rank has finished reading -- both follow from the two barriers.  Results are bit-identical to the all-reduce
- * exchange.  ccu_fmx_peer_close unmaps (also done by ccu_destroy). */
+ * where "barrier" is a stream-ordered cross-rank synchronisation -- ccu_fmx_rank_barrier_dev (a one-warp kernel over
+ * mapped flag arrays: release-store of the next epoch into every peer, acquire-spin on the own array; it gives up
+ * after ~2 s and ccu_fmx_rank_barrier_failed then reports 1) or a 4-byte ncclAllReduce on the engine's stream.
+ * A rank may read its arrays only after every rank's push kernel has completed, and may push again only after
+ * every rank has finished reading -- both follow from the two barriers.  Results are bit-identical to the
+ * all-reduce exchange.  ccu_fmx_peer_close unmaps (also done by ccu_destroy). */
 #define CCU_IPC_HANDLE_BYTES 64
-int ccu_fmx_peer_handles(ccu_handle* h, void* out /* [2 * CCU_IPC_HANDLE_BYTES]: posterior array, assignment array */);
-int ccu_fmx_peer_open(ccu_handle* h, int32_t nranks, int32_t rank, const void* handles /* [nranks][2][64] */);
+int ccu_fmx_peer_handles(ccu_handle* h, void* out /* [3 * CCU_IPC_HANDLE_BYTES]: posteriors, assignments, flags */);
+int ccu_fmx_peer_open(ccu_handle* h, int32_t nranks, int32_t rank, const void* handles /* [nranks][3][64] */);
+int ccu_fmx_rank_barrier_dev(ccu_handle* h);
+int ccu_fmx_rank_barrier_failed(ccu_handle* h, int32_t* failed);
 int ccu_fmx_peer_close(ccu_handle* h);
 int ccu_fmx_posteriors_push_dev(ccu_handle* h, int32_t apply_geno_error);
 int ccu_fmx_assign_push_dev(ccu_handle* h);

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--exchange", default="posteriors", choices=["posteriors", "stats", "push"])
+    ap.add_argument("--push-barrier", default="kernel", choices=["kernel", "nccl"])
     ap.add_argument("--graph", action="store_true", help="run the whole EM loop as one CUDA graph (captured on the second run)")
     args = ap.parse_args()
     import torch
@@ -76,7 +77,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         loc, full = run_em_distributed(eng, stats, assign, cell_ranges, slabs, init, niter=args.iters, post=post,
-                                       exchange=args.exchange, graphs=graphs)
+                                       exchange=args.exchange, graphs=graphs, push_barrier=args.push_barrier)
         e1.record()
         torch.cuda.synchronize()
         return loc, full, e0.elapsed_time(e1)
@@ -101,7 +102,8 @@ def main():
                 tok = torch.zeros(1, dtype=torch.int32, device=dev)
                 timed("posteriors_push_ms", lambda: eng.posteriors_push_dev(False))
                 timed("assign_push_ms", lambda: eng.assign_push_dev())
-                timed("rank_barrier_ms", lambda: dist.all_reduce(tok))
+                timed("rank_barrier_nccl_ms", lambda: dist.all_reduce(tok))
+                timed("rank_barrier_kernel_ms", lambda: eng.rank_barrier_dev())
         return out
 
     run()  # warm-up (NCCL channels, allocations)
@@ -144,7 +146,7 @@ def main():
                 "n_gpus": world, "iters": args.iters, "ms_per_iter": ms / args.iters,
                 "config": {"workload": "C4 freemuxlet: K=%d, %d barcodes, %d SNPs, %d entries" %
                                        (K, d["nbcs"], d["nsnps"], nnz)},
-                "exchange": args.exchange, "cuda_graph": bool(args.graph), "stats_allreduce_bytes": int(stats.numel() * 8),
+                "exchange": args.exchange, "cuda_graph": bool(args.graph), "push_barrier": args.push_barrier, "stats_allreduce_bytes": int(stats.numel() * 8),
                 "posterior_allreduce_bytes": int(post.numel() * 8), "setup": setup, "upload_s": t_upload, "phase_ms": phases, "roofline": roof,
                 "singlets": int((full["type"] == 0).sum()), "doublets": int((full["type"] == 1).sum()),
                 "matches_single_gpu": ok}
