@@ -45,7 +45,7 @@ def gather_results(local, ranges, device=None, group=None):
     buf = np.zeros(max(cap, 1), np.uint8)
     buf[:len(local) * item] = np.ascontiguousarray(local).view(np.uint8).reshape(-1)
     t = torch.from_numpy(buf)
-    if device is not None:
+    if device is not None and dist.get_backend(group) != "gloo":  # gloo gathers host tensors only
         t = t.to(device)
     outs = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(outs, t, group=group)

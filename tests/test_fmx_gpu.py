@@ -1,4 +1,6 @@
 """-m gpu parity tests of the freemuxlet kernels (through the C ABI) vs the CPU oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -294,3 +296,71 @@ def test_initial_clustering_from_gpu_distances_equals_reference(feng, name):
         clusts = initial_clusters(l2 - l0, plist, K, bf_thres=prm["bf_thres"], frac_init_clust=prm["frac_init_clust"],
                                   iter_init=10, keep_init_missing=prm["keep_init_missing"], seed=1)
         assert clusts.tolist() == fx["clust0"]
+
+
+_PEER_WORKER = r"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from cramore_b200 import FreemuxEngine
+from cramore_b200.fmx_dist import device_views, posterior_view, run_em_distributed, snp_slabs
+from cramore_b200.shard import balanced_ranges
+from cramore_b200.synth import make_dataset
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+dev = torch.device("cuda", 0)            # both ranks share the one GPU of the test box
+torch.cuda.set_device(dev)
+torch.cuda.set_stream(torch.cuda.Stream(device=dev))
+K, NITER = 5, 4                          # odd K: a slab may start at an odd element (the 8-byte store path)
+d = make_dataset("C4", nbcs=300, nsnps=2001, rbar=120, nv=5)
+init = (d["s1"] %% K).astype(np.int32)
+init[d["is_dbl"]] = -1
+eng = FreemuxEngine(0)
+eng.set_stream(torch.cuda.current_stream().cuda_stream)
+eng.configure_fmx(K, 0.5, 0.05)
+eng.upload_fmx(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], d["af"])
+stats, assign = device_views(eng, dev)
+post = posterior_view(eng, dev)
+ranges = balanced_ranges(d["cell_ptr"], world)
+slabs = snp_slabs(d["snp_idx"], d["nsnps"], world)
+out = {}
+for mode in ("push", "posteriors"):
+    loc, full = run_em_distributed(eng, stats, assign, ranges, slabs, init, niter=NITER, post=post, exchange=mode,
+                                   geno_error_every_iter=True)
+    torch.cuda.synchronize()
+    out[mode] = (full.copy(), stats.cpu().numpy().copy())
+assert np.array_equal(out["push"][0], out["posteriors"][0]), "results differ between the exchanges"
+assert np.array_equal(out["push"][1], out["posteriors"][1]), "cluster statistics differ between the exchanges"
+if rank == 0:
+    ref = FreemuxEngine(0)
+    ref.configure_fmx(K, 0.5, 0.05)
+    ref.upload_fmx(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], d["af"])
+    want, _ = ref.run_em(init, niter=NITER, geno_error_every_iter=True)
+    assert np.array_equal(want, out["push"][0]), "peer-memory exchange differs from the single-process loop"
+    assert (want["type"] == 0).sum() > 100
+    ref.close()
+dist.barrier()
+eng.close()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_peer_memory_exchange_two_processes(built, tmp_path):
+    """The CUDA-IPC exchange of the multi-GPU freemuxlet loop (posterior kernel and assignment push storing into the
+    other rank's arrays, flag barrier over mapped memory) with two processes on this box's GPU: bit-identical to the
+    all-reduce exchange and to the single-process loop.  gloo carries the host-side plumbing (NCCL refuses two ranks
+    on one device); on a multi-GPU box tools/bench_fmx.py --exchange push --check runs the same over NVLink."""
+    import subprocess
+    import sys
+    script = tmp_path / "peer_worker.py"
+    script.write_text(_PEER_WORKER % {"root": os.path.dirname(os.path.dirname(os.path.abspath(__file__)))})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29733", str(script)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2
