@@ -28,10 +28,23 @@ DEMUX_CASES = {
     "demux_missing_gp_r2": dict(ds=dict(name="C1", nbcs=40, nsnps=300, rbar=50, nv=6, seed=99), alphas=[0, 0.25, 0.5],
                                 args=["--geno-error-offset", "0.05", "--geno-error-coeff", "0.5"], drop_every=7,
                                 with_r2=True),
+    # hard genotype calls (--field GT: posteriors exactly 0 / 1) without any genotype-error mixing: every likelihood is
+    # a single tile element, mismatches cost ~23 nats per read
+    "demux_hard_gt": dict(ds=dict(name="C1", nbcs=40, nsnps=300, rbar=70, nv=7, seed=123), alphas=[0, 0.25, 0.5],
+                          args=["--geno-error-offset", "0"], field="GT"),
+    # a grid that reaches beyond 0.5 and does not contain it (no mirror pairs, ordered pairs at every alpha)
+    "demux_alpha_beyond_half": dict(ds=dict(name="C1", nbcs=36, nsnps=260, rbar=80, nv=6, seed=321),
+                                    alphas=[0, 0.3, 0.7, 1.0], args=["--doublet-prior", "0.2"]),
+    # a subset of the VCF's samples (--sm): genotype columns, sample ids and the --min-mac filter follow the subset
+    "demux_sample_subset": dict(ds=dict(name="C1", nbcs=36, nsnps=280, rbar=70, nv=9, seed=555), alphas=None,
+                                args=["--sm", "SM001", "--sm", "SM004", "--sm", "SM005", "--sm", "SM008"]),
 }
 FMX_CASES = {
     "fmx_k4": dict(ds=dict(name="C4", nbcs=80, nsnps=600, rbar=80, nv=4), K=4, args=["--geno-error", "0.1"]),
     "fmx_k3_noerr": dict(ds=dict(name="C4", nbcs=50, nsnps=400, rbar=60, nv=3, seed=5), K=3, args=[]),
+    # more clusters than the data has samples for (some stay nearly empty), a doublet prior away from 0.5
+    "fmx_k6_prior": dict(ds=dict(name="C4", nbcs=120, nsnps=700, rbar=90, nv=5, seed=8), K=6,
+                         args=["--geno-error", "0.02", "--doublet-prior", "0.3"]),
 }
 
 
@@ -52,6 +65,12 @@ FMX2_CASES = {
                                    args=["--frac-init-clust", "0.6", "--geno-error", "0.05", "--doublet-prior", "0.3"]),
     "fmx2_k3_fromfile": dict(ds=dict(name="C4", nbcs=40, nsnps=240, rbar=80, nv=3, seed=41), K=3, args=[], init_file=True),
 }
+
+
+def wanted(cases):
+    """(name, spec) of the cases to (re)generate: all, or the ones named on the command line"""
+    only = set(sys.argv[1:])
+    return [(n, sp) for n, sp in cases.items() if not only or n in only]
 
 
 def dataset(spec):
@@ -87,7 +106,7 @@ def init_clusters(d, K):
 def main():
     if not os.path.exists(REF):
         raise SystemExit("build oracle/_ref first: make -C oracle ref (needs /root/reference)")
-    for name, spec in DEMUX_CASES.items():
+    for name, spec in wanted(DEMUX_CASES):
         d = dataset(spec)
         with tempfile.TemporaryDirectory() as tmp:
             write_plp(d, os.path.join(tmp, "in"))
@@ -106,7 +125,7 @@ def main():
                             snp += 1
             else:
                 write_vcf(dv, os.path.join(tmp, "in.vcf"), with_r2=spec.get("with_r2", False))
-            args = ["demuxlet", "--plp", "in", "--vcf", "in.vcf", "--field", "GP", "--out", "out"] + spec["args"]
+            args = ["demuxlet", "--plp", "in", "--vcf", "in.vcf", "--field", spec.get("field", "GP"), "--out", "out"] + spec["args"]
             for a in (spec["alphas"] or []):
                 args += ["--alpha", repr(float(a))]
             run(args, tmp)
@@ -115,7 +134,7 @@ def main():
         json.dump({"case": name, "spec": spec, "best_text": best, "best_raw": raw},
                   open(os.path.join(HERE, "ref_%s.json" % name), "w"))
         print(name, len(raw), "rows")
-    for name, spec in FMX_CASES.items():
+    for name, spec in wanted(FMX_CASES):
         d = dataset(spec)
         K = spec["K"]
         with tempfile.TemporaryDirectory() as tmp:
@@ -134,7 +153,7 @@ def main():
                    "vcf_sites": vcf_sites(read_raw(os.path.join(tmp, "out.clust1.vcf.gz.raw")), K)}
         json.dump(out, open(os.path.join(HERE, "ref_%s.json" % name), "w"))
         print(name, len(out["samples_raw"]), "rows")
-    for name, spec in FMX_INIT_CASES.items():
+    for name, spec in wanted(FMX_INIT_CASES):
         d = dataset(spec)
         K = spec["K"]
         with tempfile.TemporaryDirectory() as tmp:
@@ -164,7 +183,7 @@ def main():
 
 
 def freemux2_cases():
-    for name, spec in FMX2_CASES.items():
+    for name, spec in wanted(FMX2_CASES):
         d = dataset(spec)
         K = spec["K"]
         with tempfile.TemporaryDirectory() as tmp:

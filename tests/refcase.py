@@ -8,8 +8,9 @@ import numpy as np
 from cramore_b200.synth import make_dataset
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DEMUX_CASES = ["demux_c1_small", "demux_grid_deep", "demux_missing_gp_r2"]
-FMX_CASES = ["fmx_k4", "fmx_k3_noerr"]
+DEMUX_CASES = ["demux_c1_small", "demux_grid_deep", "demux_missing_gp_r2", "demux_hard_gt", "demux_alpha_beyond_half",
+               "demux_sample_subset"]
+FMX_CASES = ["fmx_k4", "fmx_k3_noerr", "fmx_k6_prior"]
 FMX_INIT_CASES = ["fmx_init_k3", "fmx_init_k4_partial", "fmx_init_k3_fromfile"]
 FMX2_CASES = ["fmx2_k3_greedy", "fmx2_k4_greedy_partial", "fmx2_k3_fromfile"]
 
@@ -41,6 +42,17 @@ def demux_inputs(fx):
     def opt(flag, default):
         return float(args[args.index(flag) + 1]) if flag in args else default
 
+    if "--sm" in args:  # sample subset, in VCF column order (bcf_filtered_reader.cpp:108-127)
+        want = {args[i + 1] for i, a in enumerate(args) if a == "--sm"}
+        cols = [i for i, sid in enumerate(d["sample_ids"]) if sid in want]
+        d["gp"] = np.ascontiguousarray(np.asarray(d["gp"])[:, cols])
+        d["geno"] = np.asarray(d["geno"])[:, cols]
+        d["sample_ids"] = [d["sample_ids"][i] for i in cols]
+        d["nv"] = len(cols)
+    if spec.get("field") == "GT":  # parse_posteriors' GT branch with gt_error = 0 (sc_drop_seq.cpp:285): 0 / 1
+        gp = np.zeros((d["nsnps"], d["nv"], 3), np.float32)
+        np.put_along_axis(gp, np.asarray(d["geno"], np.int64)[:, :, None], np.float32(1.0), axis=2)
+        d["gp"] = gp
     alphas = np.asarray(spec["alphas"] if spec["alphas"] else [0.0, 0.5], np.float64)  # cmd_cram_demuxlet.cpp:85-89
     off, coeff = opt("--geno-error-offset", 0.10), opt("--geno-error-coeff", 0.0)
     err = off

@@ -50,7 +50,7 @@ def test_cli_demuxlet_best_file(built, tmp_path, name):
             if not spec.get("drop_every") or snp % spec["drop_every"] != 0:
                 f.write(ln)
             snp += 1
-    args = [CRAMORE, "demuxlet", "--plp", pre, "--vcf", vcf, "--field", "GP", "--out", str(tmp_path / "out")] + spec["args"]
+    args = [CRAMORE, "demuxlet", "--plp", pre, "--vcf", vcf, "--field", spec.get("field", "GP"), "--out", str(tmp_path / "out")] + spec["args"]
     for a in (spec["alphas"] or []):
         args += ["--alpha", repr(float(a))]
     r = subprocess.run(args, capture_output=True, text=True)

@@ -60,6 +60,7 @@ def test_oracle_freemuxlet_equals_reference(name):
     K = fx["spec"]["K"]
     args = fx["spec"]["args"]
     ge = float(args[args.index("--geno-error") + 1]) if "--geno-error" in args else 0.0
+    prior = float(args[args.index("--doublet-prior") + 1]) if "--doublet-prior" in args else 0.5
     # freemuxlet's own read filter defaults: --cap-BQ 40 --min-BQ 13 (cmd_cram_freemuxlet.cpp:27-28); synthetic
     # base qualities are already capped at 20, so the CSR is what load_from_plp builds
     plp = pyoracle.fmx_pileup(d["read_ptr"], d["al"], d["bq"], 0.5)
@@ -71,7 +72,7 @@ def test_oracle_freemuxlet_equals_reference(name):
         assert abs(l0[c] - float(r[4])) <= TIGHT * abs(float(r[4])) and abs(l2[c] - float(r[5])) <= TIGHT * abs(float(r[5]))
     clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], plp, np.asarray(fx["init"], np.int32), K, d["nsnps"])
     for it in range(10):  # cmd_cram_freemuxlet.cpp:456-457
-        res, _ = pyoracle.fmx_estep(d["cell_ptr"], d["snp_idx"], plp, af, clust, 0.5, ge, it + 1 == 10)
+        res, _ = pyoracle.fmx_estep(d["cell_ptr"], d["snp_idx"], plp, af, clust, prior, ge, it + 1 == 10)
         assign = np.where(res["type"] == 0, res["jBest"], -1).astype(np.int32)
         clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], plp, assign, K, d["nsnps"])
     rows = refcase.fmx_rows(fx)

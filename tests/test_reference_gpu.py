@@ -60,10 +60,11 @@ def test_engine_freemuxlet_equals_reference(built, name):
     K = fx["spec"]["K"]
     args = fx["spec"]["args"]
     ge = float(args[args.index("--geno-error") + 1]) if "--geno-error" in args else 0.0
+    prior = float(args[args.index("--doublet-prior") + 1]) if "--doublet-prior" in args else 0.5
     af = np.asarray(["%.5f" % a for a in d["af"]], np.float64)
     eng = FreemuxEngine(0)
     try:
-        eng.configure_fmx(K, 0.5, ge)
+        eng.configure_fmx(K, prior, ge)
         eng.upload_fmx(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], af)
         l0, l2 = eng.lmix()
         lm = [r for r in fx["lmix_raw"] if len(r) == 8]
