@@ -32,10 +32,11 @@ DEMUX_CASES = {
     # a single tile element, mismatches cost ~23 nats per read
     "demux_hard_gt": dict(ds=dict(name="C1", nbcs=40, nsnps=300, rbar=70, nv=7, seed=123), alphas=[0, 0.25, 0.5],
                           args=["--geno-error-offset", "0"], field="GT"),
-    # a grid that reaches beyond 0.5 and does not contain it (no mirror pairs, ordered pairs at every alpha).  Not 1.0:
-    # there the likelihood no longer depends on the first sample of the pair and the reference picks it by rounding
+    # a grid that reaches beyond 0.5 and does not contain it: ordered pairs at every alpha.  No alpha together with its
+    # complement (0.3 and 0.7: (j,k,0.3) and (k,j,0.7) are one hypothesis, told apart by rounding only, like the two
+    # orientations at 0.5) and not 1.0 (the likelihood no longer depends on the first sample of the pair)
     "demux_alpha_beyond_half": dict(ds=dict(name="C1", nbcs=36, nsnps=260, rbar=80, nv=6, seed=321),
-                                    alphas=[0, 0.3, 0.7, 0.9], args=["--doublet-prior", "0.2"]),
+                                    alphas=[0, 0.3, 0.6, 0.9], args=["--doublet-prior", "0.2"]),
     # a subset of the VCF's samples (--sm): genotype columns, sample ids and the --min-mac filter follow the subset
     "demux_sample_subset": dict(ds=dict(name="C1", nbcs=36, nsnps=280, rbar=70, nv=9, seed=555), alphas=None,
                                 args=["--sm", "SM001", "--sm", "SM004", "--sm", "SM005", "--sm", "SM008"]),
