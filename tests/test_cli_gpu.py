@@ -32,6 +32,28 @@ def _numeric_row_match(a, b, rtol_llk=0.011):
     return True
 
 
+def _compare_best(mine, ref, ids, min_exact=0.6):
+    """.best of this build against the reference's: rows equal, up to the alpha = 0.5 mirror orientation the reference
+    picks by rounding noise and a last printed digit."""
+    assert mine[0] == ref[0] and len(mine) == len(ref)
+    exact = 0
+    for a, b in zip(mine[1:], ref[1:]):
+        if a == b:
+            exact += 1
+            continue
+        fa, fb = a.split("\t"), b.split("\t")
+        ga, gb = fa[17].split(","), fb[17].split(",")
+        mirror = gb[2] == "0.50" and ga[:2] == gb[:2][::-1] and ids.index(gb[0]) > ids.index(gb[1])
+        if mirror:
+            for col in (5, 7, 17):  # BEST.GUESS, NEXT.GUESS, DBL.BEST.GUESS may carry the swapped pair
+                pa, pb = fa[col].split(","), fb[col].split(",")
+                if pa != pb and pa[:2] == pb[:2][::-1]:
+                    fa[col] = fb[col]
+            a = "\t".join(fa)
+        assert a == b or _numeric_row_match(a, b), (a, b)
+    assert exact >= min_exact * (len(ref) - 1)
+
+
 @pytest.mark.parametrize("name", refcase.DEMUX_CASES)
 def test_cli_demuxlet_best_file(built, tmp_path, name):
     fx = refcase.load(name)
@@ -66,26 +88,7 @@ def test_cli_demuxlet_best_file(built, tmp_path, name):
     assert open(str(tmp_path / "out_cached.best")).read() == open(str(tmp_path / "out.best")).read()
     mine = open(str(tmp_path / "out.best")).read().splitlines(keepends=True)
     ref = fx["best_text"].splitlines(keepends=True)
-    assert mine[0] == ref[0] and len(mine) == len(ref)
-    ids = d["sample_ids"]
-    exact = 0
-    for a, b in zip(mine[1:], ref[1:]):
-        if a == b:
-            exact += 1
-            continue
-        fa, fb = a.split("\t"), b.split("\t")
-        # admissible: alpha = 0.5 mirror orientation chosen by the reference's rounding noise ...
-        ga, gb = fa[17].split(","), fb[17].split(",")
-        mirror = gb[2] == "0.50" and ga[:2] == gb[:2][::-1] and ids.index(gb[0]) > ids.index(gb[1])
-        if mirror:
-            for col in (5, 7, 17):  # BEST.GUESS, NEXT.GUESS, DBL.BEST.GUESS may carry the swapped pair
-                pa, pb = fa[col].split(","), fb[col].split(",")
-                if pa != pb and pa[:2] == pb[:2][::-1]:
-                    fa[col] = fb[col]
-            a = "\t".join(fa)
-        # ... or a last printed digit
-        assert a == b or _numeric_row_match(a, b), (a, b)
-    assert exact >= 0.6 * (len(ref) - 1)
+    _compare_best(mine, ref, d["sample_ids"])
 
 
 @pytest.mark.parametrize("name", refcase.FMX_CASES)
@@ -224,3 +227,69 @@ def test_cli_demuxlet_sam_input_matches_plp_input(built, tmp_path):
         fa, fb = a.split("\t"), b.split("\t")
         assert fa[:2] == fb[:2] and int(fa[2]) <= int(fb[2]) and int(fa[3]) <= int(fb[3])
         assert _numeric_row_match("\t".join(fa[4:]), "\t".join(fb[4:])), (a, b)
+
+
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_cramore")
+live = pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/ref_cramore not built")
+
+
+@live
+@pytest.mark.parametrize("seed", range(8))
+def test_cli_demuxlet_equals_live_reference(built, tmp_path, seed):
+    """`cramore demuxlet` on the GPU against the reference's own compiled engine (oracle/_ref/ref_cramore) run on the
+    same files, for randomly drawn pool sizes, alpha grids, priors and error settings."""
+    from cramore_b200.synth import make_dataset
+    from tests.test_reference_live import _complement_free_grid
+    rng = np.random.default_rng(3000 + seed)
+    nv = int(rng.integers(2, 40))
+    d = make_dataset("C1", nbcs=int(rng.integers(10, 60)), nsnps=int(rng.integers(100, 600)), rbar=int(rng.integers(20, 200)),
+                     nv=nv, seed=7000 + seed, with_barcodes=True)
+    alphas = _complement_free_grid(rng)
+    common = ["--doublet-prior", repr(float(rng.choice([0.1, 0.5, 0.8]))), "--geno-error-offset",
+              repr(float(rng.choice([0.0, 0.01, 0.1]))), "--geno-error-coeff", repr(float(rng.choice([0.0, 0.5]))),
+              "--field", str(rng.choice(["GP", "GT"]))]
+    for a in alphas:
+        common += ["--alpha", repr(a)]
+    pre = str(tmp_path / "in")
+    write_plp(d, pre)
+    write_vcf(d, pre + ".vcf", with_r2=True)
+    r = subprocess.run([REF_BIN, "demuxlet", "--plp", "in", "--vcf", "in.vcf", "--out", "ref"] + common, capture_output=True,
+                       text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([CRAMORE, "demuxlet", "--plp", pre, "--vcf", pre + ".vcf", "--out", str(tmp_path / "mine")] + common,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    _compare_best(open(str(tmp_path / "mine.best")).read().splitlines(keepends=True),
+                  open(str(tmp_path / "ref.best")).read().splitlines(keepends=True), d["sample_ids"], min_exact=0.5)
+
+
+@live
+@pytest.mark.parametrize("seed", range(4))
+def test_cli_freemuxlet_equals_live_reference(built, tmp_path, seed):
+    from cramore_b200.synth import make_dataset
+    rng = np.random.default_rng(4000 + seed)
+    K = int(rng.integers(2, 9))
+    d = make_dataset("C4", nbcs=int(rng.integers(40, 120)), nsnps=int(rng.integers(200, 700)), rbar=int(rng.integers(40, 120)),
+                     nv=int(rng.integers(2, 7)), seed=8000 + seed, with_barcodes=True)
+    pre = str(tmp_path / "in")
+    bcs = write_plp(d, pre)
+    init = (d["s1"] % K).astype(np.int32)
+    init[d["is_dbl"]] = -1
+    init[rng.random(len(init)) < 0.3] = -1
+    with open(str(tmp_path / "init.txt"), "w") as f:
+        for b, c in zip(bcs, init):
+            f.write("%s\t%d\n" % (b, c))
+    common = ["--nsample", str(K), "--init-cluster", str(tmp_path / "init.txt"), "--iter-init", "0", "--keep-init-missing",
+              "--geno-error", repr(float(rng.choice([0.0, 0.05]))), "--doublet-prior", repr(float(rng.choice([0.3, 0.5])))]
+    r = subprocess.run([REF_BIN, "freemuxlet", "--plp", "in", "--out", "ref"] + common, capture_output=True, text=True,
+                       cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([CRAMORE, "freemuxlet", "--plp", pre, "--out", str(tmp_path / "mine")] + common, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    mine = gzip.open(str(tmp_path / "mine.clust1.samples.gz"), "rt").read().splitlines(keepends=True)
+    ref = gzip.open(str(tmp_path / "ref.clust1.samples.gz"), "rt").read().splitlines(keepends=True)
+    assert len(mine) == len(ref) and mine[0] == ref[0]
+    for a, b in zip(mine[1:], ref[1:]):
+        assert a == b or _numeric_row_match(a, b), (a, b)
+    assert sum(a == b for a, b in zip(mine, ref)) >= 0.9 * len(ref)
+    assert open(str(tmp_path / "mine.lmix")).read().splitlines()[0] == open(str(tmp_path / "ref.lmix")).read().splitlines()[0]
