@@ -11,6 +11,8 @@
 // Parity unpinned: the reference's own --sam path needs htslib and cannot be run here; the tests check this
 // reader against BAM files written by an independent Python encoder and against the --plp path on the same reads.
 #pragma once
+#include <atomic>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 
@@ -18,16 +20,168 @@
 
 namespace hostio {
 
+// BGZF (SAM spec 4.1) is a series of independent gzip members of at most 64 KiB, each announcing its compressed
+// size in a 'BC' extra field: the blocks of a batch are inflated on all host cores at once and handed out as one
+// byte stream.  zlib's gzread on the same file is a single sequential inflate -- for a real 10-50 GB BAM the read
+// loop then IS the run time of dsc-pileup / demuxlet --sam.  A file that is not BGZF (plain gzip, or not compressed)
+// goes through gzread as before.
+class BgzfStream {
+ public:
+  explicit BgzfStream(const std::string& fn) : fn_(fn) {
+    fp_ = fopen(fn.c_str(), "rb");
+    if (!fp_) fatal("Cannot open file %s for reading", fn.c_str());
+    unsigned char h[18];
+    const size_t got = fread(h, 1, sizeof(h), fp_);
+    bgzf_ = got == sizeof(h) && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C';
+    if (bgzf_) {
+      fseek(fp_, 0, SEEK_SET);
+      nthreads_ = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+      if (const char* e = getenv("CRAMORE_BGZF_THREADS")) nthreads_ = std::max(1, atoi(e));
+    } else {
+      fclose(fp_);
+      fp_ = NULL;
+      gz_ = gzopen(fn.c_str(), "rb");
+      if (!gz_) fatal("Cannot open file %s for reading", fn.c_str());
+      gzbuffer(gz_, 1 << 20);
+    }
+  }
+  ~BgzfStream() {
+    if (fp_) fclose(fp_);
+    if (gz_) gzclose(gz_);
+  }
+  BgzfStream(const BgzfStream&) = delete;
+  BgzfStream& operator=(const BgzfStream&) = delete;
+  // up to n bytes; fewer only at the end of the file
+  size_t read(void* dst, size_t n) {
+    char* p = static_cast<char*>(dst);
+    size_t done = 0;
+    if (!bgzf_) {
+      while (done < n) {
+        const int got = gzread(gz_, p + done, (unsigned)std::min<size_t>(n - done, 1u << 30));
+        if (got < 0) fatal("%s: read error", fn_.c_str());
+        if (got == 0) break;
+        done += (size_t)got;
+      }
+      return done;
+    }
+    while (done < n) {
+      if (pos_ == out_.size() && !fill()) break;
+      const size_t take = std::min(n - done, out_.size() - pos_);
+      memcpy(p + done, out_.data() + pos_, take);
+      pos_ += take;
+      done += take;
+    }
+    return done;
+  }
+
+ private:
+  struct Block {
+    size_t in_off, in_len, out_off, out_len;  // deflate payload inside in_, inflated bytes inside out_
+    uint32_t crc;
+  };
+  // reads the next batch of blocks and inflates it; false at the end of the file
+  bool fill() {
+    constexpr size_t kBatchBlocks = 1024;  // <= 64 MiB inflated
+    in_.clear();
+    std::vector<Block> blocks;
+    size_t out_total = 0;
+    unsigned char h[18];
+    while (blocks.size() < kBatchBlocks) {
+      const size_t got = fread(h, 1, 12, fp_);
+      if (got == 0) break;
+      if (got != 12 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) fatal("%s: malformed BGZF block header", fn_.c_str());
+      const size_t xlen = h[10] | ((size_t)h[11] << 8);
+      std::vector<unsigned char> extra(xlen);
+      if (fread(extra.data(), 1, xlen, fp_) != xlen) fatal("%s: truncated BGZF block", fn_.c_str());
+      size_t bsize = 0;
+      for (size_t i = 0; i + 4 <= xlen;) {
+        const size_t slen = extra[i + 2] | ((size_t)extra[i + 3] << 8);
+        if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2 && i + 6 <= xlen) bsize = (extra[i + 4] | ((size_t)extra[i + 5] << 8)) + 1;
+        i += 4 + slen;
+      }
+      if (bsize < 12 + xlen + 8) fatal("%s: BGZF block without a size field", fn_.c_str());
+      const size_t payload = bsize - 12 - xlen - 8;
+      const size_t off = in_.size();
+      in_.resize(off + payload + 8);
+      if (fread(in_.data() + off, 1, payload + 8, fp_) != payload + 8) fatal("%s: truncated BGZF block", fn_.c_str());
+      uint32_t crc, isize;
+      memcpy(&crc, in_.data() + off + payload, 4);
+      memcpy(&isize, in_.data() + off + payload + 4, 4);
+      if (isize > 65536) fatal("%s: BGZF block larger than 64 KiB", fn_.c_str());
+      if (isize == 0) {  // the empty end-of-file marker (or padding): nothing to inflate
+        in_.resize(off);
+        continue;
+      }
+      blocks.push_back({off, payload, out_total, isize, crc});
+      out_total += isize;
+    }
+    if (blocks.empty()) return false;
+    out_.resize(out_total);
+    pos_ = 0;
+    std::atomic<size_t> next{0};
+    std::atomic<int> bad{0};
+    auto work = [&]() {
+      z_stream zs;
+      memset(&zs, 0, sizeof(zs));
+      if (inflateInit2(&zs, -15) != Z_OK) {
+        bad = 1;
+        return;
+      }
+      for (size_t i = next++; i < blocks.size(); i = next++) {
+        const Block& b = blocks[i];
+        inflateReset(&zs);
+        zs.next_in = in_.data() + b.in_off;
+        zs.avail_in = (uInt)b.in_len;
+        zs.next_out = out_.data() + b.out_off;
+        zs.avail_out = (uInt)b.out_len;
+        const int rc = inflate(&zs, Z_FINISH);
+        if (rc != Z_STREAM_END || zs.avail_out != 0 ||
+            (uint32_t)crc32(crc32(0L, Z_NULL, 0), out_.data() + b.out_off, (uInt)b.out_len) != b.crc)
+          bad = 1;
+      }
+      inflateEnd(&zs);
+    };
+    const int nt = (int)std::min<size_t>((size_t)nthreads_, (blocks.size() + 15) / 16);
+    if (nt <= 1) {
+      work();
+    } else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; ++t) th.emplace_back(work);
+      for (auto& t : th) t.join();
+    }
+    if (bad) fatal("%s: corrupt BGZF block (inflate or CRC failed)", fn_.c_str());
+    return true;
+  }
+  std::string fn_;
+  FILE* fp_ = NULL;
+  gzFile gz_ = NULL;
+  bool bgzf_ = false;
+  int nthreads_ = 1;
+  std::vector<unsigned char> in_, out_;
+  size_t pos_ = 0;
+};
+
 struct BamRecord {
   int32_t tid = -1, pos = 0, l_seq = 0;
-  uint32_t mapq = 0, flag = 0;
-  std::vector<uint32_t> cigar;  // op = v & 15 ("MIDNSHP=X"), len = v >> 4
-  std::string qname, seq, qual;  // seq decoded ("=ACMGRSVTWYHKDBN"), qual = Phred + 33
-  std::vector<uint8_t> aux;
+  uint32_t mapq = 0, flag = 0, n_cigar = 0;
+  // The raw record (SAM spec 4.2) and offsets into it: nothing is decoded until somebody asks -- most reads of a
+  // single-cell BAM overlap no SNP at all, and a read that does shows one base.
+  std::vector<uint8_t> data;
+  size_t off_cigar = 0, off_seq = 0, off_qual = 0, off_aux = 0;
+  uint32_t cigar_at(uint32_t i) const {  // op = v & 15 ("MIDNSHP=X"), len = v >> 4
+    uint32_t v;
+    memcpy(&v, data.data() + off_cigar + 4ull * i, 4);
+    return v;
+  }
+  char base_at(int32_t i) const { return "=ACMGRSVTWYHKDBN"[(data[off_seq + ((size_t)i >> 1)] >> ((~i & 1) << 2)) & 15]; }
+  char qual_at(int32_t i) const { return (char)(data[off_qual + (size_t)i] + 33); }  // bam_get_qual_string
+  std::string qname() const { return std::string(reinterpret_cast<const char*>(data.data() + 32)); }
   // value of a 'Z' tag, or NULL (bam_aux_get + bam_aux2Z)
   const char* tag_z(const char* tag) const {
+    const uint8_t* aux = data.data() + off_aux;
+    const size_t naux = data.size() - off_aux;
     size_t p = 0;
-    while (p + 3 <= aux.size()) {
+    while (p + 3 <= naux) {
       const bool hit = aux[p] == (uint8_t)tag[0] && aux[p + 1] == (uint8_t)tag[1];
       const char t = (char)aux[p + 2];
       p += 3;
@@ -38,14 +192,14 @@ struct BamRecord {
         case 'i': case 'I': case 'f': len = 4; break;
         case 'Z': case 'H': {
           const size_t b = p;
-          while (p < aux.size() && aux[p] != 0) ++p;
-          if (p >= aux.size()) return NULL;
+          while (p < naux && aux[p] != 0) ++p;
+          if (p >= naux) return NULL;
           ++p;
           if (hit) return (t == 'Z') ? reinterpret_cast<const char*>(&aux[b]) : NULL;
           continue;
         }
         case 'B': {
-          if (p + 5 > aux.size()) return NULL;
+          if (p + 5 > naux) return NULL;
           const char st = (char)aux[p];
           uint32_t n;
           memcpy(&n, &aux[p + 1], 4);
@@ -63,7 +217,8 @@ struct BamRecord {
   // bam_endpos: one past the last reference base the alignment covers
   int32_t endpos() const {
     int32_t e = pos;
-    for (uint32_t c : cigar) {
+    for (uint32_t i = 0; i < n_cigar; ++i) {
+      const uint32_t c = cigar_at(i);
       const uint32_t op = c & 15;
       if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) e += (int32_t)(c >> 4);
     }
@@ -78,10 +233,7 @@ class BamReader {
   int32_t minMQ = 20;
   uint32_t exclude_flag = 0x0f04;
 
-  explicit BamReader(const std::string& fn) : fn_(fn) {
-    gz_ = gzopen(fn.c_str(), "rb");
-    if (!gz_) fatal("Cannot open file %s for reading", fn.c_str());
-    gzbuffer(gz_, 1 << 20);
+  explicit BamReader(const std::string& fn) : fn_(fn), in_(fn) {
     char magic[4];
     if (!read_exact(magic, 4) || memcmp(magic, "BAM\1", 4) != 0)
       fatal("%s is not a BAM file (SAM text and CRAM need htslib, which this build does not include; convert with "
@@ -99,9 +251,6 @@ class BamReader {
       refs.push_back(name);
     }
   }
-  ~BamReader() {
-    if (gz_) gzclose(gz_);
-  }
   // SAMFilteredReader::read(): the next record passing the filter; false at EOF
   bool read(BamRecord& r) {
     while (next(r)) {
@@ -113,16 +262,7 @@ class BamReader {
   }
 
  private:
-  bool read_exact(void* dst, size_t n) {
-    char* p = static_cast<char*>(dst);
-    while (n > 0) {
-      const int got = gzread(gz_, p, (unsigned)std::min<size_t>(n, 1u << 30));
-      if (got <= 0) return false;
-      p += got;
-      n -= (size_t)got;
-    }
-    return true;
-  }
+  bool read_exact(void* dst, size_t n) { return in_.read(dst, n) == n; }
   int32_t read_i32() {
     int32_t v = 0;
     if (!read_exact(&v, 4)) fatal("%s: truncated BAM file", fn_.c_str());
@@ -131,45 +271,33 @@ class BamReader {
   bool next(BamRecord& r) {
     int32_t block_size = 0;
     {
-      char* p = reinterpret_cast<char*>(&block_size);
-      const int got = gzread(gz_, p, 4);
+      const size_t got = in_.read(&block_size, 4);
       if (got == 0) return false;  // clean EOF
-      if (got < 0 || (got < 4 && !read_exact(p + got, (size_t)(4 - got)))) fatal("%s: truncated BAM record", fn_.c_str());
+      if (got < 4) fatal("%s: truncated BAM record", fn_.c_str());
     }
     if (block_size < 32) fatal("%s: malformed BAM record", fn_.c_str());
-    buf_.resize((size_t)block_size);
-    if (!read_exact(buf_.data(), buf_.size())) fatal("%s: truncated BAM record", fn_.c_str());
-    const uint8_t* b = buf_.data();
+    r.data.resize((size_t)block_size);
+    if (!read_exact(r.data.data(), r.data.size())) fatal("%s: truncated BAM record", fn_.c_str());
+    const uint8_t* b = r.data.data();
     auto i32 = [&](size_t off) { int32_t v; memcpy(&v, b + off, 4); return v; };
     auto u16 = [&](size_t off) { uint16_t v; memcpy(&v, b + off, 2); return v; };
     r.tid = i32(0);
     r.pos = i32(4);
     const uint32_t l_read_name = b[8];
     r.mapq = b[9];
-    const uint32_t n_cigar = u16(12);
+    r.n_cigar = u16(12);
     r.flag = u16(14);
     r.l_seq = i32(16);
-    size_t off = 32;
-    if (off + l_read_name + 4ull * n_cigar + (size_t)(r.l_seq + 1) / 2 + (size_t)r.l_seq > buf_.size() || r.l_seq < 0)
+    r.off_cigar = 32 + (size_t)l_read_name;
+    r.off_seq = r.off_cigar + 4ull * r.n_cigar;
+    r.off_qual = r.off_seq + (size_t)(r.l_seq < 0 ? 0 : r.l_seq + 1) / 2;
+    r.off_aux = r.off_qual + (size_t)(r.l_seq < 0 ? 0 : r.l_seq);
+    if (r.l_seq < 0 || l_read_name == 0 || r.off_aux > r.data.size() || b[32 + l_read_name - 1] != 0)
       fatal("%s: malformed BAM record", fn_.c_str());
-    r.qname.assign(reinterpret_cast<const char*>(b + off), l_read_name ? l_read_name - 1 : 0);
-    off += l_read_name;
-    r.cigar.resize(n_cigar);
-    if (n_cigar) memcpy(r.cigar.data(), b + off, 4ull * n_cigar);
-    off += 4ull * n_cigar;
-    static const char* kNt = "=ACMGRSVTWYHKDBN";
-    r.seq.resize((size_t)r.l_seq);
-    for (int32_t i = 0; i < r.l_seq; ++i) r.seq[i] = kNt[(b[off + (i >> 1)] >> ((~i & 1) << 2)) & 15];
-    off += (size_t)(r.l_seq + 1) / 2;
-    r.qual.resize((size_t)r.l_seq);
-    for (int32_t i = 0; i < r.l_seq; ++i) r.qual[i] = (char)(b[off + i] + 33);  // bam_get_qual_string
-    off += (size_t)r.l_seq;
-    r.aux.assign(b + off, b + buf_.size());
     return true;
   }
-  gzFile gz_ = NULL;
   std::string fn_;
-  std::vector<uint8_t> buf_;
+  BgzfStream in_;
 };
 
 constexpr int32_t kBamReadIndexNA = -1;  // BAM_READ_INDEX_NA (hts_utils.h)
@@ -182,8 +310,9 @@ inline void bam_base_at(const BamRecord& r, uint32_t pos, char& base, char& qual
   rpos = 0;
   base = 'N';
   qual = 0;
-  if (!r.cigar.empty()) {
-    for (uint32_t c : r.cigar) {
+  if (r.n_cigar) {
+    for (uint32_t ci = 0; ci < r.n_cigar; ++ci) {
+      const uint32_t c = r.cigar_at(ci);
       const char op = "MIDNSHP=XB??????"[c & 15];
       const uint32_t len = c >> 4;
       if (op == 'M') {
@@ -204,8 +333,8 @@ inline void bam_base_at(const BamRecord& r, uint32_t pos, char& base, char& qual
       }
     }
     if (rpos >= 0 && rpos <= rlen) {
-      base = (rpos < rlen) ? r.seq[(size_t)rpos] : '\0';  // the reference reads the string terminator at rpos == rlen
-      qual = (rpos < rlen) ? r.qual[(size_t)rpos] : '\0';
+      base = (rpos < rlen) ? r.base_at(rpos) : '\0';  // the reference reads the string terminator at rpos == rlen
+      qual = (rpos < rlen) ? r.qual_at(rpos) : '\0';
     } else {
       rpos = kBamReadIndexNA;
     }
@@ -382,6 +511,7 @@ inline void join_sam_vcf(const std::string& fn, const SamOptions& opt, VcfReader
   const char* gtag = opt.tagGroup.c_str();
   const char* utag = opt.tagUMI.c_str();
   BamRecord r;
+  std::string key;
   int64_t n_no_gtag = 0, n_no_utag = 0;
   std::vector<int32_t> tid_rid;  // cache of name2rid per BAM contig, refreshed when the VCF meets a new contig
   size_t tid_rid_for = 0;
@@ -435,13 +565,15 @@ inline void join_sam_vcf(const std::string& fn, const SamOptions& opt, VcfReader
           continue;
         }
       }
-      auto ins = cell_id.emplace(sbcd, (int32_t)st.bcs.size());
-      if (ins.second) {
-        st.bcs.push_back(sbcd);
+      key.assign(sbcd);  // (find first: emplace would build a node, and free it again, for every read)
+      auto it = cell_id.find(key);
+      if (it == cell_id.end()) {
+        it = cell_id.emplace(key, (int32_t)st.bcs.size()).first;
+        st.bcs.push_back(key);
         st.totl_reads.push_back(0);
         if (cell_numi) cell_numi->push_back(0);
       }
-      ibcd = ins.first->second;
+      ibcd = it->second;
     }
     ++js.nReadsTMP;
     // UMI
@@ -456,9 +588,13 @@ inline void join_sam_vcf(const std::string& fn, const SamOptions& opt, VcfReader
         if (t) z = t;
         else ++n_no_utag;
       }
-      auto ins = umi_id.emplace(z, (int32_t)umis.size());
-      if (ins.second) umis.push_back(ins.first->first);
-      iumi = ins.first->second;
+      key.assign(z);
+      auto it = umi_id.find(key);
+      if (it == umi_id.end()) {
+        it = umi_id.emplace(key, (int32_t)umis.size()).first;
+        umis.push_back(key);
+      }
+      iumi = it->second;
     }
     ++st.totl_reads[(size_t)ibcd];
     if (opt.collect_umi_loci && umi_loci) {  // dsc-pileup :296-331
@@ -469,9 +605,10 @@ inline void join_sam_vcf(const std::string& fn, const SamOptions& opt, VcfReader
         if (cell_numi) ++(*cell_numi)[(size_t)ibcd];
       }
       std::vector<UmiLocus>& loci = (*umi_loci)[ins.first->second].strand[(r.flag & 0x10) ? 1 : 0];
-      if (!r.cigar.empty()) {
+      if (r.n_cigar) {
         int32_t cpos = r.pos;
-        for (uint32_t c : r.cigar) {
+        for (uint32_t ci = 0; ci < r.n_cigar; ++ci) {
+          const uint32_t c = r.cigar_at(ci);
           const char op = "MIDNSHP=XB??????"[c & 15];
           const int32_t len = (int32_t)(c >> 4);
           if (op == 'M') {
