@@ -11,155 +11,12 @@
 // Parity unpinned: the reference's own --sam path needs htslib and cannot be run here; the tests check this
 // reader against BAM files written by an independent Python encoder and against the --plp path on the same reads.
 #pragma once
-#include <atomic>
-#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 
 #include "host_io.h"
 
 namespace hostio {
-
-// BGZF (SAM spec 4.1) is a series of independent gzip members of at most 64 KiB, each announcing its compressed
-// size in a 'BC' extra field: the blocks of a batch are inflated on all host cores at once and handed out as one
-// byte stream.  zlib's gzread on the same file is a single sequential inflate -- for a real 10-50 GB BAM the read
-// loop then IS the run time of dsc-pileup / demuxlet --sam.  A file that is not BGZF (plain gzip, or not compressed)
-// goes through gzread as before.
-class BgzfStream {
- public:
-  explicit BgzfStream(const std::string& fn) : fn_(fn) {
-    fp_ = fopen(fn.c_str(), "rb");
-    if (!fp_) fatal("Cannot open file %s for reading", fn.c_str());
-    unsigned char h[18];
-    const size_t got = fread(h, 1, sizeof(h), fp_);
-    bgzf_ = got == sizeof(h) && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C';
-    if (bgzf_) {
-      fseek(fp_, 0, SEEK_SET);
-      nthreads_ = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
-      if (const char* e = getenv("CRAMORE_BGZF_THREADS")) nthreads_ = std::max(1, atoi(e));
-    } else {
-      fclose(fp_);
-      fp_ = NULL;
-      gz_ = gzopen(fn.c_str(), "rb");
-      if (!gz_) fatal("Cannot open file %s for reading", fn.c_str());
-      gzbuffer(gz_, 1 << 20);
-    }
-  }
-  ~BgzfStream() {
-    if (fp_) fclose(fp_);
-    if (gz_) gzclose(gz_);
-  }
-  BgzfStream(const BgzfStream&) = delete;
-  BgzfStream& operator=(const BgzfStream&) = delete;
-  // up to n bytes; fewer only at the end of the file
-  size_t read(void* dst, size_t n) {
-    char* p = static_cast<char*>(dst);
-    size_t done = 0;
-    if (!bgzf_) {
-      while (done < n) {
-        const int got = gzread(gz_, p + done, (unsigned)std::min<size_t>(n - done, 1u << 30));
-        if (got < 0) fatal("%s: read error", fn_.c_str());
-        if (got == 0) break;
-        done += (size_t)got;
-      }
-      return done;
-    }
-    while (done < n) {
-      if (pos_ == out_.size() && !fill()) break;
-      const size_t take = std::min(n - done, out_.size() - pos_);
-      memcpy(p + done, out_.data() + pos_, take);
-      pos_ += take;
-      done += take;
-    }
-    return done;
-  }
-
- private:
-  struct Block {
-    size_t in_off, in_len, out_off, out_len;  // deflate payload inside in_, inflated bytes inside out_
-    uint32_t crc;
-  };
-  // reads the next batch of blocks and inflates it; false at the end of the file
-  bool fill() {
-    constexpr size_t kBatchBlocks = 1024;  // <= 64 MiB inflated
-    in_.clear();
-    std::vector<Block> blocks;
-    size_t out_total = 0;
-    unsigned char h[18];
-    while (blocks.size() < kBatchBlocks) {
-      const size_t got = fread(h, 1, 12, fp_);
-      if (got == 0) break;
-      if (got != 12 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) fatal("%s: malformed BGZF block header", fn_.c_str());
-      const size_t xlen = h[10] | ((size_t)h[11] << 8);
-      std::vector<unsigned char> extra(xlen);
-      if (fread(extra.data(), 1, xlen, fp_) != xlen) fatal("%s: truncated BGZF block", fn_.c_str());
-      size_t bsize = 0;
-      for (size_t i = 0; i + 4 <= xlen;) {
-        const size_t slen = extra[i + 2] | ((size_t)extra[i + 3] << 8);
-        if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2 && i + 6 <= xlen) bsize = (extra[i + 4] | ((size_t)extra[i + 5] << 8)) + 1;
-        i += 4 + slen;
-      }
-      if (bsize < 12 + xlen + 8) fatal("%s: BGZF block without a size field", fn_.c_str());
-      const size_t payload = bsize - 12 - xlen - 8;
-      const size_t off = in_.size();
-      in_.resize(off + payload + 8);
-      if (fread(in_.data() + off, 1, payload + 8, fp_) != payload + 8) fatal("%s: truncated BGZF block", fn_.c_str());
-      uint32_t crc, isize;
-      memcpy(&crc, in_.data() + off + payload, 4);
-      memcpy(&isize, in_.data() + off + payload + 4, 4);
-      if (isize > 65536) fatal("%s: BGZF block larger than 64 KiB", fn_.c_str());
-      if (isize == 0) {  // the empty end-of-file marker (or padding): nothing to inflate
-        in_.resize(off);
-        continue;
-      }
-      blocks.push_back({off, payload, out_total, isize, crc});
-      out_total += isize;
-    }
-    if (blocks.empty()) return false;
-    out_.resize(out_total);
-    pos_ = 0;
-    std::atomic<size_t> next{0};
-    std::atomic<int> bad{0};
-    auto work = [&]() {
-      z_stream zs;
-      memset(&zs, 0, sizeof(zs));
-      if (inflateInit2(&zs, -15) != Z_OK) {
-        bad = 1;
-        return;
-      }
-      for (size_t i = next++; i < blocks.size(); i = next++) {
-        const Block& b = blocks[i];
-        inflateReset(&zs);
-        zs.next_in = in_.data() + b.in_off;
-        zs.avail_in = (uInt)b.in_len;
-        zs.next_out = out_.data() + b.out_off;
-        zs.avail_out = (uInt)b.out_len;
-        const int rc = inflate(&zs, Z_FINISH);
-        if (rc != Z_STREAM_END || zs.avail_out != 0 ||
-            (uint32_t)crc32(crc32(0L, Z_NULL, 0), out_.data() + b.out_off, (uInt)b.out_len) != b.crc)
-          bad = 1;
-      }
-      inflateEnd(&zs);
-    };
-    const int nt = (int)std::min<size_t>((size_t)nthreads_, (blocks.size() + 15) / 16);
-    if (nt <= 1) {
-      work();
-    } else {
-      std::vector<std::thread> th;
-      for (int t = 0; t < nt; ++t) th.emplace_back(work);
-      for (auto& t : th) t.join();
-    }
-    if (bad) fatal("%s: corrupt BGZF block (inflate or CRC failed)", fn_.c_str());
-    return true;
-  }
-  std::string fn_;
-  FILE* fp_ = NULL;
-  gzFile gz_ = NULL;
-  bool bgzf_ = false;
-  int nthreads_ = 1;
-  std::vector<unsigned char> in_, out_;
-  size_t pos_ = 0;
-};
 
 struct BamRecord {
   int32_t tid = -1, pos = 0, l_seq = 0;

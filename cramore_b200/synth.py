@@ -239,6 +239,15 @@ def _bgzf_block(data):
             struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
 
 
+def bgzip(src, dst, block=60000):
+    """src re-written as BGZF (what `bgzip` / `bcftools view -Oz` produce): independent gzip members + EOF marker."""
+    data = open(src, "rb").read()
+    with open(dst, "wb") as f:
+        for i in range(0, len(data), block):
+            f.write(_bgzf_block(data[i:i + block]))
+        f.write(_bgzf_block(b""))
+
+
 def encode_bam_record(tid, pos, mapq, flag, cigar, seq, qual, qname="r", tags=()):
     """One alignment record.  cigar: [(op char, length)]; qual: raw Phred values; tags: [(two-letter tag, str)]."""
     import struct

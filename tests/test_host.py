@@ -680,3 +680,33 @@ def test_dsc_pileup_output_feeds_demuxlet_plp(built, tmp_path):
     for e in range(len(rp) - 1):
         assert sorted(zip(a["al.u8"][rp[e]:rp[e + 1]], a["bq.u8"][rp[e]:rp[e + 1]])) == \
                sorted(zip(b["al.u8"][rp[e]:rp[e + 1]], b["bq.u8"][rp[e]:rp[e + 1]])), e
+
+
+def test_vcf_plain_gzip_and_bgzf_give_the_same_inputs(built, tmp_path):
+    """The text readers take plain files, gzip and BGZF (bgzip / bcftools -Oz; blocks inflated in parallel): the engine
+    inputs built from the three forms of one VCF are identical, and a damaged block is an error, not silent garbage."""
+    import gzip
+    import shutil
+    from cramore_b200.synth import bgzip, make_dataset, write_plp, write_vcf
+    d = make_dataset("C1", nbcs=30, nsnps=3000, rbar=60, nv=12, seed=9, with_barcodes=True)   # ~0.5 MB of VCF: 9 blocks
+    pre = str(tmp_path / "in")
+    write_plp(d, pre)
+    write_vcf(d, pre + ".vcf")
+    with open(pre + ".vcf", "rb") as fi, gzip.open(pre + ".gz.vcf.gz", "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    bgzip(pre + ".vcf", pre + ".bgzf.vcf.gz")
+    assert os.path.getsize(pre + ".bgzf.vcf.gz") < os.path.getsize(pre + ".vcf") / 3
+    blobs = []
+    for vcf in (pre + ".vcf", pre + ".gz.vcf.gz", pre + ".bgzf.vcf.gz"):
+        dump = str(tmp_path / ("d%d" % len(blobs)))
+        r = subprocess.run([CRAMORE, "demuxlet", "--plp", pre, "--vcf", vcf, "--out", str(tmp_path / "o"), "--gpu-dump-inputs", dump],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        blobs.append(b"".join(open(dump + "." + n, "rb").read() for n in ("gp.f32", "snp_err.f64", "has_gp.u8", "snp_idx.i32")))
+    assert blobs[0] == blobs[1] == blobs[2] and len(blobs[0]) > 400000
+    raw = bytearray(open(pre + ".bgzf.vcf.gz", "rb").read())
+    raw[len(raw) // 2] ^= 0x5a
+    open(pre + ".bad.vcf.gz", "wb").write(bytes(raw))
+    r = subprocess.run([CRAMORE, "demuxlet", "--plp", pre, "--vcf", pre + ".bad.vcf.gz", "--out", str(tmp_path / "o"),
+                        "--gpu-dump-inputs", str(tmp_path / "bad")], capture_output=True, text=True)
+    assert r.returncode != 0 and "BGZF" in r.stderr
