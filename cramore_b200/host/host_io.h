@@ -184,11 +184,25 @@ class BgzfStream {
 };
 
 // ---- line reader over plain, gzip or BGZF text, fields split on white space (tsv_reader.cpp:27-55) ----
+// A BCF2 file (BGZF around the binary layout of the VCF 4.2 specification, section 6) is served as the lines of the
+// equivalent text VCF: header text first, then one line per record, numbers printed so that they parse back to the
+// stored value exactly (%.9g for float32).  Everything downstream -- the variant filter, parse_posteriors, INFO
+// look-ups -- therefore sees a BCF exactly as it sees a VCF, and gets the values htslib's typed accessors would
+// hand out.  Parity unpinned (no htslib here): checked against an independent BCF encoder in the tests.
 class LineReader {
  public:
-  explicit LineReader(const std::string& fn) : nlines(0), in_(fn), buf_(1 << 20), bpos_(0), blen_(0) {}
+  explicit LineReader(const std::string& fn) : nlines(0), fn_(fn), in_(fn), buf_(1 << 20), bpos_(0), blen_(0) {
+    blen_ = in_.read(buf_.data(), buf_.size());
+    if (blen_ >= 9 && memcmp(buf_.data(), "BCF\2\2", 5) == 0) open_bcf();
+  }
   bool next_line() {
     line.clear();
+    if (bcf_) {
+      if (hdr_next_ < hdr_lines_.size()) line = hdr_lines_[hdr_next_++];
+      else if (!bcf_record()) return false;
+      ++nlines;
+      return true;
+    }
     for (;;) {
       if (bpos_ == blen_) {
         blen_ = in_.read(buf_.data(), buf_.size());
@@ -230,9 +244,259 @@ class LineReader {
   int64_t nlines;
 
  private:
+  // bytes of the underlying stream, continuing after whatever next_line() has consumed
+  size_t raw(void* dst, size_t n) {
+    char* p = static_cast<char*>(dst);
+    size_t done = 0;
+    while (done < n) {
+      if (bpos_ == blen_) {
+        blen_ = in_.read(buf_.data(), buf_.size());
+        bpos_ = 0;
+        if (blen_ == 0) break;
+      }
+      const size_t take = std::min(n - done, blen_ - bpos_);
+      memcpy(p + done, buf_.data() + bpos_, take);
+      bpos_ += take;
+      done += take;
+    }
+    return done;
+  }
+  // ---- BCF2 ----
+  void open_bcf() {
+    bcf_ = true;
+    bpos_ = 5;
+    uint32_t l_text = 0;
+    if (raw(&l_text, 4) != 4) fatal("%s: truncated BCF header", fn_.c_str());
+    std::string text(l_text, '\0');
+    if (raw(&text[0], l_text) != l_text) fatal("%s: truncated BCF header", fn_.c_str());
+    while (!text.empty() && text.back() == '\0') text.pop_back();
+    size_t p = 0;
+    while (p < text.size()) {
+      size_t e = text.find('\n', p);
+      if (e == std::string::npos) e = text.size();
+      if (e > p) hdr_lines_.push_back(text.substr(p, e - p));
+      p = e + 1;
+    }
+    // dictionaries (VCF spec 6.2.1): FILTER / INFO / FORMAT ids share one, PASS is entry 0; contigs have their own.
+    // An IDX= field fixes the position, otherwise ids count up in order of first appearance.
+    auto put = [](std::vector<std::string>& dict, size_t idx, const std::string& id) {
+      if (dict.size() <= idx) dict.resize(idx + 1);
+      dict[idx] = id;
+    };
+    str_dict_.assign(1, "PASS");
+    for (const std::string& l : hdr_lines_) {
+      const bool is_str = l.compare(0, 10, "##FILTER=<") == 0 || l.compare(0, 8, "##INFO=<") == 0 || l.compare(0, 10, "##FORMAT=<") == 0;
+      const bool is_ctg = l.compare(0, 10, "##contig=<") == 0;
+      if (!is_str && !is_ctg) continue;
+      const size_t a = l.find("ID=");
+      if (a == std::string::npos) continue;
+      const std::string id = l.substr(a + 3, l.find_first_of(",>", a + 3) - a - 3);
+      const size_t x = l.find("IDX=");
+      std::vector<std::string>& dict = is_ctg ? ctg_dict_ : str_dict_;
+      if (x != std::string::npos) {
+        put(dict, (size_t)atol(l.c_str() + x + 4), id);
+      } else if (std::find(dict.begin(), dict.end(), id) == dict.end()) {
+        dict.push_back(id);
+      }
+    }
+  }
+  struct Typed {
+    int type;     // 0 missing-typed, 1 int8, 2 int16, 3 int32, 5 float, 7 char
+    size_t n;     // elements
+  };
+  static size_t type_size(int t) { return t == 1 || t == 7 ? 1 : t == 2 ? 2 : (t == 3 || t == 5) ? 4 : 0; }
+  Typed read_descriptor(const uint8_t*& p, const uint8_t* end) {
+    if (p >= end) fatal("%s: malformed BCF record", fn_.c_str());
+    const uint8_t b = *p++;
+    Typed t{b & 15, (size_t)(b >> 4)};
+    if (t.n == 15) {  // the real length follows as a typed integer
+      const Typed lt = read_descriptor(p, end);
+      int64_t v = 0;
+      if (!read_int(p, end, lt.type, &v) || v < 0) fatal("%s: malformed BCF record", fn_.c_str());
+      t.n = (size_t)v;
+    }
+    return t;
+  }
+  // one integer of the given type; false for "missing" and "end of vector" (flag says which)
+  bool read_int(const uint8_t*& p, const uint8_t* end, int type, int64_t* out, bool* eov = NULL) {
+    const size_t sz = type_size(type);
+    if (sz == 0 || type == 5 || type == 7 || p + sz > end) fatal("%s: malformed BCF record", fn_.c_str());
+    int64_t v = 0;
+    int64_t miss, stop;
+    if (type == 1) { int8_t x; memcpy(&x, p, 1); v = x; miss = INT8_MIN; stop = INT8_MIN + 1; }
+    else if (type == 2) { int16_t x; memcpy(&x, p, 2); v = x; miss = INT16_MIN; stop = INT16_MIN + 1; }
+    else { int32_t x; memcpy(&x, p, 4); v = x; miss = INT32_MIN; stop = (int64_t)INT32_MIN + 1; }
+    p += sz;
+    if (eov) *eov = (v == stop);
+    if (v == miss || v == stop) return false;
+    *out = v;
+    return true;
+  }
+  // text of a typed vector (comma separated; "." for missing); stops at an end-of-vector value
+  void append_values(std::string& out, const uint8_t*& p, const uint8_t* end, Typed t) {
+    char num[48];
+    if (t.type == 7) {
+      if (p + t.n > end) fatal("%s: malformed BCF record", fn_.c_str());
+      size_t n = 0;
+      while (n < t.n && p[n] != 0) ++n;
+      if (n == 0) out += '.';
+      else out.append(reinterpret_cast<const char*>(p), n);
+      p += t.n;
+      return;
+    }
+    bool any = false, stopped = false;
+    for (size_t i = 0; i < t.n; ++i) {
+      if (t.type == 5) {
+        if (p + 4 > end) fatal("%s: malformed BCF record", fn_.c_str());
+        uint32_t bits;
+        memcpy(&bits, p, 4);
+        p += 4;
+        if (stopped || bits == 0x7F800002u) { stopped = true; continue; }
+        if (any) out += ',';
+        if (bits == 0x7F800001u) out += '.';
+        else {
+          float f;
+          memcpy(&f, &bits, 4);
+          snprintf(num, sizeof(num), "%.9g", (double)f);
+          out += num;
+        }
+        any = true;
+      } else {
+        int64_t v = 0;
+        bool eov = false;
+        const bool ok = read_int(p, end, t.type, &v, &eov);
+        if (stopped || eov) { stopped = true; continue; }
+        if (any) out += ',';
+        if (!ok) out += '.';
+        else {
+          snprintf(num, sizeof(num), "%lld", (long long)v);
+          out += num;
+        }
+        any = true;
+      }
+    }
+    if (!any) out += '.';
+  }
+  const std::string& dict_name(const std::vector<std::string>& d, int64_t i) {
+    if (i < 0 || (size_t)i >= d.size() || d[(size_t)i].empty()) fatal("%s: BCF record refers to an id the header does not define", fn_.c_str());
+    return d[(size_t)i];
+  }
+  bool bcf_record() {
+    uint32_t len[2];
+    const size_t got = raw(len, 8);
+    if (got == 0) return false;
+    if (got != 8 || len[0] < 24) fatal("%s: truncated BCF record", fn_.c_str());
+    rec_.resize((size_t)len[0] + len[1]);
+    if (raw(rec_.data(), rec_.size()) != rec_.size()) fatal("%s: truncated BCF record", fn_.c_str());
+    const uint8_t* p = rec_.data();
+    const uint8_t* end = p + len[0];
+    int32_t chrom, pos, rlen;
+    uint32_t qbits, n_allele_info, n_fmt_sample;
+    memcpy(&chrom, p, 4); memcpy(&pos, p + 4, 4); memcpy(&rlen, p + 8, 4); memcpy(&qbits, p + 12, 4);
+    memcpy(&n_allele_info, p + 16, 4); memcpy(&n_fmt_sample, p + 20, 4);
+    p += 24;
+    const uint32_t n_allele = n_allele_info >> 16, n_info = n_allele_info & 0xffff;
+    const uint32_t n_fmt = n_fmt_sample >> 24, n_sample = n_fmt_sample & 0xffffff;
+    char num[64];
+    line = dict_name(ctg_dict_, chrom);
+    snprintf(num, sizeof(num), "\t%d\t", pos + 1);
+    line += num;
+    append_values(line, p, end, read_descriptor(p, end));  // ID
+    for (uint32_t a = 0; a < n_allele; ++a) {                // REF, then ALT comma separated
+      line += (a == 0) ? '\t' : (a == 1 ? '\t' : ',');
+      append_values(line, p, end, read_descriptor(p, end));
+    }
+    if (n_allele < 2) line += "\t.";
+    if (qbits == 0x7F800001u) line += "\t.";
+    else {
+      float q;
+      memcpy(&q, &qbits, 4);
+      snprintf(num, sizeof(num), "\t%.9g", (double)q);
+      line += num;
+    }
+    {  // FILTER
+      const Typed t = read_descriptor(p, end);
+      line += '\t';
+      if (t.n == 0) line += '.';
+      for (size_t i = 0; i < t.n; ++i) {
+        int64_t v = 0;
+        if (!read_int(p, end, t.type, &v)) continue;
+        if (i) line += ';';
+        line += dict_name(str_dict_, v);
+      }
+    }
+    line += '\t';
+    if (n_info == 0) line += '.';
+    for (uint32_t i = 0; i < n_info; ++i) {
+      const Typed kt = read_descriptor(p, end);
+      int64_t key = 0;
+      if (kt.n != 1 || !read_int(p, end, kt.type, &key)) fatal("%s: malformed BCF INFO key", fn_.c_str());
+      if (i) line += ';';
+      line += dict_name(str_dict_, key);
+      const Typed vt = read_descriptor(p, end);
+      if (vt.n == 0) continue;  // a flag
+      line += '=';
+      append_values(line, p, end, vt);
+    }
+    if (n_fmt == 0 || n_sample == 0) return true;
+    // FORMAT: one typed matrix [n_sample][n] per key; columns are gathered per sample afterwards
+    p = rec_.data() + len[0];
+    end = p + len[1];
+    std::vector<std::string> keys(n_fmt);
+    cols_.assign((size_t)n_fmt * n_sample, std::string());
+    for (uint32_t f = 0; f < n_fmt; ++f) {
+      const Typed kt = read_descriptor(p, end);
+      int64_t key = 0;
+      if (kt.n != 1 || !read_int(p, end, kt.type, &key)) fatal("%s: malformed BCF FORMAT key", fn_.c_str());
+      keys[f] = dict_name(str_dict_, key);
+      const Typed vt = read_descriptor(p, end);
+      const bool is_gt = keys[f] == "GT";
+      for (uint32_t sm = 0; sm < n_sample; ++sm) {
+        std::string& out = cols_[(size_t)f * n_sample + sm];
+        if (!is_gt) {
+          append_values(out, p, end, vt);
+          continue;
+        }
+        bool any = false, stopped = false;  // (allele + 1) << 1 | phased; 0 = missing allele
+        for (size_t i = 0; i < vt.n; ++i) {
+          int64_t v = 0;
+          bool eov = false;
+          const bool ok = read_int(p, end, vt.type, &v, &eov);
+          if (stopped || eov) { stopped = true; continue; }
+          if (!ok) v = 0;
+          if (any) out += (v & 1) ? '|' : '/';
+          if ((v >> 1) == 0) out += '.';
+          else {
+            snprintf(num, sizeof(num), "%lld", (long long)((v >> 1) - 1));
+            out += num;
+          }
+          any = true;
+        }
+        if (!any) out += '.';
+      }
+    }
+    line += '\t';
+    for (uint32_t f = 0; f < n_fmt; ++f) {
+      if (f) line += ':';
+      line += keys[f];
+    }
+    for (uint32_t sm = 0; sm < n_sample; ++sm) {
+      line += '\t';
+      for (uint32_t f = 0; f < n_fmt; ++f) {
+        if (f) line += ':';
+        line += cols_[(size_t)f * n_sample + sm];
+      }
+    }
+    return true;
+  }
+  std::string fn_;
   BgzfStream in_;
   std::vector<char> buf_;
   size_t bpos_, blen_;
+  bool bcf_ = false;
+  std::vector<std::string> hdr_lines_, str_dict_, ctg_dict_, cols_;
+  size_t hdr_next_ = 0;
+  std::vector<uint8_t> rec_;
 };
 
 // ---- gz / plain writer with printf (hts_utils.cpp:1018-1038) ----

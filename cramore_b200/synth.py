@@ -239,6 +239,48 @@ def _bgzf_block(data):
             struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
 
 
+def write_bcf(d, path, chrom="1", with_r2=False, lead_decoy=False):
+    """The records of write_vcf as BCF2.2 (VCF spec section 6: BGZF around typed binary records), written from the
+    specification with Python's struct -- an encoder independent of the reader under test.  GP values are the float32
+    of the VCF's decimals, which is what a text -> BCF conversion stores."""
+    import struct
+    text = ("##fileformat=VCFv4.2\n##FILTER=<ID=PASS,Description=\"All filters passed\">\n##contig=<ID=%s>\n"
+            '##INFO=<ID=R2,Number=1,Type=Float,Description="imputation r2">\n'
+            '##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">\n'
+            '##FORMAT=<ID=GP,Number=G,Type=Float,Description="Genotype posterior">\n'
+            "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" % chrom) + "\t".join(d["sample_ids"]) + "\n"
+    PASS, R2, GT, GP = 0, 1, 2, 3  # dictionary positions: order of first appearance, PASS first
+    hdr = text.encode() + b"\0"
+    blob = [b"BCF\2\2", struct.pack("<I", len(hdr)), hdr]
+    geno = np.asarray(d["geno"])
+    nv = len(d["sample_ids"])
+    gp_of = {0: (0.98, 0.01, 0.01), 1: (0.01, 0.98, 0.01), 2: (0.01, 0.01, 0.98)}
+
+    def record(pos1, alt, genos):
+        shared = struct.pack("<iiiI", 0, pos1 - 1, 1, 0x7F800001)                 # CHROM, POS0, rlen, QUAL missing
+        shared += struct.pack("<II", (2 << 16) | (1 if with_r2 else 0), (2 << 24) | nv)
+        shared += b"\x07"                                                        # ID: empty string
+        shared += b"\x17A" + b"\x17" + alt.encode()                              # REF, ALT
+        shared += b"\x11" + struct.pack("<b", PASS)                               # FILTER
+        if with_r2:
+            shared += b"\x11" + struct.pack("<b", R2) + b"\x15" + struct.pack("<f", 0.9)
+        indiv = b"\x11" + struct.pack("<b", GT) + b"\x21"
+        indiv += b"".join(struct.pack("<bb", ((1 if g >= 1 else 0) + 1) << 1, ((1 if g == 2 else 0) + 1) << 1) for g in genos)
+        indiv += b"\x11" + struct.pack("<b", GP) + b"\x35"
+        indiv += b"".join(struct.pack("<fff", *gp_of[int(g)]) for g in genos)
+        return struct.pack("<II", len(shared), len(indiv)) + shared + indiv
+
+    if lead_decoy:
+        blob.append(record(500, "C", [1] * nv))
+    for s in range(d["nsnps"]):
+        blob.append(record(1000 + 10 * s, "G", geno[s]))
+    data = b"".join(blob)
+    with open(path, "wb") as f:
+        for i in range(0, len(data), 60000):
+            f.write(_bgzf_block(data[i:i + 60000]))
+        f.write(_bgzf_block(b""))
+
+
 def bgzip(src, dst, block=60000):
     """src re-written as BGZF (what `bgzip` / `bcftools view -Oz` produce): independent gzip members + EOF marker."""
     data = open(src, "rb").read()

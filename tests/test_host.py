@@ -710,3 +710,98 @@ def test_vcf_plain_gzip_and_bgzf_give_the_same_inputs(built, tmp_path):
     r = subprocess.run([CRAMORE, "demuxlet", "--plp", pre, "--vcf", pre + ".bad.vcf.gz", "--out", str(tmp_path / "o"),
                         "--gpu-dump-inputs", str(tmp_path / "bad")], capture_output=True, text=True)
     assert r.returncode != 0 and "BGZF" in r.stderr
+
+
+def test_bcf_input_equals_vcf_input(built, tmp_path):
+    """A BCF2 file (written by an independent encoder, cramore_b200.synth.write_bcf) gives the engine inputs of the
+    text VCF with the same records, bit for bit: float32 posteriors, the R2-dependent error, the --min-mac filter
+    from GT, and the dsc-pileup .var.gz from the same sites."""
+    from cramore_b200.synth import make_dataset, write_bam, write_bcf, write_plp, write_vcf
+    d = make_dataset("C1", nbcs=25, nsnps=900, rbar=60, nv=9, seed=19, with_barcodes=True)
+    pre = str(tmp_path / "in")
+    write_plp(d, pre)
+    write_vcf(d, pre + ".vcf", with_r2=True)
+    write_bcf(d, pre + ".bcf", with_r2=True)
+    blobs = []
+    for vcf in (pre + ".vcf", pre + ".bcf"):
+        for field in ("GP", "GT"):
+            dump = str(tmp_path / ("d%d" % len(blobs)))
+            r = subprocess.run([CRAMORE, "demuxlet", "--plp", pre, "--vcf", vcf, "--field", field, "--geno-error-coeff", "0.4",
+                                "--out", str(tmp_path / "o"), "--gpu-dump-inputs", dump], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-2000:]
+            blobs.append(b"".join(open(dump + "." + n, "rb").read() for n in ("gp.f32", "snp_err.f64", "has_gp.u8", "snp_idx.i32"))
+                         + open(dump + ".samples.txt", "rb").read())
+    assert blobs[0] == blobs[2] and blobs[1] == blobs[3] and blobs[0] != blobs[1] and len(blobs[0]) > 90000
+    has = np.fromfile(str(tmp_path / "d0.has_gp.u8"), np.uint8)
+    assert 0 < has.sum() < len(has)   # the GT-based filter dropped some sites, in both forms alike
+    # the same through the BAM x VCF join of dsc-pileup (--sm: allele frequencies from the genotypes)
+    write_bam(d, pre + ".bam")
+    outs = []
+    for vcf in (pre + ".vcf", pre + ".bcf"):
+        out = str(tmp_path / ("p%d" % len(outs)))
+        r = subprocess.run([CRAMORE, "dsc-pileup", "--sam", pre + ".bam", "--vcf", vcf, "--out", out, "--sm", d["sample_ids"][2],
+                            "--sm", d["sample_ids"][5]], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(_gunzip(out + ".var.gz") + _gunzip(out + ".plp.gz"))
+    assert outs[0] == outs[1] and len(outs[0]) > 20000
+
+
+def test_bcf_decoder_on_hand_encoded_records(built, tmp_path):
+    """The BCF2 decoder on records built byte by byte from the specification (VCF 4.2, section 6.3): dictionary order
+    with and without IDX=, typed integers of 8/16/32 bits, a length that needs the 15+ escape, missing values and
+    end-of-vector padding, phased and half-missing genotypes, flags, strings, several filters, multi-allelic sites."""
+    import struct
+    from cramore_b200.synth import _bgzf_block
+    text = ("##fileformat=VCFv4.2\n##FILTER=<ID=PASS,Description=\"ok\">\n##FILTER=<ID=q10,Description=\"low\">\n"
+            "##contig=<ID=chrA>\n##contig=<ID=chrB>\n"
+            "##INFO=<ID=DP,Number=1,Type=Integer,Description=\"d\">\n##INFO=<ID=DB,Number=0,Type=Flag,Description=\"f\">\n"
+            "##INFO=<ID=AF,Number=A,Type=Float,Description=\"a\">\n##INFO=<ID=NOTE,Number=1,Type=String,Description=\"s\">\n"
+            "##FORMAT=<ID=GT,Number=1,Type=String,Description=\"g\">\n##FORMAT=<ID=PL,Number=G,Type=Integer,Description=\"p\">\n"
+            "##FORMAT=<ID=GP,Number=G,Type=Float,Description=\"p\",IDX=9>\n"
+            "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\tS2\n")
+    # dictionary: PASS 0, q10 1, DP 2, DB 3, AF 4, NOTE 5, GT 6, PL 7, GP 9 (IDX)
+    hdr = text.encode() + b"\0"
+
+    def tstr(sv):
+        b = sv.encode()
+        return (bytes([(len(b) << 4) | 7]) if len(b) < 15 else b"\xf7\x11" + bytes([len(b)])) + b
+
+    def rec(chrom, pos0, rid, alleles, qual, filters, info, fmt, n_sample=2):
+        sh = struct.pack("<iii", chrom, pos0, len(alleles[0])) + (struct.pack("<I", 0x7F800001) if qual is None else struct.pack("<f", qual))
+        sh += struct.pack("<II", (len(alleles) << 16) | len(info), (len(fmt) << 24) | n_sample)
+        sh += tstr(rid) + b"".join(tstr(a) for a in alleles)
+        sh += bytes([(len(filters) << 4) | 1]) + bytes(filters) if filters else b"\x00"
+        sh += b"".join(info)
+        ind = b"".join(fmt)
+        return struct.pack("<II", len(sh), len(ind)) + sh + ind
+
+    r1 = rec(0, 99, "rs1", ["A", "G"], 30.5, [0],
+             [b"\x11\x02" + b"\x12" + struct.pack("<h", 1000),            # DP=1000 as int16
+              b"\x11\x03" + b"\x00",                                        # DB flag
+              b"\x11\x04" + b"\x15" + struct.pack("<f", 0.25)],             # AF=0.25
+             [b"\x11\x06" + b"\x21" + bytes([2, 5, 4, 0x81]),               # GT: 0|1 and haploid 1 (end-of-vector padded)
+              b"\x11\x07" + b"\x32" + struct.pack("<hhhhhh", 0, 30, 300, 255, -32768, 0),   # PL, one missing
+              b"\x11\x09" + b"\x35" + struct.pack("<fff", 0.98, 0.01, 0.01) + struct.pack("<III", 0x7F800001, 0x7F800002, 0x7F800002)])
+    note = "a-string-of-more-than-fifteen-characters"
+    r2 = rec(1, 1999999, "", ["AT", "A", "ATT"], None, [0, 1],
+             [b"\x11\x02" + b"\x13" + struct.pack("<i", 70000),             # DP as int32
+              b"\x11\x05" + tstr(note),
+              b"\x11\x04" + b"\x25" + struct.pack("<f", 0.5) + struct.pack("<I", 0x7F800001)],   # AF=0.5,.
+             [b"\x11\x06" + b"\x21" + bytes([0, 2, 6, 4])])                 # GT: ./0 and 2/1
+    r3 = rec(0, 5, "x", ["C"], 0.0, [], [], [], n_sample=0)               # no ALT, no FILTER, no INFO, sites only
+    data = b"BCF\2\2" + struct.pack("<I", len(hdr)) + hdr + r1 + r2 + r3
+    path = str(tmp_path / "t.bcf")
+    with open(path, "wb") as f:
+        for i in range(0, len(data), 100):     # tiny blocks: records and even length fields straddle block borders
+            f.write(_bgzf_block(data[i:i + 100]))
+        f.write(_bgzf_block(b""))
+    r = subprocess.run([CRAMORE, "vcf-text", path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    assert lines[:len(text.splitlines())] == text.splitlines()
+    body = lines[len(text.splitlines()):]
+    assert body == [
+        "chrA\t100\trs1\tA\tG\t30.5\tPASS\tDP=1000;DB;AF=0.25\tGT:PL:GP\t0|1:0,30,300:0.980000019,0.00999999978,0.00999999978\t1:255,.,0:.",
+        "chrB\t2000000\t.\tAT\tA,ATT\t.\tPASS;q10\tDP=70000;NOTE=%s;AF=0.5,.\tGT\t./0\t2/1" % note,
+        "chrA\t6\tx\tC\t.\t0\t.\t.",
+    ]
