@@ -3,7 +3,7 @@
 // The reference reads SAM/BAM/CRAM through htslib (sam_filtered_reader.cpp) and joins the coordinate-sorted reads
 // with the VCF on the fly (cmd_cram_demuxlet.cpp:126-395).  htslib is not available to this build; BAM, however, is
 // a plain format: BGZF blocks are gzip members (zlib reads a concatenation of them transparently) around
-// little-endian records (SAM spec section 4).  This header reads BAM (not SAM text, not CRAM), applies the
+// little-endian records (SAM spec section 4).  This header reads BAM and SAM text (not CRAM), applies the
 // reference's read filter (--min-MQ, --excl-flag, sam_filtered_reader.cpp:298-310), finds the base a read shows at a
 // SNP the way bam_get_base_and_qual_and_read_and_qual does (hts_utils.cpp:279-358 -- including its quirk that only
 // CIGAR 'M' counts as aligned, '=' and 'X' are ignored), and builds the droplet store with the duplicate rule of
@@ -11,6 +11,7 @@
 // Parity unpinned: the reference's own --sam path needs htslib and cannot be run here; the tests check this
 // reader against BAM files written by an independent Python encoder and against the --plp path on the same reads.
 #pragma once
+#include <memory>
 #include <unordered_map>
 #include <unordered_set>
 
@@ -91,10 +92,31 @@ class BamReader {
   uint32_t exclude_flag = 0x0f04;
 
   explicit BamReader(const std::string& fn) : fn_(fn), in_(fn) {
-    char magic[4];
-    if (!read_exact(magic, 4) || memcmp(magic, "BAM\1", 4) != 0)
-      fatal("%s is not a BAM file (SAM text and CRAM need htslib, which this build does not include; convert with "
-            "`samtools view -b`)", fn.c_str());
+    char magic[4] = {0, 0, 0, 0};
+    const bool got4 = read_exact(magic, 4);
+    if (got4 && memcmp(magic, "CRAM", 4) == 0)
+      fatal("%s is a CRAM file: CRAM needs htslib (reference-based codecs), which this build does not include; convert "
+            "with `samtools view -b`", fn.c_str());
+    if (!got4 || memcmp(magic, "BAM\1", 4) != 0) {
+      // SAM text (plain or gzip): header lines give the contigs, alignment lines are re-encoded as BAM records
+      if (!got4 || magic[0] != '@') fatal("%s is neither BAM nor SAM text with a header", fn.c_str());
+      sam_.reset(new LineReader(fn));
+      while (sam_->next_line()) {
+        const std::string& l = sam_->line;
+        if (l.empty() || l[0] != '@') {
+          sam_pending_ = true;
+          break;
+        }
+        if (l.compare(0, 4, "@SQ\t") == 0) {
+          const size_t a = l.find("\tSN:");
+          if (a == std::string::npos) fatal("%s: @SQ line without SN", fn.c_str());
+          const size_t e = l.find('\t', a + 4);
+          refs.push_back(l.substr(a + 4, e == std::string::npos ? std::string::npos : e - a - 4));
+        }
+      }
+      for (size_t i = 0; i < refs.size(); ++i) ref_id_.emplace(refs[i], (int32_t)i);
+      return;
+    }
     const int32_t l_text = read_i32();
     std::string text((size_t)std::max(l_text, 0), '\0');
     if (l_text > 0 && !read_exact(&text[0], (size_t)l_text)) fatal("%s: truncated BAM header", fn.c_str());
@@ -125,7 +147,114 @@ class BamReader {
     if (!read_exact(&v, 4)) fatal("%s: truncated BAM file", fn_.c_str());
     return v;
   }
+  // one SAM text line -> the BAM layout of the same alignment (SAM spec 1.4 / 4.2); tags other than A, i, f, Z, H
+  // are dropped (nothing downstream reads them)
+  bool next_sam(BamRecord& r) {
+    if (!sam_pending_ && !sam_->next_line()) return false;
+    sam_pending_ = false;
+    std::string& l = sam_->line;
+    std::vector<char*> f;
+    char* p = &l[0];
+    f.push_back(p);
+    for (; *p; ++p)
+      if (*p == '\t') {
+        *p = '\0';
+        f.push_back(p + 1);
+      }
+    if (f.size() < 11) fatal("%s: SAM line %lld has %zu fields", fn_.c_str(), (long long)sam_->nlines, f.size());
+    const size_t l_name = strlen(f[0]) + 1;
+    if (l_name > 255) fatal("%s: read name too long", fn_.c_str());
+    int32_t tid = -1;
+    if (strcmp(f[2], "*") != 0) {
+      auto it = ref_id_.find(f[2]);
+      if (it == ref_id_.end()) fatal("%s: contig %s is not in the header", fn_.c_str(), f[2]);
+      tid = it->second;
+    }
+    std::vector<uint32_t> cig;
+    if (strcmp(f[5], "*") != 0)
+      for (const char* c = f[5]; *c;) {
+        char* e;
+        const unsigned long n = strtoul(c, &e, 10);
+        const char* op = strchr("MIDNSHP=X", *e);
+        if (e == c || !*e || !op) fatal("%s: malformed CIGAR %s", fn_.c_str(), f[5]);
+        cig.push_back((uint32_t)(n << 4) | (uint32_t)(op - "MIDNSHP=X"));
+        c = e + 1;
+      }
+    const bool has_seq = strcmp(f[9], "*") != 0;
+    const int32_t l_seq = has_seq ? (int32_t)strlen(f[9]) : 0;
+    std::vector<uint8_t>& d = r.data;
+    d.assign(32, 0);
+    auto put32 = [&](size_t off, int32_t v) { memcpy(d.data() + off, &v, 4); };
+    put32(0, tid);
+    put32(4, atoi(f[3]) - 1);
+    d[8] = (uint8_t)l_name;
+    d[9] = (uint8_t)atoi(f[4]);
+    const uint16_t ncig = (uint16_t)cig.size(), flag = (uint16_t)strtoul(f[1], NULL, 0);
+    memcpy(d.data() + 12, &ncig, 2);
+    memcpy(d.data() + 14, &flag, 2);
+    put32(16, l_seq);
+    put32(20, -1);
+    put32(24, -1);
+    d.insert(d.end(), f[0], f[0] + l_name);
+    for (uint32_t c : cig) {
+      uint8_t b[4];
+      memcpy(b, &c, 4);
+      d.insert(d.end(), b, b + 4);
+    }
+    static const char* kNt = "=ACMGRSVTWYHKDBN";
+    for (int32_t i = 0; i < l_seq; i += 2) {
+      auto code = [&](char ch) {
+        const char* q = strchr(kNt, toupper((unsigned char)ch));
+        return (uint8_t)(q && ch ? q - kNt : 15);
+      };
+      d.push_back((uint8_t)((code(f[9][i]) << 4) | (i + 1 < l_seq ? code(f[9][i + 1]) : 0)));
+    }
+    const bool has_qual = strcmp(f[10], "*") != 0;
+    for (int32_t i = 0; i < l_seq; ++i) d.push_back(has_qual && f[10][i] ? (uint8_t)(f[10][i] - 33) : 0xff);
+    for (size_t t = 11; t < f.size(); ++t) {
+      const char* a = f[t];
+      if (strlen(a) < 5 || a[2] != ':' || a[4] != ':') continue;
+      const char ty = a[3];
+      const char* v = a + 5;
+      if (ty == 'Z' || ty == 'H') {
+        d.push_back((uint8_t)a[0]);
+        d.push_back((uint8_t)a[1]);
+        d.push_back((uint8_t)ty);
+        d.insert(d.end(), v, v + strlen(v) + 1);
+      } else if (ty == 'A') {
+        d.push_back((uint8_t)a[0]);
+        d.push_back((uint8_t)a[1]);
+        d.push_back('A');
+        d.push_back((uint8_t)v[0]);
+      } else if (ty == 'i' || ty == 'f') {
+        d.push_back((uint8_t)a[0]);
+        d.push_back((uint8_t)a[1]);
+        d.push_back((uint8_t)ty);
+        uint8_t b[4];
+        if (ty == 'i') {
+          const int32_t x = (int32_t)strtol(v, NULL, 10);
+          memcpy(b, &x, 4);
+        } else {
+          const float x = strtof(v, NULL);
+          memcpy(b, &x, 4);
+        }
+        d.insert(d.end(), b, b + 4);
+      }
+    }
+    r.tid = tid;
+    r.pos = atoi(f[3]) - 1;
+    r.mapq = d[9];
+    r.n_cigar = ncig;
+    r.flag = flag;
+    r.l_seq = l_seq;
+    r.off_cigar = 32 + l_name;
+    r.off_seq = r.off_cigar + 4ull * ncig;
+    r.off_qual = r.off_seq + (size_t)(l_seq + 1) / 2;
+    r.off_aux = r.off_qual + (size_t)l_seq;
+    return true;
+  }
   bool next(BamRecord& r) {
+    if (sam_) return next_sam(r);
     int32_t block_size = 0;
     {
       const size_t got = in_.read(&block_size, 4);
@@ -155,6 +284,9 @@ class BamReader {
   }
   std::string fn_;
   BgzfStream in_;
+  std::unique_ptr<LineReader> sam_;  // set when the input is SAM text
+  bool sam_pending_ = false;         // sam_->line already holds the first alignment line
+  std::unordered_map<std::string, int32_t> ref_id_;
 };
 
 constexpr int32_t kBamReadIndexNA = -1;  // BAM_READ_INDEX_NA (hts_utils.h)

@@ -805,3 +805,39 @@ def test_bcf_decoder_on_hand_encoded_records(built, tmp_path):
         "chrB\t2000000\t.\tAT\tA,ATT\t.\tPASS;q10\tDP=70000;NOTE=%s;AF=0.5,.\tGT\t./0\t2/1" % note,
         "chrA\t6\tx\tC\t.\t0\t.\t.",
     ]
+
+
+def _bam_to_sam(bam, sam, gz=False):
+    """SAM text of a BAM written by the test encoder (decoded by the oracle's Python BAM parser)."""
+    import gzip
+    from oracle import dsc_pileup_py
+    refs, recs = dsc_pileup_py.read_bam(bam)
+    opener = gzip.open if gz else open
+    with opener(sam, "wt") as f:
+        f.write("@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:100000\n" % n for n in refs) + "@PG\tID:test\n")
+        for i, r in enumerate(recs):
+            cigar = "".join("%d%s" % (n, op) for op, n in r["cigar"]) or "*"
+            qual = "".join(chr(q + 33) for q in r["qual"]) or "*"
+            tags = "".join("\t%s:Z:%s" % kv for kv in r["tags"].items()) + "\tNM:i:%d\tXS:A:+\tXF:f:0.5" % (i % 3)
+            f.write("r%d\t%d\t%s\t%d\t%d\t%s\t*\t0\t0\t%s\t%s%s\n" % (
+                i, r["flag"], refs[r["tid"]] if r["tid"] >= 0 else "*", r["pos"] + 1, r["mapq"], cigar, r["seq"] or "*", qual, tags))
+
+
+@pytest.mark.parametrize("gz", [False, True])
+def test_sam_text_input_equals_bam_input(built, tmp_path, gz):
+    """--sam takes SAM text (plain or gzip) as well: every alignment line is re-encoded into the BAM record layout,
+    so dsc-pileup writes the same four files from either form of the same alignments."""
+    pre, _ = _random_alignments(tmp_path, 21)
+    sam = pre + (".sam.gz" if gz else ".sam")
+    _bam_to_sam(pre + ".bam", sam, gz)
+    outs = []
+    for src in (pre + ".bam", sam):
+        out = str(tmp_path / ("o%d" % len(outs)))
+        r = subprocess.run([CRAMORE, "dsc-pileup", "--sam", src, "--vcf", pre + ".vcf", "--out", out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([_gunzip(out + "." + ext + ".gz") for ext in ("cel", "var", "plp", "umi")])
+    assert outs[0] == outs[1] and len(outs[0][2].splitlines()) > 150
+    open(pre + ".cram", "wb").write(b"CRAM\3\0" + b"\0" * 40)
+    r = subprocess.run([CRAMORE, "dsc-pileup", "--sam", pre + ".cram", "--vcf", pre + ".vcf", "--out", str(tmp_path / "c")],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "CRAM" in r.stderr
