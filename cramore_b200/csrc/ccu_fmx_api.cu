@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
+#include <thread>
 #include <vector>
 
 #include "ccu_handle.h"
@@ -35,15 +36,17 @@ struct FmxState {
   // peer-memory exchange: every rank's posterior / assignment array (CUDA IPC mappings; [peer_rank] is our own)
   ccu::FmxPeers peers = {};
   int32_t peer_rank = -1;
+  bool peers_are_ipc = true;  // false: pointers of other handles of this process (nothing to unmap)
   void close_peers() {
     for (int r = 0; r < peers.n; ++r)
-      if (r != peer_rank) {
+      if (r != peer_rank && peers_are_ipc) {
         if (peers.post[r]) cudaIpcCloseMemHandle(peers.post[r]);
         if (peers.assign[r]) cudaIpcCloseMemHandle(peers.assign[r]);
         if (peers.flags[r]) cudaIpcCloseMemHandle(peers.flags[r]);
       }
     peers = {};
     peer_rank = -1;
+    peers_are_ipc = true;
   }
   void release() {
     close_peers();
@@ -608,6 +611,139 @@ int ccu_fmx_run_em(ccu_handle* h, const int32_t* init_assign, int32_t niter, int
   f->tm.ms_mstep = ms_m / (it > 0 ? it : 1);
   if (iters_run) *iters_run = it;
   return ccu_fmx_download_results(h, out);
+}
+
+// ---- in-process multi-GPU EM: one host thread per handle, exchange through peer memory ----
+int ccu_fmx_run_em_multi(ccu_handle** hs, int32_t n, const int64_t* cell_ptr, const int32_t* snp_idx,
+                         const int32_t* init_assign, int32_t niter, int32_t geno_error_every_iter, ccu_fmx_result* out,
+                         ccu_pileup* clusters_out) {
+  if (!hs || n < 1 || !hs[0]) return 1;
+  ccu_handle* h0 = hs[0];
+  if (n > ccu::kMaxPeers) return ccu_fail(h0, "ccu_fmx_run_em_multi: at most %d handles", ccu::kMaxPeers);
+  if (niter < 1) return ccu_fail(h0, "ccu_fmx_run_em_multi: niter must be >= 1");
+  for (int i = 0; i < n; ++i) {
+    if (!hs[i]) return ccu_fail(h0, "ccu_fmx_run_em_multi: NULL handle");
+    if (int rc = need(hs[i], true, "ccu_fmx_run_em_multi")) return rc;
+    const FmxState *a = hs[i]->fmx, *b = h0->fmx;
+    if (a->nbcs != b->nbcs || a->nsnps != b->nsnps || a->nnz != b->nnz || a->K != b->K || a->geno_error != b->geno_error ||
+        a->doublet_prior != b->doublet_prior)
+      return ccu_fail(h0, "ccu_fmx_run_em_multi: handle %d holds a different store or configuration", i);
+    for (int j = 0; j < i; ++j)
+      if (hs[j] == hs[i]) return ccu_fail(h0, "ccu_fmx_run_em_multi: handle %d given twice", i);
+  }
+  const FmxState* f0 = h0->fmx;
+  const int64_t nbcs = f0->nbcs, nsnps = f0->nsnps, nnz = f0->nnz;
+  if (nbcs > 0 && (!cell_ptr || !init_assign || !out)) return ccu_fail(h0, "ccu_fmx_run_em_multi: NULL argument");
+  if (nnz > 0 && !snp_idx) return ccu_fail(h0, "ccu_fmx_run_em_multi: NULL snp_idx");
+  // droplet ranges and SNP slabs with about nnz / n entries each
+  std::vector<int64_t> cb(n + 1, nbcs), sb(n + 1, nsnps);
+  cb[0] = sb[0] = 0;
+  {
+    std::vector<int64_t> per_snp((size_t)nsnps + 1, 0);
+    for (int64_t e = 0; e < nnz; ++e) ++per_snp[(size_t)snp_idx[e] + 1];
+    for (int64_t v = 0; v < nsnps; ++v) per_snp[(size_t)v + 1] += per_snp[(size_t)v];
+    for (int i = 1; i < n; ++i) {
+      const int64_t target = nnz * i / n;
+      cb[i] = std::lower_bound(cell_ptr, cell_ptr + nbcs + 1, target) - cell_ptr;
+      cb[i] = std::min(std::max(cb[i], cb[i - 1]), nbcs);
+      sb[i] = std::lower_bound(per_snp.begin(), per_snp.end(), target) - per_snp.begin();
+      sb[i] = std::min(std::max(sb[i], sb[i - 1]), nsnps);
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    if (int rc = ccu_fmx_set_shard(hs[i], cb[i], cb[i + 1], sb[i], sb[i + 1])) return rc;
+  // peer access between the devices, flag arrays, pointer tables
+  for (int i = 0; i < n; ++i) {
+    ccu_handle* h = hs[i];
+    FmxState* f = h->fmx;
+    CCU_CUDA(h, cudaSetDevice(h->device));
+    f->close_peers();
+    for (int j = 0; j < n; ++j)
+      if (hs[j]->device != h->device) {
+        int can = 0;
+        CCU_CUDA(h, cudaDeviceCanAccessPeer(&can, h->device, hs[j]->device));
+        if (!can) return ccu_fail(h, "ccu_fmx_run_em_multi: device %d cannot access device %d", h->device, hs[j]->device);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(hs[j]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return ccu_fail(h, "cudaDeviceEnablePeerAccess(%d -> %d): %s", h->device, hs[j]->device, cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+    CCU_CUDA(h, f->flags.reserve((ccu::kMaxPeers + 2) * sizeof(uint32_t)));
+    CCU_CUDA(h, cudaMemsetAsync(f->flags.p, 0, (ccu::kMaxPeers + 2) * sizeof(uint32_t), h->stream));
+    CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  for (int i = 0; i < n; ++i) {
+    FmxState* f = hs[i]->fmx;
+    f->peers_are_ipc = false;
+    f->peer_rank = i;
+    f->peers.n = n;
+    for (int j = 0; j < n; ++j) {
+      f->peers.post[j] = hs[j]->fmx->cgp.as<double>();
+      f->peers.assign[j] = hs[j]->fmx->assign.as<int32_t>();
+      f->peers.flags[j] = hs[j]->fmx->flags.as<uint32_t>();
+    }
+  }
+  std::vector<int> rcs(n, 0);
+  auto work = [&](int i) {
+    ccu_handle* h = hs[i];
+    FmxState* f = h->fmx;
+    auto step = [&](int rc) {
+      if (rc && !rcs[i]) rcs[i] = rc;
+      return rcs[i] == 0;
+    };
+    if (cudaSetDevice(h->device) != cudaSuccess) {
+      rcs[i] = ccu_fail(h, "cudaSetDevice(%d) failed", h->device);
+      return;
+    }
+    if (nbcs > 0 && cudaMemcpyAsync(f->assign.p, init_assign, nbcs * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
+      rcs[i] = ccu_fail(h, "ccu_fmx_run_em_multi: copying the initial assignment failed");
+      return;
+    }
+    // A rank that fails keeps launching its barriers (a missing one would only be noticed by the peers' time-out)
+    step(ccu_fmx_mstep_dev(h));
+    for (int it = 0; it < niter; ++it) {
+      const int apply = geno_error_every_iter ? 1 : (it + 1 == niter);
+      if (rcs[i] == 0) step(ccu_fmx_posteriors_push_dev(h, apply));
+      ccu_fmx_rank_barrier_dev(h);
+      if (rcs[i] == 0) step(ccu_fmx_estep_post_dev(h));
+      if (rcs[i] == 0) step(ccu_fmx_assign_push_dev(h));
+      ccu_fmx_rank_barrier_dev(h);
+      if (rcs[i] == 0) step(ccu_fmx_mstep_dev(h));
+    }
+    if (rcs[i] == 0 && cb[i + 1] > cb[i]) step(ccu_fmx_download_results(h, out + cb[i]));
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess && rcs[i] == 0) rcs[i] = ccu_fail(h, "stream synchronisation failed");
+    int32_t failed = 0;
+    if (rcs[i] == 0 && ccu_fmx_rank_barrier_failed(h, &failed) == 0 && failed)
+      rcs[i] = ccu_fail(h, "ccu_fmx_run_em_multi: a peer did not reach the barrier within its time-out");
+  };
+  if (n == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int i = 0; i < n; ++i) th.emplace_back(work, i);
+    for (auto& t : th) t.join();
+  }
+  for (int i = 0; i < n; ++i)
+    if (rcs[i]) {
+      if (i != 0) ccu_fail(h0, "ccu_fmx_run_em_multi: handle %d: %s", i, ccu_last_error(hs[i]));
+      return rcs[i];
+    }
+  if (clusters_out) {  // every handle folded its own SNP slab: stitch the slabs together
+    const int32_t K = f0->K;
+    std::vector<ccu_pileup> tmp((size_t)K * nsnps);
+    for (int i = 0; i < n; ++i) {
+      if (sb[i + 1] == sb[i]) continue;
+      if (int rc = ccu_fmx_get_clusters(hs[i], tmp.data())) return rc;
+      for (int32_t k = 0; k < K; ++k)
+        memcpy(clusters_out + (size_t)k * nsnps + sb[i], tmp.data() + (size_t)k * nsnps + sb[i],
+               (size_t)(sb[i + 1] - sb[i]) * sizeof(ccu_pileup));
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    cudaSetDevice(hs[i]->device);
+    hs[i]->fmx->close_peers();
+  }
+  return 0;
 }
 
 int ccu_fmx_pair_distances(ccu_handle* h, int64_t* npairs, int64_t* nrecords, float* ms) {

@@ -48,7 +48,7 @@ ABI_SYMBOLS = [
     "ccu_fmx_estep_post_dev", "ccu_fmx_pair_distances", "ccu_fmx_get_pair_distances", "ccu_fmx_initial_clusters",
     "ccu_fmx_greedy_clusters", "ccu_fmx_get_voting_pairs", "ccu_fmx_peer_handles", "ccu_fmx_peer_open",
     "ccu_fmx_peer_close", "ccu_fmx_posteriors_push_dev", "ccu_fmx_assign_push_dev", "ccu_fmx_rank_barrier_dev",
-    "ccu_fmx_rank_barrier_failed",
+    "ccu_fmx_rank_barrier_failed", "ccu_fmx_run_em_multi",
 ]
 
 
@@ -379,6 +379,24 @@ class FreemuxEngine(DemuxEngine):
         t = FmxTimings()
         self._check(self.lib.ccu_fmx_get_timings(self.h, C.byref(t)))
         return t.as_dict()
+
+
+def run_em_multi(engines, cell_ptr, snp_idx, init_assign, niter=10, geno_error_every_iter=False, want_clusters=False):
+    """ccu_fmx_run_em_multi: the EM loop sharded over several FreemuxEngine handles of this process (each configured
+    and uploaded with the same store), exchange through peer memory.  Returns (results[nbcs], clusters or None)."""
+    lib = engines[0].lib
+    n = len(engines)
+    arr = (C.c_void_p * n)(*[e.h for e in engines])
+    cp = np.ascontiguousarray(cell_ptr, np.int64)
+    si = np.ascontiguousarray(snp_idx, np.int32)
+    a = np.ascontiguousarray(init_assign, np.int32)
+    out = np.zeros(engines[0].nbcs, FMX_RESULT_DTYPE)
+    cl = np.zeros((engines[0].K, engines[0].nsnps), PILEUP_DTYPE) if want_clusters else None
+    rc = lib.ccu_fmx_run_em_multi(arr, C.c_int32(n), _ptr(cp), _ptr(si), _ptr(a), C.c_int32(niter),
+                                  C.c_int32(int(geno_error_every_iter)), _ptr(out), _ptr(cl))
+    if rc:
+        raise EngineError(lib.ccu_last_error(engines[0].h).decode())
+    return out, cl
 
 
 def initial_clusters(cell_scores, pairs, nclust, bf_thres=5.41, frac_init_clust=1.0, iter_init=10,

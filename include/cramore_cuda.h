@@ -218,6 +218,16 @@ int ccu_fmx_estep_post_dev(ccu_handle* h);
  * every rank has finished reading -- both follow from the two barriers.  Results are bit-identical to the
  * all-reduce exchange.  ccu_fmx_peer_close unmaps (also done by ccu_destroy). */
 #define CCU_IPC_HANDLE_BYTES 64
+/* The same exchange inside ONE process: n handles on different devices (or several on one), each configured and
+ * uploaded with the same store.  One host thread per handle runs the loop of cmd_cram_freemuxlet.cpp:359-370 +
+ * :457-653 on its droplet range and SNP slab (about nnz / n entries each), peers are reached through
+ * cudaDeviceEnablePeerAccess, the two per-iteration exchanges are the push kernels and the flag barrier above.
+ * cell_ptr / snp_idx: the host arrays that were uploaded (for the partition).  out: host [nbcs];
+ * clusters_out: optional host [nclust][nsnps], the cluster pileups after the last M-step.
+ * Bit-identical to ccu_fmx_run_em (no early stop: freemux2's stop_when_stable needs a host decision per iteration). */
+int ccu_fmx_run_em_multi(ccu_handle** handles, int32_t n, const int64_t* cell_ptr, const int32_t* snp_idx,
+                         const int32_t* init_assign, int32_t niter, int32_t geno_error_every_iter, ccu_fmx_result* out,
+                         ccu_pileup* clusters_out);
 int ccu_fmx_peer_handles(ccu_handle* h, void* out /* [3 * CCU_IPC_HANDLE_BYTES]: posteriors, assignments, flags */);
 int ccu_fmx_peer_open(ccu_handle* h, int32_t nranks, int32_t rank, const void* handles /* [nranks][3][64] */);
 int ccu_fmx_rank_barrier_dev(ccu_handle* h);

@@ -293,3 +293,35 @@ def test_cli_freemuxlet_equals_live_reference(built, tmp_path, seed):
         assert a == b or _numeric_row_match(a, b), (a, b)
     assert sum(a == b for a, b in zip(mine, ref)) >= 0.9 * len(ref)
     assert open(str(tmp_path / "mine.lmix")).read().splitlines()[0] == open(str(tmp_path / "ref.lmix")).read().splitlines()[0]
+
+
+@pytest.mark.parametrize("name", ["fmx_k4", "fmx_k6_prior"])
+def test_cli_freemuxlet_over_several_handles(built, tmp_path, name):
+    """`cramore freemuxlet --gpu-devices a,b,c`: the EM loop sharded over several engine handles (ccu_fmx_run_em_multi,
+    peer-memory exchange) writes the files of the single-device run, which equal the reference's."""
+    import torch
+    fx = refcase.load(name)
+    d = refcase.dataset(fx)
+    K = fx["spec"]["K"]
+    pre = str(tmp_path / "in")
+    bcs = write_plp(d, pre)
+    with open(str(tmp_path / "init.txt"), "w") as f:
+        for b, c in zip(bcs, fx["init"]):
+            f.write("%s\t%d\n" % (b, c))
+    ndev = torch.cuda.device_count()
+    devs = ",".join(str(i % ndev) for i in range(3))
+    outs = {}
+    for tag, extra in (("one", []), ("many", ["--gpu-devices", devs])):
+        out = str(tmp_path / tag)
+        r = subprocess.run([CRAMORE, "freemuxlet", "--plp", pre, "--out", out, "--nsample", str(K), "--init-cluster",
+                            str(tmp_path / "init.txt"), "--iter-init", "0", "--keep-init-missing"] + fx["spec"]["args"] + extra,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        vcf = [ln for ln in gzip.open(out + ".clust1.vcf.gz", "rt").read().splitlines() if not ln.startswith("##fileDate")]
+        outs[tag] = (gzip.open(out + ".clust1.samples.gz", "rt").read(), vcf, open(out + ".lmix").read())
+    assert outs["one"] == outs["many"]
+    ref = fx["samples_text"].splitlines(keepends=True)
+    mine = outs["many"][0].splitlines(keepends=True)
+    assert len(mine) == len(ref)
+    for a, b in zip(mine, ref):
+        assert a == b or _numeric_row_match(a, b), (a, b)

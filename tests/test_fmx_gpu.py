@@ -364,3 +364,39 @@ def test_peer_memory_exchange_two_processes(built, tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2
+
+
+@pytest.mark.parametrize("nhandles", [2, 3])
+def test_in_process_multi_handle_em_is_bitwise_single(built, nhandles):
+    """ccu_fmx_run_em_multi -- one host thread per handle, push kernels and the flag barrier between handles of ONE
+    process -- with several handles on this box's GPU (on a multi-GPU box: one per device): results and the stitched
+    cluster pileups are bit-identical to the single-handle loop."""
+    import torch
+    from cramore_b200 import FreemuxEngine
+    from cramore_b200.engine import run_em_multi
+    ndev = torch.cuda.device_count()
+    K, NITER = 6, 5
+    d = make_dataset("C4", nbcs=500, nsnps=2500, rbar=120, nv=6)
+    init = (d["s1"] % K).astype(np.int32)
+    init[d["is_dbl"]] = -1
+    engs = []
+    try:
+        for i in range(nhandles):
+            e = FreemuxEngine(i % ndev)
+            e.configure_fmx(K, 0.4, 0.03)
+            e.upload_fmx(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], d["af"])
+            engs.append(e)
+        res, clusters = run_em_multi(engs, d["cell_ptr"], d["snp_idx"], init, niter=NITER, want_clusters=True)
+        ref = FreemuxEngine(0)
+        engs.append(ref)
+        ref.configure_fmx(K, 0.4, 0.03)
+        ref.upload_fmx(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], d["af"])
+        want, _ = ref.run_em(init, niter=NITER)
+        assert np.array_equal(res, want)
+        assert (want["type"] == 0).sum() > 200
+        wc = ref.clusters()
+        for f in wc.dtype.names:
+            assert np.array_equal(clusters[f], wc[f]), f
+    finally:
+        for e in engs:
+            e.close()
