@@ -683,6 +683,19 @@ int ccu_fmx_run_em_multi(ccu_handle** hs, int32_t n, const int64_t* cell_ptr, co
       f->peers.flags[j] = hs[j]->fmx->flags.as<uint32_t>();
     }
   }
+  // Dry pass, one handle after the other and without barriers: every kernel of the loop gets loaded into its
+  // context and every buffer reaches its final size.  Inside the loop nothing may need a device-wide pause any more
+  // -- a lazy kernel load or a cudaMalloc on a device where a peer's barrier kernel is spinning (several handles on
+  // one device) would wait for that kernel, which waits for us.  What the pass writes is overwritten below.
+  for (int i = 0; i < n; ++i) {
+    ccu_handle* h = hs[i];
+    CCU_CUDA(h, cudaSetDevice(h->device));
+    if (nbcs > 0) CCU_CUDA(h, cudaMemsetAsync(h->fmx->assign.p, 0xff, nbcs * sizeof(int32_t), h->stream));
+    if (ccu_fmx_mstep_dev(h) || ccu_fmx_posteriors_push_dev(h, 1) || ccu_fmx_estep_post_dev(h) || ccu_fmx_assign_push_dev(h))
+      return hs[i] == h0 ? 1 : ccu_fail(h0, "ccu_fmx_run_em_multi: handle %d: %s", i, ccu_last_error(h));
+    CCU_CUDA(h, ccu::preload_fmx_rank_barrier());
+    CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   std::vector<int> rcs(n, 0);
   auto work = [&](int i) {
     ccu_handle* h = hs[i];

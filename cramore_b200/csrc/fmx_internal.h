@@ -81,6 +81,7 @@ cudaError_t launch_fmx_assign_push(const FmxDev& d, const FmxPeers& peers, cudaS
 // The epoch lives in device memory, so the launch can sit in a replayed CUDA graph.  A rank that waits longer than
 // ~2 s gives up and raises the error flag (flags[kMaxPeers + 1]) instead of hanging the GPU.
 cudaError_t launch_fmx_rank_barrier(const FmxPeers& peers, int rank, cudaStream_t st);
+cudaError_t preload_fmx_rank_barrier();
 cudaError_t launch_fmx_estep(const FmxDev& d, cudaStream_t st);
 // int32 count of droplets whose (type, jBest, kBest) differ between two result arrays
 // counts bitwise differences between the shared-reciprocal division of the pileup kernels and __ddiv_rn
