@@ -565,12 +565,14 @@ inline void join_sam_vcf(const std::string& fn, const SamOptions& opt, VcfReader
       ibcd = it->second;
     }
     ++js.nReadsTMP;
-    // UMI
-    int32_t iumi;
-    {
+    // UMI: looked up when it is needed -- for the covered regions of dsc-pileup, or once the read shows a base at a
+    // SNP (most reads of a single-cell BAM overlap none).  A random UMI (--tag-UMI '') is drawn for every read,
+    // as the reference does, so that the rand() sequence stays the same (:298-301).
+    int32_t iumi = -1;
+    auto resolve_umi = [&]() {
       const char* z = ".";
       if (opt.tagUMI.empty()) {
-        snprintf(numbuf, sizeof(numbuf), "%x", rand());  // a random UMI (:298-301)
+        snprintf(numbuf, sizeof(numbuf), "%x", rand());
         z = numbuf;
       } else {
         const char* t = r.tag_z(utag);
@@ -584,7 +586,8 @@ inline void join_sam_vcf(const std::string& fn, const SamOptions& opt, VcfReader
         umis.push_back(key);
       }
       iumi = it->second;
-    }
+    };
+    if (opt.tagUMI.empty() || (opt.collect_umi_loci && umi_loci)) resolve_umi();
     ++st.totl_reads[(size_t)ibcd];
     if (opt.collect_umi_loci && umi_loci) {  // dsc-pileup :296-331
       const uint64_t key = ((uint64_t)(uint32_t)ibcd << 32) | (uint32_t)iumi;
@@ -626,6 +629,7 @@ inline void join_sam_vcf(const std::string& fn, const SamOptions& opt, VcfReader
       if (rpos + opt.minTD > r.l_seq) continue;
       const uint8_t allele = (base == v.ref) ? 0 : ((base == v.alt) ? 1 : 2);
       const int bq = qual - 33 > opt.capBQ ? opt.capBQ : qual - 33;
+      if (iumi < 0) resolve_umi();
       if (seen.insert({ibcd, (int32_t)i, iumi}).second) {  // sc_dropseq_lib_t::add_read: the first read wins
         recs.push_back({ibcd, (int32_t)i, iumi, allele, (uint8_t)bq, (int64_t)recs.size()});
         ++nv_pass;

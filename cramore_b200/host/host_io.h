@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <map>
 #include <set>
 #include <stdexcept>
@@ -68,6 +69,12 @@ class BgzfStream {
     }
   }
   ~BgzfStream() {
+    if (ahead_.valid()) {
+      try {
+        ahead_.get();
+      } catch (...) {
+      }
+    }
     if (fp_) fclose(fp_);
     if (gz_) gzclose(gz_);
   }
@@ -101,9 +108,19 @@ class BgzfStream {
     size_t in_off, in_len, out_off, out_len;  // deflate payload inside in_, inflated bytes inside out_
     uint32_t crc;
   };
-  // reads the next batch of blocks and inflates it; false at the end of the file
+  // The next batch is read and inflated by a helper thread while the caller works through the current one.
   bool fill() {
-    constexpr size_t kBatchBlocks = 1024;  // <= 64 MiB inflated
+    if (!ahead_.valid()) ahead_ = std::async(std::launch::async, [this]() { return produce(next_); });
+    const bool ok = ahead_.get();  // rethrows what fatal() threw in the helper
+    if (!ok) return false;
+    out_.swap(next_);
+    pos_ = 0;
+    ahead_ = std::async(std::launch::async, [this]() { return produce(next_); });
+    return true;
+  }
+  // reads the next batch of blocks and inflates it into `out_`; false at the end of the file
+  bool produce(std::vector<unsigned char>& out_) {
+    constexpr size_t kBatchBlocks = 512;  // <= 32 MiB inflated
     in_.clear();
     std::vector<Block> blocks;
     size_t out_total = 0;
@@ -139,7 +156,6 @@ class BgzfStream {
     }
     if (blocks.empty()) return false;
     out_.resize(out_total);
-    pos_ = 0;
     std::atomic<size_t> next{0};
     std::atomic<int> bad{0};
     auto work = [&]() {
@@ -179,7 +195,8 @@ class BgzfStream {
   gzFile gz_ = NULL;
   bool bgzf_ = false;
   int nthreads_ = 1;
-  std::vector<unsigned char> in_, out_;
+  std::vector<unsigned char> in_, out_, next_;
+  std::future<bool> ahead_;
   size_t pos_ = 0;
 };
 
