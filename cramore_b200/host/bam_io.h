@@ -373,10 +373,11 @@ struct UmiLocusLess {
 };
 
 // genomeLoci::add (genomeLoci.h:227-237) on a sorted vector standing in for the std::set
-inline void insert_locus(std::vector<UmiLocus>& v, const UmiLocus& x, const UmiLocusLess& less) {
+inline bool insert_locus(std::vector<UmiLocus>& v, const UmiLocus& x, const UmiLocusLess& less) {
   auto it = std::lower_bound(v.begin(), v.end(), x, less);
-  if (it != v.end() && !less(x, *it)) return;  // an equivalent element is there already
+  if (it != v.end() && !less(x, *it)) return false;  // an equivalent element is there already
   v.insert(it, x);
+  return true;
 }
 // genomeLoci::resolveOverlaps (genomeLoci.h:255-287): neighbours sharing a base are merged (touching ones are not)
 inline void resolve_overlaps(std::vector<UmiLocus>& v, const UmiLocusLess& less) {
@@ -400,6 +401,118 @@ inline void resolve_overlaps(std::vector<UmiLocus>& v, const UmiLocusLess& less)
     }
   }
 }
+
+// Open-addressing indices for the hot look-ups of the join (droplet tag, UMI tag, (droplet, UMI) pair): one probe
+// in a flat table instead of a node chase -- std::unordered_map<std::string, int> costs ~0.5 us per read here.
+class FlatStrIndex {
+ public:
+  // id of `s` (ids count up from 0 in order of first appearance); *is_new tells whether it was just added
+  int32_t get(const char* s, size_t n, bool* is_new) {
+    if ((names_.size() + 1) * 2 > slots_.size()) grow();
+    const uint64_t h = hash(s, n);
+    const size_t mask = slots_.size() - 1;
+    for (size_t i = (size_t)h & mask;; i = (i + 1) & mask) {
+      Slot& sl = slots_[i];
+      if (sl.id < 0) {
+        sl.h = h;
+        sl.id = (int32_t)names_.size();
+        names_.emplace_back(s, n);
+        *is_new = true;
+        return sl.id;
+      }
+      if (sl.h == h) {
+        const std::string& nm = names_[(size_t)sl.id];
+        if (nm.size() == n && memcmp(nm.data(), s, n) == 0) {
+          *is_new = false;
+          return sl.id;
+        }
+      }
+    }
+  }
+  const std::vector<std::string>& names() const { return names_; }
+
+ private:
+  struct Slot {
+    uint64_t h;
+    int32_t id;
+  };
+  static uint64_t hash(const char* s, size_t n) {
+    uint64_t h = 0x9e3779b97f4a7c15ull ^ (n * 0xff51afd7ed558ccdull);
+    while (n >= 8) {
+      uint64_t w;
+      memcpy(&w, s, 8);
+      h = (h ^ w) * 0xc4ceb9fe1a85ec53ull;
+      h ^= h >> 29;
+      s += 8;
+      n -= 8;
+    }
+    uint64_t w = 0;
+    memcpy(&w, s, n);
+    h = (h ^ w) * 0xc4ceb9fe1a85ec53ull;
+    return h ^ (h >> 32);
+  }
+  void grow() {
+    std::vector<Slot> old;
+    old.swap(slots_);
+    slots_.assign(old.empty() ? 1024 : old.size() * 2, Slot{0, -1});
+    const size_t mask = slots_.size() - 1;
+    for (const Slot& sl : old)
+      if (sl.id >= 0) {
+        size_t i = (size_t)sl.h & mask;
+        while (slots_[i].id >= 0) i = (i + 1) & mask;
+        slots_[i] = sl;
+      }
+  }
+  std::vector<Slot> slots_;
+  std::vector<std::string> names_;
+};
+
+class FlatU64Index {
+ public:
+  // value stored for `key`, or -1; put() adds a key that is not there yet
+  int64_t find(uint64_t key) const {
+    if (slots_.empty()) return -1;
+    const size_t mask = slots_.size() - 1;
+    for (size_t i = (size_t)mix(key) & mask;; i = (i + 1) & mask) {
+      if (slots_[i].val < 0) return -1;
+      if (slots_[i].key == key) return slots_[i].val;
+    }
+  }
+  void put(uint64_t key, int64_t val) {
+    if ((n_ + 1) * 2 > slots_.size()) grow();
+    const size_t mask = slots_.size() - 1;
+    size_t i = (size_t)mix(key) & mask;
+    while (slots_[i].val >= 0) i = (i + 1) & mask;
+    slots_[i] = {key, val};
+    ++n_;
+  }
+
+ private:
+  struct Slot {
+    uint64_t key;
+    int64_t val;
+  };
+  static uint64_t mix(uint64_t x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    return x;
+  }
+  void grow() {
+    std::vector<Slot> old;
+    old.swap(slots_);
+    slots_.assign(old.empty() ? 1024 : old.size() * 2, Slot{0, -1});
+    const size_t mask = slots_.size() - 1;
+    for (const Slot& sl : old)
+      if (sl.val >= 0) {
+        size_t i = (size_t)mix(sl.key) & mask;
+        while (slots_[i].val >= 0) i = (i + 1) & mask;
+        slots_[i] = sl;
+      }
+  }
+  std::vector<Slot> slots_;
+  size_t n_ = 0;
+};
 
 struct SamVariant {
   int32_t rid, pos1;  // VCF contig id, 1-based position
@@ -493,14 +606,13 @@ inline void join_sam_vcf(const std::string& fn, const SamOptions& opt, VcfReader
   };
   std::vector<Rec> recs;
   std::unordered_set<Key, KeyHash> seen;
-  std::unordered_map<std::string, int32_t> cell_id, umi_id;
-  std::vector<std::string> umis;
-  std::unordered_map<uint64_t, size_t> loci_at;  // (cell, umi) -> index into *umi_loci
+  FlatStrIndex cell_id, umi_id;
+  const std::vector<std::string>& umis = umi_id.names();
+  FlatU64Index loci_at;  // (cell, umi) -> index into *umi_loci
   const UmiLocusLess less{&br.refs};
   const char* gtag = opt.tagGroup.c_str();
   const char* utag = opt.tagUMI.c_str();
   BamRecord r;
-  std::string key;
   int64_t n_no_gtag = 0, n_no_utag = 0;
   std::vector<int32_t> tid_rid;  // cache of name2rid per BAM contig, refreshed when the VCF meets a new contig
   size_t tid_rid_for = 0;
@@ -554,15 +666,13 @@ inline void join_sam_vcf(const std::string& fn, const SamOptions& opt, VcfReader
           continue;
         }
       }
-      key.assign(sbcd);  // (find first: emplace would build a node, and free it again, for every read)
-      auto it = cell_id.find(key);
-      if (it == cell_id.end()) {
-        it = cell_id.emplace(key, (int32_t)st.bcs.size()).first;
-        st.bcs.push_back(key);
+      bool fresh = false;
+      ibcd = cell_id.get(sbcd, strlen(sbcd), &fresh);
+      if (fresh) {
+        st.bcs.push_back(sbcd);
         st.totl_reads.push_back(0);
         if (cell_numi) cell_numi->push_back(0);
       }
-      ibcd = it->second;
     }
     ++js.nReadsTMP;
     // UMI: looked up when it is needed -- for the covered regions of dsc-pileup, or once the read shows a base at a
@@ -579,24 +689,22 @@ inline void join_sam_vcf(const std::string& fn, const SamOptions& opt, VcfReader
         if (t) z = t;
         else ++n_no_utag;
       }
-      key.assign(z);
-      auto it = umi_id.find(key);
-      if (it == umi_id.end()) {
-        it = umi_id.emplace(key, (int32_t)umis.size()).first;
-        umis.push_back(key);
-      }
-      iumi = it->second;
+      bool fresh = false;
+      iumi = umi_id.get(z, strlen(z), &fresh);
     };
     if (opt.tagUMI.empty() || (opt.collect_umi_loci && umi_loci)) resolve_umi();
     ++st.totl_reads[(size_t)ibcd];
     if (opt.collect_umi_loci && umi_loci) {  // dsc-pileup :296-331
-      const uint64_t key = ((uint64_t)(uint32_t)ibcd << 32) | (uint32_t)iumi;
-      auto ins = loci_at.emplace(key, umi_loci->size());
-      if (ins.second) {
+      const uint64_t lkey = ((uint64_t)(uint32_t)ibcd << 32) | (uint32_t)iumi;
+      int64_t at = loci_at.find(lkey);
+      if (at < 0) {
+        at = (int64_t)umi_loci->size();
+        loci_at.put(lkey, at);
         umi_loci->push_back({ibcd, iumi, {}});
         if (cell_numi) ++(*cell_numi)[(size_t)ibcd];
       }
-      std::vector<UmiLocus>& loci = (*umi_loci)[ins.first->second].strand[(r.flag & 0x10) ? 1 : 0];
+      std::vector<UmiLocus>& loci = (*umi_loci)[(size_t)at].strand[(r.flag & 0x10) ? 1 : 0];
+      bool grew = false;
       if (r.n_cigar) {
         int32_t cpos = r.pos;
         for (uint32_t ci = 0; ci < r.n_cigar; ++ci) {
@@ -604,13 +712,13 @@ inline void join_sam_vcf(const std::string& fn, const SamOptions& opt, VcfReader
           const char op = "MIDNSHP=XB??????"[c & 15];
           const int32_t len = (int32_t)(c >> 4);
           if (op == 'M') {
-            insert_locus(loci, {r.tid, cpos + 1, cpos + len}, less);
+            grew |= insert_locus(loci, {r.tid, cpos + 1, cpos + len}, less);
             cpos += len;
           } else if (op == 'D' || op == 'N') {
             cpos += len;
           }
         }
-        resolve_overlaps(loci, less);
+        if (grew) resolve_overlaps(loci, less);  // an unchanged, already resolved set stays as it is
       }
     }
     if (noBCF) continue;
