@@ -210,7 +210,8 @@ class BamReader {
       d.push_back((uint8_t)((code(f[9][i]) << 4) | (i + 1 < l_seq ? code(f[9][i + 1]) : 0)));
     }
     const bool has_qual = strcmp(f[10], "*") != 0;
-    for (int32_t i = 0; i < l_seq; ++i) d.push_back(has_qual && f[10][i] ? (uint8_t)(f[10][i] - 33) : 0xff);
+    const int32_t l_qual = has_qual ? (int32_t)strlen(f[10]) : 0;
+    for (int32_t i = 0; i < l_seq; ++i) d.push_back(i < l_qual ? (uint8_t)(f[10][i] - 33) : 0xff);
     for (size_t t = 11; t < f.size(); ++t) {
       const char* a = f[t];
       if (strlen(a) < 5 || a[2] != ':' || a[4] != ':') continue;
