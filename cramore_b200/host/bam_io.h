@@ -706,7 +706,9 @@ inline void join_sam_vcf(const std::string& fn, const SamOptions& opt, VcfReader
       }
       std::vector<UmiLocus>& loci = (*umi_loci)[(size_t)at].strand[(r.flag & 0x10) ? 1 : 0];
       bool grew = false;
-      if (r.n_cigar) {
+      // (an alignment without a valid contig -- unmapped but let through by the flag masks, or a damaged record --
+      // has no region to report; the reference would index its contig table with that id)
+      if (r.n_cigar && r.tid >= 0 && r.tid < (int32_t)br.refs.size()) {
         int32_t cpos = r.pos;
         for (uint32_t ci = 0; ci < r.n_cigar; ++ci) {
           const uint32_t c = r.cigar_at(ci);
