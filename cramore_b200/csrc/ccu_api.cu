@@ -245,6 +245,44 @@ int ccu_demux_set_genotypes(ccu_handle* h, int64_t nsnps, const float* gp, const
   return 0;
 }
 
+// The reference keeps sc_snp_t::gps (sc_drop_seq.h:115-127): nv*3 doubles per SNP, genotype error already mixed
+// in (sc_drop_seq.cpp:287-315), or NULL where the VCF had no usable record.  A patched cmdCramDemuxlet can hand
+// those pointers over as they are.
+int ccu_demux_set_genotypes_mixed(ccu_handle* h, int64_t nsnps, const double* const* gps) {
+  if (!h) return 1;
+  if (!h->configured) return fail(h, "ccu_demux_set_genotypes_mixed: call ccu_demux_configure first");
+  if (nsnps < 0 || (nsnps > 0 && !gps)) return fail(h, "ccu_demux_set_genotypes_mixed: bad arguments");
+  if (nsnps > 2147483647LL) return fail(h, "ccu_demux_set_genotypes_mixed: more than 2^31-1 SNPs");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  const size_t row = (size_t)h->nvp * 3;
+  CCU_CUDA(h, h->d_G.reserve((size_t)nsnps * row * sizeof(double) + 16));
+  CCU_CUDA(h, h->d_hasgp.reserve(nsnps + 16));
+  h->has_gp_flags = true;
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_X0], h->stream));
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_GP0], h->stream));
+  // staged through a bounded host buffer: rows padded to nvp samples, zero rows where gps[s] == NULL
+  const int64_t chunk = std::max<int64_t>(1, (int64_t)((64u << 20) / (row * sizeof(double))));
+  std::vector<double> stage((size_t)std::min(chunk, std::max<int64_t>(nsnps, 1)) * row);
+  std::vector<uint8_t> flags((size_t)nsnps);
+  for (int64_t b = 0; b < nsnps; b += chunk) {
+    const int64_t e = std::min(nsnps, b + chunk);
+    std::fill(stage.begin(), stage.begin() + (size_t)(e - b) * row, 0.0);
+    for (int64_t s = b; s < e; ++s) {
+      flags[(size_t)s] = gps[s] != nullptr;
+      if (gps[s]) memcpy(&stage[(size_t)(s - b) * row], gps[s], (size_t)h->nv * 3 * sizeof(double));
+    }
+    CCU_CUDA(h, cudaMemcpyAsync(h->d_G.as<double>() + (size_t)b * row, stage.data(), (size_t)(e - b) * row * sizeof(double),
+                                cudaMemcpyHostToDevice, h->stream));
+    CCU_CUDA(h, cudaStreamSynchronize(h->stream));  // the staging buffer is reused
+  }
+  if (nsnps > 0) CCU_CUDA(h, cudaMemcpyAsync(h->d_hasgp.p, flags.data(), nsnps, cudaMemcpyHostToDevice, h->stream));
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_GP1], h->stream));
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->tm.ms_genotypes = ev_ms(h, EV_GP0, EV_GP1);
+  h->nsnps = nsnps;
+  return 0;
+}
+
 int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx,
                      const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq) {
   if (!h) return 1;

@@ -48,7 +48,7 @@ ABI_SYMBOLS = [
     "ccu_fmx_estep_post_dev", "ccu_fmx_pair_distances", "ccu_fmx_get_pair_distances", "ccu_fmx_initial_clusters",
     "ccu_fmx_greedy_clusters", "ccu_fmx_get_voting_pairs", "ccu_fmx_peer_handles", "ccu_fmx_peer_open",
     "ccu_fmx_peer_close", "ccu_fmx_posteriors_push_dev", "ccu_fmx_assign_push_dev", "ccu_fmx_rank_barrier_dev",
-    "ccu_fmx_rank_barrier_failed", "ccu_fmx_run_em_multi",
+    "ccu_fmx_rank_barrier_failed", "ccu_fmx_run_em_multi", "ccu_demux_set_genotypes_mixed",
 ]
 
 

@@ -98,6 +98,10 @@ int ccu_demux_configure(ccu_handle* h, int32_t nv, int32_t nalpha, const double*
  * FP64 matrix on the device, bit-identical to the host loop. */
 int ccu_demux_set_genotypes(ccu_handle* h, int64_t nsnps, const float* gp, const double* snp_err,
                             const uint8_t* has_gp);
+/* The same from the reference's own per-SNP arrays: gps[s] = sc_snp_t::gps of SNP s (sc_drop_seq.h:115-127: nv*3
+ * doubles, genotype error already mixed in by sc_drop_seq.cpp:287-315 / cmd_cram_demuxlet.cpp:241-268), or NULL for
+ * a SNP without genotypes.  Lets a patched cmdCramDemuxlet pass `scl.snps[s].gps` through unchanged. */
+int ccu_demux_set_genotypes_mixed(ccu_handle* h, int64_t nsnps, const double* const* gps);
 
 /* The whole engine for nbcs droplets, replaces cmd_cram_demuxlet.cpp:636-906 (tile :655-725,
  * pairwise accumulation :733-747, posterior normaliser :804-821, top-2 scans :827-906).

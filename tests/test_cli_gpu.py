@@ -325,3 +325,36 @@ def test_cli_freemuxlet_over_several_handles(built, tmp_path, name):
     assert len(mine) == len(ref)
     for a, b in zip(mine, ref):
         assert a == b or _numeric_row_match(a, b), (a, b)
+
+
+REF_GPU_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_cramore_gpu")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GPU_BIN), reason="oracle/_ref/ref_cramore_gpu not built (make -C oracle ref_gpu)")
+@pytest.mark.parametrize("name", refcase.DEMUX_CASES)
+def test_patched_reference_command_runs_on_the_engine(built, tmp_path, name):
+    """THE drop-in: the reference's own cmdCramDemuxlet -- its option parser, load_from_plp, VCF join and genotype-error
+    mixing, compiled from /root/reference unmodified up to line 426 -- with the likelihood loop replaced by the patch
+    of INTEGRATION.md section 1 (oracle/ref_shim/demuxlet_gpu_patch.inc) and linked against libcramore_cuda.so, writes the
+    .best file the stock reference writes."""
+    fx = refcase.load(name)
+    d = refcase.dataset(fx)
+    spec = fx["spec"]
+    write_plp(d, str(tmp_path / "in"))
+    write_vcf(d, str(tmp_path / "full.vcf"), with_r2=spec.get("with_r2", False))
+    with open(str(tmp_path / "in.vcf"), "w") as f:
+        snp = 0
+        for ln in open(str(tmp_path / "full.vcf")):
+            if ln.startswith("#"):
+                f.write(ln)
+                continue
+            if not spec.get("drop_every") or snp % spec["drop_every"] != 0:
+                f.write(ln)
+            snp += 1
+    args = [REF_GPU_BIN, "demuxlet", "--plp", "in", "--vcf", "in.vcf", "--field", spec.get("field", "GP"), "--out", "out"] + spec["args"]
+    for a in (spec["alphas"] or []):
+        args += ["--alpha", repr(float(a))]
+    r = subprocess.run(args, capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-3000:]
+    _compare_best(open(str(tmp_path / "out.best")).read().splitlines(keepends=True),
+                  fx["best_text"].splitlines(keepends=True), d["sample_ids"])

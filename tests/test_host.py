@@ -879,3 +879,22 @@ def test_binary_readers_survive_damaged_files(built, tmp_path):
             seen.add(r.returncode)
             assert r.returncode in (0, 1, 134), (kind, trial, r.returncode, r.stderr[-500:])
         assert 134 in seen or 1 in seen   # some of the damage was noticed
+
+
+def test_patched_reference_has_no_cpu_path(tmp_path):
+    """oracle/_ref/ref_cramore_gpu (the reference's cmdCramDemuxlet spliced onto the engine) on a box without a GPU:
+    it loads the inputs with the reference's own code and then stops with the reference's FATAL ERROR -- there is
+    nothing to fall back to."""
+    import torch
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_cramore_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_cramore_gpu not built")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by tests/test_cli_gpu.py")
+    from cramore_b200.synth import make_dataset, write_plp, write_vcf
+    d = make_dataset("C1", nbcs=5, nsnps=40, rbar=20, nv=3, with_barcodes=True)
+    write_plp(d, str(tmp_path / "in"))
+    write_vcf(d, str(tmp_path / "in.vcf"))
+    r = subprocess.run([exe, "demuxlet", "--plp", "in", "--vcf", "in.vcf", "--out", "out"], capture_output=True, text=True,
+                       cwd=str(tmp_path))
+    assert r.returncode != 0 and "ccu_create" in r.stderr and not os.path.exists(str(tmp_path / "out.best"))
