@@ -358,3 +358,39 @@ def test_patched_reference_command_runs_on_the_engine(built, tmp_path, name):
     assert r.returncode == 0, r.stderr[-3000:]
     _compare_best(open(str(tmp_path / "out.best")).read().splitlines(keepends=True),
                   fx["best_text"].splitlines(keepends=True), d["sample_ids"])
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GPU_BIN), reason="oracle/_ref/ref_cramore_gpu not built (make -C oracle ref_gpu)")
+@pytest.mark.parametrize("name", refcase.FMX_CASES + refcase.FMX_INIT_CASES)
+def test_patched_reference_freemuxlet_runs_on_the_engine(built, tmp_path, name):
+    """The reference's own cmdCramFreemuxlet -- options, load_from_plp, --init-cluster file, and its writers of
+    .clust1.vcf.gz / .clust1.samples.gz, all compiled from /root/reference -- with lines 105-653 replaced by the engine
+    calls of INTEGRATION.md section 2 (oracle/ref_shim/freemuxlet_gpu_patch.inc): same .clust0 / .clust1 files as the
+    stock reference."""
+    fx = refcase.load(name)
+    d = refcase.dataset(fx)
+    K = fx["spec"]["K"]
+    bcs = write_plp(d, str(tmp_path / "in"))
+    args = [REF_GPU_BIN, "freemuxlet", "--plp", "in", "--out", "out", "--nsample", str(K), "--aux-files"] + fx["spec"]["args"]
+    if name in refcase.FMX_CASES:
+        args += ["--init-cluster", "init.txt", "--iter-init", "0", "--keep-init-missing"]
+    elif fx["init"] is not None:
+        args += ["--init-cluster", "init.txt"]
+    if fx["init"] is not None:
+        with open(str(tmp_path / "init.txt"), "w") as f:
+            for b, c in zip(bcs, fx["init"]):
+                if c >= 0 or name in refcase.FMX_CASES:
+                    f.write("%s\t%d\n" % (b, c))
+    r = subprocess.run(args, capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-3000:]
+    if "clust0" in fx:
+        c0 = gzip.open(str(tmp_path / "out.clust0.samples.gz"), "rt").read().splitlines()
+        assert [int(ln.split("\t")[2]) for ln in c0[1:]] == fx["clust0"]
+    mine = gzip.open(str(tmp_path / "out.clust1.samples.gz"), "rt").read().splitlines(keepends=True)
+    ref = fx["samples_text"].splitlines(keepends=True)
+    assert len(mine) == len(ref) and mine[0] == ref[0]
+    for a, b in zip(mine[1:], ref[1:]):
+        assert a == b or _numeric_row_match(a, b), (a, b)
+    assert sum(a == b for a, b in zip(mine, ref)) >= 0.9 * len(ref)
+    vcf = [ln for ln in gzip.open(str(tmp_path / "out.clust1.vcf.gz"), "rt").read().splitlines() if not ln.startswith("#")]
+    assert len(vcf) >= 40 and all(len(ln.split("\t")) == 9 + K for ln in vcf)
