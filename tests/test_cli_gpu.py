@@ -394,3 +394,34 @@ def test_patched_reference_freemuxlet_runs_on_the_engine(built, tmp_path, name):
     assert sum(a == b for a, b in zip(mine, ref)) >= 0.9 * len(ref)
     vcf = [ln for ln in gzip.open(str(tmp_path / "out.clust1.vcf.gz"), "rt").read().splitlines() if not ln.startswith("#")]
     assert len(vcf) >= 40 and all(len(ln.split("\t")) == 9 + K for ln in vcf)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GPU_BIN), reason="oracle/_ref/ref_cramore_gpu not built (make -C oracle ref_gpu)")
+@pytest.mark.parametrize("name", refcase.FMX2_CASES)
+def test_patched_reference_freemux2_runs_on_the_engine(built, tmp_path, name):
+    """cmdCramFreemux2 of the reference with lines 106-607 replaced by engine calls (oracle/ref_shim/freemux2_gpu_patch.inc):
+    greedy initial clusters, .lmix and the final files equal the stock reference's."""
+    fx = refcase.load(name)
+    d = refcase.dataset(fx)
+    K = fx["spec"]["K"]
+    bcs = write_plp(d, str(tmp_path / "in"))
+    args = [REF_GPU_BIN, "freemux2", "--plp", "in", "--out", "out", "--nsample", str(K), "--aux-files", "--seed", "7"] + fx["spec"]["args"]
+    if fx["init"] is not None:
+        with open(str(tmp_path / "init.txt"), "w") as f:
+            for b, c in zip(bcs, fx["init"]):
+                if c >= 0:
+                    f.write("%s\t%d\n" % (b, c))
+        args += ["--init-cluster", "init.txt"]
+    r = subprocess.run(args, capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-3000:]
+    c0 = gzip.open(str(tmp_path / "out.clust0.samples.gz"), "rt").read().splitlines()
+    assert [int(ln.split("\t")[2]) for ln in c0[1:]] == fx["clust0"]
+    mine = gzip.open(str(tmp_path / "out.clust1.samples.gz"), "rt").read().splitlines(keepends=True)
+    ref = fx["samples_text"].splitlines(keepends=True)
+    assert len(mine) == len(ref) and mine[0] == ref[0]
+    for a, b in zip(mine[1:], ref[1:]):
+        assert a == b or _numeric_row_match(a, b), (a, b)
+    lm, rlm = open(str(tmp_path / "out.lmix")).read().splitlines(), fx["lmix_text"].splitlines()
+    assert len(lm) == len(rlm) and lm[0] == rlm[0]
+    for a, b in zip(lm[1:], rlm[1:]):
+        assert a == b or _numeric_row_match(a, b), (a, b)
