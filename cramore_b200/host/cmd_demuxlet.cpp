@@ -155,6 +155,7 @@ int cmdDemuxlet(int argc, char** argv) {
     vr.minMAC = minMAC;
     vr.minCallRate = minCallRate;
     vr.maxAlleles = 2;
+    vr.prefetch(field.c_str(), 0);  // what both ingestion paths ask for (all but the first SNP of the --sam path)
     const int32_t nv = vr.nsamples();
 
     PlpFilters flt;

@@ -624,14 +624,25 @@ inline float fast_strtof(const char* s, const char** end) {
 
 struct VcfRecord {
   int32_t rid = -1, pos1 = 0;  // 1-based position
-  std::string ref, alt;
+  std::string chrom, ref, alt;
   int32_t n_allele = 0;
   std::string info;
   std::vector<std::string> fmt;
-  std::vector<char*> cols;  // sample columns (pointers into line)
+  std::vector<uint32_t> col_off;  // sample columns: offsets into line (NUL-terminated fields)
   std::string line;
+  // filled by the parsers (per record, so that a batch of records can be parsed on several threads)
+  std::vector<double> acs;
+  int32_t an = 0;
+  std::vector<int32_t> gts;
+  std::vector<float> gp;   // posteriors of the pre-fetch field, [nv*3]
+  bool gp_ok = false, pass = false;
+  std::string error;       // text of a fatal() raised while this record was parsed ahead
 };
 
+// Sequential cursor over the records that pass the variant filter.  Records are read in batches and tokenised,
+// filtered and (when a pre-fetch field is set) turned into float posteriors on all host cores at once; the cursor
+// then serves them in file order, so callers see exactly the sequence of the one-record-at-a-time reader this
+// replaced -- the parse of a 64-sample line costs ~10 us, 200,000 of them were most of a C2 run.
 class VcfReader {
  public:
   std::vector<std::string> chroms, samples;
@@ -641,7 +652,7 @@ class VcfReader {
   int64_t nRead = 0, nSkip = 0;
   bool eof = false;
   VcfRecord cur;
-  std::vector<double> acs;
+  std::vector<double> acs;  // allele counts / number of the current record (after read(), parse_posteriors("GT"/"PL"))
   int32_t an = 0;
 
   VcfReader(const std::string& fn, const std::set<std::string>& sm_ids, bool allow_no_samples = false) : lr_(fn) {
@@ -668,6 +679,8 @@ class VcfReader {
     for (int32_t i = 0; i < (int32_t)samples.size(); ++i)
       if (sm_ids.empty() || sm_ids.count(samples[i])) sm_icols.push_back(i);
     if (sm_icols.empty() && !allow_no_samples) fatal("No sample to read from %s", fn.c_str());
+    nthreads_ = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    if (const char* e = getenv("CRAMORE_VCF_THREADS")) nthreads_ = std::max(1, atoi(e));
   }
 
   int32_t nsamples() const { return (int32_t)sm_icols.size(); }
@@ -680,118 +693,48 @@ class VcfReader {
     return (int)chroms.size() - 1;
   }
 
+  // The posteriors most records will be asked for: computed ahead, in parallel, for every record that passes the
+  // filter.  parse_posteriors() with other arguments still works (it computes on the spot).
+  void prefetch(const char* field, double gt_error) {
+    prefetch_field_ = field;
+    prefetch_gt_error_ = gt_error;
+  }
+
   // BCFFilteredReader::read(): advance to the next variant passing the filter; false at EOF
   bool read() {
-    while (lr_.next_line()) {
-      if (lr_.line.empty() || lr_.line[0] == '#') continue;
-      parse_line();
-      ++nRead;
-      // passed_vfilter (bcf_filtered_reader.cpp:571-645): with no genotype-based threshold set (require_GT false,
-      // bcf_filter_arg.h:109-113) it returns true before it ever looks at the allele count
-      const bool require_GT = minMAC > 0 || minCallRate > 0;
-      bool pass = !require_GT || cur.n_allele <= maxAlleles;
-      if (pass && require_GT) {
-        if (!parse_genotypes()) fatal("Cannot find the field GT from the VCF file at position %s:%d", chroms[cur.rid].c_str(), cur.pos1);
-        if (minCallRate > (double)an / (2.0 * (double)sm_icols.size())) pass = false;
-        const int32_t ac = an - (int32_t)acs[0];
-        if (ac < minMAC || an - ac < minMAC) pass = false;
+    for (;;) {
+      if (next_ == batch_n_ && !fill_batch()) {
+        eof = true;
+        return false;
       }
-      if (pass) return true;
-      ++nSkip;
+      VcfRecord& r = batch_[next_++];
+      if (!r.error.empty()) throw std::runtime_error(r.error);  // fatal() already printed it
+      r.rid = chrom_id(r.chrom);
+      ++nRead;
+      if (!r.pass) {
+        ++nSkip;
+        continue;
+      }
+      std::swap(cur, r);
+      acs = cur.acs;
+      an = cur.an;
+      return true;
     }
-    eof = true;
-    return false;
   }
 
   // posteriors of the selected samples for the current record: out[nv*3] (float, bcf_filtered_reader.h:168-170)
   bool parse_posteriors(const char* field, double gt_error, float* out) {
-    const int32_t nv = nsamples();
+    if (cur.gp_ok && prefetch_field_ == field && prefetch_gt_error_ == gt_error) {
+      memcpy(out, cur.gp.data(), sizeof(float) * cur.gp.size());
+      return true;
+    }
     if (cur.n_allele != 2) fatal("parse_posteriors: only biallelic sites are supported (%s:%d)", chroms[cur.rid].c_str(), cur.pos1);
-    if (strcmp(field, "GT") == 0) {  // :414-452
-      if (!parse_genotypes()) return false;
-      for (int32_t i = 0; i < nv; ++i) {
-        const int32_t a1 = gts_[2 * i], a2 = gts_[2 * i + 1];
-        const int32_t g = (a1 < 0 || a2 < 0) ? -1 : (a1 > a2 ? a1 * (a1 + 1) / 2 + a2 : a2 * (a2 + 1) / 2 + a1);
-        if (g < 0) {
-          for (int32_t j = 0, l = 0; j < 2; ++j)
-            for (int32_t k = 0; k <= j; ++k, ++l)
-              out[i * 3 + l] = (float)((j == k ? 1.0 : 2.0) * (acs[j] + 1.0 / 2) / (an + 1.0) * (acs[k] + 1.0 / 2) / (an + 1.0));
-        } else {
-          for (int32_t j = 0; j < 3; ++j) out[i * 3 + j] = (g == j) ? 1.0 - gt_error : gt_error / (3 - 1.0);
-        }
-      }
-      return true;
-    }
-    if (strcmp(field, "PL") == 0) {  // parse_likelihoods, bcf_filtered_reader.cpp:289-365 (diploid samples)
-      // ten EM iterations for the allele frequency under HWE; the posteriors of the last one are the output.
-      // toProb(pl) = pow(0.1, pl * 0.1), capped at pl = 255 (PhredHelper.cpp:31, PhredHelper.h:40).
-      // Parity unpinned: the reference's own reader is htslib-bound and not buildable here (DESIGN.md section 6).
-      const int fi = fmt_index("PL");
-      if (fi < 0) return false;
-      pls_.resize((size_t)nv * 3);
-      for (int32_t i = 0; i < nv; ++i) {
-        const char* p = sample_field(sm_icols[i], fi);
-        for (int j = 0; j < 3; ++j) {
-          char* e;
-          long v = (*p == '.') ? 255 : strtol(p, &e, 10);  // a missing value carries no information either way
-          if (*p == '.') e = const_cast<char*>(p) + 1;
-          pls_[(size_t)i * 3 + j] = (uint32_t)(v < 0 ? 0 : v);
-          p = (*e == ',') ? e + 1 : e;
-        }
-      }
-      acs.assign(2, 0.5);
-      double gp[3];
-      for (int it = 0; it < 10; ++it) {
-        double newacs[2] = {0, 0};
-        an = 0;
-        for (int32_t i = 0; i < nv; ++i) {
-          double sumgp = 0;
-          for (int j = 0, l = 0; j < 2; ++j)
-            for (int k = 0; k <= j; ++k, ++l) {
-              const uint32_t pl = pls_[(size_t)i * 3 + l];
-              sumgp += (gp[l] = (j == k ? 1 : 2) * acs[j] * acs[k] * pow(0.1, (pl > 255 ? 255 : pl) * 0.1));
-            }
-          for (int j = 0, l = 0; j < 2; ++j)
-            for (int k = 0; k <= j; ++k, ++l) {
-              gp[l] /= sumgp;
-              newacs[j] += gp[l];
-              newacs[k] += gp[l];
-            }
-          an += 2;
-          if (it + 1 == 10)
-            for (int l = 0; l < 3; ++l) out[i * 3 + l] = (float)gp[l];
-        }
-        for (int j = 0; j < 2; ++j) acs[j] = newacs[j] / an;
-      }
-      for (int j = 0; j < 2; ++j) acs[j] *= an;
-      return true;
-    }
-    const int fi = fmt_index(field);
-    if (fi < 0) return false;
-    float gpSums[3] = {1.0f / 4.0f, 2.0f / 4.0f, 1.0f / 4.0f};  // :462-468 (nalleles = 2)
-    for (int32_t i = 0; i < nv; ++i) {  // :474-485
-      const char* p = sample_field(sm_icols[i], fi);
-      float g[3];
-      for (int j = 0; j < 3; ++j) {
-        const char* e;
-        g[j] = fast_strtof(p, &e);
-        p = (*e == ',') ? e + 1 : e;
-      }
-      float sumgp = 0;
-      for (int j = 0; j < 3; ++j) sumgp += g[j];
-      for (int j = 0; j < 3; ++j) {
-        g[j] /= sumgp;
-        gpSums[j] += g[j];
-        out[i * 3 + j] = g[j];
-      }
-    }
-    for (int j = 0; j < 3; ++j) gpSums[j] /= (int32_t)(nv + 1.0);
-    for (int32_t i = 0; i < nv; ++i)  // :490-496
-      for (int j = 0; j < 3; ++j) out[i * 3 + j] = ((1.0 - gt_error) * out[i * 3 + j] + gt_error * gpSums[j]);
-    return true;
+    const bool ok = compute_posteriors(cur, field, gt_error, out);
+    acs = cur.acs;
+    an = cur.an;
+    return ok;
   }
 
-  // one float INFO value; false if absent
   bool info_float(const char* tag, float* v) const {
     const char* s = info_value(tag);
     if (s) *v = strtof(s, NULL);
@@ -822,51 +765,114 @@ class VcfReader {
       if (!an_) fatal("Cannot find AN field from INFO field at %s:%d", chroms[cur.rid].c_str(), cur.pos1);
       return (double)strtol(ac, NULL, 10) / (double)strtol(an_, NULL, 10);
     }
-    parse_genotypes();
+    parse_genotypes(cur);
+    acs = cur.acs;
+    an = cur.an;
     return (double)acs[1] / (double)an;
   }
 
  private:
-  void parse_line() {
-    cur.line.swap(lr_.line);
-    std::vector<char*> f;
-    char* p = &cur.line[0];
-    f.push_back(p);
-    for (; *p; ++p)
+  // ---- batch: read B lines, parse them on nthreads_ threads ----
+  bool fill_batch() {
+    constexpr size_t kBatch = 2048;
+    if (batch_.size() < kBatch) batch_.resize(kBatch);
+    batch_n_ = 0;
+    next_ = 0;
+    while (batch_n_ < kBatch && lr_.next_line()) {
+      if (lr_.line.empty() || lr_.line[0] == '#') continue;
+      VcfRecord& r = batch_[batch_n_++];
+      r.line.swap(lr_.line);
+      r.error.clear();
+      r.gp_ok = false;
+      r.pass = false;
+    }
+    if (batch_n_ == 0) return false;
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+      for (size_t i = next++; i < batch_n_; i = next++) {
+        VcfRecord& r = batch_[i];
+        try {
+          parse_record(r);
+        } catch (const std::exception& e) {
+          r.error = e.what();
+          if (r.error.empty()) r.error = "malformed VCF record";
+        }
+      }
+    };
+    const int nt = (int)std::min<size_t>((size_t)nthreads_, (batch_n_ + 63) / 64);
+    if (nt <= 1) {
+      work();
+    } else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; ++t) th.emplace_back(work);
+      for (auto& t : th) t.join();
+    }
+    return true;
+  }
+  // everything about one record that does not depend on the records before it
+  void parse_record(VcfRecord& r) const {
+    tokenize(r);
+    // passed_vfilter (bcf_filtered_reader.cpp:571-645): with no genotype-based threshold set (require_GT false,
+    // bcf_filter_arg.h:109-113) it returns true before it ever looks at the allele count
+    const bool require_GT = minMAC > 0 || minCallRate > 0;
+    bool pass = !require_GT || r.n_allele <= maxAlleles;
+    if (pass && require_GT) {  // vfilt.require_GT, bcf_filtered_reader.cpp:613-645
+      if (!parse_genotypes(r)) fatal("Cannot find the field GT from the VCF file at position %s:%d", r.chrom.c_str(), r.pos1);
+      if (minCallRate > (double)r.an / (2.0 * (double)sm_icols.size())) pass = false;
+      const int32_t ac = r.an - (int32_t)r.acs[0];
+      if (ac < minMAC || r.an - ac < minMAC) pass = false;
+    }
+    r.pass = pass;
+    if (pass && !prefetch_field_.empty() && r.n_allele == 2 && !sm_icols.empty()) {
+      r.gp.resize((size_t)nsamples() * 3);
+      // the filter's allele counts are what read() hands out; the pre-fetch (whose PL branch re-estimates them)
+      // must not disturb them
+      const std::vector<double> acs_keep = r.acs;
+      const int32_t an_keep = r.an;
+      r.gp_ok = compute_posteriors(r, prefetch_field_.c_str(), prefetch_gt_error_, r.gp.data());
+      r.acs = acs_keep;
+      r.an = an_keep;
+    }
+  }
+  void tokenize(VcfRecord& r) const {
+    std::vector<uint32_t> f;
+    char* base = &r.line[0];
+    f.push_back(0);
+    for (char* p = base; *p; ++p)
       if (*p == '\t') {
         *p = '\0';
-        f.push_back(p + 1);
+        f.push_back((uint32_t)(p + 1 - base));
       }
     if (f.size() < 8) fatal("Malformed VCF record (%zu columns)", f.size());
-    cur.rid = chrom_id(f[0]);
-    cur.pos1 = atoi(f[1]);
-    cur.ref = f[3];
-    cur.alt = f[4];
-    cur.n_allele = (cur.alt == ".") ? 1 : 2 + (int32_t)std::count(cur.alt.begin(), cur.alt.end(), ',');
-    cur.info = f[7];
-    cur.fmt.clear();
-    cur.cols.clear();
+    r.chrom = base + f[0];
+    r.pos1 = atoi(base + f[1]);
+    r.ref = base + f[3];
+    r.alt = base + f[4];
+    r.n_allele = (r.alt == ".") ? 1 : 2 + (int32_t)std::count(r.alt.begin(), r.alt.end(), ',');
+    r.info = base + f[7];
+    r.fmt.clear();
+    r.col_off.clear();
     if (f.size() > 9) {
-      const char* q = f[8];
+      const char* q = base + f[8];
       while (true) {
         const char* e = strchr(q, ':');
         if (!e) {
-          cur.fmt.push_back(q);
+          r.fmt.push_back(q);
           break;
         }
-        cur.fmt.push_back(std::string(q, e - q));
+        r.fmt.push_back(std::string(q, e - q));
         q = e + 1;
       }
-      cur.cols.assign(f.begin() + 9, f.end());
+      r.col_off.assign(f.begin() + 9, f.end());
     }
   }
-  int fmt_index(const char* key) const {
-    for (size_t i = 0; i < cur.fmt.size(); ++i)
-      if (cur.fmt[i] == key) return (int)i;
+  static int fmt_index(const VcfRecord& r, const char* key) {
+    for (size_t i = 0; i < r.fmt.size(); ++i)
+      if (r.fmt[i] == key) return (int)i;
     return -1;
   }
-  const char* sample_field(int col, int idx) const {
-    const char* p = cur.cols[col];
+  static const char* sample_field(const VcfRecord& r, int col, int idx) {
+    const char* p = r.line.data() + r.col_off[(size_t)col];
     for (int i = 0; i < idx; ++i) {
       p = strchr(p, ':');
       if (!p) return ".";
@@ -875,15 +881,15 @@ class VcfReader {
     return p;
   }
   // bcf_filtered_reader.cpp:198-254: allele counts over the selected samples
-  bool parse_genotypes() {
-    const int gi = fmt_index("GT");
+  bool parse_genotypes(VcfRecord& r) const {
+    const int gi = fmt_index(r, "GT");
     if (gi < 0) return false;
     const int32_t nv = nsamples();
-    gts_.resize(2 * nv);
-    acs.assign(cur.n_allele, 0.0);
-    an = 0;
+    r.gts.resize(2 * (size_t)nv);
+    r.acs.assign((size_t)r.n_allele, 0.0);
+    r.an = 0;
     for (int32_t i = 0; i < nv; ++i) {
-      const char* p = sample_field(sm_icols[i], gi);
+      const char* p = sample_field(r, sm_icols[i], gi);
       int a[2] = {-1, -1};
       int k = 0;
       while (*p && *p != ':' && k < 2) {
@@ -897,19 +903,108 @@ class VcfReader {
         ++k;
         if (*p == '/' || *p == '|') ++p;
       }
-      gts_[2 * i] = a[0];
-      gts_[2 * i + 1] = a[1];
+      r.gts[2 * (size_t)i] = a[0];
+      r.gts[2 * (size_t)i + 1] = a[1];
       for (int j = 0; j < 2; ++j)
-        if (a[j] >= 0 && a[j] < cur.n_allele) {
-          ++an;
-          ++acs[a[j]];
+        if (a[j] >= 0 && a[j] < r.n_allele) {
+          ++r.an;
+          ++r.acs[(size_t)a[j]];
         }
     }
     return true;
   }
+  // BCFFilteredReader::parse_posteriors (bcf_filtered_reader.cpp:406-500) for a biallelic record
+  bool compute_posteriors(VcfRecord& r, const char* field, double gt_error, float* out) const {
+    const int32_t nv = nsamples();
+    if (strcmp(field, "GT") == 0) {  // :414-452
+      if (!parse_genotypes(r)) return false;
+      for (int32_t i = 0; i < nv; ++i) {
+        const int32_t a1 = r.gts[2 * (size_t)i], a2 = r.gts[2 * (size_t)i + 1];
+        const int32_t g = (a1 < 0 || a2 < 0) ? -1 : (a1 > a2 ? a1 * (a1 + 1) / 2 + a2 : a2 * (a2 + 1) / 2 + a1);
+        if (g < 0) {
+          for (int32_t j = 0, l = 0; j < 2; ++j)
+            for (int32_t k = 0; k <= j; ++k, ++l)
+              out[i * 3 + l] = (float)((j == k ? 1.0 : 2.0) * (r.acs[j] + 1.0 / 2) / (r.an + 1.0) * (r.acs[k] + 1.0 / 2) / (r.an + 1.0));
+        } else {
+          for (int32_t j = 0; j < 3; ++j) out[i * 3 + j] = (g == j) ? 1.0 - gt_error : gt_error / (3 - 1.0);
+        }
+      }
+      return true;
+    }
+    if (strcmp(field, "PL") == 0) {  // parse_likelihoods, bcf_filtered_reader.cpp:289-365 (diploid samples)
+      // ten EM iterations for the allele frequency under HWE; the posteriors of the last one are the output.
+      // toProb(pl) = pow(0.1, pl * 0.1), capped at pl = 255 (PhredHelper.cpp:31, PhredHelper.h:40).
+      // Parity unpinned: the reference's own reader is htslib-bound and not buildable here (DESIGN.md section 6).
+      const int fi = fmt_index(r, "PL");
+      if (fi < 0) return false;
+      std::vector<uint32_t> pls((size_t)nv * 3);
+      for (int32_t i = 0; i < nv; ++i) {
+        const char* p = sample_field(r, sm_icols[i], fi);
+        for (int j = 0; j < 3; ++j) {
+          char* e;
+          long v = (*p == '.') ? 255 : strtol(p, &e, 10);  // a missing value carries no information either way
+          if (*p == '.') e = const_cast<char*>(p) + 1;
+          pls[(size_t)i * 3 + j] = (uint32_t)(v < 0 ? 0 : v);
+          p = (*e == ',') ? e + 1 : e;
+        }
+      }
+      r.acs.assign(2, 0.5);
+      double gp[3];
+      for (int it = 0; it < 10; ++it) {
+        double newacs[2] = {0, 0};
+        r.an = 0;
+        for (int32_t i = 0; i < nv; ++i) {
+          double sumgp = 0;
+          for (int j = 0, l = 0; j < 2; ++j)
+            for (int k = 0; k <= j; ++k, ++l) {
+              const uint32_t pl = pls[(size_t)i * 3 + l];
+              sumgp += (gp[l] = (j == k ? 1 : 2) * r.acs[j] * r.acs[k] * pow(0.1, (pl > 255 ? 255 : pl) * 0.1));
+            }
+          for (int j = 0, l = 0; j < 2; ++j)
+            for (int k = 0; k <= j; ++k, ++l) {
+              gp[l] /= sumgp;
+              newacs[j] += gp[l];
+              newacs[k] += gp[l];
+            }
+          r.an += 2;
+          if (it + 1 == 10)
+            for (int l = 0; l < 3; ++l) out[i * 3 + l] = (float)gp[l];
+        }
+        for (int j = 0; j < 2; ++j) r.acs[j] = newacs[j] / r.an;
+      }
+      for (int j = 0; j < 2; ++j) r.acs[j] *= r.an;
+      return true;
+    }
+    const int fi = fmt_index(r, field);
+    if (fi < 0) return false;
+    float gpSums[3] = {1.0f / 4.0f, 2.0f / 4.0f, 1.0f / 4.0f};  // :462-468 (nalleles = 2)
+    for (int32_t i = 0; i < nv; ++i) {  // :474-485
+      const char* p = sample_field(r, sm_icols[i], fi);
+      float g[3];
+      for (int j = 0; j < 3; ++j) {
+        const char* e;
+        g[j] = fast_strtof(p, &e);
+        p = (*e == ',') ? e + 1 : e;
+      }
+      float sumgp = 0;
+      for (int j = 0; j < 3; ++j) sumgp += g[j];
+      for (int j = 0; j < 3; ++j) {
+        g[j] /= sumgp;
+        gpSums[j] += g[j];
+        out[i * 3 + j] = g[j];
+      }
+    }
+    for (int j = 0; j < 3; ++j) gpSums[j] /= (int32_t)(nv + 1.0);
+    for (int32_t i = 0; i < nv; ++i)  // :490-496
+      for (int j = 0; j < 3; ++j) out[i * 3 + j] = ((1.0 - gt_error) * out[i * 3 + j] + gt_error * gpSums[j]);
+    return true;
+  }
   LineReader lr_;
-  std::vector<int32_t> gts_;
-  std::vector<uint32_t> pls_;
+  std::vector<VcfRecord> batch_;
+  size_t batch_n_ = 0, next_ = 0;
+  int nthreads_ = 1;
+  std::string prefetch_field_;
+  double prefetch_gt_error_ = 0;
 };
 
 // ---- droplet store flattened to CSR ----
