@@ -111,3 +111,71 @@ def test_oracle_freemuxlet_equals_live_reference(tmp_path, seed):
         assert f[1] == bcs[c] and f[4] == names[int(res["type"][c])], (seed, c, line)
         assert f[5] == "%d,%d" % (res["jBest"][c], res["kBest"][c]) and f[7] == "%d,%d" % (res["jNext"][c], res["kNext"][c])
         assert f[6] == "%.2f" % res["bestLLK"][c] and f[8] == "%.2f" % res["nextLLK"][c], (seed, c, line)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_freemux2_equals_live_reference(tmp_path, seed):
+    """freemux2 (cmd_cram_freemux2.cpp) on random cases: the library's greedy cluster-pileup initialisation gives the
+    reference's .clust0, and the oracle's EM in the freemux2 flavour (genotype error on every iteration, stop once no
+    call changes) ends in the reference's .clust1.samples.gz rows."""
+    from cramore_b200.engine import greedy_clusters
+    rng = np.random.default_rng(5000 + seed)
+    K = int(rng.integers(2, 7))
+    d = make_dataset("C4", nbcs=int(rng.integers(30, 90)), nsnps=int(rng.integers(200, 500)), rbar=int(rng.integers(40, 110)),
+                     nv=int(rng.integers(2, 6)), seed=9000 + seed, with_barcodes=True)
+    ge = float(rng.choice([0.02, 0.1]))
+    prior = float(rng.choice([0.3, 0.5]))
+    frac = float(rng.choice([0.5, 1.0]))
+    bcs = write_plp(d, str(tmp_path / "in"))
+    _run_ref(["freemux2", "--plp", "in", "--out", "out", "--nsample", str(K), "--aux-files", "--seed", "11", "--geno-error", repr(ge),
+              "--doublet-prior", repr(prior), "--frac-init-clust", repr(frac)], str(tmp_path))
+    c0 = [int(ln.split("\t")[2]) for ln in gzip.open(str(tmp_path / "out.clust0.samples.gz"), "rt").read().splitlines()[1:]]
+    ref_rows = gzip.open(str(tmp_path / "out.clust1.samples.gz"), "rt").read().splitlines()[1:]
+
+    # freemux2's read filter defaults cap base qualities at 20 (cmd_cram_freemux2.cpp:24); the synthetic ones already are
+    plp = pyoracle.fmx_pileup(d["read_ptr"], d["al"], d["bq"], 0.5)
+    af = np.asarray(["%.5f" % a for a in d["af"]], np.float64)
+    l0, l2 = pyoracle.fmx_lmix(d["cell_ptr"], d["snp_idx"], plp, af)
+    clusts = greedy_clusters(d["cell_ptr"], d["snp_idx"], plp, af, l2 - l0, K, d["nsnps"], frac_init_clust=frac)
+    assert clusts.tolist() == c0, seed
+    clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], plp, clusts, K, d["nsnps"])
+    prev = None
+    for it in range(10):
+        res, _ = pyoracle.fmx_estep(d["cell_ptr"], d["snp_idx"], plp, af, clust, prior, ge, True)
+        assign = np.where(res["type"] == 0, res["jBest"], -1).astype(np.int32)
+        clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], plp, assign, K, d["nsnps"])
+        key = np.where(res["type"] == 0, res["sBest"], -1 - res["type"])
+        if prev is not None and np.array_equal(key, prev):
+            break
+        prev = key
+    names = {0: "SNG", 1: "DBL", 2: "AMB"}
+    assert len(ref_rows) == d["nbcs"]
+    for c, line in enumerate(ref_rows):
+        f = line.split("\t")
+        assert f[1] == bcs[c] and f[4] == names[int(res["type"][c])], (seed, c, line)
+        assert f[5] == "%d,%d" % (res["jBest"][c], res["kBest"][c]) and f[6] == "%.2f" % res["bestLLK"][c], (seed, c, line)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_initial_clustering_equals_live_reference(tmp_path, seed):
+    """freemuxlet without --init-cluster on random cases: pairwise distances (oracle) + the library's host votes with
+    the reference's rand() call order give the .clust0 the reference itself wrote, for random thresholds and fractions."""
+    from cramore_b200.engine import initial_clusters
+    from tests import refcase
+    rng = np.random.default_rng(7000 + seed)
+    K = int(rng.integers(2, 6))
+    d = make_dataset("C4", nbcs=int(rng.integers(30, 70)), nsnps=int(rng.integers(150, 400)), rbar=int(rng.integers(60, 120)),
+                     nv=int(rng.integers(2, 5)), seed=9500 + seed, with_barcodes=True)
+    bf = float(rng.choice([2.0, 5.41, 8.0]))
+    frac = float(rng.choice([0.6, 1.0]))
+    write_plp(d, str(tmp_path / "in"))
+    _run_ref(["freemuxlet", "--plp", "in", "--out", "out", "--nsample", str(K), "--aux-files", "--bf-thres", repr(bf),
+              "--frac-init-clust", repr(frac)], str(tmp_path))
+    c0 = [int(ln.split("\t")[2]) for ln in gzip.open(str(tmp_path / "out.clust0.samples.gz"), "rt").read().splitlines()[1:]]
+    plp = pyoracle.fmx_pileup(d["read_ptr"], d["al"], d["bq"], 0.5)
+    af = np.asarray(["%.5f" % a for a in d["af"]], np.float64)
+    l0, l2 = pyoracle.fmx_lmix(d["cell_ptr"], d["snp_idx"], plp, af)
+    dense = pyoracle.fmx_pair_dist(d["cell_ptr"], d["snp_idx"], plp, af, d["nsnps"])
+    clusts = initial_clusters(l2 - l0, refcase.sparse_pairs(dense), K, bf_thres=bf, frac_init_clust=frac, iter_init=10,
+                              keep_init_missing=False, init=None, seed=1)
+    assert clusts.tolist() == c0, (seed, K, bf, frac)
