@@ -1164,13 +1164,38 @@ inline void load_plp(const std::string& prefix, const PlpFilters& flt, DropletSt
     notice("Finished loading %u UMIs in total..", numi);
   }
   // reference iteration order: droplet id, SNP id (std::map<int32_t,...>), UMI string (std::map<std::string,...>)
-  std::sort(recs.begin(), recs.end(), [](const ReadRec& a, const ReadRec& b) {
-    if (a.cell != b.cell) return a.cell < b.cell;
-    if (a.snp != b.snp) return a.snp < b.snp;
-    if (a.key != b.key) return a.key < b.key;
-    return a.nd < b.nd;
-  });
+  // (one counting pass by droplet, then every droplet's few hundred reads sorted on their own, droplets spread over
+  // the host cores: the same order as one big sort by (droplet, SNP, key, digits), at a fraction of its cost)
   const int32_t nb = st.nbcs();
+  {
+    std::vector<size_t> start((size_t)nb + 1, 0);
+    for (const ReadRec& r : recs) ++start[(size_t)r.cell + 1];
+    for (int32_t c = 0; c < nb; ++c) start[(size_t)c + 1] += start[(size_t)c];
+    std::vector<ReadRec> by_cell(recs.size());
+    {
+      std::vector<size_t> fill(start.begin(), start.end() - 1);
+      for (const ReadRec& r : recs) by_cell[fill[(size_t)r.cell]++] = r;
+    }
+    recs.swap(by_cell);
+    std::atomic<int32_t> next{0};
+    auto work = [&]() {
+      for (int32_t c = next++; c < nb; c = next++)
+        std::sort(recs.begin() + (ptrdiff_t)start[(size_t)c], recs.begin() + (ptrdiff_t)start[(size_t)c + 1],
+                  [](const ReadRec& a, const ReadRec& b) {
+                    if (a.snp != b.snp) return a.snp < b.snp;
+                    if (a.key != b.key) return a.key < b.key;
+                    return a.nd < b.nd;
+                  });
+    };
+    const int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    if (nt <= 1 || recs.size() < 100000) {
+      work();
+    } else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; ++t) th.emplace_back(work);
+      for (auto& t : th) t.join();
+    }
+  }
   st.cell_ptr.assign(nb + 1, 0);
   st.uniq_reads.assign(nb, 0);
   st.read_ptr.assign(1, 0);
