@@ -898,3 +898,29 @@ def test_patched_reference_has_no_cpu_path(tmp_path):
     r = subprocess.run([exe, "demuxlet", "--plp", "in", "--vcf", "in.vcf", "--out", "out"], capture_output=True, text=True,
                        cwd=str(tmp_path))
     assert r.returncode != 0 and "ccu_create" in r.stderr and not os.path.exists(str(tmp_path / "out.best"))
+
+
+def test_bgzf_stream_across_many_batches(built, tmp_path):
+    """The BGZF reader hands out batches of 512 blocks, the next one inflated by a helper thread while the current one
+    is consumed: a text of several thousand tiny blocks (lines straddling block and batch borders) comes back intact,
+    with one inflate thread and with many."""
+    from cramore_b200.synth import _bgzf_block
+    rng = np.random.default_rng(5)
+    lines = ["##fileformat=VCFv4.2", "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO"]
+    for i in range(20000):
+        lines.append("1\t%d\t.\tA\tC\t.\tPASS\tX=%s" % (i + 1, "".join("ACGT"[j] for j in rng.integers(0, 4, int(rng.integers(0, 60))))))
+    text = ("\n".join(lines) + "\n").encode()
+    path = str(tmp_path / "many.vcf.gz")
+    with open(path, "wb") as f:
+        off = 0
+        while off < len(text):
+            n = int(rng.integers(1, 400))
+            f.write(_bgzf_block(text[off:off + n]))
+            if rng.integers(50) == 0:
+                f.write(_bgzf_block(b""))   # empty blocks may appear anywhere (bgzip writes one at every flush)
+            off += n
+        f.write(_bgzf_block(b""))
+    for threads in ("1", "7"):
+        r = subprocess.run([CRAMORE, "vcf-text", path], capture_output=True, env=dict(os.environ, CRAMORE_BGZF_THREADS=threads))
+        assert r.returncode == 0, r.stderr[-1000:]
+        assert r.stdout == text
