@@ -214,35 +214,62 @@ int ccu_demux_configure(ccu_handle* h, int32_t nv, int32_t nalpha, const double*
   return 0;
 }
 
-int ccu_demux_set_genotypes(ccu_handle* h, int64_t nsnps, const float* gp, const double* snp_err,
-                            const uint8_t* has_gp) {
+// Device-side staging of the genotype inputs (include/cramore_cuda.h): reserve the float matrix, the per-SNP error
+// and flag arrays and hand their device addresses to the caller, who fills them on the engine's stream -- a plain
+// host->device copy, or (multi-GPU) a copy of one SNP slab per rank completed by an all-gather over NVLink.
+int ccu_demux_genotypes_stage(ccu_handle* h, int64_t nsnps, void** gp_dev, void** snp_err_dev, void** has_gp_dev) {
   if (!h) return 1;
-  if (!h->configured) return fail(h, "ccu_demux_set_genotypes: call ccu_demux_configure first");
-  if (nsnps < 0 || (nsnps > 0 && (!gp || !snp_err))) return fail(h, "ccu_demux_set_genotypes: bad arguments");
-  if (nsnps > 2147483647LL) return fail(h, "ccu_demux_set_genotypes: more than 2^31-1 SNPs");
+  if (!h->configured) return fail(h, "ccu_demux_genotypes_stage: call ccu_demux_configure first");
+  if (nsnps < 0) return fail(h, "ccu_demux_genotypes_stage: bad arguments");
+  if (nsnps > 2147483647LL) return fail(h, "ccu_demux_genotypes_stage: more than 2^31-1 SNPs");
   CCU_CUDA(h, cudaSetDevice(h->device));
   const size_t nf = (size_t)nsnps * h->nv * 3;
   CCU_CUDA(h, h->d_gpf.reserve(nf * sizeof(float) + 16));
   CCU_CUDA(h, h->d_err.reserve(nsnps * sizeof(double) + 16));
   CCU_CUDA(h, h->d_avg.reserve(nsnps * 4 * sizeof(double) + 16));
   CCU_CUDA(h, h->d_G.reserve((size_t)nsnps * h->nvp * 3 * sizeof(double) + 16));
-  h->has_gp_flags = has_gp != nullptr;
-  if (has_gp) CCU_CUDA(h, h->d_hasgp.reserve(nsnps + 16));
+  CCU_CUDA(h, h->d_hasgp.reserve(nsnps + 16));
+  if (gp_dev) *gp_dev = h->d_gpf.p;
+  if (snp_err_dev) *snp_err_dev = h->d_err.p;
+  if (has_gp_dev) *has_gp_dev = h->d_hasgp.p;
+  h->nsnps = -1;  // nothing usable until the commit
+  h->staged_snps = nsnps;
+  return 0;
+}
+
+int ccu_demux_genotypes_commit(ccu_handle* h, int64_t nsnps, int32_t use_has_gp) {
+  if (!h) return 1;
+  if (!h->configured) return fail(h, "ccu_demux_genotypes_commit: call ccu_demux_configure first");
+  if (nsnps < 0 || nsnps != h->staged_snps)
+    return fail(h, "ccu_demux_genotypes_commit: %lld SNPs were not staged by ccu_demux_genotypes_stage", (long long)nsnps);
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  h->has_gp_flags = use_has_gp != 0;
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_GP0], h->stream));
+  CCU_CUDA(h, ccu::launch_gp_prepare(h->d_gpf.as<float>(), h->d_err.as<double>(),
+                                     use_has_gp ? h->d_hasgp.as<uint8_t>() : nullptr, nsnps, h->nv, h->nvp,
+                                     h->d_avg.as<double>(), h->d_G.as<double>(), h->stream));
+  CCU_CUDA(h, cudaEventRecord(h->ev[EV_GP1], h->stream));
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->tm.ms_genotypes = ev_ms(h, EV_GP0, EV_GP1);
+  h->nsnps = nsnps;
+  h->have_avg = true;
+  return 0;
+}
+
+int ccu_demux_set_genotypes(ccu_handle* h, int64_t nsnps, const float* gp, const double* snp_err,
+                            const uint8_t* has_gp) {
+  if (!h) return 1;
+  if (!h->configured) return fail(h, "ccu_demux_set_genotypes: call ccu_demux_configure first");
+  if (nsnps < 0 || (nsnps > 0 && (!gp || !snp_err))) return fail(h, "ccu_demux_set_genotypes: bad arguments");
+  if (int rc = ccu_demux_genotypes_stage(h, nsnps, nullptr, nullptr, nullptr)) return rc;
+  const size_t nf = (size_t)nsnps * h->nv * 3;
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_X0], h->stream));
   if (nsnps > 0) {
     CCU_CUDA(h, cudaMemcpyAsync(h->d_gpf.p, gp, nf * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CCU_CUDA(h, cudaMemcpyAsync(h->d_err.p, snp_err, nsnps * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     if (has_gp) CCU_CUDA(h, cudaMemcpyAsync(h->d_hasgp.p, has_gp, nsnps, cudaMemcpyHostToDevice, h->stream));
   }
-  CCU_CUDA(h, cudaEventRecord(h->ev[EV_GP0], h->stream));
-  CCU_CUDA(h, ccu::launch_gp_prepare(h->d_gpf.as<float>(), h->d_err.as<double>(),
-                                     has_gp ? h->d_hasgp.as<uint8_t>() : nullptr, nsnps, h->nv, h->nvp,
-                                     h->d_avg.as<double>(), h->d_G.as<double>(), h->stream));
-  CCU_CUDA(h, cudaEventRecord(h->ev[EV_GP1], h->stream));
-  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
-  h->tm.ms_genotypes = ev_ms(h, EV_GP0, EV_GP1);
-  h->nsnps = nsnps;
-  return 0;
+  return ccu_demux_genotypes_commit(h, nsnps, has_gp != nullptr);
 }
 
 // The reference keeps sc_snp_t::gps (sc_drop_seq.h:115-127): nv*3 doubles per SNP, genotype error already mixed
@@ -280,6 +307,8 @@ int ccu_demux_set_genotypes_mixed(ccu_handle* h, int64_t nsnps, const double* co
   CCU_CUDA(h, cudaStreamSynchronize(h->stream));
   h->tm.ms_genotypes = ev_ms(h, EV_GP0, EV_GP1);
   h->nsnps = nsnps;
+  h->have_avg = false;
+  h->staged_snps = -1;
   return 0;
 }
 
@@ -396,6 +425,12 @@ int ccu_demux_wait(ccu_handle* h) {
   if (!h->ran) return fail(h, "ccu_demux_wait: nothing has been run");
   CCU_CUDA(h, cudaSetDevice(h->device));
   return collect_run_timings(h);
+}
+
+void* ccu_demux_results_dev(ccu_handle* h, int64_t* nbcs) {
+  if (!h || !h->ran) return nullptr;
+  if (nbcs) *nbcs = h->nbcs;
+  return h->d_results.p;
 }
 
 int ccu_demux_download(ccu_handle* h, ccu_demux_result* out) {

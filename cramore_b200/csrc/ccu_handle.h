@@ -61,7 +61,9 @@ struct ccu_handle {
 
   // genotypes
   int64_t nsnps = -1;
+  int64_t staged_snps = -1;   // SNPs reserved by ccu_demux_genotypes_stage and not committed yet
   bool has_gp_flags = false;
+  bool have_avg = false;      // d_avg holds the per-SNP averages of the float matrix (set_genotypes / commit)
   DevBuf d_gpf, d_err, d_hasgp, d_avg, d_G;
 
   // droplets

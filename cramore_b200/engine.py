@@ -49,6 +49,8 @@ ABI_SYMBOLS = [
     "ccu_fmx_greedy_clusters", "ccu_fmx_get_voting_pairs", "ccu_fmx_peer_handles", "ccu_fmx_peer_open",
     "ccu_fmx_peer_close", "ccu_fmx_posteriors_push_dev", "ccu_fmx_assign_push_dev", "ccu_fmx_rank_barrier_dev",
     "ccu_fmx_rank_barrier_failed", "ccu_fmx_run_em_multi", "ccu_demux_set_genotypes_mixed",
+    "ccu_demux_genotypes_stage", "ccu_demux_genotypes_commit", "ccu_demux_results_dev",
+    "ccu_demux_refine", "ccu_demux_refine_mixed",
 ]
 
 
@@ -66,7 +68,7 @@ def load_library():
         lib.ccu_demux_best_header.restype = C.c_char_p
         for name in ABI_SYMBOLS:
             fn = getattr(lib, name)
-            if name in ("ccu_fmx_stats_dev", "ccu_fmx_assign_dev", "ccu_fmx_post_dev"):
+            if name in ("ccu_fmx_stats_dev", "ccu_fmx_assign_dev", "ccu_fmx_post_dev", "ccu_demux_results_dev"):
                 fn.restype = C.c_void_p
             elif name not in ("ccu_last_error", "ccu_demux_best_header"):
                 fn.restype = C.c_int
@@ -130,6 +132,23 @@ class DemuxEngine:
         hg = None if has_gp is None else np.ascontiguousarray(has_gp, np.uint8)
         self._check(self.lib.ccu_demux_set_genotypes(self.h, C.c_int64(nsnps), _ptr(gp), _ptr(err), _ptr(hg)))
         self.nsnps = nsnps
+
+    def genotypes_stage(self, nsnps):
+        """ccu_demux_genotypes_stage: device addresses of the float matrix [nsnps][nv][3], the per-SNP error (f64)
+        and the has-genotype flags (u8), to be filled on the engine's stream before genotypes_commit."""
+        gp, err, hg = C.c_void_p(0), C.c_void_p(0), C.c_void_p(0)
+        self._check(self.lib.ccu_demux_genotypes_stage(self.h, C.c_int64(nsnps), C.byref(gp), C.byref(err), C.byref(hg)))
+        return gp.value, err.value, hg.value
+
+    def genotypes_commit(self, nsnps, use_has_gp=False):
+        self._check(self.lib.ccu_demux_genotypes_commit(self.h, C.c_int64(nsnps), C.c_int32(int(use_has_gp))))
+        self.nsnps = nsnps
+
+    def results_dev(self):
+        """(device pointer, nbcs) of the result records of the last run."""
+        n = C.c_int64(0)
+        p = self.lib.ccu_demux_results_dev(self.h, C.byref(n))
+        return p, n.value
 
     @staticmethod
     def _csr(cell_ptr, snp_idx, read_ptr, al, bq):
@@ -433,6 +452,25 @@ def greedy_clusters(cell_ptr, snp_idx, plp, af, cell_scores, nclust, nsnps, frac
     if rc:
         raise ValueError("ccu_fmx_greedy_clusters: bad arguments")
     return clusts
+
+
+def refine(results, cell_ptr, snp_idx, read_ptr, al, bq, nv, alphas, gp_f32, snp_err, has_gp=None, nthreads=0):
+    """ccu_demux_refine: the reported candidates re-scored in the reference's operation order (host code of the
+    library, for byte-identical .best rows).  Returns a refined copy of `results`."""
+    lib = load_library()
+    cp, si, rp, a, q = DemuxEngine._csr(cell_ptr, snp_idx, read_ptr, al, bq)
+    al_ = np.ascontiguousarray(alphas, np.float64)
+    gp = np.ascontiguousarray(gp_f32, np.float32)
+    nsnps = gp.shape[0]
+    err = np.ascontiguousarray(np.broadcast_to(np.asarray(snp_err, np.float64), (nsnps,)))
+    hg = None if has_gp is None else np.ascontiguousarray(has_gp, np.uint8)
+    out = np.ascontiguousarray(results).copy()
+    rc = lib.ccu_demux_refine(C.c_int64(len(cp) - 1), _ptr(cp), _ptr(si), _ptr(rp), _ptr(a), _ptr(q), C.c_int32(nv),
+                              C.c_int32(len(al_)), _ptr(al_), C.c_int64(nsnps), _ptr(gp), _ptr(err), _ptr(hg),
+                              C.c_int32(nthreads), _ptr(out))
+    if rc:
+        raise EngineError("ccu_demux_refine: bad arguments")
+    return out
 
 
 def classify(results, nv, alphas, doublet_prior=0.5):

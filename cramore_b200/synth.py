@@ -45,8 +45,11 @@ def make_genotypes(rng, nsnps, nv):
     return af, geno, gp
 
 
-def make_droplets(rng, geno, nbcs, rbar, doublet_rate, min_bq=13, cap_bq=20, chunk=2_000_000):
-    """Simulated droplets -> CSR (cell_ptr, snp_idx, read_ptr, al, bq) + truth."""
+def make_droplets(rng, geno, nbcs, rbar, doublet_rate, min_bq=13, cap_bq=20, chunk=2_000_000, snp_skew=0.0):
+    """Simulated droplets -> CSR (cell_ptr, snp_idx, read_ptr, al, bq) + truth.
+    snp_skew > 0: the SNP of a read is drawn from a Zipf law P(rank r) ~ 1/r^snp_skew over a random permutation of
+    the panel instead of uniformly -- expression in real scRNA-seq is skewed, so a few SNPs collect many reads of a
+    droplet and a large share of the (cell, SNP) entries holds two or more reads."""
     nsnps, nv = geno.shape
     is_dbl = rng.random(nbcs) < doublet_rate
     s1 = rng.integers(0, nv, nbcs)
@@ -55,7 +58,14 @@ def make_droplets(rng, geno, nbcs, rbar, doublet_rate, min_bq=13, cap_bq=20, chu
     nreads = rng.poisson(rbar, nbcs).astype(np.int64)
     R = int(nreads.sum())
     cell = np.repeat(np.arange(nbcs, dtype=np.int64), nreads)
-    snp = rng.integers(0, nsnps, R).astype(np.int64)
+    if snp_skew > 0:
+        w = 1.0 / np.power(np.arange(1, nsnps + 1, dtype=np.float64), snp_skew)
+        cdf = np.cumsum(w)
+        cdf /= cdf[-1]
+        perm = rng.permutation(nsnps)
+        snp = perm[np.minimum(np.searchsorted(cdf, rng.random(R), side="right"), nsnps - 1)].astype(np.int64)
+    else:
+        snp = rng.integers(0, nsnps, R).astype(np.int64)
     src = np.where(rng.random(R) < 0.5, s1[cell], s2[cell])
     g = np.empty(R, np.int8)
     for a in range(0, R, chunk):  # gather in chunks to bound temporaries
@@ -111,7 +121,7 @@ def make_barcodes(rng, nbcs):
 
 
 def make_dataset(name="C1", nbcs=None, nsnps=None, nv=None, rbar=None, seed=None, droplet_seed_offset=0,
-                 geno_error_offset=0.10, with_barcodes=False):
+                 geno_error_offset=0.10, with_barcodes=False, snp_skew=0.0):
     """Dataset of a named BASELINE config (any size field can be overridden for tests)."""
     cfg = dict(CONFIGS[name])
     if nbcs is not None:
@@ -126,8 +136,8 @@ def make_dataset(name="C1", nbcs=None, nsnps=None, nv=None, rbar=None, seed=None
     rng_g = np.random.Generator(np.random.Philox(key=seed))
     af, geno, gp = make_genotypes(rng_g, cfg["nsnps"], cfg["nv"])
     rng_d = np.random.Generator(np.random.Philox(key=seed + 7919 * (1 + droplet_seed_offset)))
-    d = make_droplets(rng_d, geno, cfg["nbcs"], cfg["rbar"], cfg["doublet_rate"])
-    d.update(name=name, cfg=cfg, seed=seed, gp=gp, af=af, geno=geno,
+    d = make_droplets(rng_d, geno, cfg["nbcs"], cfg["rbar"], cfg["doublet_rate"], snp_skew=snp_skew)
+    d.update(snp_skew=snp_skew, name=name, cfg=cfg, seed=seed, gp=gp, af=af, geno=geno,
              snp_err=np.full(cfg["nsnps"], geno_error_offset, np.float64),
              alphas=np.asarray(cfg["alphas"], np.float64), nv=cfg["nv"], nsnps=cfg["nsnps"], nbcs=cfg["nbcs"],
              sample_ids=["SM%03d" % i for i in range(cfg["nv"])])

@@ -103,6 +103,16 @@ int ccu_demux_set_genotypes(ccu_handle* h, int64_t nsnps, const float* gp, const
  * a SNP without genotypes.  Lets a patched cmdCramDemuxlet pass `scl.snps[s].gps` through unchanged. */
 int ccu_demux_set_genotypes_mixed(ccu_handle* h, int64_t nsnps, const double* const* gps);
 
+/* Multi-GPU form of ccu_demux_set_genotypes (no reference counterpart: the reference is one process and scales by
+ * --group-list, cmd_cram_demuxlet.cpp:75, every process parsing the whole VCF).  The genotype matrix is replicated
+ * on every GPU, but only ONE copy has to cross PCIe: ccu_demux_genotypes_stage reserves the device arrays
+ * (float [nsnps][nv][3], double [nsnps], uint8 [nsnps]) and returns their DEVICE addresses; the caller fills them on
+ * the engine's stream -- each rank copies its own SNP slab host->device and an all-gather over NVLink (NCCL, or
+ * cudaMemcpyPeerAsync inside one process) completes the matrix -- and ccu_demux_genotypes_commit runs the mixing
+ * kernels of sc_drop_seq.cpp:287-315 on what is there.  use_has_gp == 0: every SNP has genotypes. */
+int ccu_demux_genotypes_stage(ccu_handle* h, int64_t nsnps, void** gp_dev, void** snp_err_dev, void** has_gp_dev);
+int ccu_demux_genotypes_commit(ccu_handle* h, int64_t nsnps, int32_t use_has_gp);
+
 /* The whole engine for nbcs droplets, replaces cmd_cram_demuxlet.cpp:636-906 (tile :655-725,
  * pairwise accumulation :733-747, posterior normaliser :804-821, top-2 scans :827-906).
  * out[nbcs] in CSR barcode order.  Equivalent to upload + run + download. */
@@ -116,6 +126,9 @@ int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const
 int ccu_demux_run(ccu_handle* h);  /* asynchronous on the stream */
 int ccu_demux_wait(ccu_handle* h); /* wait for the last run and refresh ccu_get_timings() */
 int ccu_demux_download(ccu_handle* h, ccu_demux_result* out);
+/* Device address of the ccu_demux_result[nbcs] array of the last run (valid until the next upload): lets a
+ * multi-GPU driver gather the shards' records over NVLink (ncclAllGather) instead of through the host. */
+void* ccu_demux_results_dev(ccu_handle* h, int64_t* nbcs);
 
 /* Decision + row formatting (host code, cmd_cram_demuxlet.cpp:921-1013). */
 int ccu_demux_classify(const ccu_demux_result* r, int32_t nv, int32_t nalpha, const double* alpha,
@@ -126,6 +139,25 @@ int ccu_demux_best_row(char* buf, int32_t buflen, int32_t int_id, const char* ba
                        int32_t nalpha, const double* alpha, double doublet_prior,
                        const char* const* sample_ids);
 const char* ccu_demux_best_header(void);
+
+/* Text-level drop-in for <out>.best: re-scores the candidates a row can name -- the two best singlets and the two
+ * best doublets the engine reported, plus the mirror orientation (k, j, 1 - alpha) of each of those doublets where
+ * the grid holds 1 - alpha (at alpha = 0.5: (k, j)) -- in the reference's own IEEE operation sequence
+ * (cmd_cram_demuxlet.cpp:655-747: per-read tile loop, (g_j[l]*g_k[m])*pG l-outer / m-inner, sum of the host libm's
+ * log in SNP order) and re-applies the reference's top-2 update rule (:827-837, :883-906) to them, in place.
+ * Afterwards the indices, the orientation of mirror pairs and every printed LLK equal the reference's bit for bit
+ * (the engine's own values agree to ~1e-13 relative, which cannot decide a last-bit tie).  Host code, threads over
+ * droplets (nthreads <= 0: all cores), O(entries x (9 nalpha + candidates)): it decides the print, the search over
+ * all hypotheses stays on the GPU.  Needs no handle and no device.
+ *   ccu_demux_refine        genotypes as for ccu_demux_set_genotypes (float posteriors + per-SNP error + flags)
+ *   ccu_demux_refine_mixed  genotypes as for ccu_demux_set_genotypes_mixed (the reference's scl.snps[s].gps) */
+int ccu_demux_refine(int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx, const int64_t* read_ptr,
+                     const uint8_t* al, const uint8_t* bq, int32_t nv, int32_t nalpha, const double* alpha,
+                     int64_t nsnps, const float* gp, const double* snp_err, const uint8_t* has_gp, int32_t nthreads,
+                     ccu_demux_result* inout);
+int ccu_demux_refine_mixed(int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx, const int64_t* read_ptr,
+                           const uint8_t* al, const uint8_t* bq, int32_t nv, int32_t nalpha, const double* alpha,
+                           int64_t nsnps, const double* const* gps, int32_t nthreads, ccu_demux_result* inout);
 
 /* Inspection (parity tests): copy device intermediates of the last upload/run back.
  * tiles: [nnz][nalpha*9] (cmd_cram_demuxlet.cpp:655-725); gps: [snp_end-snp_begin][nv][3]
