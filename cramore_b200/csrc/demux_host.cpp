@@ -65,7 +65,7 @@ int ccu_demux_best_row(char* buf, int32_t buflen, int32_t int_id, const char* ba
   if (c.alphaBest < 0 || c.alphaNext < 0 || r->dBestA < 0) return -1;
   static const char* const kType[3] = {"SNG", "DBL", "AMB"};
   // cmd_cram_demuxlet.cpp:993
-  return snprintf(buf, buflen,
+  const int n = snprintf(buf, buflen,
                   "%d\t%s\t%u\t%d\t%s\t%s,%s,%.2lf\t%.2lf\t%s,%s,%.2lf\t%.2lf\t%.2lf\t%.2lg\t%.2lg\t%s\t%.2lf\t%s\t"
                   "%.2lf\t%.5lf\t%s,%s,%.2lf\t%.2lf\t%.2lf\n",
                   int_id, barcode, nsnps_cell, nreads_cell, kType[c.type], ids[c.jBest], ids[c.kBest],
@@ -73,6 +73,7 @@ int ccu_demux_best_row(char* buf, int32_t buflen, int32_t int_id, const char* ba
                   c.bestLLK - c.nextLLK, c.bestPP, c.sngPP, ids[r->sBest], r->sngBestLLK, ids[r->sNext],
                   r->sngNextLLK, c.sngOnlyPP, ids[r->dBest1], ids[r->dBest2], alpha[r->dBestA], r->dblBestLLK,
                   r->sngBestLLK - r->dblBestLLK);
+  return (n < 0 || n >= buflen) ? -2 : n;  // -2: the row does not fit buflen (nothing usable was written)
 }
 
 }  // extern "C"

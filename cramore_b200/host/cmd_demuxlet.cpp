@@ -58,6 +58,7 @@ int cmdDemuxlet(int argc, char** argv) {
   // defaults of cmd_cram_demuxlet.cpp:7-36
   std::string samFile, tagGroup("CB"), tagUMI("UB"), plpPrefix, vcfFile, field("GP"), r2Info("R2"), smList, outPrefix,
       groupList, gpuDevices("0"), dumpPrefix, loadPrefix;
+  bool gpuNoRefine = false;
   double genoErrorOffset = 0.10, genoErrorCoeffR2 = 0.00, minCallRate = 0.5, doublet_prior = 0.5;
   int32_t minMAC = 1, samVerbose = 1000000, vcfVerbose = 10000, capBQ = 20, minBQ = 13, minMQ = 20, minTD = 0,
           exclFlag = 0x0f04, minTotalReads = 0, minUMIs = 0, minCoveredSNPs = 0;
@@ -83,7 +84,7 @@ int cmdDemuxlet(int argc, char** argv) {
   pl.add("sm-list", &smList, "File containing the list of sample IDs to compare");
   pl.group("Output Options");
   pl.add("out", &outPrefix, "Output file prefix");
-  pl.add("alpha", &gridAlpha, "Grid of alpha to search for (default is 0.1, 0.2, 0.3, 0.4, 0.5)");
+  pl.add("alpha", &gridAlpha, "Grid of alpha to search for (default is 0, 0.5; the first value must be 0: singlets are read from it)");
   pl.add("doublet-prior", &doublet_prior, "Prior of doublet");
   pl.add("sam-verbose", &samVerbose, "Verbose message frequency for SAM/BAM/CRAM");
   pl.add("vcf-verbose", &vcfVerbose, "Verbose message frequency for VCF/BCF");
@@ -100,6 +101,7 @@ int cmdDemuxlet(int argc, char** argv) {
   pl.add("min-snp", &minCoveredSNPs, "Minimum number of SNPs with coverage for a droplet/cell to be considered");
   pl.group("GPU engine options (additions of this build)");
   pl.add("gpu-devices", &gpuDevices, "Comma-separated CUDA device ids; droplets are sharded across them");
+  pl.add("gpu-no-refine", &gpuNoRefine, "Skip the host pass that re-scores the reported best/next guesses in the reference's own operation order (rows then agree with the reference to ~1e-13 in the likelihoods instead of byte for byte)");
   pl.add("gpu-dump-inputs", &dumpPrefix, "Write the flattened engine inputs to PREFIX.* and exit without touching a GPU");
   pl.add("gpu-load-inputs", &loadPrefix, "Binary sidecar cache: read the engine inputs written by --gpu-dump-inputs instead of parsing --plp/--vcf (droplet and variant filters are those of the dump)");
   if (!pl.read(argc, argv)) return 1;
@@ -109,6 +111,11 @@ int cmdDemuxlet(int argc, char** argv) {
     gridAlpha.push_back(0.5);
   }
   const int32_t nAlpha = (int32_t)gridAlpha.size();
+  // What the engine cannot take is refused here, before any file is read (the reference is undefined for the first
+  // two: its doublet indices stay -1 and index the sample table)
+  if (nAlpha < 2) fatal("--alpha : the grid needs 0 and at least one doublet fraction (e.g. --alpha 0 --alpha 0.5)");
+  if (gridAlpha[0] != 0.0) fatal("--alpha : the first value must be 0 (singlet likelihoods are read from it); got %lg", gridAlpha[0]);
+  if (nAlpha > CCU_MAX_ALPHA) fatal("--alpha : at most %d values are supported (got %d)", CCU_MAX_ALPHA, nAlpha);
   if (!samFile.empty() && !plpPrefix.empty()) fatal("with --plp option, neither --sam option cannot be used");
   if (outPrefix.empty()) fatal("Missing required option(s) : --out");
   if (loadPrefix.empty() && ((plpPrefix.empty() && samFile.empty()) || vcfFile.empty()))
@@ -299,6 +306,7 @@ int cmdDemuxlet(int argc, char** argv) {
   }
   const int32_t nv = nv_total;
   const int64_t nrows = (int64_t)row_bcs.size();
+  if (nv < 2) fatal("--vcf / --sm : at least 2 samples are needed to tell singlets from doublets (got %d)", nv);
 
   // ---- engine: one handle per GPU, contiguous row ranges balanced by entry count ----
   notice("Starting to identify best matching individual IDs");
@@ -341,6 +349,12 @@ int cmdDemuxlet(int argc, char** argv) {
   }
   for (int d = 0; d < ndev; ++d)
     if (!errs[d].empty()) fatal("%s", errs[d].c_str());
+  // ---- the hypotheses a row names, re-scored in the reference's own operation order (cmd_cram_demuxlet.cpp:655-747):
+  // orientation of alpha = 0.5 mirror pairs and every printed digit then equal the reference's (demux_refine.cpp)
+  if (!gpuNoRefine &&
+      ccu_demux_refine(nrows, cell_ptr.data(), snp_idx.data(), read_ptr.data(), al.data(), bq.data(), nv, nAlpha,
+                       gridAlpha.data(), nsnps_total, gp_f32.data(), snp_err.data(), has_gp.data(), 0, res.data()))
+    fatal("ccu_demux_refine: bad arguments");
 
   // ---- <out>.best: header :629, rows :993 ----
   Writer wbest(outPrefix + ".best", false);
@@ -348,14 +362,16 @@ int cmdDemuxlet(int argc, char** argv) {
   wbest.write(hdr, (int)strlen(hdr));
   std::vector<const char*> ids(nv);
   for (int32_t j = 0; j < nv; ++j) ids[j] = sample_ids[j].c_str();
-  char row[8192];
+  std::vector<char> row(8192);
   for (int64_t r = 0; r < nrows; ++r) {
-    const int n = ccu_demux_best_row(row, sizeof(row), row_int_id[r], row_bcs[r].c_str(),
-                                     (uint32_t)(cell_ptr[r + 1] - cell_ptr[r]),
-                                     (uint32_t)(read_ptr[cell_ptr[r + 1]] - read_ptr[cell_ptr[r]]), &res[r], nv, nAlpha,
-                                     gridAlpha.data(), doublet_prior, ids.data());
+    int n;
+    while ((n = ccu_demux_best_row(row.data(), (int32_t)row.size(), row_int_id[r], row_bcs[r].c_str(),
+                                   (uint32_t)(cell_ptr[r + 1] - cell_ptr[r]),
+                                   (uint32_t)(read_ptr[cell_ptr[r + 1]] - read_ptr[cell_ptr[r]]), &res[r], nv, nAlpha,
+                                   gridAlpha.data(), doublet_prior, ids.data())) == -2)
+      row.resize(row.size() * 4);  // very long sample ids / barcodes
     if (n < 0) fatal("cannot format the row of droplet %s", row_bcs[r].c_str());
-    wbest.write(row, n);
+    wbest.write(row.data(), n);
   }
   wbest.close();
   notice("Finished writing output files");

@@ -519,15 +519,22 @@ class LineReader {
 // ---- gz / plain writer with printf (hts_utils.cpp:1018-1038) ----
 class Writer {
  public:
-  Writer(const std::string& fn, bool gz) : fp_(NULL), gz_(NULL) {
+  Writer(const std::string& fn, bool gz) : fp_(NULL), gz_(NULL), fn_(fn) {
     if (gz) gz_ = gzopen(fn.c_str(), "wb");
     else fp_ = fopen(fn.c_str(), "w");
     if (!fp_ && !gz_) fatal("Cannot open file %s for writing", fn.c_str());
   }
   ~Writer() { close(); }
+  // A short write or a failing close (disk full, quota) is fatal: a truncated output file must not exit 0.
   void close() {
-    if (fp_) fclose(fp_);
-    if (gz_) gzclose(gz_);
+    if (fp_ && fclose(fp_) != 0) {
+      fp_ = NULL;
+      fatal("Cannot finish writing %s", fn_.c_str());
+    }
+    if (gz_ && gzclose(gz_) != Z_OK) {
+      gz_ = NULL;
+      fatal("Cannot finish writing %s", fn_.c_str());
+    }
     fp_ = NULL;
     gz_ = NULL;
   }
@@ -537,17 +544,27 @@ class Writer {
     va_start(ap, fmt);
     int n = vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    if (n >= (int)sizeof(buf)) n = (int)sizeof(buf) - 1;
-    write(buf, n);
+    if (n < 0) fatal("Cannot format a line of %s", fn_.c_str());
+    if (n < (int)sizeof(buf)) {
+      write(buf, n);
+      return;
+    }
+    std::vector<char> big((size_t)n + 1);  // a line longer than the stack buffer: format it again, in full
+    va_start(ap, fmt);
+    vsnprintf(big.data(), big.size(), fmt, ap);
+    va_end(ap);
+    write(big.data(), n);
   }
   void write(const char* s, int n) {
-    if (fp_) fwrite(s, 1, n, fp_);
-    else gzwrite(gz_, s, n);
+    if (n <= 0) return;
+    const bool ok = fp_ ? fwrite(s, 1, (size_t)n, fp_) == (size_t)n : gzwrite(gz_, s, (unsigned)n) == n;
+    if (!ok) fatal("Cannot write to %s", fn_.c_str());
   }
 
  private:
   FILE* fp_;
   gzFile gz_;
+  std::string fn_;
 };
 
 // ---- text VCF reader: sequential cursor with the variant filter of cmdCramDemuxlet ----

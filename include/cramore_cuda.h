@@ -133,7 +133,9 @@ void* ccu_demux_results_dev(ccu_handle* h, int64_t* nbcs);
 /* Decision + row formatting (host code, cmd_cram_demuxlet.cpp:921-1013). */
 int ccu_demux_classify(const ccu_demux_result* r, int32_t nv, int32_t nalpha, const double* alpha,
                        double doublet_prior, ccu_demux_call* call);
-/* snprintf semantics; header line is ccu_demux_best_header(). */
+/* Returns the length of the row written to buf (newline included); -1: the result names an undefined sample or alpha
+ * index; -2: the row does not fit buflen (long sample ids / barcodes: retry with a larger buffer).  Header line:
+ * ccu_demux_best_header(). */
 int ccu_demux_best_row(char* buf, int32_t buflen, int32_t int_id, const char* barcode,
                        uint32_t nsnps_cell, int32_t nreads_cell, const ccu_demux_result* r, int32_t nv,
                        int32_t nalpha, const double* alpha, double doublet_prior,

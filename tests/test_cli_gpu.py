@@ -32,26 +32,13 @@ def _numeric_row_match(a, b, rtol_llk=0.011):
     return True
 
 
-def _compare_best(mine, ref, ids, min_exact=0.6):
-    """.best of this build against the reference's: rows equal, up to the alpha = 0.5 mirror orientation the reference
-    picks by rounding noise and a last printed digit."""
-    assert mine[0] == ref[0] and len(mine) == len(ref)
-    exact = 0
-    for a, b in zip(mine[1:], ref[1:]):
-        if a == b:
-            exact += 1
-            continue
-        fa, fb = a.split("\t"), b.split("\t")
-        ga, gb = fa[17].split(","), fb[17].split(",")
-        mirror = gb[2] == "0.50" and ga[:2] == gb[:2][::-1] and ids.index(gb[0]) > ids.index(gb[1])
-        if mirror:
-            for col in (5, 7, 17):  # BEST.GUESS, NEXT.GUESS, DBL.BEST.GUESS may carry the swapped pair
-                pa, pb = fa[col].split(","), fb[col].split(",")
-                if pa != pb and pa[:2] == pb[:2][::-1]:
-                    fa[col] = fb[col]
-            a = "\t".join(fa)
-        assert a == b or _numeric_row_match(a, b), (a, b)
-    assert exact >= min_exact * (len(ref) - 1)
+def _compare_best(mine, ref):
+    """.best of this build against the reference's: the same bytes.  The engine's likelihoods agree with the
+    reference's to ~1e-13; the rows are identical as text because the hypotheses they name are re-scored on the host in
+    the reference's own operation order (ccu_demux_refine), which also settles the orientation of alpha = 0.5 pairs."""
+    assert len(mine) == len(ref)
+    for a, b in zip(mine, ref):
+        assert a == b, (a, b)
 
 
 @pytest.mark.parametrize("name", refcase.DEMUX_CASES)
@@ -88,7 +75,7 @@ def test_cli_demuxlet_best_file(built, tmp_path, name):
     assert open(str(tmp_path / "out_cached.best")).read() == open(str(tmp_path / "out.best")).read()
     mine = open(str(tmp_path / "out.best")).read().splitlines(keepends=True)
     ref = fx["best_text"].splitlines(keepends=True)
-    _compare_best(mine, ref, d["sample_ids"])
+    _compare_best(mine, ref)
 
 
 @pytest.mark.parametrize("name", refcase.FMX_CASES)
@@ -260,7 +247,7 @@ def test_cli_demuxlet_equals_live_reference(built, tmp_path, seed):
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     _compare_best(open(str(tmp_path / "mine.best")).read().splitlines(keepends=True),
-                  open(str(tmp_path / "ref.best")).read().splitlines(keepends=True), d["sample_ids"], min_exact=0.5)
+                  open(str(tmp_path / "ref.best")).read().splitlines(keepends=True))
 
 
 @live
@@ -357,7 +344,7 @@ def test_patched_reference_command_runs_on_the_engine(built, tmp_path, name):
     r = subprocess.run(args, capture_output=True, text=True, cwd=str(tmp_path))
     assert r.returncode == 0, r.stderr[-3000:]
     _compare_best(open(str(tmp_path / "out.best")).read().splitlines(keepends=True),
-                  fx["best_text"].splitlines(keepends=True), d["sample_ids"])
+                  fx["best_text"].splitlines(keepends=True))
 
 
 @pytest.mark.skipif(not os.path.exists(REF_GPU_BIN), reason="oracle/_ref/ref_cramore_gpu not built (make -C oracle ref_gpu)")

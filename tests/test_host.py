@@ -924,3 +924,84 @@ def test_bgzf_stream_across_many_batches(built, tmp_path):
         r = subprocess.run([CRAMORE, "vcf-text", path], capture_output=True, env=dict(os.environ, CRAMORE_BGZF_THREADS=threads))
         assert r.returncode == 0, r.stderr[-1000:]
         assert r.stdout == text
+
+
+REF_GPU_BIN_DUMP = os.path.join(ROOT, "oracle", "_ref", "ref_cramore_gpu")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GPU_BIN_DUMP), reason="oracle/_ref/ref_cramore_gpu not built (make -C oracle ref_gpu)")
+@pytest.mark.parametrize("case", ["plain", "filters", "gt_r2"])
+def test_own_loader_equals_the_references_own_maps(built, tmp_path, case):
+    """CSR bit-exactness against the REFERENCE's data structures, not a re-derivation: the reference's own
+    load_from_plp / add_cell / add_snp / add_umi (sc_drop_seq.cpp:27-91, 103-384, compiled unmodified into
+    oracle/_ref/ref_cramore_gpu) fill sc_dropseq_lib_t, the patch of INTEGRATION.md section 1 flattens those maps, and
+    CCU_PATCH_DUMP_INPUTS writes the result before any GPU call.  `cramore demuxlet --gpu-dump-inputs` (this repo's
+    loader, host_io.h) must produce the same bytes: droplet order, SNP order, read order inside an entry, alleles,
+    capped qualities, INT_IDs -- and the same genotype doubles once its float posteriors are mixed."""
+    from cramore_b200.synth import make_dataset, write_plp, write_vcf
+    from oracle import pyoracle
+    d = make_dataset("C1", nbcs=90, nsnps=140, rbar=170, nv=5, seed=77, with_barcodes=True)  # many multi-read entries
+    pre = str(tmp_path / "in")
+    write_plp(d, pre)
+    write_vcf(d, pre + ".vcf", with_r2=True)
+    common = ["--plp", "in", "--vcf", "in.vcf", "--out", "o"]
+    if case == "filters":
+        (tmp_path / "grp.txt").write_text("\n".join(b for i, b in enumerate(d["barcodes"]) if i % 4 != 2) + "\n")
+        common += ["--group-list", "grp.txt", "--min-snp", "95", "--min-umi", "150", "--cap-BQ", "17", "--min-BQ", "14",
+                   "--geno-error-offset", "0.05", "--geno-error-coeff", "0.5"]
+    if case == "gt_r2":
+        common += ["--field", "GT", "--geno-error-offset", "0.02", "--geno-error-coeff", "0.3", "--min-mac", "2"]
+    r = subprocess.run([REF_GPU_BIN_DUMP, "demuxlet"] + common, capture_output=True, text=True, cwd=str(tmp_path),
+                       env=dict(os.environ, CCU_PATCH_DUMP_INPUTS="ref"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([CRAMORE, "demuxlet"] + common + ["--gpu-dump-inputs", "mine"], capture_output=True, text=True,
+                       cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    for name in ("cell_ptr.i64", "snp_idx.i32", "read_ptr.i64", "al.u8", "bq.u8", "has_gp.u8", "barcodes.txt",
+                 "row_int_id.i32"):
+        a, b = (tmp_path / ("ref." + name)).read_bytes(), (tmp_path / ("mine." + name)).read_bytes()
+        assert len(a) > 0 and a == b, name
+    # genotypes: the reference holds mixed doubles (sc_drop_seq.cpp:287-315), this build float posteriors + per-SNP
+    # error that the engine mixes on the device with the same operations (tests/test_demux_gpu.py pins the kernel to
+    # this very oracle function)
+    has = np.fromfile(str(tmp_path / "mine.has_gp.u8"), dtype="u1")
+    gp = np.fromfile(str(tmp_path / "mine.gp.f32"), dtype="<f4").reshape(len(has), -1, 3)
+    err = np.fromfile(str(tmp_path / "mine.snp_err.f64"), dtype="<f8")
+    mixed = pyoracle.mix_genotypes(gp, err, has)
+    ref = np.fromfile(str(tmp_path / "ref.gps.f64"), dtype="<f8").reshape(mixed.shape)
+    assert has.sum() > 20 and np.array_equal(mixed[has == 1], ref[has == 1])
+
+
+def test_cli_rejects_unusable_alpha_grids_before_reading_anything(built, tmp_path):
+    """The engine refuses grids the reference is undefined for (no doublet fraction, first value not 0) and grids
+    beyond CCU_MAX_ALPHA; the command line says so, naming the option, before it opens any input file."""
+    base = [CRAMORE, "demuxlet", "--plp", str(tmp_path / "absent"), "--vcf", str(tmp_path / "absent.vcf"), "--out",
+            str(tmp_path / "o")]
+    for extra, word in ((["--alpha", "0.1", "--alpha", "0.5"], "first value must be 0"),
+                        (["--alpha", "0"], "at least one doublet fraction"),
+                        (sum((["--alpha", repr(i / 64.0)] for i in range(40)), []), "at most 32")):
+        r = subprocess.run(base + extra, capture_output=True, text=True)
+        assert r.returncode != 0 and "--alpha" in r.stderr and word in r.stderr, r.stderr[-500:]
+        assert "Cannot open" not in r.stderr  # refused before any attempt to open the inputs
+
+
+def test_best_row_reports_a_short_buffer(built):
+    import ctypes as C
+    from cramore_b200 import RESULT_DTYPE, load_library
+    lib = load_library()
+    res = np.zeros(1, RESULT_DTYPE)
+    res["sNext"] = 1
+    res["dBest2"] = 1
+    res["dBestA"] = 1
+    a = np.asarray([0.0, 0.5])
+    ids = (C.c_char_p * 2)(b"S" * 300, b"T" * 300)
+    small = C.create_string_buffer(256)
+    n = lib.ccu_demux_best_row(small, C.c_int32(256), C.c_int32(0), b"BC", C.c_uint32(1), C.c_int32(1),
+                               C.c_void_p(res.ctypes.data), C.c_int32(2), C.c_int32(2), C.c_void_p(a.ctypes.data),
+                               C.c_double(0.5), ids)
+    assert n == -2
+    big = C.create_string_buffer(8192)
+    n = lib.ccu_demux_best_row(big, C.c_int32(8192), C.c_int32(0), b"BC", C.c_uint32(1), C.c_int32(1),
+                               C.c_void_p(res.ctypes.data), C.c_int32(2), C.c_int32(2), C.c_void_p(a.ctypes.data),
+                               C.c_double(0.5), ids)
+    assert n > 2000 and big.raw[n - 1:n] == b"\n"

@@ -94,3 +94,53 @@ def test_refine_rejects_bad_arguments(built):
     from cramore_b200.engine import EngineError
     with pytest.raises(EngineError):  # SNP id outside the genotype matrix
         refine(res, [0, 1], [7], [0, 1], [0], [20], 4, alphas, gp, 0.1)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_refine_on_grids_with_complements_against_the_live_reference(built, tmp_path, seed):
+    """Grids holding alpha together with 1 - alpha: (j,k,alpha) and (k,j,1-alpha) are one model, and which of the two
+    the reference prints is rounding in its own summation.  The refinement re-scores both and reproduces the
+    reference's file (oracle/_ref/ref_cramore run on the same inputs)."""
+    import os
+    from cramore_b200.synth import make_dataset, write_plp, write_vcf
+    from tests.test_reference_live import REF as REF_BIN, _run_ref
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/ref_cramore not built")
+    rng = np.random.default_rng(700 + seed)
+    nv = int(rng.integers(2, 9))
+    d = make_dataset("C1", nbcs=int(rng.integers(10, 40)), nsnps=int(rng.integers(60, 300)), rbar=int(rng.integers(20, 120)),
+                     nv=nv, seed=9100 + seed, with_barcodes=True)
+    alphas = [[0.0, 0.3, 0.7], [0.0, 0.25, 0.5, 0.75], [0.0, 0.1, 0.4, 0.6, 0.9], [0.0, 0.2, 0.5, 0.8],
+              [0.0, 0.45, 0.55], [0.0, 0.05, 0.35, 0.5, 0.65]][seed]
+    pre = str(tmp_path / "in")
+    write_plp(d, pre)
+    write_vcf(d, pre + ".vcf")
+    args = ["demuxlet", "--plp", "in", "--vcf", "in.vcf", "--field", "GP", "--out", "out"]
+    for a in alphas:
+        args += ["--alpha", repr(a)]
+    _run_ref(args, str(tmp_path))
+    ref_lines = open(str(tmp_path / "out.best")).read().splitlines(keepends=True)
+    ac = np.asarray(d["geno"], np.int64).sum(axis=1)
+    has_gp = ((ac >= 1) & (2 * nv - ac >= 1)).astype(np.uint8)  # --min-mac 1 (cmd_cram_demuxlet.cpp:27)
+    al = np.asarray(alphas, np.float64)
+    snp_err = np.full(d["nsnps"], 0.1)
+    gps = pyoracle.mix_genotypes(d["gp"], snp_err, has_gp)
+    exact, _, _ = pyoracle.demux_score(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], gps, al, 0.5,
+                                       has_gp=has_gp)
+    noisy = engine_like(exact, al, rng)
+    # the engine may also report the two orientations the other way round
+    for c in range(len(noisy)):
+        if rng.random() < 0.5:
+            r = noisy[c].copy()
+            n1, n2 = r["dBestA"], r["dNextA"]
+            if al[n2] == 1.0 - al[n1] and r["dBest1"] == r["dNext2"] and r["dBest2"] == r["dNext1"]:
+                for a, b in (("dBest1", "dNext1"), ("dBest2", "dNext2"), ("dBestA", "dNextA"), ("dblBestLLK", "dblNextLLK")):
+                    noisy[a][c], noisy[b][c] = r[b], r[a]
+    fixed = refine(noisy, d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], nv, al, d["gp"], snp_err, has_gp)
+    fixed["sumLLK"], fixed["sngLLK"] = exact["sumLLK"], exact["sngLLK"]
+    order = sorted(range(d["nbcs"]), key=lambda i: d["barcodes"][i])
+    cp, rp = d["cell_ptr"], d["read_ptr"]
+    for rank, c in enumerate(order):
+        mine = best_row(rank, d["barcodes"][c], int(cp[c + 1] - cp[c]), int(rp[cp[c + 1]] - rp[cp[c]]), fixed[c], nv, al,
+                        0.5, d["sample_ids"])
+        assert mine == ref_lines[1 + rank], (seed, c)
