@@ -605,26 +605,31 @@ def measure_fmx(ctx, iters=10):
         torch.cuda.synchronize()
         return ctx.max_over_ranks(a.elapsed_time(b))
 
-    forms = ["push", "posteriors"] if world > 1 else ["single"]
+    # "push": the fused loop -- M-step kernel forms the posteriors and stores them into every rank's array over NVLink,
+    # decision kernel does the same with the assignments, epoch flags inside the kernels order the ranks (at N = 1 the
+    # same two launches + decision per iteration without peers); "posteriors": the NCCL form (all-reduce of the
+    # posterior array, all-gather of the assignments) kept beside it
+    forms = ["push", "posteriors"] if world > 1 else ["push"]
     sampler = ClockSampler(local)
     res = {}
     launches = 0
     sampler.begin()
     for form in forms:
-        ex = "posteriors" if form == "single" else form
-        run(ex)  # warm-up: NCCL channels, peer mappings, allocations
-        full, ms, nl = run(ex)
+        run(form)  # warm-up: NCCL channels, peer mappings, allocations
+        full, ms, nl = run(form)
         launches += 2 * nl
         res[form] = {"ms_per_iter": ms / iters, "ms_total": ms, "launches_per_run": nl, "_full": full}
-    # per-phase device times of this rank's shard (one extra pass, a synchronise around each phase; max over ranks)
-    phases = {"estep_ms": phase(lambda: eng.estep_post_dev()), "mstep_ms": phase(lambda: eng.mstep_dev())}
+    # per-phase device times of this rank's shard (one extra pass, a synchronise around each phase; max over ranks).
+    # The fused calls run without their in-kernel waits here: every rank is inside the same phase anyway.
+    # (M-step first: it leaves the posteriors of every SNP, on every rank, that the E-step call insists on)
+    phases = {"mstep_ms": phase(lambda: eng.mstep_fused_dev(False, False, False))}
+    ctx.barrier()
+    phases["estep_ms"] = phase(lambda: eng.estep_fused_dev(False))
+    ctx.barrier()
+    phases["mstep_with_stats_records_ms"] = phase(lambda: eng.mstep_fused_dev(False, True, False))
     if world > 1:
-        phases["posteriors_push_ms"] = phase(lambda: eng.posteriors_push_dev(False))
-        phases["assign_push_ms"] = phase(lambda: eng.assign_push_dev())
-        phases["rank_barrier_ms"] = phase(lambda: eng.rank_barrier_dev())
+        phases["rank_barrier_kernel_ms"] = phase(lambda: eng.rank_barrier_dev())
         phases["allreduce_posteriors_ms"] = phase(lambda: dist.all_reduce(post))
-    else:
-        phases["posteriors_ms"] = phase(lambda: eng.posteriors_dev(False))
     sampler.end()
     clocks = sampler.summary()
 
@@ -649,19 +654,27 @@ def measure_fmx(ctx, iters=10):
         except Exception:
             hbm_peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
         nobs = int(np.unique(d["snp_idx"]).size)
-        # algorithmic bytes of SURVEY 8(d): E-step 84 B pileup + 24*K B gathered cluster posteriors per entry;
-        # M-step 84 B pileup per entry in, 84 B per (cluster, observed SNP) out.  Per-rank shard = 1/N of each.
-        e_bytes = (84 + 24 * K) * nnz / world
-        m_bytes = (84 * nnz + 84 * K * nobs) / world
-        # FP64 instructions of the E-step as built (DESIGN.md 4), per entry
-        e_flops = 2.0 * fmx_estep_fp64_instr(K) * nnz / world
+        # Algorithmic bytes per launch, per-rank shard = 1/N of each.  E-step: a single-read entry is
+        # 20 B ((gl[0]/2, b) + SNP id) + 8*K B of gathered mean genotypes, an entry with >= 2 reads 84 B + 24*K B
+        # (SURVEY 8(d)'s figure).  M-step: 88 B pileup + 4 B droplet id per entry in, (24 + 8) B of posteriors and mean
+        # genotypes per (cluster, SNP of the slab) out (the 96-byte statistics records only on the last iteration).
+        al_ne2 = (np.asarray(d["al"]) != 2).astype(np.int64)
+        csum = np.concatenate([[0], np.cumsum(al_ne2)])
+        neff = csum[np.asarray(d["read_ptr"][1:])] - csum[np.asarray(d["read_ptr"][:-1])]
+        n_gen = int((neff > 1).sum())
+        n_aff = nnz - n_gen
+        e_bytes = ((20 + 8 * K) * n_aff + (84 + 24 * K) * n_gen) / world
+        m_bytes = (92 * nnz + 32 * K * d["nsnps"]) / world
+        # FP64 instructions of the E-step as built, per entry
+        e_flops = 2.0 * (fmx_estep_fp64_instr(K, False) * n_aff + fmx_estep_fp64_instr(K, True) * n_gen) / world
         fp64_peak = ctx.fp64_peak
         roof = [{"kernel": "fmx E-step (F2)", "bound": "hbm (SURVEY 8d)", "achieved": e_bytes / (phases["estep_ms"] * 1e-3) / 1e9,
                  "peak": hbm_peak, "unit": "GB/s", "frac": e_bytes / (phases["estep_ms"] * 1e-3) / 1e9 / hbm_peak,
                  "algorithmic_bytes_per_launch": int(e_bytes), "ms": phases["estep_ms"], "peak_source": peak_src,
                  "fp64": {"achieved": e_flops / (phases["estep_ms"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                           "frac": e_flops / (phases["estep_ms"] * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
-                          "note": "the posterior array lives in L2, so the binding resources are the FP64 pipe and "
+                          "note": "needed FP64 flops (2 per pair and SNP on single-read entries) / time; the mean-genotype "
+                                  "array (K*8 B per SNP) lives in L2, so the binding resources are the FP64 pipe and "
                                   "shared-memory wavefronts (ncu rows under profiles/), not HBM"}},
                 {"kernel": "fmx M-step (F3)", "bound": "hbm", "achieved": m_bytes / (phases["mstep_ms"] * 1e-3) / 1e9,
                  "peak": hbm_peak, "unit": "GB/s", "frac": m_bytes / (phases["mstep_ms"] * 1e-3) / 1e9 / hbm_peak,
@@ -673,6 +686,7 @@ def measure_fmx(ctx, iters=10):
                "scaling": "strong", "n_gpus": world, "iters": iters,
                "exchange": {f: {k: v for k, v in res[f].items() if not k.startswith("_")} for f in forms},
                "ms_per_iter": res[forms[0]]["ms_per_iter"], "phase_ms": phases, "clocks": clocks,
+               "entries_single_read": n_aff, "entries_general": n_gen,
                "matches_single_gpu": ok, "single_gpu_ms_per_iter_wall": single_ms,
                "speedup_vs_single_gpu_wall": (single_ms / res[forms[0]]["ms_per_iter"]) if single_ms else None,
                "posterior_exchange_bytes": int(post.numel() * 8), "stats_allreduce_bytes_once": int(stats.numel() * 8),
@@ -682,9 +696,11 @@ def measure_fmx(ctx, iters=10):
     return out
 
 
-def fmx_estep_fp64_instr(K):
-    """FP64 instructions per (droplet, SNP) entry of the E-step kernel as built for K <= 16."""
-    return 4 * (K * (K + 1) // 2) + 9 * K
+def fmx_estep_fp64_instr(K, general):
+    """FP64 instructions per (droplet, SNP) entry the algorithm needs: an entry with >= 2 reads takes
+    t = GL^T p per cluster (9) and 4 per pair; a single-read entry u = a/2 + b m per cluster (1) and 2 per pair."""
+    npairs = K * (K + 1) // 2
+    return (4 * npairs + 9 * K) if general else (2 * npairs + K)
 
 
 def main():

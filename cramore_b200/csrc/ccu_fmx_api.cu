@@ -23,14 +23,20 @@ int64_t ccu_fmx_pairs_records(const FmxPairs* ps);
 
 struct FmxState {
   bool configured = false, uploaded = false, have_stats = false, have_estep = false, have_post = false;
+  // the posterior / mean-genotype arrays: post_full = they hold every SNP (not only this rank's slab), computed with
+  // the genotype-error flag post_apply; cgm_stale = the mean genotypes have to be re-derived from the posteriors
+  bool post_full = false, cgm_stale = false;
+  int post_apply = -1;
+  long long timeout_cycles = 0;
   int32_t K = 0;
   double doublet_prior = 0.5, geno_error = 0.0;
   int64_t nbcs = 0, nsnps = 0, nnz = 0, nreads = 0, max_segment = 0;
   int64_t cell_begin = 0, cell_end = 0, snp_begin = 0, snp_end = 0;
   DevBuf cell_ptr, snp_idx, read_ptr, al, bq, af;
   DevBuf gl, cnt, logdenom, csc_ptr, csc_cell, csc_gl, csc_cnt;
-  DevBuf assign, stats, cgp, llk, results, scan, scratch, flags;
-  cudaEvent_t ev[2] = {nullptr, nullptr};
+  DevBuf eclass, egen, eab, esnp, gcnt;
+  DevBuf assign, stats, cgp, cgm, llk, results, scan, scratch, flags, counter;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   ccu_fmx_timings tm = {};
   FmxPairs* pairs = nullptr;
   // peer-memory exchange: every rank's posterior / assignment array (CUDA IPC mappings; [peer_rank] is our own)
@@ -41,6 +47,7 @@ struct FmxState {
     for (int r = 0; r < peers.n; ++r)
       if (r != peer_rank && peers_are_ipc) {
         if (peers.post[r]) cudaIpcCloseMemHandle(peers.post[r]);
+        if (peers.postm[r]) cudaIpcCloseMemHandle(peers.postm[r]);
         if (peers.assign[r]) cudaIpcCloseMemHandle(peers.assign[r]);
         if (peers.flags[r]) cudaIpcCloseMemHandle(peers.flags[r]);
       }
@@ -52,7 +59,8 @@ struct FmxState {
     close_peers();
     ccu_fmx_pairs_release(pairs);
     DevBuf* all[] = {&cell_ptr, &snp_idx, &read_ptr, &al, &bq, &af, &gl, &cnt, &logdenom, &csc_ptr, &csc_cell,
-                     &csc_gl, &csc_cnt, &assign, &stats, &cgp, &llk, &results, &scan, &scratch, &flags};
+                     &csc_gl, &csc_cnt, &eclass, &egen, &eab, &esnp, &gcnt, &assign, &stats, &cgp, &cgm, &llk, &results,
+                     &scan, &scratch, &flags, &counter};
     for (DevBuf* b : all) b->release();
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
@@ -99,6 +107,12 @@ ccu::FmxDev fmx_view(const ccu_handle* h) {
   d.assign = f->assign.as<int32_t>();
   d.stats = f->stats.as<double>();
   d.cgp = f->cgp.as<double>();
+  d.cgm = f->cgm.as<double>();
+  d.eclass = f->eclass.as<uint8_t>();
+  d.egen = f->egen.as<int32_t>();
+  d.eab = f->eab.as<double2>();
+  d.esnp = f->esnp.as<int32_t>();
+  d.gcnt = f->gcnt.as<int32_t>();
   d.llk = f->llk.as<double>();
   d.results = f->results.as<ccu_fmx_result>();
   d.scan = f->scan.as<ccu::FmxScan>();
@@ -128,6 +142,27 @@ int need(ccu_handle* h, bool uploaded, const char* who) {
   return 0;
 }
 
+// How the kernels of the loop take part in the cross-rank ordering (FmxSync): in-kernel when asked for and peers are
+// mapped, otherwise not at all (single GPU, or the caller orders the ranks itself).
+ccu::FmxSync make_sync(const ccu_handle* h, bool in_kernel) {
+  const FmxState* f = h->fmx;
+  ccu::FmxSync s;
+  memset(&s, 0, sizeof(s));
+  const bool on = in_kernel && f->peers.n > 1;
+  s.wait = on ? 1 : 0;
+  s.arrive = on ? 1 : 0;
+  s.rank = f->peer_rank < 0 ? 0 : f->peer_rank;
+  s.timeout_cycles = f->timeout_cycles;
+  s.counter = f->counter.as<unsigned int>();
+  return s;
+}
+
+ccu::FmxPeers no_peers() {
+  ccu::FmxPeers p;
+  memset(&p, 0, sizeof(p));
+  return p;
+}
+
 int reserve_shard_buffers(ccu_handle* h) {
   FmxState* f = h->fmx;
   const int64_t ncell = f->cell_end - f->cell_begin;
@@ -149,15 +184,23 @@ int ccu_fmx_configure(ccu_handle* h, int32_t nclust, double doublet_prior, doubl
   CCU_CUDA(h, cudaSetDevice(h->device));
   if (!h->fmx) {
     h->fmx = new FmxState();
-    cudaEventCreate(&h->fmx->ev[0]);
-    cudaEventCreate(&h->fmx->ev[1]);
+    for (auto& e : h->fmx->ev) cudaEventCreate(&e);
+    // how long a kernel of the multi-GPU loop waits for its peers before it raises the error flag instead of
+    // hanging the GPU: CCU_FMX_BARRIER_TIMEOUT_S seconds (default 30 -- a late peer_open, a lazy module load or
+    // host-thread contention on a healthy run must not trip it)
+    int khz = 1900000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+    double secs = 30.0;
+    if (const char* v = getenv("CCU_FMX_BARRIER_TIMEOUT_S")) secs = atof(v) > 0 ? atof(v) : secs;
+    h->fmx->timeout_cycles = (long long)(secs * 1e3 * (double)khz);
   }
   FmxState* f = h->fmx;
   f->K = nclust;
   f->doublet_prior = doublet_prior;
   f->geno_error = geno_error;
   f->configured = true;
-  f->uploaded = f->have_stats = f->have_estep = f->have_post = false;
+  f->uploaded = f->have_stats = f->have_estep = f->have_post = f->post_full = false;
+  f->post_apply = -1;
   return 0;
 }
 
@@ -193,7 +236,8 @@ int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* ce
   f->cell_end = nbcs;
   f->snp_begin = 0;
   f->snp_end = nsnps;
-  f->uploaded = f->have_stats = f->have_estep = f->have_post = false;
+  f->uploaded = f->have_stats = f->have_estep = f->have_post = f->post_full = false;
+  f->post_apply = -1;
   CCU_CUDA(h, f->cell_ptr.reserve((nbcs + 1) * sizeof(int64_t)));
   CCU_CUDA(h, f->snp_idx.reserve(nnz * sizeof(int32_t) + 16));
   CCU_CUDA(h, f->read_ptr.reserve((nnz + 1) * sizeof(int64_t)));
@@ -210,6 +254,14 @@ int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* ce
   CCU_CUDA(h, f->assign.reserve(nbcs * sizeof(int32_t) + 16));
   CCU_CUDA(h, f->stats.reserve((size_t)f->K * nsnps * ccu::kStatStride * sizeof(double) + 16));
   CCU_CUDA(h, f->cgp.reserve((size_t)f->K * nsnps * 3 * sizeof(double) + 16));
+  CCU_CUDA(h, f->cgm.reserve((size_t)f->K * nsnps * sizeof(double) + 16));
+  CCU_CUDA(h, f->eclass.reserve((size_t)nnz + 16));
+  CCU_CUDA(h, f->egen.reserve((size_t)nnz * sizeof(int32_t) + 16));
+  CCU_CUDA(h, f->eab.reserve((size_t)nnz * sizeof(double2) + 16));
+  CCU_CUDA(h, f->esnp.reserve((size_t)nnz * sizeof(int32_t) + 16));
+  CCU_CUDA(h, f->gcnt.reserve((size_t)nbcs * sizeof(int32_t) + 16));
+  CCU_CUDA(h, f->counter.reserve(16));
+  CCU_CUDA(h, cudaMemsetAsync(f->counter.p, 0, 16, st));
   if (int rc = reserve_shard_buffers(h)) return rc;
   CCU_CUDA(h, cudaMemcpyAsync(f->cell_ptr.p, cell_ptr, (nbcs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   if (nnz > 0) {
@@ -228,8 +280,9 @@ int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* ce
   {  // F1: alpha = 0.5, cmd_cram_freemuxlet.cpp:133
     Timer t(h, &f->tm.ms_pileup);
     CCU_CUDA(h, ccu::launch_fmx_pileup(d, 0.5, st));
+    CCU_CUDA(h, ccu::launch_fmx_compact(d, st));  // the E-step's view: general entries listed, single-read ones packed
     t.stop_sync();
-    f->tm.launches += nnz > 0 ? 1 : 0;
+    f->tm.launches += nnz > 0 ? 2 : 0;
   }
   {  // SNP-major index: stable radix sort of (snp, entry id); entries of one SNP stay in ascending droplet order
     Timer t(h, &f->tm.ms_csc);
@@ -321,15 +374,20 @@ int ccu_fmx_get_pileups(ccu_handle* h, ccu_pileup* out) {
   return 0;
 }
 
+// M-step of this shard's SNP slab.  The fused kernel also leaves the posteriors / mean genotypes of the slab (without
+// the genotype-error mix; ccu_fmx_estep_dev recomputes them when it needs the other flavour or more than the slab).
 int ccu_fmx_mstep_dev(ccu_handle* h) {
   if (int rc = need(h, true, "ccu_fmx_mstep")) return rc;
   CCU_CUDA(h, cudaSetDevice(h->device));
   FmxState* f = h->fmx;
-  cudaEventRecord(f->ev[0], h->stream);
-  CCU_CUDA(h, ccu::launch_fmx_mstep(fmx_view(h), h->stream));
-  cudaEventRecord(f->ev[1], h->stream);
+  cudaEventRecord(f->ev[2], h->stream);
+  CCU_CUDA(h, ccu::launch_fmx_mstep(fmx_view(h), 0, 1, no_peers(), make_sync(h, false), h->stream));
+  cudaEventRecord(f->ev[3], h->stream);
   f->tm.launches += 1;
   f->have_stats = true;
+  f->post_full = (f->snp_begin == 0 && f->snp_end == f->nsnps);
+  f->post_apply = 0;
+  f->cgm_stale = false;
   return 0;
 }
 
@@ -343,8 +401,8 @@ int ccu_fmx_mstep(ccu_handle* h, const int32_t* assign) {
   if (f->nbcs > 0)
     CCU_CUDA(h, cudaMemcpyAsync(f->assign.p, assign, f->nbcs * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
   if (int rc = ccu_fmx_mstep_dev(h)) return rc;
-  CCU_CUDA(h, cudaEventSynchronize(f->ev[1]));
-  cudaEventElapsedTime(&f->tm.ms_mstep, f->ev[0], f->ev[1]);
+  CCU_CUDA(h, cudaEventSynchronize(f->ev[3]));
+  cudaEventElapsedTime(&f->tm.ms_mstep, f->ev[2], f->ev[3]);
   return 0;
 }
 
@@ -354,12 +412,19 @@ int ccu_fmx_estep_dev(ccu_handle* h, int32_t apply_geno_error) {
   if (!f->have_stats) return ccu_fail(h, "ccu_fmx_estep: no cluster statistics yet (run ccu_fmx_mstep first)");
   CCU_CUDA(h, cudaSetDevice(h->device));
   const ccu::FmxDev d = fmx_view(h);
-  CCU_CUDA(h, ccu::launch_fmx_cgp(d, apply_geno_error, false, h->stream));
+  const int apply = apply_geno_error ? 1 : 0;
+  if (!f->post_full || f->post_apply != apply || f->cgm_stale) {  // posteriors of every SNP from the statistics array
+    CCU_CUDA(h, ccu::launch_fmx_cgp(d, apply, false, h->stream));
+    f->tm.launches += 1;
+    f->post_full = true;
+    f->post_apply = apply;
+    f->cgm_stale = false;
+  }
   cudaEventRecord(f->ev[0], h->stream);
-  CCU_CUDA(h, ccu::launch_fmx_estep(d, h->stream));
+  CCU_CUDA(h, ccu::launch_fmx_estep(d, no_peers(), make_sync(h, false), h->stream));
   cudaEventRecord(f->ev[1], h->stream);
-  f->tm.launches += 3;  // posteriors, E-step, decision
-  f->have_estep = true;
+  f->tm.launches += 2;  // E-step, decision
+  f->have_estep = f->have_post = true;
   return 0;
 }
 
@@ -371,6 +436,9 @@ int ccu_fmx_posteriors_dev(ccu_handle* h, int32_t apply_geno_error) {
   CCU_CUDA(h, ccu::launch_fmx_cgp(fmx_view(h), apply_geno_error, true, h->stream));
   f->tm.launches += 1;
   f->have_post = true;
+  f->post_full = false;  // the caller completes the array with a sum-all-reduce
+  f->post_apply = apply_geno_error ? 1 : 0;
+  f->cgm_stale = true;
   return 0;
 }
 
@@ -379,8 +447,46 @@ int ccu_fmx_estep_post_dev(ccu_handle* h) {
   FmxState* f = h->fmx;
   if (!f->have_post) return ccu_fail(h, "ccu_fmx_estep_post: no posteriors yet (run ccu_fmx_posteriors_dev first)");
   CCU_CUDA(h, cudaSetDevice(h->device));
+  const ccu::FmxDev d = fmx_view(h);
+  if (f->cgm_stale) {  // the posterior array was completed by a collective: derive the mean genotypes from it
+    CCU_CUDA(h, ccu::launch_fmx_cgm(d, h->stream));
+    f->tm.launches += 1;
+    f->cgm_stale = false;
+  }
   cudaEventRecord(f->ev[0], h->stream);
-  CCU_CUDA(h, ccu::launch_fmx_estep(fmx_view(h), h->stream));
+  CCU_CUDA(h, ccu::launch_fmx_estep(d, no_peers(), make_sync(h, false), h->stream));
+  cudaEventRecord(f->ev[1], h->stream);
+  f->tm.launches += 2;  // E-step, decision
+  f->have_estep = true;
+  return 0;
+}
+
+// ---- the fused loop: two launches + the decision per iteration, exchange inside the kernels ----
+int ccu_fmx_mstep_fused_dev(ccu_handle* h, int32_t apply_geno_error_next, int32_t want_stats, int32_t in_kernel_sync) {
+  if (int rc = need(h, true, "ccu_fmx_mstep_fused")) return rc;
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  FmxState* f = h->fmx;
+  cudaEventRecord(f->ev[2], h->stream);
+  CCU_CUDA(h, ccu::launch_fmx_mstep(fmx_view(h), apply_geno_error_next ? 1 : 0, want_stats ? 1 : 0, f->peers,
+                                    make_sync(h, in_kernel_sync != 0), h->stream));
+  cudaEventRecord(f->ev[3], h->stream);
+  f->tm.launches += 1;
+  if (want_stats) f->have_stats = true;
+  f->have_post = true;
+  f->post_full = f->peers.n > 1 || (f->snp_begin == 0 && f->snp_end == f->nsnps);  // peers fill the other slabs
+  f->post_apply = apply_geno_error_next ? 1 : 0;
+  f->cgm_stale = false;
+  return 0;
+}
+
+int ccu_fmx_estep_fused_dev(ccu_handle* h, int32_t in_kernel_sync) {
+  if (int rc = need(h, true, "ccu_fmx_estep_fused")) return rc;
+  FmxState* f = h->fmx;
+  if (!f->have_post || !f->post_full)
+    return ccu_fail(h, "ccu_fmx_estep_fused: the posteriors of every SNP are needed (ccu_fmx_mstep_fused_dev on every rank first)");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  cudaEventRecord(f->ev[0], h->stream);
+  CCU_CUDA(h, ccu::launch_fmx_estep(fmx_view(h), f->peers, make_sync(h, in_kernel_sync != 0), h->stream));
   cudaEventRecord(f->ev[1], h->stream);
   f->tm.launches += 2;  // E-step, decision
   f->have_estep = true;
@@ -392,17 +498,18 @@ int ccu_fmx_peer_handles(ccu_handle* h, void* out) {
   if (int rc = need(h, true, "ccu_fmx_peer_handles")) return rc;
   FmxState* f = h->fmx;
   if (!out) return ccu_fail(h, "ccu_fmx_peer_handles: NULL output");
-  if (!f->cgp.p || !f->assign.p) return ccu_fail(h, "ccu_fmx_peer_handles: call ccu_fmx_set_shard first");
+  if (!f->cgp.p || !f->cgm.p || !f->assign.p) return ccu_fail(h, "ccu_fmx_peer_handles: call ccu_fmx_set_shard first");
   static_assert(sizeof(cudaIpcMemHandle_t) == CCU_IPC_HANDLE_BYTES, "CUDA IPC handle size");
   CCU_CUDA(h, cudaSetDevice(h->device));
   // the flag array of the peer-memory barrier: zeroed here, i.e. before any peer can learn its address
   CCU_CUDA(h, f->flags.reserve((ccu::kMaxPeers + 2) * sizeof(uint32_t)));
   CCU_CUDA(h, cudaMemsetAsync(f->flags.p, 0, (ccu::kMaxPeers + 2) * sizeof(uint32_t), h->stream));
   CCU_CUDA(h, cudaStreamSynchronize(h->stream));
-  cudaIpcMemHandle_t hd[3];
+  cudaIpcMemHandle_t hd[4];
   CCU_CUDA(h, cudaIpcGetMemHandle(&hd[0], f->cgp.p));
-  CCU_CUDA(h, cudaIpcGetMemHandle(&hd[1], f->assign.p));
-  CCU_CUDA(h, cudaIpcGetMemHandle(&hd[2], f->flags.p));
+  CCU_CUDA(h, cudaIpcGetMemHandle(&hd[1], f->cgm.p));
+  CCU_CUDA(h, cudaIpcGetMemHandle(&hd[2], f->assign.p));
+  CCU_CUDA(h, cudaIpcGetMemHandle(&hd[3], f->flags.p));
   memcpy(out, hd, sizeof(hd));
   return 0;
 }
@@ -421,17 +528,18 @@ int ccu_fmx_peer_open(ccu_handle* h, int32_t nranks, int32_t rank, const void* h
   for (int r = 0; r < nranks; ++r) {
     if (r == rank) {
       f->peers.post[r] = f->cgp.as<double>();
+      f->peers.postm[r] = f->cgm.as<double>();
       f->peers.assign[r] = f->assign.as<int32_t>();
       f->peers.flags[r] = f->flags.as<uint32_t>();
       continue;
     }
-    void *pp = nullptr, *pa = nullptr, *pf = nullptr;
-    cudaError_t e = cudaIpcOpenMemHandle(&pp, hd[3 * r], cudaIpcMemLazyEnablePeerAccess);
-    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pa, hd[3 * r + 1], cudaIpcMemLazyEnablePeerAccess);
-    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pf, hd[3 * r + 2], cudaIpcMemLazyEnablePeerAccess);
-    f->peers.post[r] = static_cast<double*>(pp);
-    f->peers.assign[r] = static_cast<int32_t*>(pa);
-    f->peers.flags[r] = static_cast<uint32_t*>(pf);
+    void* pp[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k) e = cudaIpcOpenMemHandle(&pp[k], hd[4 * r + k], cudaIpcMemLazyEnablePeerAccess);
+    f->peers.post[r] = static_cast<double*>(pp[0]);
+    f->peers.postm[r] = static_cast<double*>(pp[1]);
+    f->peers.assign[r] = static_cast<int32_t*>(pp[2]);
+    f->peers.flags[r] = static_cast<uint32_t*>(pp[3]);
     if (e != cudaSuccess) {
       f->peers.n = r + 1;
       f->close_peers();
@@ -449,24 +557,15 @@ int ccu_fmx_peer_close(ccu_handle* h) {
   return 0;
 }
 
-int ccu_fmx_posteriors_push_dev(ccu_handle* h, int32_t apply_geno_error) {
-  if (int rc = need(h, true, "ccu_fmx_posteriors_push")) return rc;
-  FmxState* f = h->fmx;
-  if (!f->have_stats) return ccu_fail(h, "ccu_fmx_posteriors_push: no cluster statistics yet (run ccu_fmx_mstep first)");
-  if (f->peers.n < 1) return ccu_fail(h, "ccu_fmx_posteriors_push: call ccu_fmx_peer_open first");
-  CCU_CUDA(h, cudaSetDevice(h->device));
-  CCU_CUDA(h, ccu::launch_fmx_cgp_push(fmx_view(h), apply_geno_error, f->peers, h->stream));
-  f->tm.launches += 1;
-  f->have_post = true;
-  return 0;
-}
-
+// Full barrier across the ranks as one tiny kernel (arrive + wait): what orders the un-synchronised form of the
+// fused calls (in_kernel_sync = 0), e.g. several handles on ONE device, where a kernel that spins at its head could
+// keep the peer it waits for from being scheduled.
 int ccu_fmx_rank_barrier_dev(ccu_handle* h) {
   if (int rc = need(h, true, "ccu_fmx_rank_barrier")) return rc;
   FmxState* f = h->fmx;
   if (f->peers.n < 1) return ccu_fail(h, "ccu_fmx_rank_barrier: call ccu_fmx_peer_open first");
   CCU_CUDA(h, cudaSetDevice(h->device));
-  CCU_CUDA(h, ccu::launch_fmx_rank_barrier(f->peers, f->peer_rank, h->stream));
+  CCU_CUDA(h, ccu::launch_fmx_sync(f->peers, make_sync(h, true), h->stream));
   f->tm.launches += (f->peers.n > 1) ? 1 : 0;
   return 0;
 }
@@ -478,21 +577,19 @@ int ccu_fmx_rank_barrier_failed(ccu_handle* h, int32_t* failed) {
   *failed = 0;
   if (!f->flags.p) return 0;
   CCU_CUDA(h, cudaSetDevice(h->device));
-  uint32_t v = 0;
+  uint32_t v[ccu::kMaxPeers + 2] = {};
   CCU_CUDA(h, cudaStreamSynchronize(h->stream));
-  CCU_CUDA(h, cudaMemcpy(&v, f->flags.as<uint32_t>() + ccu::kMaxPeers + 1, sizeof(v), cudaMemcpyDeviceToHost));
-  *failed = v ? 1 : 0;
-  return 0;
-}
-
-int ccu_fmx_assign_push_dev(ccu_handle* h) {
-  if (int rc = need(h, true, "ccu_fmx_assign_push")) return rc;
-  FmxState* f = h->fmx;
-  if (!f->have_estep) return ccu_fail(h, "ccu_fmx_assign_push: no E-step has run");
-  if (f->peers.n < 1) return ccu_fail(h, "ccu_fmx_assign_push: call ccu_fmx_peer_open first");
-  CCU_CUDA(h, cudaSetDevice(h->device));
-  CCU_CUDA(h, ccu::launch_fmx_assign_push(fmx_view(h), f->peers, h->stream));
-  f->tm.launches += 1;
+  CCU_CUDA(h, cudaMemcpy(v, f->flags.p, sizeof(v), cudaMemcpyDeviceToHost));
+  if (v[ccu::kMaxPeers + 1]) {
+    *failed = 1;
+    char late[256] = "";
+    size_t n = 0;
+    for (int r = 0; r < f->peers.n && n + 24 < sizeof(late); ++r)
+      if (r != f->peer_rank && (int32_t)(v[r] - v[ccu::kMaxPeers]) < 0)
+        n += (size_t)snprintf(late + n, sizeof(late) - n, " %d(at %u)", r, v[r]);
+    ccu_fail(h, "freemuxlet multi-GPU loop: rank %d gave up waiting at epoch %u; ranks behind:%s (time-out: CCU_FMX_BARRIER_TIMEOUT_S)",
+             f->peer_rank, v[ccu::kMaxPeers], n ? late : " none (a peer gave up first)");
+  }
   return 0;
 }
 
@@ -574,22 +671,23 @@ int ccu_fmx_run_em(ccu_handle* h, const int32_t* init_assign, int32_t niter, int
   if (f->cell_begin != 0 || f->cell_end != f->nbcs || f->snp_begin != 0 || f->snp_end != f->nsnps)
     return ccu_fail(h, "ccu_fmx_run_em: single-GPU loop needs the full shard (use the *_dev calls with collectives)");
   if (niter < 1) return ccu_fail(h, "ccu_fmx_run_em: niter must be >= 1");
-  if (int rc = ccu_fmx_mstep(h, init_assign)) return rc;  // cmd_cram_freemuxlet.cpp:359-370
+  if (f->peers.n > 1) return ccu_fail(h, "ccu_fmx_run_em: peers are mapped on this handle (ccu_fmx_peer_close first)");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  for (int64_t c = 0; c < f->nbcs; ++c)
+    if (!init_assign || init_assign[c] >= f->K) return ccu_fail(h, "ccu_fmx_run_em: bad initial assignment at droplet %lld", (long long)c);
+  if (f->nbcs > 0)
+    CCU_CUDA(h, cudaMemcpyAsync(f->assign.p, init_assign, f->nbcs * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  // geno_error is applied by the E-step of the last iteration only (freemuxlet, :485) or of every iteration (freemux2,
+  // cmd_cram_freemux2.cpp:410-415); the M-step before it forms the posteriors, so it gets the flag of the E-step
+  // that follows.  The 96-byte statistics records are only written by the M-step that may be the last one.
+  auto apply_at = [&](int it) { return geno_error_every_iter ? 1 : (it + 1 == niter ? 1 : 0); };
+  if (int rc = ccu_fmx_mstep_fused_dev(h, apply_at(0), 0, 0)) return rc;  // cmd_cram_freemuxlet.cpp:359-370
   std::vector<ccu_fmx_result> prev, cur;
-  float ms_e = 0, ms_m = 0;
   int it = 0;
   for (; it < niter; ++it) {
-    const int apply = geno_error_every_iter ? 1 : (it + 1 == niter);  // :485 vs freemux2 :410
-    if (int rc = ccu_fmx_estep_dev(h, apply)) return rc;
-    cudaEvent_t e0 = f->ev[0], e1 = f->ev[1];
-    CCU_CUDA(h, cudaEventSynchronize(e1));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    ms_e += ms;
-    if (int rc = ccu_fmx_mstep_dev(h)) return rc;  // :639-650 (assign was written by the E-step)
-    CCU_CUDA(h, cudaEventSynchronize(f->ev[1]));
-    cudaEventElapsedTime(&ms, f->ev[0], f->ev[1]);
-    ms_m += ms;
+    if (int rc = ccu_fmx_estep_fused_dev(h, 0)) return rc;
+    const bool maybe_last = stop_when_stable || it + 1 == niter;
+    if (int rc = ccu_fmx_mstep_fused_dev(h, apply_at(it + 1), maybe_last ? 1 : 0, 0)) return rc;  // :639-650
     if (stop_when_stable) {  // cmd_cram_freemux2.cpp:518-604
       cur.resize(f->nbcs);
       if (int rc = ccu_fmx_download_results(h, cur.data())) return rc;
@@ -607,8 +705,10 @@ int ccu_fmx_run_em(ccu_handle* h, const int32_t* init_assign, int32_t niter, int
       }
     }
   }
-  f->tm.ms_estep = ms_e / (it > 0 ? it : 1);
-  f->tm.ms_mstep = ms_m / (it > 0 ? it : 1);
+  // device times of the last iteration's two phases
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&f->tm.ms_estep, f->ev[0], f->ev[1]);
+  cudaEventElapsedTime(&f->tm.ms_mstep, f->ev[2], f->ev[3]);
   if (iters_run) *iters_run = it;
   return ccu_fmx_download_results(h, out);
 }
@@ -679,21 +779,30 @@ int ccu_fmx_run_em_multi(ccu_handle** hs, int32_t n, const int64_t* cell_ptr, co
     f->peers.n = n;
     for (int j = 0; j < n; ++j) {
       f->peers.post[j] = hs[j]->fmx->cgp.as<double>();
+      f->peers.postm[j] = hs[j]->fmx->cgm.as<double>();
       f->peers.assign[j] = hs[j]->fmx->assign.as<int32_t>();
       f->peers.flags[j] = hs[j]->fmx->flags.as<uint32_t>();
     }
   }
-  // Dry pass, one handle after the other and without barriers: every kernel of the loop gets loaded into its
+  // With one handle per device the kernels of the loop order the ranks themselves (arrival at the tail of the
+  // producer, wait at the head of the consumer).  Several handles on ONE device must not do that: a consumer kernel
+  // spinning at its head can fill the device and keep the producer it waits for from ever being scheduled; there the
+  // ranks are ordered by the one-warp barrier kernel between the launches, which always fits beside other work.
+  bool distinct = true;
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j) distinct = distinct && hs[i]->device != hs[j]->device;
+  const int in_kernel = (distinct && n > 1) ? 1 : 0;
+  // Dry pass, one handle after the other and without any cross-rank wait: every kernel of the loop gets loaded into its
   // context and every buffer reaches its final size.  Inside the loop nothing may need a device-wide pause any more
-  // -- a lazy kernel load or a cudaMalloc on a device where a peer's barrier kernel is spinning (several handles on
-  // one device) would wait for that kernel, which waits for us.  What the pass writes is overwritten below.
+  // -- a lazy kernel load or a cudaMalloc on a device where a peer's kernel is spinning would wait for that kernel,
+  // which waits for us.  What the pass writes is overwritten below.
   for (int i = 0; i < n; ++i) {
     ccu_handle* h = hs[i];
     CCU_CUDA(h, cudaSetDevice(h->device));
     if (nbcs > 0) CCU_CUDA(h, cudaMemsetAsync(h->fmx->assign.p, 0xff, nbcs * sizeof(int32_t), h->stream));
-    if (ccu_fmx_mstep_dev(h) || ccu_fmx_posteriors_push_dev(h, 1) || ccu_fmx_estep_post_dev(h) || ccu_fmx_assign_push_dev(h))
+    if (ccu_fmx_mstep_fused_dev(h, 1, 1, 0) || ccu_fmx_estep_fused_dev(h, 0))
       return hs[i] == h0 ? 1 : ccu_fail(h0, "ccu_fmx_run_em_multi: handle %d: %s", i, ccu_last_error(h));
-    CCU_CUDA(h, ccu::preload_fmx_rank_barrier());
+    CCU_CUDA(h, ccu::preload_fmx_sync());
     CCU_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   std::vector<int> rcs(n, 0);
@@ -712,22 +821,21 @@ int ccu_fmx_run_em_multi(ccu_handle** hs, int32_t n, const int64_t* cell_ptr, co
       rcs[i] = ccu_fail(h, "ccu_fmx_run_em_multi: copying the initial assignment failed");
       return;
     }
-    // A rank that fails keeps launching its barriers (a missing one would only be noticed by the peers' time-out)
-    step(ccu_fmx_mstep_dev(h));
+    auto apply_at = [&](int it) { return geno_error_every_iter ? 1 : (it + 1 == niter ? 1 : 0); };
+    // A rank that fails keeps its peers in step (a missing arrival would only be noticed by their time-out)
+    auto phase = [&](int rc) {
+      if (rcs[i] == 0) step(rc);
+      if (!in_kernel || rcs[i] != 0) ccu_fmx_rank_barrier_dev(h);
+    };
+    phase(ccu_fmx_mstep_fused_dev(h, apply_at(0), 0, in_kernel));
     for (int it = 0; it < niter; ++it) {
-      const int apply = geno_error_every_iter ? 1 : (it + 1 == niter);
-      if (rcs[i] == 0) step(ccu_fmx_posteriors_push_dev(h, apply));
-      ccu_fmx_rank_barrier_dev(h);
-      if (rcs[i] == 0) step(ccu_fmx_estep_post_dev(h));
-      if (rcs[i] == 0) step(ccu_fmx_assign_push_dev(h));
-      ccu_fmx_rank_barrier_dev(h);
-      if (rcs[i] == 0) step(ccu_fmx_mstep_dev(h));
+      phase(rcs[i] == 0 ? ccu_fmx_estep_fused_dev(h, in_kernel) : 1);
+      phase(rcs[i] == 0 ? ccu_fmx_mstep_fused_dev(h, apply_at(it + 1), it + 1 == niter, in_kernel) : 1);
     }
     if (rcs[i] == 0 && cb[i + 1] > cb[i]) step(ccu_fmx_download_results(h, out + cb[i]));
     if (cudaStreamSynchronize(h->stream) != cudaSuccess && rcs[i] == 0) rcs[i] = ccu_fail(h, "stream synchronisation failed");
     int32_t failed = 0;
-    if (rcs[i] == 0 && ccu_fmx_rank_barrier_failed(h, &failed) == 0 && failed)
-      rcs[i] = ccu_fail(h, "ccu_fmx_run_em_multi: a peer did not reach the barrier within its time-out");
+    if (rcs[i] == 0 && ccu_fmx_rank_barrier_failed(h, &failed) == 0 && failed) rcs[i] = 1;  // message set by the check
   };
   if (n == 1) {
     work(0);

@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "ccu_fmx_get_timings", "ccu_fmx_selftest_division", "ccu_fmx_post_dev", "ccu_fmx_posteriors_dev",
     "ccu_fmx_estep_post_dev", "ccu_fmx_pair_distances", "ccu_fmx_get_pair_distances", "ccu_fmx_initial_clusters",
     "ccu_fmx_greedy_clusters", "ccu_fmx_get_voting_pairs", "ccu_fmx_peer_handles", "ccu_fmx_peer_open",
-    "ccu_fmx_peer_close", "ccu_fmx_posteriors_push_dev", "ccu_fmx_assign_push_dev", "ccu_fmx_rank_barrier_dev",
+    "ccu_fmx_peer_close", "ccu_fmx_mstep_fused_dev", "ccu_fmx_estep_fused_dev", "ccu_fmx_rank_barrier_dev",
     "ccu_fmx_rank_barrier_failed", "ccu_fmx_run_em_multi", "ccu_demux_set_genotypes_mixed",
     "ccu_demux_genotypes_stage", "ccu_demux_genotypes_commit", "ccu_demux_results_dev",
     "ccu_demux_refine", "ccu_demux_refine_mixed",
@@ -319,7 +319,7 @@ class FreemuxEngine(DemuxEngine):
         self._check(self.lib.ccu_fmx_estep_post_dev(self.h))
 
     # ---- peer-memory exchange (CUDA IPC over NVLink), see include/cramore_cuda.h ----
-    IPC_BYTES = 3 * 64
+    IPC_BYTES = 4 * 64
 
     def peer_handles(self):
         buf = C.create_string_buffer(self.IPC_BYTES)
@@ -336,19 +336,26 @@ class FreemuxEngine(DemuxEngine):
     def peer_close(self):
         self._check(self.lib.ccu_fmx_peer_close(self.h))
 
-    def posteriors_push_dev(self, apply_geno_error=False):
-        self._check(self.lib.ccu_fmx_posteriors_push_dev(self.h, C.c_int32(1 if apply_geno_error else 0)))
+    def mstep_fused_dev(self, apply_geno_error_next=False, want_stats=False, in_kernel_sync=True):
+        """M-step of this shard's slab + posteriors of the next E-step, stored into every rank's arrays."""
+        self._check(self.lib.ccu_fmx_mstep_fused_dev(self.h, C.c_int32(int(bool(apply_geno_error_next))),
+                                                     C.c_int32(int(bool(want_stats))), C.c_int32(int(bool(in_kernel_sync)))))
 
-    def assign_push_dev(self):
-        self._check(self.lib.ccu_fmx_assign_push_dev(self.h))
+    def estep_fused_dev(self, in_kernel_sync=True):
+        """E-step + decision of this shard's droplets, assignments stored into every rank's vector."""
+        self._check(self.lib.ccu_fmx_estep_fused_dev(self.h, C.c_int32(int(bool(in_kernel_sync)))))
 
     def rank_barrier_dev(self):
         self._check(self.lib.ccu_fmx_rank_barrier_dev(self.h))
 
     def rank_barrier_failed(self):
+        """True when a kernel of the multi-GPU loop gave up waiting for a peer; last_error() then says who and where."""
         v = C.c_int32(0)
         self._check(self.lib.ccu_fmx_rank_barrier_failed(self.h, C.byref(v)))
         return bool(v.value)
+
+    def last_error(self):
+        return self.lib.ccu_last_error(self.h).decode()
 
     def mstep_dev(self):
         self._check(self.lib.ccu_fmx_mstep_dev(self.h))

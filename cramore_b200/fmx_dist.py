@@ -12,6 +12,10 @@
             itself is all-reduced once, after the last M-step (it is only needed for the cluster VCF).
   per iteration: posteriors of the slab -> all-reduce -> E-step -> all-gather of the assignment vector -> M-step.
   exchange="stats" keeps the heavier form (all-reduce of the 12-double statistics every iteration).
+  exchange="push" (the B200 form, and the single-GPU loop): the fused kernels -- the M-step kernel forms the
+            posteriors of its slab and stores them into every rank's array over NVLink, the decision kernel does the
+            same with the assignments, and the ranks are ordered by epoch flags inside those kernels
+            (include/cramore_cuda.h); two launches + the decision per iteration, no collective on the payload.
 
 The engine object only has to provide the methods used below, which lets the CPU test suite drive the
 same loop over gloo with a numpy stand-in."""
@@ -74,9 +78,7 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
         exchange = "posteriors" if post is not None else "stats"
     if exchange not in ("posteriors", "stats", "push") or (exchange == "posteriors" and post is None):
         raise ValueError("exchange must be 'stats', 'posteriors' (needs the posterior tensor) or 'push'")
-    if exchange == "push" and not multi:
-        exchange = "posteriors" if post is not None else "stats"
-    if exchange == "push":
+    if exchange == "push" and multi:
         # the mappings persist on the engine (they are tied to its arrays, not to one EM run)
         key = (dist.get_world_size(group), rank)
         if getattr(eng, "_peer_world", None) != key:
@@ -91,12 +93,10 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
             token = graphs.setdefault("_barrier_token", token)
 
     def rank_barrier():
-        # stream-ordered: completes here only after every rank's stream has reached it, i.e. after their push kernels
-        if push_barrier == "kernel":
-            eng.rank_barrier_dev()  # one-warp kernel over mapped flag arrays (no collective at all)
-        else:
-            sync()
-            dist.all_reduce(token, op=dist.ReduceOp.SUM, group=group)
+        # push_barrier == "nccl": a 4-byte all-reduce on the shared stream orders the ranks between the fused kernels
+        # (instead of the epoch flags inside them); completes only after every rank's stream has reached it
+        sync()
+        dist.all_reduce(token, op=dist.ReduceOp.SUM, group=group)
 
     def exchange_assign():
         # each rank owns assign[cb:ce]; a sum of (value + 1) over zero-filled vectors is an all-gather
@@ -120,27 +120,39 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
         sync()
         dist.all_reduce(post, op=dist.ReduceOp.SUM, group=group)
 
+    def apply_at(it):  # geno_error for the E-step of iteration `it` (:485 vs cmd_cram_freemux2.cpp:410)
+        return bool(geno_error_every_iter) or (it + 1 == niter)
+
+    def em_loop_fused():
+        in_kernel = (not multi) or push_barrier == "kernel"
+
+        def order():
+            if multi and not in_kernel:
+                rank_barrier()
+        eng.mstep_fused_dev(apply_at(0), False, in_kernel)
+        order()
+        for it in range(niter):
+            eng.estep_fused_dev(in_kernel)
+            order()
+            eng.mstep_fused_dev(apply_at(it + 1), it + 1 == niter, in_kernel)
+            order()
+        exchange_stats()  # once: the full statistics are only needed for the output
+
     def em_loop():
+        if exchange == "push":
+            return em_loop_fused()
         eng.mstep_dev()
         if exchange == "stats":
             exchange_stats()
         for it in range(niter):
-            apply = bool(geno_error_every_iter) or (it + 1 == niter)
+            apply = apply_at(it)
             if exchange == "stats":
                 eng.estep_dev(apply)
-            elif exchange == "push":
-                eng.posteriors_push_dev(apply)
-                rank_barrier()
-                eng.estep_post_dev()
             else:
                 eng.posteriors_dev(apply)
                 exchange_post()
                 eng.estep_post_dev()
-            if exchange == "push":
-                eng.assign_push_dev()
-                rank_barrier()
-            else:
-                exchange_assign()
+            exchange_assign()
             eng.mstep_dev()
             if exchange == "stats":
                 exchange_stats()
@@ -166,8 +178,8 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
         graphs[key].replay()
     sync()
     local = eng.download_results()
-    if exchange == "push" and push_barrier == "kernel" and eng.rank_barrier_failed():
-        raise RuntimeError("freemuxlet peer-memory exchange: a rank did not reach the barrier within its time-out")
+    if exchange == "push" and multi and push_barrier == "kernel" and eng.rank_barrier_failed():
+        raise RuntimeError(eng.last_error())
     if not multi:
         return local, local
     device = None if stats.device.type == "cpu" else stats.device

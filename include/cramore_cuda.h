@@ -242,37 +242,51 @@ void* ccu_fmx_stats_dev(ccu_handle* h, int64_t* n_doubles);
 void* ccu_fmx_post_dev(ccu_handle* h, int64_t* n_doubles);
 int ccu_fmx_posteriors_dev(ccu_handle* h, int32_t apply_geno_error);
 int ccu_fmx_estep_post_dev(ccu_handle* h);
-/* Peer-memory exchange (no reference counterpart: the reference is one process).  With one process per GPU on an
- * NVLink / NVSwitch box the two per-iteration exchanges need no collective on the payload: every rank maps the
- * posterior and assignment arrays of all ranks (CUDA IPC) and the producing kernels store straight into them.
- *   setup, after ccu_fmx_set_shard: ccu_fmx_peer_handles(h, mine) -> all-gather of the CCU_IPC_HANDLE_BYTES*3 bytes
+/* The fused loop (what ccu_fmx_run_em and the multi-GPU drivers run): two calls per iteration.
+ *   ccu_fmx_mstep_fused_dev  M-step of this shard's SNP slab; the kernel forms the genotype posteriors (and their mean
+ *                            genotypes) of the slab from the registers that hold the finished statistics -- with the
+ *                            genotype-error mix of cmd_cram_freemuxlet.cpp:485-489 iff apply_geno_error_next, i.e. the
+ *                            flag of the E-step that FOLLOWS -- and stores them into the arrays of every rank;
+ *                            want_stats = 0 skips the 96-byte statistics records (only the output after the last
+ *                            iteration reads them)
+ *   ccu_fmx_estep_fused_dev  E-step + decision of this shard's droplets; the decision kernel stores the new
+ *                            assignments into the vector of every rank
+ * Peer-memory exchange (no reference counterpart: the reference is one process).  With one process (or handle) per
+ * GPU on an NVLink / NVSwitch box the two per-iteration exchanges need no collective on the payload: every rank maps
+ * the posterior, mean-genotype and assignment arrays of all ranks (CUDA IPC across processes, peer access inside one)
+ * and the producing kernels store straight into them.
+ *   setup, after ccu_fmx_set_shard: ccu_fmx_peer_handles(h, mine) -> all-gather of the 4 * CCU_IPC_HANDLE_BYTES bytes
  *          (any host channel) -> ccu_fmx_peer_open(h, nranks, rank, all)
- *   per iteration: ccu_fmx_posteriors_push_dev -> barrier -> ccu_fmx_estep_post_dev -> ccu_fmx_assign_push_dev ->
- *          barrier -> ccu_fmx_mstep_dev
- * where "barrier" is a stream-ordered cross-rank synchronisation -- ccu_fmx_rank_barrier_dev (a one-warp kernel over
- * mapped flag arrays: release-store of the next epoch into every peer, acquire-spin on the own array; it gives up
- * after ~2 s and ccu_fmx_rank_barrier_failed then reports 1) or a 4-byte ncclAllReduce on the engine's stream.
- * A rank may read its arrays only after every rank's push kernel has completed, and may push again only after
- * every rank has finished reading -- both follow from the two barriers.  Results are bit-identical to the
- * all-reduce exchange.  ccu_fmx_peer_close unmaps (also done by ccu_destroy). */
+ * A rank may read its arrays only after every rank's producing kernel has completed, and may be written to again
+ * only after it has finished reading.  in_kernel_sync = 1 makes the kernels do that themselves: the last CTA of a
+ * producer release-stores the rank's next epoch into its slot of every peer's flag array, the consumer kernel
+ * acquire-spins at its head until every slot of its own array has got there -- no launch, no collective, and the
+ * stores of one CTA travel over NVLink while the others still compute.  A wait longer than
+ * CCU_FMX_BARRIER_TIMEOUT_S (default 30 s) raises an error flag instead of hanging the GPU, every later kernel of
+ * the loop then returns at once, and ccu_fmx_rank_barrier_failed reports it (message: rank, epoch, ranks behind).
+ * in_kernel_sync = 0 leaves the ordering to the caller: ccu_fmx_rank_barrier_dev (the same protocol as one one-warp
+ * kernel; required when several handles share ONE device, where a kernel spinning at its head could keep the peer it
+ * waits for from being scheduled) or a collective on the engine's stream after each of the two calls.
+ * Without peers (single GPU) the two calls are simply the loop of cmd_cram_freemuxlet.cpp:457-653.  Results are
+ * bit-identical whatever the number of ranks.  ccu_fmx_peer_close unmaps (also done by ccu_destroy). */
 #define CCU_IPC_HANDLE_BYTES 64
 /* The same exchange inside ONE process: n handles on different devices (or several on one), each configured and
  * uploaded with the same store.  One host thread per handle runs the loop of cmd_cram_freemuxlet.cpp:359-370 +
  * :457-653 on its droplet range and SNP slab (about nnz / n entries each), peers are reached through
- * cudaDeviceEnablePeerAccess, the two per-iteration exchanges are the push kernels and the flag barrier above.
+ * cudaDeviceEnablePeerAccess, the two per-iteration exchanges happen inside the fused kernels above.
  * cell_ptr / snp_idx: the host arrays that were uploaded (for the partition).  out: host [nbcs];
  * clusters_out: optional host [nclust][nsnps], the cluster pileups after the last M-step.
  * Bit-identical to ccu_fmx_run_em (no early stop: freemux2's stop_when_stable needs a host decision per iteration). */
 int ccu_fmx_run_em_multi(ccu_handle** handles, int32_t n, const int64_t* cell_ptr, const int32_t* snp_idx,
                          const int32_t* init_assign, int32_t niter, int32_t geno_error_every_iter, ccu_fmx_result* out,
                          ccu_pileup* clusters_out);
-int ccu_fmx_peer_handles(ccu_handle* h, void* out /* [3 * CCU_IPC_HANDLE_BYTES]: posteriors, assignments, flags */);
-int ccu_fmx_peer_open(ccu_handle* h, int32_t nranks, int32_t rank, const void* handles /* [nranks][3][64] */);
+int ccu_fmx_peer_handles(ccu_handle* h, void* out /* [4 * CCU_IPC_HANDLE_BYTES]: posteriors, mean genotypes, assignments, flags */);
+int ccu_fmx_peer_open(ccu_handle* h, int32_t nranks, int32_t rank, const void* handles /* [nranks][4][64] */);
 int ccu_fmx_rank_barrier_dev(ccu_handle* h);
 int ccu_fmx_rank_barrier_failed(ccu_handle* h, int32_t* failed);
 int ccu_fmx_peer_close(ccu_handle* h);
-int ccu_fmx_posteriors_push_dev(ccu_handle* h, int32_t apply_geno_error);
-int ccu_fmx_assign_push_dev(ccu_handle* h);
+int ccu_fmx_mstep_fused_dev(ccu_handle* h, int32_t apply_geno_error_next, int32_t want_stats, int32_t in_kernel_sync);
+int ccu_fmx_estep_fused_dev(ccu_handle* h, int32_t in_kernel_sync);
 void* ccu_fmx_assign_dev(ccu_handle* h, int64_t* n_int32);
 int ccu_fmx_mstep_dev(ccu_handle* h);
 int ccu_fmx_estep_dev(ccu_handle* h, int32_t apply_geno_error);

@@ -311,14 +311,15 @@ from cramore_b200.synth import make_dataset
 
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
-dev = torch.device("cuda", 0)            # both ranks share the one GPU of the test box
+ndev = torch.cuda.device_count()
+dev = torch.device("cuda", rank %% ndev)  # one GPU per rank where the box has them (stores cross NVLink); else shared
 torch.cuda.set_device(dev)
 torch.cuda.set_stream(torch.cuda.Stream(device=dev))
 K, NITER = 5, 4                          # odd K: a slab may start at an odd element (the 8-byte store path)
 d = make_dataset("C4", nbcs=300, nsnps=2001, rbar=120, nv=5)
 init = (d["s1"] %% K).astype(np.int32)
 init[d["is_dbl"]] = -1
-eng = FreemuxEngine(0)
+eng = FreemuxEngine(rank %% ndev)
 eng.set_stream(torch.cuda.current_stream().cuda_stream)
 eng.configure_fmx(K, 0.5, 0.05)
 eng.upload_fmx(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], d["af"])
@@ -327,11 +328,13 @@ post = posterior_view(eng, dev)
 ranges = balanced_ranges(d["cell_ptr"], world)
 slabs = snp_slabs(d["snp_idx"], d["nsnps"], world)
 out = {}
-for mode in ("push", "posteriors"):
-    loc, full = run_em_distributed(eng, stats, assign, ranges, slabs, init, niter=NITER, post=post, exchange=mode,
-                                   geno_error_every_iter=True)
+for mode in ("push", "push-nccl-ordered", "posteriors"):
+    loc, full = run_em_distributed(eng, stats, assign, ranges, slabs, init, niter=NITER, post=post,
+                                   exchange=mode.split("-")[0], geno_error_every_iter=True,
+                                   push_barrier="nccl" if mode.endswith("ordered") else "kernel")
     torch.cuda.synchronize()
     out[mode] = (full.copy(), stats.cpu().numpy().copy())
+assert np.array_equal(out["push"][0], out["push-nccl-ordered"][0]) and np.array_equal(out["push"][1], out["push-nccl-ordered"][1])
 assert np.array_equal(out["push"][0], out["posteriors"][0]), "results differ between the exchanges"
 assert np.array_equal(out["push"][1], out["posteriors"][1]), "cluster statistics differ between the exchanges"
 if rank == 0:
@@ -340,6 +343,7 @@ if rank == 0:
     ref.upload_fmx(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], d["af"])
     want, _ = ref.run_em(init, niter=NITER, geno_error_every_iter=True)
     assert np.array_equal(want, out["push"][0]), "peer-memory exchange differs from the single-process loop"
+    assert np.array_equal(ref.clusters()["gls"].reshape(-1, 9), out["push"][1].reshape(-1, 12)[:, :9]), "cluster pileups differ"
     assert (want["type"] == 0).sum() > 100
     ref.close()
 dist.barrier()
@@ -350,10 +354,11 @@ print("rank", rank, "ok")
 
 
 def test_peer_memory_exchange_two_processes(built, tmp_path):
-    """The CUDA-IPC exchange of the multi-GPU freemuxlet loop (posterior kernel and assignment push storing into the
-    other rank's arrays, flag barrier over mapped memory) with two processes on this box's GPU: bit-identical to the
-    all-reduce exchange and to the single-process loop.  gloo carries the host-side plumbing (NCCL refuses two ranks
-    on one device); on a multi-GPU box tools/bench_fmx.py --exchange push --check runs the same over NVLink."""
+    """The CUDA-IPC exchange of the multi-GPU freemuxlet loop (the M-step kernel storing its slab's posteriors and the
+    decision kernel its assignments into the other rank's arrays, the ranks ordered by epoch flags inside those
+    kernels or by a collective between them) with two processes: on two GPUs where the box has them (the stores then
+    cross NVLink), else both on the one GPU.  Bit-identical to the all-reduce exchange and to the single-process
+    loop.  gloo carries the host-side plumbing (NCCL refuses two ranks on one device)."""
     import subprocess
     import sys
     script = tmp_path / "peer_worker.py"
@@ -364,6 +369,67 @@ def test_peer_memory_exchange_two_processes(built, tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2
+
+
+_TIMEOUT_WORKER = r"""
+import os, sys, time
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from cramore_b200 import FreemuxEngine
+from cramore_b200.synth import make_dataset
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+ndev = torch.cuda.device_count()
+torch.cuda.set_device(rank %% ndev)
+K = 4
+d = make_dataset("C4", nbcs=200, nsnps=1000, rbar=80, nv=4)
+eng = FreemuxEngine(rank %% ndev)
+eng.configure_fmx(K, 0.5, 0.0)
+eng.upload_fmx(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], d["af"])
+half = d["nbcs"] // 2
+eng.set_shard(rank * half, (rank + 1) * half, rank * 500, (rank + 1) * 500)
+everyone = [None] * world
+dist.all_gather_object(everyone, eng.peer_handles())
+eng.peer_open(rank, everyone)
+if rank == 0:
+    # rank 1 never launches its M-step: the E-step's wait at its head must give up (CCU_FMX_BARRIER_TIMEOUT_S = 1),
+    # raise the flag, and every later kernel of the loop must return at once instead of computing on stale data
+    t0 = time.time()
+    eng.mstep_fused_dev(False, False, True)
+    eng.estep_fused_dev(True)
+    eng.mstep_fused_dev(False, False, True)
+    eng.estep_fused_dev(True)
+    eng.synchronize()
+    dt = time.time() - t0
+    assert eng.rank_barrier_failed(), "the wait did not time out"
+    msg = eng.last_error()
+    assert "rank 0" in msg and "ranks behind: 1" in msg and "CCU_FMX_BARRIER_TIMEOUT_S" in msg, msg
+    assert 0.5 < dt < 20.0, dt
+    print("timeout reported after %%.1f s: %%s" %% (dt, msg))
+dist.barrier()
+eng.close()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_peer_wait_times_out_instead_of_hanging(built, tmp_path):
+    """A rank whose peer never arrives: the kernel waiting at its head gives up after CCU_FMX_BARRIER_TIMEOUT_S, raises
+    the error flag, the remaining kernels of the loop return at once, and the host gets a message naming the rank,
+    the epoch and the ranks that were behind."""
+    import subprocess
+    import sys
+    script = tmp_path / "timeout_worker.py"
+    script.write_text(_TIMEOUT_WORKER % {"root": os.path.dirname(os.path.dirname(os.path.abspath(__file__)))})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", CCU_FMX_BARRIER_TIMEOUT_S="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29735", str(script)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2 and "timeout reported" in r.stdout
 
 
 @pytest.mark.parametrize("nhandles", [2, 3])

@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--nsnps", type=int, default=None)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--check", action="store_true")
-    ap.add_argument("--exchange", default="posteriors", choices=["posteriors", "stats", "push"])
+    ap.add_argument("--exchange", default="push", choices=["posteriors", "stats", "push"])
     ap.add_argument("--push-barrier", default="kernel", choices=["kernel", "nccl"])
     ap.add_argument("--graph", action="store_true", help="run the whole EM loop as one CUDA graph (captured on the second run)")
     args = ap.parse_args()
@@ -93,15 +93,15 @@ def main():
             b.record()
             torch.cuda.synchronize()
             out[name] = a.elapsed_time(b)
-        timed("estep_ms", lambda: eng.estep_dev(False))
-        timed("mstep_ms", lambda: eng.mstep_dev())
+        timed("estep_ms", lambda: eng.estep_fused_dev(False))
+        timed("mstep_ms", lambda: eng.mstep_fused_dev(False, False, False))
+        timed("estep_unfused_ms", lambda: eng.estep_dev(False))
+        timed("mstep_unfused_ms", lambda: eng.mstep_dev())
         if world > 1:
             timed("allreduce_stats_ms", lambda: dist.all_reduce(stats))
             timed("allreduce_posteriors_ms", lambda: dist.all_reduce(post))
             if args.exchange == "push":
                 tok = torch.zeros(1, dtype=torch.int32, device=dev)
-                timed("posteriors_push_ms", lambda: eng.posteriors_push_dev(False))
-                timed("assign_push_ms", lambda: eng.assign_push_dev())
                 timed("rank_barrier_nccl_ms", lambda: dist.all_reduce(tok))
                 timed("rank_barrier_kernel_ms", lambda: eng.rank_barrier_dev())
         return out
@@ -133,8 +133,8 @@ def main():
         except Exception:
             hbm_peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
         nobs = int(np.unique(d["snp_idx"]).size)
-        e_bytes = (84 + 24 * K) * nnz / world
-        m_bytes = (84 * nnz + 84 * K * nobs) / world
+        e_bytes = (20 + 8 * K) * nnz / world  # single-read entries: (gl[0]/2, b) + SNP id + K mean genotypes
+        m_bytes = (92 * nnz + 32 * K * d["nsnps"]) / world  # pileups + droplet ids in, posteriors + mean genotypes out
         roof = []
         for name, key, nbytes in (("fmx_estep_rows_kernel (F2)", "estep_ms", e_bytes),
                                   ("fmx_mstep_kernel (F3)", "mstep_ms", m_bytes)):
