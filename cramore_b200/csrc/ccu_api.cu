@@ -67,6 +67,7 @@ ccu::DemuxDev dev_view(const ccu_handle* h) {
   d.al = h->d_al.as<uint8_t>();
   d.bq = h->d_bq.as<uint8_t>();
   d.tiles = h->d_tiles.as<double>();
+  d.tslot = h->d_tslot.as<int32_t>();
   d.vaff = h->d_vaff.as<double>();
   d.vent = h->d_vent.as<int64_t>();
   d.vsnp = h->d_vsnp.as<int32_t>();
@@ -137,7 +138,7 @@ int ccu_destroy(ccu_handle* h) {
   DevBuf* bufs[] = {&h->d_alpha, &h->d_ptab, &h->d_half, &h->d_phred, &h->d_gpf, &h->d_err, &h->d_hasgp,
                     &h->d_avg, &h->d_G, &h->d_cell_ptr, &h->d_snp_idx, &h->d_read_ptr, &h->d_al, &h->d_bq,
                     &h->d_tiles, &h->d_vaff, &h->d_eclass, &h->d_vent, &h->d_vsnp, &h->d_vcnt, &h->d_sng, &h->d_fmat, &h->d_pm, &h->d_pe, &h->d_maxbq, &h->d_partials, &h->d_results, &h->d_dbg, &h->d_flag,
-                    &h->d_sink};
+                    &h->d_sink, &h->d_tslot, &h->d_scan, &h->d_ngen};
   for (DevBuf* b : bufs) b->release();
   ccu_fmx_release(h);
   for (int i = 0; i < EV_COUNT; ++i)
@@ -330,7 +331,17 @@ int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const
   CCU_CUDA(h, h->d_read_ptr.reserve((nnz + 1) * sizeof(int64_t)));
   CCU_CUDA(h, h->d_al.reserve(nreads + 16));
   CCU_CUDA(h, h->d_bq.reserve(nreads + 16));
-  CCU_CUDA(h, h->d_tiles.reserve((size_t)nnz * h->nA * ccu::kTileStride * sizeof(double) + 16));
+  if (nnz > 2147483647LL) return fail(h, "ccu_demux_upload: more than 2^31-1 (cell,SNP) entries in one call (ccu_demux_score splits a store into ranges)");
+  CCU_CUDA(h, h->d_tslot.reserve((size_t)nnz * sizeof(int32_t) + 16));
+  CCU_CUDA(h, h->d_ngen.reserve(16));
+  {
+    size_t need = 0;
+    ccu::DemuxDev q;
+    memset(&q, 0, sizeof(q));
+    q.nnz = nnz;
+    CCU_CUDA(h, ccu::launch_tile(q, false, nullptr, 0, &need, h->stream));
+    CCU_CUDA(h, h->d_scan.reserve(need + 16));
+  }
   CCU_CUDA(h, h->d_vent.reserve(nnz * sizeof(int64_t) + 16));
   CCU_CUDA(h, h->d_vsnp.reserve(nnz * sizeof(int32_t) + 16));
   CCU_CUDA(h, h->d_vcnt.reserve(2 * nbcs * sizeof(int32_t) + 16));
@@ -356,7 +367,22 @@ int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const
     CCU_CUDA(h, cudaMemcpyAsync(h->d_bq.p, bq, nreads, cudaMemcpyHostToDevice, h->stream));
   }
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_X1], h->stream));
+  // Full 9 x nAlpha tiles are only kept for the entries with two or more informative reads (one entry in two thousand
+  // in sparse single-cell data, a third with skewed coverage): count them, on the device, and size the buffer to that
+  // (80 * nAlpha bytes per entry: 3.5 GB at C2 if it were kept for every entry).
+  unsigned long long ngen = 0;
+  {
+    ccu::DemuxDev q;
+    memset(&q, 0, sizeof(q));
+    q.nnz = nnz;
+    q.read_ptr = h->d_read_ptr.as<int64_t>();
+    q.al = h->d_al.as<uint8_t>();
+    CCU_CUDA(h, ccu::launch_count_general(q, h->d_ngen.as<unsigned long long>(), h->stream));
+    CCU_CUDA(h, cudaMemcpyAsync(&ngen, h->d_ngen.p, sizeof(ngen), cudaMemcpyDeviceToHost, h->stream));
+  }
   CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->ngen = (int64_t)ngen;
+  CCU_CUDA(h, h->d_tiles.reserve((size_t)h->ngen * h->nA * ccu::kTileStride * sizeof(double) + 16));
   h->tm.ms_h2d = ev_ms(h, EV_X0, EV_X1);
   h->nbcs = nbcs;
   h->nnz = nnz;
@@ -393,7 +419,7 @@ int ccu_demux_run(ccu_handle* h) {
     h->validated = true;
   }
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_RUN0], st));
-  CCU_CUDA(h, ccu::launch_tile(d, false, st));
+  CCU_CUDA(h, ccu::launch_tile(d, false, h->d_scan.p, h->d_scan.cap, nullptr, st));
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_TILE], st));
   CCU_CUDA(h, ccu::launch_compact(d, st));
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_COMPACT], st));
@@ -403,7 +429,7 @@ int ccu_demux_run(ccu_handle* h) {
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_SCORE], st));
   CCU_CUDA(h, ccu::launch_finalize(d, plan, st));
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_FIN], st));
-  h->tm.launches = (h->nbcs > 0 ? 4 : 0) + (h->nnz > 0 ? 2 : 0) + nvalidate;
+  h->tm.launches = (h->nbcs > 0 ? 4 : 0) + (h->nnz > 0 ? 3 : 0) + nvalidate;  // + entry, prefix sum, tile kernels
   h->tm.score_ctas = grid;
   h->tm.score_items = h->nbcs * plan.items_per_cell;
   h->ran = true;
@@ -452,7 +478,10 @@ int ccu_demux_download(ccu_handle* h, ccu_demux_result* out) {
 // Device scratch one droplet range needs (the per-entry tiles and single-read likelihood rows dominate).
 static double demux_scratch_bytes(const ccu_handle* h, int64_t ncell, int64_t nnz, int64_t nreads) {
   const ccu::ScorePlan plan = ccu::make_score_plan(h->nv, h->nA, h->alpha.data());
-  const double per_entry = (double)h->nA * ccu::kTileStride * 8 + (double)h->nvp * 8 + 8 + 4 + 1 + 32 + 4 + 8;
+  // full tiles are kept for the entries with >= 2 informative reads only; how many that is is known after the upload,
+  // so the estimate charges a quarter of the entries (real data: well under that; beyond it the allocation itself
+  // fails cleanly and the caller can lower CCU_DEMUX_MAX_SCRATCH_MB)
+  const double per_entry = 0.25 * (double)h->nA * ccu::kTileStride * 8 + (double)h->nvp * 8 + 8 + 4 + 1 + 32 + 4 + 8 + 4;
   const double per_cell = (double)h->nv * 8 + (double)h->nvp * 12 + 16 + sizeof(ccu_demux_result) +
                           (double)plan.items_per_cell * ccu::kScoreWarps * sizeof(ccu::ItemPartial);
   return per_entry * (double)nnz + per_cell * (double)ncell + 2.0 * (double)nreads;
@@ -546,9 +575,13 @@ int ccu_demux_get_tiles(ccu_handle* h, double* tiles) {
   CCU_CUDA(h, cudaSetDevice(h->device));
   const size_t rowp = (size_t)h->nA * ccu::kTileStride;
   std::vector<double> tmp((size_t)h->nnz * rowp);
-  CCU_CUDA(h, ccu::launch_tile(dev_view(h), true, h->stream));  // materialise the affine entries' tiles too
+  // inspection only: the tile of EVERY entry (the engine itself keeps those of the general entries), in a scratch buffer
+  CCU_CUDA(h, h->d_dbg.reserve(tmp.size() * sizeof(double) + 16));
+  ccu::DemuxDev d = dev_view(h);
+  d.tiles = h->d_dbg.as<double>();
+  CCU_CUDA(h, ccu::launch_tile(d, true, h->d_scan.p, h->d_scan.cap, nullptr, h->stream));
   CCU_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (h->nnz > 0) CCU_CUDA(h, cudaMemcpy(tmp.data(), h->d_tiles.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (h->nnz > 0) CCU_CUDA(h, cudaMemcpy(tmp.data(), h->d_dbg.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
   for (int64_t e = 0; e < h->nnz; ++e)
     for (int n = 0; n < h->nA; ++n)
       memcpy(tiles + ((size_t)e * h->nA + n) * 9, tmp.data() + e * rowp + n * ccu::kTileStride, 9 * sizeof(double));

@@ -71,7 +71,8 @@ struct ccu_handle {
   bool ran = false;
   DevBuf d_cell_ptr, d_snp_idx, d_read_ptr, d_al, d_bq;
   DevBuf d_tiles, d_vaff, d_eclass, d_vent, d_vsnp, d_vcnt, d_sng, d_fmat, d_pm, d_pe, d_maxbq, d_partials, d_results,
-      d_dbg, d_sink, d_flag;
+      d_dbg, d_sink, d_flag, d_tslot, d_scan, d_ngen;
+  int64_t ngen = 0;  // entries with >= 2 informative reads in the uploaded store (sizes the tile buffer)
   double scratch_fits = 0.0;  // largest scratch need (bytes) that ran in one piece on this handle
   bool validated = false;  // the uploaded CSR passed demux_validate_kernel
 

@@ -52,8 +52,10 @@ struct DemuxDev {
   const uint8_t* al;
   const uint8_t* bq;
   // intermediates
-  double* tiles;           // [nnz][nA][kTileStride]; rows of general entries only, unless materialised
-                           //       for ccu_demux_get_tiles
+  double* tiles;           // [general entries][nA][kTileStride] (tslot != NULL: the row of entry e is tslot[e]),
+                           //       or [nnz][nA][kTileStride] with every row materialised (tslot == NULL:
+                           //       ccu_demux_get_tiles)
+  int32_t* tslot;          // [nnz] exclusive prefix sum of eclass: tile row of a general entry
   double* vaff;            // [nnz][4] {pG[0][0][.], pG[0][1][.], pG[0][2][.], 0} of every entry
   uint8_t* eclass;         // [nnz] 0 = at most one informative read (tile affine in the allele
                            //       fraction), 1 = general
@@ -88,7 +90,12 @@ cudaError_t launch_gp_prepare(const float* gp_f32, const double* snp_err, const 
                               int64_t nsnps, int nv, int nvp, double* avg_tmp, double* G,
                               cudaStream_t st);
 cudaError_t launch_validate(const DemuxDev& d, int64_t nreads, uint32_t* flag, cudaStream_t st);
-cudaError_t launch_tile(const DemuxDev& d, bool all_entries, cudaStream_t st);
+// number of entries with >= 2 informative reads -> *count_dev (what sizes the tile buffer; once per upload)
+cudaError_t launch_count_general(const DemuxDev& d, unsigned long long* count_dev, cudaStream_t st);
+// scan_tmp / scan_bytes: scratch of the prefix sum over the entry classes (scan_bytes = 0: return the size needed in
+// *scan_need and do nothing)
+cudaError_t launch_tile(const DemuxDev& d, bool all_entries, void* scan_tmp, size_t scan_bytes, size_t* scan_need,
+                        cudaStream_t st);
 cudaError_t launch_compact(const DemuxDev& d, cudaStream_t st);
 cudaError_t launch_sample(const DemuxDev& d, cudaStream_t st);
 // dbg != NULL: also dump (mantissa, exponent) of every computed llksAB entry of cells [dbg_c0, dbg_c1)

@@ -21,7 +21,10 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <cub/device/device_scan.cuh>
+
 #include "demux_internal.h"
+#include "div_exact.cuh"
 
 namespace ccu {
 
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(kTileWarps * 32)
     demux_tile_kernel(int64_t nnz, const int64_t* __restrict__ read_ptr, const uint8_t* __restrict__ al,
                       const uint8_t* __restrict__ bq, int nA, const double* __restrict__ ptab,
                       const double* __restrict__ phred, const uint8_t* __restrict__ eclass, int all_entries,
-                      double* __restrict__ tiles, double* __restrict__ vaff) {
+                      const int32_t* __restrict__ tslot, double* __restrict__ tiles, double* __restrict__ vaff) {
   constexpr int EPW = 32 / GL;  // entries per warp per pass
   __shared__ double s_err[256];
   __shared__ double s_mat[256];
@@ -327,9 +330,18 @@ __global__ void __launch_bounds__(kTileWarps * 32)
       }
 #pragma unroll
       for (int d = GL / 2; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-      if (use && has_alpha) {
+      if (use && has_alpha) {  // :696 -- nine IEEE divisions by one divisor: the reciprocal is refined once
+        unsigned lo = (unsigned)__double2hiint(mx);    // (div_exact.cuh; bit-identical to v[t] / mx)
 #pragma unroll
-        for (int t = 0; t < 9; ++t) v[t] = v[t] / mx;  // :696
+        for (int t = 0; t < 9; ++t) lo = min(lo, (unsigned)__double2hiint(v[t]));
+        if (lo >= kDivLoHi) {  // everything in [2^-500, 1]: a deep entry whose small values fade out takes the plain path
+          const double y = rcp_refined(mx);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) v[t] = div_with_rcp(v[t], mx, y);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) v[t] = v[t] / mx;
+        }
       }
     }
     // :704-725
@@ -362,7 +374,7 @@ __global__ void __launch_bounds__(kTileWarps * 32)
     for (int sb = 0; sb < EPW; ++sb) {
       const int64_t es = __shfl_sync(0xffffffffu, e, sb * GL);
       if (__shfl_sync(0xffffffffu, (int)valid, sb * GL)) {
-        double* dst = tiles + es * rowlen;
+        double* dst = tiles + (tslot ? (int64_t)tslot[es] : es) * rowlen;
         for (int i = lane; i < rowlen; i += 32) dst[i] = s_out[warp][sb * rowlen + i];
       }
     }
@@ -403,7 +415,37 @@ cudaError_t launch_validate(const DemuxDev& d, int64_t nreads, uint32_t* flag, c
   return cudaGetLastError();
 }
 
-cudaError_t launch_tile(const DemuxDev& d, bool all_entries, cudaStream_t st) {
+// entries with >= 2 informative reads (the same test as demux_entry_kernel), counted once per upload
+__global__ void __launch_bounds__(256)
+    demux_count_general_kernel(int64_t nnz, const int64_t* __restrict__ read_ptr, const uint8_t* __restrict__ al,
+                               unsigned long long* __restrict__ count) {
+  unsigned n = 0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+    int nuse = 0;
+    for (int64_t r = read_ptr[e]; r < read_ptr[e + 1] && nuse < 2; ++r) nuse += (al[r] != 2);
+    n += (nuse > 1);
+  }
+  n = __reduce_add_sync(0xffffffffu, n);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(count, (unsigned long long)n);
+}
+
+cudaError_t launch_count_general(const DemuxDev& d, unsigned long long* count_dev, cudaStream_t st) {
+  cudaError_t e0 = cudaMemsetAsync(count_dev, 0, sizeof(unsigned long long), st);
+  if (e0 != cudaSuccess || d.nnz == 0) return e0;
+  int64_t blocks = (d.nnz + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  demux_count_general_kernel<<<(unsigned)blocks, 256, 0, st>>>(d.nnz, d.read_ptr, d.al, count_dev);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tile(const DemuxDev& d, bool all_entries, void* scan_tmp, size_t scan_bytes, size_t* scan_need,
+                        cudaStream_t st) {
+  if (scan_bytes == 0) {  // size query of the prefix sum
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, (const uint8_t*)nullptr, (int32_t*)nullptr, (int)(d.nnz > 0 ? d.nnz : 1), st);
+    if (scan_need) *scan_need = need;
+    return cudaSuccess;
+  }
   cudaError_t e0 = cudaMemsetAsync(d.maxbq, 0, sizeof(int32_t), st);
   if (e0 != cudaSuccess) return e0;
   if (d.nnz == 0) return cudaSuccess;
@@ -413,6 +455,10 @@ cudaError_t launch_tile(const DemuxDev& d, bool all_entries, cudaStream_t st) {
     demux_entry_kernel<<<(unsigned)blocks, 256, 0, st>>>(d.nnz, d.read_ptr, d.al, d.bq, d.phred, d.vaff, d.eclass,
                                                          d.maxbq);
   }
+  if (!all_entries) {  // tile row of every general entry = number of general entries before it
+    e0 = cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, d.eclass, d.tslot, (int)d.nnz, st);
+    if (e0 != cudaSuccess) return e0;
+  }
   int gl = 2;
   while (gl < d.nA) gl <<= 1;
   int64_t per_block = (int64_t)kTileWarps * 32;
@@ -421,7 +467,7 @@ cudaError_t launch_tile(const DemuxDev& d, bool all_entries, cudaStream_t st) {
 #define CCU_TILE(GL)                                                                                 \
   demux_tile_kernel<GL><<<(unsigned)blocks, kTileWarps * 32, 0, st>>>(d.nnz, d.read_ptr, d.al, d.bq, d.nA, d.ptab, \
                                                                        d.phred, d.eclass, all_entries ? 1 : 0,      \
-                                                                       d.tiles, d.vaff)
+                                                                       all_entries ? nullptr : d.tslot, d.tiles, d.vaff)
   switch (gl) {
     case 2: CCU_TILE(2); break;
     case 4: CCU_TILE(4); break;
@@ -771,7 +817,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
             const double* grow = d.G + snp * (int64_t)d.nvp * 3;
             bulk_g2s(slot, grow + (int64_t)j0 * 3, Cfg::GJ_BYTES, bar);
             bulk_g2s(slot + Cfg::GJ_BYTES, grow + (int64_t)k0 * 3, kbytes, bar);
-            bulk_g2s(slot + Cfg::GJ_BYTES + Cfg::GK_BYTES, d.tiles + (e * d.nA + n0) * kTileStride, pbytes, bar);
+            bulk_g2s(slot + Cfg::GJ_BYTES + Cfg::GK_BYTES, d.tiles + ((int64_t)d.tslot[e] * d.nA + n0) * kTileStride, pbytes, bar);
           }
         } else if (cnt > 0 && lane <= krows / 32) {
           // part 0: the j tile; parts 1..: the 32-sample tiles of the k tile
@@ -1242,7 +1288,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
   for (int i = 0; i < ng; ++i) {
     const int64_t e = d.vent[base + i];
     const double* g = d.G + (int64_t)d.vsnp[base + i] * grow;
-    const double* tile = d.tiles + e * d.nA * kTileStride;
+    const double* tile = d.tiles + (int64_t)d.tslot[e] * d.nA * kTileStride;
 #pragma unroll
     for (int q = 0; q < PPL; ++q)
       if (pn[q] > 0) {

@@ -1,4 +1,5 @@
-"""Small fixed demuxlet run for ncu captures: C2 shape, a few thousand barcodes, 3 engine runs."""
+"""Small fixed demuxlet run for ncu captures: a BASELINE shape, a few thousand barcodes, 3 engine runs.
+usage: python tools/prof_demux.py [nbcs] [config] [snp_skew] [rbar]"""
 import os
 import sys
 
@@ -8,7 +9,9 @@ from cramore_b200.synth import make_dataset
 
 nbcs = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
 name = sys.argv[2] if len(sys.argv) > 2 else "C2"
-d = make_dataset(name, nbcs=nbcs)
+skew = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
+rbar = int(sys.argv[4]) if len(sys.argv) > 4 else None
+d = make_dataset(name, nbcs=nbcs, snp_skew=skew, rbar=rbar)
 eng = DemuxEngine(0)
 eng.configure(d["nv"], d["alphas"], 0.5)
 eng.set_genotypes(d["gp"], d["snp_err"])
