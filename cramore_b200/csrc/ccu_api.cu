@@ -239,6 +239,7 @@ int ccu_demux_genotypes_stage(ccu_handle* h, int64_t nsnps, void** gp_dev, void*
 }
 
 int ccu_demux_genotypes_commit(ccu_handle* h, int64_t nsnps, int32_t use_has_gp) {
+  CcuRange nvtx_range("ccu_demux_genotypes_commit");
   if (!h) return 1;
   if (!h->configured) return fail(h, "ccu_demux_genotypes_commit: call ccu_demux_configure first");
   if (nsnps < 0 || nsnps != h->staged_snps)
@@ -259,6 +260,7 @@ int ccu_demux_genotypes_commit(ccu_handle* h, int64_t nsnps, int32_t use_has_gp)
 
 int ccu_demux_set_genotypes(ccu_handle* h, int64_t nsnps, const float* gp, const double* snp_err,
                             const uint8_t* has_gp) {
+  CcuRange nvtx_range("ccu_demux_set_genotypes");
   if (!h) return 1;
   if (!h->configured) return fail(h, "ccu_demux_set_genotypes: call ccu_demux_configure first");
   if (nsnps < 0 || (nsnps > 0 && (!gp || !snp_err))) return fail(h, "ccu_demux_set_genotypes: bad arguments");
@@ -277,6 +279,7 @@ int ccu_demux_set_genotypes(ccu_handle* h, int64_t nsnps, const float* gp, const
 // in (sc_drop_seq.cpp:287-315), or NULL where the VCF had no usable record.  A patched cmdCramDemuxlet can hand
 // those pointers over as they are.
 int ccu_demux_set_genotypes_mixed(ccu_handle* h, int64_t nsnps, const double* const* gps) {
+  CcuRange nvtx_range("ccu_demux_set_genotypes_mixed");
   if (!h) return 1;
   if (!h->configured) return fail(h, "ccu_demux_set_genotypes_mixed: call ccu_demux_configure first");
   if (nsnps < 0 || (nsnps > 0 && !gps)) return fail(h, "ccu_demux_set_genotypes_mixed: bad arguments");
@@ -313,8 +316,41 @@ int ccu_demux_set_genotypes_mixed(ccu_handle* h, int64_t nsnps, const double* co
   return 0;
 }
 
+// One process driving several GPUs: the genotype matrix is uploaded and mixed once (on `src`) and every other handle
+// takes its copy over NVLink (cudaMemcpyPeerAsync on its own stream), instead of one PCIe upload per device.
+int ccu_demux_copy_genotypes(ccu_handle* dst, ccu_handle* src) {
+  CcuRange nvtx_range("ccu_demux_copy_genotypes");
+  if (!dst || !src) return 1;
+  if (dst == src) return 0;
+  if (!dst->configured || !src->configured || src->nsnps < 0)
+    return fail(dst, "ccu_demux_copy_genotypes: configure both handles and set the genotypes of the source first");
+  if (dst->nv != src->nv) return fail(dst, "ccu_demux_copy_genotypes: the handles are configured for %d and %d samples", dst->nv, src->nv);
+  CCU_CUDA(dst, cudaSetDevice(src->device));
+  CCU_CUDA(dst, cudaStreamSynchronize(src->stream));  // the source matrix is complete
+  CCU_CUDA(dst, cudaSetDevice(dst->device));
+  const int64_t nsnps = src->nsnps;
+  const size_t gbytes = (size_t)nsnps * src->nvp * 3 * sizeof(double);
+  CCU_CUDA(dst, dst->d_G.reserve(gbytes + 16));
+  CCU_CUDA(dst, dst->d_hasgp.reserve(nsnps + 16));
+  CCU_CUDA(dst, cudaEventRecord(dst->ev[EV_GP0], dst->stream));
+  if (nsnps > 0) {
+    CCU_CUDA(dst, cudaMemcpyPeerAsync(dst->d_G.p, dst->device, src->d_G.p, src->device, gbytes, dst->stream));
+    if (src->has_gp_flags)
+      CCU_CUDA(dst, cudaMemcpyPeerAsync(dst->d_hasgp.p, dst->device, src->d_hasgp.p, src->device, (size_t)nsnps, dst->stream));
+  }
+  CCU_CUDA(dst, cudaEventRecord(dst->ev[EV_GP1], dst->stream));
+  CCU_CUDA(dst, cudaStreamSynchronize(dst->stream));
+  dst->tm.ms_genotypes = ev_ms(dst, EV_GP0, EV_GP1);
+  dst->has_gp_flags = src->has_gp_flags;
+  dst->have_avg = false;
+  dst->staged_snps = -1;
+  dst->nsnps = nsnps;
+  return 0;
+}
+
 int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx,
                      const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq) {
+  CcuRange nvtx_range("ccu_demux_upload");
   if (!h) return 1;
   if (!h->configured) return fail(h, "ccu_demux_upload: call ccu_demux_configure first");
   if (nbcs < 0 || !cell_ptr) return fail(h, "ccu_demux_upload: bad arguments");
@@ -393,6 +429,7 @@ int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const
 }
 
 int ccu_demux_run(ccu_handle* h) {
+  CcuRange nvtx_range("ccu_demux_run");
   if (!h) return 1;
   if (!h->configured || h->nsnps < 0 || h->nbcs < 0)
     return fail(h, "ccu_demux_run: configure, set_genotypes and upload must precede run");
@@ -460,6 +497,7 @@ void* ccu_demux_results_dev(ccu_handle* h, int64_t* nbcs) {
 }
 
 int ccu_demux_download(ccu_handle* h, ccu_demux_result* out) {
+  CcuRange nvtx_range("ccu_demux_download");
   if (!h) return 1;
   if (!h->ran) return fail(h, "ccu_demux_download: nothing has been run");
   if (h->nbcs > 0 && !out) return fail(h, "ccu_demux_download: out is NULL");
@@ -489,6 +527,7 @@ static double demux_scratch_bytes(const ccu_handle* h, int64_t ncell, int64_t nn
 
 int ccu_demux_score(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx,
                     const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq, ccu_demux_result* out) {
+  CcuRange nvtx_range("ccu_demux_score");
   if (!h) return 1;
   if (!h->configured) return fail(h, "ccu_demux_score: call ccu_demux_configure first");
   if (nbcs < 0 || !cell_ptr) return fail(h, "ccu_demux_score: bad arguments");

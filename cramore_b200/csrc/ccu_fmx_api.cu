@@ -206,6 +206,7 @@ int ccu_fmx_configure(ccu_handle* h, int32_t nclust, double doublet_prior, doubl
 
 int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* cell_ptr, const int32_t* snp_idx,
                    const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq, const double* af) {
+  CcuRange nvtx_range("ccu_fmx_upload");
   if (int rc = need(h, false, "ccu_fmx_upload")) return rc;
   if (nbcs < 0 || nsnps < 0 || !cell_ptr || (nsnps > 0 && !af)) return ccu_fail(h, "ccu_fmx_upload: bad arguments");
   if (cell_ptr[0] != 0) return ccu_fail(h, "ccu_fmx_upload: cell_ptr[0] must be 0");
@@ -334,6 +335,7 @@ int ccu_fmx_set_shard(ccu_handle* h, int64_t cell_begin, int64_t cell_end, int64
 }
 
 int ccu_fmx_lmix(ccu_handle* h, double* llk0, double* llk2) {
+  CcuRange nvtx_range("ccu_fmx_lmix");
   if (int rc = need(h, true, "ccu_fmx_lmix")) return rc;
   FmxState* f = h->fmx;
   if (f->nbcs > 0 && (!llk0 || !llk2)) return ccu_fail(h, "ccu_fmx_lmix: NULL output");
@@ -463,6 +465,7 @@ int ccu_fmx_estep_post_dev(ccu_handle* h) {
 
 // ---- the fused loop: two launches + the decision per iteration, exchange inside the kernels ----
 int ccu_fmx_mstep_fused_dev(ccu_handle* h, int32_t apply_geno_error_next, int32_t want_stats, int32_t in_kernel_sync) {
+  CcuRange nvtx_range("ccu_fmx_mstep_fused_dev");
   if (int rc = need(h, true, "ccu_fmx_mstep_fused")) return rc;
   CCU_CUDA(h, cudaSetDevice(h->device));
   FmxState* f = h->fmx;
@@ -480,6 +483,7 @@ int ccu_fmx_mstep_fused_dev(ccu_handle* h, int32_t apply_geno_error_next, int32_
 }
 
 int ccu_fmx_estep_fused_dev(ccu_handle* h, int32_t in_kernel_sync) {
+  CcuRange nvtx_range("ccu_fmx_estep_fused_dev");
   if (int rc = need(h, true, "ccu_fmx_estep_fused")) return rc;
   FmxState* f = h->fmx;
   if (!f->have_post || !f->post_full)
@@ -666,6 +670,7 @@ void* ccu_fmx_assign_dev(ccu_handle* h, int64_t* n_int32) {
 
 int ccu_fmx_run_em(ccu_handle* h, const int32_t* init_assign, int32_t niter, int32_t geno_error_every_iter,
                    int32_t stop_when_stable, ccu_fmx_result* out, int32_t* iters_run) {
+  CcuRange nvtx_range("ccu_fmx_run_em");
   if (int rc = need(h, true, "ccu_fmx_run_em")) return rc;
   FmxState* f = h->fmx;
   if (f->cell_begin != 0 || f->cell_end != f->nbcs || f->snp_begin != 0 || f->snp_end != f->nsnps)
@@ -717,6 +722,7 @@ int ccu_fmx_run_em(ccu_handle* h, const int32_t* init_assign, int32_t niter, int
 int ccu_fmx_run_em_multi(ccu_handle** hs, int32_t n, const int64_t* cell_ptr, const int32_t* snp_idx,
                          const int32_t* init_assign, int32_t niter, int32_t geno_error_every_iter, ccu_fmx_result* out,
                          ccu_pileup* clusters_out) {
+  CcuRange nvtx_range("ccu_fmx_run_em_multi");
   if (!hs || n < 1 || !hs[0]) return 1;
   ccu_handle* h0 = hs[0];
   if (n > ccu::kMaxPeers) return ccu_fail(h0, "ccu_fmx_run_em_multi: at most %d handles", ccu::kMaxPeers);
@@ -868,6 +874,7 @@ int ccu_fmx_run_em_multi(ccu_handle** hs, int32_t n, const int64_t* cell_ptr, co
 }
 
 int ccu_fmx_pair_distances(ccu_handle* h, int64_t* npairs, int64_t* nrecords, float* ms) {
+  CcuRange nvtx_range("ccu_fmx_pair_distances");
   if (int rc = need(h, true, "ccu_fmx_pair_distances")) return rc;
   CCU_CUDA(h, cudaSetDevice(h->device));
   FmxState* f = h->fmx;

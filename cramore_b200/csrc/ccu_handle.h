@@ -2,6 +2,7 @@
 // ccu_fmx_api.cu: freemuxlet).  Not part of the public ABI.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -9,6 +10,13 @@
 #include <vector>
 
 #include "cramore_cuda.h"
+
+// NVTX range around an entry point of the C ABI: shows up in Nsight Systems / ncu --nvtx next to the kernels it
+// launches; a no-op when no tool is attached (header-only NVTX v3).
+struct CcuRange {
+  explicit CcuRange(const char* name) { nvtxRangePushA(name); }
+  ~CcuRange() { nvtxRangePop(); }
+};
 
 struct DevBuf {
   void* p = nullptr;

@@ -50,7 +50,7 @@ ABI_SYMBOLS = [
     "ccu_fmx_peer_close", "ccu_fmx_mstep_fused_dev", "ccu_fmx_estep_fused_dev", "ccu_fmx_rank_barrier_dev",
     "ccu_fmx_rank_barrier_failed", "ccu_fmx_run_em_multi", "ccu_demux_set_genotypes_mixed",
     "ccu_demux_genotypes_stage", "ccu_demux_genotypes_commit", "ccu_demux_results_dev",
-    "ccu_demux_refine", "ccu_demux_refine_mixed",
+    "ccu_demux_refine", "ccu_demux_refine_mixed", "ccu_demux_copy_genotypes",
 ]
 
 
@@ -143,6 +143,11 @@ class DemuxEngine:
     def genotypes_commit(self, nsnps, use_has_gp=False):
         self._check(self.lib.ccu_demux_genotypes_commit(self.h, C.c_int64(nsnps), C.c_int32(int(use_has_gp))))
         self.nsnps = nsnps
+
+    def copy_genotypes_from(self, other):
+        """ccu_demux_copy_genotypes: take `other`'s mixed genotype matrix (device-to-device; NVLink across GPUs)."""
+        self._check(self.lib.ccu_demux_copy_genotypes(self.h, other.h))
+        self.nsnps = other.nsnps
 
     def results_dev(self):
         """(device pointer, nbcs) of the result records of the last run."""

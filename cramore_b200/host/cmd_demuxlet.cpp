@@ -3,6 +3,7 @@
 // everything between "ingestion finished" (:425) and "row printed" (:993) runs in libcramore_cuda.so.
 // --sam reads BAM through the built-in reader of bam_io.h (SAM text and CRAM need htslib, which this build does not
 // link: they are rejected with an error).
+#include <chrono>
 #include <thread>
 
 #include "cli_params.h"
@@ -57,7 +58,7 @@ std::vector<int> parse_devices(const std::string& s) {
 int cmdDemuxlet(int argc, char** argv) {
   // defaults of cmd_cram_demuxlet.cpp:7-36
   std::string samFile, tagGroup("CB"), tagUMI("UB"), plpPrefix, vcfFile, field("GP"), r2Info("R2"), smList, outPrefix,
-      groupList, gpuDevices("0"), dumpPrefix, loadPrefix;
+      groupList, gpuDevices("0"), dumpPrefix, loadPrefix, timingsFile;
   bool gpuNoRefine = false;
   double genoErrorOffset = 0.10, genoErrorCoeffR2 = 0.00, minCallRate = 0.5, doublet_prior = 0.5;
   int32_t minMAC = 1, samVerbose = 1000000, vcfVerbose = 10000, capBQ = 20, minBQ = 13, minMQ = 20, minTD = 0,
@@ -102,6 +103,7 @@ int cmdDemuxlet(int argc, char** argv) {
   pl.group("GPU engine options (additions of this build)");
   pl.add("gpu-devices", &gpuDevices, "Comma-separated CUDA device ids; droplets are sharded across them");
   pl.add("gpu-no-refine", &gpuNoRefine, "Skip the host pass that re-scores the reported best/next guesses in the reference's own operation order (rows then agree with the reference to ~1e-13 in the likelihoods instead of byte for byte)");
+  pl.add("gpu-timings", &timingsFile, "Write the device times of the engine's kernels (first device) and the host time of the refinement pass to this file as one JSON object");
   pl.add("gpu-dump-inputs", &dumpPrefix, "Write the flattened engine inputs to PREFIX.* and exit without touching a GPU");
   pl.add("gpu-load-inputs", &loadPrefix, "Binary sidecar cache: read the engine inputs written by --gpu-dump-inputs instead of parsing --plp/--vcf (droplet and variant filters are those of the dump)");
   if (!pl.read(argc, argv)) return 1;
@@ -320,13 +322,17 @@ int cmdDemuxlet(int argc, char** argv) {
     cut[d] = std::lower_bound(cell_ptr.begin(), cell_ptr.end(), target) - cell_ptr.begin();
     cut[d] = std::min<int64_t>(std::max(cut[d], cut[d - 1]), nrows);
   }
+  // The genotype matrix crosses PCIe once: the first device uploads and mixes it, the others copy the mixed matrix
+  // from it over NVLink (ccu_demux_copy_genotypes); then every device scores its own range of rows.
   std::vector<std::string> errs(ndev);
+  std::vector<ccu_handle*> hs(ndev, (ccu_handle*)NULL);
+  for (int d = 0; d < ndev; ++d) {
+    if (ccu_create(devs[d], &hs[d])) fatal("%s", ccu_last_error(NULL));
+    if (ccu_demux_configure(hs[d], nv, nAlpha, gridAlpha.data(), doublet_prior)) fatal("%s", ccu_last_error(hs[d]));
+  }
+  if (ccu_demux_set_genotypes(hs[0], nsnps_total, gp_f32.data(), snp_err.data(), has_gp.data())) fatal("%s", ccu_last_error(hs[0]));
   auto work = [&](int d) {
-    ccu_handle* h = NULL;
-    if (ccu_create(devs[d], &h)) {
-      errs[d] = ccu_last_error(NULL);
-      return;
-    }
+    ccu_handle* h = hs[d];
     const int64_t b = cut[d], e = cut[d + 1];
     std::vector<int64_t> cp(cell_ptr.begin() + b, cell_ptr.begin() + e + 1), rp;
     const int64_t e0 = cp.front(), e1 = cp.back();
@@ -334,11 +340,9 @@ int cmdDemuxlet(int argc, char** argv) {
     rp.assign(read_ptr.begin() + e0, read_ptr.begin() + e1 + 1);
     const int64_t r0 = rp.front();
     for (auto& x : rp) x -= r0;
-    if (ccu_demux_configure(h, nv, nAlpha, gridAlpha.data(), doublet_prior) ||
-        ccu_demux_set_genotypes(h, nsnps_total, gp_f32.data(), snp_err.data(), has_gp.data()) ||
+    if ((d > 0 && ccu_demux_copy_genotypes(h, hs[0])) ||
         ccu_demux_score(h, e - b, cp.data(), snp_idx.data() + e0, rp.data(), al.data() + r0, bq.data() + r0, res.data() + b))
       errs[d] = ccu_last_error(h);
-    ccu_destroy(h);
   };
   if (ndev == 1) {
     work(0);
@@ -347,14 +351,30 @@ int cmdDemuxlet(int argc, char** argv) {
     for (int d = 0; d < ndev; ++d) th.emplace_back(work, d);
     for (auto& t : th) t.join();
   }
+  ccu_timings tm0;
+  const bool have_tm = ccu_get_timings(hs[0], &tm0) == 0;
+  for (int d = 0; d < ndev; ++d) ccu_destroy(hs[d]);
   for (int d = 0; d < ndev; ++d)
     if (!errs[d].empty()) fatal("%s", errs[d].c_str());
   // ---- the hypotheses a row names, re-scored in the reference's own operation order (cmd_cram_demuxlet.cpp:655-747):
   // orientation of alpha = 0.5 mirror pairs and every printed digit then equal the reference's (demux_refine.cpp)
+  const auto t_ref0 = std::chrono::steady_clock::now();
   if (!gpuNoRefine &&
       ccu_demux_refine(nrows, cell_ptr.data(), snp_idx.data(), read_ptr.data(), al.data(), bq.data(), nv, nAlpha,
                        gridAlpha.data(), nsnps_total, gp_f32.data(), snp_err.data(), has_gp.data(), 0, res.data()))
     fatal("ccu_demux_refine: bad arguments");
+  const double ms_refine = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_ref0).count();
+  if (!timingsFile.empty() && have_tm) {  // machine-readable per-kernel timing (SURVEY section 5 build notes)
+    Writer wt(timingsFile, false);
+    wt.printf("{\"droplets\": %lld, \"entries\": %lld, \"samples\": %d, \"alphas\": %d, \"devices\": %d, "
+              "\"ms_genotypes\": %.4f, \"ms_csr_h2d\": %.4f, \"ms_tile\": %.4f, \"ms_singlet\": %.4f, \"ms_score\": %.4f, "
+              "\"ms_finalize\": %.4f, \"ms_kernels\": %.4f, \"ms_result_d2h\": %.4f, \"kernel_launches\": %d, "
+              "\"score_ctas\": %d, \"score_items\": %lld, \"ms_refine_host\": %.3f}\n",
+              (long long)nrows, (long long)cell_ptr[nrows], nv, nAlpha, ndev, tm0.ms_genotypes, tm0.ms_h2d, tm0.ms_tile,
+              tm0.ms_singlet, tm0.ms_score, tm0.ms_finalize, tm0.ms_run, tm0.ms_d2h, tm0.launches, tm0.score_ctas,
+              (long long)tm0.score_items, gpuNoRefine ? 0.0 : ms_refine);
+    wt.close();
+  }
 
   // ---- <out>.best: header :629, rows :993 ----
   Writer wbest(outPrefix + ".best", false);

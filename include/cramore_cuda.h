@@ -112,6 +112,9 @@ int ccu_demux_set_genotypes_mixed(ccu_handle* h, int64_t nsnps, const double* co
  * kernels of sc_drop_seq.cpp:287-315 on what is there.  use_has_gp == 0: every SNP has genotypes. */
 int ccu_demux_genotypes_stage(ccu_handle* h, int64_t nsnps, void** gp_dev, void** snp_err_dev, void** has_gp_dev);
 int ccu_demux_genotypes_commit(ccu_handle* h, int64_t nsnps, int32_t use_has_gp);
+/* One process, several handles (one per device): dst takes the mixed matrix of src (whose genotypes were set by any of
+ * the calls above) over NVLink instead of uploading it again.  Both handles configured for the same sample count. */
+int ccu_demux_copy_genotypes(ccu_handle* dst, ccu_handle* src);
 
 /* The whole engine for nbcs droplets, replaces cmd_cram_demuxlet.cpp:636-906 (tile :655-725,
  * pairwise accumulation :733-747, posterior normaliser :804-821, top-2 scans :827-906).

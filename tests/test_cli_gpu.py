@@ -412,3 +412,31 @@ def test_patched_reference_freemux2_runs_on_the_engine(built, tmp_path, name):
     assert len(lm) == len(rlm) and lm[0] == rlm[0]
     for a, b in zip(lm[1:], rlm[1:]):
         assert a == b or _numeric_row_match(a, b), (a, b)
+
+
+def test_cli_demuxlet_over_several_devices(built, tmp_path):
+    """`cramore demuxlet --gpu-devices a,b,c`: rows split into contiguous ranges, one engine handle and host thread per
+    entry of the list (distinct GPUs where the box has them, else handles sharing the GPU), the genotype matrix uploaded
+    once and copied between the handles (ccu_demux_copy_genotypes): the same .best, byte for byte, as on one device --
+    which in turn is the reference's.  --gpu-timings leaves the machine-readable kernel times."""
+    import json
+    import torch
+    fx = refcase.load("demux_grid_deep")
+    d = refcase.dataset(fx)
+    spec = fx["spec"]
+    pre = str(tmp_path / "in")
+    write_plp(d, pre)
+    write_vcf(d, pre + ".vcf", with_r2=spec.get("with_r2", False))
+    ndev = torch.cuda.device_count()
+    common = [CRAMORE, "demuxlet", "--plp", pre, "--vcf", pre + ".vcf", "--field", spec.get("field", "GP")] + spec["args"]
+    for a in (spec["alphas"] or []):
+        common += ["--alpha", repr(float(a))]
+    outs = {}
+    for name, devs in (("one", "0"), ("three", ",".join(str(i % ndev) for i in range(3)))):
+        r = subprocess.run(common + ["--out", str(tmp_path / name), "--gpu-devices", devs, "--gpu-timings",
+                                     str(tmp_path / (name + ".json"))], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        outs[name] = open(str(tmp_path / (name + ".best"))).read()
+    assert outs["one"] == outs["three"] == fx["best_text"]
+    tm = json.load(open(str(tmp_path / "three.json")))
+    assert tm["devices"] == 3 and tm["droplets"] == d["nbcs"] and tm["ms_score"] > 0 and tm["kernel_launches"] >= 5
