@@ -627,6 +627,26 @@ int ccu_demux_get_tiles(ccu_handle* h, double* tiles) {
   return 0;
 }
 
+// The per-(droplet, sample) singlet log-likelihoods llksAB[j][0][0] of the last run (what <out>.single lists) and,
+// optionally, llks00[0] per droplet.
+int ccu_demux_get_singlets(ccu_handle* h, double* llk, double* llk0) {
+  if (!h) return 1;
+  if (!h->ran) return fail(h, "ccu_demux_get_singlets: nothing has been run");
+  if (h->nbcs > 0 && !llk) return fail(h, "ccu_demux_get_singlets: NULL output");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  if (h->nbcs == 0) return 0;
+  CCU_CUDA(h, cudaMemcpyAsync(llk, h->d_sng.p, (size_t)h->nbcs * h->nv * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (llk0) {
+    CCU_CUDA(h, h->d_dbg.reserve(((size_t)h->nsnps * 4 + (size_t)h->nbcs) * sizeof(double) + 16));
+    double* gp0 = h->d_dbg.as<double>();
+    double* out = gp0 + (size_t)h->nsnps * 4;
+    CCU_CUDA(h, ccu::launch_llk00(dev_view(h), gp0, out, h->stream));
+    CCU_CUDA(h, cudaMemcpyAsync(llk0, out, (size_t)h->nbcs * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int ccu_demux_get_genotypes(ccu_handle* h, int64_t snp_begin, int64_t snp_end, double* gps) {
   if (!h) return 1;
   if (h->nsnps < 0) return fail(h, "ccu_demux_get_genotypes: no genotypes set");

@@ -106,6 +106,8 @@ cudaError_t launch_dbg_convert(double2* dbg, double* llk, int64_t n, cudaStream_
 cudaError_t launch_finalize(const DemuxDev& d, const ScorePlan& plan, cudaStream_t st);
 cudaError_t launch_singlet_to_dbg(const DemuxDev& d, double* llk_dbg, int64_t c0, int64_t c1,
                                   cudaStream_t st);
+// llks00[0] per droplet (gp0_tmp: [nsnps][4] scratch); after a run
+cudaError_t launch_llk00(const DemuxDev& d, double* gp0_tmp, double* out, cudaStream_t st);
 cudaError_t launch_fp64_peak(double* sink, int iters, int num_sms, cudaStream_t st);
 
 }  // namespace ccu

@@ -1562,6 +1562,58 @@ cudaError_t launch_finalize(const DemuxDev& d, const ScorePlan& plan, cudaStream
 }
 
 // ------------------------------------------------------------------------------------------
+// <out>.single support: llks00[0] of cmd_cram_demuxlet.cpp:427-440, :762-773 -- the likelihood of the droplet under
+// two fully unspecified samples, sum_snp log sum_{l,m} gp0[l] gp0[m] pG[0][l][m] with gp0 the mean genotype
+// distribution of the pool at the SNP.  Only computed on request (ccu_demux_get_singlets): the reference itself
+// never prints it (dead code there), so it is kept out of the scoring run.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) demux_gp0_kernel(DemuxDev d, double* __restrict__ gp0) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= d.nsnps) return;
+  double a0 = 0, a1 = 0, a2 = 0;
+  const double* g = d.G + s * (int64_t)d.nvp * 3;
+  for (int j = 0; j < d.nv; ++j) {  // :431-434, in sample order
+    a0 = __dadd_rn(a0, g[3 * j]);
+    a1 = __dadd_rn(a1, g[3 * j + 1]);
+    a2 = __dadd_rn(a2, g[3 * j + 2]);
+  }
+  gp0[s * 4] = a0 / d.nv;
+  gp0[s * 4 + 1] = a1 / d.nv;
+  gp0[s * 4 + 2] = a2 / d.nv;
+  gp0[s * 4 + 3] = 0;
+}
+
+__global__ void __launch_bounds__(256) demux_llk00_kernel(DemuxDev d, const double* __restrict__ gp0, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= d.nbcs) return;
+  const int64_t base = d.cell_ptr[c];
+  const int cnt = d.vcnt_g[c] + d.vcnt_a[c];
+  double acc = 0.0;
+  for (int i = lane; i < cnt; i += 32) {
+    // alpha[0] == 0: pG[0][l][m] = v(l) for every m (vaff holds v for every entry)
+    const double4 v = reinterpret_cast<const double4*>(d.vaff)[d.vent[base + i]];
+    const double* p = gp0 + (int64_t)d.vsnp[base + i] * 4;
+    const double vl[3] = {v.x, v.y, v.z};
+    double sum = 0.0;
+#pragma unroll
+    for (int l = 0; l < 3; ++l)
+#pragma unroll
+      for (int m = 0; m < 3; ++m) sum = __dadd_rn(sum, __dmul_rn(__dmul_rn(p[l], p[m]), vl[l]));  // :764-770
+    acc += log(sum);
+  }
+#pragma unroll
+  for (int dd = 16; dd >= 1; dd >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, dd);
+  if (lane == 0) out[c] = acc;
+}
+
+cudaError_t launch_llk00(const DemuxDev& d, double* gp0_tmp, double* out, cudaStream_t st) {
+  if (d.nsnps > 0) demux_gp0_kernel<<<(unsigned)((d.nsnps + 127) / 128), 128, 0, st>>>(d, gp0_tmp);
+  if (d.nbcs > 0) demux_llk00_kernel<<<(unsigned)((d.nbcs * 32 + 255) / 256), 256, 0, st>>>(d, gp0_tmp, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // FP64 roofline denominator: 8 independent DFMA chains per thread
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters) {

@@ -50,7 +50,7 @@ ABI_SYMBOLS = [
     "ccu_fmx_peer_close", "ccu_fmx_mstep_fused_dev", "ccu_fmx_estep_fused_dev", "ccu_fmx_rank_barrier_dev",
     "ccu_fmx_rank_barrier_failed", "ccu_fmx_run_em_multi", "ccu_demux_set_genotypes_mixed",
     "ccu_demux_genotypes_stage", "ccu_demux_genotypes_commit", "ccu_demux_results_dev",
-    "ccu_demux_refine", "ccu_demux_refine_mixed", "ccu_demux_copy_genotypes",
+    "ccu_demux_refine", "ccu_demux_refine_mixed", "ccu_demux_copy_genotypes", "ccu_demux_get_singlets",
 ]
 
 
@@ -213,6 +213,13 @@ class DemuxEngine:
         out = np.zeros((cell_end - cell_begin, self.nv, self.nv, self.nA), np.float64)
         self._check(self.lib.ccu_demux_get_llk(self.h, C.c_int64(cell_begin), C.c_int64(cell_end), _ptr(out)))
         return out
+
+    def singlets(self, want_llk0=True):
+        """(llk[nbcs][nv], llk0[nbcs] or None): every sample's singlet log-likelihood of the last run and llks00[0]."""
+        llk = np.zeros((self.nbcs, self.nv), np.float64)
+        llk0 = np.zeros(self.nbcs, np.float64) if want_llk0 else None
+        self._check(self.lib.ccu_demux_get_singlets(self.h, _ptr(llk), _ptr(llk0)))
+        return llk, llk0
 
     def fp64_peak_tflops(self, ms=200.0):
         v = C.c_double(0)

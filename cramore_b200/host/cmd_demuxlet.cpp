@@ -4,6 +4,7 @@
 // --sam reads BAM through the built-in reader of bam_io.h (SAM text and CRAM need htslib, which this build does not
 // link: they are rejected with an error).
 #include <chrono>
+#include <cmath>
 #include <thread>
 
 #include "cli_params.h"
@@ -59,7 +60,7 @@ int cmdDemuxlet(int argc, char** argv) {
   // defaults of cmd_cram_demuxlet.cpp:7-36
   std::string samFile, tagGroup("CB"), tagUMI("UB"), plpPrefix, vcfFile, field("GP"), r2Info("R2"), smList, outPrefix,
       groupList, gpuDevices("0"), dumpPrefix, loadPrefix, timingsFile;
-  bool gpuNoRefine = false;
+  bool gpuNoRefine = false, writeSingle = false;
   double genoErrorOffset = 0.10, genoErrorCoeffR2 = 0.00, minCallRate = 0.5, doublet_prior = 0.5;
   int32_t minMAC = 1, samVerbose = 1000000, vcfVerbose = 10000, capBQ = 20, minBQ = 13, minMQ = 20, minTD = 0,
           exclFlag = 0x0f04, minTotalReads = 0, minUMIs = 0, minCoveredSNPs = 0;
@@ -103,6 +104,7 @@ int cmdDemuxlet(int argc, char** argv) {
   pl.group("GPU engine options (additions of this build)");
   pl.add("gpu-devices", &gpuDevices, "Comma-separated CUDA device ids; droplets are sharded across them");
   pl.add("gpu-no-refine", &gpuNoRefine, "Skip the host pass that re-scores the reported best/next guesses in the reference's own operation order (rows then agree with the reference to ~1e-13 in the likelihoods instead of byte for byte)");
+  pl.add("write-single", &writeSingle, "Also write [out].single: one row per droplet and sample with the singlet log-likelihood (the file the reference's documentation names; its writer is commented out there, cmd_cram_demuxlet.cpp:516-563)");
   pl.add("gpu-timings", &timingsFile, "Write the device times of the engine's kernels (first device) and the host time of the refinement pass to this file as one JSON object");
   pl.add("gpu-dump-inputs", &dumpPrefix, "Write the flattened engine inputs to PREFIX.* and exit without touching a GPU");
   pl.add("gpu-load-inputs", &loadPrefix, "Binary sidecar cache: read the engine inputs written by --gpu-dump-inputs instead of parsing --plp/--vcf (droplet and variant filters are those of the dump)");
@@ -130,6 +132,7 @@ int cmdDemuxlet(int argc, char** argv) {
   std::vector<float> gp_f32;
   std::vector<double> snp_err;
   std::vector<std::string> row_bcs, sample_ids;
+  std::vector<int32_t> row_totl, row_uniq;  // RD.TOTL / RD.UNIQ of <out>.single (empty after --gpu-load-inputs)
   int32_t nv_total = 0;
   int64_t nsnps_total = 0;
   if (!loadPrefix.empty()) {
@@ -283,6 +286,10 @@ int cmdDemuxlet(int argc, char** argv) {
       cell_ptr.push_back((int64_t)snp_idx.size());
     }
     for (int32_t i : row_cell) row_bcs.push_back(st.bcs[i]);
+    for (int32_t i : row_cell) {
+      row_totl.push_back((int32_t)st.totl_reads[i]);
+      row_uniq.push_back((int32_t)st.uniq_reads[i]);
+    }
     for (int32_t j = 0; j < nv; ++j) sample_ids.push_back(vr.sample_id(j));
     nv_total = nv;
     nsnps_total = st.nsnps();
@@ -315,6 +322,7 @@ int cmdDemuxlet(int argc, char** argv) {
   const std::vector<int> devs = parse_devices(gpuDevices);
   const int ndev = (int)devs.size();
   std::vector<ccu_demux_result> res(nrows);
+  std::vector<double> sng_llk(writeSingle ? (size_t)nrows * nv : 0), llk00(writeSingle ? (size_t)nrows : 0);
   std::vector<int64_t> cut(ndev + 1, nrows);
   cut[0] = 0;
   for (int d = 1; d < ndev; ++d) {
@@ -341,7 +349,8 @@ int cmdDemuxlet(int argc, char** argv) {
     const int64_t r0 = rp.front();
     for (auto& x : rp) x -= r0;
     if ((d > 0 && ccu_demux_copy_genotypes(h, hs[0])) ||
-        ccu_demux_score(h, e - b, cp.data(), snp_idx.data() + e0, rp.data(), al.data() + r0, bq.data() + r0, res.data() + b))
+        ccu_demux_score(h, e - b, cp.data(), snp_idx.data() + e0, rp.data(), al.data() + r0, bq.data() + r0, res.data() + b) ||
+        (writeSingle && e > b && ccu_demux_get_singlets(h, sng_llk.data() + (size_t)b * nv, llk00.data() + b)))
       errs[d] = ccu_last_error(h);
   };
   if (ndev == 1) {
@@ -394,6 +403,27 @@ int cmdDemuxlet(int argc, char** argv) {
     wbest.write(row.data(), n);
   }
   wbest.close();
+  if (writeSingle) {
+    // <out>.single: header of cmd_cram_demuxlet.cpp:516, row format of :552-563 (commented out in the reference, so
+    // no build of it writes this file: parity unpinned).  LLK1 = the engine's singlet log-likelihood llksAB[j][0][0],
+    // LLK0 = llks00[0] (:762-773), POSTPRB = exp(LLK1 - log sum_j exp LLK1) accumulated as at :530-535.  RD.PASS is
+    // not kept by this loader and repeats RD.UNIQ.
+    Writer ws(outPrefix + ".single", false);
+    ws.printf("BARCODE\tSM_ID\tRD.TOTL\tRD.PASS\tRD.UNIQ\tN.SNP\tLLK1\tLLK0\tPOSTPRB\n");
+    for (int64_t r = 0; r < nrows; ++r) {
+      const double* llk = &sng_llk[(size_t)r * nv];
+      double sumLLK = -1e300;
+      for (int32_t j = 0; j < nv; ++j)
+        sumLLK = (sumLLK > llk[j]) ? sumLLK + log(1.0 + exp(llk[j] - sumLLK)) : llk[j] + log(1.0 + exp(sumLLK - llk[j]));
+      const int32_t uniq = (int32_t)(read_ptr[cell_ptr[r + 1]] - read_ptr[cell_ptr[r]]);
+      const int32_t totl = row_totl.empty() ? uniq : row_totl[r];
+      for (int32_t j = 0; j < nv; ++j)
+        ws.printf("%s\t%s\t%d\t%d\t%d\t%d\t%.5lf\t%.5lf\t%.3lg\n", row_bcs[r].c_str(), sample_ids[j].c_str(), totl,
+                  row_uniq.empty() ? uniq : row_uniq[r], uniq, (int32_t)(cell_ptr[r + 1] - cell_ptr[r]), llk[j], llk00[r],
+                  exp(llk[j] - sumLLK));
+    }
+    ws.close();
+  }
   notice("Finished writing output files");
   return 0;
 }

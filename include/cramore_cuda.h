@@ -164,6 +164,13 @@ int ccu_demux_refine_mixed(int64_t nbcs, const int64_t* cell_ptr, const int32_t*
                            const uint8_t* al, const uint8_t* bq, int32_t nv, int32_t nalpha, const double* alpha,
                            int64_t nsnps, const double* const* gps, int32_t nthreads, ccu_demux_result* inout);
 
+/* <out>.single / <out>.sing2 (named by the command's documentation; the writers are commented out in the reference,
+ * cmd_cram_demuxlet.cpp:516, :552-563, :839-848): every sample's singlet log-likelihood of the last run,
+ * llk[nbcs][nv] = llksAB[j][0][0], and -- llk0 != NULL -- llks00[0] per droplet (:427-440, :762-773: both samples
+ * unspecified, genotypes drawn from the pool's mean distribution at the SNP).  Parity unpinned by construction: no
+ * build of the reference writes these files. */
+int ccu_demux_get_singlets(ccu_handle* h, double* llk, double* llk0);
+
 /* Inspection (parity tests): copy device intermediates of the last upload/run back.
  * tiles: [nnz][nalpha*9] (cmd_cram_demuxlet.cpp:655-725); gps: [snp_end-snp_begin][nv][3]
  * (sc_snp_t::gps); llk: [cell_end-cell_begin][nv][nv][nalpha] = llksAB (:746) where the engine

@@ -440,3 +440,58 @@ def test_cli_demuxlet_over_several_devices(built, tmp_path):
     assert outs["one"] == outs["three"] == fx["best_text"]
     tm = json.load(open(str(tmp_path / "three.json")))
     assert tm["devices"] == 3 and tm["droplets"] == d["nbcs"] and tm["ms_score"] > 0 and tm["kernel_launches"] >= 5
+
+
+def test_cli_write_single(built, tmp_path):
+    """<out>.single (cmd_cram_demuxlet.cpp:516, :552-563; the reference's own writer is commented out, so the check is
+    against the oracle's per-sample singlet log-likelihoods llksAB[j][0][0] and a direct evaluation of llks00[0],
+    :762-773): header, one row per (droplet, sample), LLK1 / LLK0 to the printed precision, posteriors summing to 1."""
+    from oracle import pyoracle
+    fx = refcase.load("demux_missing_gp_r2")
+    d, alphas, prior, snp_err, has_gp = refcase.demux_inputs(fx)
+    spec = fx["spec"]
+    pre = str(tmp_path / "in")
+    write_plp(d, pre)
+    write_vcf(d, str(tmp_path / "full.vcf"), with_r2=spec.get("with_r2", False))
+    with open(pre + ".vcf", "w") as f:
+        snp = 0
+        for ln in open(str(tmp_path / "full.vcf")):
+            if ln.startswith("#"):
+                f.write(ln)
+                continue
+            if not spec.get("drop_every") or snp % spec["drop_every"] != 0:
+                f.write(ln)
+            snp += 1
+    args = [CRAMORE, "demuxlet", "--plp", pre, "--vcf", pre + ".vcf", "--out", str(tmp_path / "out"), "--write-single"] + spec["args"]
+    for a in (spec["alphas"] or []):
+        args += ["--alpha", repr(float(a))]
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert open(str(tmp_path / "out.best")).read() == fx["best_text"]
+    lines = open(str(tmp_path / "out.single")).read().splitlines()
+    assert lines[0] == "BARCODE\tSM_ID\tRD.TOTL\tRD.PASS\tRD.UNIQ\tN.SNP\tLLK1\tLLK0\tPOSTPRB"
+    nv = d["nv"]
+    assert len(lines) == 1 + d["nbcs"] * nv
+    gps = pyoracle.mix_genotypes(d["gp"], snp_err, has_gp)
+    _, llk, _ = pyoracle.demux_score(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], gps, alphas, prior,
+                                     has_gp=has_gp, want_llk=True)
+    gp0 = gps.sum(axis=1) / nv
+    order = sorted(range(d["nbcs"]), key=lambda i: d["barcodes"][i])
+    cp, rp = d["cell_ptr"], d["read_ptr"]
+    for rank, c in enumerate(order):
+        llk0 = 0.0
+        for e in range(cp[c], cp[c + 1]):
+            s = d["snp_idx"][e]
+            if not has_gp[s]:
+                continue
+            pg = pyoracle.demux_tile(d["al"][rp[e]:rp[e + 1]], d["bq"][rp[e]:rp[e + 1]], alphas)[:9].reshape(3, 3)
+            llk0 += np.log(sum(gp0[s][l] * gp0[s][m] * pg[l, m] for l in range(3) for m in range(3)))
+        post = 0.0
+        for j in range(nv):
+            f = lines[1 + rank * nv + j].split("\t")
+            assert f[0] == d["barcodes"][c] and f[1] == d["sample_ids"][j] and int(f[5]) == cp[c + 1] - cp[c]
+            assert int(f[4]) == rp[cp[c + 1]] - rp[cp[c]]
+            assert abs(float(f[6]) - llk[c, j, 0, 0]) <= 1e-5 + 1e-9 * abs(llk[c, j, 0, 0])
+            assert abs(float(f[7]) - llk0) <= 1e-5 + 1e-9 * abs(llk0)
+            post += float(f[8])
+        assert abs(post - 1.0) < 0.02  # %.3lg per value
