@@ -136,7 +136,6 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
             order()
             eng.mstep_fused_dev(apply_at(it + 1), it + 1 == niter, in_kernel)
             order()
-        exchange_stats()  # once: the full statistics are only needed for the output
 
     def em_loop():
         if exchange == "push":
@@ -156,11 +155,16 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
             eng.mstep_dev()
             if exchange == "stats":
                 exchange_stats()
+
+    def finish():
+        # once, after the loop: every rank folded only its own SNP slab, the full statistics are needed for the output
         if exchange != "stats":
-            exchange_stats()  # once: the full statistics are only needed for the output
+            exchange_stats()
 
     assign.copy_(torch.as_tensor(np.ascontiguousarray(init_assign, np.int32)).to(assign.device))
     key = (exchange, niter, bool(geno_error_every_iter), cb, ce, sb, se)
+    # graphs: the loop itself (kernels only in the "push" form with in-kernel ordering -- no collective inside the
+    # captured region) replayed as one CUDA graph; the final all-reduce of the statistics stays outside
     if graphs is None or stats.device.type == "cpu":
         em_loop()
     elif key not in graphs:
@@ -176,6 +180,7 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
             eng.set_stream(outer.cuda_stream)
             graphs[key] = g
         graphs[key].replay()
+    finish()
     sync()
     local = eng.download_results()
     if exchange == "push" and multi and push_barrier == "kernel" and eng.rank_barrier_failed():
