@@ -61,7 +61,7 @@ def snp_slabs(snp_idx, nsnps, world):
 
 def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign, niter=10,
                        geno_error_every_iter=False, group=None, sync=None, post=None, exchange=None, graphs=None,
-                       push_barrier="kernel"):
+                       push_barrier="kernel", timing=None):
     """cmd_cram_freemuxlet.cpp:359-370 + :457-653 across ranks.  `stats`/`assign` (and `post`) are torch
     tensors aliasing the engine's arrays (device_views / posterior_view, or CPU tensors of a stand-in
     engine).  exchange: "posteriors" (default when `post` is given) or "stats".  Returns this rank's
@@ -127,7 +127,7 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
         in_kernel = (not multi) or push_barrier == "kernel"
 
         def order():
-            if multi and not in_kernel:
+            if multi and push_barrier == "nccl":
                 rank_barrier()
         eng.mstep_fused_dev(apply_at(0), False, in_kernel)
         order()
@@ -165,6 +165,10 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
     key = (exchange, niter, bool(geno_error_every_iter), cb, ce, sb, se)
     # graphs: the loop itself (kernels only in the "push" form with in-kernel ordering -- no collective inside the
     # captured region) replayed as one CUDA graph; the final all-reduce of the statistics stays outside
+    ev = None
+    if timing is not None and stats.device.type == "cuda":
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     if graphs is None or stats.device.type == "cpu":
         em_loop()
     elif key not in graphs:
@@ -180,10 +184,13 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
             eng.set_stream(outer.cuda_stream)
             graphs[key] = g
         graphs[key].replay()
+    if ev is not None:
+        ev[1].record()
+        timing["loop_events"] = ev
     finish()
     sync()
     local = eng.download_results()
-    if exchange == "push" and multi and push_barrier == "kernel" and eng.rank_barrier_failed():
+    if exchange == "push" and multi and push_barrier in ("kernel", "none") and eng.rank_barrier_failed():
         raise RuntimeError(eng.last_error())
     if not multi:
         return local, local

@@ -28,7 +28,8 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--exchange", default="push", choices=["posteriors", "stats", "push"])
-    ap.add_argument("--push-barrier", default="kernel", choices=["kernel", "nccl"])
+    ap.add_argument("--push-barrier", default="kernel", choices=["kernel", "nccl", "none"],
+                    help="how the ranks are ordered in the push exchange; none = no ordering at all (WRONG results, timing probe)")
     ap.add_argument("--graph", action="store_true", help="run the whole EM loop as one CUDA graph (captured on the second run)")
     args = ap.parse_args()
     import torch
@@ -76,10 +77,12 @@ def main():
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        tm = {}
         loc, full = run_em_distributed(eng, stats, assign, cell_ranges, slabs, init, niter=args.iters, post=post,
-                                       exchange=args.exchange, graphs=graphs, push_barrier=args.push_barrier)
+                                       exchange=args.exchange, graphs=graphs, push_barrier=args.push_barrier, timing=tm)
         e1.record()
         torch.cuda.synchronize()
+        run.loop_ms = tm["loop_events"][0].elapsed_time(tm["loop_events"][1])
         return loc, full, e0.elapsed_time(e1)
 
     def breakdown():
@@ -110,11 +113,12 @@ def main():
     if args.graph:
         run()  # captures the loop, then replays it once
     loc, full, ms = run()
+    loop_ms = run.loop_ms
     phases = breakdown()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, loop_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms, loop_ms = float(t[0].item()), float(t[1].item())
     ok = None
     if args.check and rank == 0:
         ref_eng = FreemuxEngine(local)
@@ -144,6 +148,7 @@ def main():
                          "peak_source": peak_src})
         line = {"metric": "freemuxlet EM iterations/s", "value": args.iters / (ms * 1e-3), "unit": "iter/s",
                 "n_gpus": world, "iters": args.iters, "ms_per_iter": ms / args.iters,
+                "ms_per_iter_loop_only": loop_ms / (args.iters + 0.3),
                 "config": {"workload": "C4 freemuxlet: K=%d, %d barcodes, %d SNPs, %d entries" %
                                        (K, d["nbcs"], d["nsnps"], nnz)},
                 "exchange": args.exchange, "cuda_graph": bool(args.graph), "push_barrier": args.push_barrier, "stats_allreduce_bytes": int(stats.numel() * 8),
