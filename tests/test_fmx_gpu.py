@@ -189,41 +189,6 @@ def test_shard_invariance_and_slab_sum(feng):
     assert np.array_equal(total[..., 9], full_stats["nreads"])
 
 
-def test_estep_alternative_kernels_match_default(built):
-    """CCU_FMX_ESTEP=mma selects the DMMA (FP64 tensor) E-step kernel and CCU_FMX_ESTEP=rows1 the one-row-per-lane
-    kernel for K <= 16; both must give the default kernel's likelihoods to 1e-12 and identical decisions (run in
-    subprocesses: the switch is read once per process)."""
-    import os
-    import subprocess
-    import sys
-    code = r'''
-import numpy as np, sys
-from cramore_b200 import FreemuxEngine
-from cramore_b200.synth import make_dataset
-K = int(sys.argv[1])
-d = make_dataset("C4", nbcs=150, nsnps=2000, rbar=150)
-a = (d["s1"] % K).astype(np.int32); a[d["is_dbl"]] = -1
-e = FreemuxEngine(0); e.configure_fmx(K, 0.5, 0.05)
-e.upload_fmx(d["cell_ptr"], d["snp_idx"], d["read_ptr"], d["al"], d["bq"], d["af"])
-e.mstep(a); res, nxt = e.estep(apply_geno_error=True)
-np.save(sys.argv[2], e.fmx_llk()); np.save(sys.argv[3], nxt)
-'''
-    import tempfile
-    import numpy as np
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    with tempfile.TemporaryDirectory() as tmp:
-        for K in (7, 16, 21):
-            out = {}
-            for mode in ("rows", "rows1", "mma"):
-                env = dict(os.environ, CCU_FMX_ESTEP=mode, PYTHONPATH=root)
-                f1, f2 = os.path.join(tmp, "llk_%s.npy" % mode), os.path.join(tmp, "nxt_%s.npy" % mode)
-                subprocess.check_call([sys.executable, "-c", code, str(K), f1, f2], env=env, cwd=root)
-                out[mode] = (np.load(f1), np.load(f2))
-            for mode in ("rows1", "mma"):
-                np.testing.assert_allclose(out[mode][0], out["rows"][0], rtol=1e-12, atol=1e-12)
-                assert np.array_equal(out[mode][1], out["rows"][1])
-
-
 def test_posterior_exchange_path_is_bitwise_equal(feng):
     """ccu_fmx_posteriors_dev + ccu_fmx_estep_post_dev (the multi-GPU per-iteration form) give the results of
     ccu_fmx_estep_dev bitwise; slab posteriors are disjoint, so their sum over slabs is the full array."""
