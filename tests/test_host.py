@@ -285,7 +285,9 @@ def _help_flags(cmd):
 
 def test_cli_flag_surface(built):
     d = _help_flags("demuxlet")
-    assert d[:len(REF_DEMUX_FLAGS)] == REF_DEMUX_FLAGS and all(f.startswith("gpu-") for f in d[len(REF_DEMUX_FLAGS):])
+    # beyond the reference's flags only engine options (--gpu-*) and the opt-in <out>.single writer
+    assert d[:len(REF_DEMUX_FLAGS)] == REF_DEMUX_FLAGS and all(f.startswith("gpu-") or f == "write-single"
+                                                              for f in d[len(REF_DEMUX_FLAGS):])
     f = _help_flags("freemuxlet")
     assert f[:len(REF_FMX_FLAGS)] == REF_FMX_FLAGS and all(x.startswith("gpu-") for x in f[len(REF_FMX_FLAGS):])
     assert _help_flags("dsc-pileup") == REF_DSC_FLAGS
