@@ -33,7 +33,7 @@ struct FmxState {
   int64_t nbcs = 0, nsnps = 0, nnz = 0, nreads = 0, max_segment = 0;
   int64_t cell_begin = 0, cell_end = 0, snp_begin = 0, snp_end = 0;
   DevBuf cell_ptr, snp_idx, read_ptr, al, bq, af;
-  DevBuf gl, cnt, logdenom, csc_ptr, csc_cell, csc_gl, csc_cnt;
+  DevBuf gl, cnt, logdenom, csc_ptr, csc_cell, csc_row;
   DevBuf eclass, egen, eab, esnp, gcnt;
   DevBuf assign, stats, cgp, cgm, llk, results, scan, scratch, flags, counter;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -59,7 +59,7 @@ struct FmxState {
     close_peers();
     ccu_fmx_pairs_release(pairs);
     DevBuf* all[] = {&cell_ptr, &snp_idx, &read_ptr, &al, &bq, &af, &gl, &cnt, &logdenom, &csc_ptr, &csc_cell,
-                     &csc_gl, &csc_cnt, &eclass, &egen, &eab, &esnp, &gcnt, &assign, &stats, &cgp, &cgm, &llk, &results,
+                     &csc_row, &eclass, &egen, &eab, &esnp, &gcnt, &assign, &stats, &cgp, &cgm, &llk, &results,
                      &scan, &scratch, &flags, &counter};
     for (DevBuf* b : all) b->release();
     for (auto& e : ev)
@@ -102,8 +102,7 @@ ccu::FmxDev fmx_view(const ccu_handle* h) {
   d.logdenom = f->logdenom.as<double>();
   d.csc_ptr = f->csc_ptr.as<int64_t>();
   d.csc_cell = f->csc_cell.as<int32_t>();
-  d.csc_gl = f->csc_gl.as<double>();
-  d.csc_cnt = f->csc_cnt.as<int4>();
+  d.csc_row = f->csc_row.as<double>();
   d.assign = f->assign.as<int32_t>();
   d.stats = f->stats.as<double>();
   d.cgp = f->cgp.as<double>();
@@ -230,6 +229,9 @@ int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* ce
       const int32_t s = snp_idx[e];
       if (s < 0 || s >= nsnps) return ccu_fail(h, "ccu_fmx_upload: snp_idx[%lld] = %d out of range", (long long)e, s);
       mx = std::max(mx, ++per_snp[s]);
+      if (read_ptr[e + 1] - read_ptr[e] > (int64_t)ccu::kCntMask)  // the packed counts of the SNP-major rows
+        return ccu_fail(h, "ccu_fmx_upload: entry %lld has %lld reads (at most %lld per droplet and SNP)", (long long)e,
+                        (long long)(read_ptr[e + 1] - read_ptr[e]), (long long)ccu::kCntMask);
     }
     f->max_segment = mx;
   }
@@ -250,8 +252,7 @@ int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* ce
   CCU_CUDA(h, f->logdenom.reserve((size_t)nnz * sizeof(double) + 16));
   CCU_CUDA(h, f->csc_ptr.reserve((nsnps + 1) * sizeof(int64_t)));
   CCU_CUDA(h, f->csc_cell.reserve((size_t)nnz * sizeof(int32_t) + 16));
-  CCU_CUDA(h, f->csc_gl.reserve((size_t)nnz * 9 * sizeof(double) + 16));
-  CCU_CUDA(h, f->csc_cnt.reserve((size_t)nnz * sizeof(int4) + 16));
+  CCU_CUDA(h, f->csc_row.reserve((size_t)nnz * ccu::kCscRow * sizeof(double) + 32));
   CCU_CUDA(h, f->assign.reserve(nbcs * sizeof(int32_t) + 16));
   CCU_CUDA(h, f->stats.reserve((size_t)f->K * nsnps * ccu::kStatStride * sizeof(double) + 16));
   CCU_CUDA(h, f->cgp.reserve((size_t)f->K * nsnps * 3 * sizeof(double) + 16));

@@ -60,22 +60,26 @@ __global__ void __launch_bounds__(256)
     while ((a + 1) * a / 2 <= p) ++a;
     const int64_t b = p - a * (a - 1) / 2;
     const int64_t ia = b0 + a, ib = b0 + b;
-    const double* gi = d.csc_gl + ia * 9;
-    const double* gj = d.csc_gl + ib * 9;
+    const double* ra = d.csc_row + ia * kCscRow;
+    const double* rb = d.csc_row + ib * kCscRow;
+    const double gi[3] = {ra[0], ra[4], ra[8]};  // gls[0], gls[4], gls[8]
+    const double gj[3] = {rb[0], rb[4], rb[8]};
     double lk0 = 0.0, lk2 = 0.0;
 #pragma unroll
     for (int x = 0; x < 3; ++x) {  // :202-207
-      const double gix = gi[x * 4];
-      lk2 = __dadd_rn(lk2, __dmul_rn(__dmul_rn(gix, gj[x * 4]), gps[x]));
+      const double gix = gi[x];
+      lk2 = __dadd_rn(lk2, __dmul_rn(__dmul_rn(gix, gj[x]), gps[x]));
 #pragma unroll
       for (int y = 0; y < 3; ++y)
-        lk0 = __dadd_rn(lk0, __dmul_rn(__dmul_rn(__dmul_rn(gix, gj[y * 4]), gps[x]), gps[y]));
+        lk0 = __dadd_rn(lk0, __dmul_rn(__dmul_rn(__dmul_rn(gix, gj[y]), gps[x]), gps[y]));
     }
     const int64_t r = r0 + p;
     keys[r] = (uint64_t)d.csc_cell[ia] * (uint64_t)d.nbcs + (uint64_t)d.csc_cell[ib];  // droplets ascend inside a SNP
     rec_id[r] = (uint32_t)r;
     rec_llk[r] = make_double2(log(lk0), log(lk2));
-    rec_reads[r] = make_int2(d.csc_cnt[ia].x, d.csc_cnt[ib].x);
+    // nreads of the two entries (low 21 bits of the packed counts)
+    rec_reads[r] = make_int2((int)((unsigned long long)__double_as_longlong(ra[9]) & kCntMask),
+                             (int)((unsigned long long)__double_as_longlong(rb[9]) & kCntMask));
   }
 }
 

@@ -10,6 +10,14 @@ namespace ccu {
 
 constexpr int kStatStride = 12;   // doubles per (cluster,SNP): gls[9], nreads, nref, nalt
 constexpr int kFmxMaxClust = 64;  // K(K+1)/2 <= 2080 pair likelihoods per droplet
+// SNP-major rows of the M-step: 80 bytes, 16-byte aligned; the read counts of an entry take 21 bits each
+// (ccu_fmx_upload refuses a (droplet, SNP) entry with 2^21 reads or more)
+constexpr int kCscRow = 10;
+constexpr int kCntBits = 21;
+constexpr unsigned long long kCntMask = (1ull << kCntBits) - 1;
+__host__ __device__ inline unsigned long long fmx_pack_counts(int nreads, int nref, int nalt) {
+  return (unsigned long long)nreads | ((unsigned long long)nref << kCntBits) | ((unsigned long long)nalt << (2 * kCntBits));
+}
 
 // Reduced scans of one droplet's pair likelihoods (E-step kernel -> decision kernel)
 struct FmxScan {
@@ -50,8 +58,7 @@ struct FmxDev {
   // SNP-major copy for the M-step
   int64_t* csc_ptr;          // [nsnps+1]
   int32_t* csc_cell;         // [nnz] droplet id, ascending inside a SNP
-  double* csc_gl;            // [nnz][9]
-  int4* csc_cnt;             // [nnz]
+  double* csc_row;           // [nnz][kCscRow]: gl[0..8], then nreads / nref / nalt packed into the tenth slot
   // EM state
   int32_t* assign;           // [nbcs] cluster of the droplet in the next M-step, or -1
   double* stats;             // [K][nsnps][kStatStride]

@@ -91,9 +91,12 @@ def test_lmix_scores(feng):
     np.testing.assert_allclose(l2, r2, rtol=RTOL)
 
 
+# shapes: ~100 droplets per SNP (some SNP beyond 128: the general kernel), ~15 per SNP (balanced work lists, one
+# pass), ~65 per SNP (balanced work lists; with K = 2 the per-thread lists exceed one pass)
+@pytest.mark.parametrize("shape", [(400, 800, 200), (300, 3000, 150), (400, 1200, 200)])
 @pytest.mark.parametrize("K", [2, 5, 16])
-def test_mstep_bit_exact(feng, K):
-    d = small_c4(nbcs=400, nsnps=800, rbar=200)
+def test_mstep_bit_exact(feng, K, shape):
+    d = small_c4(nbcs=shape[0], nsnps=shape[1], rbar=shape[2])
     upload(feng, d, K)
     assign = noisy_init(d, K)
     feng.mstep(assign)
