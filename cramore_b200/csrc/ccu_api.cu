@@ -61,6 +61,7 @@ ccu::DemuxDev dev_view(const ccu_handle* h) {
   d.nbcs = h->nbcs;
   d.nnz = h->nnz;
   d.nreads = h->nreads;
+  d.ngen = h->ngen;
   d.cell_ptr = h->d_cell_ptr.as<int64_t>();
   d.snp_idx = h->d_snp_idx.as<int32_t>();
   d.read_ptr = h->d_read_ptr.as<int64_t>();

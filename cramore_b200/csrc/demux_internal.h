@@ -46,6 +46,7 @@ struct DemuxDev {
   const uint8_t* has_gp;   // [nsnps]
   // droplet store
   int64_t nbcs, nnz, nreads;
+  int64_t ngen;            // entries with two or more informative reads (counted at upload)
   const int64_t* cell_ptr;
   const int32_t* snp_idx;
   const int64_t* read_ptr;

@@ -257,14 +257,16 @@ __global__ void __launch_bounds__(256)
 // reduction.  The Phred tables sit in shared memory.  Rows are staged through shared memory so
 // that the warp writes each one as a contiguous run.  Only general entries are processed unless
 // `all_entries` is set (ccu_demux_get_tiles).
-constexpr int kTileWarps = 8;
+constexpr int kTileWarps = 4;   // 96 registers: 5 CTAs of 4 warps per SM (8-warp CTAs fit twice)
+constexpr int kTileOcc = 5;
 
 template <int GL>
-__global__ void __launch_bounds__(kTileWarps * 32)
+__global__ void __launch_bounds__(kTileWarps * 32, kTileOcc)
     demux_tile_kernel(int64_t nnz, const int64_t* __restrict__ read_ptr, const uint8_t* __restrict__ al,
                       const uint8_t* __restrict__ bq, int nA, const double* __restrict__ ptab,
                       const double* __restrict__ phred, const uint8_t* __restrict__ eclass, int all_entries,
-                      const int32_t* __restrict__ tslot, double* __restrict__ tiles, double* __restrict__ vaff) {
+                      const int32_t* __restrict__ tslot, double* __restrict__ tiles, double* __restrict__ vaff,
+                      unsigned long long* __restrict__ next_batch, int batch) {
   constexpr int EPW = 32 / GL;  // entries per warp per pass
   __shared__ double s_err[256];
   __shared__ double s_mat[256];
@@ -289,8 +291,17 @@ __global__ void __launch_bounds__(kTileWarps * 32)
 
   // A warp looks at 32 entries at a time (one coalesced read of their classes) and works only on those that need
   // a full tile, EPW of them per pass: with sparse single-cell data that is one entry in two thousand.
-  const int64_t warps_total = (int64_t)gridDim.x * kTileWarps;
-  for (int64_t base = ((int64_t)blockIdx.x * kTileWarps + warp) * 32; base < nnz; base += warps_total * 32) {
+  // The cost of an entry is its read count (hundreds on a hot SNP, a dependent chain per read), so the warps do not
+  // own fixed slices: each takes the next batch of `batch` 32-entry groups from a global counter when it is done
+  // (a static split left 12 % of the warp slots busy on skewed coverage: every CTA waited for its deepest entry).
+  for (;;) {
+    unsigned long long b0 = 0;
+    if (lane == 0) b0 = atomicAdd(next_batch, 1ull);
+    b0 = __shfl_sync(0xffffffffu, b0, 0);
+    const int64_t first = (int64_t)b0 * batch * 32;
+    if (first >= nnz) break;
+    const int64_t last = min(nnz, first + (int64_t)batch * 32);
+  for (int64_t base = first; base < last; base += 32) {
     const int64_t el = base + lane;
     unsigned todo = __ballot_sync(0xffffffffu, (el < nnz) && (all_entries || eclass[el] != 0));
     while (todo != 0u) {
@@ -381,6 +392,7 @@ __global__ void __launch_bounds__(kTileWarps * 32)
     __syncwarp();
     }
   }
+  }
 }
 
 // ---- input check: the droplet store is caller data and every later kernel indexes with it.  bit 0: cell_ptr is
@@ -446,7 +458,8 @@ cudaError_t launch_tile(const DemuxDev& d, bool all_entries, void* scan_tmp, siz
     if (scan_need) *scan_need = need;
     return cudaSuccess;
   }
-  cudaError_t e0 = cudaMemsetAsync(d.maxbq, 0, sizeof(int32_t), st);
+  // maxbq[0] and, in the same 16-byte buffer, the tile kernel's batch counter
+  cudaError_t e0 = cudaMemsetAsync(d.maxbq, 0, 16, st);
   if (e0 != cudaSuccess) return e0;
   if (d.nnz == 0) return cudaSuccess;
   {
@@ -461,13 +474,18 @@ cudaError_t launch_tile(const DemuxDev& d, bool all_entries, void* scan_tmp, siz
   }
   int gl = 2;
   while (gl < d.nA) gl <<= 1;
-  int64_t per_block = (int64_t)kTileWarps * 32;
+  // persistent warps (kTileOcc CTAs of kTileWarps per SM) fed from a counter; batches of 32-entry groups: one group where a
+  // sizeable share of the entries needs a tile, 32 groups where hardly any does (fewer trips to the counter)
+  const int batch = (all_entries || d.ngen * 64 > d.nnz) ? 1 : 32;
+  int64_t per_block = (int64_t)kTileWarps * 32 * batch;
   int64_t blocks = (d.nnz + per_block - 1) / per_block;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148 * kTileOcc) blocks = 148 * kTileOcc;
+  unsigned long long* next_batch = reinterpret_cast<unsigned long long*>(d.maxbq) + 1;
 #define CCU_TILE(GL)                                                                                 \
   demux_tile_kernel<GL><<<(unsigned)blocks, kTileWarps * 32, 0, st>>>(d.nnz, d.read_ptr, d.al, d.bq, d.nA, d.ptab, \
                                                                        d.phred, d.eclass, all_entries ? 1 : 0,      \
-                                                                       all_entries ? nullptr : d.tslot, d.tiles, d.vaff)
+                                                                       all_entries ? nullptr : d.tslot, d.tiles, d.vaff, \
+                                                                       next_batch, batch)
   switch (gl) {
     case 2: CCU_TILE(2); break;
     case 4: CCU_TILE(4); break;
