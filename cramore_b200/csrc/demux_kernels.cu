@@ -252,146 +252,144 @@ __global__ void __launch_bounds__(256)
   if (lane == 0 && qmax > 0) atomicMax(maxbq, qmax);  // bounds the smallest single-read factor for K2
 }
 
-// K1b: the full 9 x nAlpha tile.  GL lanes cooperate on one entry, lane n owning the 9 values of
-// alpha[n]; the running maximum over all 9*nA values (:686-687, :711-712) is a group shuffle
-// reduction.  The Phred tables sit in shared memory.  Rows are staged through shared memory so
-// that the warp writes each one as a contiguous run.  Only general entries are processed unless
-// `all_entries` is set (ccu_demux_get_tiles).
-constexpr int kTileWarps = 4;   // 96 registers: 5 CTAs of 4 warps per SM (8-warp CTAs fit twice)
-constexpr int kTileOcc = 5;
+// K1b: the full 9 x nAlpha tile of the entries with two or more informative reads (every entry when `all_entries`
+// is set: ccu_demux_get_tiles).  One entry per warp at a time: its 9 * nA values are spread over the 32 lanes (NS
+// per lane), so the per-read chain -- 9 * nA multiply-adds, the running maximum over all of them (:686-687), 9 * nA
+// divisions by it (:692-699) -- costs NS multiply-adds, one warp-wide maximum and NS divisions per lane, and a
+// warp's trip count is the read count of ITS entry (a lane-per-alpha layout with two entries per warp ran
+// max(reads) trips on 11 of 16 lanes).  The maximum of non-negative doubles is the maximum of their bit patterns:
+// two integer warp reductions (REDUX) on the high and low words.  The reads of an entry are fetched 32 at a time,
+// one per lane, and handed round by shuffles; the Phred tables sit in shared memory (err / 3 precomputed: the same
+// IEEE division the reference does per read).  Rows are staged through shared memory so that the warp writes each
+// one as a contiguous run.
+//
+// The cost of an entry is its read count (hundreds on a hot SNP), so the warps do not own fixed slices: each takes
+// the next batch of `batch` 32-entry groups from a global counter when it is done (a static split left 12 % of the
+// warp slots busy on skewed coverage: every CTA waited for its deepest entry).
+constexpr int kTileWarps = 4;
+constexpr int kTileOcc = 8;
 
-template <int GL>
+template <int NS>
 __global__ void __launch_bounds__(kTileWarps * 32, kTileOcc)
     demux_tile_kernel(int64_t nnz, const int64_t* __restrict__ read_ptr, const uint8_t* __restrict__ al,
                       const uint8_t* __restrict__ bq, int nA, const double* __restrict__ ptab,
                       const double* __restrict__ phred, const uint8_t* __restrict__ eclass, int all_entries,
                       const int32_t* __restrict__ tslot, double* __restrict__ tiles, double* __restrict__ vaff,
                       unsigned long long* __restrict__ next_batch, int batch) {
-  constexpr int EPW = 32 / GL;  // entries per warp per pass
-  __shared__ double s_err[256];
+  __shared__ double s_err3[256];
   __shared__ double s_mat[256];
-  __shared__ double s_out[kTileWarps][EPW * GL * kTileStride];
+  __shared__ double s_out[kTileWarps][CCU_MAX_ALPHA * kTileStride];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-    s_err[i] = phred[i];
+    s_err3[i] = phred[i] / 3.0;  // :666-667
     s_mat[i] = phred[256 + i];
   }
   __syncthreads();
 
+  constexpr uint32_t kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = lane % GL;   // alpha index
-  const int sub = lane / GL; // entry within the warp pass
-  const bool has_alpha = n < nA;
-  double p[9], omp[9];
+  const int nval = 9 * nA;
+  double p[NS], omp[NS];
+  int opos[NS];  // where the value goes in the staged row: alpha * kTileStride + (l, m)
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    p[t] = has_alpha ? ptab[n * 9 + t] : 0.0;
-    omp[t] = has_alpha ? ptab[nA * 9 + n * 9 + t] : 0.0;
+  for (int s = 0; s < NS; ++s) {
+    const int vi = s * 32 + lane;
+    const bool ok = vi < nval;
+    p[s] = ok ? ptab[vi] : 0.0;
+    omp[s] = ok ? ptab[nval + vi] : 0.0;
+    opos[s] = ok ? (vi / 9) * kTileStride + vi % 9 : -1;
   }
   const int rowlen = nA * kTileStride;
+  double* out = s_out[warp];
 
-  // A warp looks at 32 entries at a time (one coalesced read of their classes) and works only on those that need
-  // a full tile, EPW of them per pass: with sparse single-cell data that is one entry in two thousand.
-  // The cost of an entry is its read count (hundreds on a hot SNP, a dependent chain per read), so the warps do not
-  // own fixed slices: each takes the next batch of `batch` 32-entry groups from a global counter when it is done
-  // (a static split left 12 % of the warp slots busy on skewed coverage: every CTA waited for its deepest entry).
   for (;;) {
     unsigned long long b0 = 0;
     if (lane == 0) b0 = atomicAdd(next_batch, 1ull);
-    b0 = __shfl_sync(0xffffffffu, b0, 0);
+    b0 = __shfl_sync(kFull, b0, 0);
     const int64_t first = (int64_t)b0 * batch * 32;
     if (first >= nnz) break;
     const int64_t last = min(nnz, first + (int64_t)batch * 32);
-  for (int64_t base = first; base < last; base += 32) {
-    const int64_t el = base + lane;
-    unsigned todo = __ballot_sync(0xffffffffu, (el < nnz) && (all_entries || eclass[el] != 0));
-    while (todo != 0u) {
-    const unsigned bit = __fns(todo, 0, sub + 1);  // the sub-th entry still to do (0xffffffff: none)
-    const bool valid = bit != 0xffffffffu;
-    const int64_t e = base + (valid ? (int)bit : 0);
+    for (int64_t base = first; base < last; base += 32) {
+      const int64_t el = base + lane;
+      unsigned todo = __ballot_sync(kFull, (el < nnz) && (all_entries || eclass[el] != 0));
+      while (todo != 0u) {
+        const int64_t e = base + (__ffs(todo) - 1);
+        todo &= todo - 1;
+        const int64_t r0 = read_ptr[e];
+        const int cnt = (int)(read_ptr[e + 1] - r0);
+        double v[NS];
 #pragma unroll
-    for (int i = 0; i < EPW; ++i) todo &= todo - 1;
-    int64_t r0 = 0;
-    int cnt = 0;
-    if (valid) {
-      r0 = read_ptr[e];
-      cnt = (int)(read_ptr[e + 1] - r0);
-    }
-    int maxcnt = cnt;
+        for (int s = 0; s < NS; ++s) v[s] = 1.0;  // :657
+        for (int i0 = 0; i0 < cnt; i0 += 32) {
+          const int mine = (i0 + lane < cnt) ? ((int)al[r0 + i0 + lane] | ((int)bq[r0 + i0 + lane] << 8)) : 2;
+          const int nhere = min(32, cnt - i0);
+          for (int i = 0; i < nhere; ++i) {
+            const int aq = __shfl_sync(kFull, mine, i);
+            const int a = aq & 0xff, q = aq >> 8;
+            if (a == 2) continue;  // :664 (warp-uniform)
+            const double pR = (a == 0) ? s_mat[q] : s_err3[q];  // :666
+            const double pA = (a == 1) ? s_mat[q] : s_err3[q];  // :667
+            double mx = 0.0;
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, d));
-
-    double v[9];
+            for (int s = 0; s < NS; ++s) {
+              if (opos[s] >= 0) {
+                v[s] = __dmul_rn(v[s], __dadd_rn(__dmul_rn(pR, omp[s]), __dmul_rn(pA, p[s])));  // :685
+                mx = fmax(mx, v[s]);
+              }
+            }
+            // the largest of all 9 * nA values (:686-687)
+            const unsigned hi = (unsigned)__double2hiint(mx);
+            const unsigned ghi = __reduce_max_sync(kFull, hi);
+            const unsigned glo = __reduce_max_sync(kFull, (hi == ghi) ? (unsigned)__double2loint(mx) : 0u);
+            mx = __hiloint2double((int)ghi, (int)glo);
+            // :696 -- NS IEEE divisions by one divisor: the reciprocal is refined once (div_exact.cuh; bit-identical
+            // to v / mx, which a lane takes instead whenever a value has left [2^-500, 1])
+            unsigned lo = ghi;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) v[t] = 1.0;  // :657
-
-    for (int i = 0; i < maxcnt; ++i) {
-      const bool act = i < cnt;
-      const int a = act ? al[r0 + i] : 2;
-      const int q = act ? bq[r0 + i] : 0;
-      const bool use = (a != 2);  // :664
-      double mx = 0.0;
-      if (use && has_alpha) {
-        const double pR = (a == 0) ? s_mat[q] : s_err[q] / 3.0;  // :666
-        const double pA = (a == 1) ? s_mat[q] : s_err[q] / 3.0;  // :667
+            for (int s = 0; s < NS; ++s)
+              if (opos[s] >= 0) lo = min(lo, (unsigned)__double2hiint(v[s]));
+            if (lo >= kDivLoHi) {
+              const double y = rcp_refined(mx);
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          v[t] = __dmul_rn(v[t], __dadd_rn(__dmul_rn(pR, omp[t]), __dmul_rn(pA, p[t])));  // :685
-          mx = fmax(mx, v[t]);
+              for (int s = 0; s < NS; ++s) v[s] = div_with_rcp(v[s], mx, y);
+            } else {
+#pragma unroll
+              for (int s = 0; s < NS; ++s) v[s] = v[s] / mx;
+            }
+          }
         }
-      }
+        // :704-725
+        double mx = 0.0;
 #pragma unroll
-      for (int d = GL / 2; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-      if (use && has_alpha) {  // :696 -- nine IEEE divisions by one divisor: the reciprocal is refined once
-        unsigned lo = (unsigned)__double2hiint(mx);    // (div_exact.cuh; bit-identical to v[t] / mx)
-#pragma unroll
-        for (int t = 0; t < 9; ++t) lo = min(lo, (unsigned)__double2hiint(v[t]));
-        if (lo >= kDivLoHi) {  // everything in [2^-500, 1]: a deep entry whose small values fade out takes the plain path
-          const double y = rcp_refined(mx);
-#pragma unroll
-          for (int t = 0; t < 9; ++t) v[t] = div_with_rcp(v[t], mx, y);
-        } else {
-#pragma unroll
-          for (int t = 0; t < 9; ++t) v[t] = v[t] / mx;
+        for (int s = 0; s < NS; ++s) {
+          if (opos[s] >= 0) {
+            v[s] = __dadd_rn(v[s], 1e-10);
+            mx = fmax(mx, v[s]);
+          }
         }
+        {
+          const unsigned hi = (unsigned)__double2hiint(mx);
+          const unsigned ghi = __reduce_max_sync(kFull, hi);
+          const unsigned glo = __reduce_max_sync(kFull, (hi == ghi) ? (unsigned)__double2loint(mx) : 0u);
+          mx = __hiloint2double((int)ghi, (int)glo);
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          if (opos[s] >= 0) out[opos[s]] = v[s] / mx;
+        for (int n = lane; n < nA; n += 32) out[n * kTileStride + 9] = 0.0;
+        __syncwarp();
+        if (lane == 0) {
+          double4 w;
+          w.x = out[0];
+          w.y = out[3];
+          w.z = out[6];
+          w.w = 0.0;
+          reinterpret_cast<double4*>(vaff)[e] = w;
+        }
+        double* dst = tiles + (tslot ? (int64_t)tslot[e] : e) * rowlen;
+        for (int i = lane; i < rowlen; i += 32) dst[i] = out[i];
+        __syncwarp();
       }
     }
-    // :704-725
-    double mx = 0.0;
-    if (has_alpha) {
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        v[t] = __dadd_rn(v[t], 1e-10);
-        mx = fmax(mx, v[t]);
-      }
-    }
-#pragma unroll
-    for (int d = GL / 2; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    if (has_alpha) {
-      double* o = &s_out[warp][sub * rowlen + n * kTileStride];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) o[t] = v[t] / mx;
-      o[9] = 0.0;
-      if (valid && n == 0) {
-        double4 w;
-        w.x = o[0];
-        w.y = o[3];
-        w.z = o[6];
-        w.w = 0.0;
-        reinterpret_cast<double4*>(vaff)[e] = w;
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int sb = 0; sb < EPW; ++sb) {
-      const int64_t es = __shfl_sync(0xffffffffu, e, sb * GL);
-      if (__shfl_sync(0xffffffffu, (int)valid, sb * GL)) {
-        double* dst = tiles + (tslot ? (int64_t)tslot[es] : es) * rowlen;
-        for (int i = lane; i < rowlen; i += 32) dst[i] = s_out[warp][sb * rowlen + i];
-      }
-    }
-    __syncwarp();
-    }
-  }
   }
 }
 
@@ -472,27 +470,25 @@ cudaError_t launch_tile(const DemuxDev& d, bool all_entries, void* scan_tmp, siz
     e0 = cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, d.eclass, d.tslot, (int)d.nnz, st);
     if (e0 != cudaSuccess) return e0;
   }
-  int gl = 2;
-  while (gl < d.nA) gl <<= 1;
-  // persistent warps (kTileOcc CTAs of kTileWarps per SM) fed from a counter; batches of 32-entry groups: one group where a
-  // sizeable share of the entries needs a tile, 32 groups where hardly any does (fewer trips to the counter)
+  // persistent warps (kTileOcc CTAs of kTileWarps per SM) fed from a counter; batches of 32-entry groups: one group
+  // where a sizeable share of the entries needs a tile, 32 groups where hardly any does (fewer trips to the counter)
   const int batch = (all_entries || d.ngen * 64 > d.nnz) ? 1 : 32;
   int64_t per_block = (int64_t)kTileWarps * 32 * batch;
   int64_t blocks = (d.nnz + per_block - 1) / per_block;
   if (blocks > 148 * kTileOcc) blocks = 148 * kTileOcc;
   unsigned long long* next_batch = reinterpret_cast<unsigned long long*>(d.maxbq) + 1;
-#define CCU_TILE(GL)                                                                                 \
-  demux_tile_kernel<GL><<<(unsigned)blocks, kTileWarps * 32, 0, st>>>(d.nnz, d.read_ptr, d.al, d.bq, d.nA, d.ptab, \
+  const int ns = (9 * d.nA + 31) / 32;  // values per lane
+#define CCU_TILE(NS)                                                                                 \
+  demux_tile_kernel<NS><<<(unsigned)blocks, kTileWarps * 32, 0, st>>>(d.nnz, d.read_ptr, d.al, d.bq, d.nA, d.ptab, \
                                                                        d.phred, d.eclass, all_entries ? 1 : 0,      \
                                                                        all_entries ? nullptr : d.tslot, d.tiles, d.vaff, \
                                                                        next_batch, batch)
-  switch (gl) {
-    case 2: CCU_TILE(2); break;
-    case 4: CCU_TILE(4); break;
-    case 8: CCU_TILE(8); break;
-    case 16: CCU_TILE(16); break;
-    default: CCU_TILE(32); break;
-  }
+  if (ns <= 1) CCU_TILE(1);
+  else if (ns <= 2) CCU_TILE(2);
+  else if (ns <= 3) CCU_TILE(3);
+  else if (ns <= 4) CCU_TILE(4);
+  else if (ns <= 6) CCU_TILE(6);
+  else CCU_TILE(9);
 #undef CCU_TILE
   return cudaGetLastError();
 }
