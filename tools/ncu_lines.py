@@ -11,13 +11,19 @@ from collections import defaultdict
 def main():
     rep, cubin, kern = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    short = kern.split("ILi")[0]  # template arguments are part of the mangled section name only
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + short],
+                         capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     H = rows[hdr]
     c_s, c_n, c_i = H.index("# Samples"), H.index("Warp Stall Sampling (Not-issued Samples)"), H.index("Instructions Executed")
     stall_cols = [i for i, h in enumerate(H) if h.startswith("stall_")]
     sass = rows[hdr + 1:]
+    for i, r in enumerate(sass):  # a report with several launches of the kernel: the first one
+        if r and r[0] == "Kernel Name":
+            sass = sass[:i]
+            break
     dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
     # the function's section
     lines, cur, infn = [], None, False
