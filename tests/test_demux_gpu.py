@@ -18,7 +18,12 @@ def test_genotype_mixing_bit_exact(engine):
     assert np.array_equal(engine.genotypes(), gps)
 
 
-@pytest.mark.parametrize("alphas", [[0, 0.5], [0, 0.25, 0.5], [round(0.05 * i, 2) for i in range(11)]])
+# 2, 3, 5, 9, 11, 21 and 32 alphas: 1, 1, 2, 3, 4, 6 and 9 tile values per lane in the tile kernel
+@pytest.mark.parametrize("alphas", [[0, 0.5], [0, 0.25, 0.5], [0, 0.1, 0.2, 0.35, 0.5],
+                                    [round(0.0625 * i, 4) for i in range(9)],
+                                    [round(0.05 * i, 2) for i in range(11)],
+                                    [round(0.025 * i, 3) for i in range(21)],
+                                    [round(0.5 * i / 31, 6) for i in range(32)]])
 def test_tiles_bit_exact(engine, alphas):
     d = make_dataset("C1", nbcs=50, nsnps=300, rbar=120)  # ~120 reads over 300 SNPs: multi-read entries
     d["alphas"] = np.asarray(alphas, np.float64)
