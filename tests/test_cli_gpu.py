@@ -221,7 +221,8 @@ live = pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/ref_c
 
 
 @live
-@pytest.mark.parametrize("seed", range(8))
+# CCU_LIVE_DEMUX_CASES / CCU_LIVE_FMX_CASES widen the random sweeps against the compiled reference (default 8 / 4)
+@pytest.mark.parametrize("seed", range(int(os.environ.get("CCU_LIVE_DEMUX_CASES", "8"))))
 def test_cli_demuxlet_equals_live_reference(built, tmp_path, seed):
     """`cramore demuxlet` on the GPU against the reference's own compiled engine (oracle/_ref/ref_cramore) run on the
     same files, for randomly drawn pool sizes, alpha grids, priors and error settings."""
@@ -251,7 +252,7 @@ def test_cli_demuxlet_equals_live_reference(built, tmp_path, seed):
 
 
 @live
-@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("CCU_LIVE_FMX_CASES", "4"))))
 def test_cli_freemuxlet_equals_live_reference(built, tmp_path, seed):
     from cramore_b200.synth import make_dataset
     rng = np.random.default_rng(4000 + seed)
