@@ -35,7 +35,7 @@ struct FmxState {
   DevBuf cell_ptr, snp_idx, read_ptr, al, bq, af;
   DevBuf gl, cnt, logdenom, csc_ptr, csc_cell, csc_row;
   DevBuf eclass, egen, eab, esnp, gcnt;
-  DevBuf assign, stats, cgp, cgm, llk, results, scan, scratch, flags, counter;
+  DevBuf assign, stats, cgp, cgm, llk, results, scan, scratch, flags, counter, snp_gen;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   ccu_fmx_timings tm = {};
   FmxPairs* pairs = nullptr;
@@ -59,7 +59,7 @@ struct FmxState {
     close_peers();
     ccu_fmx_pairs_release(pairs);
     DevBuf* all[] = {&cell_ptr, &snp_idx, &read_ptr, &al, &bq, &af, &gl, &cnt, &logdenom, &csc_ptr, &csc_cell,
-                     &csc_row, &eclass, &egen, &eab, &esnp, &gcnt, &assign, &stats, &cgp, &cgm, &llk, &results,
+                     &csc_row, &eclass, &egen, &eab, &esnp, &gcnt, &snp_gen, &assign, &stats, &cgp, &cgm, &llk, &results,
                      &scan, &scratch, &flags, &counter};
     for (DevBuf* b : all) b->release();
     for (auto& e : ev)
@@ -105,6 +105,7 @@ ccu::FmxDev fmx_view(const ccu_handle* h) {
   d.csc_row = f->csc_row.as<double>();
   d.assign = f->assign.as<int32_t>();
   d.stats = f->stats.as<double>();
+  d.snp_gen = f->snp_gen.as<uint8_t>();
   d.cgp = f->cgp.as<double>();
   d.cgm = f->cgm.as<double>();
   d.eclass = f->eclass.as<uint8_t>();
@@ -264,6 +265,8 @@ int ccu_fmx_upload(ccu_handle* h, int64_t nbcs, int64_t nsnps, const int64_t* ce
   CCU_CUDA(h, f->gcnt.reserve((size_t)nbcs * sizeof(int32_t) + 16));
   CCU_CUDA(h, f->counter.reserve(16));
   CCU_CUDA(h, cudaMemsetAsync(f->counter.p, 0, 16, st));
+  CCU_CUDA(h, f->snp_gen.reserve((size_t)nsnps + 16));
+  CCU_CUDA(h, cudaMemsetAsync(f->snp_gen.p, 0, (size_t)nsnps + 16, st));  // set by the compaction kernel
   if (int rc = reserve_shard_buffers(h)) return rc;
   CCU_CUDA(h, cudaMemcpyAsync(f->cell_ptr.p, cell_ptr, (nbcs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   if (nnz > 0) {

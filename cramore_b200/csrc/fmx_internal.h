@@ -10,6 +10,7 @@ namespace ccu {
 
 constexpr int kStatStride = 12;   // doubles per (cluster,SNP): gls[9], nreads, nref, nalt
 constexpr int kFmxMaxClust = 64;  // K(K+1)/2 <= 2080 pair likelihoods per droplet
+constexpr int kFmxAffineMaxK = 16;  // up to here the E-step takes single-read entries by the affine identity (rows2 kernels)
 // SNP-major rows of the M-step: 80 bytes, 16-byte aligned; the read counts of an entry take 21 bits each
 // (ccu_fmx_upload refuses a (droplet, SNP) entry with 2^21 reads or more)
 constexpr int kCscRow = 10;
@@ -55,6 +56,8 @@ struct FmxDev {
   double2* eab;              // [nnz]
   int32_t* esnp;             // [nnz]
   int32_t* gcnt;             // [nbcs]
+  uint8_t* snp_gen;          // [nsnps] 1 = some droplet has a general entry at the SNP (the only SNPs whose posterior
+                             //         TRIPLES the E-step for K <= kFmxAffineMaxK reads; the others need the mean genotype)
   // SNP-major copy for the M-step
   int64_t* csc_ptr;          // [nsnps+1]
   int32_t* csc_cell;         // [nnz] droplet id, ascending inside a SNP
