@@ -711,6 +711,10 @@ def measure_fmx(ctx, iters=10):
                "matches_single_gpu": ok, "single_gpu_ms_per_iter_wall": single_ms,
                "speedup_vs_single_gpu_wall": (single_ms / res[forms[0]]["ms_per_iter"]) if single_ms else None,
                "posterior_exchange_bytes": int(post.numel() * 8), "stats_allreduce_bytes_once": int(stats.numel() * 8),
+               # push form, per rank and iteration: its slab's mean genotypes (8 B per SNP and cluster) to every peer, and
+               # posterior triples only at SNPs with an entry of >= 2 reads (at most one SNP per such entry)
+               "push_bytes_per_rank_per_iter": int((world - 1) / world * K * (8 * d["nsnps"] + 24 * min(n_gen, d["nsnps"])))
+               if K <= 16 else int((world - 1) / world * K * 32 * d["nsnps"]),
                "setup": setup, "upload_s": t_upload, "roofline_fmx": roof, "gpu_launches": launches,
                "singlets": int((full["type"] == 0).sum()), "doublets": int((full["type"] == 1).sum())}
     graphs.clear()
