@@ -256,7 +256,11 @@ int ccu_fmx_estep_post_dev(ccu_handle* h);
  *   ccu_fmx_mstep_fused_dev  M-step of this shard's SNP slab; the kernel forms the genotype posteriors (and their mean
  *                            genotypes) of the slab from the registers that hold the finished statistics -- with the
  *                            genotype-error mix of cmd_cram_freemuxlet.cpp:485-489 iff apply_geno_error_next, i.e. the
- *                            flag of the E-step that FOLLOWS -- and stores them into the arrays of every rank;
+ *                            flag of the E-step that FOLLOWS -- and stores them into its own arrays and, of them, what
+ *                            the peers' E-step reads into the arrays of every other rank: the mean genotypes, and the
+ *                            posterior triples at the SNPs where some droplet has an entry with two or more reads
+ *                            (every SNP when K > 16).  After a fused loop with peers a rank's posterior array is
+ *                            therefore complete for its own slab only; the statistics are the loop's output;
  *                            want_stats = 0 skips the 96-byte statistics records (only the output after the last
  *                            iteration reads them)
  *   ccu_fmx_estep_fused_dev  E-step + decision of this shard's droplets; the decision kernel stores the new
