@@ -401,7 +401,8 @@ def test_peer_wait_times_out_instead_of_hanging(built, tmp_path):
 
 
 @pytest.mark.parametrize("nhandles", [2, 3])
-def test_in_process_multi_handle_em_is_bitwise_single(built, nhandles):
+@pytest.mark.parametrize("K", [6, 20])  # 20: every entry by the bilinear form, so the peers get every posterior triple
+def test_in_process_multi_handle_em_is_bitwise_single(built, nhandles, K):
     """ccu_fmx_run_em_multi -- one host thread per handle, push kernels and the flag barrier between handles of ONE
     process -- with several handles on this box's GPU (on a multi-GPU box: one per device): results and the stitched
     cluster pileups are bit-identical to the single-handle loop."""
@@ -409,7 +410,7 @@ def test_in_process_multi_handle_em_is_bitwise_single(built, nhandles):
     from cramore_b200 import FreemuxEngine
     from cramore_b200.engine import run_em_multi
     ndev = torch.cuda.device_count()
-    K, NITER = 6, 5
+    NITER = 5
     d = make_dataset("C4", nbcs=500, nsnps=2500, rbar=120, nv=6)
     init = (d["s1"] % K).astype(np.int32)
     init[d["is_dbl"]] = -1
