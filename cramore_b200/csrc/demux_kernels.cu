@@ -656,6 +656,17 @@ cudaError_t launch_singlet_to_dbg(const DemuxDev& d, double* llk_dbg, int64_t c0
 #ifndef CCU_SCA1
 #define CCU_SCA1 32
 #endif
+// Consumer groups out of step (TK == 1 only).  The 16 consumer warps form two groups of eight by k half -- two
+// warps of each group on every SM sub-partition -- and group 1 stays at least CCU_LAG chunks behind the warps of
+// group 0 that share its sub-partition, so that the integer work of one group's item epilogue and its ring
+// hand-overs issue under the other group's DFMAs instead of all sixteen warps leaving the FP64 pipe together.
+// 0 = all warps in step (one block-wide barrier per general chunk).
+#ifndef CCU_LAG
+#define CCU_LAG 0
+#endif
+#ifndef CCU_SC1
+#define CCU_SC1 8   // SNPs per general chunk at TK == 1 (4 halves the T buffers: room for a deeper ring)
+#endif
 constexpr int kNSWanted = CCU_NS;                   // raw ring stages (fewer where shared memory is short)
 constexpr int kTJ = 2;                              // samples j per thread
 constexpr int kConsumers = kScoreThreads;           // 16 consumer warps
@@ -669,6 +680,10 @@ static_assert(kScoreThreads == 512, "thread mapping below assumes 16 consumer wa
 
 __device__ __forceinline__ void consumer_bar() {
   asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+}
+__device__ __forceinline__ void group_bar(int grp) {  // one of the two consumer groups (CCU_LAG > 0)
+  if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(kConsumers / 2) : "memory");
+  else asm volatile("bar.sync 2, %0;" ::"n"(kConsumers / 2) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -684,9 +699,10 @@ struct ChunkMeta {   // published by the producer with each ring stage
 
 template <int AC, int TK>
 struct ScoreCfg {
-  static constexpr int SC = (TK >= 8) ? 4 : 8;  // SNPs per general chunk (bounded by shared memory)
+  static constexpr int SC = (TK >= 8) ? 4 : (TK == 1) ? CCU_SC1 : 8;  // SNPs per general chunk (bounded by shared memory)
   static constexpr int SCA = (TK == 1) ? CCU_SCA1 : (TK <= 4) ? 16 : 8;  // entries per affine chunk
   static constexpr int NCOL = AC * TK;
+  static constexpr int LAG = (TK == 1) ? CCU_LAG : 0;  // chunks group 1 stays behind group 0 (0: one group)
   static constexpr int TROW0 = NCOL * 3;
   // row stride (doubles) of a thread's T block: even, and (stride/2) odd => the 8 distinct
   // 16-byte segments a warp reads per LDS.128 fall into distinct bank groups
@@ -712,14 +728,27 @@ struct ScoreCfg {
   static constexpr int OFF_ALPHA = OFF_META + META_BYTES;
   static constexpr int OFF_BAR = OFF_ALPHA + ALPHA_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 2 * NS * 8 + 16;
-  // T-compute task split: NG alpha groups per (SNP slot, k) pair, APT alphas per task
+  // T-compute task split: NG alpha groups per (SNP slot, k) pair, APT alphas per task.  TTHREADS threads share
+  // TPAIRS pairs (a consumer group builds the rows of its own k half when the groups run out of step); NG is the
+  // divisor of AC that needs the fewest alpha evaluations per thread, rounds counted whole.
   static constexpr int PAIRS = SC * KT;
-  static constexpr int NG = (PAIRS >= kConsumers) ? 1 : (kConsumers / PAIRS);
+  static constexpr int TTHREADS = (LAG > 0) ? kConsumers / 2 : kConsumers;
+  static constexpr int TPAIRS = (LAG > 0) ? PAIRS / 2 : PAIRS;
+  static constexpr int t_cost(int ng) { return ((TPAIRS * ng + TTHREADS - 1) / TTHREADS) * (AC / ng); }
+  static constexpr int pick_ng() {
+    int best = 1;
+    for (int ng = 2; ng <= AC; ++ng)
+      if (AC % ng == 0 && (ng & (ng - 1)) == 0 && t_cost(ng) < t_cost(best)) best = ng;  // power-of-two decode first
+    for (int ng = 2; ng <= AC; ++ng)
+      if (AC % ng == 0 && t_cost(ng) < t_cost(best)) best = ng;
+    return best;
+  }
+  static constexpr int NG = pick_ng();
   static constexpr int APT = AC / NG;
   static_assert(NCOL % 2 == 0, "columns are processed in pairs");
   static_assert(TROW % 2 == 0, "16-byte aligned T rows");
   static_assert(AC % NG == 0, "alpha groups must divide the chunk");
-  static_assert((KT & (KT - 1)) == 0 && (NG & (NG - 1)) == 0, "power-of-two task decode");
+  static_assert((KT & (KT - 1)) == 0, "power-of-two task decode");
   static_assert(STAGE_BYTES % 16 == 0 && OFF_T % 16 == 0, "bulk copy alignment");
   static_assert(sizeof(ChunkMeta) == 32, "ChunkMeta layout");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -753,6 +782,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
   // zero the ring once (partial k-tiles / alpha chunks leave their tail untouched)
   for (int i = tid; i < kNS * Cfg::STAGE_BYTES / 8; i += kScoreBlock) reinterpret_cast<double*>(raw)[i] = 0.0;
   if (tid < 48) s_alpha[tid] = (tid < d.nA) ? d.alpha[tid] : 0.0;
+  if (tid < kConsumers / 32) reinterpret_cast<int*>(smem + Cfg::OFF_RED)[tid] = 0;
   if (tid == 0) {
     for (int s = 0; s < kNS; ++s) {
       mbar_init(smem_u32(&full[s]), 1);
@@ -848,20 +878,34 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
 
   // ======================= consumer warps =======================
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
-  const int kidx = (warp & 3) * 8 + (lane & 7);  // k-lane 0..31
-  const int jg = (warp >> 2) * 4 + (lane >> 3);  // j-group 0..15
+  // Warps w, w+4, w+8, w+12 share an SM sub-partition.  In step (LAG == 0) they share the k-lanes and differ in j;
+  // out of step they share the j-groups and differ in k, so that a group (k half = warp >> 3) owns its T rows.
+  constexpr int kLag = Cfg::LAG;
+  const int kidx = (kLag > 0) ? (warp >> 2) * 8 + (lane & 7) : (warp & 3) * 8 + (lane & 7);   // k-lane 0..31
+  const int jg = (kLag > 0) ? (warp & 3) * 4 + (lane >> 3) : (warp >> 2) * 4 + (lane >> 3);   // j-group 0..15
+  // the group is read through a lane-0 broadcast so that the compiler knows it is warp-uniform: a branch on a
+  // value derived from threadIdx counts as divergent, and behind one the alphas of the pair loop no longer travel
+  // as uniform-register operands (25.5 ms instead of 20.1 on C2)
+  const int warp_u = (kLag > 0) ? __shfl_sync(0xffffffffu, warp, 0) : 0;
+  const int cgrp = warp_u >> 3;
+  volatile int* prog = reinterpret_cast<volatile int*>(smem + Cfg::OFF_RED);  // chunks finished, per warp of group 0
 
   // T[s][klane][(kk*AC + a)*3 + l] = sum_m g_k[m] * pG[a][l][m]
   auto compute_T = [&](int cnt, int stage, int tb) {
     double* T = Tbuf + tb * (Cfg::T_BYTES / 8);
     const unsigned char* st = raw + stage * Cfg::STAGE_BYTES;
+    // out of step: a group builds the rows of its own k half with its own 256 threads
+    constexpr int kThreadsT = Cfg::TTHREADS;
+    constexpr int kKTg = (kLag > 0) ? Cfg::KT / 2 : Cfg::KT;
+    constexpr int kTasks = Cfg::TPAIRS * Cfg::NG;
+    const int tidg = (kLag > 0) ? (tid & (kConsumers / 2 - 1)) : tid;
 #pragma unroll
-    for (int u0 = 0; u0 < Cfg::PAIRS * Cfg::NG; u0 += kConsumers) {
-      const int u = u0 + tid;
-      const int grp = u & (Cfg::NG - 1);
+    for (int u0 = 0; u0 < kTasks; u0 += kThreadsT) {
+      const int u = u0 + tidg;
+      const int grp = u % Cfg::NG;
       const int pr = u / Cfg::NG;
-      const int kabs = pr & (Cfg::KT - 1);
-      const int s = pr / Cfg::KT;
+      const int kabs = (pr & (kKTg - 1)) + cgrp * kKTg;
+      const int s = (u < kTasks) ? pr / kKTg : kSC;  // past the last task of a ragged round: no SNP slot
       if (s < cnt) {
         const unsigned char* slot = st + s * Cfg::SLOT_BYTES;
         const double* gk = reinterpret_cast<const double*>(slot + Cfg::GJ_BYTES) + kabs * 3;
@@ -1097,47 +1141,123 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
         emax = max(emax, e);
       }
     }
-    // pass 2: sum of w * m * 2^(e - emax) and the thread's top-2 (scan order = increasing pos); branch-free,
-    // two interleaved partial sums
-    double la0 = 0.0, la1 = 0.0;
-    double bm1 = 0.0, bm2 = 0.0;
-    int be1 = INT_MIN, be2 = INT_MIN, bt1 = -1, bt2 = -1;  // t = jj*NCOL + cc
-#pragma unroll
-    for (int jj = 0; jj < kTJ; ++jj) {
-#pragma unroll
-      for (int cc = 0; cc < Cfg::NCOL; ++cc) {
-        const double m = acc[jj][cc];
-        const int e = aex[jj][cc];
-        const double w = ((half_mask >> (n0 + cc % AC)) & 1u) ? whalf[jj][cc / AC] : 1.0;
-        if (cc & 1) la1 = fma(w * m, pow2_nonpos(e - emax), la1);
-        else la0 = fma(w * m, pow2_nonpos(e - emax), la0);
-        const bool gt1 = (e > be1) || (e == be1 && m > bm1);  // empty products carry e = kLseEmpty > INT_MIN
-        const bool gt2 = (e > be2) || (e == be2 && m > bm2);
-        bm2 = gt1 ? bm1 : (gt2 ? m : bm2);
-        be2 = gt1 ? be1 : (gt2 ? e : be2);
-        bt2 = gt1 ? bt1 : (gt2 ? (jj * Cfg::NCOL + cc) : bt2);
-        bm1 = gt1 ? m : bm1;
-        be1 = gt1 ? e : be1;
-        bt1 = gt1 ? (jj * Cfg::NCOL + cc) : bt1;
-      }
-    }
-    double la = la0 + la1;
-    int le = (la > 0.0) ? emax : kLseEmpty;
     auto pos_of = [&](int t) {
       const int jj = t / Cfg::NCOL, cc = t - jj * Cfg::NCOL;
       return ((j0 + jg * kTJ + jj) * d.nv + (k0 + kidx * TK + cc / AC)) * d.nA + n0 + cc % AC;
     };
+    double la;
+    int le;
     Cand b1, b2;
-    b1.m = bm1; b1.e = (bm1 > 0.0) ? be1 : INT_MIN; b1.pos = (bm1 > 0.0) ? pos_of(bt1) : -1;
-    b2.m = bm2; b2.e = (bm2 > 0.0) ? be2 : INT_MIN; b2.pos = (bm2 > 0.0) ? pos_of(bt2) : -1;
+    // pass 2, fast form.  With the WARP's largest exponent E known first (one REDUX), every product becomes the plain
+    // double x = m * 2^(e - E) by an integer add on its high word (0 below 2^-1022 of the largest: nothing in the
+    // sum), and order by x is order by (e, m).  So the sum is a chain of DFMAs reduced by plain adds, the thread's
+    // top-2 a chain of compares on doubles, and the warp's top-2 two arg-max rounds of three REDUX each (high word,
+    // low word, smallest position among equals) instead of five shuffle rounds over two (m, e, pos) candidates:
+    // 2.15 -> ~1.2 ms of C2's 20.1 ms went to this epilogue, most of it latency of the old chains.
+    // Exactness: x is exact for every product it does not flush, ties are broken as before (scan order inside a
+    // thread, position across threads); when a live product was flushed AND the warp shows fewer than two visible
+    // candidates, the exact (m, e) form below runs instead (a droplet whose best hypothesis leads every other one of
+    // the warp by more than 708 nats).
+    const int Emax = __reduce_max_sync(kFull, emax);
+    bool need_exact;
+    {
+      double s0 = 0.0, s1 = 0.0, v1 = 0.0, v2 = 0.0;
+      int t1 = 0, t2 = 0;
+      bool lost = false;
 #pragma unroll
-    for (int dd = 16; dd >= 1; dd >>= 1) {
-      const double oa = __shfl_xor_sync(kFull, la, dd);
-      const int oe = __shfl_xor_sync(kFull, le, dd);
-      lse_add(la, le, oa, oe);
-      const Cand o1 = cand_shfl_xor(b1, dd), o2 = cand_shfl_xor(b2, dd);
-      cand_insert(b1, b2, o1);
-      cand_insert(b1, b2, o2);
+      for (int jj = 0; jj < kTJ; ++jj) {
+#pragma unroll
+        for (int cc = 0; cc < Cfg::NCOL; ++cc) {
+          const double m = acc[jj][cc];
+          const int e = aex[jj][cc];
+          const int dd = e - Emax;  // <= 0; empty products carry e = kLseEmpty and m = 0
+          const bool vis = dd >= -1022;
+          lost = lost || (!vis && e != kLseEmpty);
+          const double x = vis ? __hiloint2double(__double2hiint(m) + dd * (1 << 20), __double2loint(m)) : 0.0;
+          const double w = ((half_mask >> (n0 + cc % AC)) & 1u) ? whalf[jj][cc / AC] : 1.0;
+          if (cc & 1) s1 = fma(w, x, s1);
+          else s0 = fma(w, x, s0);
+          const int t = jj * Cfg::NCOL + cc;
+          const bool g1 = x > v1;
+          const double mn = g1 ? v1 : x;
+          const int tn = g1 ? t1 : t;
+          v1 = g1 ? x : v1;
+          t1 = g1 ? t : t1;
+          const bool g2 = mn > v2;
+          v2 = g2 ? mn : v2;
+          t2 = g2 ? tn : t2;
+        }
+      }
+      la = s0 + s1;
+#pragma unroll
+      for (int dd = 16; dd >= 1; dd >>= 1) la += __shfl_xor_sync(kFull, la, dd);
+      le = (la > 0.0) ? Emax : kLseEmpty;
+      // warp arg-max, twice: the winner hands its second value up
+      auto warp_pick = [&](Cand& out) {
+        const uint32_t hi = (uint32_t)__double2hiint(v1), lo = (uint32_t)__double2loint(v1);
+        const uint32_t H = __reduce_max_sync(kFull, hi);
+        const uint32_t L = __reduce_max_sync(kFull, (hi == H) ? lo : 0u);
+        const bool own = (hi == H) && (lo == L) && ((H | L) != 0u);
+        const uint32_t mypos = own ? (uint32_t)pos_of(t1) : 0xffffffffu;
+        const uint32_t P = __reduce_min_sync(kFull, mypos);
+        if (own && mypos == P) {  // at most one lane: positions are unique
+          v1 = v2;
+          t1 = t2;
+          v2 = 0.0;
+        }
+        if ((H | L) != 0u) {
+          out.m = __hiloint2double((int)((H & 0x000fffffu) | 0x3ff00000u), (int)L);
+          out.e = Emax + (int)(H >> 20) - 1023;
+          out.pos = (int)P;
+        } else {
+          out = cand_empty();
+        }
+      };
+      warp_pick(b1);
+      warp_pick(b2);
+      need_exact = __any_sync(kFull, lost) && b2.pos < 0;
+#ifdef CCU_EPI_EXACT  // test builds: always the exact form
+      need_exact = true;
+#endif
+    }
+    if (need_exact) {
+      // pass 2, exact form: sum of w * m * 2^(e - emax) and the thread's top-2 (scan order = increasing pos); branch-free,
+      // two interleaved partial sums
+      double la0 = 0.0, la1 = 0.0;
+      double bm1 = 0.0, bm2 = 0.0;
+      int be1 = INT_MIN, be2 = INT_MIN, bt1 = -1, bt2 = -1;  // t = jj*NCOL + cc
+#pragma unroll
+      for (int jj = 0; jj < kTJ; ++jj) {
+#pragma unroll
+        for (int cc = 0; cc < Cfg::NCOL; ++cc) {
+          const double m = acc[jj][cc];
+          const int e = aex[jj][cc];
+          const double w = ((half_mask >> (n0 + cc % AC)) & 1u) ? whalf[jj][cc / AC] : 1.0;
+          if (cc & 1) la1 = fma(w * m, pow2_nonpos(e - emax), la1);
+          else la0 = fma(w * m, pow2_nonpos(e - emax), la0);
+          const bool gt1 = (e > be1) || (e == be1 && m > bm1);  // empty products carry e = kLseEmpty > INT_MIN
+          const bool gt2 = (e > be2) || (e == be2 && m > bm2);
+          bm2 = gt1 ? bm1 : (gt2 ? m : bm2);
+          be2 = gt1 ? be1 : (gt2 ? e : be2);
+          bt2 = gt1 ? bt1 : (gt2 ? (jj * Cfg::NCOL + cc) : bt2);
+          bm1 = gt1 ? m : bm1;
+          be1 = gt1 ? e : be1;
+          bt1 = gt1 ? (jj * Cfg::NCOL + cc) : bt1;
+        }
+      }
+      la = la0 + la1;
+      le = (la > 0.0) ? emax : kLseEmpty;
+      b1.m = bm1; b1.e = (bm1 > 0.0) ? be1 : INT_MIN; b1.pos = (bm1 > 0.0) ? pos_of(bt1) : -1;
+      b2.m = bm2; b2.e = (bm2 > 0.0) ? be2 : INT_MIN; b2.pos = (bm2 > 0.0) ? pos_of(bt2) : -1;
+#pragma unroll
+      for (int dd = 16; dd >= 1; dd >>= 1) {
+        const double oa = __shfl_xor_sync(kFull, la, dd);
+        const int oe = __shfl_xor_sync(kFull, le, dd);
+        lse_add(la, le, oa, oe);
+        const Cand o1 = cand_shfl_xor(b1, dd), o2 = cand_shfl_xor(b2, dd);
+        cand_insert(b1, b2, o1);
+        cand_insert(b1, b2, o2);
+      }
     }
     if (lane == 0) {
       ItemPartial p;
@@ -1158,10 +1278,23 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
   uint32_t gt = 0;  // general chunks seen so far (T double buffer)
   for (uint32_t g = 0;; ++g) {
     const int stage = g % kNS;
+    if constexpr (kLag > 0) {
+      // group 1 starts chunk g once the two warps of group 0 on its sub-partition have finished chunk g + kLag - 1
+      // (or the stream).  Pacing only -- nothing read below depends on it.
+      if (cgrp == 1) {
+        const int wa = warp_u & 3;
+        while (min(prog[wa], prog[wa + 4]) < (int)g + kLag) __nanosleep(40);
+      }
+    }
     mbar_wait(smem_u32(&full[stage]), (g / kNS) & 1);
     const ChunkMeta* mt = &meta[stage];
     const int cnt = mt->cnt, flags = mt->flags;
-    if (!(flags & 1)) break;
+    if (!(flags & 1)) {
+      if constexpr (kLag > 0) {
+        if (cgrp == 0 && lane == 0) prog[warp] = INT_MAX;
+      }
+      break;
+    }
     const int m_cell = mt->cell, m_j0 = mt->j0, m_k0 = mt->k0, m_n0 = mt->n0;
     const int64_t m_item = mt->item;
     // the item's global constants are fetched before its last chunk so the loads fly while it is multiplied in
@@ -1178,13 +1311,19 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
       }
       budget -= kGenBits * cnt;
       compute_T(cnt, stage, gt & 1);
-      consumer_bar();
+      if constexpr (kLag > 0) group_bar(cgrp);
+      else consumer_bar();
       main_general(cnt, stage, gt & 1);
       ++gt;
     }
     if (flags & 2) epilogue(m_cell, m_j0, m_k0, m_n0, m_item);
     __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&empty[stage]));  // this warp is done with ring stage `stage`
+    if (lane == 0) {
+      mbar_arrive(smem_u32(&empty[stage]));  // this warp is done with ring stage `stage`
+      if constexpr (kLag > 0) {
+        if (cgrp == 0) prog[warp] = (int)g + 1;
+      }
+    }
   }
 }
 
