@@ -82,6 +82,17 @@ __device__ __forceinline__ void renorm(double& m, int& e) {
   }
 }
 
+// The same inside the hot loop, where only the exponent has to come down: a zero stays zero and a subnormal stays
+// what it is (every later factor is <= 1, so it ends as exactly 0 in the epilogue's full renormalisation).
+__device__ __forceinline__ void renorm_live(double& m, int& e) {
+  const int hi = __double2hiint(m);
+  const int ex = hi >> 20;  // products are non-negative: no sign bit
+  if (ex != 0) {
+    e += ex - 1023;
+    m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(m));
+  }
+}
+
 __device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {
   if (a.e != b.e) return a.e > b.e;
   if (a.m != b.m) return a.m > b.m;
@@ -942,7 +953,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
 #pragma unroll
     for (int jj = 0; jj < kTJ; ++jj)
 #pragma unroll
-      for (int cc = 0; cc < Cfg::NCOL; ++cc) renorm(acc[jj][cc], aex[jj][cc]);
+      for (int cc = 0; cc < Cfg::NCOL; ++cc) renorm_live(acc[jj][cc], aex[jj][cc]);
   };
   // Underflow budget (binary orders of magnitude a running product may still lose before it must
   // be renormalised).  A general factor is >= ~1e-10 (the +1e-10 floor of :704-725) = 34 bits; an
@@ -1126,7 +1137,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
     }
     const int nal = d.nA - n0;  // valid alphas of this chunk (>= AC unless the grid was padded)
     // pass 1: final (mantissa, exponent) of every product and the largest exponent (branch-free)
-    int emax = kLseEmpty;
+    int emax = kLseEmpty, nlive = 0;
 #pragma unroll
     for (int jj = 0; jj < kTJ; ++jj) {
 #pragma unroll
@@ -1135,7 +1146,9 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
         int e = aex[jj][cc] + ejk[jj][cc / AC];
         renorm(m, e);
         if ((cc % AC) >= nal) m = 0.0;
-        e = (m > 0.0) ? e : kLseEmpty;
+        const bool live = m > 0.0;
+        e = live ? e : kLseEmpty;
+        nlive += live ? 1 : 0;
         acc[jj][cc] = m;
         aex[jj][cc] = e;
         emax = max(emax, e);
@@ -1155,15 +1168,14 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
     // low word, smallest position among equals) instead of five shuffle rounds over two (m, e, pos) candidates:
     // 2.15 -> ~1.2 ms of C2's 20.1 ms went to this epilogue, most of it latency of the old chains.
     // Exactness: x is exact for every product it does not flush, ties are broken as before (scan order inside a
-    // thread, position across threads); when a live product was flushed AND the warp shows fewer than two visible
-    // candidates, the exact (m, e) form below runs instead (a droplet whose best hypothesis leads every other one of
-    // the warp by more than 708 nats).
+    // thread, position across threads); when the warp shows fewer than two visible
+    // candidates although it holds two live products or more, the exact (m, e) form below runs instead (a droplet
+    // whose best hypothesis leads every other one of the warp by more than 708 nats).
     const int Emax = __reduce_max_sync(kFull, emax);
     bool need_exact;
     {
       double s0 = 0.0, s1 = 0.0, v1 = 0.0, v2 = 0.0;
       int t1 = 0, t2 = 0;
-      bool lost = false;
 #pragma unroll
       for (int jj = 0; jj < kTJ; ++jj) {
 #pragma unroll
@@ -1171,12 +1183,14 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
           const double m = acc[jj][cc];
           const int e = aex[jj][cc];
           const int dd = e - Emax;  // <= 0; empty products carry e = kLseEmpty and m = 0
-          const bool vis = dd >= -1022;
-          lost = lost || (!vis && e != kLseEmpty);
-          const double x = vis ? __hiloint2double(__double2hiint(m) + dd * (1 << 20), __double2loint(m)) : 0.0;
-          const double w = ((half_mask >> (n0 + cc % AC)) & 1u) ? whalf[jj][cc / AC] : 1.0;
-          if (cc & 1) s1 = fma(w, x, s1);
-          else s0 = fma(w, x, s0);
+          const double x = (dd >= -1022) ? __hiloint2double(__double2hiint(m) + dd * (1 << 20), __double2loint(m)) : 0.0;
+          if ((half_mask >> (n0 + cc % AC)) & 1u) {  // warp-uniform: a predicated DFMA beside a predicated DADD
+            if (cc & 1) s1 = fma(whalf[jj][cc / AC], x, s1);
+            else s0 = fma(whalf[jj][cc / AC], x, s0);
+          } else {
+            if (cc & 1) s1 += x;
+            else s0 += x;
+          }
           const int t = jj * Cfg::NCOL + cc;
           const bool g1 = x > v1;
           const double mn = g1 ? v1 : x;
@@ -1215,7 +1229,9 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
       };
       warp_pick(b1);
       warp_pick(b2);
-      need_exact = __any_sync(kFull, lost) && b2.pos < 0;
+      // fewer than two visible candidates although the warp holds two live products or more: some were flushed
+      need_exact = false;
+      if (b2.pos < 0) need_exact = __reduce_add_sync(kFull, nlive) >= 2;
 #ifdef CCU_EPI_EXACT  // test builds: always the exact form
       need_exact = true;
 #endif
