@@ -665,7 +665,7 @@ cudaError_t launch_singlet_to_dbg(const DemuxDev& d, double* llk_dbg, int64_t c0
 #define CCU_NS 3
 #endif
 #ifndef CCU_SCA1
-#define CCU_SCA1 32
+#define CCU_SCA1 64
 #endif
 // Consumer groups out of step (TK == 1 only).  The 16 consumer warps form two groups of eight by k half -- two
 // warps of each group on every SM sub-partition -- and group 1 stays at least CCU_LAG chunks behind the warps of
