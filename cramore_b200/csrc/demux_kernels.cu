@@ -667,13 +667,17 @@ cudaError_t launch_singlet_to_dbg(const DemuxDev& d, double* llk_dbg, int64_t c0
 #ifndef CCU_SCA1
 #define CCU_SCA1 64
 #endif
-// Consumer groups out of step (TK == 1 only).  The 16 consumer warps form two groups of eight by k half -- two
-// warps of each group on every SM sub-partition -- and group 1 stays at least CCU_LAG chunks behind the warps of
-// group 0 that share its sub-partition, so that the integer work of one group's item epilogue and its ring
-// hand-overs issue under the other group's DFMAs instead of all sixteen warps leaving the FP64 pipe together.
-// 0 = all warps in step (one block-wide barrier per general chunk).
-#ifndef CCU_LAG
-#define CCU_LAG 0
+// Consumer groups out of step (the LAGP template parameter, TK == 1 only).  The 16 consumer warps form two groups of
+// eight by k half -- two warps of each group on every SM sub-partition -- and group 1 stays at least LAGP chunks
+// behind the warps of group 0 that share its sub-partition: a group builds the T rows of its own k half and meets at
+// its own barrier, so one group's T build, barrier and ring hand-over issue under the other group's DFMAs.
+// Measured (B200): general chunks gain (skewed coverage, a third of the entries general: 6.54 -> 5.81 ms with LAGP = 1
+// and a five-stage ring of 32-entry chunks), affine chunks do not (C2 within 1 %, C5 1.3 % slower, and the deeper ring
+// costs the 64-entry chunks their room) -- whatever lag and ring depth, the item epilogue was NOT hidden behind the
+// other group's products.  So the launch picks LAGP = 1 for stores with more than a tenth of
+// their entries general and 0 otherwise; CCU_LAG_MODE forces it (0 / 1) for A/B builds.
+#ifndef CCU_LAG_MODE
+#define CCU_LAG_MODE -1
 #endif
 #ifndef CCU_SC1
 #define CCU_SC1 8   // SNPs per general chunk at TK == 1 (4 halves the T buffers: room for a deeper ring)
@@ -692,7 +696,7 @@ static_assert(kScoreThreads == 512, "thread mapping below assumes 16 consumer wa
 __device__ __forceinline__ void consumer_bar() {
   asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
 }
-__device__ __forceinline__ void group_bar(int grp) {  // one of the two consumer groups (CCU_LAG > 0)
+__device__ __forceinline__ void group_bar(int grp) {  // one of the two consumer groups (LAGP > 0)
   if (grp == 0) asm volatile("bar.sync 1, %0;" ::"n"(kConsumers / 2) : "memory");
   else asm volatile("bar.sync 2, %0;" ::"n"(kConsumers / 2) : "memory");
 }
@@ -708,12 +712,13 @@ struct ChunkMeta {   // published by the producer with each ring stage
   int64_t item;
 };
 
-template <int AC, int TK>
+template <int AC, int TK, int LAGP = 0>
 struct ScoreCfg {
   static constexpr int SC = (TK >= 8) ? 4 : (TK == 1) ? CCU_SC1 : 8;  // SNPs per general chunk (bounded by shared memory)
-  static constexpr int SCA = (TK == 1) ? CCU_SCA1 : (TK <= 4) ? 16 : 8;  // entries per affine chunk
+  static constexpr int LAG = (TK == 1) ? LAGP : 0;  // chunks group 1 stays behind group 0 (0: one group)
+  static constexpr int SCA = (TK == 1) ? (LAG > 0 ? 32 : CCU_SCA1) : (TK <= 4) ? 16 : 8;  // entries per affine chunk
+  static constexpr int NSW = (LAG > 0) ? 5 : kNSWanted;  // ring stages wanted
   static constexpr int NCOL = AC * TK;
-  static constexpr int LAG = (TK == 1) ? CCU_LAG : 0;  // chunks group 1 stays behind group 0 (0: one group)
   static constexpr int TROW0 = NCOL * 3;
   // row stride (doubles) of a thread's T block: even, and (stride/2) odd => the 8 distinct
   // 16-byte segments a warp reads per LDS.128 fall into distinct bank groups
@@ -730,7 +735,7 @@ struct ScoreCfg {
   static constexpr int T_BYTES = SC * 32 * TROW * 8;
   static constexpr int RED_BYTES = (kConsumers / 32) * 64;
   static constexpr int FIXED_BYTES = 2 * T_BYTES + RED_BYTES + 48 * 8 + 64;
-  static constexpr int NS = ((kNSWanted * (STAGE_BYTES + 32 + 16) + FIXED_BYTES) <= 227 * 1024) ? kNSWanted : 3;
+  static constexpr int NS = ((NSW * (STAGE_BYTES + 32 + 16) + FIXED_BYTES) <= 227 * 1024) ? NSW : 3;
   static constexpr int META_BYTES = NS * (int)sizeof(ChunkMeta);
   static constexpr int ALPHA_BYTES = 48 * 8;
   static constexpr int OFF_T = NS * STAGE_BYTES;
@@ -772,11 +777,11 @@ struct WarpRed {
 };
 static_assert(sizeof(WarpRed) <= 64, "WarpRed slot");
 
-template <int AC, int TK>
+template <int AC, int TK, int LAGP>
 __global__ void __launch_bounds__(kScoreBlock, 1)
     demux_score_kernel(DemuxDev d, int njt, int nkt, int nac, int64_t nitems, uint32_t half_mask,
                        double2* __restrict__ dbg, int64_t dbg_c0, int64_t dbg_c1) {
-  using Cfg = ScoreCfg<AC, TK>;
+  using Cfg = ScoreCfg<AC, TK, LAGP>;
   constexpr int kSC = Cfg::SC;
   constexpr int kSCA = Cfg::SCA;
   constexpr int kNS = Cfg::NS;
@@ -1392,11 +1397,11 @@ ScorePlan make_score_plan(int nv, int nA, const double* alpha) {
   return p;
 }
 
-template <int AC, int TK>
+template <int AC, int TK, int LAGP>
 static cudaError_t launch_score_t(const DemuxDev& d, const ScorePlan& plan, int num_sms, double2* llk_dbg,
                                   int64_t c0, int64_t c1, int* grid_out, cudaStream_t st) {
-  using Cfg = ScoreCfg<AC, TK>;
-  cudaError_t err = cudaFuncSetAttribute(demux_score_kernel<AC, TK>,
+  using Cfg = ScoreCfg<AC, TK, LAGP>;
+  cudaError_t err = cudaFuncSetAttribute(demux_score_kernel<AC, TK, LAGP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
   if (err != cudaSuccess) return err;
   const int64_t nitems = d.nbcs * plan.items_per_cell;
@@ -1405,7 +1410,7 @@ static cudaError_t launch_score_t(const DemuxDev& d, const ScorePlan& plan, int 
   uint32_t half_mask = 0;
   for (int n = 0; n < d.nA && n < 32; ++n)
     if (plan.is_half[n]) half_mask |= 1u << n;
-  demux_score_kernel<AC, TK><<<grid, kScoreBlock, Cfg::SMEM_BYTES, st>>>(d, plan.njt, plan.nkt, plan.nac, nitems,
+  demux_score_kernel<AC, TK, LAGP><<<grid, kScoreBlock, Cfg::SMEM_BYTES, st>>>(d, plan.njt, plan.nkt, plan.nac, nitems,
                                                                         half_mask, llk_dbg, c0, c1);
   return cudaGetLastError();
 }
@@ -1583,10 +1588,15 @@ cudaError_t launch_score(const DemuxDev& d, const ScorePlan& plan, int num_sms, 
     return cudaGetLastError();
   }
   switch (plan.ac) {
-    case 10: return launch_score_t<10, 1>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
-    case 5: return launch_score_t<5, 2>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
-    case 2: return launch_score_t<2, 4>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
-    default: return launch_score_t<1, 8>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
+    case 10: {
+      // out-of-step consumer groups where general chunks carry weight (see CCU_LAG_MODE above)
+      const bool lag = (CCU_LAG_MODE >= 0) ? (CCU_LAG_MODE > 0) : (d.ngen * 10 > d.nnz);
+      if (lag) return launch_score_t<10, 1, 1>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
+      return launch_score_t<10, 1, 0>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
+    }
+    case 5: return launch_score_t<5, 2, 0>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
+    case 2: return launch_score_t<2, 4, 0>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
+    default: return launch_score_t<1, 8, 0>(d, plan, num_sms, llk_dbg, dbg_c0, dbg_c1, grid_out, st);
   }
 }
 
