@@ -388,7 +388,7 @@ int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const
   CCU_CUDA(h, h->d_fmat.reserve((size_t)nnz * h->nvp * sizeof(double) + 16));
   CCU_CUDA(h, h->d_pm.reserve((size_t)nbcs * h->nvp * sizeof(double) + 16));
   CCU_CUDA(h, h->d_pe.reserve((size_t)nbcs * h->nvp * sizeof(int32_t) + 16));
-  CCU_CUDA(h, h->d_maxbq.reserve(16));
+  CCU_CUDA(h, h->d_maxbq.reserve(32));  // deepest quality, the tile kernel's batch counter, K2's item counter
   CCU_CUDA(h, h->d_partials.reserve((size_t)nbcs * plan.items_per_cell * ccu::kScoreWarps * sizeof(ccu::ItemPartial) + 16));
   CCU_CUDA(h, h->d_results.reserve(nbcs * sizeof(ccu_demux_result) + 16));
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_X0], h->stream));

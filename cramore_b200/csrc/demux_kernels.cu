@@ -780,7 +780,8 @@ static_assert(sizeof(WarpRed) <= 64, "WarpRed slot");
 template <int AC, int TK, int LAGP>
 __global__ void __launch_bounds__(kScoreBlock, 1)
     demux_score_kernel(DemuxDev d, int njt, int nkt, int nac, int64_t nitems, uint32_t half_mask,
-                       double2* __restrict__ dbg, int64_t dbg_c0, int64_t dbg_c1) {
+                       double2* __restrict__ dbg, int64_t dbg_c0, int64_t dbg_c1,
+                       unsigned long long* __restrict__ next_item) {
   using Cfg = ScoreCfg<AC, TK, LAGP>;
   constexpr int kSC = Cfg::SC;
   constexpr int kSCA = Cfg::SCA;
@@ -814,9 +815,14 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
     if (warp != kConsumers / 32) return;
     const int ipc = njt * nkt * nac;
+    // Items are handed out by a global counter (the first one per CTA by its index): droplets differ in depth, and
+    // with fixed strides the whole grid waited for the CTA that drew the deepest ones.  The counter is read one item
+    // ahead, so its round trip hides behind the item being streamed.
     int64_t item = blockIdx.x;
     uint32_t g = 0;
     while (true) {
+      unsigned long long nxt = 0;
+      if (lane == 0) nxt = atomicAdd(next_item, 1ull);
       const bool valid = item < nitems;
       int32_t cell = 0, ng = 0, na = 0, nchg = 0, nch = 1, j0 = 0, k0 = 0, n0 = 1;
       int64_t ent0 = 0;
@@ -887,7 +893,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
         }
       }
       if (!valid) break;  // the chunk just published was the end-of-stream sentinel
-      item += gridDim.x;
+      item = (int64_t)gridDim.x + (int64_t)__shfl_sync(0xffffffffu, nxt, 0);
     }
     return;
   }
@@ -1410,8 +1416,12 @@ static cudaError_t launch_score_t(const DemuxDev& d, const ScorePlan& plan, int 
   uint32_t half_mask = 0;
   for (int n = 0; n < d.nA && n < 32; ++n)
     if (plan.is_half[n]) half_mask |= 1u << n;
+  // work counter of the launch: the 8 bytes behind the tile kernel's (d.maxbq: [0] deepest quality, [8] tile batches)
+  unsigned long long* next_item = reinterpret_cast<unsigned long long*>(d.maxbq) + 2;
+  err = cudaMemsetAsync(next_item, 0, sizeof(unsigned long long), st);
+  if (err != cudaSuccess) return err;
   demux_score_kernel<AC, TK, LAGP><<<grid, kScoreBlock, Cfg::SMEM_BYTES, st>>>(d, plan.njt, plan.nkt, plan.nac, nitems,
-                                                                        half_mask, llk_dbg, c0, c1);
+                                                                              half_mask, llk_dbg, c0, c1, next_item);
   return cudaGetLastError();
 }
 
