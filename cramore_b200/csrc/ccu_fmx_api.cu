@@ -113,7 +113,7 @@ ccu::FmxDev fmx_view(const ccu_handle* h) {
   d.eab = f->eab.as<double2>();
   d.esnp = f->esnp.as<int32_t>();
   d.gcnt = f->gcnt.as<int32_t>();
-  d.llk = f->llk.as<double>();
+  d.llk = nullptr;  // the pair log-likelihood matrix is written only for ccu_fmx_get_llk (which runs the E-step again)
   d.results = f->results.as<ccu_fmx_result>();
   d.scan = f->scan.as<ccu::FmxScan>();
   d.cell_begin = f->cell_begin;
@@ -167,7 +167,7 @@ int reserve_shard_buffers(ccu_handle* h) {
   FmxState* f = h->fmx;
   const int64_t ncell = f->cell_end - f->cell_begin;
   const int64_t npairs = (int64_t)f->K * (f->K + 1) / 2;
-  CCU_CUDA(h, f->llk.reserve((size_t)ncell * npairs * sizeof(double) + 16));
+  (void)npairs;  // llk[ncell][npairs] is allocated by ccu_fmx_get_llk, the only reader
   CCU_CUDA(h, f->results.reserve((size_t)ncell * sizeof(ccu_fmx_result) + 16));
   CCU_CUDA(h, f->scan.reserve((size_t)ncell * sizeof(ccu::FmxScan) + 16));
   return 0;
@@ -641,6 +641,14 @@ int ccu_fmx_get_llk(ccu_handle* h, double* llk) {
   const int64_t n = (f->cell_end - f->cell_begin) * ((int64_t)f->K * (f->K + 1) / 2);
   if (n == 0) return 0;
   CCU_CUDA(h, cudaSetDevice(h->device));
+  // Inspection only: an E-step never stores the matrix (its epilogue works on the products, not on their logs).  The
+  // E-step is run again here on the cluster posteriors as they stand -- right after ccu_fmx_estep those are the ones
+  // it used -- with the log-domain epilogue, which writes every llk[droplet][pair]; results and assignments are
+  // rewritten with the same values.
+  CCU_CUDA(h, f->llk.reserve((size_t)n * sizeof(double) + 16));
+  ccu::FmxDev d = fmx_view(h);
+  d.llk = f->llk.as<double>();
+  CCU_CUDA(h, ccu::launch_fmx_estep(d, no_peers(), make_sync(h, false), h->stream));
   CCU_CUDA(h, cudaStreamSynchronize(h->stream));
   CCU_CUDA(h, cudaMemcpy(llk, f->llk.p, n * sizeof(double), cudaMemcpyDeviceToHost));
   return 0;

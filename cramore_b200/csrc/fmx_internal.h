@@ -25,6 +25,10 @@ struct FmxScan {
   double sv1, sv2, dv1, dv2;      // best / next singlet and doublet log-likelihood
   int32_t si1, si2, di1, di2;     // cluster of the singlets, pair index j(j+1)/2+k of the doublets (INT_MAX: none)
   double ssum, asum, smax, vmax;  // sum exp(llk + prior - max) over singlets / all, and the two maxima
+  // form 1 (product domain, the fast epilogue of the row kernels): sv* / dv* are likelihoods scaled by 2^-es / 2^-ed,
+  // ssum / asum the plain sums of the scaled singlet / doublet likelihoods (no priors), smax / vmax unused; the
+  // decision kernel takes the logs.  form 0: everything above is in the log domain.
+  int32_t es, ed, form, _pad;
 };
 
 struct FmxDev {
