@@ -232,7 +232,9 @@ int ccu_fmx_mstep(ccu_handle* h, const int32_t* assign);
  * out: host [cell_end-cell_begin]; assign_out (optional): host int32 [cell_end-cell_begin], the
  * M-step input of the next iteration (jBest for confident singlets, else -1, :641-643). */
 int ccu_fmx_estep(ccu_handle* h, int32_t apply_geno_error, ccu_fmx_result* out, int32_t* assign_out);
-/* llks[pair] of the last E-step, [cells of the shard][K(K+1)/2], pair = j(j+1)/2+k (inspection). */
+/* llks[pair], [cells of the shard][K(K+1)/2], pair = j(j+1)/2+k (inspection).  An E-step does not keep the matrix: this
+ * call runs the E-step again on the cluster posteriors as they stand (right after ccu_fmx_estep: the ones it used) with
+ * the epilogue that takes every pair's log, and rewrites results and assignments with the same values. */
 int ccu_fmx_get_llk(ccu_handle* h, double* llk);
 int ccu_fmx_get_clusters(ccu_handle* h, ccu_pileup* out /* [K][nsnps] */);
 

@@ -107,6 +107,23 @@ def test_mstep_bit_exact(feng, K, shape):
     assert np.array_equal(got["gls"], ref["gls"])  # ordered, clamped fold: bit-exact
 
 
+@pytest.mark.parametrize("K", [4, 16])
+def test_estep_deep_droplets_take_the_log_form(feng, K):
+    """~2,900 covered SNPs per droplet: the next singlet lies more than 708 nats (2^-1022) below the best one, so the
+    product-domain epilogue cannot show it and must hand the droplet to the log-domain form; same results either way."""
+    d = small_c4(nbcs=24, nsnps=4000, rbar=5000, seed=11)
+    upload(feng, d, K)
+    assign = (d["s1"] % K).astype(np.int32)
+    assign[d["is_dbl"]] = -1
+    feng.mstep(assign)
+    res, _ = feng.estep(apply_geno_error=False)
+    clust = pyoracle.fmx_mstep(d["cell_ptr"], d["snp_idx"], d["plp"], assign, K, d["nsnps"])
+    ref, ref_llk = pyoracle.fmx_estep(d["cell_ptr"], d["snp_idx"], d["plp"], d["af"], clust, 0.5, 0.0, False, want_llk=True)
+    assert (ref["sngBestLLK"] - ref["sngNextLLK"]).max() > 750.0  # the case is what it claims to be
+    assert_fmx_results(res, ref, ref_llk, K)
+    np.testing.assert_allclose(feng.fmx_llk(), ref_llk, rtol=RTOL, atol=1e-12)
+
+
 @pytest.mark.parametrize("K,geno_error", [(2, 0.0), (3, 0.1), (16, 0.0), (16, 0.1), (20, 0.05), (33, 0.0)])
 def test_estep_llk_and_decisions(feng, K, geno_error):
     d = small_c4(nbcs=120, nsnps=2000, rbar=150)
