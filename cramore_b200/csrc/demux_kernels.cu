@@ -18,6 +18,8 @@
 // reported value is taken at the very end.  This is the same real number as the reference's sum of logs to
 // ~1e-13 relative (FP64 throughout).
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 #include <math_constants.h>
 #include <stdint.h>
 
@@ -781,7 +783,7 @@ template <int AC, int TK, int LAGP>
 __global__ void __launch_bounds__(kScoreBlock, 1)
     demux_score_kernel(DemuxDev d, int njt, int nkt, int nac, int64_t nitems, uint32_t half_mask,
                        double2* __restrict__ dbg, int64_t dbg_c0, int64_t dbg_c1,
-                       unsigned long long* __restrict__ next_item) {
+                       unsigned long long* __restrict__ next_item, int force_exact) {
   using Cfg = ScoreCfg<AC, TK, LAGP>;
   constexpr int kSC = Cfg::SC;
   constexpr int kSCA = Cfg::SCA;
@@ -1243,7 +1245,8 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
       // fewer than two visible candidates although the warp holds two live products or more: some were flushed
       need_exact = false;
       if (b2.pos < 0) need_exact = __reduce_add_sync(kFull, nlive) >= 2;
-#ifdef CCU_EPI_EXACT  // test builds: always the exact form
+      need_exact = need_exact || (force_exact != 0);  // CCU_DEMUX_EXACT_EPILOGUE=1: tests drive the exact form
+#ifdef CCU_EPI_EXACT  // A/B builds: always the exact form
       need_exact = true;
 #endif
     }
@@ -1416,12 +1419,15 @@ static cudaError_t launch_score_t(const DemuxDev& d, const ScorePlan& plan, int 
   uint32_t half_mask = 0;
   for (int n = 0; n < d.nA && n < 32; ++n)
     if (plan.is_half[n]) half_mask |= 1u << n;
+  const char* fe = getenv("CCU_DEMUX_EXACT_EPILOGUE");
+  const int force_exact = (fe && fe[0] == '1') ? 1 : 0;
   // work counter of the launch: the 8 bytes behind the tile kernel's (d.maxbq: [0] deepest quality, [8] tile batches)
   unsigned long long* next_item = reinterpret_cast<unsigned long long*>(d.maxbq) + 2;
   err = cudaMemsetAsync(next_item, 0, sizeof(unsigned long long), st);
   if (err != cudaSuccess) return err;
   demux_score_kernel<AC, TK, LAGP><<<grid, kScoreBlock, Cfg::SMEM_BYTES, st>>>(d, plan.njt, plan.nkt, plan.nac, nitems,
-                                                                              half_mask, llk_dbg, c0, c1, next_item);
+                                                                              half_mask, llk_dbg, c0, c1, next_item,
+                                                                              force_exact);
   return cudaGetLastError();
 }
 

@@ -225,6 +225,33 @@ def test_exact_ties_follow_the_scan_order(engine):
         np.testing.assert_allclose(res["dblNextLLK"], ref["dblNextLLK"], rtol=1e-9)
 
 
+def test_tiled_epilogue_forms_agree(engine, monkeypatch):
+    """The tiled K2 reduces an item's products in the product domain (likelihoods rescaled to the warp's largest
+    exponent, REDUX arg-max) and keeps the (mantissa, exponent) form for warps that would lose a candidate below
+    2^-1022; CCU_DEMUX_EXACT_EPILOGUE=1 sends every warp through the latter.  Candidates are exact in both (same indices,
+    same bits), the sums agree to rounding -- on a pool with exactly tied samples, at 40 samples x 8 alphas (two alpha
+    chunks) and at the C2 shape (one chunk of ten)."""
+    for nv, alphas in ((40, [0, 0.1, 0.2, 0.3, 0.35, 0.4, 0.45, 0.5]), (64, [round(0.05 * i, 2) for i in range(11)])):
+        d = make_dataset("C1", nbcs=24, nsnps=1500, nv=nv, rbar=120, seed=5)
+        gp = np.array(d["gp"], np.float32).reshape(-1, nv, 3)
+        gp[:, 7] = gp[:, 2]    # exact ties between samples, inside a thread's pair and across lanes / warps
+        gp[:, 33] = gp[:, 2]
+        gp[:, 20] = gp[:, 19]
+        d["gp"] = gp.reshape(np.asarray(d["gp"]).shape)
+        d["alphas"] = np.asarray(alphas, np.float64)
+        fast = engine_run(engine, d)
+        _, ref, ref_llk, _ = oracle_run(d, want_llk=True)
+        assert_results_match(fast, ref, d["alphas"], ref_llk)
+        monkeypatch.setenv("CCU_DEMUX_EXACT_EPILOGUE", "1")
+        exact = engine_run(engine, d)
+        monkeypatch.delenv("CCU_DEMUX_EXACT_EPILOGUE")
+        for f in ("sBest", "sNext", "dBest1", "dBest2", "dBestA", "dNext1", "dNext2", "dNextA",
+                  "sngBestLLK", "sngNextLLK", "dblBestLLK", "dblNextLLK"):
+            assert np.array_equal(fast[f], exact[f]), (nv, f)
+        for f in ("sumLLK", "sngLLK"):
+            np.testing.assert_allclose(fast[f], exact[f], rtol=1e-13, atol=0, err_msg=f)
+
+
 def test_twenty_thousand_reads_on_one_snp(engine):
     """One (droplet, SNP) entry with 20,000 reads: the per-read product of cmd_cram_demuxlet.cpp:655-700 is renormalised
     by its running maximum in the reference; the tile kernel must survive the same depth without underflow."""
