@@ -689,16 +689,17 @@ def measure_fmx(ctx, iters=10):
                           "frac": e_flops / (phases["estep_ms"] * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
                           "note": "needed FP64 flops (2 per pair and SNP on single-read entries) / time; the mean-genotype "
                                   "array (K*8 B per SNP) lives in L2, so HBM does not bind"},
-                 "binding": {"resource": "instruction issue (warp schedulers)", "frac_ncu": 0.61,
-                             "source": "profiles/r02_fmx_kernels_ncu_full.csv: smsp__issue_active 60.8 %, FP64 pipe 36 %, "
-                                       "shared-memory wavefronts 35 %, DRAM 5 % of peak at C4 on one GPU (static figures "
+                 "binding": {"resource": "instruction issue (warp schedulers) and the L2 round trip of the operand fetch one step ahead",
+                             "frac_ncu": 0.59,
+                             "source": "profiles/r02b_fmx_kernels_ncu_full.csv: smsp__issue_active 59.5 %, FP64 pipe 43 %, "
+                                       "shared-memory wavefronts 45 %, DRAM 4 % of peak at C4 on one GPU (static figures "
                                        "of that capture, not measured in this run)"}},
                 {"kernel": "fmx M-step (F3)", "bound": "hbm", "achieved": m_bytes / (phases["mstep_ms"] * 1e-3) / 1e9,
                  "peak": hbm_peak, "unit": "GB/s", "frac": m_bytes / (phases["mstep_ms"] * 1e-3) / 1e9 / hbm_peak,
                  "algorithmic_bytes_per_launch": int(m_bytes), "ms": phases["mstep_ms"], "peak_source": peak_src,
                  "binding": {"resource": "latency of the ordered fold (dependent chain per warp) at 28 warps per SM",
                              "frac_ncu": 0.53,
-                             "source": "profiles/r02_fmx_kernels_ncu_full.csv: smsp__issue_active 52.8 %, FP64 pipe 28 %, "
+                             "source": "profiles/r02b_fmx_kernels_ncu_full.csv: smsp__issue_active 52.7 %, FP64 pipe 28 %, "
                                        "DRAM 46 % of peak at C4 on one GPU (static figures of that capture)"}}]
         out = {"config": {"workload": "C4 freemuxlet EM: K=%d, %d barcodes, %d SNPs, %d entries, %d iterations; E-step "
                                       "barcode-sharded, M-step SNP-slab-sharded over %d GPU(s)" %

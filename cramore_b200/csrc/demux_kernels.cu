@@ -43,6 +43,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+#ifndef CCU_PRODUCER_SLEEP_NS
+#define CCU_PRODUCER_SLEEP_NS 200
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {
@@ -54,6 +57,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!ok);
+}
+// The producer's wait for a free ring stage: it has a chunk or more of slack, and a bare try_wait loop came back every
+// ~24 cycles -- 7 % of the kernel's instructions, all issued on the one sub-partition the producer warp shares with four
+// consumer warps.  Sleeping between the tries takes them out of the instruction count; K2's time did not move
+// (18.69 ms at C2 with 50, 200 or 1000 ns), so the spins were not what the consumers waited for.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(CCU_PRODUCER_SLEEP_NS);
+  }
 }
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -848,7 +869,7 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
       const uint32_t kbytes = (uint32_t)krows * 24u, pbytes = (uint32_t)nal * (kTileStride * 8);
       for (int chunk = 0; chunk < nch; ++chunk, ++g) {
         const int stage = g % kNS;
-        if (g >= (uint32_t)kNS) mbar_wait(smem_u32(&empty[stage]), ((g / kNS) - 1) & 1);
+        if (g >= (uint32_t)kNS) mbar_wait_relaxed(smem_u32(&empty[stage]), ((g / kNS) - 1) & 1);
         const uint32_t bar = smem_u32(&full[stage]);
         const bool affine = chunk >= nchg;
         int cnt;
