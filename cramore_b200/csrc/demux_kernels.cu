@@ -683,12 +683,15 @@ cudaError_t launch_singlet_to_dbg(const DemuxDev& d, double* llk_dbg, int64_t c0
 //                f_j + alpha (f_k - f_j).  The s_j s_k products are per-droplet constants applied
 //                in the item epilogue;
 //   * at the end of an item the products become log-sum-exp / top-2 partials (no log needed:
-//     ordering by (exponent, mantissa) is ordering by LLK).
+//     ordering by (exponent, mantissa) is ordering by LLK; the epilogue rescales them to the warp's
+//     largest exponent and works on plain doubles, see `epilogue` below);
+//   * items are handed out by a global counter (the first one per CTA by its index), read one
+//     item ahead by the producer warp.
 #ifndef CCU_NS
-#define CCU_NS 3
+#define CCU_NS 3     // ring stages of the in-step kernel
 #endif
 #ifndef CCU_SCA1
-#define CCU_SCA1 64
+#define CCU_SCA1 64  // entries per affine chunk at TK == 1 (32: 19.07 ms at C2, 64: 18.83, 96 with two stages: 18.94)
 #endif
 // Consumer groups out of step (the LAGP template parameter, TK == 1 only).  The 16 consumer warps form two groups of
 // eight by k half -- two warps of each group on every SM sub-partition -- and group 1 stays at least LAGP chunks
@@ -1032,7 +1035,6 @@ __global__ void __launch_bounds__(kScoreBlock, 1)
   // instructions per (j,k) for the coefficients plus 2 DFMA + 1 DMUL per alpha, i.e. 1.8 instead of 2.1 per
   // likelihood and SNP.  With every alpha in [0, 0.5] each factor is >= half its f_j, so the expanded form has
   // no cancellation to speak of (terms / value <= ~4); grids reaching beyond 0.5 use the one-SNP form.
-  // The alphas are re-read from shared memory inside the loop (broadcast LDS.128) to keep 20 registers free.
   auto main_affine = [&](int cnt, int stage, int n0) {
     const double* fj_base = reinterpret_cast<const double*>(raw + stage * Cfg::STAGE_BYTES) + jg * kTJ;
     // the thread's TK consecutive samples k sit inside one 32-sample part
