@@ -65,9 +65,17 @@ def run_em_distributed(eng, stats, assign, cell_ranges, snp_ranges, init_assign,
     """cmd_cram_freemuxlet.cpp:359-370 + :457-653 across ranks.  `stats`/`assign` (and `post`) are torch
     tensors aliasing the engine's arrays (device_views / posterior_view, or CPU tensors of a stand-in
     engine).  exchange: "posteriors" (default when `post` is given) or "stats".  Returns this rank's
-    per-droplet results and every rank's results gathered in barcode order."""
+    per-droplet results and every rank's results gathered in barcode order.
+
+    Stream order: with device tensors the engine is put on torch's CURRENT stream here (`eng.set_stream`), and stays
+    there: its kernels, the copies into `assign` / `post` and the NCCL collectives below are then ordered by that one
+    stream, which is what the loop relies on (the engine's own default is a separate non-blocking stream, on which a
+    collective could read half-written posteriors).  `sync` is only needed by stand-in engines that do not run on the
+    stream (CPU tests)."""
     import torch
     import torch.distributed as dist
+    if stats.device.type == "cuda":
+        eng.set_stream(torch.cuda.current_stream(stats.device).cuda_stream)
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     rank = dist.get_rank(group) if multi else 0
     cb, ce = cell_ranges[rank]
