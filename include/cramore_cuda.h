@@ -100,7 +100,11 @@ int ccu_demux_set_genotypes(ccu_handle* h, int64_t nsnps, const float* gp, const
                             const uint8_t* has_gp);
 /* The same from the reference's own per-SNP arrays: gps[s] = sc_snp_t::gps of SNP s (sc_drop_seq.h:115-127: nv*3
  * doubles, genotype error already mixed in by sc_drop_seq.cpp:287-315 / cmd_cram_demuxlet.cpp:241-268), or NULL for
- * a SNP without genotypes.  Lets a patched cmdCramDemuxlet pass `scl.snps[s].gps` through unchanged. */
+ * a SNP without genotypes.  Lets a patched cmdCramDemuxlet pass `scl.snps[s].gps` through unchanged.
+ * The rows are taken as they are (no validation): they must be genotype PROBABILITIES -- non-negative, each sample's
+ * three values summing to about 1, as the reference's mixing leaves them.  The scoring kernel renormalises its running
+ * products on a budget that assumes every per-SNP factor is at least ~2^-34 (the read-error floor times a row sum
+ * near 1); rows that sum to ~0 make a droplet's likelihood exactly 0 (log-likelihood -inf) rather than tiny. */
 int ccu_demux_set_genotypes_mixed(ccu_handle* h, int64_t nsnps, const double* const* gps);
 
 /* Multi-GPU form of ccu_demux_set_genotypes (no reference counterpart: the reference is one process and scales by
