@@ -141,6 +141,8 @@ int ccu_destroy(ccu_handle* h) {
                     &h->d_tiles, &h->d_vaff, &h->d_eclass, &h->d_vent, &h->d_vsnp, &h->d_vcnt, &h->d_sng, &h->d_fmat, &h->d_pm, &h->d_pe, &h->d_maxbq, &h->d_partials, &h->d_results, &h->d_dbg, &h->d_flag,
                     &h->d_sink, &h->d_tslot, &h->d_scan, &h->d_ngen};
   for (DevBuf* b : bufs) b->release();
+  for (DevBuf& b : h->d_in2) b.release();
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   ccu_fmx_release(h);
   for (int i = 0; i < EV_COUNT; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -349,19 +351,9 @@ int ccu_demux_copy_genotypes(ccu_handle* dst, ccu_handle* src) {
   return 0;
 }
 
-int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx,
-                     const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq) {
-  CcuRange nvtx_range("ccu_demux_upload");
-  if (!h) return 1;
-  if (!h->configured) return fail(h, "ccu_demux_upload: call ccu_demux_configure first");
-  if (nbcs < 0 || !cell_ptr) return fail(h, "ccu_demux_upload: bad arguments");
-  const int64_t nnz = cell_ptr[nbcs] - cell_ptr[0];
-  if (cell_ptr[0] != 0) return fail(h, "ccu_demux_upload: cell_ptr[0] must be 0");
-  if (nnz < 0 || (nnz > 0 && (!snp_idx || !read_ptr))) return fail(h, "ccu_demux_upload: bad CSR arrays");
-  const int64_t nreads = nnz > 0 ? read_ptr[nnz] - read_ptr[0] : 0;
-  if (nnz > 0 && read_ptr[0] != 0) return fail(h, "ccu_demux_upload: read_ptr[0] must be 0");
-  if (nreads < 0 || (nreads > 0 && (!al || !bq))) return fail(h, "ccu_demux_upload: bad read arrays");
-  CCU_CUDA(h, cudaSetDevice(h->device));
+// Device buffers of one droplet store (inputs and scratch; the tile buffer is sized after the upload, when the
+// number of entries with two or more reads is known).  No-op for a store no larger than one reserved before.
+static int demux_reserve(ccu_handle* h, int64_t nbcs, int64_t nnz, int64_t nreads) {
   const ccu::ScorePlan plan = ccu::make_score_plan(h->nv, h->nA, h->alpha.data());
   CCU_CUDA(h, h->d_cell_ptr.reserve((nbcs + 1) * sizeof(int64_t)));
   CCU_CUDA(h, h->d_snp_idx.reserve(nnz * sizeof(int32_t) + 16));
@@ -391,6 +383,26 @@ int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const
   CCU_CUDA(h, h->d_maxbq.reserve(32));  // deepest quality, the tile kernel's batch counter, K2's item counter
   CCU_CUDA(h, h->d_partials.reserve((size_t)nbcs * plan.items_per_cell * ccu::kScoreWarps * sizeof(ccu::ItemPartial) + 16));
   CCU_CUDA(h, h->d_results.reserve(nbcs * sizeof(ccu_demux_result) + 16));
+  return 0;
+}
+
+// The upload proper.  ent_base / read_base: a slice of a larger store handed over with that store's offsets (cell_ptr
+// starts at ent_base, read_ptr at read_base, the other arrays already point at the slice): the pointer arrays are
+// rebased on the device, so the host never rewrites them.
+static int demux_upload_impl(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx,
+                             const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq, int64_t ent_base,
+                             int64_t read_base) {
+  if (!h) return 1;
+  if (!h->configured) return fail(h, "ccu_demux_upload: call ccu_demux_configure first");
+  if (nbcs < 0 || !cell_ptr) return fail(h, "ccu_demux_upload: bad arguments");
+  const int64_t nnz = cell_ptr[nbcs] - cell_ptr[0];
+  if (cell_ptr[0] != ent_base) return fail(h, "ccu_demux_upload: cell_ptr[0] must be 0");
+  if (nnz < 0 || (nnz > 0 && (!snp_idx || !read_ptr))) return fail(h, "ccu_demux_upload: bad CSR arrays");
+  const int64_t nreads = nnz > 0 ? read_ptr[nnz] - read_ptr[0] : 0;
+  if (nnz > 0 && read_ptr[0] != read_base) return fail(h, "ccu_demux_upload: read_ptr[0] must be 0");
+  if (nreads < 0 || (nreads > 0 && (!al || !bq))) return fail(h, "ccu_demux_upload: bad read arrays");
+  CCU_CUDA(h, cudaSetDevice(h->device));
+  if (int rc = demux_reserve(h, nbcs, nnz, nreads)) return rc;
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_X0], h->stream));
   CCU_CUDA(h, cudaMemcpyAsync(h->d_cell_ptr.p, cell_ptr, (nbcs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
                               h->stream));
@@ -404,6 +416,8 @@ int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const
     CCU_CUDA(h, cudaMemcpyAsync(h->d_bq.p, bq, nreads, cudaMemcpyHostToDevice, h->stream));
   }
   CCU_CUDA(h, cudaEventRecord(h->ev[EV_X1], h->stream));
+  CCU_CUDA(h, ccu::launch_rebase(h->d_cell_ptr.as<int64_t>(), nbcs + 1, ent_base, h->stream));
+  if (nnz > 0) CCU_CUDA(h, ccu::launch_rebase(h->d_read_ptr.as<int64_t>(), nnz + 1, read_base, h->stream));
   // Full 9 x nAlpha tiles are only kept for the entries with two or more informative reads (one entry in two thousand
   // in sparse single-cell data, a third with skewed coverage): count them, on the device, and size the buffer to that
   // (80 * nAlpha bytes per entry: 3.5 GB at C2 if it were kept for every entry).
@@ -427,6 +441,13 @@ int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const
   h->ran = false;
   h->validated = false;
   return 0;
+}
+
+int ccu_demux_upload(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx,
+                     const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq) {
+  CcuRange nvtx_range("ccu_demux_upload");
+  if (h) h->partial = false;
+  return demux_upload_impl(h, nbcs, cell_ptr, snp_idx, read_ptr, al, bq, 0, 0);
 }
 
 int ccu_demux_run(ccu_handle* h) {
@@ -492,7 +513,7 @@ int ccu_demux_wait(ccu_handle* h) {
 }
 
 void* ccu_demux_results_dev(ccu_handle* h, int64_t* nbcs) {
-  if (!h || !h->ran) return nullptr;
+  if (!h || !h->ran || h->partial) return nullptr;
   if (nbcs) *nbcs = h->nbcs;
   return h->d_results.p;
 }
@@ -526,6 +547,70 @@ static double demux_scratch_bytes(const ccu_handle* h, int64_t ncell, int64_t nn
   return per_entry * (double)nnz + per_cell * (double)ncell + 2.0 * (double)nreads;
 }
 
+// A store in two parts, the second part's upload under the first part's kernels.  Every kernel of a pass needs the whole
+// of its store, so inside ONE pass the host->device copy cannot hide; droplets are independent, so a small first part
+// (an eighth of the entries) is uploaded and started, and while it is scored the rest crosses PCIe on a second stream
+// into a second set of store arrays (pointer arrays sent with the whole store's offsets and rebased on the device).
+// Results are bitwise those of the single pass.  All buffers are reserved for the larger part before anything runs:
+// growing one later would free it under the running kernels (cudaFree waits -- correct, but serial).
+static int demux_score_two_parts(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx,
+                                 const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq, ccu_demux_result* out,
+                                 int64_t n0) {
+  const int64_t e0 = cell_ptr[n0], e1 = cell_ptr[nbcs];
+  const int64_t r0 = read_ptr[e0], r1 = read_ptr[e1];
+  const int64_t nb1 = nbcs - n0, nnz1 = e1 - e0, nr1 = r1 - r0;
+  if (!h->aux_stream) CCU_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+  if (int rc = demux_reserve(h, std::max(n0, nb1), std::max(e0, nnz1), std::max(r0, nr1))) return rc;
+  CCU_CUDA(h, h->d_in2[0].reserve((nb1 + 1) * sizeof(int64_t)));
+  CCU_CUDA(h, h->d_in2[1].reserve(nnz1 * sizeof(int32_t) + 16));
+  CCU_CUDA(h, h->d_in2[2].reserve((nnz1 + 1) * sizeof(int64_t)));
+  CCU_CUDA(h, h->d_in2[3].reserve(nr1 + 16));
+  CCU_CUDA(h, h->d_in2[4].reserve(nr1 + 16));
+  // ---- part 0: upload, start
+  if (int rc = demux_upload_impl(h, n0, cell_ptr, snp_idx, read_ptr, al, bq, 0, 0)) return rc;
+  {  // room for part 1's tiles at part 0's rate of entries with two or more reads (and a half more)
+    const double rate = e0 > 0 ? (double)h->ngen / (double)e0 : 0.0;
+    const size_t guess = (size_t)(1.5 * rate * (double)nnz1) + 4096;
+    CCU_CUDA(h, h->d_tiles.reserve(guess * h->nA * ccu::kTileStride * sizeof(double) + 16));
+  }
+  if (int rc = ccu_demux_run(h)) return rc;
+  ccu_timings sum = h->tm;
+  // ---- part 1's arrays into the other set, on the auxiliary stream, while part 0 is scored
+  DevBuf* cur[5] = {&h->d_cell_ptr, &h->d_snp_idx, &h->d_read_ptr, &h->d_al, &h->d_bq};
+  for (int i = 0; i < 5; ++i) std::swap(*cur[i], h->d_in2[i]);
+  cudaStream_t main_stream = h->stream;
+  h->stream = h->aux_stream;
+  const int rc1 = demux_upload_impl(h, nb1, cell_ptr + n0, snp_idx + e0, read_ptr + e0, al + r0, bq + r0, e0, r0);
+  h->stream = main_stream;
+  if (rc1) return rc1;
+  const float h2d1 = h->tm.ms_h2d;
+  // ---- part 0's results (its kernels read the first set and the scratch; nothing above touched either)
+  if (collect_run_timings(h)) return 1;
+  sum.ms_tile = h->tm.ms_tile;
+  sum.ms_singlet = h->tm.ms_singlet;
+  sum.ms_score = h->tm.ms_score;
+  sum.ms_finalize = h->tm.ms_finalize;
+  sum.ms_run = h->tm.ms_run;
+  CCU_CUDA(h, cudaMemcpyAsync(out, h->d_results.p, n0 * sizeof(ccu_demux_result), cudaMemcpyDeviceToHost, h->stream));
+  CCU_CUDA(h, cudaStreamSynchronize(h->stream));
+  // ---- part 1
+  if (int rc = ccu_demux_run(h)) return rc;
+  if (int rc = ccu_demux_download(h, out + n0)) return rc;
+  sum.ms_tile += h->tm.ms_tile;
+  sum.ms_singlet += h->tm.ms_singlet;
+  sum.ms_score += h->tm.ms_score;
+  sum.ms_finalize += h->tm.ms_finalize;
+  sum.ms_run += h->tm.ms_run;
+  sum.ms_h2d += h2d1;
+  sum.ms_d2h = h->tm.ms_d2h;
+  sum.launches += h->tm.launches;
+  sum.score_items += h->tm.score_items;
+  sum.score_ctas = h->tm.score_ctas;
+  h->tm = sum;
+  h->partial = true;
+  return 0;
+}
+
 int ccu_demux_score(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx,
                     const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq, ccu_demux_result* out) {
   CcuRange nvtx_range("ccu_demux_score");
@@ -550,6 +635,20 @@ int ccu_demux_score(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const 
     const size_t held = h->d_tiles.cap + h->d_fmat.cap + h->d_vaff.cap + h->d_vent.cap + h->d_partials.cap;  // reusable
     budget = 0.85 * ((double)free_b + (double)held);
     if (cap) budget = std::min(budget, atof(cap) * 1048576.0);
+  }
+  if (h) h->partial = false;
+  if (need <= budget && !cap && nbcs >= 4096 && nnz >= (1 << 20) && out && snp_idx && read_ptr && cell_ptr[0] == 0 &&
+      read_ptr[0] == 0 && !getenv("CCU_DEMUX_NO_PIPELINE")) {
+    // first part: the droplets that hold the first eighth of the entries
+    const int64_t n0 = std::lower_bound(cell_ptr, cell_ptr + nbcs, cell_ptr[nbcs] / 8) - cell_ptr;
+    // (a store whose arrays are not in order takes the single pass, whose device-side validation names the defect)
+    const bool sane = n0 > 0 && n0 < nbcs && cell_ptr[n0] > 0 && cell_ptr[n0] < cell_ptr[nbcs] &&
+                      read_ptr[cell_ptr[n0]] >= 0 && read_ptr[cell_ptr[n0]] <= read_ptr[cell_ptr[nbcs]];
+    if (sane) {
+      const int rc = demux_score_two_parts(h, nbcs, cell_ptr, snp_idx, read_ptr, al, bq, out, n0);
+      if (rc == 0 && need > h->scratch_fits) h->scratch_fits = need;
+      return rc;
+    }
   }
   if (nbcs == 0 || need <= budget) {
     const bool trace = getenv("CCU_TRACE") != nullptr;  // host wall clock of the phases, to stderr
@@ -606,12 +705,14 @@ int ccu_demux_score(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const 
   }
   sum.ms_genotypes = h->tm.ms_genotypes;
   h->tm = sum;
+  h->partial = nbatch > 1;
   return 0;
 }
 
 int ccu_demux_get_tiles(ccu_handle* h, double* tiles) {
   if (!h) return 1;
   if (!h->ran) return fail(h, "ccu_demux_get_tiles: nothing has been run");
+  if (h->partial) return fail(h, "ccu_demux_get_tiles: the last ccu_demux_score ran its store in parts and the handle holds only the last one: use ccu_demux_upload + ccu_demux_run (or set CCU_DEMUX_NO_PIPELINE=1) to inspect a store");
   CCU_CUDA(h, cudaSetDevice(h->device));
   const size_t rowp = (size_t)h->nA * ccu::kTileStride;
   std::vector<double> tmp((size_t)h->nnz * rowp);
@@ -633,6 +734,7 @@ int ccu_demux_get_tiles(ccu_handle* h, double* tiles) {
 int ccu_demux_get_singlets(ccu_handle* h, double* llk, double* llk0) {
   if (!h) return 1;
   if (!h->ran) return fail(h, "ccu_demux_get_singlets: nothing has been run");
+  if (h->partial) return fail(h, "ccu_demux_get_singlets: the last ccu_demux_score ran its store in parts and the handle holds only the last one: use ccu_demux_upload + ccu_demux_run (or set CCU_DEMUX_NO_PIPELINE=1) to inspect a store");
   if (h->nbcs > 0 && !llk) return fail(h, "ccu_demux_get_singlets: NULL output");
   CCU_CUDA(h, cudaSetDevice(h->device));
   if (h->nbcs == 0) return 0;
@@ -664,6 +766,7 @@ int ccu_demux_get_genotypes(ccu_handle* h, int64_t snp_begin, int64_t snp_end, d
 int ccu_demux_get_llk(ccu_handle* h, int64_t cell_begin, int64_t cell_end, double* llk) {
   if (!h) return 1;
   if (!h->ran) return fail(h, "ccu_demux_get_llk: run the engine first");
+  if (h->partial) return fail(h, "ccu_demux_get_llk: the last ccu_demux_score ran its store in parts and the handle holds only the last one: use ccu_demux_upload + ccu_demux_run (or set CCU_DEMUX_NO_PIPELINE=1) to inspect a store");
   if (cell_begin < 0 || cell_end > h->nbcs || cell_begin > cell_end) return fail(h, "ccu_demux_get_llk: bad range");
   const int64_t nc = cell_end - cell_begin;
   if (nc == 0) return 0;

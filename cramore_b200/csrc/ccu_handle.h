@@ -78,11 +78,17 @@ struct ccu_handle {
   int64_t nbcs = -1, nnz = 0, nreads = 0;
   bool ran = false;
   DevBuf d_cell_ptr, d_snp_idx, d_read_ptr, d_al, d_bq;
+  // second set of the five store arrays and a stream of its own: ccu_demux_score uploads the second part of a store
+  // into them while the first part is being scored (ccu_api.cu)
+  DevBuf d_in2[5];
+  cudaStream_t aux_stream = nullptr;
   DevBuf d_tiles, d_vaff, d_eclass, d_vent, d_vsnp, d_vcnt, d_sng, d_fmat, d_pm, d_pe, d_maxbq, d_partials, d_results,
       d_dbg, d_sink, d_flag, d_tslot, d_scan, d_ngen;
   int64_t ngen = 0;  // entries with >= 2 informative reads in the uploaded store (sizes the tile buffer)
   double scratch_fits = 0.0;  // largest scratch need (bytes) that ran in one piece on this handle
   bool validated = false;  // the uploaded CSR passed demux_validate_kernel
+  bool partial = false;    // the handle holds the LAST PART of a store that ccu_demux_score ran in parts: the inspection
+                           // calls (tiles, llk, singlets, device results) refuse instead of answering for the wrong droplets
 
   // freemuxlet (owned by ccu_fmx_api.cu)
   FmxState* fmx = nullptr;

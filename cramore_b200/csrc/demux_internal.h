@@ -93,6 +93,8 @@ cudaError_t launch_gp_prepare(const float* gp_f32, const double* snp_err, const 
 cudaError_t launch_validate(const DemuxDev& d, int64_t nreads, uint32_t* flag, cudaStream_t st);
 // number of entries with >= 2 informative reads -> *count_dev (what sizes the tile buffer; once per upload)
 cudaError_t launch_count_general(const DemuxDev& d, unsigned long long* count_dev, cudaStream_t st);
+// p[i] -= base for i < n (pointer arrays of a store slice uploaded with the whole store's offsets)
+cudaError_t launch_rebase(int64_t* p, int64_t n, int64_t base, cudaStream_t st);
 // scan_tmp / scan_bytes: scratch of the prefix sum over the entry classes (scan_bytes = 0: return the size needed in
 // *scan_need and do nothing)
 cudaError_t launch_tile(const DemuxDev& d, bool all_entries, void* scan_tmp, size_t scan_bytes, size_t* scan_need,

@@ -459,6 +459,19 @@ cudaError_t launch_validate(const DemuxDev& d, int64_t nreads, uint32_t* flag, c
   return cudaGetLastError();
 }
 
+// p[i] -= base: the pointer arrays of a store's second part arrive with the offsets of the whole store
+__global__ void __launch_bounds__(256) demux_rebase_kernel(int64_t* __restrict__ p, int64_t n, int64_t base) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] -= base;
+}
+
+cudaError_t launch_rebase(int64_t* p, int64_t n, int64_t base, cudaStream_t st) {
+  if (n <= 0 || base == 0) return cudaSuccess;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  demux_rebase_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, n, base);
+  return cudaGetLastError();
+}
+
 // entries with >= 2 informative reads (the same test as demux_entry_kernel), counted once per upload
 __global__ void __launch_bounds__(256)
     demux_count_general_kernel(int64_t nnz, const int64_t* __restrict__ read_ptr, const uint8_t* __restrict__ al,

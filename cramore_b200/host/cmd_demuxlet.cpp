@@ -339,6 +339,8 @@ int cmdDemuxlet(int argc, char** argv) {
     if (ccu_demux_configure(hs[d], nv, nAlpha, gridAlpha.data(), doublet_prior)) fatal("%s", ccu_last_error(hs[d]));
   }
   if (ccu_demux_set_genotypes(hs[0], nsnps_total, gp_f32.data(), snp_err.data(), has_gp.data())) fatal("%s", ccu_last_error(hs[0]));
+  // <out>.single reads the engine's singlet table after the scoring: the store must then be scored in one piece
+  if (writeSingle) setenv("CCU_DEMUX_NO_PIPELINE", "1", 1);
   auto work = [&](int d) {
     ccu_handle* h = hs[d];
     const int64_t b = cut[d], e = cut[d + 1];

@@ -175,6 +175,25 @@ def test_scoring_in_memory_bounded_ranges(engine, monkeypatch):
     assert np.array_equal(whole, parts)
 
 
+def test_scoring_in_two_overlapped_parts(engine, monkeypatch):
+    """A large store is scored in two parts, the second part's upload (on a second stream, into a second set of store
+    arrays, pointer arrays rebased on the device) under the first part's kernels: results are bitwise those of the single
+    pass (CCU_DEMUX_NO_PIPELINE=1), and the inspection calls refuse a handle that holds only the last part."""
+    from cramore_b200.engine import EngineError
+    d = make_dataset("C2", nbcs=6000, nsnps=200_000)
+    assert d["cell_ptr"][-1] >= 1 << 20
+    parts = engine_run(engine, d)
+    launches_parts = engine.timings()["launches"]
+    with pytest.raises(EngineError):
+        engine.llk(0, 2)
+    monkeypatch.setenv("CCU_DEMUX_NO_PIPELINE", "1")
+    whole = engine_run(engine, d)
+    assert launches_parts > engine.timings()["launches"]  # two passes against one
+    monkeypatch.delenv("CCU_DEMUX_NO_PIPELINE")
+    assert np.array_equal(whole, parts)
+    assert engine.llk(0, 2).shape[0] == 2
+
+
 def test_two_samples_and_widest_pool(engine):
     """nv = 2 (one doublet pair; a single sample is refused like one alpha is: the reference's doublet scan would index
     sample -1) and the C3 shape (256 samples, 11 alphas: 65,280 ordered pairs per alpha) on two droplets."""
