@@ -122,7 +122,12 @@ int ccu_demux_copy_genotypes(ccu_handle* dst, ccu_handle* src);
 
 /* The whole engine for nbcs droplets, replaces cmd_cram_demuxlet.cpp:636-906 (tile :655-725,
  * pairwise accumulation :733-747, posterior normaliser :804-821, top-2 scans :827-906).
- * out[nbcs] in CSR barcode order.  Equivalent to upload + run + download. */
+ * out[nbcs] in CSR barcode order.  Equivalent to upload + run + download -- with the same results bit for bit, but a
+ * large store (4,096 droplets and 2^20 entries or more) is scored in two parts, the second part's host->device copy
+ * under the first part's kernels, and a store whose scratch does not fit the free device memory in as many droplet
+ * ranges as it takes.  The handle then holds only the LAST part: ccu_demux_get_llk / _get_tiles / _get_singlets /
+ * _results_dev refuse it (error message); to inspect a store, use ccu_demux_upload + ccu_demux_run, or set
+ * CCU_DEMUX_NO_PIPELINE=1 in the environment. */
 int ccu_demux_score(ccu_handle* h, int64_t nbcs, const int64_t* cell_ptr, const int32_t* snp_idx,
                     const int64_t* read_ptr, const uint8_t* al, const uint8_t* bq,
                     ccu_demux_result* out);
