@@ -535,7 +535,9 @@ def measure_demux(ctx, d, steps, warmup, fp64_peak=None):
                         ("genotype_mix_kernels", "csr_h2d", "kernels", "result_d2h"), e2e_dev)},
                     "genotype_upload": ("host pointer, whole matrix" if world == 1 else
                                         "1/%d SNP slab per rank host->device + in-place NCCL all-gather over NVLink" % world),
-                    "includes": "genotype matrix upload + mixing, CSR upload, all kernels, result download"
+                    "includes": "genotype matrix upload + mixing, CSR upload, all kernels, result download (ccu_demux_score scores a "
+                                "store of this size in two parts, the second part's upload under the first part's kernels; "
+                                "device_ms_inside lists the sums of both parts)"
                                 + (", all-gather of the result records + copy of the full table to rank 0's host" if world > 1 else ""),
                     "bytes_are": "per rank (rank 0)"},
             "gpu_launches": launches, "roofline": roofline, "roofline_k1": roofline_k1, "kernel_ms": kernel_ms,
