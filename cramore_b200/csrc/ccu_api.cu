@@ -570,7 +570,7 @@ static int demux_score_two_parts(ccu_handle* h, int64_t nbcs, const int64_t* cel
   if (int rc = demux_upload_impl(h, n0, cell_ptr, snp_idx, read_ptr, al, bq, 0, 0)) return rc;
   {  // room for part 1's tiles at part 0's rate of entries with two or more reads (and a half more)
     const double rate = e0 > 0 ? (double)h->ngen / (double)e0 : 0.0;
-    const size_t guess = (size_t)(1.5 * rate * (double)nnz1) + 4096;
+    const size_t guess = std::min<size_t>((size_t)(1.5 * rate * (double)nnz1) + 4096, (size_t)nnz1);
     CCU_CUDA(h, h->d_tiles.reserve(guess * h->nA * ccu::kTileStride * sizeof(double) + 16));
   }
   if (int rc = ccu_demux_run(h)) return rc;
